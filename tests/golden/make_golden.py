@@ -1,0 +1,171 @@
+"""Generates tests/golden/*.npz by running the REAL reference model
+(/root/reference, read-only, imported in place -- nothing is copied) on seeded
+synthetic inputs and seeded weights.  Runs only in the dev container; the
+fixtures it writes are committed and are what travels to the GPU box.
+
+    python tests/golden/make_golden.py            # all fixtures
+    python tests/golden/make_golden.py small      # one fixture
+
+Shims: `pytorch_transformers.modeling_bert` -> oracle/pt_bert.py (absent
+third-party dependency, restated), `editdistance` -> stub (only the ANLS metric
+uses it).  Gumbel noise is injected by temporarily replacing
+torch.nn.functional.gumbel_softmax with the same formula fed from the fixture's
+noise tensors (reference stg.py:41,89 call F.gumbel_softmax in eval too).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = os.environ.get("T2S_REFERENCE_ROOT", "/root/reference")
+sys.path.insert(0, ROOT)
+
+from vitxt_gqa_b200 import synth  # noqa: E402
+
+# name -> (Dims kwargs, batch, input seed, weight seed, weight variant, mode)
+FIXTURES = {
+    # tiny shapes: fast CPU checks of every code path (ties, pads, short videos)
+    "t2s_small_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2), 3, 11, 0, "stress", "eval"),
+    "t2s_small_train": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2), 3, 12, 0, "stress", "train"),
+    "t2s_small_default": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2), 2, 13, 1, "default", "eval"),
+    # BASELINE config 1: t2s_abinet shapes, batch 1 (+1), eval
+    "t2s_abinet_eval": (dict(), 2, 1235, 0, "stress", "eval"),
+    "t2s_clipocr_train": (dict(frame_topk=1, ocr_topk=1), 2, 1237, 0, "stress", "train"),
+    "m4c_small_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=1, ocr_topk=1, model="m4c"), 3, 14, 0, "stress", "eval"),
+    "m4c_abinet_eval": (dict(frame_topk=1, ocr_topk=1, model="m4c"), 2, 1238, 0, "stress", "eval"),
+}
+
+
+def install_shims():
+    sys.path.insert(0, REF)
+    ed = types.ModuleType("editdistance")
+    ed.eval = lambda a, b: 0
+    sys.modules["editdistance"] = ed
+    from oracle import pt_bert
+    pkg = types.ModuleType("pytorch_transformers")
+    pkg.modeling_bert = pt_bert
+    sys.modules["pytorch_transformers"] = pkg
+    sys.modules["pytorch_transformers.modeling_bert"] = pt_bert
+
+
+class AttrDict(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    @classmethod
+    def wrap(cls, v):
+        if isinstance(v, dict):
+            return cls({k: cls.wrap(x) for k, x in v.items()})
+        if isinstance(v, list):
+            return [cls.wrap(x) for x in v]
+        return v
+
+
+class Writer:
+    def write(self, *a, **k):
+        pass
+
+
+def build_reference_model(d, sd):
+    from pythia.common.registry import registry
+    registry.register("writer", Writer())
+    registry.register("config", AttrDict.wrap({"datasets": "vtextgqa",
+                                               "training_parameters": {"evalai_inference": False}}))
+    registry.register("vtextgqa_num_final_outputs", d.num_outputs)
+    registry.register("vtextgqa_answer_processor", AttrDict(BOS_IDX=1, EOS_IDX=2, PAD_IDX=0))
+    cfg = AttrDict.wrap(synth.model_config_for_dims(d))
+    if d.model == "t2s":
+        from pythia.models.t2s import T2S as Model
+    else:
+        from pythia.models.m4c import M4C as Model
+    torch.manual_seed(0)
+    model = Model(cfg)
+    model.build()
+    missing, unexpected = model.load_state_dict(sd, strict=True), None
+    return model
+
+
+class InjectGumbel:
+    """F.gumbel_softmax replacement consuming pre-drawn noise keyed by shape."""
+
+    def __init__(self, noise_by_shape):
+        self.noise = noise_by_shape
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self.F, self.orig = F, F.gumbel_softmax
+
+        def fake(logits, tau=1, hard=False, eps=1e-10, dim=-1):
+            g = self.noise[tuple(logits.shape)]
+            y = ((logits + g) / tau).softmax(dim)
+            if not hard:
+                return y
+            idx = y.max(dim, keepdim=True)[1]
+            yh = torch.zeros_like(logits).scatter_(dim, idx, 1.0)
+            return yh - y.detach() + y
+        F.gumbel_softmax = fake
+        return self
+
+    def __exit__(self, *a):
+        self.F.gumbel_softmax = self.orig
+
+
+def run_fixture(name):
+    dkw, B, in_seed, w_seed, variant, mode = FIXTURES[name]
+    d = synth.Dims(**dkw)
+    sd = synth.make_state_dict(d, seed=w_seed, variant=variant)
+    inp = synth.make_inputs(d, B, seed=in_seed, train=(mode == "train"))
+    model = build_reference_model(d, sd)
+    # dropout must be off for parity (SURVEY hard part 9); eval() does that, and for the
+    # train-mode fixture we zero every Dropout.p instead so self.training stays True.
+    if mode == "train":
+        model.train()
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+    else:
+        model.eval()
+    from pythia.common.sample import SampleList
+    sl = synth.to_sample_list(inp, SampleList, with_noise=False)
+    captured = {}
+    hooks = []
+    if d.model == "t2s":
+        def cap_temporal(mod, args, out):
+            captured["neg_frame_topk_mask"] = out[2].detach().clone()
+        hooks.append(model.Grounding_Module.frame_grounding_indicator.register_forward_hook(cap_temporal))
+    noise = {tuple(inp["gumbel_frame"].shape): inp["gumbel_frame"], tuple(inp["gumbel_ocr"].shape): inp["gumbel_ocr"]}
+    with torch.no_grad(), InjectGumbel(noise):
+        out = model.forward(sl)
+    for h in hooks:
+        h.remove()
+    res = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in out.items()}
+    # losses through the reference's own loss classes (modules/losses.py:323-385)
+    from pythia.modules.losses import POSBCEWithMaskLoss, InfoNCE
+    with torch.no_grad():
+        res["loss_pos_bce"] = POSBCEWithMaskLoss()(sl, out).numpy()
+        if d.model == "t2s":
+            res["loss_info_nce"] = InfoNCE()(sl, out).numpy()
+    for k, v in captured.items():
+        res[k] = v.numpy()
+    meta = dict(dims=dkw, batch=B, in_seed=in_seed, w_seed=w_seed, variant=variant, mode=mode,
+                torch=torch.__version__)
+    res["meta"] = np.asarray(repr(meta))
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **res)
+    print(name, {k: getattr(v, "shape", None) for k, v in res.items()}, "%.1f KB" % (os.path.getsize(path) / 1e3))
+
+
+if __name__ == "__main__":
+    install_shims()
+    torch.set_num_threads(os.cpu_count())
+    names = sys.argv[1:] or list(FIXTURES)
+    for n in names:
+        key = [k for k in FIXTURES if k == n or k.startswith(n)]
+        for k in key:
+            run_fixture(k)

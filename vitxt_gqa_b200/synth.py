@@ -1,0 +1,321 @@
+"""Synthetic t2s_abinet-shaped inputs and seeded random-init weights.
+
+There is no dataset and no checkpoint offline, so every parity / bench input is
+generated here from a seeded CPU `torch.Generator` (bit-reproducible on a given
+torch build).  Field names, shapes and dtypes follow what the reference dataset
+hands the model (reference pythia/datasets/videoqa/vtextgqa/dataset.py:83-287,
+consumed at pythia/models/t2s.py:177-258): int64 ids and masks, fp32 features,
+`temporal_id` = `frame_id` repeated per OCR slot (t2s.py:486-492 requires it),
+pad OCR slots all carry one identical "<pad>" feature pair (dataset.py:140).
+"""
+import math
+from dataclasses import dataclass, field
+
+import torch
+
+
+@dataclass
+class Dims:
+    """Shape parameters of one config (names after reference config keys)."""
+    txt_len: int = 20          # text_processor.max_length
+    frames: int = 64           # grounding.frame_num
+    ocr_per_frame: int = 15    # grounding.ocr_frame_num
+    dec_steps: int = 12        # answer_processor.max_copy_steps
+    vocab: int = 5000          # |fixed answer vocab|
+    hidden: int = 768
+    vit_dim: int = 1024
+    ft_dim: int = 300
+    phoc_dim: int = 604
+    id_dim: int = 50
+    frame_topk: int = 5
+    ocr_topk: int = 5
+    text_layers: int = 3
+    qtv_layers: int = 2
+    mmt_layers: int = 3
+    ground_enc_layers: int = 2   # Grounding_Module.encoder: dead weights
+    word_vocab: int = 30522
+    model: str = "t2s"           # "t2s" | "m4c"
+
+    @property
+    def ocr(self):
+        return self.frames * self.ocr_per_frame
+
+    @property
+    def num_outputs(self):
+        return self.vocab + self.ocr
+
+
+def dims_from_config(model_cfg, vocab=5000, model="t2s"):
+    g = model_cfg["grounding"]
+    return Dims(
+        frames=int(g["frame_num"]), ocr_per_frame=int(g["ocr_frame_num"]),
+        vocab=vocab, frame_topk=int(g["frame_topk"]), ocr_topk=int(g["ocr_topk"]),
+        text_layers=int(model_cfg["text_bert"]["num_hidden_layers"]),
+        qtv_layers=int(model_cfg["translayers"]["num_hidden_layers"]),
+        mmt_layers=int(model_cfg["mmt"]["num_hidden_layers"]),
+        ground_enc_layers=int(model_cfg["encoder"]["num_hidden_layers"]),
+        model=model,
+    )
+
+
+def model_config_for_dims(d: Dims):
+    """`model_attributes.<model>` dict for arbitrary dims (stress sweep / small tests)."""
+    t2s = d.model == "t2s"
+    return {
+        "lr_scale_frcn": 0.1, "lr_scale_text_bert": 0.1, "lr_scale_mmt": 1.0,
+        "text_bert_init_from_bert_base": False,
+        "text_bert": {"num_hidden_layers": d.text_layers},
+        "obj": {"mmt_in_dim": d.vit_dim + (d.id_dim if t2s else 0), "dropout_prob": 0.1},
+        "ocr": {"mmt_in_dim": d.ft_dim + d.phoc_dim + (2 * d.id_dim if t2s else 0), "dropout_prob": 0.1},
+        "translayers": {"hidden_size": d.hidden, "num_hidden_layers": d.qtv_layers},
+        "grounding": {"frame_topk": d.frame_topk, "ocr_topk": d.ocr_topk, "max_ocr_num": d.ocr,
+                      "frame_num": d.frames, "ocr_frame_num": d.ocr_per_frame, "hidden_size": d.hidden},
+        "encoder": {"hidden_size": d.hidden, "num_hidden_layers": d.ground_enc_layers},
+        "mmt": {"hidden_size": d.hidden, "num_hidden_layers": d.mmt_layers},
+        "classifier": {"type": "linear", "ocr_max_num": d.ocr,
+                       "ocr_ptr_net": {"hidden_size": d.hidden, "query_key_size": d.hidden}, "params": {}},
+        "metrics": [],
+        "losses": ([{"type": "pos_bce_loss", "weight": 1.0, "params": {}},
+                    {"type": "InfoNCE", "weight": 1000, "params": {}}] if t2s else
+                   [{"type": "pos_bce_loss", "weight": 1.0, "params": {}}]),
+    }
+
+
+# --------------------------------------------------------------------------- inputs
+def make_inputs(d: Dims, batch: int, seed: int = 1234, full_frames: bool = False, train: bool = False):
+    """Returns an ordered dict of CPU tensors (the SampleList fields) plus the
+    injected Gumbel noise `gumbel_frame [B,2,F]`, `gumbel_ocr [B,2,O]`
+    (= -log(Exp(1)), the quantity F.gumbel_softmax adds to the logits)."""
+    g = torch.Generator().manual_seed(seed)
+    B, F, Of, O = batch, d.frames, d.ocr_per_frame, d.ocr
+
+    def randint(lo, hi, shape):
+        return torch.randint(lo, hi + 1, shape, generator=g, dtype=torch.int64)
+
+    out = {}
+    text_len = randint(5, d.txt_len, (B,))
+    text = randint(1000, d.word_vocab - 1, (B, d.txt_len))
+    text = text * (torch.arange(d.txt_len)[None, :] < text_len[:, None])
+    out["text"], out["text_len"] = text, text_len
+
+    lo_f = min(8, F)
+    n_frames = torch.full((B,), F, dtype=torch.int64) if full_frames else randint(lo_f, F, (B,))
+    max_step = max(1, min(10, 3999 // max(F, 1)))
+    step = randint(1, max_step, (B,))
+    pos = torch.arange(F)[None, :]
+    fvalid = pos < n_frames[:, None]
+    out["frame_id"] = (1 + pos * step[:, None]) * fvalid
+    out["frame_mask"] = fvalid.to(torch.int64)
+    vf = torch.randn(B, F, d.vit_dim, generator=g)
+    out["video_feat"] = vf * fvalid[:, :, None]
+
+    out["temporal_id"] = out["frame_id"].repeat_interleave(Of, dim=1)
+    n_ocr = randint(0, Of, (B, F)) * fvalid
+    slot = torch.arange(Of)[None, None, :]
+    ovalid = (slot < n_ocr[:, :, None]).reshape(B, O)
+    out["ocr_mask"] = ovalid.to(torch.int64)
+    out["track_id"] = randint(1, 200, (B, O)) * ovalid
+    pad_ft = torch.randn(d.ft_dim, generator=g) * 0.3
+    pad_phoc = (torch.rand(d.phoc_dim, generator=g) < 0.04).float()
+    ft = torch.randn(B, O, d.ft_dim, generator=g) * 0.3
+    phoc = (torch.rand(B, O, d.phoc_dim, generator=g) < 0.04).float()
+    out["context_feature_0"] = torch.where(ovalid[:, :, None], ft, pad_ft)
+    out["context_feature_1"] = torch.where(ovalid[:, :, None], phoc, pad_phoc)
+    c = torch.rand(B, O, 2, 2, generator=g).sort(dim=2).values   # [.., (lo,hi), (x,y)]
+    box = torch.stack([c[:, :, 0, 0], c[:, :, 0, 1], c[:, :, 1, 0], c[:, :, 1, 1]], -1)
+    out["ocr_bbox_coordinates"] = box * ovalid[:, :, None]
+
+    T, n_out = d.dec_steps, d.num_outputs
+    if train:
+        alen = randint(1, min(6, T - 1), (B,))
+        idx = randint(4, n_out - 1, (B, T))
+        tpos = torch.arange(T)[None, :]
+        prev = torch.where((tpos >= 1) & (tpos <= alen[:, None]), idx, torch.zeros_like(idx))
+        prev[:, 0] = 1
+        out["train_prev_inds"] = prev
+        out["train_loss_mask"] = (tpos <= alen[:, None]).float()
+    else:
+        out["train_prev_inds"] = torch.zeros(B, T, dtype=torch.int64)
+        alen = randint(1, min(6, T - 1), (B,))
+        out["train_loss_mask"] = (torch.arange(T)[None, :] <= alen[:, None]).float()
+    targets = torch.zeros(B, T, n_out)
+    tgt_idx = randint(4, n_out - 1, (B, T, 2))
+    targets.scatter_(2, tgt_idx, 1.0)
+    out["targets"] = targets * out["train_loss_mask"][:, :, None]
+
+    if d.model == "m4c":
+        mid = (n_frames - 1) // 2
+        out["middel_frame_idx"] = (mid + 1)[:, None]                      # 1-based position
+        out["middel_frame_id"] = out["frame_id"].gather(1, mid[:, None])
+        out["mid_img_feat"] = out["video_feat"].gather(1, mid[:, None, None].expand(B, 1, d.vit_dim))
+
+    ef = torch.empty(B, 2, F).exponential_(generator=g)
+    eo = torch.empty(B, 2, O).exponential_(generator=g)
+    out["gumbel_frame"] = -ef.log()
+    out["gumbel_ocr"] = -eo.log()
+    return out
+
+
+SAMPLE_FIELDS = ("text", "text_len", "video_feat", "frame_id", "frame_mask", "context_feature_0",
+                 "context_feature_1", "temporal_id", "track_id", "ocr_bbox_coordinates", "ocr_mask",
+                 "train_prev_inds", "targets", "train_loss_mask",
+                 "mid_img_feat", "middel_frame_id", "middel_frame_idx")
+
+
+def to_sample_list(inputs, sample_list_cls, with_noise=True, dataset_name="vtextgqa", dataset_type="val"):
+    sl = sample_list_cls()
+    for k in SAMPLE_FIELDS:
+        if k in inputs:
+            sl.add_field(k, inputs[k])
+    if with_noise:
+        sl.add_field("gumbel_frame", inputs["gumbel_frame"])
+        sl.add_field("gumbel_ocr", inputs["gumbel_ocr"])
+    sl.add_field("dataset_name", dataset_name)
+    sl.add_field("dataset_type", dataset_type)
+    return sl
+
+
+# --------------------------------------------------------------------------- weights
+def _bert_layer_shapes(prefix, hidden, inter):
+    s = {}
+    for n in ("query", "key", "value"):
+        s[f"{prefix}.attention.self.{n}.weight"] = (hidden, hidden)
+        s[f"{prefix}.attention.self.{n}.bias"] = (hidden,)
+    s[f"{prefix}.attention.output.dense.weight"] = (hidden, hidden)
+    s[f"{prefix}.attention.output.dense.bias"] = (hidden,)
+    s[f"{prefix}.attention.output.LayerNorm.weight"] = (hidden,)
+    s[f"{prefix}.attention.output.LayerNorm.bias"] = (hidden,)
+    s[f"{prefix}.intermediate.dense.weight"] = (inter, hidden)
+    s[f"{prefix}.intermediate.dense.bias"] = (inter,)
+    s[f"{prefix}.output.dense.weight"] = (hidden, inter)
+    s[f"{prefix}.output.dense.bias"] = (hidden,)
+    s[f"{prefix}.output.LayerNorm.weight"] = (hidden,)
+    s[f"{prefix}.output.LayerNorm.bias"] = (hidden,)
+    return s
+
+
+def param_shapes(d: Dims):
+    """Ordered {state_dict key: shape}; key names are the reference's
+    (SURVEY 8b 'Parameter naming'; reference t2s.py:43-151,378-451,521-527,
+    548-554,636-646,673-687; m4c.py equivalents)."""
+    H, I = d.hidden, 4 * d.hidden
+    t2s = d.model == "t2s"
+    s = {}
+    s["text_bert.embeddings.word_embeddings.weight"] = (d.word_vocab, H)
+    s["text_bert.embeddings.position_embeddings.weight"] = (512, H)
+    s["text_bert.embeddings.token_type_embeddings.weight"] = (2, H)
+    s["text_bert.embeddings.LayerNorm.weight"] = (H,)
+    s["text_bert.embeddings.LayerNorm.bias"] = (H,)
+    for i in range(d.text_layers):
+        s.update(_bert_layer_shapes(f"text_bert.encoder.layer.{i}", H, I))
+    s["frame_embeddings.weight"] = (4000, d.id_dim)
+    obj_in = d.vit_dim + (d.id_dim if t2s else 0)
+    ocr_in = d.ft_dim + d.phoc_dim + (2 * d.id_dim if t2s else 0)
+    s["linear_obj_feat_to_mmt_in.weight"] = (H, obj_in)
+    s["linear_obj_feat_to_mmt_in.bias"] = (H,)
+    s["obj_feat_layer_norm.weight"] = (H,)
+    s["obj_feat_layer_norm.bias"] = (H,)
+    s["obj_frame_layer_norm.weight"] = (H,)
+    s["obj_frame_layer_norm.bias"] = (H,)
+    s["linear_obj_frame_to_mmt_in.weight"] = (H, d.id_dim)
+    s["linear_obj_frame_to_mmt_in.bias"] = (H,)
+    s["linear_ocr_feat_to_mmt_in.weight"] = (H, ocr_in)
+    s["linear_ocr_feat_to_mmt_in.bias"] = (H,)
+    s["linear_ocr_bbox_to_mmt_in.weight"] = (H, 4)
+    s["linear_ocr_bbox_to_mmt_in.bias"] = (H,)
+    s["temporal_position_embeddings.weight"] = (4000, d.id_dim)
+    s["track_position_embeddings.weight"] = (4000, d.id_dim)
+    s["ocr_feat_layer_norm.weight"] = (H,)
+    s["ocr_feat_layer_norm.bias"] = (H,)
+    s["ocr_bbox_layer_norm.weight"] = (H,)
+    s["ocr_bbox_layer_norm.bias"] = (H,)
+    if t2s:
+        for i in range(d.qtv_layers):
+            s.update(_bert_layer_shapes(f"TransLayer.encoder.layer.{i}", H, I))
+        g = "Grounding_Module"
+        s[f"{g}.q_linear.weight"] = (H, H)
+        s[f"{g}.q_linear.bias"] = (H,)
+        s[f"{g}.frame_attn.weight"] = (1, 2 * H)
+        s[f"{g}.frame_attn.bias"] = (1,)
+        s[f"{g}.self_attn.weight"] = (1, H)
+        s[f"{g}.self_attn.bias"] = (1,)
+        for ind, names in (("frame_grounding_indicator", ("frame_pos_att", "frame_neg_att")),
+                           ("ocr_grounding_indicator", ("ocr_pos_att", "ocr_neg_att"))):
+            for n in names:
+                for lin in ("linear_q", "linear_k"):
+                    s[f"{g}.{ind}.{n}.{lin}.weight"] = (H, H)
+                    s[f"{g}.{ind}.{n}.{lin}.bias"] = (H,)
+        for i in range(d.ground_enc_layers):
+            s.update(_bert_layer_shapes(f"{g}.encoder.layer.{i}", H, I))
+    else:
+        g = "PostHoc"
+        s[f"{g}.q_linear.weight"] = (H, H)
+        s[f"{g}.q_linear.bias"] = (H,)
+        s[f"{g}.self_attn.weight"] = (1, H)
+        s[f"{g}.self_attn.bias"] = (1,)
+        for lin in ("linear_q", "linear_k"):
+            s[f"{g}.ocr_att.{lin}.weight"] = (H, H)
+            s[f"{g}.ocr_att.{lin}.bias"] = (H,)
+    p = "mmt.prev_pred_embeddings"
+    s[f"{p}.position_embeddings.weight"] = (100, H)
+    s[f"{p}.token_type_embeddings.weight"] = (5, H)
+    for ln in ("ans_layer_norm", "ocr_layer_norm", "emb_layer_norm"):
+        s[f"{p}.{ln}.weight"] = (H,)
+        s[f"{p}.{ln}.bias"] = (H,)
+    for i in range(d.mmt_layers):
+        s.update(_bert_layer_shapes(f"mmt.encoder.layer.{i}", H, I))
+    s["ocr_ptr_net.query.weight"] = (H, H)
+    s["ocr_ptr_net.query.bias"] = (H,)
+    s["ocr_ptr_net.key.weight"] = (H, H)
+    s["ocr_ptr_net.key.bias"] = (H,)
+    s["classifier.module.weight"] = (d.vocab, H)
+    s["classifier.module.bias"] = (d.vocab,)
+    return s
+
+
+_BERT_PREFIXES = ("text_bert.", "TransLayer.", "mmt.")
+
+
+def make_state_dict(d: Dims, seed: int = 0, variant: str = "default"):
+    """Seeded random-init weights, by key name, as CPU fp32 tensors.
+
+    Distributions follow the reference's initialisers: N(0, 0.02) for every
+    Linear/Embedding inside a BertPreTrainedModel (text_bert / TransLayer / mmt,
+    via init_weights), PyTorch defaults elsewhere (Linear U(+-1/sqrt(in)),
+    Embedding N(0,1), LayerNorm 1/0).  variant="stress": additionally
+    classifier weight x0.05 and bias 0 so the greedy decode is non-degenerate
+    (SURVEY hard part 8), LayerNorm affine parameters perturbed and Linear
+    biases inside BERT stacks made non-zero, so parity exercises every term.
+    """
+    assert variant in ("default", "stress")
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    shapes = param_shapes(d)
+    for k, shape in shapes.items():
+        is_ln = "LayerNorm" in k or "layer_norm" in k
+        in_bert = k.startswith(_BERT_PREFIXES)
+        if is_ln:
+            base = torch.ones(shape) if k.endswith("weight") else torch.zeros(shape)
+            if variant == "stress":
+                base = base + 0.1 * torch.randn(shape, generator=g)
+            t = base
+        elif k.endswith("bias"):
+            if in_bert:
+                t = torch.zeros(shape)
+                if variant == "stress":
+                    t = 0.02 * torch.randn(shape, generator=g)
+            else:
+                w_in = shapes[k[:-4] + "weight"][1]
+                t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(w_in)
+        elif in_bert:
+            t = torch.randn(shape, generator=g) * 0.02
+        elif "embeddings.weight" in k:          # nn.Embedding default N(0,1)
+            t = torch.randn(shape, generator=g)
+        else:                                   # nn.Linear default: U(+-1/sqrt(fan_in))
+            t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(shape[1])
+        sd[k] = t.contiguous()
+    sd["text_bert.embeddings.word_embeddings.weight"][0].zero_()     # padding_idx=0
+    if variant == "stress":
+        sd["classifier.module.weight"] *= 0.05
+        sd["classifier.module.bias"].zero_()
+    return sd
