@@ -1,0 +1,131 @@
+/* libt2s_sm100 -- C ABI of the B200-native forward/grounding path of T2S-QA / M4C.
+ *
+ * The reference has no FFI for this path: every device operation is a stock ATen call made from
+ * pythia/models/t2s.py, pythia/models/m4c.py, pythia/modules/spatio_temporal_grounding.py and
+ * pythia/modules/losses.py.  Each entry point below replaces the ATen call group cited beside it
+ * (paths relative to /root/reference/pythia); INTEGRATION.md shows the ctypes binding a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises,
+ *     nothing allocates (workspaces are passed in, see *_workspace_bytes)
+ *   - return value: 0 = ok, < 0 = argument error (T2S_ERR_*), > 0 = cudaError_t of the launch;
+ *     t2s_last_error() returns a thread-local description of the last failure
+ *   - matrices are row-major; `ld*` are row pitches in ELEMENTS; dims are in elements
+ *   - ids / masks coming from the dataset are int64 as in the reference
+ */
+#ifndef T2S_B200_H
+#define T2S_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T2S_ABI_VERSION 1
+
+/* t2s_gemm_* flags */
+#define T2S_GEMM_GELU 1     /* erf-GELU after bias (BertIntermediate, modeling_bert.gelu)           */
+#define T2S_GEMM_OUT_F32 2  /* bf16 GEMM: store C as fp32 instead of bf16                           */
+#define T2S_GEMM_RES_F32 4  /* bf16 GEMM: residual operand is fp32 instead of bf16                  */
+
+int t2s_abi_version(void);
+const char* t2s_last_error(void);
+
+/* K1  C[M,N] = epi(A[M,K] . W[N,K]^T + bias (+ residual)); A, W bf16; tcgen05 + TMA + TMEM.
+ * Replaces nn.Linear/addmm of BertSelfAttention.query/key/value, BertSelfOutput.dense,
+ * BertIntermediate.dense(+gelu), BertOutput.dense (via models/t2s.py:622), ClassifierLayer
+ * (modules/layers.py:101-107), OcrPtrNet.query/key (models/t2s.py:653,659).
+ * block_n: 0 = auto, or 64 / 128 / 256.  lda, ldw multiples of 8; bases 16-byte aligned. */
+int t2s_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                  const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K,
+                  int flags, int block_n, void* stream);
+
+/* K1f same contraction in fp32 on the FMA pipes (grounding chain: TextBert t2s.py:538, obj/OCR
+ * encoders t2s.py:211,248, QTV t2s.py:423, Grounding_Module.q_linear t2s.py:472). K % 4 == 0.
+ * a_rows_per_group > 0 gathers A row m from (m / per) * a_group_rows + a_row_off + m % per. */
+int t2s_gemm_f32(const float* A, long long lda, const float* W, long long ldw, const float* bias,
+                 const float* residual, long long ldr, float* C, long long ldc, int M, int N, int K,
+                 int flags, int a_rows_per_group, int a_group_rows, int a_row_off, void* stream);
+
+/* K2  masked multi-head attention over a fused [rows, 3H] q|k|v buffer (head size 64).
+ * Replaces BertSelfAttention matmul/+mask/softmax/matmul and the [B,1,L,L] masks of
+ * models/t2s.py:413-419,533-534,609-618.  key_idx[b, 0..n_keys[b]) lists the valid key rows. */
+int t2s_attn_f32(const float* qkv, long long ld, int B, int L, int H, int heads, const int* key_idx,
+                 const int* n_keys, int key_stride, float* out, long long ldo, void* stream);
+int t2s_attn_bf16(const void* qkv, long long ld, int B, int L, int H, int heads, const int* key_idx,
+                  const int* n_keys, int key_stride, void* out, long long ldo, void* stream);
+/* decoder rows t0..t0+nq-1 (nq <= 16): valid encoder keys + causal decoder keys (t2s.py:574-579,609-615) */
+int t2s_attn_dec(const void* qkv_enc, long long ld_enc, int L_enc, const void* qkv_dec, long long ld_dec,
+                 int T, int B, int H, int heads, const int* key_idx, const int* n_keys, int key_stride,
+                 int t0, int nq, void* out, long long ldo, void* stream);
+
+/* K3  BertEmbeddings: LN(word[id] + position[row % L] + token_type[0])  (via models/t2s.py:530) */
+int t2s_bert_embed_ln(const long long* ids, int rows, int L, int H, const float* word, const float* pos,
+                      const float* type0, const float* gamma, const float* beta, float eps, float* out,
+                      long long ldo, void* stream);
+/* K3  [normalize(f0) | normalize(f1) | tab0[id0] | tab1[id1] | 0-pad] -> fp32 rows
+ * (F.normalize + nn.Embedding + torch.cat of models/t2s.py:195-207 and 223-244) */
+int t2s_feat_concat(const float* f0, int d0, const float* f1, int d1, const long long* id0, const float* tab0,
+                    const long long* id1, const float* tab1, int id_dim, int rows, float* out, long long ldo,
+                    int k_pad, void* stream);
+/* K4  y = LN(x (+ res)); optional epilogue y = tanh_base + tanh(y) (QTV residual, t2s.py:430-432);
+ * fp32 and/or bf16 output; output rows remapped as (r / rows_per_group) * out_group_rows +
+ * out_row_off + r % rows_per_group when rows_per_group > 0 (writes straight into the joint
+ * [txt; frames; ocr] buffer instead of torch.cat, t2s.py:392-395). */
+int t2s_add_ln(const void* x, int x_bf16, long long ldx, const void* res, int res_bf16, long long ldr,
+               const float* gamma, const float* beta, float eps, int rows, int H, const float* tanh_base,
+               long long ld_base, float* out32, long long ldo32, void* out16, long long ldo16,
+               int rows_per_group, int out_group_rows, int out_row_off, void* stream);
+/* K3  LN(h) + LN(W2 . bbox + b2)  (models/t2s.py:246-252) */
+int t2s_ocr_finish(const float* h, long long ldh, const float* bbox, const float* w2, const float* b2,
+                   const float* g1, const float* be1, const float* g2, const float* be2, float eps, int rows,
+                   int H, float* out, long long ldo, int rows_per_group, int out_group_rows, int out_row_off,
+                   void* stream);
+/* K3  PrevPredEmbeddings.forward for decoder positions t0..t0+nt-1 (models/t2s.py:690-723) */
+int t2s_prev_embed(const long long* prev_inds, int ld_prev, int B, int t0, int nt, int T, int V, int H,
+                   const float* ans_w, const float* ocr_emb, long long ocr_batch_stride, long long ld_ocr,
+                   const float* pos_emb, const float* type_emb, const float* ans_g, const float* ans_b,
+                   const float* ocr_g, const float* ocr_b, const float* emb_g, const float* emb_b, float eps,
+                   void* out16, float* out32, long long ldo, void* stream);
+int t2s_cast_rows_bf16(const float* x, long long ldx, int rows, int H, void* out, long long ldo,
+                       int rows_per_group, int out_group_rows, int out_row_off, void* stream);
+
+/* K5  grounding (models/t2s.py:453-518, modules/spatio_temporal_grounding.py:15-142, m4c.py:356-422) */
+int t2s_mask_prep(const long long* text_len, const long long* frame_mask, const long long* ocr_mask, int B,
+                  int Lt, int F, int O, float* joint, void* stream);
+int t2s_build_keys(const float* mask, int B, int L, int* key_idx, int* n_keys, int key_stride, void* stream);
+int t2s_question_pool(const float* qp, int B, int Lt, int H, const float* w, const float* bw,
+                      const float* txt_mask, int mask_stride, float* gq, void* stream);
+int t2s_sim_scores(const float* gq, const float* X, long long batch_stride, long long ldx, int row0, int N,
+                   int H, int B, float* sim, void* stream);
+int t2s_temporal_select(const float* sim, int sim_stride, const float* joint_mask, int B, int Lt, int F,
+                        int Of, const float* gumbel, const long long* frame_id, const long long* temporal_id,
+                        int topk, const float* pos_override, const float* neg_override,
+                        long long* ground_frame, float* pos_joint, float* neg_joint, float* slot_mask,
+                        float* dbg_score, void* stream);
+int t2s_spatial_select(const float* sim, int sim_stride, int sim_off, const float* slot_mask,
+                       const float* joint_mask, int B, int L_joint, int ocr_off, int F, int Of,
+                       const float* gumbel, const float* boxes, int topk, int mode, float* ground_box,
+                       float* pos_joint, float* neg_joint, float* dbg_score, void* stream);
+int t2s_middle_frame_slots(const long long* mid_id, const long long* temporal_id, int B, int O,
+                           float* slot_mask, void* stream);
+
+/* K6  pointer scores written into scores[:, :, V:], argmax feedback (models/t2s.py:661-666,285,353-354) */
+int t2s_ptr_score(const void* q, long long ldq, int B, int T, int t0, int nq, const void* keyp,
+                  long long key_batch_stride, long long ldk, int O, int H, const float* mask,
+                  long long mask_stride, float* scores, long long ld_scores, int V, void* stream);
+int t2s_argmax_feedback(const float* scores, long long ld_scores, int B, int T, int t0, int nt, int N,
+                        long long* prev_inds, int ld_prev, long long* argmax_out, void* stream);
+
+/* K7  losses (modules/losses.py:329-343 and 361-385) */
+long long t2s_loss_workspace_bytes(int B, int T);
+int t2s_pos_bce_loss(const float* scores, const float* targets, const float* loss_mask, int B, int T, int N,
+                     void* workspace, float* out, void* stream);
+int t2s_info_nce_loss(const float* ref, const float* pos, const float* neg, int B, int T, int N,
+                      float temperature, void* workspace, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T2S_B200_H */

@@ -187,7 +187,9 @@ def temporal_indicator(q, frames, frame_mask, frame_id, topk, gumbels, neg_topk_
         neg_topk = neg_topk_override
     pos_f = torch.nonzero(pos_topk, as_tuple=False)[:, 1].view(B, topk)
     ground_frame = torch.gather(frame_id, 1, pos_f)
-    return ground_frame, pos_topk, neg_topk, dict(frame_score=pos, frame_pos_sel=pos_mask, frame_neg_score=neg)
+    return ground_frame, pos_topk, neg_topk, dict(frame_score=pos, frame_pos_sel=pos_mask, frame_neg_score=neg,
+                                                  frame_pos_topk=pos_topk, frame_neg_topk=neg_topk,
+                                                  n_pos_frames=(pos_mask != 0).sum(1))
 
 
 def spatial_indicator(q, ocr, boxes, attn_mask, o_topk, frame_num, o_frame_num, gumbels):

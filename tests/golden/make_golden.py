@@ -137,6 +137,7 @@ def run_fixture(name):
     hooks = []
     if d.model == "t2s":
         def cap_temporal(mod, args, out):
+            captured["pos_frame_topk_mask"] = out[1].detach().clone()
             captured["neg_frame_topk_mask"] = out[2].detach().clone()
         hooks.append(model.Grounding_Module.frame_grounding_indicator.register_forward_hook(cap_temporal))
     noise = {tuple(inp["gumbel_frame"].shape): inp["gumbel_frame"], tuple(inp["gumbel_ocr"].shape): inp["gumbel_ocr"]}

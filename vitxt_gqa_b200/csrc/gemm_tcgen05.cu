@@ -1,0 +1,364 @@
+// K1: bf16 GEMM on the 5th-gen tensor cores.  C[M,N] = epi(A[M,K] . W[N,K]^T + bias)
+//
+// Replaces every `addmm` the reference issues for the dense layers of the
+// fusion transformer (BertSelfAttention.query/key/value fused to N=2304,
+// BertSelfOutput.dense, BertIntermediate.dense + erf-GELU, BertOutput.dense,
+// the classifier `nn.Linear(768, V)` of reference pythia/modules/layers.py:101,
+// OcrPtrNet.query/key of pythia/models/t2s.py:645-646) -- SURVEY 2.3.
+//
+// Design (one CTA per SM, persistent over output tiles, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of a 128x64 A tile and a
+//               BNx64 W tile (both K-major, 128B swizzle) into a STAGES-deep smem ring,
+//               completion on `full[s]` mbarriers.
+//   warp 1      MMA issuer: one elected lane issues 4 x tcgen05.mma (M=128, N=BN, K=16)
+//               per k-block into a TMEM accumulator; tcgen05.commit releases the smem
+//               slot (`empty[s]`) and, after the last k-block, publishes the accumulator
+//               (`tfull[a]`).  Two accumulators (2 x BN TMEM columns) so the epilogue of
+//               tile i overlaps the main loop of tile i+1.
+//   warps 2..9  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> bias /
+//               erf-GELU / residual -> bf16 or fp32 -> 16-byte global stores.
+// Tiles are walked n-fastest so the CTAs running concurrently share one A row-block
+// through L2 and A streams from HBM once.
+#include "common.cuh"
+#include "../../include/t2s_b200.h"
+
+namespace t2s {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;          // 64 bf16 = one 128-byte swizzle row
+constexpr int GEMM_THREADS = 320;    // 10 warps
+constexpr int GEMM_EPI_WARPS = 8;
+
+struct GemmEpi {
+    void* C;
+    const float* bias;
+    const void* residual;
+    long long ldc, ldr;
+    int flags;
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = 2 * BN;     // 512 / 256 / 128: powers of two >= 32
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         GemmEpi ep, int M, int N, int K) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_n = (N + BN - 1) / BN;
+    const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
+    const int tiles = num_m * num_n;
+    const int kblocks = (K + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(&tfull[a], 1);
+                mbar_init(&tempty[a], GEMM_EPI_WARPS);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                if (lane == 0) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(sa, &tmA, &full[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * GEMM_BK, n_blk * BN);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t da = make_sw128_kmajor_desc(sa);
+                    const uint64_t db = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        // +32 B per K=16 step inside the swizzle atom == +2 in the (addr >> 4) field
+                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (kb == kblocks - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    } else {
+        // ------------------------------------------------ epilogue (8 warps)
+        const int ew = warp - 2;
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                // which half of the BN columns
+        constexpr int COLS_PER_WARP = BN / 2;
+        const bool gelu = ep.flags & T2S_GEMM_GELU;
+        const bool out_f32 = ep.flags & T2S_GEMM_OUT_F32;
+        const bool res_f32 = ep.flags & T2S_GEMM_RES_F32;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * GEMM_BM + quarter * 32 + lane;
+            const bool row_ok = row < M;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
+                uint32_t r[32];
+                const int cw = half * COLS_PER_WARP + c0;
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cw, r);
+                tmem_ld_wait();
+                const int col0 = n_blk * BN + cw;
+                if (row_ok && col0 < N) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {      // 4 groups of 8 columns
+                        const int col = col0 + g * 8;
+                        if (col >= N) break;
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+                        const bool full8 = col + 8 <= N;
+                        if (ep.bias) {
+                            if (full8) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 4));
+                                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                            } else {
+                                for (int j = 0; j < 8; ++j) if (col + j < N) v[j] += __ldg(ep.bias + col + j);
+                            }
+                        }
+                        if (gelu) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+                        }
+                        if (ep.residual) {
+                            if (res_f32) {
+                                const float* rp = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + col;
+                                if (full8) {
+                                    const float4 a0 = *reinterpret_cast<const float4*>(rp);
+                                    const float4 a1 = *reinterpret_cast<const float4*>(rp + 4);
+                                    v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+                                    v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+                                } else {
+                                    for (int j = 0; j < 8; ++j) if (col + j < N) v[j] += rp[j];
+                                }
+                            } else {
+                                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + col;
+                                if (full8) {
+                                    const uint4 a = *reinterpret_cast<const uint4*>(rp);
+                                    v[0] += bf16lo(a.x); v[1] += bf16hi(a.x); v[2] += bf16lo(a.y); v[3] += bf16hi(a.y);
+                                    v[4] += bf16lo(a.z); v[5] += bf16hi(a.z); v[6] += bf16lo(a.w); v[7] += bf16hi(a.w);
+                                } else {
+                                    for (int j = 0; j < 8; ++j) if (col + j < N) v[j] += __bfloat162float(rp[j]);
+                                }
+                            }
+                        }
+                        if (out_f32) {
+                            float* cp = reinterpret_cast<float*>(ep.C) + (long long)row * ep.ldc + col;
+                            if (full8) {
+                                *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+                                *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                            } else {
+                                for (int j = 0; j < 8; ++j) if (col + j < N) cp[j] = v[j];
+                            }
+                        } else {
+                            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(ep.C) + (long long)row * ep.ldc + col;
+                            if (full8) {
+                                uint4 o;
+                                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                                *reinterpret_cast<uint4*>(cp) = o;
+                            } else {
+                                for (int j = 0; j < 8; ++j) if (col + j < N) cp[j] = __float2bfloat16_rn(v[j]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2D bf16 row-major [rows, cols] with row pitch `ld` elements; box = box_rows x 64, 128B swizzle.
+static int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld,
+                          int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return T2S_ERR_DRIVER;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed: CUresult %d (ptr %p rows %lld cols %lld ld %lld)", (int)r, ptr, rows,
+                  cols, ld);
+        return T2S_ERR_DRIVER;
+    }
+    return T2S_OK;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& ep, int M, int N, int K,
+                       cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr_set = true;
+    }
+    const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K);
+    return launch_status("gemm_bf16_tcgen05");
+}
+
+}  // namespace t2s
+
+using namespace t2s;
+
+extern "C" int t2s_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                             const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K,
+                             int flags, int block_n, void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0) { set_error("gemm_bf16: bad shape %d %d %d", M, N, K); return T2S_ERR_SHAPE; }
+    if ((lda % 8) || (ldw % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) {
+        set_error("gemm_bf16: A/W need 16-byte aligned base and row pitch (lda %lld ldw %lld)", lda, ldw);
+        return T2S_ERR_ALIGN;
+    }
+    const bool out_f32 = flags & T2S_GEMM_OUT_F32;
+    if ((ldc % (out_f32 ? 4 : 8)) || (reinterpret_cast<uintptr_t>(C) & 15)) {
+        set_error("gemm_bf16: C needs 16-byte aligned base and row pitch (ldc %lld)", ldc);
+        return T2S_ERR_ALIGN;
+    }
+    if (residual && ((ldr % ((flags & T2S_GEMM_RES_F32) ? 4 : 8)) || (reinterpret_cast<uintptr_t>(residual) & 15))) {
+        set_error("gemm_bf16: residual alignment (ldr %lld)", ldr);
+        return T2S_ERR_ALIGN;
+    }
+    if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) { set_error("gemm_bf16: bias alignment"); return T2S_ERR_ALIGN; }
+    int bn = block_n;
+    if (bn == 0) {
+        // largest tile that still gives every SM work; small problems take the narrow tile
+        const long long mt = (M + GEMM_BM - 1) / GEMM_BM;
+        if (mt * ((N + 255) / 256) >= num_sms()) bn = 256;
+        else if (mt * ((N + 127) / 128) >= num_sms()) bn = 128;
+        else bn = 64;
+    }
+    CUtensorMap ta, tb;
+    int rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tb, W, N, K, ldw, bn);
+    if (rc) return rc;
+    GemmEpi ep{C, bias, residual, ldc, ldr, flags};
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (bn) {
+        case 256: return launch_gemm<256>(ta, tb, ep, M, N, K, st);
+        case 128: return launch_gemm<128>(ta, tb, ep, M, N, K, st);
+        case 64: return launch_gemm<64>(ta, tb, ep, M, N, K, st);
+        default: set_error("gemm_bf16: block_n must be 0, 64, 128 or 256"); return T2S_ERR_ARG;
+    }
+}

@@ -1,0 +1,341 @@
+// K3 / K4: embedding gathers, L2-normalise + concat, and (residual +) LayerNorm rows.
+// All kernels are HBM-bound streaming kernels: one warp per 768-wide row, 16-byte vector
+// accesses, row statistics by warp shuffle, nothing staged in shared memory.
+//
+// Reference call sites replaced:
+//   t2s_bert_embed_ln   BertEmbeddings (word+position+token_type -> LN), via pythia/models/t2s.py:530
+//   t2s_feat_concat     F.normalize + nn.Embedding + torch.cat of t2s.py:195-207 and 223-244
+//   t2s_add_ln          BertSelfOutput/BertOutput LayerNorm(x + residual); obj_feat_layer_norm
+//                       (t2s.py:209-213); QTV's x + tanh(enc(x)) (t2s.py:430-432) as an epilogue
+//   t2s_ocr_finish      LN(linear_ocr_feat) + LN(linear_ocr_bbox(bbox)) of t2s.py:246-252
+//   t2s_prev_embed      PrevPredEmbeddings.forward (t2s.py:690-723), gathering only the rows used
+#include "common.cuh"
+#include "../../include/t2s_b200.h"
+
+namespace t2s {
+
+constexpr int NE_THREADS = 128;      // 4 rows per CTA
+constexpr int NE_MAXV = 8;           // H <= 1024 (H % 128 == 0)
+
+struct RowMap {           // out_row = (r / per) * group + off + r % per
+    int per, group, off;
+    __device__ __forceinline__ long long operator()(int r) const {
+        return per > 0 ? (long long)(r / per) * group + off + (r % per) : (long long)r;
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    return make_float4(bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y));
+}
+__device__ __forceinline__ void store4_bf16(__nv_bfloat16* p, float4 v) {
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = o;
+}
+
+// LayerNorm of one row held as nv float4 per lane (element index = (i*32 + lane)*4).
+__device__ __forceinline__ void warp_layernorm(float4 (&x)[NE_MAXV], int nv, int H, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, float eps, int lane) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NE_MAXV; ++i)
+        if (i < nv) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    const float mean = warp_sum(s) / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NE_MAXV; ++i)
+        if (i < nv) {
+            const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    const float var = warp_sum(q) / (float)H;
+    const float rstd = 1.0f / sqrtf(var + eps);
+#pragma unroll
+    for (int i = 0; i < NE_MAXV; ++i)
+        if (i < nv) {
+            const int e = (i * 32 + lane) * 4;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + e));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + e));
+            x[i].x = (x[i].x - mean) * rstd * g.x + bb.x;
+            x[i].y = (x[i].y - mean) * rstd * g.y + bb.y;
+            x[i].z = (x[i].z - mean) * rstd * g.z + bb.z;
+            x[i].w = (x[i].w - mean) * rstd * g.w + bb.w;
+        }
+}
+
+// ------------------------------------------------------------------------------- BertEmbeddings
+__global__ void __launch_bounds__(NE_THREADS)
+bert_embed_ln_kernel(const long long* __restrict__ ids, int rows, int L, int H, const float* __restrict__ word,
+                     const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, float* __restrict__ out, long long ldo) {
+    const int row = blockIdx.x * (NE_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nv = H / 128;
+    const long long id = ids[row];
+    const int p = row % L;
+    float4 x[NE_MAXV];
+#pragma unroll
+    for (int i = 0; i < NE_MAXV; ++i)
+        if (i < nv) {
+            const int e = (i * 32 + lane) * 4;
+            const float4 w = *reinterpret_cast<const float4*>(word + id * H + e);
+            const float4 q = *reinterpret_cast<const float4*>(pos + (long long)p * H + e);
+            const float4 t = *reinterpret_cast<const float4*>(type0 + e);
+            x[i] = make_float4((w.x + q.x) + t.x, (w.y + q.y) + t.y, (w.z + q.z) + t.z, (w.w + q.w) + t.w);
+        }
+    warp_layernorm(x, nv, H, gamma, beta, eps, lane);
+#pragma unroll
+    for (int i = 0; i < NE_MAXV; ++i)
+        if (i < nv) *reinterpret_cast<float4*>(out + (long long)row * ldo + (i * 32 + lane) * 4) = x[i];
+}
+
+// ------------------------------------------------------------------------------- normalise + concat
+// out[r] = [ f0/max(|f0|,1e-12) | f1/max(|f1|,1e-12) | tab0[id0[r]] | tab1[id1[r]] | 0-pad ]  (fp32)
+__global__ void __launch_bounds__(NE_THREADS)
+feat_concat_kernel(const float* __restrict__ f0, int d0, const float* __restrict__ f1, int d1,
+                   const long long* __restrict__ id0, const float* __restrict__ tab0,
+                   const long long* __restrict__ id1, const float* __restrict__ tab1, int id_dim, int rows,
+                   float* __restrict__ out, long long ldo, int k_pad) {
+    const int row = blockIdx.x * (NE_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float* o = out + (long long)row * ldo;
+    int col = 0;
+    for (int seg = 0; seg < 2; ++seg) {
+        const float* f = seg == 0 ? f0 : f1;
+        const int d = seg == 0 ? d0 : d1;
+        if (!f) continue;
+        const float* src = f + (long long)row * d;
+        float ss = 0.f;
+        for (int e = lane; e < d; e += 32) { const float v = src[e]; ss = fmaf(v, v, ss); }
+        const float denom = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);     // F.normalize: x / max(||x||, eps)
+        for (int e = lane; e < d; e += 32) o[col + e] = src[e] / denom;
+        col += d;
+    }
+    for (int seg = 0; seg < 2; ++seg) {
+        const long long* idp = seg == 0 ? id0 : id1;
+        const float* tab = seg == 0 ? tab0 : tab1;
+        if (!idp) continue;
+        const float* src = tab + idp[row] * id_dim;
+        for (int e = lane; e < id_dim; e += 32) o[col + e] = src[e];
+        col += id_dim;
+    }
+    for (int e = col + lane; e < k_pad; e += 32) o[e] = 0.f;
+}
+
+// ------------------------------------------------------------------------------- (residual +) LayerNorm
+template <typename TX, typename TR>
+__global__ void __launch_bounds__(NE_THREADS)
+add_ln_kernel(const TX* __restrict__ x, long long ldx, const TR* __restrict__ res, long long ldr,
+              const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int rows, int H,
+              const float* __restrict__ tanh_base, long long ld_base, float* __restrict__ out32, long long ldo32,
+              __nv_bfloat16* __restrict__ out16, long long ldo16, RowMap map) {
+    const int row = blockIdx.x * (NE_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nv = H / 128;
+    float4 v[NE_MAXV];
+#pragma unroll
+    for (int i = 0; i < NE_MAXV; ++i)
+        if (i < nv) {
+            const int e = (i * 32 + lane) * 4;
+            v[i] = load4<TX>(x + (long long)row * ldx + e);
+            if (res) {
+                const float4 r = load4<TR>(res + (long long)row * ldr + e);
+                v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+            }
+        }
+    warp_layernorm(v, nv, H, gamma, beta, eps, lane);
+    const long long orow = map(row);
+#pragma unroll
+    for (int i = 0; i < NE_MAXV; ++i)
+        if (i < nv) {
+            const int e = (i * 32 + lane) * 4;
+            if (tanh_base) {
+                const float4 b = *reinterpret_cast<const float4*>(tanh_base + orow * ld_base + e);
+                v[i].x = b.x + tanhf(v[i].x); v[i].y = b.y + tanhf(v[i].y);
+                v[i].z = b.z + tanhf(v[i].z); v[i].w = b.w + tanhf(v[i].w);
+            }
+            if (out32) *reinterpret_cast<float4*>(out32 + orow * ldo32 + e) = v[i];
+            if (out16) store4_bf16(out16 + orow * ldo16 + e, v[i]);
+        }
+}
+
+// ------------------------------------------------------------------------------- OCR: LN(h) + LN(W2.bbox + b2)
+__global__ void __launch_bounds__(NE_THREADS)
+ocr_finish_kernel(const float* __restrict__ h, long long ldh, const float* __restrict__ bbox,
+                  const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ g1,
+                  const float* __restrict__ be1, const float* __restrict__ g2, const float* __restrict__ be2,
+                  float eps, int rows, int H, float* __restrict__ out, long long ldo, RowMap map) {
+    const int row = blockIdx.x * (NE_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nv = H / 128;
+    const float4 bx = *reinterpret_cast<const float4*>(bbox + (long long)row * 4);
+    float4 a[NE_MAXV], c[NE_MAXV];
+#pragma unroll
+    for (int i = 0; i < NE_MAXV; ++i)
+        if (i < nv) {
+            const int e = (i * 32 + lane) * 4;
+            a[i] = *reinterpret_cast<const float4*>(h + (long long)row * ldh + e);
+            float r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(w2 + (long long)(e + j) * 4));
+                // same association order as a K=4 dot product accumulated left to right, then + bias
+                r[j] = fmaf(bx.w, w.w, fmaf(bx.z, w.z, fmaf(bx.y, w.y, bx.x * w.x))) + __ldg(b2 + e + j);
+            }
+            c[i] = make_float4(r[0], r[1], r[2], r[3]);
+        }
+    warp_layernorm(a, nv, H, g1, be1, eps, lane);
+    warp_layernorm(c, nv, H, g2, be2, eps, lane);
+    const long long orow = map(row);
+#pragma unroll
+    for (int i = 0; i < NE_MAXV; ++i)
+        if (i < nv) {
+            const int e = (i * 32 + lane) * 4;
+            *reinterpret_cast<float4*>(out + orow * ldo + e) =
+                make_float4(a[i].x + c[i].x, a[i].y + c[i].y, a[i].z + c[i].z, a[i].w + c[i].w);
+        }
+}
+
+// ------------------------------------------------------------------------------- PrevPredEmbeddings
+// dec[b, t] = LN_ans(Wcls[idx]) or LN_ocr(ocr_emb[b, idx - V])  +  LN_emb(pos[t] + type[idx >= V])
+__global__ void __launch_bounds__(NE_THREADS)
+prev_embed_kernel(const long long* __restrict__ prev_inds, int ld_prev, int B, int t0, int nt, int V, int H,
+                  const float* __restrict__ ans_w, const float* __restrict__ ocr_emb, long long ocr_batch_stride,
+                  long long ld_ocr, const float* __restrict__ pos_emb, const float* __restrict__ type_emb,
+                  const float* __restrict__ ans_g, const float* __restrict__ ans_b, const float* __restrict__ ocr_g,
+                  const float* __restrict__ ocr_b, const float* __restrict__ emb_g, const float* __restrict__ emb_b,
+                  float eps, __nv_bfloat16* __restrict__ out16, float* __restrict__ out32, long long ldo, int T) {
+    const int w = blockIdx.x * (NE_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= B * nt) return;
+    const int b = w / nt, t = t0 + w % nt;
+    const int nv = H / 128;
+    const long long idx = prev_inds[(long long)b * ld_prev + t];
+    const bool is_ocr = idx >= V;
+    const float* src = is_ocr ? ocr_emb + (long long)b * ocr_batch_stride + (idx - V) * ld_ocr : ans_w + idx * H;
+    const float* ty = type_emb + (is_ocr ? H : 0);
+    float4 r[NE_MAXV], e[NE_MAXV];
+#pragma unroll
+    for (int i = 0; i < NE_MAXV; ++i)
+        if (i < nv) {
+            const int c = (i * 32 + lane) * 4;
+            r[i] = *reinterpret_cast<const float4*>(src + c);
+            const float4 p = *reinterpret_cast<const float4*>(pos_emb + (long long)t * H + c);
+            const float4 q = *reinterpret_cast<const float4*>(ty + c);
+            e[i] = make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w);
+        }
+    warp_layernorm(r, nv, H, is_ocr ? ocr_g : ans_g, is_ocr ? ocr_b : ans_b, eps, lane);
+    warp_layernorm(e, nv, H, emb_g, emb_b, eps, lane);
+    const long long orow = (long long)b * T + t;
+#pragma unroll
+    for (int i = 0; i < NE_MAXV; ++i)
+        if (i < nv) {
+            const int c = (i * 32 + lane) * 4;
+            const float4 v = make_float4(r[i].x + e[i].x, r[i].y + e[i].y, r[i].z + e[i].z, r[i].w + e[i].w);
+            if (out16) store4_bf16(out16 + orow * ldo + c, v);
+            if (out32) *reinterpret_cast<float4*>(out32 + orow * ldo + c) = v;
+        }
+}
+
+// ------------------------------------------------------------------------------- fp32 -> bf16 rows
+__global__ void cast_rows_bf16_kernel(const float* __restrict__ x, long long ldx, int rows, int H,
+                                      __nv_bfloat16* __restrict__ out, long long ldo, RowMap map) {
+    const long long n4 = (long long)rows * (H / 4);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / (H / 4)), c = (int)(i % (H / 4)) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + (long long)row * ldx + c);
+        store4_bf16(out + map(row) * ldo + c, v);
+    }
+}
+
+static inline int rows_grid(int rows) { return (rows + NE_THREADS / 32 - 1) / (NE_THREADS / 32); }
+static inline bool h_ok(int H) { return H % 128 == 0 && H / 128 <= NE_MAXV && H > 0; }
+
+}  // namespace t2s
+
+using namespace t2s;
+
+extern "C" int t2s_bert_embed_ln(const long long* ids, int rows, int L, int H, const float* word, const float* pos,
+                                 const float* type0, const float* gamma, const float* beta, float eps, float* out,
+                                 long long ldo, void* stream) {
+    if (!h_ok(H) || rows <= 0) { set_error("bert_embed_ln: H %d must be a multiple of 128 <= 1024", H); return T2S_ERR_SHAPE; }
+    bert_embed_ln_kernel<<<rows_grid(rows), NE_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        ids, rows, L, H, word, pos, type0, gamma, beta, eps, out, ldo);
+    return launch_status("bert_embed_ln");
+}
+
+extern "C" int t2s_feat_concat(const float* f0, int d0, const float* f1, int d1, const long long* id0, const float* tab0,
+                               const long long* id1, const float* tab1, int id_dim, int rows, float* out, long long ldo,
+                               int k_pad, void* stream) {
+    const int k = (f0 ? d0 : 0) + (f1 ? d1 : 0) + (id0 ? id_dim : 0) + (id1 ? id_dim : 0);
+    if (rows <= 0 || k > k_pad || k_pad > ldo) { set_error("feat_concat: bad widths k %d k_pad %d ldo %lld", k, k_pad, ldo); return T2S_ERR_SHAPE; }
+    feat_concat_kernel<<<rows_grid(rows), NE_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        f0, d0, f1, d1, id0, tab0, id1, tab1, id_dim, rows, out, ldo, k_pad);
+    return launch_status("feat_concat");
+}
+
+extern "C" int t2s_add_ln(const void* x, int x_bf16, long long ldx, const void* res, int res_bf16, long long ldr,
+                          const float* gamma, const float* beta, float eps, int rows, int H, const float* tanh_base,
+                          long long ld_base, float* out32, long long ldo32, void* out16, long long ldo16,
+                          int rows_per_group, int out_group_rows, int out_row_off, void* stream) {
+    if (!h_ok(H) || rows <= 0) { set_error("add_ln: H %d must be a multiple of 128 <= 1024", H); return T2S_ERR_SHAPE; }
+    if (!out32 && !out16) { set_error("add_ln: no output"); return T2S_ERR_ARG; }
+    RowMap map{rows_per_group, out_group_rows, out_row_off};
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = rows_grid(rows);
+    __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(out16);
+#define T2S_LN_LAUNCH(TX, TR)                                                                                     \
+    add_ln_kernel<TX, TR><<<grid, NE_THREADS, 0, st>>>(reinterpret_cast<const TX*>(x), ldx,                       \
+                                                       reinterpret_cast<const TR*>(res), ldr, gamma, beta, eps,   \
+                                                       rows, H, tanh_base, ld_base, out32, ldo32, o16, ldo16, map)
+    if (x_bf16) {
+        if (res_bf16 || !res) T2S_LN_LAUNCH(__nv_bfloat16, __nv_bfloat16);
+        else T2S_LN_LAUNCH(__nv_bfloat16, float);
+    } else {
+        if (res_bf16 && res) T2S_LN_LAUNCH(float, __nv_bfloat16);
+        else T2S_LN_LAUNCH(float, float);
+    }
+#undef T2S_LN_LAUNCH
+    return launch_status("add_ln");
+}
+
+extern "C" int t2s_ocr_finish(const float* h, long long ldh, const float* bbox, const float* w2, const float* b2,
+                              const float* g1, const float* be1, const float* g2, const float* be2, float eps, int rows,
+                              int H, float* out, long long ldo, int rows_per_group, int out_group_rows, int out_row_off,
+                              void* stream) {
+    if (!h_ok(H) || rows <= 0) { set_error("ocr_finish: H %d must be a multiple of 128 <= 1024", H); return T2S_ERR_SHAPE; }
+    RowMap map{rows_per_group, out_group_rows, out_row_off};
+    ocr_finish_kernel<<<rows_grid(rows), NE_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        h, ldh, bbox, w2, b2, g1, be1, g2, be2, eps, rows, H, out, ldo, map);
+    return launch_status("ocr_finish");
+}
+
+extern "C" int t2s_prev_embed(const long long* prev_inds, int ld_prev, int B, int t0, int nt, int T, int V, int H,
+                              const float* ans_w, const float* ocr_emb, long long ocr_batch_stride, long long ld_ocr,
+                              const float* pos_emb, const float* type_emb, const float* ans_g, const float* ans_b,
+                              const float* ocr_g, const float* ocr_b, const float* emb_g, const float* emb_b, float eps,
+                              void* out16, float* out32, long long ldo, void* stream) {
+    if (!h_ok(H) || B <= 0 || nt <= 0 || t0 < 0 || t0 + nt > T) { set_error("prev_embed: bad arguments"); return T2S_ERR_SHAPE; }
+    prev_embed_kernel<<<rows_grid(B * nt), NE_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        prev_inds, ld_prev, B, t0, nt, V, H, ans_w, ocr_emb, ocr_batch_stride, ld_ocr, pos_emb, type_emb, ans_g, ans_b,
+        ocr_g, ocr_b, emb_g, emb_b, eps, reinterpret_cast<__nv_bfloat16*>(out16), out32, ldo, T);
+    return launch_status("prev_embed");
+}
+
+extern "C" int t2s_cast_rows_bf16(const float* x, long long ldx, int rows, int H, void* out, long long ldo,
+                                  int rows_per_group, int out_group_rows, int out_row_off, void* stream) {
+    if (H % 4 || rows <= 0) { set_error("cast_rows_bf16: H %% 4"); return T2S_ERR_SHAPE; }
+    RowMap map{rows_per_group, out_group_rows, out_row_off};
+    const long long n4 = (long long)rows * (H / 4);
+    int grid = (int)((n4 + 255) / 256);
+    if (grid > num_sms() * 16) grid = num_sms() * 16;
+    cast_rows_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, ldx, rows, H, reinterpret_cast<__nv_bfloat16*>(out), ldo, map);
+    return launch_status("cast_rows_bf16");
+}

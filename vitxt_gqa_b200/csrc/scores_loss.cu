@@ -1,0 +1,218 @@
+// K6 / K7: pointer-network scores, greedy argmax feedback, and the two training losses.
+//
+// Reference call sites replaced:
+//   OcrPtrNet.forward matmul / sqrt(768) / + raw 0/1 mask   pythia/models/t2s.py:661-666 (Q1)
+//   torch.cat([fixed_scores, dynamic_ocr_scores])            t2s.py:285 -- both heads write into one
+//                                                            [B, T, V+O] fp32 buffer, no concat
+//   pos_scores.argmax(-1) -> prev_inds[:, 1:]                t2s.py:353-354
+//   POSBCEWithMaskLoss.forward                               pythia/modules/losses.py:329-343
+//   InfoNCE.forward                                          losses.py:361-385
+#include "common.cuh"
+#include "../../include/t2s_b200.h"
+
+namespace t2s {
+
+// scores[b, t0+i, V+o] = (q[b,t0+i] . keyp[b,o]) / sqrt(H) + mask[b,o]
+constexpr int PS_THREADS = 256, PS_ROWS = 64, PS_MAXQ = 16;
+
+__global__ void __launch_bounds__(PS_THREADS)
+ptr_score_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, int T, int t0, int nq,
+                 const __nv_bfloat16* __restrict__ keyp, long long key_batch_stride, long long ldk, int O, int H,
+                 const float* __restrict__ mask, long long mask_stride, float* __restrict__ scores, long long ld_scores,
+                 int V, float denom) {
+    extern __shared__ float qs[];     // [nq][H]
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < nq * H; i += PS_THREADS) {
+        const int r = i / H, d = i % H;
+        qs[i] = __bfloat162float(q[((long long)b * T + t0 + r) * ldq + d]);
+    }
+    __syncthreads();
+    const int o_end = min(O, (int)(blockIdx.x + 1) * PS_ROWS);
+    for (int o = blockIdx.x * PS_ROWS + warp; o < o_end; o += PS_THREADS / 32) {
+        const __nv_bfloat16* kp = keyp + (long long)b * key_batch_stride + (long long)o * ldk;
+        float acc[PS_MAXQ];
+#pragma unroll
+        for (int r = 0; r < PS_MAXQ; ++r) acc[r] = 0.f;
+        for (int d = lane * 8; d < H; d += 256) {
+            const uint4 kv = *reinterpret_cast<const uint4*>(kp + d);
+            const float kf[8] = {bf16lo(kv.x), bf16hi(kv.x), bf16lo(kv.y), bf16hi(kv.y),
+                                 bf16lo(kv.z), bf16hi(kv.z), bf16lo(kv.w), bf16hi(kv.w)};
+#pragma unroll
+            for (int r = 0; r < PS_MAXQ; ++r)
+                if (r < nq) {
+                    const float4 q0 = *reinterpret_cast<const float4*>(qs + r * H + d);
+                    const float4 q1 = *reinterpret_cast<const float4*>(qs + r * H + d + 4);
+                    acc[r] = fmaf(q0.x, kf[0], acc[r]); acc[r] = fmaf(q0.y, kf[1], acc[r]);
+                    acc[r] = fmaf(q0.z, kf[2], acc[r]); acc[r] = fmaf(q0.w, kf[3], acc[r]);
+                    acc[r] = fmaf(q1.x, kf[4], acc[r]); acc[r] = fmaf(q1.y, kf[5], acc[r]);
+                    acc[r] = fmaf(q1.z, kf[6], acc[r]); acc[r] = fmaf(q1.w, kf[7], acc[r]);
+                }
+        }
+        const float m = mask[(long long)b * mask_stride + o];
+#pragma unroll
+        for (int r = 0; r < PS_MAXQ; ++r)
+            if (r < nq) {
+                const float s = warp_sum(acc[r]);
+                if (lane == 0) scores[((long long)b * T + t0 + r) * ld_scores + V + o] = s / denom + m;
+            }
+    }
+}
+
+// argmax over a row of N fp32 scores (first maximum wins); writes prev_inds[b, t+1] when t+1 < T
+__global__ void __launch_bounds__(256)
+argmax_feedback_kernel(const float* __restrict__ scores, long long ld_scores, int T, int t0, int nt, int N,
+                       long long* __restrict__ prev_inds, int ld_prev, long long* __restrict__ argmax_out) {
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    const int w = blockIdx.x, b = w / nt, t = t0 + w % nt;
+    const float* row = scores + ((long long)b * T + t) * ld_scores;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float v = row[i];
+        if (v > best) { best = v; bi = i; }      // strided ascending: first max per thread is kept
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
+            if (sv[k] > best || (sv[k] == best && si[k] < bi)) { best = sv[k]; bi = si[k]; }
+        if (argmax_out) argmax_out[(long long)b * T + t] = bi;
+        if (prev_inds && t + 1 < T) prev_inds[(long long)b * ld_prev + t + 1] = bi;
+    }
+}
+
+// ------------------------------------------------------------------------------- masked BCE-with-logits
+__global__ void __launch_bounds__(256)
+bce_partial_kernel(const float* __restrict__ scores, const float* __restrict__ targets, const float* __restrict__ loss_mask,
+                   long long rows, int N, double* __restrict__ partial) {
+    __shared__ float red[33];
+    double acc = 0.0;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const float m = loss_mask[r];
+        if (m == 0.f) continue;                       // uniform per block: whole CTA skips the row
+        const float* x = scores + r * N;
+        const float* z = targets + r * N;
+        float s = 0.f;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const float xv = x[i], zv = z[i];
+            // (1 - z) * x - log_sigmoid(x),  log_sigmoid(x) = min(x, 0) - log1p(exp(-|x|))
+            s += ((1.f - zv) * xv - (fminf(xv, 0.f) - log1pf(expf(-fabsf(xv))))) * m;
+        }
+        s = block_sum(s, red);
+        acc += (double)s;
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void bce_final_kernel(const double* __restrict__ partial, int n, const float* __restrict__ loss_mask,
+                                 long long rows, float* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += partial[i];
+        float c = 0.f;
+        for (long long r = 0; r < rows; ++r) c += loss_mask[r];
+        out[0] = (float)(s / (double)fmaxf(c, 1.f));
+    }
+}
+
+// ------------------------------------------------------------------------------- InfoNCE (per-sample 2-way)
+// stats[row] = { |ref|^2, |pos|^2, |neg|^2, ref.pos, ref.neg } for row = (b, t)
+__global__ void __launch_bounds__(256)
+nce_rowstats_kernel(const float* __restrict__ ref, const float* __restrict__ pos, const float* __restrict__ neg, int N,
+                    float* __restrict__ stats) {
+    __shared__ float red[33];
+    const long long r = blockIdx.x;
+    const float* a = ref + r * N;
+    const float* p = pos + r * N;
+    const float* n = neg + r * N;
+    float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float av = a[i], pv = p[i], nv = n[i];
+        s[0] = fmaf(av, av, s[0]); s[1] = fmaf(pv, pv, s[1]); s[2] = fmaf(nv, nv, s[2]);
+        s[3] = fmaf(av, pv, s[3]); s[4] = fmaf(av, nv, s[4]);
+    }
+    for (int k = 0; k < 5; ++k) {
+        const float v = block_sum(s[k], red);
+        if (threadIdx.x == 0) stats[r * 5 + k] = v;
+    }
+}
+__global__ void nce_final_kernel(const float* __restrict__ stats, int B, int T, float temperature, float* __restrict__ out) {
+    __shared__ float red[33];
+    float acc = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float qq = 0.f, pp = 0.f, nn = 0.f, qp = 0.f, qn = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float* s = stats + ((long long)b * T + t) * 5;
+            const float nr = fmaxf(sqrtf(s[0]), 1e-12f), np = fmaxf(sqrtf(s[1]), 1e-12f), ng = fmaxf(sqrtf(s[2]), 1e-12f);
+            qq += s[0] / (nr * nr); pp += s[1] / (np * np); nn += s[2] / (ng * ng);
+            qp += s[3] / (nr * np); qn += s[4] / (nr * ng);
+        }
+        const float cp = qp / (fmaxf(sqrtf(qq), 1e-8f) * fmaxf(sqrtf(pp), 1e-8f));
+        const float cn = qn / (fmaxf(sqrtf(qq), 1e-8f) * fmaxf(sqrtf(nn), 1e-8f));
+        const float lp = cp / temperature, ln = cn / temperature;
+        const float mx = fmaxf(lp, ln);
+        acc += (mx + logf(expf(lp - mx) + expf(ln - mx))) - lp;     // -log_softmax(logits)[0]
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[0] = acc / (float)B;
+}
+
+}  // namespace t2s
+
+using namespace t2s;
+
+extern "C" int t2s_ptr_score(const void* q, long long ldq, int B, int T, int t0, int nq, const void* keyp,
+                             long long key_batch_stride, long long ldk, int O, int H, const float* mask,
+                             long long mask_stride, float* scores, long long ld_scores, int V, void* stream) {
+    if (nq < 1 || nq > PS_MAXQ || (H % 256) || (ldk % 8) || t0 < 0 || t0 + nq > T) { set_error("ptr_score: bad arguments"); return T2S_ERR_SHAPE; }
+    const size_t smem = (size_t)nq * H * sizeof(float);
+    static size_t attr = 48 * 1024;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(ptr_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("ptr_score attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr = smem;
+    }
+    dim3 grid((O + PS_ROWS - 1) / PS_ROWS, B);
+    ptr_score_kernel<<<grid, PS_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(q), ldq, T, t0, nq, reinterpret_cast<const __nv_bfloat16*>(keyp),
+        key_batch_stride, ldk, O, H, mask, mask_stride, scores, ld_scores, V, sqrtf((float)H));
+    return launch_status("ptr_score");
+}
+
+extern "C" int t2s_argmax_feedback(const float* scores, long long ld_scores, int B, int T, int t0, int nt, int N,
+                                   long long* prev_inds, int ld_prev, long long* argmax_out, void* stream) {
+    if (B <= 0 || nt <= 0 || t0 < 0 || t0 + nt > T) { set_error("argmax_feedback: bad arguments"); return T2S_ERR_SHAPE; }
+    argmax_feedback_kernel<<<B * nt, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(scores, ld_scores, T, t0, nt, N, prev_inds, ld_prev, argmax_out);
+    return launch_status("argmax_feedback");
+}
+
+extern "C" long long t2s_loss_workspace_bytes(int B, int T) {
+    return (long long)(1024 * sizeof(double)) + (long long)B * T * 5 * sizeof(float);
+}
+
+extern "C" int t2s_pos_bce_loss(const float* scores, const float* targets, const float* loss_mask, int B, int T, int N,
+                                void* workspace, float* out, void* stream) {
+    if (B <= 0 || T <= 0 || N <= 0) { set_error("pos_bce_loss: bad shape"); return T2S_ERR_SHAPE; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long rows = (long long)B * T;
+    const int grid = (int)(rows < 1024 ? rows : 1024);
+    bce_partial_kernel<<<grid, 256, 0, st>>>(scores, targets, loss_mask, rows, N, reinterpret_cast<double*>(workspace));
+    bce_final_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const double*>(workspace), grid, loss_mask, rows, out);
+    return launch_status("pos_bce_loss");
+}
+
+extern "C" int t2s_info_nce_loss(const float* ref, const float* pos, const float* neg, int B, int T, int N,
+                                 float temperature, void* workspace, float* out, void* stream) {
+    if (B <= 0 || T <= 0 || N <= 0) { set_error("info_nce_loss: bad shape"); return T2S_ERR_SHAPE; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    float* stats = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 1024 * sizeof(double));
+    nce_rowstats_kernel<<<B * T, 256, 0, st>>>(ref, pos, neg, N, stats);
+    nce_final_kernel<<<1, 256, 0, st>>>(stats, B, T, temperature, out);
+    return launch_status("info_nce_loss");
+}

@@ -1,0 +1,102 @@
+"""ctypes binding of libt2s_sm100.so (include/t2s_b200.h).
+
+The shared library is the product; this module only loads it, declares the
+argument types and turns non-zero return codes into exceptions.  There is no
+fallback: if the library is missing or fails to load, importing callers get a
+RuntimeError that says how to build it.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libt2s_sm100.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+GEMM_GELU, GEMM_OUT_F32, GEMM_RES_F32 = 1, 2, 4
+
+_p, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+
+# name -> argtypes, in the order of include/t2s_b200.h
+SIGNATURES = {
+    "t2s_gemm_bf16": [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p],
+    "t2s_gemm_f32": [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p],
+    "t2s_attn_f32": [_p, _ll, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _p],
+    "t2s_attn_bf16": [_p, _ll, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _p],
+    "t2s_attn_dec": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _ll, _p],
+    "t2s_bert_embed_ln": [_p, _i, _i, _i, _p, _p, _p, _p, _p, _f, _p, _ll, _p],
+    "t2s_feat_concat": [_p, _i, _p, _i, _p, _p, _p, _p, _i, _i, _p, _ll, _i, _p],
+    "t2s_add_ln": [_p, _i, _ll, _p, _i, _ll, _p, _p, _f, _i, _i, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p],
+    "t2s_ocr_finish": [_p, _ll, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _p, _ll, _i, _i, _i, _p],
+    "t2s_prev_embed": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _ll, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _f,
+                       _p, _p, _ll, _p],
+    "t2s_cast_rows_bf16": [_p, _ll, _i, _i, _p, _ll, _i, _i, _i, _p],
+    "t2s_mask_prep": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+    "t2s_build_keys": [_p, _i, _i, _p, _p, _i, _p],
+    "t2s_question_pool": [_p, _i, _i, _i, _p, _p, _p, _i, _p, _p],
+    "t2s_sim_scores": [_p, _p, _ll, _ll, _i, _i, _i, _i, _p, _p],
+    "t2s_temporal_select": [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p],
+    "t2s_spatial_select": [_p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p],
+    "t2s_middle_frame_slots": [_p, _p, _i, _i, _p, _p],
+    "t2s_ptr_score": [_p, _ll, _i, _i, _i, _i, _p, _ll, _ll, _i, _i, _p, _ll, _p, _ll, _i, _p],
+    "t2s_argmax_feedback": [_p, _ll, _i, _i, _i, _i, _i, _p, _i, _p, _p],
+    "t2s_pos_bce_loss": [_p, _p, _p, _i, _i, _i, _p, _p, _p],
+    "t2s_info_nce_loss": [_p, _p, _p, _i, _i, _i, _f, _p, _p, _p],
+}
+PLAIN = {"t2s_abi_version": (_i, []), "t2s_last_error": (ctypes.c_char_p, []),
+         "t2s_loss_workspace_bytes": (_ll, [_i, _i])}
+
+EXPORTED_SYMBOLS = sorted(list(SIGNATURES) + list(PLAIN))
+
+
+class T2SLibraryError(RuntimeError):
+    pass
+
+
+def build_library(verbose=False):
+    """Compile csrc/*.cu for sm_100a into libt2s_sm100.so (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise T2SLibraryError("building libt2s_sm100.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    if verbose:
+        print(r.stdout[-2000:])
+    return LIB_PATH
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise T2SLibraryError(
+                "libt2s_sm100.so not found at %s -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C vitxt_gqa_b200/csrc`. There is no CPU or PyTorch fallback for this path." % LIB_PATH)
+        self.cdll = ctypes.CDLL(LIB_PATH)
+        self.launches = 0
+        for name, (res, args) in PLAIN.items():
+            fn = getattr(self.cdll, name)
+            fn.restype, fn.argtypes = res, args
+            setattr(self, name[4:], fn)
+        if self.cdll.t2s_abi_version() != 1:
+            raise T2SLibraryError("libt2s_sm100.so ABI version mismatch")
+        for name, args in SIGNATURES.items():
+            fn = getattr(self.cdll, name)
+            fn.restype, fn.argtypes = _i, args
+            setattr(self, name[4:], self._checked(name, fn))
+
+    def _checked(self, name, fn):
+        def call(*args):
+            rc = fn(*args)
+            if rc != 0:
+                raise T2SLibraryError("%s failed (rc=%d): %s" % (name, rc, self.cdll.t2s_last_error().decode()))
+            self.launches += 1
+        call.__name__ = name
+        return call
+
+
+_LIB = None
+
+
+def get_lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = _Lib()
+    return _LIB

@@ -1,0 +1,724 @@
+"""Registered models `t2s` and `m4c`: the reference's model API in front of libt2s_sm100.
+
+Drop-in for reference pythia/models/t2s.py (`T2S`) and pythia/models/m4c.py (`M4C`):
+same registry keys, same constructor / build() / forward(sample_list) contract,
+same result-dict keys, same `state_dict` names and shapes, same
+`get_optimizer_parameters`.  The module tree below only HOLDS the parameters
+(nn.Linear / nn.Embedding / nn.LayerNorm objects under the reference's attribute
+names); `forward` never calls them -- it enqueues the kernel schedule of
+DESIGN.md on the current CUDA stream through the C ABI.  PyTorch supplies device
+memory, the stream and (elsewhere) torch.distributed; there is no PyTorch or CPU
+compute fallback: without the CUDA library, or with CPU inputs and no GPU, the
+model raises.
+
+Schedule (eval): fp32 grounding chain (TextBert -> obj/OCR encoders -> QTV ->
+grounding) -> bf16 answer transformer with the reference's 36 full passes
+collapsed to the arithmetic they actually need: per variant (ref/pos/neg) one
+encoder pass over the 1044 encoder rows whose K/V are kept, the `pos` variant
+decoded greedily one decoder row at a time, then `ref` and `neg` decoder rows in
+one 12-row pass with the final prev_inds (encoder rows never see decoder rows and
+decoder rows are causal: reference t2s.py:574-579,609-615).
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import lib as _lib
+from . import losses as _losses  # noqa: F401  (registers pos_bce_loss / InfoNCE)
+from .pythia_api import BaseModel, registry
+
+LN_EPS_BERT = 1e-12    # config.layer_norm_eps of BertConfig (BERT-internal + PrevPred LayerNorms)
+LN_EPS_EMBED = 1e-5    # BertLayerNorm(hidden) class default == nn.LayerNorm default
+
+
+# =============================================================================== parameter holders
+class _SelfAttn(nn.Module):
+    def __init__(self, h):
+        super().__init__()
+        self.query, self.key, self.value = nn.Linear(h, h), nn.Linear(h, h), nn.Linear(h, h)
+
+
+class _DenseLN(nn.Module):
+    def __init__(self, i, o):
+        super().__init__()
+        self.dense = nn.Linear(i, o)
+        self.LayerNorm = nn.LayerNorm(o, eps=LN_EPS_BERT)
+
+
+class _Attention(nn.Module):
+    def __init__(self, h):
+        super().__init__()
+        self.self = _SelfAttn(h)
+        self.output = _DenseLN(h, h)
+
+
+class _Intermediate(nn.Module):
+    def __init__(self, h, i):
+        super().__init__()
+        self.dense = nn.Linear(h, i)
+
+
+class _BertLayer(nn.Module):
+    def __init__(self, h, i):
+        super().__init__()
+        self.attention = _Attention(h)
+        self.intermediate = _Intermediate(h, i)
+        self.output = _DenseLN(i, h)
+
+
+class _BertEncoder(nn.Module):
+    def __init__(self, h, n_layers):
+        super().__init__()
+        self.layer = nn.ModuleList([_BertLayer(h, 4 * h) for _ in range(n_layers)])
+
+
+class _BertEmbeddings(nn.Module):
+    def __init__(self, h, vocab=30522):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(vocab, h, padding_idx=0)
+        self.position_embeddings = nn.Embedding(512, h)
+        self.token_type_embeddings = nn.Embedding(2, h)
+        self.LayerNorm = nn.LayerNorm(h, eps=LN_EPS_BERT)
+
+
+def _bert_init(module, std=0.02):
+    """BertPreTrainedModel.init_weights (pytorch_transformers 1.2.0)."""
+    for m in module.modules():
+        if isinstance(m, (nn.Linear, nn.Embedding)):
+            m.weight.data.normal_(mean=0.0, std=std)
+        elif isinstance(m, nn.LayerNorm):
+            m.bias.data.zero_()
+            m.weight.data.fill_(1.0)
+        if isinstance(m, nn.Linear) and m.bias is not None:
+            m.bias.data.zero_()
+
+
+class TextBert(nn.Module):       # reference t2s.py:521-527
+    def __init__(self, h, n_layers):
+        super().__init__()
+        self.embeddings = _BertEmbeddings(h)
+        self.encoder = _BertEncoder(h, n_layers)
+        _bert_init(self)
+
+
+class QTV(nn.Module):            # reference t2s.py:378-382
+    def __init__(self, h, n_layers):
+        super().__init__()
+        self.encoder = _BertEncoder(h, n_layers)
+        _bert_init(self)
+
+
+class _AttentionScore(nn.Module):    # reference stg.py:6-13 (linear_q / linear_k are never applied, Q5)
+    def __init__(self, h):
+        super().__init__()
+        self.linear_q, self.linear_k = nn.Linear(h, h), nn.Linear(h, h)
+
+
+class _TemporalIndicator(nn.Module):
+    def __init__(self, h):
+        super().__init__()
+        self.frame_pos_att, self.frame_neg_att = _AttentionScore(h), _AttentionScore(h)
+
+
+class _SpatialIndicator(nn.Module):
+    def __init__(self, h):
+        super().__init__()
+        self.ocr_pos_att, self.ocr_neg_att = _AttentionScore(h), _AttentionScore(h)
+
+
+class GroundingModule(nn.Module):    # reference t2s.py:434-451 (frame_attn / encoder are dead weights, Q18)
+    def __init__(self, h, n_enc_layers):
+        super().__init__()
+        self.q_linear = nn.Linear(h, h)
+        self.frame_attn = nn.Linear(2 * h, 1)
+        self.self_attn = nn.Linear(h, 1)
+        self.frame_grounding_indicator = _TemporalIndicator(h)
+        self.ocr_grounding_indicator = _SpatialIndicator(h)
+        self.encoder = _BertEncoder(h, n_enc_layers)
+
+
+class PostHocAttention(nn.Module):   # reference m4c.py:334-346
+    def __init__(self, h):
+        super().__init__()
+        self.q_linear = nn.Linear(h, h)
+        self.self_attn = nn.Linear(h, 1)
+        self.ocr_att = _AttentionScore(h)
+
+
+class _PrevPredEmbeddings(nn.Module):    # reference t2s.py:673-688
+    def __init__(self, h):
+        super().__init__()
+        self.position_embeddings = nn.Embedding(100, h)
+        self.token_type_embeddings = nn.Embedding(5, h)
+        self.ans_layer_norm = nn.LayerNorm(h, eps=LN_EPS_BERT)
+        self.ocr_layer_norm = nn.LayerNorm(h, eps=LN_EPS_BERT)
+        self.emb_layer_norm = nn.LayerNorm(h, eps=LN_EPS_BERT)
+
+
+class MMT(nn.Module):            # reference t2s.py:548-554
+    def __init__(self, h, n_layers):
+        super().__init__()
+        self.prev_pred_embeddings = _PrevPredEmbeddings(h)
+        self.encoder = _BertEncoder(h, n_layers)
+        _bert_init(self)
+
+
+class OcrPtrNet(nn.Module):      # reference t2s.py:636-646
+    def __init__(self, hidden_size, query_key_size=None):
+        super().__init__()
+        query_key_size = hidden_size if query_key_size is None else query_key_size
+        self.query = nn.Linear(hidden_size, query_key_size)
+        self.key = nn.Linear(hidden_size, query_key_size)
+
+
+class ClassifierLayer(nn.Module):    # reference modules/layers.py:91-107, "linear" only
+    def __init__(self, classifier_type, in_dim, out_dim, **kwargs):
+        super().__init__()
+        if classifier_type != "linear":
+            raise NotImplementedError("Unknown classifier type: %s" % classifier_type)
+        self.module = nn.Linear(in_dim, out_dim)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+# =============================================================================== shared engine
+class _FusionModelBase(BaseModel):
+    """Everything T2S and M4C share: construction, weight packing, the kernel schedule."""
+
+    MODEL = "t2s"
+
+    def __init__(self, config):
+        super().__init__(config)
+        self._datasets = registry.get("config").datasets.split(",")
+        self.hidden = int(self.config.mmt.hidden_size)
+        self._packed = None
+        self._packed_key = None
+        self._ws = {}
+        self.parity_hooks = {}     # test-only overrides, e.g. {"neg_frame_topk": tensor [B,F]}
+        self.last_debug = {}
+
+    # ---------------------------------------------------------------- build (reference t2s.py:31-151)
+    def build(self):
+        cfg, h = self.config, self.hidden
+        if h != 768:
+            raise NotImplementedError("the B200 path is built for hidden_size 768 (12 heads x 64)")
+        self.finetune_modules = []
+        self.text_bert = TextBert(h, int(cfg.text_bert.num_hidden_layers))
+        if cfg.text_bert_init_from_bert_base:
+            self._load_bert_base()
+            self.finetune_modules.append({"module": self.text_bert, "lr_scale": cfg.lr_scale_text_bert})
+        else:
+            self.writer.write("NOT initializing text_bert from BERT_BASE")
+        self.text_bert_out_linear = nn.Identity()
+        self.frame_embeddings = nn.Embedding(4000, 50)
+        self.linear_obj_feat_to_mmt_in = nn.Linear(int(cfg.obj.mmt_in_dim), h)
+        self.obj_feat_layer_norm = nn.LayerNorm(h, eps=LN_EPS_EMBED)
+        self.obj_frame_layer_norm = nn.LayerNorm(h, eps=LN_EPS_EMBED)
+        self.linear_obj_frame_to_mmt_in = nn.Linear(50, h)
+        self.linear_ocr_feat_to_mmt_in = nn.Linear(int(cfg.ocr.mmt_in_dim), h)
+        self.linear_ocr_bbox_to_mmt_in = nn.Linear(4, h)
+        self.temporal_position_embeddings = nn.Embedding(4000, 50)
+        self.track_position_embeddings = nn.Embedding(4000, 50)
+        self.ocr_feat_layer_norm = nn.LayerNorm(h, eps=LN_EPS_EMBED)
+        self.ocr_bbox_layer_norm = nn.LayerNorm(h, eps=LN_EPS_EMBED)
+        self._build_grounding()
+        self.mmt = MMT(h, int(cfg.mmt.num_hidden_layers))
+        self.finetune_modules.append({"module": self.mmt, "lr_scale": cfg.lr_scale_mmt})
+        self.ocr_ptr_net = OcrPtrNet(**cfg.classifier.ocr_ptr_net)
+        num_choices = registry.get(self._datasets[0] + "_num_final_outputs")
+        num_choices -= int(cfg.classifier.ocr_max_num)
+        self.classifier = ClassifierLayer(cfg["classifier"]["type"], in_dim=h, out_dim=num_choices,
+                                          **cfg["classifier"]["params"])
+        self.answer_processor = registry.get(self._datasets[0] + "_answer_processor")
+        g = cfg.grounding
+        self.frame_topk, self.ocr_topk = int(g.frame_topk), int(g.ocr_topk)
+        self.frame_num, self.ocr_frame_num = int(g.frame_num), int(g.ocr_frame_num)
+
+    def _load_bert_base(self):
+        """text_bert_init_from_bert_base (reference t2s.py:47-56) reads a HuggingFace bert-base-uncased
+        checkpoint from '../../huggingface/bert-base-uncased'; load it by key name when it is there."""
+        import os
+        path = os.path.join("..", "..", "huggingface", "bert-base-uncased", "pytorch_model.bin")
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                "text_bert_init_from_bert_base=true needs %s (as the reference does); "
+                "set text_bert_init_from_bert_base=false for random init" % path)
+        sd = torch.load(path, map_location="cpu")
+        own = self.text_bert.state_dict()
+        for k in own:
+            for cand in ("bert." + k, k):
+                if cand in sd:
+                    own[k].copy_(sd[cand])
+                    break
+
+    def _build_grounding(self):
+        raise NotImplementedError
+
+    # ---------------------------------------------------------------- optimizer groups (reference t2s.py:356-376)
+    def get_optimizer_parameters(self, config):
+        groups = []
+        base_lr = config.optimizer_attributes.params.lr
+        finetune = set()
+        for m in self.finetune_modules:
+            groups.append({"params": list(m["module"].parameters()), "lr": base_lr * m["lr_scale"]})
+            finetune.update(list(m["module"].parameters()))
+        groups.insert(0, {"params": [p for p in self.parameters() if p not in finetune]})
+        return groups
+
+    # ---------------------------------------------------------------- weight packing
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _pack_layer(self, layer, bf16):
+        a = layer.attention
+        wqkv = torch.cat([a.self.query.weight, a.self.key.weight, a.self.value.weight], 0).detach()
+        bqkv = torch.cat([a.self.query.bias, a.self.key.bias, a.self.value.bias], 0).detach().float().contiguous()
+        cast = (lambda w: w.detach().to(torch.bfloat16).contiguous()) if bf16 else (lambda w: w.detach().float().contiguous())
+        f32 = lambda t: t.detach().float().contiguous()
+        return dict(
+            wqkv=cast(wqkv), bqkv=bqkv,
+            wo=cast(a.output.dense.weight), bo=f32(a.output.dense.bias),
+            ln1g=f32(a.output.LayerNorm.weight), ln1b=f32(a.output.LayerNorm.bias),
+            wi=cast(layer.intermediate.dense.weight), bi=f32(layer.intermediate.dense.bias),
+            wo2=cast(layer.output.dense.weight), bo2=f32(layer.output.dense.bias),
+            ln2g=f32(layer.output.LayerNorm.weight), ln2b=f32(layer.output.LayerNorm.bias))
+
+    def _pack(self, device):
+        key = (str(device),) + self._weights_key()
+        if self._packed is not None and self._packed_key == key:
+            return self._packed
+        f32 = lambda t: t.detach().float().contiguous()
+
+        def padk(w, kp):       # [N, K] -> [N, kp] zero padded, fp32
+            out = torch.zeros(w.shape[0], kp, device=w.device, dtype=torch.float32)
+            out[:, :w.shape[1]] = w.detach().float()
+            return out
+
+        P = {}
+        P["text"] = [self._pack_layer(l, False) for l in self.text_bert.encoder.layer]
+        if hasattr(self, "TransLayer"):
+            P["qtv"] = [self._pack_layer(l, False) for l in self.TransLayer.encoder.layer]
+        P["mmt"] = [self._pack_layer(l, True) for l in self.mmt.encoder.layer]
+        k_obj = self.linear_obj_feat_to_mmt_in.weight.shape[1]
+        k_ocr = self.linear_ocr_feat_to_mmt_in.weight.shape[1]
+        P["k_obj"], P["k_ocr"] = k_obj, k_ocr
+        P["k_obj_pad"], P["k_ocr_pad"] = _round_up(k_obj, 16), _round_up(k_ocr, 16)
+        P["w_obj"] = padk(self.linear_obj_feat_to_mmt_in.weight, P["k_obj_pad"])
+        P["w_ocr"] = padk(self.linear_ocr_feat_to_mmt_in.weight, P["k_ocr_pad"])
+        P["w_cls"] = self.classifier.module.weight.detach().to(torch.bfloat16).contiguous()
+        P["w_ptr_q"] = self.ocr_ptr_net.query.weight.detach().to(torch.bfloat16).contiguous()
+        P["w_ptr_k"] = self.ocr_ptr_net.key.weight.detach().to(torch.bfloat16).contiguous()
+        P["f32"] = {n: f32(p) for n, p in self.named_parameters()}
+        self._packed, self._packed_key = P, key
+        return P
+
+    # ---------------------------------------------------------------- workspaces
+    def _workspace(self, B, device, dims):
+        key = (B, str(device)) + tuple(sorted(dims.items()))
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        H, Lt, F, O, T, V = 768, dims["Lt"], dims["F"], dims["O"], dims["T"], dims["V"]
+        Le = Lt + F + O
+        Me, Md = B * Le, B * T
+        f32 = dict(device=device, dtype=torch.float32)
+        b16 = dict(device=device, dtype=torch.bfloat16)
+        i32 = dict(device=device, dtype=torch.int32)
+        n_mmt = len(self.mmt.encoder.layer)
+        variants = dims["variants"]
+        ws = dict(
+            # fp32 grounding chain
+            xt=torch.empty(B * Lt, H, **f32), xt2=torch.empty(B * Lt, H, **f32),
+            a_obj=torch.empty(B * F, _round_up(dims["k_obj"], 16), **f32),
+            a_ocr=torch.empty(B * O, _round_up(dims["k_ocr"], 16), **f32),
+            h_obj=torch.empty(B * F, H, **f32), h_ocr=torch.empty(B * O, H, **f32),
+            J0=torch.empty(Me, H, **f32), J1=torch.empty(Me, H, **f32),
+            fx=torch.empty(Me, H, **f32), fqkv=torch.empty(Me, 3 * H, **f32), fctx=torch.empty(Me, H, **f32),
+            fh=torch.empty(Me, H, **f32), fx1=torch.empty(Me, H, **f32), fint=torch.empty(Me, 4 * H, **f32),
+            jm_ref=torch.empty(B, Le, **f32), jm_pos=torch.zeros(B, Le, **f32), jm_neg=torch.zeros(B, Le, **f32),
+            jm_txt=torch.empty(B, Lt, **f32),
+            keys_txt=torch.empty(B, Lt, **i32), nk_txt=torch.empty(B, **i32),
+            keys={v: torch.empty(B, Le, **i32) for v in variants},
+            nk={v: torch.empty(B, **i32) for v in variants},
+            qp=torch.empty(B * Lt, H, **f32), gq=torch.empty(B, H, **f32), sim=torch.empty(B, F + O, **f32),
+            slot=torch.empty(B, O, **f32),
+            # bf16 answer transformer
+            X16=torch.empty(Me, H, **b16),
+            qkv0=torch.empty(Me, 3 * H, **b16),
+            qkv={v: [None] + [torch.empty(Me, 3 * H, **b16) for _ in range(n_mmt - 1)] for v in variants},
+            ctx=torch.empty(Me, H, **b16), hb=torch.empty(Me, H, **b16), x1=torch.empty(Me, H, **b16),
+            xa=torch.empty(Me, H, **b16), xb=torch.empty(Me, H, **b16), inter=torch.empty(Me, 4 * H, **b16),
+            keyp={v: torch.empty(Me, H, **b16) for v in variants},
+            # decoder rows
+            xd=torch.empty(Md, H, **b16), xd1=torch.empty(Md, H, **b16), xd2=torch.empty(Md, H, **b16),
+            hd=torch.empty(Md, H, **b16), ctxd=torch.empty(Md, H, **b16), interd=torch.empty(Md, 4 * H, **b16),
+            qd=torch.empty(Md, H, **b16),
+            qkvd={v: [torch.empty(Md, 3 * H, **b16) for _ in range(n_mmt)] for v in variants},
+            prev=torch.zeros(B, T, device=device, dtype=torch.int64),
+            loss_ws=torch.empty(int(_lib.get_lib().loss_workspace_bytes(B, T)), device=device, dtype=torch.uint8),
+        )
+        self._ws[key] = ws
+        return ws
+
+    # ---------------------------------------------------------------- kernel-level building blocks
+    def _layer_f32(self, L, lw, x, M, rows_L, keys, nk, key_stride, ws, st, out, tanh_base=None, out16=None,
+                   remap=(0, 0, 0)):
+        """One post-LN BERT layer in fp32 over `M` rows grouped in samples of `rows_L`.  Final LN -> `out`."""
+        H = 768
+        B = M // rows_L
+        qkv, ctx, h, x1, inter = ws["fqkv"], ws["fctx"], ws["fh"], ws["fx1"], ws["fint"]
+        L.gemm_f32(_ptr(x), H, _ptr(lw["wqkv"]), H, _ptr(lw["bqkv"]), None, 0, _ptr(qkv), 3 * H, M, 3 * H, H, 0,
+                   0, 0, 0, st)
+        L.attn_f32(_ptr(qkv), 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride, _ptr(ctx), H, st)
+        L.gemm_f32(_ptr(ctx), H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), _ptr(x), H, _ptr(h), H, M, H, H, 0, 0, 0, 0, st)
+        L.add_ln(_ptr(h), 0, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H, None, 0,
+                 _ptr(x1), H, None, 0, 0, 0, 0, st)
+        L.gemm_f32(_ptr(x1), H, _ptr(lw["wi"]), H, _ptr(lw["bi"]), None, 0, _ptr(inter), 4 * H, M, 4 * H, H,
+                   _lib.GEMM_GELU, 0, 0, 0, st)
+        L.gemm_f32(_ptr(inter), 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), _ptr(x1), H, _ptr(h), H, M, H,
+                   4 * H, 0, 0, 0, 0, st)
+        L.add_ln(_ptr(h), 0, H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H,
+                 _ptr(tanh_base), H, _ptr(out), H, _ptr(out16), H, remap[0], remap[1], remap[2], st)
+
+    def _text_bert(self, L, P, ws, inp, B, Lt, Le, st):
+        """TextBert (reference t2s.py:529-545); last layer's LN lands in rows [b*Le, b*Le+Lt) of J0."""
+        H, f = 768, P["f32"]
+        e = "text_bert.embeddings."
+        L.bert_embed_ln(_ptr(inp["text"]), B * Lt, Lt, H, _ptr(f[e + "word_embeddings.weight"]),
+                        _ptr(f[e + "position_embeddings.weight"]), _ptr(f[e + "token_type_embeddings.weight"]),
+                        _ptr(f[e + "LayerNorm.weight"]), _ptr(f[e + "LayerNorm.bias"]), LN_EPS_BERT,
+                        _ptr(ws["xt"]), H, st)
+        x, y = ws["xt"], ws["xt2"]
+        n = len(P["text"])
+        for i, lw in enumerate(P["text"]):
+            last = i == n - 1
+            self._layer_f32(L, lw, x, B * Lt, Lt, ws["keys_txt"], ws["nk_txt"], Lt, ws, st,
+                            out=ws["J0"] if last else y, remap=(Lt, Le, 0) if last else (0, 0, 0))
+            x, y = y, x
+
+    def _encode_obj_ocr(self, L, P, ws, inp, B, Lt, F, O, Le, st, m4c=False):
+        """obj / OCR encoders (reference t2s.py:192-258; m4c.py:186-250) into rows of J0."""
+        H, f = 768, P["f32"]
+        n_obj = 1 if m4c else F
+        vit = inp["mid_img_feat"] if m4c else inp["video_feat"]
+        L.feat_concat(_ptr(vit), vit.shape[-1], None, 0, None if m4c else _ptr(inp["frame_id"]),
+                      None if m4c else _ptr(f["frame_embeddings.weight"]), None, None, 50, B * n_obj,
+                      _ptr(ws["a_obj"]), P["k_obj_pad"], P["k_obj_pad"], st)
+        L.gemm_f32(_ptr(ws["a_obj"]), P["k_obj_pad"], _ptr(P["w_obj"]), P["k_obj_pad"],
+                   _ptr(f["linear_obj_feat_to_mmt_in.bias"]), None, 0, _ptr(ws["h_obj"]), H, B * n_obj, H,
+                   P["k_obj_pad"], 0, 0, 0, 0, st)
+        L.add_ln(_ptr(ws["h_obj"]), 0, H, None, 0, 0, _ptr(f["obj_feat_layer_norm.weight"]),
+                 _ptr(f["obj_feat_layer_norm.bias"]), LN_EPS_EMBED, B * n_obj, H, None, 0, _ptr(ws["J0"]), H, None, 0,
+                 n_obj, Le, Lt, st)
+        c0, c1 = inp["context_feature_0"], inp["context_feature_1"]
+        L.feat_concat(_ptr(c0), c0.shape[-1], _ptr(c1), c1.shape[-1],
+                      None if m4c else _ptr(inp["temporal_id"]), None if m4c else _ptr(f["temporal_position_embeddings.weight"]),
+                      None if m4c else _ptr(inp["track_id"]), None if m4c else _ptr(f["track_position_embeddings.weight"]),
+                      50, B * O, _ptr(ws["a_ocr"]), P["k_ocr_pad"], P["k_ocr_pad"], st)
+        L.gemm_f32(_ptr(ws["a_ocr"]), P["k_ocr_pad"], _ptr(P["w_ocr"]), P["k_ocr_pad"],
+                   _ptr(f["linear_ocr_feat_to_mmt_in.bias"]), None, 0, _ptr(ws["h_ocr"]), H, B * O, H,
+                   P["k_ocr_pad"], 0, 0, 0, 0, st)
+        L.ocr_finish(_ptr(ws["h_ocr"]), H, _ptr(inp["ocr_bbox_coordinates"]), _ptr(f["linear_ocr_bbox_to_mmt_in.weight"]),
+                     _ptr(f["linear_ocr_bbox_to_mmt_in.bias"]), _ptr(f["ocr_feat_layer_norm.weight"]),
+                     _ptr(f["ocr_feat_layer_norm.bias"]), _ptr(f["ocr_bbox_layer_norm.weight"]),
+                     _ptr(f["ocr_bbox_layer_norm.bias"]), LN_EPS_EMBED, B * O, H, _ptr(ws["J0"]), H, O, Le,
+                     Lt + n_obj, st)
+
+    def _mmt_encoder(self, L, P, ws, variants, B, Le, st):
+        """Encoder rows of the answer transformer for each variant; keeps per-layer q|k|v and the
+        pointer-net key projection of the last layer (reference t2s.py:622-631, 659)."""
+        H, M = 768, B * Le
+        layers = P["mmt"]
+        f = P["f32"]
+        lw0 = layers[0]
+        # layer-0 q|k|v only depends on the (variant-independent) input rows: compute once
+        L.gemm_bf16(_ptr(ws["X16"]), H, _ptr(lw0["wqkv"]), H, _ptr(lw0["bqkv"]), None, 0, _ptr(ws["qkv0"]), 3 * H,
+                    M, 3 * H, H, 0, 0, st)
+        for v in variants:
+            x = ws["X16"]
+            ping = [ws["xa"], ws["xb"]]
+            for li, lw in enumerate(layers):
+                if li == 0:
+                    qkv = ws["qkv0"]
+                else:
+                    qkv = ws["qkv"][v][li]
+                    L.gemm_bf16(_ptr(x), H, _ptr(lw["wqkv"]), H, _ptr(lw["bqkv"]), None, 0, _ptr(qkv), 3 * H,
+                                M, 3 * H, H, 0, 0, st)
+                L.attn_bf16(_ptr(qkv), 3 * H, B, Le, H, 12, _ptr(ws["keys"][v]), _ptr(ws["nk"][v]), Le,
+                            _ptr(ws["ctx"]), H, st)
+                L.gemm_bf16(_ptr(ws["ctx"]), H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), _ptr(x), H, _ptr(ws["hb"]), H,
+                            M, H, H, 0, 0, st)
+                L.add_ln(_ptr(ws["hb"]), 1, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H,
+                         None, 0, None, 0, _ptr(ws["x1"]), H, 0, 0, 0, st)
+                L.gemm_bf16(_ptr(ws["x1"]), H, _ptr(lw["wi"]), H, _ptr(lw["bi"]), None, 0, _ptr(ws["inter"]),
+                            4 * H, M, 4 * H, H, _lib.GEMM_GELU, 0, st)
+                L.gemm_bf16(_ptr(ws["inter"]), 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), _ptr(ws["x1"]), H,
+                            _ptr(ws["hb"]), H, M, H, 4 * H, 0, 0, st)
+                out = ping[li & 1]
+                L.add_ln(_ptr(ws["hb"]), 1, H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H,
+                         None, 0, None, 0, _ptr(out), H, 0, 0, 0, st)
+                x = out
+            L.gemm_bf16(_ptr(x), H, _ptr(P["w_ptr_k"]), H, _ptr(f["ocr_ptr_net.key.bias"]), None, 0,
+                        _ptr(ws["keyp"][v]), H, M, H, H, 0, 0, st)
+
+    def _decode_rows(self, L, P, ws, v, jm, scores, B, Le, T, V, O, n_obj, Lt, t0, nq, st):
+        """Decoder rows t0..t0+nq-1 of variant `v` through all layers, then both score heads
+        (reference t2s.py:566-568, 622-631, 279-286)."""
+        H, f = 768, P["f32"]
+        pp = "mmt.prev_pred_embeddings."
+        ocr_row0 = Lt + n_obj
+        L.prev_embed(_ptr(ws["prev"]), T, B, t0, nq, T, V, H, _ptr(f["classifier.module.weight"]),
+                     ws["J1"].data_ptr() + ocr_row0 * H * 4, Le * H, H,
+                     _ptr(f[pp + "position_embeddings.weight"]), _ptr(f[pp + "token_type_embeddings.weight"]),
+                     _ptr(f[pp + "ans_layer_norm.weight"]), _ptr(f[pp + "ans_layer_norm.bias"]),
+                     _ptr(f[pp + "ocr_layer_norm.weight"]), _ptr(f[pp + "ocr_layer_norm.bias"]),
+                     _ptr(f[pp + "emb_layer_norm.weight"]), _ptr(f[pp + "emb_layer_norm.bias"]), LN_EPS_BERT,
+                     _ptr(ws["xd"]), None, H, st)
+        if nq == T:
+            M, rs, off = B * T, 1, 0          # all decoder rows, contiguous
+        else:
+            assert nq == 1
+            M, rs, off = B, T, t0             # one row per sample, T rows apart
+
+        def at(t, width, esize=2):            # pointer to row t0 of a [B*T, width] buffer
+            return t.data_ptr() + off * width * esize
+
+        x = ws["xd"]
+        ping = [ws["xd1"], ws["xd2"]]
+        for li, lw in enumerate(P["mmt"]):
+            qkvd = ws["qkvd"][v][li]
+            qkve = ws["qkv0"] if li == 0 else ws["qkv"][v][li]
+            L.gemm_bf16(at(x, H), rs * H, _ptr(lw["wqkv"]), H, _ptr(lw["bqkv"]), None, 0, at(qkvd, 3 * H),
+                        rs * 3 * H, M, 3 * H, H, 0, 0, st)
+            L.attn_dec(_ptr(qkve), 3 * H, Le, _ptr(qkvd), 3 * H, T, B, H, 12, _ptr(ws["keys"][v]), _ptr(ws["nk"][v]),
+                       Le, t0, nq, _ptr(ws["ctxd"]), H, st)
+            L.gemm_bf16(at(ws["ctxd"], H), rs * H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), at(x, H), rs * H,
+                        at(ws["hd"], H), rs * H, M, H, H, 0, 0, st)
+            L.add_ln(at(ws["hd"], H), 1, rs * H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H,
+                     None, 0, None, 0, at(ws["x1"], H), rs * H, 0, 0, 0, st)
+            L.gemm_bf16(at(ws["x1"], H), rs * H, _ptr(lw["wi"]), H, _ptr(lw["bi"]), None, 0, at(ws["interd"], 4 * H),
+                        rs * 4 * H, M, 4 * H, H, _lib.GEMM_GELU, 0, st)
+            L.gemm_bf16(at(ws["interd"], 4 * H), rs * 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), at(ws["x1"], H),
+                        rs * H, at(ws["hd"], H), rs * H, M, H, 4 * H, 0, 0, st)
+            out = ping[li & 1]
+            L.add_ln(at(ws["hd"], H), 1, rs * H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H,
+                     None, 0, None, 0, at(out, H), rs * H, 0, 0, 0, st)
+            x = out
+        N = V + O
+        L.gemm_bf16(at(x, H), rs * H, _ptr(P["w_cls"]), H, _ptr(f["classifier.module.bias"]), None, 0,
+                    scores.data_ptr() + off * N * 4, rs * N, M, V, H, _lib.GEMM_OUT_F32, 0, st)
+        L.gemm_bf16(at(x, H), rs * H, _ptr(P["w_ptr_q"]), H, _ptr(f["ocr_ptr_net.query.bias"]), None, 0,
+                    at(ws["qd"], H), rs * H, M, H, H, 0, 0, st)
+        L.ptr_score(_ptr(ws["qd"]), H, B, T, t0, nq, ws["keyp"][v].data_ptr() + ocr_row0 * H * 2, Le * H, H, O, H,
+                    jm.data_ptr() + ocr_row0 * 4, Le, _ptr(scores), N, V, st)
+
+    # ---------------------------------------------------------------- input plumbing
+    _I64 = ("text", "text_len", "frame_id", "frame_mask", "temporal_id", "track_id", "ocr_mask", "train_prev_inds",
+            "middel_frame_id", "middel_frame_idx")
+    _F32 = ("video_feat", "context_feature_0", "context_feature_1", "ocr_bbox_coordinates", "mid_img_feat",
+            "gumbel_frame", "gumbel_ocr")
+
+    def _device(self):
+        return next(self.parameters()).device
+
+    def _gather_inputs(self, sample_list, names):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise _lib.T2SLibraryError(
+                "the %s forward path runs only on a CUDA device (sm_100a); move the model with .to('cuda'). "
+                "There is no CPU fallback." % self.MODEL)
+        out = {}
+        for n in names:
+            if n not in sample_list:
+                continue
+            t = sample_list[n]
+            want = torch.int64 if n in self._I64 else torch.float32
+            out[n] = t.to(device=dev, dtype=want, non_blocking=True).contiguous()
+        return out
+
+    def forward(self, sample_list):
+        raise NotImplementedError
+
+
+# =============================================================================== T2S
+@registry.register_model("t2s")
+class T2S(_FusionModelBase):
+    MODEL = "t2s"
+
+    def _build_grounding(self):
+        cfg, h = self.config, self.hidden
+        self.TransLayer = QTV(h, int(cfg.translayers.num_hidden_layers))
+        self.Grounding_Module = GroundingModule(h, int(cfg.encoder.num_hidden_layers))
+
+    def forward(self, sample_list):
+        L = _lib.get_lib()
+        inp = self._gather_inputs(sample_list, self._I64 + self._F32)
+        dev = self._device()
+        B, Lt = inp["text"].shape
+        F = inp["video_feat"].shape[1]
+        O = inp["ocr_mask"].shape[1]
+        T = inp["train_prev_inds"].shape[1]
+        V = self.classifier.module.weight.shape[0]
+        Of = O // F
+        if F != self.frame_num or Of != self.ocr_frame_num or O != F * Of:
+            raise ValueError("inputs have %d frames x %d OCR slots but the config says %d x %d"
+                             % (F, Of, self.frame_num, self.ocr_frame_num))
+        Le, H = Lt + F + O, 768
+        P = self._pack(dev)
+        variants = ("pos", "ref", "neg")
+        ws = self._workspace(B, dev, dict(Lt=Lt, F=F, O=O, T=T, V=V, k_obj=P["k_obj"], k_ocr=P["k_ocr"],
+                                          variants=variants))
+        st = torch.cuda.current_stream(dev).cuda_stream
+        f = P["f32"]
+
+        # ---- masks and key lists
+        L.mask_prep(_ptr(inp["text_len"]), _ptr(inp["frame_mask"]), _ptr(inp["ocr_mask"]), B, Lt, F, O,
+                    _ptr(ws["jm_ref"]), st)
+        L.mask_prep(_ptr(inp["text_len"]), None, None, B, Lt, 0, 0, _ptr(ws["jm_txt"]), st)
+        L.build_keys(_ptr(ws["jm_txt"]), B, Lt, _ptr(ws["keys_txt"]), _ptr(ws["nk_txt"]), Lt, st)
+        L.build_keys(_ptr(ws["jm_ref"]), B, Le, _ptr(ws["keys"]["ref"]), _ptr(ws["nk"]["ref"]), Le, st)
+
+        # ---- fp32 grounding chain
+        self._text_bert(L, P, ws, inp, B, Lt, Le, st)
+        self._encode_obj_ocr(L, P, ws, inp, B, Lt, F, O, Le, st)
+        x, n = ws["J0"], len(P["qtv"])
+        if n > 2 and "fx2" not in ws:
+            ws["fx2"] = torch.empty_like(ws["fx"])
+        for i, lw in enumerate(P["qtv"]):
+            last = i == n - 1
+            out = ws["J1"] if last else (ws["fx"] if i % 2 == 0 else ws["fx2"])
+            self._layer_f32(L, lw, x, B * Le, Le, ws["keys"]["ref"], ws["nk"]["ref"], Le, ws, st, out=out,
+                            tanh_base=ws["J0"] if last else None, out16=ws["X16"] if last else None)
+            x = out
+
+        # ---- grounding (K5)
+        g = "Grounding_Module."
+        L.gemm_f32(_ptr(ws["J1"]), H, _ptr(f[g + "q_linear.weight"]), H, _ptr(f[g + "q_linear.bias"]), None, 0,
+                   _ptr(ws["qp"]), H, B * Lt, H, H, 0, Lt, Le, 0, st)
+        L.question_pool(_ptr(ws["qp"]), B, Lt, H, _ptr(f[g + "self_attn.weight"]), _ptr(f[g + "self_attn.bias"]),
+                        _ptr(ws["jm_ref"]), Le, _ptr(ws["gq"]), st)
+        L.sim_scores(_ptr(ws["gq"]), _ptr(ws["J1"]), Le * H, H, Lt, F + O, H, B, _ptr(ws["sim"]), st)
+        if "gumbel_frame" in inp:
+            gf, go = inp["gumbel_frame"], inp["gumbel_ocr"]
+        else:   # F.gumbel_softmax draws -log(Exp(1)) noise (reference stg.py:41,89); torch RNG is plumbing here
+            gf = -torch.empty(B, 2, F, device=dev).exponential_().log()
+            go = -torch.empty(B, 2, O, device=dev).exponential_().log()
+        ground_frame = torch.empty(B, self.frame_topk, device=dev, dtype=torch.int64)
+        kk = min(self.ocr_topk, Of)
+        ground_box = torch.empty(B, F * kk, 4, device=dev, dtype=torch.float32)
+        pos_ovr = self.parity_hooks.get("pos_frame_topk")
+        neg_ovr = self.parity_hooks.get("neg_frame_topk")
+        dbg = self.parity_hooks.get("debug", False)
+        dbg_f = torch.empty(B, F, device=dev) if dbg else None
+        dbg_o = torch.empty(B, O, device=dev) if dbg else None
+        L.temporal_select(_ptr(ws["sim"]), F + O, _ptr(ws["jm_ref"]), B, Lt, F, Of, _ptr(gf), _ptr(inp["frame_id"]),
+                          _ptr(inp["temporal_id"]), self.frame_topk,
+                          _ptr(pos_ovr.to(dev).float().contiguous()) if pos_ovr is not None else None,
+                          _ptr(neg_ovr.to(dev).float().contiguous()) if neg_ovr is not None else None,
+                          _ptr(ground_frame), _ptr(ws["jm_pos"]), _ptr(ws["jm_neg"]), _ptr(ws["slot"]), _ptr(dbg_f), st)
+        L.spatial_select(_ptr(ws["sim"]), F + O, F, _ptr(ws["slot"]), _ptr(ws["jm_ref"]), B, Le, Lt + F, F, Of, _ptr(go),
+                         _ptr(inp["ocr_bbox_coordinates"]), self.ocr_topk, 0, _ptr(ground_box), _ptr(ws["jm_pos"]),
+                         _ptr(ws["jm_neg"]), _ptr(dbg_o), st)
+        L.build_keys(_ptr(ws["jm_pos"]), B, Le, _ptr(ws["keys"]["pos"]), _ptr(ws["nk"]["pos"]), Le, st)
+        L.build_keys(_ptr(ws["jm_neg"]), B, Le, _ptr(ws["keys"]["neg"]), _ptr(ws["nk"]["neg"]), Le, st)
+
+        # ---- bf16 answer transformer
+        jm = {"ref": ws["jm_ref"], "pos": ws["jm_pos"], "neg": ws["jm_neg"]}
+        N = V + O
+        scores = {v: torch.empty(B, T, N, device=dev, dtype=torch.float32) for v in variants}
+        self._mmt_encoder(L, P, ws, variants, B, Le, st)
+        if self.training:
+            ws["prev"].copy_(inp["train_prev_inds"])
+            for v in variants:
+                self._decode_rows(L, P, ws, v, jm[v], scores[v], B, Le, T, V, O, F, Lt, 0, T, st)
+        else:
+            ws["prev"].zero_()
+            ws["prev"][:, 0] = int(self.answer_processor.BOS_IDX)
+            for t in range(T):     # greedy decode drives only the `pos` variant (reference t2s.py:353, Q15)
+                self._decode_rows(L, P, ws, "pos", jm["pos"], scores["pos"], B, Le, T, V, O, F, Lt, t, 1, st)
+                L.argmax_feedback(_ptr(scores["pos"]), N, B, T, t, 1, N, _ptr(ws["prev"]), T, None, st)
+            for v in ("ref", "neg"):
+                self._decode_rows(L, P, ws, v, jm[v], scores[v], B, Le, T, V, O, F, Lt, 0, T, st)
+        if dbg:
+            self.last_debug = dict(J0=ws["J0"].view(B, Le, H), J1=ws["J1"].view(B, Le, H), sim=ws["sim"],
+                                   gq=ws["gq"], frame_score=dbg_f, ocr_score=dbg_o, jm_pos=ws["jm_pos"],
+                                   jm_neg=ws["jm_neg"], jm_ref=ws["jm_ref"], slot=ws["slot"], prev_inds=ws["prev"])
+        return {
+            "ref_scores": scores["ref"], "pos_scores": scores["pos"], "neg_scores": scores["neg"],
+            "ground_box": ground_box, "ground_frame": ground_frame,
+            "frame_topk": torch.tensor(self.frame_topk, device=dev), "ocr_topk": torch.tensor(self.ocr_topk, device=dev),
+        }
+
+
+# =============================================================================== M4C
+@registry.register_model("m4c")
+class M4C(_FusionModelBase):
+    MODEL = "m4c"
+
+    def _build_grounding(self):
+        self.PostHoc = PostHocAttention(self.hidden)
+
+    def forward(self, sample_list):
+        L = _lib.get_lib()
+        inp = self._gather_inputs(sample_list, self._I64 + self._F32)
+        dev = self._device()
+        B, Lt = inp["text"].shape
+        F, Of = self.frame_num, self.ocr_frame_num
+        O = inp["ocr_mask"].shape[1]
+        T = inp["train_prev_inds"].shape[1]
+        V = self.classifier.module.weight.shape[0]
+        if O != F * Of:
+            raise ValueError("inputs have %d OCR slots but the config says %d x %d" % (O, F, Of))
+        Le, H = Lt + 1 + O, 768      # one object token: the middle frame (reference m4c.py:188,420)
+        P = self._pack(dev)
+        variants = ("pos",)
+        ws = self._workspace(B, dev, dict(Lt=Lt, F=1, O=O, T=T, V=V, k_obj=P["k_obj"], k_ocr=P["k_ocr"],
+                                          variants=variants))
+        st = torch.cuda.current_stream(dev).cuda_stream
+        f = P["f32"]
+        ones = torch.ones(B, 1, device=dev, dtype=torch.int64)
+        L.mask_prep(_ptr(inp["text_len"]), _ptr(ones), _ptr(inp["ocr_mask"]), B, Lt, 1, O, _ptr(ws["jm_ref"]), st)
+        L.mask_prep(_ptr(inp["text_len"]), None, None, B, Lt, 0, 0, _ptr(ws["jm_txt"]), st)
+        L.build_keys(_ptr(ws["jm_txt"]), B, Lt, _ptr(ws["keys_txt"]), _ptr(ws["nk_txt"]), Lt, st)
+        self._text_bert(L, P, ws, inp, B, Lt, Le, st)
+        self._encode_obj_ocr(L, P, ws, inp, B, Lt, 1, O, Le, st, m4c=True)
+        # no QTV in M4C: the joint buffer feeds the answer transformer directly
+        ws["J1"].copy_(ws["J0"])
+        L.cast_rows_bf16(_ptr(ws["J0"]), H, B * Le, H, _ptr(ws["X16"]), H, 0, 0, 0, st)
+        g = "PostHoc."
+        L.gemm_f32(_ptr(ws["J1"]), H, _ptr(f[g + "q_linear.weight"]), H, _ptr(f[g + "q_linear.bias"]), None, 0,
+                   _ptr(ws["qp"]), H, B * Lt, H, H, 0, Lt, Le, 0, st)
+        L.question_pool(_ptr(ws["qp"]), B, Lt, H, _ptr(f[g + "self_attn.weight"]), _ptr(f[g + "self_attn.bias"]),
+                        _ptr(ws["jm_ref"]), Le, _ptr(ws["gq"]), st)
+        L.sim_scores(_ptr(ws["gq"]), _ptr(ws["J1"]), Le * H, H, Lt + 1, O, H, B, _ptr(ws["sim"]), st)
+        L.middle_frame_slots(_ptr(inp["middel_frame_id"]), _ptr(inp["temporal_id"]), B, O, _ptr(ws["slot"]), st)
+        kk = min(self.ocr_topk, Of)
+        ground_box = torch.zeros(B, kk, 4, device=dev, dtype=torch.float32)
+        ws["jm_pos"].copy_(ws["jm_ref"])
+        L.spatial_select(_ptr(ws["sim"]), O, 0, _ptr(ws["slot"]), _ptr(ws["jm_ref"]), B, Le, Lt + 1, F, Of, None,
+                         _ptr(inp["ocr_bbox_coordinates"]), self.ocr_topk, 1, _ptr(ground_box), _ptr(ws["jm_pos"]),
+                         None, None, st)
+        L.build_keys(_ptr(ws["jm_pos"]), B, Le, _ptr(ws["keys"]["pos"]), _ptr(ws["nk"]["pos"]), Le, st)
+        N = V + O
+        scores = torch.empty(B, T, N, device=dev, dtype=torch.float32)
+        self._mmt_encoder(L, P, ws, variants, B, Le, st)
+        if self.training:
+            ws["prev"].copy_(inp["train_prev_inds"])
+            self._decode_rows(L, P, ws, "pos", ws["jm_pos"], scores, B, Le, T, V, O, 1, Lt, 0, T, st)
+        else:
+            ws["prev"].zero_()
+            ws["prev"][:, 0] = int(self.answer_processor.BOS_IDX)
+            for t in range(T):
+                self._decode_rows(L, P, ws, "pos", ws["jm_pos"], scores, B, Le, T, V, O, 1, Lt, t, 1, st)
+                L.argmax_feedback(_ptr(scores), N, B, T, t, 1, N, _ptr(ws["prev"]), T, None, st)
+        return {
+            "pos_scores": scores, "ground_box": ground_box, "ground_frame": inp["middel_frame_id"],
+            "frame_topk": torch.tensor(self.frame_topk, device=dev), "ocr_topk": torch.tensor(self.ocr_topk, device=dev),
+        }
