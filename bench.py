@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- T2S-QA forward + grounding throughput (samples/s) on B200, next to the CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B]
+
+One "step" = one eval-mode `T2S.forward(sample_list)` (TextBert -> obj/OCR encoders -> QTV ->
+temporal/spatial grounding -> 12-step greedy decode of the answer transformer -> ref/pos/neg scores
++ both losses) over one batch of synthetic t2s_abinet-shaped inputs (BASELINE.json configs[1]:
+batch 64 per GPU).  Ranks are independent replicas over different batches (samples are
+independent; no data-path collective): weak scaling.
+
+Printed JSON line (rank 0):
+  value     samples/s with the inputs already resident in HBM (CUDA events, max over ranks)
+  e2e       samples/s through the public API `model(sample_list)` from PINNED HOST tensors, with the
+            H2D copy of the inputs and the D2H read of what the reference's Metrics consume
+            (pos_scores, ground_frame, ground_box, losses) inside the timed region
+  roofline  the kernel with the largest share of the step, from CUDA events bracketing every launch
+            of an instrumented repeat of the same steps (see DESIGN.md "Measurement")
+  cpu_baseline  the CPU oracle (reference schedule: 36 full passes) on this box's host cores
+`--impl reference` times that CPU path alone, K steps of batch 1.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "T2S-QA fwd+grounding samples/s"
+WORKLOAD = "t2s_abinet eval forward+grounding, batch 64/GPU, F=64 frames x 15 OCR, V=5000, 12 decode steps"
+
+# algorithmic work of one sample: the reference's 36 passes collapse to front + 3 variants
+H, I, LT, F_, OF, T_, V_ = 768, 3072, 20, 64, 15, 12, 5000
+
+
+def algorithmic_gflop_per_sample():
+    O = F_ * OF
+    g = 2 * (4 * H * H + 2 * H * I)
+    rows = lambda lq, lk, n: n * (lq * g + 4 * lq * lk * H)
+    lq = LT + F_ + O
+    lm = lq + T_
+    front = rows(LT, LT, 3) + 2 * F_ * 1074 * H + 2 * O * 1004 * H + 2 * O * 4 * H + rows(lq, lq, 2)
+    variant = rows(lq, lq, 3) + rows(T_, lm, 3) + 2 * O * H * H + 2 * T_ * H * V_ + 2 * T_ * H * H + 2 * T_ * O * H
+    return (front + 3 * variant) / 1e9
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            z = json.load(open(p))
+            return dict(hbm=float(z["hbm_gbs"]), tf=float(z["bf16_tflops"]),
+                        tf_sus=float(z.get("bf16_tflops_sustained", z["bf16_tflops"])), src="measured")
+        except Exception:
+            pass
+    # B200_PROFILING.md fallback (file absent in this checkout)
+    return dict(hbm=6650.0, tf=1590.0, tf_sus=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w": statistics.median(power), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU path
+def cpu_reference_step(sd, d, inp):
+    """The reference's own schedule (36 full MMT passes, t2s.py:288-354) restated on CPU: oracle/."""
+    from oracle import t2s_oracle as O
+    with torch.no_grad():
+        out = O.forward_t2s(sd, d, inp, schedule="literal")
+        O.pos_bce_loss(out["pos_scores"], inp["targets"], inp["train_loss_mask"])
+        O.info_nce(out["ref_scores"], out["pos_scores"], out["neg_scores"])
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from vitxt_gqa_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    d = synth.Dims()
+    sd = synth.make_state_dict(d, seed=0, variant="stress")
+    inp = synth.make_inputs(d, 1, seed=1235, full_frames=True)
+    for _ in range(args.warmup):
+        cpu_reference_step(sd, d, inp)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(sd, d, inp)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    sample = "batch 1 per step, reference schedule (36 full passes), fp32, torch CPU threads=%d" % cores
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": 1},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------ B200 path
+def kernel_work(name, a):
+    """(flops, bytes) one launch is asked to do, from its C-ABI arguments (include/t2s_b200.h)."""
+    if name == "t2s_gemm_bf16":
+        M, N, K = a[9], a[10], a[11]
+        return 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N)
+    if name == "t2s_gemm_f32":
+        M, N, K = a[9], a[10], a[11]
+        return 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)
+    if name in ("t2s_attn_f32", "t2s_attn_bf16"):
+        B, L, Hh = a[2], a[3], a[4]
+        es = 4 if name.endswith("f32") else 2
+        return 4.0 * B * L * L * Hh, es * 4.0 * B * L * Hh      # dense upper bound on the key count
+    if name == "t2s_add_ln":
+        rows, Hh = a[9], a[10]
+        return 8.0 * rows * Hh, (2 if a[1] else 4) * 2.0 * rows * Hh
+    return 0.0, 0.0
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from vitxt_gqa_b200 import lib as tlib, model as tmodel, synth
+    from vitxt_gqa_b200.pythia_api import SampleList, load_yaml_config, register_defaults
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = load_yaml_config("t2s_abinet.yml", {"model_attributes.t2s.text_bert_init_from_bert_base": False})
+    mcfg = cfg.model_attributes.t2s
+    d = synth.dims_from_config(mcfg, vocab=V_)
+    register_defaults(vocab_size=d.vocab, ocr_max_num=d.ocr)
+    model = tmodel.T2S(mcfg)
+    model.build()
+    model.init_losses_and_metrics()
+    model.load_state_dict(synth.make_state_dict(d, seed=0, variant="stress"))
+    model = model.to(dev).eval()
+    B = args.batch
+    inp = synth.make_inputs(d, B, seed=1235 + rank, full_frames=True)
+    host = synth.to_sample_list(inp, SampleList)
+    for k in list(host.keys()):
+        if torch.is_tensor(host[k]):
+            host[k] = host[k].pin_memory()
+    resident = host.to(dev)
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+    L = tlib.get_lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        # ---- leg 1: inputs resident in HBM
+        for _ in range(args.warmup):
+            model(resident)
+        clocks = ClockSampler(local)
+        barrier()
+        if rank == 0:
+            clocks.start()
+        l0 = L.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            model(resident)
+        e1.record()
+        barrier()
+        launches = L.launches - l0
+        ms_dev = max_over_ranks(e0.elapsed_time(e1))
+        clk = clocks.stop() if rank == 0 else None
+
+        # ---- leg 2: end to end from pinned host memory through model(sample_list)
+        d2h_keys = ("pos_scores", "ground_frame", "ground_box")
+        out = model(resident)
+        pinned_out = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in d2h_keys}
+        pinned_loss = {k: torch.empty(1).pin_memory() for k in out["losses"]}
+        d2h = sum(v.numel() * v.element_size() for v in list(pinned_out.values()) + list(pinned_loss.values()))
+
+        def e2e_step():
+            o = model(host.to(dev, non_blocking=True))
+            for k in d2h_keys:
+                pinned_out[k].copy_(o[k], non_blocking=True)
+            for k, v in o["losses"].items():
+                pinned_loss[k].copy_(v, non_blocking=True)
+            torch.cuda.synchronize()          # the caller reads the result of every step
+
+        for _ in range(min(args.warmup, 3)):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+        # ---- leg 3: per-launch CUDA events on the launching stream, same steps again
+        prof_steps = min(args.steps, 3)
+        L.start_timing()
+        for _ in range(prof_steps):
+            model(resident)
+        rec = L.stop_timing()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    per = {}
+    for name, a, ms in rec:
+        fl, by = kernel_work(name, a)
+        p = per.setdefault(name, dict(ms=0.0, n=0, flops=0.0, bytes=0.0))
+        p["ms"] += ms; p["n"] += 1; p["flops"] += fl; p["bytes"] += by
+    tot = sum(p["ms"] for p in per.values())
+    top = max(per, key=lambda k: per[k]["ms"])
+    tp = per[top]
+    tensor_bound = top.startswith("t2s_gemm") or top.startswith("t2s_attn")
+    if tensor_bound:
+        ach = tp["flops"] / (tp["ms"] * 1e-3) / 1e12
+        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tf_sus"], "traffic": None,
+                "peak_source": peaks["src"] + " sustained bf16 (kernel timed inside a long step)"}
+    else:
+        ach = tp["bytes"] / (tp["ms"] * 1e-3) / 1e9
+        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"]}
+    roof.update(launches_per_step=tp["n"] / prof_steps, avg_launch_ms=tp["ms"] / tp["n"],
+                share_of_step=tp["ms"] / tot)
+    kernels = {k[4:]: {"share": round(v["ms"] / tot, 4), "ms_per_step": round(v["ms"] / prof_steps, 3),
+                       "launches_per_step": v["n"] / prof_steps,
+                       "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else None}
+               for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])}
+
+    # ---- CPU baseline: the reference schedule restated on CPU, bounded sample (N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd_cpu = synth.make_state_dict(d, seed=0, variant="stress")
+        one = synth.make_inputs(d, 1, seed=1235, full_frames=True)
+        t0 = time.perf_counter()
+        cpu_reference_step(sd_cpu, d, one)
+        dt = time.perf_counter() - t0
+        cpu = {"value": 1.0 / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": "1 eval forward of batch 1 (reference schedule, 36 full passes), fp32 torch CPU, "
+                         "%d threads, %.1f s" % (cores, dt)}
+
+    samples = B * world * args.steps
+    gf = algorithmic_gflop_per_sample()
+    line = {
+        "metric": METRIC, "value": samples / (ms_dev * 1e-3), "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 answer transformer + fp32 grounding chain (fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "l2": "inputs (%.0f MB/step) and activations exceed L2"
+                   % (h2d / 1e6), "algorithmic_gflop_per_sample": round(gf, 1)},
+        "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "model_tflops": round(samples * gf / 1e3 / (ms_dev * 1e-3) / world, 1),
+        "kernels": kernels,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

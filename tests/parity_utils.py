@@ -75,3 +75,22 @@ def score_errors(ref, got):
     got = torch.as_tensor(got).float().cpu()
     diff = (ref - got).abs()
     return diff.max().item(), diff.mean().item()
+
+
+def reference_prev_inds(ref_pos_scores, bos_idx=1):
+    """prev_inds of the reference's LAST decode iteration (t2s.py:321,353): [BOS, argmax(pos_scores)[:-1]]."""
+    ref = torch.as_tensor(ref_pos_scores)
+    prev = torch.zeros(ref.shape[:2], dtype=torch.int64)
+    prev[:, 0] = bos_idx
+    prev[:, 1:] = ref.argmax(-1)[:, :-1]
+    return prev
+
+
+def agreeing_prefix_mask(ref_pos_scores, got_pos_scores):
+    """[B,T] bool: rows whose decoder INPUTS are identical in both runs -- row t of a sample is comparable
+    iff the answer indices agreed on every earlier row (greedy decode feeds them back)."""
+    ra = torch.as_tensor(ref_pos_scores).float().cpu().argmax(-1)
+    ga = torch.as_tensor(got_pos_scores).float().cpu().argmax(-1)
+    agree = (ra == ga).long()
+    before = torch.cumprod(torch.cat([torch.ones_like(agree[:, :1]), agree[:, :-1]], 1), 1)
+    return before.bool()

@@ -1,0 +1,192 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares (no compute calls without a GPU), the reference-facing API (registry, configs, SampleList,
+state_dict names, optimizer groups) behaves like the reference's, the product path refuses to run
+without CUDA, and the data-parallel helpers work across two gloo ranks."""
+import ctypes
+import os
+import re
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vitxt_gqa_b200 import dp, lib as tlib, synth
+from vitxt_gqa_b200.pythia_api import ConfigNode, SampleList, load_yaml_config, register_defaults, registry
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------- C ABI
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "t2s_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(t2s_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    if not os.path.exists(tlib.LIB_PATH):
+        tlib.build_library()
+    cdll = ctypes.CDLL(tlib.LIB_PATH)
+    names = _header_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(cdll, n), "libt2s_sm100.so does not export " + n
+    assert sorted(tlib.EXPORTED_SYMBOLS) == names, "ctypes table and header disagree"
+    cdll.t2s_abi_version.restype = ctypes.c_int
+    assert cdll.t2s_abi_version() == 1
+
+
+def test_library_is_sm100a_tcgen05_tma():
+    """The shipped GEMM really is the Blackwell path: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA)."""
+    import subprocess
+    if not os.path.exists(tlib.LIB_PATH):
+        tlib.build_library()
+    sass = subprocess.run(["cuobjdump", "-sass", tlib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in sass, mnemonic + " missing from the SASS"
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    L = tlib.get_lib()
+    with pytest.raises(tlib.T2SLibraryError):
+        L.gemm_bf16(None, 768, None, 768, None, None, 0, None, 768, 0, 768, 768, 0, 0, None)   # M = 0
+    with pytest.raises(tlib.T2SLibraryError):
+        L.attn_bf16(None, 2304, 1, 20, 700, 12, None, None, 20, None, 768, None)                # head size != 64
+
+
+# ------------------------------------------------------------------------------- reference-facing API
+def test_registered_models_and_losses():
+    import vitxt_gqa_b200.model  # noqa: F401
+    for key in ("t2s", "m4c"):
+        assert registry.get_model_class(key) is not None
+    for key in ("pos_bce_loss", "InfoNCE"):
+        assert registry.get_loss_class(key) is not None
+
+
+@pytest.mark.parametrize("name,model,topk,w", [("t2s_abinet.yml", "t2s", 5, 1000), ("t2s_clipocr.yml", "t2s", 1, 100),
+                                              ("m4c_abinet.yml", "m4c", None, None)])
+def test_packaged_configs_load(name, model, topk, w):
+    cfg = load_yaml_config(name, {"model_attributes.%s.text_bert_init_from_bert_base" % model: False})
+    m = cfg.model_attributes[model]
+    assert m.mmt.hidden_size == 768 and m.classifier.ocr_max_num == 960
+    assert m.text_bert_init_from_bert_base is False
+    if model == "t2s":
+        assert m.obj.mmt_in_dim == 1074 and m.ocr.mmt_in_dim == 1004
+        assert m.grounding.frame_topk == topk and m.grounding.frame_num == 64 and m.grounding.ocr_frame_num == 15
+        assert [l["weight"] for l in m.losses if l["type"] == "InfoNCE"] == [w]
+    else:
+        assert m.obj.mmt_in_dim == 1024 and m.ocr.mmt_in_dim == 904
+
+
+def test_sample_list_semantics():
+    sl = SampleList()
+    sl.add_field("text", torch.zeros(3, 20, dtype=torch.int64))
+    sl["dataset_name"] = "vtextgqa"
+    assert sl.text.shape == (3, 20) and sl["dataset_name"] == "vtextgqa" and sl.get_batch_size() == 3
+    with pytest.raises(AssertionError):
+        sl.add_field("bad", torch.zeros(4, 2))
+    with pytest.raises(AttributeError):
+        sl.missing
+    assert isinstance(sl.to("cpu"), type(sl))
+
+
+def _build(d):
+    from vitxt_gqa_b200 import model as tmodel
+    register_defaults(vocab_size=d.vocab, ocr_max_num=d.ocr)
+    m = (tmodel.T2S if d.model == "t2s" else tmodel.M4C)(ConfigNode(synth.model_config_for_dims(d)))
+    m.build()
+    m.init_losses_and_metrics()
+    return m
+
+
+@pytest.mark.parametrize("kind", ["t2s", "m4c"])
+def test_state_dict_names_and_shapes_match_the_reference(kind):
+    """synth.param_shapes is the reference's state_dict (tests/golden/make_golden.py loads it strict into the
+    real reference model); ours must be identical, dead weights included."""
+    d = synth.Dims(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2, model=kind)
+    m = _build(d)
+    want = synth.param_shapes(d)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert set(got) == set(want), (sorted(set(want) - set(got))[:5], sorted(set(got) - set(want))[:5])
+    assert all(got[k] == tuple(want[k]) for k in want)
+    m.load_state_dict(synth.make_state_dict(d, seed=0), strict=True)
+
+
+def test_optimizer_groups_follow_the_reference():
+    d = synth.Dims(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2)
+    m = _build(d)
+    groups = m.get_optimizer_parameters(ConfigNode({"optimizer_attributes": {"params": {"lr": 1e-4}}}))
+    # text_bert is only a fine-tune group when initialised from bert-base (reference t2s.py:47-56)
+    assert len(groups) == 2 and "lr" not in groups[0] and groups[1]["lr"] == pytest.approx(1e-4)
+    n = sum(p.numel() for g in groups for p in g["params"])
+    assert n == sum(p.numel() for p in m.parameters())
+
+
+def test_forward_refuses_to_run_without_cuda():
+    d = synth.Dims(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2)
+    m = _build(d).eval()
+    sl = synth.to_sample_list(synth.make_inputs(d, 2, seed=1), SampleList)
+    with pytest.raises(tlib.T2SLibraryError):
+        m(sl)
+
+
+def test_synthetic_inputs_are_reproducible_and_dataset_shaped():
+    d = synth.Dims()
+    a, b = synth.make_inputs(d, 2, seed=7), synth.make_inputs(d, 2, seed=7)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert a["video_feat"].shape == (2, 64, 1024) and a["context_feature_1"].shape == (2, 960, 604)
+    assert a["frame_mask"].dtype == torch.int64 and a["ocr_mask"].dtype == torch.int64
+    assert torch.equal(a["temporal_id"], a["frame_id"].repeat_interleave(15, dim=1))
+    pads = a["ocr_mask"][0] == 0
+    assert pads.any() and (a["context_feature_0"][0][pads] == a["context_feature_0"][0][pads][0]).all()
+
+
+# ------------------------------------------------------------------------------- two gloo ranks
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        d = synth.Dims(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2)
+        full = synth.to_sample_list(synth.make_inputs(d, 4, seed=3), SampleList)
+        mine = dp.shard_sample_list(full)
+        assert mine.get_batch_size() == 2 and mine["dataset_name"] == "vtextgqa"
+        assert torch.equal(mine.video_feat, full.video_feat[rank * 2:(rank + 1) * 2])
+        # stand-in for the per-rank model output: deterministic function of the shard
+        out = {"pos_scores": mine.video_feat[:, :12, :30].clone(), "ground_frame": mine.frame_id[:, :3].clone()}
+        g = dp.gather_predictions(out)
+        assert torch.equal(g["pos_scores"], full.video_feat[:, :12, :30])
+        assert torch.equal(g["ground_frame"], full.frame_id[:, :3])
+        red = dp.reduce_dict({"b": torch.tensor(float(rank + 1)), "a": torch.tensor(10.0 * (rank + 1))})
+        if rank == 0:
+            assert float(red["a"]) == pytest.approx(15.0) and float(red["b"]) == pytest.approx(1.5)
+        with pytest.raises(RuntimeError):
+            dp.per_rank_batch(5)
+        q.put((rank, "ok"))
+    except Exception as e:      # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_helpers_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, "ok"), (1, "ok")], res

@@ -15,17 +15,41 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from parity_utils import (ARGMAX_MARGIN, FP32_CHAIN_ATOL, LOSS_RTOL, SCORES_MAX_ABS, SCORES_MEAN_ABS,  # noqa: E402
-                          build_b200_model, load_golden, margin_aware_argmax_check, sample_list, score_errors)
+                          agreeing_prefix_mask, build_b200_model, load_golden, margin_aware_argmax_check,
+                          reference_prev_inds, sample_list, score_errors)
 from vitxt_gqa_b200 import synth  # noqa: E402
 
 
-def _check_scores(name, ref, got, train):
-    mx, mean = score_errors(ref, got)
+def _check_scores(name, ref, got, train, rows=None):
+    """Logit tolerance on every row (or on `rows` [B,T] only), answer indices margin-aware."""
+    ref_t, got_t = torch.as_tensor(ref).float().cpu(), torch.as_tensor(got).float().cpu()
+    if rows is not None:
+        ref_t, got_t = ref_t[rows], got_t[rows]
+    mx, mean = score_errors(ref_t, got_t)
     assert mx <= SCORES_MAX_ABS and mean <= SCORES_MEAN_ABS, (name, mx, mean)
     if not train:
         checked, mism, low = margin_aware_argmax_check(ref, got)
         assert mism == 0, (name, "answer argmax mismatch outside the margin band", checked, mism, low)
     return mx, mean
+
+
+def _check_eval_scores(fixture, z, out, model, sl, keys):
+    """Greedy decode is autoregressive: a flip inside the stated margin band legitimately changes every later
+    row of that sample.  (1) free-running: indices margin-aware, logits on the rows whose inputs agree;
+    (2) teacher-forced with the reference's own prev_inds: every row of every variant within tolerance."""
+    rows = agreeing_prefix_mask(z["pos_scores"], out["pos_scores"])
+    for key in keys:
+        _check_scores(fixture + ":free:" + key, z[key], out[key], key != "pos_scores", rows=rows)
+    hooks = dict(model.parity_hooks)
+    model.parity_hooks = dict(hooks, force_prev_inds=reference_prev_inds(z["pos_scores"]))
+    with torch.no_grad():
+        forced = model(sl)
+    torch.cuda.synchronize()
+    model.parity_hooks = hooks
+    for key in keys:
+        _check_scores(fixture + ":forced:" + key, z[key], forced[key], True)
+    n_flip = int((~rows).any(1).sum())
+    return n_flip
 
 
 @pytest.mark.parametrize("fixture", ["t2s_small_eval", "t2s_small_default", "t2s_small_train",
@@ -61,8 +85,17 @@ def test_t2s_against_reference_golden(fixture):
     assert np.array_equal(out["ground_frame"].cpu().numpy(), z["ground_frame"])
     assert np.array_equal(out["ground_box"].cpu().numpy(), z["ground_box"]), "grounded OCR boxes differ"
     assert int(out["frame_topk"]) == int(z["frame_topk"]) and int(out["ocr_topk"]) == int(z["ocr_topk"])
-    for key in ("pos_scores", "ref_scores", "neg_scores"):
-        _check_scores(fixture + ":" + key, z[key], out[key], train)
+    keys = ("pos_scores", "ref_scores", "neg_scores")
+    if train:
+        for key in keys:
+            _check_scores(fixture + ":" + key, z[key], out[key], True)
+    else:
+        n_flip = _check_eval_scores(fixture, z, out, model, sl, keys)
+        if n_flip:      # losses are functions of the free-running scores: compare them on the forced run
+            model.parity_hooks["force_prev_inds"] = reference_prev_inds(z["pos_scores"])
+            with torch.no_grad():
+                out = model(sl)
+            torch.cuda.synchronize()
     losses = {k_.split("/")[-1]: float(v) for k_, v in out["losses"].items()}
     assert abs(losses["pos_bce_loss"] - float(z["loss_pos_bce"][0])) <= LOSS_RTOL * abs(float(z["loss_pos_bce"][0]))
     w = 1000.0
@@ -79,7 +112,12 @@ def test_m4c_against_reference_golden(fixture):
     torch.cuda.synchronize()
     assert np.array_equal(out["ground_frame"].cpu().numpy(), z["ground_frame"])
     assert np.array_equal(out["ground_box"].cpu().numpy(), z["ground_box"])
-    _check_scores(fixture, z["pos_scores"], out["pos_scores"], False)
+    sl = sample_list(inp)
+    if _check_eval_scores(fixture, z, out, model, sl, ("pos_scores",)):
+        model.parity_hooks["force_prev_inds"] = reference_prev_inds(z["pos_scores"])
+        with torch.no_grad():
+            out = model(sl)
+        torch.cuda.synchronize()
     loss = float(list(out["losses"].values())[0])
     assert abs(loss - float(z["loss_pos_bce"][0])) <= LOSS_RTOL * abs(float(z["loss_pos_bce"][0]))
 

@@ -71,6 +71,7 @@ class _Lib:
                 "or `make -C vitxt_gqa_b200/csrc`. There is no CPU or PyTorch fallback for this path." % LIB_PATH)
         self.cdll = ctypes.CDLL(LIB_PATH)
         self.launches = 0
+        self.timing = None
         for name, (res, args) in PLAIN.items():
             fn = getattr(self.cdll, name)
             fn.restype, fn.argtypes = res, args
@@ -84,12 +85,31 @@ class _Lib:
 
     def _checked(self, name, fn):
         def call(*args):
+            rec = self.timing
+            if rec is not None:
+                import torch
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()          # torch's current stream == the stream every caller passes down
             rc = fn(*args)
             if rc != 0:
                 raise T2SLibraryError("%s failed (rc=%d): %s" % (name, rc, self.cdll.t2s_last_error().decode()))
             self.launches += 1
+            if rec is not None:
+                e1.record()
+                rec.append((name, args, e0, e1))
         call.__name__ = name
         return call
+
+    def start_timing(self):
+        """Measurement aid for bench.py: bracket every launch with CUDA events on the launching stream."""
+        self.timing = []
+
+    def stop_timing(self):
+        """-> [(entry point, args, milliseconds)] after synchronising."""
+        import torch
+        torch.cuda.synchronize()
+        rec, self.timing = self.timing or [], None
+        return [(n, a, e0.elapsed_time(e1)) for n, a, e0, e1 in rec]
 
 
 _LIB = None

@@ -613,15 +613,17 @@ class T2S(_FusionModelBase):
         ground_frame = torch.empty(B, self.frame_topk, device=dev, dtype=torch.int64)
         kk = min(self.ocr_topk, Of)
         ground_box = torch.empty(B, F * kk, 4, device=dev, dtype=torch.float32)
+        # test-only overrides; the device copies must stay referenced until the launch is enqueued
         pos_ovr = self.parity_hooks.get("pos_frame_topk")
         neg_ovr = self.parity_hooks.get("neg_frame_topk")
+        pos_ovr = pos_ovr.to(dev).float().contiguous() if pos_ovr is not None else None
+        neg_ovr = neg_ovr.to(dev).float().contiguous() if neg_ovr is not None else None
         dbg = self.parity_hooks.get("debug", False)
         dbg_f = torch.empty(B, F, device=dev) if dbg else None
         dbg_o = torch.empty(B, O, device=dev) if dbg else None
         L.temporal_select(_ptr(ws["sim"]), F + O, _ptr(ws["jm_ref"]), B, Lt, F, Of, _ptr(gf), _ptr(inp["frame_id"]),
                           _ptr(inp["temporal_id"]), self.frame_topk,
-                          _ptr(pos_ovr.to(dev).float().contiguous()) if pos_ovr is not None else None,
-                          _ptr(neg_ovr.to(dev).float().contiguous()) if neg_ovr is not None else None,
+                          _ptr(pos_ovr), _ptr(neg_ovr),
                           _ptr(ground_frame), _ptr(ws["jm_pos"]), _ptr(ws["jm_neg"]), _ptr(ws["slot"]), _ptr(dbg_f), st)
         L.spatial_select(_ptr(ws["sim"]), F + O, F, _ptr(ws["slot"]), _ptr(ws["jm_ref"]), B, Le, Lt + F, F, Of, _ptr(go),
                          _ptr(inp["ocr_bbox_coordinates"]), self.ocr_topk, 0, _ptr(ground_box), _ptr(ws["jm_pos"]),
@@ -641,9 +643,13 @@ class T2S(_FusionModelBase):
         else:
             ws["prev"].zero_()
             ws["prev"][:, 0] = int(self.answer_processor.BOS_IDX)
+            forced = self.parity_hooks.get("force_prev_inds")     # test-only teacher forcing of the feedback
+            forced = forced.to(dev) if forced is not None else None
             for t in range(T):     # greedy decode drives only the `pos` variant (reference t2s.py:353, Q15)
                 self._decode_rows(L, P, ws, "pos", jm["pos"], scores["pos"], B, Le, T, V, O, F, Lt, t, 1, st)
                 L.argmax_feedback(_ptr(scores["pos"]), N, B, T, t, 1, N, _ptr(ws["prev"]), T, None, st)
+                if forced is not None and t + 1 < T:
+                    ws["prev"][:, t + 1].copy_(forced[:, t + 1])
             for v in ("ref", "neg"):
                 self._decode_rows(L, P, ws, v, jm[v], scores[v], B, Le, T, V, O, F, Lt, 0, T, st)
         if dbg:
@@ -715,9 +721,13 @@ class M4C(_FusionModelBase):
         else:
             ws["prev"].zero_()
             ws["prev"][:, 0] = int(self.answer_processor.BOS_IDX)
+            forced = self.parity_hooks.get("force_prev_inds")
+            forced = forced.to(dev) if forced is not None else None
             for t in range(T):
                 self._decode_rows(L, P, ws, "pos", ws["jm_pos"], scores, B, Le, T, V, O, 1, Lt, t, 1, st)
                 L.argmax_feedback(_ptr(scores), N, B, T, t, 1, N, _ptr(ws["prev"]), T, None, st)
+                if forced is not None and t + 1 < T:
+                    ws["prev"][:, t + 1].copy_(forced[:, t + 1])
         return {
             "pos_scores": scores, "ground_box": ground_box, "ground_frame": inp["middel_frame_id"],
             "frame_topk": torch.tensor(self.frame_topk, device=dev), "ocr_topk": torch.tensor(self.ocr_topk, device=dev),
