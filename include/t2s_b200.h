@@ -28,6 +28,7 @@ extern "C" {
 #define T2S_GEMM_GELU 1     /* erf-GELU after bias (BertIntermediate, modeling_bert.gelu)           */
 #define T2S_GEMM_OUT_F32 2  /* bf16 GEMM: store C as fp32 instead of bf16                           */
 #define T2S_GEMM_RES_F32 4  /* bf16 GEMM: residual operand is fp32 instead of bf16                  */
+#define T2S_GEMM_OUT_SPLIT 8 /* bf16 GEMM: store C as bf16 hi|lo, hi at [.,0..N), lo at [.,N..2N)       */
 
 int t2s_abi_version(void);
 const char* t2s_last_error(void);
@@ -41,6 +42,19 @@ int t2s_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, co
                   const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K,
                   int flags, int block_n, void* stream);
 
+/* K1x "bf16x3": fp32-class contraction on the bf16 tensor pipe for the grounding chain (TextBert
+ * t2s.py:538, obj/OCR encoders t2s.py:211,248, QTV t2s.py:423), whose top-k indices must match the fp32
+ * reference.  A [M,2K] and W [N,2K] hold fp32 values split as bf16 hi|lo (lo at column K; see
+ * t2s_split_bf16); the kernel accumulates hi.hi + hi.lo + lo.hi in fp32 (error ~2^-17 relative per product).
+ * K % 64 == 0.  Same epilogues as t2s_gemm_bf16. */
+int t2s_gemm_bf16x3(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                    const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K,
+                    int flags, int block_n, void* stream);
+/* fp32 rows [rows,K] -> bf16 hi|lo rows [rows,2K']: hi = bf16(x) at column c, lo = bf16(x - hi) at column
+ * lo_off + c; columns K..lo_off of both halves are zero-filled (lo_off >= K, multiple of 8). */
+int t2s_split_bf16(const float* x, long long ldx, int rows, int K, int lo_off, void* out, long long ldo,
+                   void* stream);
+
 /* K1f same contraction in fp32 on the FMA pipes (grounding chain: TextBert t2s.py:538, obj/OCR
  * encoders t2s.py:211,248, QTV t2s.py:423, Grounding_Module.q_linear t2s.py:472). K % 4 == 0.
  * a_rows_per_group > 0 gathers A row m from (m / per) * a_group_rows + a_row_off + m % per. */
@@ -52,7 +66,8 @@ int t2s_gemm_f32(const float* A, long long lda, const float* W, long long ldw, c
  * Replaces BertSelfAttention matmul/+mask/softmax/matmul and the [B,1,L,L] masks of
  * models/t2s.py:413-419,533-534,609-618.  key_idx[b, 0..n_keys[b]) lists the valid key rows. */
 int t2s_attn_f32(const float* qkv, long long ld, int B, int L, int H, int heads, const int* key_idx,
-                 const int* n_keys, int key_stride, float* out, long long ldo, void* stream);
+                 const int* n_keys, int key_stride, float* out, long long ldo, void* out_split,
+                 long long ldo_split, void* stream);   /* out_split: optional bf16 hi|lo copy (lo at column H) */
 int t2s_attn_bf16(const void* qkv, long long ld, int B, int L, int H, int heads, const int* key_idx,
                   const int* n_keys, int key_stride, void* out, long long ldo, void* stream);
 /* decoder rows t0..t0+nq-1 (nq <= 16): valid encoder keys + causal decoder keys (t2s.py:574-579,609-615) */
@@ -77,6 +92,11 @@ int t2s_add_ln(const void* x, int x_bf16, long long ldx, const void* res, int re
                const float* gamma, const float* beta, float eps, int rows, int H, const float* tanh_base,
                long long ld_base, float* out32, long long ldo32, void* out16, long long ldo16,
                int rows_per_group, int out_group_rows, int out_row_off, void* stream);
+/* same, with out16 written as bf16 hi|lo (lo at column H) -- the operand format of t2s_gemm_bf16x3 */
+int t2s_add_ln_split(const void* x, int x_bf16, long long ldx, const void* res, int res_bf16, long long ldr,
+                     const float* gamma, const float* beta, float eps, int rows, int H, const float* tanh_base,
+                     long long ld_base, float* out32, long long ldo32, void* out16, long long ldo16,
+                     int rows_per_group, int out_group_rows, int out_row_off, void* stream);
 /* K3  LN(h) + LN(W2 . bbox + b2)  (models/t2s.py:246-252) */
 int t2s_ocr_finish(const float* h, long long ldh, const float* bbox, const float* w2, const float* b2,
                    const float* g1, const float* be1, const float* g2, const float* be2, float eps, int rows,

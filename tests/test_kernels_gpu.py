@@ -101,6 +101,70 @@ def test_gemm_bf16_strided_rows(L):
     assert S[:, t0, V:].abs().max().item() == 0 and S[:, :t0].abs().max().item() == 0
 
 
+# ------------------------------------------------------------------------------- K1x bf16x3 GEMM
+def _split(x, kp=None):
+    k = x.shape[1]
+    kp = k if kp is None else kp
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    out = torch.zeros(x.shape[0], 2 * kp, device=x.device, dtype=torch.bfloat16)
+    out[:, :k], out[:, kp:kp + k] = hi, lo
+    return out
+
+
+@pytest.mark.parametrize("M,N,K,flags", [
+    (1280, 2304, 768, tlib.GEMM_OUT_F32), (1044, 768, 768, tlib.GEMM_OUT_F32 | tlib.GEMM_RES_F32),
+    (777, 3072, 768, tlib.GEMM_GELU | tlib.GEMM_OUT_SPLIT), (300, 768, 3072, tlib.GEMM_OUT_F32 | tlib.GEMM_RES_F32),
+    (64, 768, 1088, tlib.GEMM_OUT_F32), (4100, 768, 1024, tlib.GEMM_OUT_F32)])
+def test_gemm_bf16x3(L, M, N, K, flags):
+    """fp32-class accuracy from three bf16 tensor-core products (hi.hi + hi.lo + lo.hi)."""
+    A, W, bias = rnd(M, K, seed=21), rnd(N, K, scale=0.05, seed=22), rnd(N, seed=23)
+    res = rnd(M, N, seed=24) if flags & tlib.GEMM_RES_F32 else None
+    As, Ws = _split(A), _split(W)
+    split_out = bool(flags & tlib.GEMM_OUT_SPLIT)
+    C = torch.zeros(M, 2 * N if split_out else N, device="cuda", dtype=torch.bfloat16 if split_out else torch.float32)
+    L.gemm_bf16x3(P(As), 2 * K, P(Ws), 2 * K, P(bias), P(res), N, P(C), C.shape[1], M, N, K, flags, 0, stream())
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t() + bias.double()
+    if flags & tlib.GEMM_GELU:
+        ref = gelu(ref)
+    if res is not None:
+        ref = ref + res.double()
+    got = (C[:, :N].float() + C[:, N:].float()) if split_out else C
+    err = (got.double() - ref).abs().max().item()
+    scale = (A.abs().double() @ W.abs().double().t()).max().item()      # sum |a||w|: what the 2^-17 applies to
+    assert err <= 2 ** -15 * scale + 1e-6, (err, scale)
+    # and it really is fp32-class: a plain bf16 contraction of the same operands is >30x worse
+    bf = (A.to(torch.bfloat16).double() @ W.to(torch.bfloat16).double().t() + bias.double())
+    if not (flags & tlib.GEMM_GELU) and res is None:
+        assert err * 30 < (bf - ref).abs().max().item()
+
+
+def test_split_bf16(L):
+    rows, K, ldx, lo_off = 1000, 1074, 1076, 1088       # ragged K, 16-byte aligned row pitch
+    x = rnd(rows, ldx, seed=31)[:, :K]
+    out = torch.full((rows, 2 * lo_off), 7.0, device="cuda", dtype=torch.bfloat16)
+    L.split_bf16(P(x), ldx, rows, K, lo_off, P(out), 2 * lo_off, stream())
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, :K], x.to(torch.bfloat16))
+    assert torch.equal(out[:, lo_off:lo_off + K], (x - x.to(torch.bfloat16).float()).to(torch.bfloat16))
+    assert out[:, K:lo_off].abs().max().item() == 0 and out[:, lo_off + K:].abs().max().item() == 0
+
+
+def test_add_ln_split(L):
+    rows, H = 999, 768
+    x, r = rnd(rows, H, seed=32), rnd(rows, H, seed=33)
+    g, b = 1 + 0.1 * rnd(H, seed=34), 0.1 * rnd(H, seed=35)
+    o32 = torch.zeros(rows, H, device="cuda")
+    o16 = torch.zeros(rows, 2 * H, device="cuda", dtype=torch.bfloat16)
+    L.add_ln_split(P(x), 0, H, P(r), 0, H, P(g), P(b), 1e-12, rows, H, None, 0, P(o32), H, P(o16), 2 * H, 0, 0, 0, stream())
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm((x + r).double(), (H,), g.double(), b.double(), 1e-12).float()
+    assert (o32 - ref).abs().max().item() <= 1e-5
+    assert torch.equal(o16[:, :H], o32.to(torch.bfloat16))
+    assert torch.equal(o16[:, H:], (o32 - o32.to(torch.bfloat16).float()).to(torch.bfloat16))
+
+
 # ------------------------------------------------------------------------------- K1f fp32 GEMM
 @pytest.mark.parametrize("M,N,K", [(1280, 2304, 768), (100, 768, 3072), (4097, 768, 1088), (1, 768, 768), (960, 768, 16)])
 def test_gemm_f32(L, M, N, K):
@@ -154,10 +218,15 @@ def test_attn_f32(B, L):
     qkv = rnd(B * L, 3 * H, seed=11)
     mask, keys, nk = _keys(B, L, seed=B + L)
     out = torch.zeros(B * L, H, device="cuda")
-    lib.attn_f32(P(qkv), 3 * H, B, L, H, 12, P(keys), P(nk), L, P(out), H, stream())
+    osp = torch.zeros(B * L, 2 * H, device="cuda", dtype=torch.bfloat16)
+    lib.attn_f32(P(qkv), 3 * H, B, L, H, 12, P(keys), P(nk), L, P(out), H, P(osp), 2 * H, stream())
     torch.cuda.synchronize()
     ref = _attn_ref(qkv, B, L, H, keys, nk).float()
     assert (out - ref).abs().max().item() <= 2e-5        # fp32, softmax-normalised outputs of O(1)
+    # bf16 hi|lo copy: hi is the bf16 rounding, hi + lo reproduces the fp32 value to 2^-17 relative
+    assert torch.equal(osp[:, :H], out.to(torch.bfloat16))
+    rec = osp[:, :H].float() + osp[:, H:].float()
+    assert (rec - out).abs().max().item() <= 2 ** -16 * out.abs().max().item()
 
 
 @pytest.mark.parametrize("B,L", [(2, 64), (2, 52), (3, 200), (1, 1044)])

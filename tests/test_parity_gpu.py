@@ -133,10 +133,11 @@ def test_t2s_intermediates_against_oracle():
     dbg = ref["debug"]
     model = build_b200_model(d, sd)
     model.parity_hooks = {"debug": True, "pos_frame_topk": dbg["frame_pos_topk"], "neg_frame_topk": dbg["frame_neg_topk"]}
+    sl = sample_list(inp)
     with torch.no_grad():
-        out = model.forward(sample_list(inp))
+        out = model.forward(sl)
     torch.cuda.synchronize()
-    got = model.last_debug
+    got = dict(model.last_debug)
     Lt, F = d.txt_len, d.frames
     j0 = torch.cat([dbg["txt0"], dbg["obj0"], dbg["ocr0"]], 1)
     j1 = torch.cat([dbg["txt"], dbg["obj"], dbg["ocr"]], 1)
@@ -154,8 +155,7 @@ def test_t2s_intermediates_against_oracle():
     assert torch.equal(out["ground_frame"].cpu(), ref["ground_frame"])
     assert torch.equal(out["ground_box"].cpu(), ref["ground_box"])
     assert torch.equal(got["prev_inds"].cpu()[:, 0], dbg["prev_inds"][:, 0])
-    for key in ("pos_scores", "ref_scores", "neg_scores"):
-        _check_scores(key, ref[key], out[key], False)
+    _check_eval_scores("oracle", ref, out, model, sl, ("pos_scores", "ref_scores", "neg_scores"))
 
 
 def test_t2s_batch_invariance_at_baseline_shape():

@@ -28,7 +28,8 @@ constexpr int AF_SMEM = 4 * AF_BQ * AF_PITCH * 4;
 
 __global__ void __launch_bounds__(AF_THREADS, 2)
 attn_f32_kernel(const float* __restrict__ qkv, long long ld, int L, int H, const int* __restrict__ key_idx,
-                const int* __restrict__ n_keys, int key_stride, float* __restrict__ out, long long ldo, float scale) {
+                const int* __restrict__ n_keys, int key_stride, float* __restrict__ out, long long ldo,
+                __nv_bfloat16* __restrict__ out_split, long long ldos, float scale) {
     extern __shared__ __align__(16) float sm[];
     float(*Qs)[AF_PITCH] = reinterpret_cast<float(*)[AF_PITCH]>(sm);
     float(*Ks)[AF_PITCH] = reinterpret_cast<float(*)[AF_PITCH]>(sm + AF_BQ * AF_PITCH);
@@ -152,7 +153,16 @@ attn_f32_kernel(const float* __restrict__ qkv, long long ld, int L, int H, const
         if (r < L) {
             const float inv = 1.0f / l_i[i];
             float4 v = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
-            *reinterpret_cast<float4*>(out + ((long long)b * L + r) * ldo + h * DH + tx * 4) = v;
+            if (out) *reinterpret_cast<float4*>(out + ((long long)b * L + r) * ldo + h * DH + tx * 4) = v;
+            if (out_split) {     // bf16 hi|lo (lo at column H): operand format of t2s_gemm_bf16x3
+                uint2 hi, lo;
+                hi.x = pack_bf16x2(v.x, v.y); hi.y = pack_bf16x2(v.z, v.w);
+                lo.x = pack_bf16x2(v.x - bf16lo(hi.x), v.y - bf16hi(hi.x));
+                lo.y = pack_bf16x2(v.z - bf16lo(hi.y), v.w - bf16hi(hi.y));
+                __nv_bfloat16* op = out_split + ((long long)b * L + r) * ldos + h * DH + tx * 4;
+                *reinterpret_cast<uint2*>(op) = hi;
+                *reinterpret_cast<uint2*>(op + H) = lo;
+            }
         }
     }
 }
@@ -330,25 +340,32 @@ attn_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int L, int
 }
 
 // =============================================================================== decoder rows
-constexpr int AD_THREADS = 128, AD_MAXQ = 16;
+constexpr int AD_THREADS = 256, AD_MAXQ = 16, AD_WARPS = AD_THREADS / 32;
 
 // Queries: decoder positions t0 .. t0+nq-1 of sample b (rows of `qkv_dec`, [B, T, 3H] bf16).
 // Keys: the n_keys[b] valid encoder rows of `qkv_enc` ([B, L_enc, 3H]) followed by decoder
 // positions 0 .. t0+nq-1 (causal: query i sees decoder key j iff j <= t0+i).
+//
+// One CTA per (head, sample).  HBM/L2-bound: every K and V row of the head (128 B each) is read once
+// per chunk of QC queries, 8 lanes x 16 B per row so that a warp load covers four full 128-byte rows;
+// the key loops are unrolled four deep to keep 16 lines in flight per warp.  Scores are staged in
+// shared memory, softmax is one warp per query row (shuffle reductions), the P.V partial sums of
+// the 32 key slices are reduced by shuffle + shared memory.
+template <int QC>
 __global__ void __launch_bounds__(AD_THREADS)
 attn_dec_kernel(const __nv_bfloat16* __restrict__ qkv_enc, long long ld_enc, int L_enc,
                 const __nv_bfloat16* __restrict__ qkv_dec, long long ld_dec, int T, int H,
                 const int* __restrict__ key_idx, const int* __restrict__ n_keys, int key_stride,
                 int t0, int nq, __nv_bfloat16* __restrict__ out, long long ldo, float scale, int max_keys) {
     extern __shared__ __align__(16) float dsm[];
-    float* Qs = dsm;                          // [nq][64]
-    float* Ss = Qs + AD_MAXQ * DH;            // [nq][max_keys]
-    float* Os = Ss + AD_MAXQ * max_keys;      // [4 warps][nq][64]
-    __shared__ float red[33];
+    float* Qs = dsm;                                   // [AD_MAXQ][64], pre-scaled
+    float* Ss = Qs + AD_MAXQ * DH;                     // [QC][max_keys]
+    float* Os = Ss + QC * max_keys;                    // [AD_WARPS][QC][64]
+    int* s_idx = reinterpret_cast<int*>(Os + AD_WARPS * QC * DH);   // [max_keys] row offsets of the encoder keys
     const int b = blockIdx.y, h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = lane & 7, sub = lane >> 3;           // 16-byte chunk of the 128-byte row / row within the warp load
     const int n_enc = n_keys[b];
-    const int n_dec = t0 + nq;
-    const int nk = n_enc + n_dec;
+    const int nk = n_enc + t0 + nq;
     const int* kidx = key_idx + (long long)b * key_stride;
     const __nv_bfloat16* enc = qkv_enc + (long long)b * L_enc * ld_enc + h * DH;
     const __nv_bfloat16* dec = qkv_dec + (long long)b * T * ld_dec + h * DH;
@@ -357,81 +374,115 @@ attn_dec_kernel(const __nv_bfloat16* __restrict__ qkv_enc, long long ld_enc, int
         const int q = i / DH, d = i % DH;
         Qs[q * DH + d] = __bfloat162float(dec[(long long)(t0 + q) * ld_dec + d]) * scale;
     }
+    for (int k = tid; k < n_enc; k += AD_THREADS) s_idx[k] = kidx[k];
     __syncthreads();
-    // pass 1: one key per thread
-    for (int k = tid; k < nk; k += AD_THREADS) {
-        const bool is_dec = k >= n_enc;
-        const int j = k - n_enc;
-        const __nv_bfloat16* kp = (is_dec ? dec + (long long)j * ld_dec : enc + (long long)kidx[k] * ld_enc) + H;
-        float acc[AD_MAXQ];
+
+    auto row_ptr = [&](int k) -> const __nv_bfloat16* {
+        return k < n_enc ? enc + (long long)s_idx[k] * ld_enc : dec + (long long)(k - n_enc) * ld_dec;
+    };
+
+    for (int q0 = 0; q0 < nq; q0 += QC) {
+        // ---- scores: S[q][k] = q . K[k]
+        float qf[QC][8];
 #pragma unroll
-        for (int q = 0; q < AD_MAXQ; ++q) acc[q] = 0.f;
+        for (int q = 0; q < QC; ++q)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint4 kv = *reinterpret_cast<const uint4*>(kp + c * 8);
-            const float kf[8] = {bf16lo(kv.x), bf16hi(kv.x), bf16lo(kv.y), bf16hi(kv.y),
-                                 bf16lo(kv.z), bf16hi(kv.z), bf16lo(kv.w), bf16hi(kv.w)};
+            for (int e = 0; e < 8; ++e) qf[q][e] = (q0 + q < nq) ? Qs[(q0 + q) * DH + c * 8 + e] : 0.f;
+        for (int k0 = warp * 4; k0 < nk; k0 += AD_WARPS * 4 * 4) {     // warp-uniform trip count (shuffles inside)
+            const int kb = k0 + sub;
+            uint4 kv[4];
 #pragma unroll
-            for (int q = 0; q < AD_MAXQ; ++q) {
-                if (q < nq) {
-                    const float* qp = Qs + q * DH + c * 8;
+            for (int u = 0; u < 4; ++u) {
+                const int k = kb + u * AD_WARPS * 4;
+                kv[u] = k < nk ? *reinterpret_cast<const uint4*>(row_ptr(k) + H + c * 8) : make_uint4(0, 0, 0, 0);
+            }
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[q] = fmaf(qp[e], kf[e], acc[q]);
+            for (int u = 0; u < 4; ++u) {
+                const int k = kb + u * AD_WARPS * 4;
+                const float kf[8] = {bf16lo(kv[u].x), bf16hi(kv[u].x), bf16lo(kv[u].y), bf16hi(kv[u].y),
+                                     bf16lo(kv[u].z), bf16hi(kv[u].z), bf16lo(kv[u].w), bf16hi(kv[u].w)};
+#pragma unroll
+                for (int q = 0; q < QC; ++q) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) a = fmaf(qf[q][e], kf[e], a);
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    a += __shfl_xor_sync(0xffffffffu, a, 4);
+                    if (c == 0 && k < nk) {
+                        const int j = k - n_enc;          // decoder key position (causal)
+                        Ss[q * max_keys + k] = (j > t0 + q0 + q) ? -INFINITY : a;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- softmax: one warp per query row
+        for (int q = warp; q < QC; q += AD_WARPS) {
+            if (q0 + q >= nq) continue;
+            float* srow = Ss + q * max_keys;
+            float mx = -INFINITY;
+            for (int k = lane; k < nk; k += 32) mx = fmaxf(mx, srow[k]);
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int k = lane; k < nk; k += 32) {
+                const float p = expf(srow[k] - mx);
+                srow[k] = p;
+                sum += p;
+            }
+            const float inv = 1.0f / warp_sum(sum);
+            for (int k = lane; k < nk; k += 32) srow[k] *= inv;
+        }
+        __syncthreads();
+        // ---- O[q] = sum_k P[q][k] V[k]; this thread: dims c*8..c*8+7 of key slice (warp*4+sub) mod 32
+        float acc[QC][8];
+#pragma unroll
+        for (int q = 0; q < QC; ++q)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[q][e] = 0.f;
+        for (int k0 = warp * 4; k0 < nk; k0 += AD_WARPS * 4 * 4) {
+            const int kb = k0 + sub;
+            uint4 vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = kb + u * AD_WARPS * 4;
+                vv[u] = k < nk ? *reinterpret_cast<const uint4*>(row_ptr(k) + 2 * H + c * 8) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = kb + u * AD_WARPS * 4;
+                if (k < nk) {
+                    const float vf[8] = {bf16lo(vv[u].x), bf16hi(vv[u].x), bf16lo(vv[u].y), bf16hi(vv[u].y),
+                                         bf16lo(vv[u].z), bf16hi(vv[u].z), bf16lo(vv[u].w), bf16hi(vv[u].w)};
+#pragma unroll
+                    for (int q = 0; q < QC; ++q) {
+                        const float p = Ss[q * max_keys + k];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[q][e] = fmaf(p, vf[e], acc[q][e]);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int q = 0; q < AD_MAXQ; ++q)
-            if (q < nq) Ss[q * max_keys + k] = (is_dec && j > t0 + q) ? -INFINITY : acc[q];
-    }
-    __syncthreads();
-    // softmax per query row (block-wide reductions)
-    for (int q = 0; q < nq; ++q) {
-        float mx = -INFINITY;
-        for (int k = tid; k < nk; k += AD_THREADS) mx = fmaxf(mx, Ss[q * max_keys + k]);
-        mx = block_max(mx, red);
-        float sum = 0.f;
-        for (int k = tid; k < nk; k += AD_THREADS) {
-            const float p = expf(Ss[q * max_keys + k] - mx);
-            Ss[q * max_keys + k] = p;
-            sum += p;
-        }
-        sum = block_sum(sum, red);
-        const float inv = 1.0f / sum;
-        for (int k = tid; k < nk; k += AD_THREADS) Ss[q * max_keys + k] *= inv;
-    }
-    __syncthreads();
-    // pass 2: warps stride over keys, lanes own 2 of the 64 dims
-    float oacc[AD_MAXQ][2];
+        for (int q = 0; q < QC; ++q)
 #pragma unroll
-    for (int q = 0; q < AD_MAXQ; ++q) oacc[q][0] = oacc[q][1] = 0.f;
-    for (int k = warp; k < nk; k += 4) {
-        const bool is_dec = k >= n_enc;
-        const __nv_bfloat16* vp = (is_dec ? dec + (long long)(k - n_enc) * ld_dec : enc + (long long)kidx[k] * ld_enc) + 2 * H;
-        const uint32_t vv = *reinterpret_cast<const uint32_t*>(vp + lane * 2);
-        const float v0 = bf16lo(vv), v1 = bf16hi(vv);
+            for (int e = 0; e < 8; ++e) {
+                float a = acc[q][e];
+                a += __shfl_xor_sync(0xffffffffu, a, 8);
+                a += __shfl_xor_sync(0xffffffffu, a, 16);
+                if (sub == 0) Os[(warp * QC + q) * DH + c * 8 + e] = a;
+            }
+        __syncthreads();
+        for (int i = tid; i < QC * DH; i += AD_THREADS) {
+            const int q = i / DH, d = i % DH;
+            if (q0 + q < nq) {
+                float v = 0.f;
 #pragma unroll
-        for (int q = 0; q < AD_MAXQ; ++q) {
-            if (q < nq) {
-                const float p = Ss[q * max_keys + k];
-                oacc[q][0] = fmaf(p, v0, oacc[q][0]);
-                oacc[q][1] = fmaf(p, v1, oacc[q][1]);
+                for (int w = 0; w < AD_WARPS; ++w) v += Os[(w * QC + q) * DH + d];
+                out[((long long)b * T + t0 + q0 + q) * ldo + h * DH + d] = __float2bfloat16_rn(v);
             }
         }
-    }
-#pragma unroll
-    for (int q = 0; q < AD_MAXQ; ++q)
-        if (q < nq) {
-            Os[(warp * AD_MAXQ + q) * DH + lane * 2] = oacc[q][0];
-            Os[(warp * AD_MAXQ + q) * DH + lane * 2 + 1] = oacc[q][1];
-        }
-    __syncthreads();
-    for (int i = tid; i < nq * DH; i += AD_THREADS) {
-        const int q = i / DH, d = i % DH;
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) v += Os[(w * AD_MAXQ + q) * DH + d];
-        out[((long long)b * T + t0 + q) * ldo + h * DH + d] = __float2bfloat16_rn(v);
+        __syncthreads();     // Ss / Os are reused by the next query chunk
     }
 }
 
@@ -440,7 +491,12 @@ attn_dec_kernel(const __nv_bfloat16* __restrict__ qkv_enc, long long ld_enc, int
 using namespace t2s;
 
 extern "C" int t2s_attn_f32(const float* qkv, long long ld, int B, int L, int H, int heads, const int* key_idx,
-                            const int* n_keys, int key_stride, float* out, long long ldo, void* stream) {
+                            const int* n_keys, int key_stride, float* out, long long ldo, void* out_split,
+                            long long ldo_split, void* stream) {
+    if ((!out && !out_split) || (out_split && (ldo_split < 2LL * H || (ldo_split % 4)))) {
+        set_error("attn_f32: needs an output (split pitch >= 2H)");
+        return T2S_ERR_ARG;
+    }
     if (H != heads * DH || (ld % 4) || (ldo % 4)) { set_error("attn_f32: head size must be 64 (H %d heads %d)", H, heads); return T2S_ERR_SHAPE; }
     static bool attr = false;
     if (!attr) {
@@ -450,7 +506,8 @@ extern "C" int t2s_attn_f32(const float* qkv, long long ld, int B, int L, int H,
     }
     dim3 grid((L + AF_BQ - 1) / AF_BQ, heads, B);
     attn_f32_kernel<<<grid, AF_THREADS, AF_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
-        qkv, ld, L, H, key_idx, n_keys, key_stride, out, ldo, 0.125f);
+        qkv, ld, L, H, key_idx, n_keys, key_stride, out, ldo, reinterpret_cast<__nv_bfloat16*>(out_split), ldo_split,
+        0.125f);
     return launch_status("attn_f32");
 }
 
@@ -472,17 +529,27 @@ extern "C" int t2s_attn_dec(const void* qkv_enc, long long ld_enc, int L_enc, co
         return T2S_ERR_SHAPE;
     }
     const int max_keys = ((L_enc + T + 3) / 4) * 4;
-    const int smem = (AD_MAXQ * DH + AD_MAXQ * max_keys + 4 * AD_MAXQ * DH) * 4;
+    const int qc = nq == 1 ? 1 : 4;
+    const int smem = (AD_MAXQ * DH + qc * max_keys + AD_WARPS * qc * DH + max_keys) * 4;
     if (smem > 200 * 1024) { set_error("attn_dec: %d keys exceed the shared-memory score buffer", max_keys); return T2S_ERR_SHAPE; }
-    static int attr_bytes = 0;
-    if (smem > attr_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(attn_dec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static int attr_bytes[2] = {48 * 1024, 48 * 1024};
+    if (smem > attr_bytes[qc == 1 ? 0 : 1]) {
+        cudaError_t e = qc == 1
+            ? cudaFuncSetAttribute(attn_dec_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+            : cudaFuncSetAttribute(attn_dec_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { set_error("attn_dec attr: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_bytes = smem;
+        attr_bytes[qc == 1 ? 0 : 1] = smem;
     }
     dim3 grid(heads, B);
-    attn_dec_kernel<<<grid, AD_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(qkv_enc), ld_enc, L_enc, reinterpret_cast<const __nv_bfloat16*>(qkv_dec),
-        ld_dec, T, H, key_idx, n_keys, key_stride, t0, nq, reinterpret_cast<__nv_bfloat16*>(out), ldo, 0.125f, max_keys);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* pe = reinterpret_cast<const __nv_bfloat16*>(qkv_enc);
+    const __nv_bfloat16* pd = reinterpret_cast<const __nv_bfloat16*>(qkv_dec);
+    __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(out);
+    if (qc == 1)
+        attn_dec_kernel<1><<<grid, AD_THREADS, smem, st>>>(pe, ld_enc, L_enc, pd, ld_dec, T, H, key_idx, n_keys,
+                                                           key_stride, t0, nq, po, ldo, 0.125f, max_keys);
+    else
+        attn_dec_kernel<4><<<grid, AD_THREADS, smem, st>>>(pe, ld_enc, L_enc, pd, ld_dec, T, H, key_idx, n_keys,
+                                                           key_stride, t0, nq, po, ldo, 0.125f, max_keys);
     return launch_status("attn_dec");
 }

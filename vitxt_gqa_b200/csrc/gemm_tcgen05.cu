@@ -35,6 +35,7 @@ struct GemmEpi {
     const void* residual;
     long long ldc, ldr;
     int flags;
+    int c_lo_off;   // T2S_GEMM_OUT_SPLIT: column offset of the `lo` half of the bf16 hi|lo output
 };
 
 template <int BN>
@@ -50,7 +51,7 @@ struct GemmCfg {
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         GemmEpi ep, int M, int N, int K) {
+                         GemmEpi ep, int M, int N, int K, int k_lo_off) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -65,7 +66,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int num_n = (N + BN - 1) / BN;
     const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
     const int tiles = num_m * num_n;
-    const int kblocks = (K + GEMM_BK - 1) / GEMM_BK;
+    // k_lo_off > 0: "bf16x3" mode.  A and W hold fp32 values split as bf16 hi|lo (lo at column k_lo_off) and
+    // the k loop runs three segments -- hi.hi, hi.lo, lo.hi -- into the same fp32 accumulator (the lo.lo
+    // term is below 2^-16 relative and is dropped), giving fp32-class products on the bf16 tensor pipe.
+    const int kseg = (K + GEMM_BK - 1) / GEMM_BK;
+    const int kblocks = k_lo_off > 0 ? 3 * kseg : kseg;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -100,11 +105,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             for (int kb = 0; kb < kblocks; ++kb) {
                 if (lane == 0) {
+                    const int seg = kb / kseg, kk = (kb - seg * kseg) * GEMM_BK;
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(sa, &tmA, &full[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * GEMM_BK, n_blk * BN);
+                    tma_load_2d(sa, &tmA, &full[stage], kk + (seg == 2 ? k_lo_off : 0), m_blk * GEMM_BM);
+                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kk + (seg == 1 ? k_lo_off : 0), n_blk * BN);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -149,6 +155,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const bool gelu = ep.flags & T2S_GEMM_GELU;
         const bool out_f32 = ep.flags & T2S_GEMM_OUT_F32;
         const bool res_f32 = ep.flags & T2S_GEMM_RES_F32;
+        const bool out_split = ep.flags & T2S_GEMM_OUT_SPLIT;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -224,8 +231,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                 o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
                                 o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
                                 *reinterpret_cast<uint4*>(cp) = o;
+                                if (out_split) {       // lo = bf16(v - hi)
+                                    uint4 l;
+                                    l.x = pack_bf16x2(v[0] - bf16lo(o.x), v[1] - bf16hi(o.x));
+                                    l.y = pack_bf16x2(v[2] - bf16lo(o.y), v[3] - bf16hi(o.y));
+                                    l.z = pack_bf16x2(v[4] - bf16lo(o.z), v[5] - bf16hi(o.z));
+                                    l.w = pack_bf16x2(v[6] - bf16lo(o.w), v[7] - bf16hi(o.w));
+                                    *reinterpret_cast<uint4*>(cp + ep.c_lo_off) = l;
+                                }
                             } else {
-                                for (int j = 0; j < 8; ++j) if (col + j < N) cp[j] = __float2bfloat16_rn(v[j]);
+                                for (int j = 0; j < 8; ++j) if (col + j < N) {
+                                    const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
+                                    cp[j] = hi;
+                                    if (out_split) cp[ep.c_lo_off + j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi));
+                                }
                             }
                         }
                     }
@@ -300,7 +319,7 @@ int num_sms() {
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& ep, int M, int N, int K,
-                       cudaStream_t st) {
+                       int k_lo_off, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -314,7 +333,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     }
     const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K);
+    gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K, k_lo_off);
     return launch_status("gemm_bf16_tcgen05");
 }
 
@@ -322,24 +341,31 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
 
 using namespace t2s;
 
-extern "C" int t2s_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
-                             const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K,
-                             int flags, int block_n, void* stream) {
-    if (M <= 0 || N <= 0 || K <= 0) { set_error("gemm_bf16: bad shape %d %d %d", M, N, K); return T2S_ERR_SHAPE; }
+static int gemm_entry(const char* who, bool x3, const void* A, long long lda, const void* W, long long ldw,
+                      const float* bias, const void* residual, long long ldr, void* C, long long ldc, int M, int N,
+                      int K, int flags, int block_n, void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0) { set_error("%s: bad shape %d %d %d", who, M, N, K); return T2S_ERR_SHAPE; }
     if ((lda % 8) || (ldw % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) {
-        set_error("gemm_bf16: A/W need 16-byte aligned base and row pitch (lda %lld ldw %lld)", lda, ldw);
+        set_error("%s: A/W need 16-byte aligned base and row pitch (lda %lld ldw %lld)", who, lda, ldw);
         return T2S_ERR_ALIGN;
+    }
+    if (x3 && ((K % GEMM_BK) || lda < 2LL * K || ldw < 2LL * K)) {
+        set_error("%s: split operands need K %% 64 == 0 and row pitch >= 2K (K %d lda %lld ldw %lld)", who, K, lda, ldw);
+        return T2S_ERR_SHAPE;
     }
     const bool out_f32 = flags & T2S_GEMM_OUT_F32;
+    const bool out_split = flags & T2S_GEMM_OUT_SPLIT;
+    if (out_f32 && out_split) { set_error("%s: OUT_F32 and OUT_SPLIT are exclusive", who); return T2S_ERR_ARG; }
     if ((ldc % (out_f32 ? 4 : 8)) || (reinterpret_cast<uintptr_t>(C) & 15)) {
-        set_error("gemm_bf16: C needs 16-byte aligned base and row pitch (ldc %lld)", ldc);
+        set_error("%s: C needs 16-byte aligned base and row pitch (ldc %lld)", who, ldc);
         return T2S_ERR_ALIGN;
     }
+    if (out_split && ((N % 8) || ldc < 2LL * N)) { set_error("%s: OUT_SPLIT needs N %% 8 == 0 and ldc >= 2N", who); return T2S_ERR_SHAPE; }
     if (residual && ((ldr % ((flags & T2S_GEMM_RES_F32) ? 4 : 8)) || (reinterpret_cast<uintptr_t>(residual) & 15))) {
-        set_error("gemm_bf16: residual alignment (ldr %lld)", ldr);
+        set_error("%s: residual alignment (ldr %lld)", who, ldr);
         return T2S_ERR_ALIGN;
     }
-    if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) { set_error("gemm_bf16: bias alignment"); return T2S_ERR_ALIGN; }
+    if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) { set_error("%s: bias alignment", who); return T2S_ERR_ALIGN; }
     int bn = block_n;
     if (bn == 0) {
         // largest tile that still gives every SM work; small problems take the narrow tile
@@ -348,17 +374,31 @@ extern "C" int t2s_gemm_bf16(const void* A, long long lda, const void* W, long l
         else if (mt * ((N + 127) / 128) >= num_sms()) bn = 128;
         else bn = 64;
     }
+    const int kcols = x3 ? 2 * K : K;      // columns the tensor maps may touch
     CUtensorMap ta, tb;
-    int rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM);
+    int rc = make_tmap_bf16(&ta, A, M, kcols, lda, GEMM_BM);
     if (rc) return rc;
-    rc = make_tmap_bf16(&tb, W, N, K, ldw, bn);
+    rc = make_tmap_bf16(&tb, W, N, kcols, ldw, bn);
     if (rc) return rc;
-    GemmEpi ep{C, bias, residual, ldc, ldr, flags};
+    GemmEpi ep{C, bias, residual, ldc, ldr, flags, N};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int k_lo = x3 ? K : 0;
     switch (bn) {
-        case 256: return launch_gemm<256>(ta, tb, ep, M, N, K, st);
-        case 128: return launch_gemm<128>(ta, tb, ep, M, N, K, st);
-        case 64: return launch_gemm<64>(ta, tb, ep, M, N, K, st);
-        default: set_error("gemm_bf16: block_n must be 0, 64, 128 or 256"); return T2S_ERR_ARG;
+        case 256: return launch_gemm<256>(ta, tb, ep, M, N, K, k_lo, st);
+        case 128: return launch_gemm<128>(ta, tb, ep, M, N, K, k_lo, st);
+        case 64: return launch_gemm<64>(ta, tb, ep, M, N, K, k_lo, st);
+        default: set_error("%s: block_n must be 0, 64, 128 or 256", who); return T2S_ERR_ARG;
     }
+}
+
+extern "C" int t2s_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                             const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K,
+                             int flags, int block_n, void* stream) {
+    return gemm_entry("gemm_bf16", false, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, flags, block_n, stream);
+}
+
+extern "C" int t2s_gemm_bf16x3(const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                               const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K,
+                               int flags, int block_n, void* stream) {
+    return gemm_entry("gemm_bf16x3", true, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, flags, block_n, stream);
 }

@@ -39,6 +39,16 @@ __device__ __forceinline__ void store4_bf16(__nv_bfloat16* p, float4 v) {
     o.y = pack_bf16x2(v.z, v.w);
     *reinterpret_cast<uint2*>(p) = o;
 }
+// bf16 hi|lo split of 4 fp32 values: hi = bf16(v) at p, lo = bf16(v - hi) at p + lo_off
+__device__ __forceinline__ void store4_split(__nv_bfloat16* p, long long lo_off, float4 v) {
+    uint2 o, l;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    l.x = pack_bf16x2(v.x - bf16lo(o.x), v.y - bf16hi(o.x));
+    l.y = pack_bf16x2(v.z - bf16lo(o.y), v.w - bf16hi(o.y));
+    *reinterpret_cast<uint2*>(p) = o;
+    *reinterpret_cast<uint2*>(p + lo_off) = l;
+}
 
 // LayerNorm of one row held as nv float4 per lane (element index = (i*32 + lane)*4).
 __device__ __forceinline__ void warp_layernorm(float4 (&x)[NE_MAXV], int nv, int H, const float* __restrict__ gamma,
@@ -130,7 +140,7 @@ feat_concat_kernel(const float* __restrict__ f0, int d0, const float* __restrict
 }
 
 // ------------------------------------------------------------------------------- (residual +) LayerNorm
-template <typename TX, typename TR>
+template <typename TX, typename TR, bool SPLIT>
 __global__ void __launch_bounds__(NE_THREADS)
 add_ln_kernel(const TX* __restrict__ x, long long ldx, const TR* __restrict__ res, long long ldr,
               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int rows, int H,
@@ -162,7 +172,10 @@ add_ln_kernel(const TX* __restrict__ x, long long ldx, const TR* __restrict__ re
                 v[i].z = b.z + tanhf(v[i].z); v[i].w = b.w + tanhf(v[i].w);
             }
             if (out32) *reinterpret_cast<float4*>(out32 + orow * ldo32 + e) = v[i];
-            if (out16) store4_bf16(out16 + orow * ldo16 + e, v[i]);
+            if (out16) {
+                if (SPLIT) store4_split(out16 + orow * ldo16 + e, H, v[i]);
+                else store4_bf16(out16 + orow * ldo16 + e, v[i]);
+            }
         }
 }
 
@@ -254,6 +267,25 @@ __global__ void cast_rows_bf16_kernel(const float* __restrict__ x, long long ldx
     }
 }
 
+// fp32 rows -> bf16 hi|lo rows (operand format of t2s_gemm_bf16x3); zero-fills the K..lo_off padding
+__global__ void split_bf16_kernel(const float* __restrict__ x, long long ldx, int rows, int K, int lo_off,
+                                  __nv_bfloat16* __restrict__ out, long long ldo) {
+    const int c4n = lo_off / 4;
+    const long long n4 = (long long)rows * c4n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / c4n), c = (int)(i % c4n) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c + 4 <= K) v = *reinterpret_cast<const float4*>(x + (long long)row * ldx + c);
+        else if (c < K) {
+            const float* p = x + (long long)row * ldx + c;
+            v.x = p[0];
+            if (c + 1 < K) v.y = p[1];
+            if (c + 2 < K) v.z = p[2];
+        }
+        store4_split(out + (long long)row * ldo + c, lo_off, v);
+    }
+}
+
 static inline int rows_grid(int rows) { return (rows + NE_THREADS / 32 - 1) / (NE_THREADS / 32); }
 static inline bool h_ok(int H) { return H % 128 == 0 && H / 128 <= NE_MAXV && H > 0; }
 
@@ -280,29 +312,65 @@ extern "C" int t2s_feat_concat(const float* f0, int d0, const float* f1, int d1,
     return launch_status("feat_concat");
 }
 
-extern "C" int t2s_add_ln(const void* x, int x_bf16, long long ldx, const void* res, int res_bf16, long long ldr,
-                          const float* gamma, const float* beta, float eps, int rows, int H, const float* tanh_base,
-                          long long ld_base, float* out32, long long ldo32, void* out16, long long ldo16,
-                          int rows_per_group, int out_group_rows, int out_row_off, void* stream) {
+static int add_ln_entry(bool split, const void* x, int x_bf16, long long ldx, const void* res, int res_bf16,
+                        long long ldr, const float* gamma, const float* beta, float eps, int rows, int H,
+                        const float* tanh_base, long long ld_base, float* out32, long long ldo32, void* out16,
+                        long long ldo16, int rows_per_group, int out_group_rows, int out_row_off, void* stream) {
     if (!h_ok(H) || rows <= 0) { set_error("add_ln: H %d must be a multiple of 128 <= 1024", H); return T2S_ERR_SHAPE; }
     if (!out32 && !out16) { set_error("add_ln: no output"); return T2S_ERR_ARG; }
+    if (split && (!out16 || ldo16 < 2LL * H)) { set_error("add_ln_split: needs out16 with row pitch >= 2H"); return T2S_ERR_ARG; }
     RowMap map{rows_per_group, out_group_rows, out_row_off};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = rows_grid(rows);
     __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(out16);
-#define T2S_LN_LAUNCH(TX, TR)                                                                                     \
-    add_ln_kernel<TX, TR><<<grid, NE_THREADS, 0, st>>>(reinterpret_cast<const TX*>(x), ldx,                       \
-                                                       reinterpret_cast<const TR*>(res), ldr, gamma, beta, eps,   \
-                                                       rows, H, tanh_base, ld_base, out32, ldo32, o16, ldo16, map)
-    if (x_bf16) {
-        if (res_bf16 || !res) T2S_LN_LAUNCH(__nv_bfloat16, __nv_bfloat16);
-        else T2S_LN_LAUNCH(__nv_bfloat16, float);
+#define T2S_LN_LAUNCH(TX, TR, SP)                                                                                 \
+    add_ln_kernel<TX, TR, SP><<<grid, NE_THREADS, 0, st>>>(reinterpret_cast<const TX*>(x), ldx,                   \
+                                                           reinterpret_cast<const TR*>(res), ldr, gamma, beta,    \
+                                                           eps, rows, H, tanh_base, ld_base, out32, ldo32, o16,   \
+                                                           ldo16, map)
+    if (split) {
+        if (x_bf16) { set_error("add_ln_split: fp32 input only"); return T2S_ERR_ARG; }
+        if (res_bf16 && res) T2S_LN_LAUNCH(float, __nv_bfloat16, true);
+        else T2S_LN_LAUNCH(float, float, true);
+    } else if (x_bf16) {
+        if (res_bf16 || !res) T2S_LN_LAUNCH(__nv_bfloat16, __nv_bfloat16, false);
+        else T2S_LN_LAUNCH(__nv_bfloat16, float, false);
     } else {
-        if (res_bf16 && res) T2S_LN_LAUNCH(float, __nv_bfloat16);
-        else T2S_LN_LAUNCH(float, float);
+        if (res_bf16 && res) T2S_LN_LAUNCH(float, __nv_bfloat16, false);
+        else T2S_LN_LAUNCH(float, float, false);
     }
 #undef T2S_LN_LAUNCH
     return launch_status("add_ln");
+}
+
+extern "C" int t2s_add_ln(const void* x, int x_bf16, long long ldx, const void* res, int res_bf16, long long ldr,
+                          const float* gamma, const float* beta, float eps, int rows, int H, const float* tanh_base,
+                          long long ld_base, float* out32, long long ldo32, void* out16, long long ldo16,
+                          int rows_per_group, int out_group_rows, int out_row_off, void* stream) {
+    return add_ln_entry(false, x, x_bf16, ldx, res, res_bf16, ldr, gamma, beta, eps, rows, H, tanh_base, ld_base, out32,
+                        ldo32, out16, ldo16, rows_per_group, out_group_rows, out_row_off, stream);
+}
+
+extern "C" int t2s_add_ln_split(const void* x, int x_bf16, long long ldx, const void* res, int res_bf16, long long ldr,
+                                const float* gamma, const float* beta, float eps, int rows, int H,
+                                const float* tanh_base, long long ld_base, float* out32, long long ldo32, void* out16,
+                                long long ldo16, int rows_per_group, int out_group_rows, int out_row_off, void* stream) {
+    return add_ln_entry(true, x, x_bf16, ldx, res, res_bf16, ldr, gamma, beta, eps, rows, H, tanh_base, ld_base, out32,
+                        ldo32, out16, ldo16, rows_per_group, out_group_rows, out_row_off, stream);
+}
+
+extern "C" int t2s_split_bf16(const float* x, long long ldx, int rows, int K, int lo_off, void* out, long long ldo,
+                              void* stream) {
+    if (rows <= 0 || K <= 0 || lo_off < K || (lo_off % 8) || ldo < 2LL * lo_off || (ldx % 4) || (ldo % 8)) {
+        set_error("split_bf16: bad shape (K %d lo_off %d ldx %lld ldo %lld)", K, lo_off, ldx, ldo);
+        return T2S_ERR_SHAPE;
+    }
+    const long long n4 = (long long)rows * (lo_off / 4);
+    int grid = (int)((n4 + 255) / 256);
+    if (grid > num_sms() * 16) grid = num_sms() * 16;
+    split_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, ldx, rows, K, lo_off, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+    return launch_status("split_bf16");
 }
 
 extern "C" int t2s_ocr_finish(const float* h, long long ldh, const float* bbox, const float* w2, const float* b2,

@@ -20,6 +20,7 @@ one 12-row pass with the final prev_inds (encoder rows never see decoder rows an
 decoder rows are causal: reference t2s.py:574-579,609-615).
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -203,6 +204,12 @@ class _FusionModelBase(BaseModel):
         self._ws = {}
         self.parity_hooks = {}     # test-only overrides, e.g. {"neg_frame_topk": tensor [B,F]}
         self.last_debug = {}
+        # arithmetic of the grounding chain (TextBert, obj/OCR encoders, QTV): "bf16x3" = fp32 operands split as
+        # bf16 hi|lo, three tcgen05 products per contraction (fp32-class, default); "fp32" = FMA-pipe GEMMs
+        self.grounding_precision = os.environ.get(
+            "T2S_B200_GROUNDING", str(self.config.get("b200_grounding_precision", "bf16x3")))
+        if self.grounding_precision not in ("bf16x3", "fp32"):
+            raise ValueError("b200_grounding_precision must be 'bf16x3' or 'fp32'")
 
     # ---------------------------------------------------------------- build (reference t2s.py:31-151)
     def build(self):
@@ -276,11 +283,25 @@ class _FusionModelBase(BaseModel):
     def _weights_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def _pack_layer(self, layer, bf16):
+    @staticmethod
+    def _split_w(w, k_pad=None):
+        """fp32 [N,K] -> bf16 hi|lo [N, 2*k_pad] (operand format of t2s_gemm_bf16x3), zero padded along K."""
+        w = w.detach().float()
+        n, k = w.shape
+        kp = k if k_pad is None else k_pad
+        hi = w.to(torch.bfloat16)
+        lo = (w - hi.float()).to(torch.bfloat16)
+        out = torch.zeros(n, 2 * kp, device=w.device, dtype=torch.bfloat16)
+        out[:, :k], out[:, kp:kp + k] = hi, lo
+        return out
+
+    def _pack_layer(self, layer, mode):
+        """mode: "bf16" (answer transformer), "bf16x3" (split operands) or "fp32"."""
         a = layer.attention
         wqkv = torch.cat([a.self.query.weight, a.self.key.weight, a.self.value.weight], 0).detach()
         bqkv = torch.cat([a.self.query.bias, a.self.key.bias, a.self.value.bias], 0).detach().float().contiguous()
-        cast = (lambda w: w.detach().to(torch.bfloat16).contiguous()) if bf16 else (lambda w: w.detach().float().contiguous())
+        cast = {"bf16": lambda w: w.detach().to(torch.bfloat16).contiguous(), "bf16x3": self._split_w,
+                "fp32": lambda w: w.detach().float().contiguous()}[mode]
         f32 = lambda t: t.detach().float().contiguous()
         return dict(
             wqkv=cast(wqkv), bqkv=bqkv,
@@ -291,7 +312,7 @@ class _FusionModelBase(BaseModel):
             ln2g=f32(layer.output.LayerNorm.weight), ln2b=f32(layer.output.LayerNorm.bias))
 
     def _pack(self, device):
-        key = (str(device),) + self._weights_key()
+        key = (str(device), self.grounding_precision) + self._weights_key()
         if self._packed is not None and self._packed_key == key:
             return self._packed
         f32 = lambda t: t.detach().float().contiguous()
@@ -302,16 +323,22 @@ class _FusionModelBase(BaseModel):
             return out
 
         P = {}
-        P["text"] = [self._pack_layer(l, False) for l in self.text_bert.encoder.layer]
+        gp = self.grounding_precision
+        x3 = gp == "bf16x3"
+        P["text"] = [self._pack_layer(l, gp) for l in self.text_bert.encoder.layer]
         if hasattr(self, "TransLayer"):
-            P["qtv"] = [self._pack_layer(l, False) for l in self.TransLayer.encoder.layer]
-        P["mmt"] = [self._pack_layer(l, True) for l in self.mmt.encoder.layer]
+            P["qtv"] = [self._pack_layer(l, gp) for l in self.TransLayer.encoder.layer]
+        P["mmt"] = [self._pack_layer(l, "bf16") for l in self.mmt.encoder.layer]
         k_obj = self.linear_obj_feat_to_mmt_in.weight.shape[1]
         k_ocr = self.linear_ocr_feat_to_mmt_in.weight.shape[1]
         P["k_obj"], P["k_ocr"] = k_obj, k_ocr
-        P["k_obj_pad"], P["k_ocr_pad"] = _round_up(k_obj, 16), _round_up(k_ocr, 16)
-        P["w_obj"] = padk(self.linear_obj_feat_to_mmt_in.weight, P["k_obj_pad"])
-        P["w_ocr"] = padk(self.linear_ocr_feat_to_mmt_in.weight, P["k_ocr_pad"])
+        P["k_obj_pad"], P["k_ocr_pad"] = _round_up(k_obj, 64 if x3 else 16), _round_up(k_ocr, 64 if x3 else 16)
+        if x3:
+            P["w_obj"] = self._split_w(self.linear_obj_feat_to_mmt_in.weight, P["k_obj_pad"])
+            P["w_ocr"] = self._split_w(self.linear_ocr_feat_to_mmt_in.weight, P["k_ocr_pad"])
+        else:
+            P["w_obj"] = padk(self.linear_obj_feat_to_mmt_in.weight, P["k_obj_pad"])
+            P["w_ocr"] = padk(self.linear_ocr_feat_to_mmt_in.weight, P["k_ocr_pad"])
         P["w_cls"] = self.classifier.module.weight.detach().to(torch.bfloat16).contiguous()
         P["w_ptr_q"] = self.ocr_ptr_net.query.weight.detach().to(torch.bfloat16).contiguous()
         P["w_ptr_k"] = self.ocr_ptr_net.key.weight.detach().to(torch.bfloat16).contiguous()
@@ -321,7 +348,7 @@ class _FusionModelBase(BaseModel):
 
     # ---------------------------------------------------------------- workspaces
     def _workspace(self, B, device, dims):
-        key = (B, str(device)) + tuple(sorted(dims.items()))
+        key = (B, str(device), self.grounding_precision) + tuple(sorted(dims.items()))
         ws = self._ws.get(key)
         if ws is not None:
             return ws
@@ -336,12 +363,12 @@ class _FusionModelBase(BaseModel):
         ws = dict(
             # fp32 grounding chain
             xt=torch.empty(B * Lt, H, **f32), xt2=torch.empty(B * Lt, H, **f32),
-            a_obj=torch.empty(B * F, _round_up(dims["k_obj"], 16), **f32),
-            a_ocr=torch.empty(B * O, _round_up(dims["k_ocr"], 16), **f32),
+            a_obj=torch.empty(B * F, dims["k_obj_pad"], **f32),
+            a_ocr=torch.empty(B * O, dims["k_ocr_pad"], **f32),
             h_obj=torch.empty(B * F, H, **f32), h_ocr=torch.empty(B * O, H, **f32),
             J0=torch.empty(Me, H, **f32), J1=torch.empty(Me, H, **f32),
             fx=torch.empty(Me, H, **f32), fqkv=torch.empty(Me, 3 * H, **f32), fctx=torch.empty(Me, H, **f32),
-            fh=torch.empty(Me, H, **f32), fx1=torch.empty(Me, H, **f32), fint=torch.empty(Me, 4 * H, **f32),
+            fh=torch.empty(Me, H, **f32), fx1=torch.empty(Me, H, **f32),
             jm_ref=torch.empty(B, Le, **f32), jm_pos=torch.zeros(B, Le, **f32), jm_neg=torch.zeros(B, Le, **f32),
             jm_txt=torch.empty(B, Lt, **f32),
             keys_txt=torch.empty(B, Lt, **i32), nk_txt=torch.empty(B, **i32),
@@ -364,28 +391,73 @@ class _FusionModelBase(BaseModel):
             prev=torch.zeros(B, T, device=device, dtype=torch.int64),
             loss_ws=torch.empty(int(_lib.get_lib().loss_workspace_bytes(B, T)), device=device, dtype=torch.uint8),
         )
+        if self.grounding_precision == "bf16x3":    # bf16 hi|lo operand buffers of t2s_gemm_bf16x3
+            ws.update(xs=torch.empty(Me, 2 * H, **b16), ctxs=torch.empty(Me, 2 * H, **b16),
+                      x1s=torch.empty(Me, 2 * H, **b16), inters=torch.empty(Me, 8 * H, **b16),
+                      a_obj_s=torch.empty(B * F, 2 * dims["k_obj_pad"], **b16),
+                      a_ocr_s=torch.empty(B * O, 2 * dims["k_ocr_pad"], **b16))
+        else:
+            ws.update(fint=torch.empty(Me, 4 * H, **f32))
         self._ws[key] = ws
         return ws
 
     # ---------------------------------------------------------------- kernel-level building blocks
     def _layer_f32(self, L, lw, x, M, rows_L, keys, nk, key_stride, ws, st, out, tanh_base=None, out16=None,
-                   remap=(0, 0, 0)):
-        """One post-LN BERT layer in fp32 over `M` rows grouped in samples of `rows_L`.  Final LN -> `out`."""
+                   remap=(0, 0, 0), first=True, feeds_next=False):
+        """One post-LN BERT layer of the grounding chain over `M` rows grouped in samples of `rows_L`; fp32
+        activations in and out (final LN -> `out`).  `first`: the layer input has no bf16 hi|lo copy in ws["xs"]
+        yet; `feeds_next`: the final LN also writes the hi|lo copy the next layer contracts with."""
         H = 768
         B = M // rows_L
-        qkv, ctx, h, x1, inter = ws["fqkv"], ws["fctx"], ws["fh"], ws["fx1"], ws["fint"]
-        L.gemm_f32(_ptr(x), H, _ptr(lw["wqkv"]), H, _ptr(lw["bqkv"]), None, 0, _ptr(qkv), 3 * H, M, 3 * H, H, 0,
-                   0, 0, 0, st)
-        L.attn_f32(_ptr(qkv), 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride, _ptr(ctx), H, st)
-        L.gemm_f32(_ptr(ctx), H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), _ptr(x), H, _ptr(h), H, M, H, H, 0, 0, 0, 0, st)
-        L.add_ln(_ptr(h), 0, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H, None, 0,
-                 _ptr(x1), H, None, 0, 0, 0, 0, st)
-        L.gemm_f32(_ptr(x1), H, _ptr(lw["wi"]), H, _ptr(lw["bi"]), None, 0, _ptr(inter), 4 * H, M, 4 * H, H,
-                   _lib.GEMM_GELU, 0, 0, 0, st)
-        L.gemm_f32(_ptr(inter), 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), _ptr(x1), H, _ptr(h), H, M, H,
-                   4 * H, 0, 0, 0, 0, st)
+        qkv, h, x1 = ws["fqkv"], ws["fh"], ws["fx1"]
+        F32, RES, GELU, SPLIT = _lib.GEMM_OUT_F32, _lib.GEMM_RES_F32, _lib.GEMM_GELU, _lib.GEMM_OUT_SPLIT
+        if self.grounding_precision == "bf16x3":
+            xs, ctxs, x1s, inters = ws["xs"], ws["ctxs"], ws["x1s"], ws["inters"]
+            if first:
+                L.split_bf16(_ptr(x), H, M, H, H, _ptr(xs), 2 * H, st)
+            L.gemm_bf16x3(_ptr(xs), 2 * H, _ptr(lw["wqkv"]), 2 * H, _ptr(lw["bqkv"]), None, 0, _ptr(qkv), 3 * H,
+                          M, 3 * H, H, F32, 0, st)
+            L.attn_f32(_ptr(qkv), 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride, None, H,
+                       _ptr(ctxs), 2 * H, st)
+            L.gemm_bf16x3(_ptr(ctxs), 2 * H, _ptr(lw["wo"]), 2 * H, _ptr(lw["bo"]), _ptr(x), H, _ptr(h), H,
+                          M, H, H, F32 | RES, 0, st)
+            L.add_ln_split(_ptr(h), 0, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H, None, 0,
+                           _ptr(x1), H, _ptr(x1s), 2 * H, 0, 0, 0, st)
+            L.gemm_bf16x3(_ptr(x1s), 2 * H, _ptr(lw["wi"]), 2 * H, _ptr(lw["bi"]), None, 0, _ptr(inters), 8 * H,
+                          M, 4 * H, H, GELU | SPLIT, 0, st)
+            L.gemm_bf16x3(_ptr(inters), 8 * H, _ptr(lw["wo2"]), 8 * H, _ptr(lw["bo2"]), _ptr(x1), H, _ptr(h), H,
+                          M, H, 4 * H, F32 | RES, 0, st)
+            if feeds_next:
+                assert out16 is None and tanh_base is None and remap == (0, 0, 0)
+                L.add_ln_split(_ptr(h), 0, H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H,
+                               None, 0, _ptr(out), H, _ptr(xs), 2 * H, 0, 0, 0, st)
+                return
+        else:
+            ctx, inter = ws["fctx"], ws["fint"]
+            L.gemm_f32(_ptr(x), H, _ptr(lw["wqkv"]), H, _ptr(lw["bqkv"]), None, 0, _ptr(qkv), 3 * H, M, 3 * H, H, 0,
+                       0, 0, 0, st)
+            L.attn_f32(_ptr(qkv), 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride, _ptr(ctx), H, None, 0, st)
+            L.gemm_f32(_ptr(ctx), H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), _ptr(x), H, _ptr(h), H, M, H, H, 0, 0, 0, 0, st)
+            L.add_ln(_ptr(h), 0, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H, None, 0,
+                     _ptr(x1), H, None, 0, 0, 0, 0, st)
+            L.gemm_f32(_ptr(x1), H, _ptr(lw["wi"]), H, _ptr(lw["bi"]), None, 0, _ptr(inter), 4 * H, M, 4 * H, H,
+                       GELU, 0, 0, 0, st)
+            L.gemm_f32(_ptr(inter), 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), _ptr(x1), H, _ptr(h), H, M, H,
+                       4 * H, 0, 0, 0, 0, st)
         L.add_ln(_ptr(h), 0, H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H,
                  _ptr(tanh_base), H, _ptr(out), H, _ptr(out16), H, remap[0], remap[1], remap[2], st)
+
+    def _linear_f32(self, L, P, ws, which, rows, bias, out, st):
+        """obj / OCR input projection (K = 1074 / 1004 padded) in the grounding-chain arithmetic."""
+        H = 768
+        a, kp, w = ws["a_" + which], P["k_%s_pad" % which], P["w_" + which]
+        if self.grounding_precision == "bf16x3":
+            a_s = ws["a_%s_s" % which]
+            L.split_bf16(_ptr(a), kp, rows, kp, kp, _ptr(a_s), 2 * kp, st)
+            L.gemm_bf16x3(_ptr(a_s), 2 * kp, _ptr(w), 2 * kp, _ptr(bias), None, 0, _ptr(out), H, rows, H, kp,
+                          _lib.GEMM_OUT_F32, 0, st)
+        else:
+            L.gemm_f32(_ptr(a), kp, _ptr(w), kp, _ptr(bias), None, 0, _ptr(out), H, rows, H, kp, 0, 0, 0, 0, st)
 
     def _text_bert(self, L, P, ws, inp, B, Lt, Le, st):
         """TextBert (reference t2s.py:529-545); last layer's LN lands in rows [b*Le, b*Le+Lt) of J0."""
@@ -400,7 +472,8 @@ class _FusionModelBase(BaseModel):
         for i, lw in enumerate(P["text"]):
             last = i == n - 1
             self._layer_f32(L, lw, x, B * Lt, Lt, ws["keys_txt"], ws["nk_txt"], Lt, ws, st,
-                            out=ws["J0"] if last else y, remap=(Lt, Le, 0) if last else (0, 0, 0))
+                            out=ws["J0"] if last else y, remap=(Lt, Le, 0) if last else (0, 0, 0),
+                            first=(i == 0), feeds_next=not last)
             x, y = y, x
 
     def _encode_obj_ocr(self, L, P, ws, inp, B, Lt, F, O, Le, st, m4c=False):
@@ -411,9 +484,7 @@ class _FusionModelBase(BaseModel):
         L.feat_concat(_ptr(vit), vit.shape[-1], None, 0, None if m4c else _ptr(inp["frame_id"]),
                       None if m4c else _ptr(f["frame_embeddings.weight"]), None, None, 50, B * n_obj,
                       _ptr(ws["a_obj"]), P["k_obj_pad"], P["k_obj_pad"], st)
-        L.gemm_f32(_ptr(ws["a_obj"]), P["k_obj_pad"], _ptr(P["w_obj"]), P["k_obj_pad"],
-                   _ptr(f["linear_obj_feat_to_mmt_in.bias"]), None, 0, _ptr(ws["h_obj"]), H, B * n_obj, H,
-                   P["k_obj_pad"], 0, 0, 0, 0, st)
+        self._linear_f32(L, P, ws, "obj", B * n_obj, f["linear_obj_feat_to_mmt_in.bias"], ws["h_obj"], st)
         L.add_ln(_ptr(ws["h_obj"]), 0, H, None, 0, 0, _ptr(f["obj_feat_layer_norm.weight"]),
                  _ptr(f["obj_feat_layer_norm.bias"]), LN_EPS_EMBED, B * n_obj, H, None, 0, _ptr(ws["J0"]), H, None, 0,
                  n_obj, Le, Lt, st)
@@ -422,9 +493,7 @@ class _FusionModelBase(BaseModel):
                       None if m4c else _ptr(inp["temporal_id"]), None if m4c else _ptr(f["temporal_position_embeddings.weight"]),
                       None if m4c else _ptr(inp["track_id"]), None if m4c else _ptr(f["track_position_embeddings.weight"]),
                       50, B * O, _ptr(ws["a_ocr"]), P["k_ocr_pad"], P["k_ocr_pad"], st)
-        L.gemm_f32(_ptr(ws["a_ocr"]), P["k_ocr_pad"], _ptr(P["w_ocr"]), P["k_ocr_pad"],
-                   _ptr(f["linear_ocr_feat_to_mmt_in.bias"]), None, 0, _ptr(ws["h_ocr"]), H, B * O, H,
-                   P["k_ocr_pad"], 0, 0, 0, 0, st)
+        self._linear_f32(L, P, ws, "ocr", B * O, f["linear_ocr_feat_to_mmt_in.bias"], ws["h_ocr"], st)
         L.ocr_finish(_ptr(ws["h_ocr"]), H, _ptr(inp["ocr_bbox_coordinates"]), _ptr(f["linear_ocr_bbox_to_mmt_in.weight"]),
                      _ptr(f["linear_ocr_bbox_to_mmt_in.bias"]), _ptr(f["ocr_feat_layer_norm.weight"]),
                      _ptr(f["ocr_feat_layer_norm.bias"]), _ptr(f["ocr_bbox_layer_norm.weight"]),
@@ -573,8 +642,8 @@ class T2S(_FusionModelBase):
         Le, H = Lt + F + O, 768
         P = self._pack(dev)
         variants = ("pos", "ref", "neg")
-        ws = self._workspace(B, dev, dict(Lt=Lt, F=F, O=O, T=T, V=V, k_obj=P["k_obj"], k_ocr=P["k_ocr"],
-                                          variants=variants))
+        ws = self._workspace(B, dev, dict(Lt=Lt, F=F, O=O, T=T, V=V, k_obj_pad=P["k_obj_pad"],
+                                          k_ocr_pad=P["k_ocr_pad"], variants=variants))
         st = torch.cuda.current_stream(dev).cuda_stream
         f = P["f32"]
 
@@ -595,7 +664,8 @@ class T2S(_FusionModelBase):
             last = i == n - 1
             out = ws["J1"] if last else (ws["fx"] if i % 2 == 0 else ws["fx2"])
             self._layer_f32(L, lw, x, B * Le, Le, ws["keys"]["ref"], ws["nk"]["ref"], Le, ws, st, out=out,
-                            tanh_base=ws["J0"] if last else None, out16=ws["X16"] if last else None)
+                            tanh_base=ws["J0"] if last else None, out16=ws["X16"] if last else None,
+                            first=(i == 0), feeds_next=not last)
             x = out
 
         # ---- grounding (K5)
@@ -685,8 +755,8 @@ class M4C(_FusionModelBase):
         Le, H = Lt + 1 + O, 768      # one object token: the middle frame (reference m4c.py:188,420)
         P = self._pack(dev)
         variants = ("pos",)
-        ws = self._workspace(B, dev, dict(Lt=Lt, F=1, O=O, T=T, V=V, k_obj=P["k_obj"], k_ocr=P["k_ocr"],
-                                          variants=variants))
+        ws = self._workspace(B, dev, dict(Lt=Lt, F=1, O=O, T=T, V=V, k_obj_pad=P["k_obj_pad"],
+                                          k_ocr_pad=P["k_ocr_pad"], variants=variants))
         st = torch.cuda.current_stream(dev).cuda_stream
         f = P["f32"]
         ones = torch.ones(B, 1, device=dev, dtype=torch.int64)
