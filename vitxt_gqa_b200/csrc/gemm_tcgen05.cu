@@ -16,7 +16,10 @@
 //               (`tfull[a]`).  Two accumulators (2 x BN TMEM columns) so the epilogue of
 //               tile i overlaps the main loop of tile i+1.
 //   warps 2..9  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> bias /
-//               erf-GELU / residual -> bf16 or fp32 -> 16-byte global stores.
+//               erf-GELU / residual -> bf16, fp32 or bf16 hi|lo -> per-warp 128B-swizzled
+//               shared-memory box (32 rows x 128 B) -> TMA store (full-line writes, clipped
+//               to the matrix bounds by the tensor map; a lane-per-row register layout would
+//               otherwise scatter 16-byte stores over 32 rows per instruction).
 // Tiles are walked n-fastest so the CTAs running concurrently share one A row-block
 // through L2 and A streams from HBM once.
 #include "common.cuh"
@@ -45,18 +48,20 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int TMEM_COLS = 2 * BN;     // 512 / 256 / 128: powers of two >= 32
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * 4096;    // one 32-row x 128-byte box per epilogue warp
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         GemmEpi ep, int M, int N, int K, int k_lo_off) {
+                         const __grid_constant__ CUtensorMap tmC, GemmEpi ep, int M, int N, int K, int k_lo_off) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;      // 1024-byte aligned (STAGE_BYTES is a multiple of 1024)
+    uint64_t* full = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
@@ -75,6 +80,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -150,100 +156,147 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ------------------------------------------------ epilogue (8 warps)
         const int ew = warp - 2;
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                // which half of the BN columns
-        constexpr int COLS_PER_WARP = BN / 2;
+        // BN >= 128: two warps per lane quarter split the columns; BN == 64: warps 0..3 take all 64 columns
+        constexpr int ACTIVE = BN >= 128 ? 8 : 4;
+        constexpr int COLS_PER_WARP = BN / (ACTIVE / 4);
+        const bool active = ew < ACTIVE;
+        const int half = ew >> 2;
         const bool gelu = ep.flags & T2S_GEMM_GELU;
         const bool out_f32 = ep.flags & T2S_GEMM_OUT_F32;
         const bool res_f32 = ep.flags & T2S_GEMM_RES_F32;
         const bool out_split = ep.flags & T2S_GEMM_OUT_SPLIT;
+        uint8_t* box = staging + ew * 4096;      // this warp's staging box: 32 rows x 128 B, 128B swizzle
+        uint8_t* my_row = box + lane * 128;
+        const int sw = lane & 7;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const int row = m_blk * GEMM_BM + quarter * 32 + lane;
+            const int row0 = m_blk * GEMM_BM + quarter * 32;
+            const int row = row0 + lane;
             const bool row_ok = row < M;
+            if (active) {
+                uint32_t lo_keep[16];            // OUT_SPLIT: lo half of the first chunk of a box
 #pragma unroll 1
-            for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
-                uint32_t r[32];
-                const int cw = half * COLS_PER_WARP + c0;
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cw, r);
-                tmem_ld_wait();
-                const int col0 = n_blk * BN + cw;
-                if (row_ok && col0 < N) {
+                for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
+                    uint32_t r[32];
+                    const int cw = half * COLS_PER_WARP + c0;
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cw, r);
+                    tmem_ld_wait();
+                    const int col0 = n_blk * BN + cw;
+                    if (col0 >= N) break;        // warp-uniform: the whole 32-column chunk is outside the matrix
+                    const bool full32 = col0 + 32 <= N;
+                    float v[32];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {      // 4 groups of 8 columns
-                        const int col = col0 + g * 8;
-                        if (col >= N) break;
-                        float v[8];
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (ep.bias) {
+                        if (full32) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-                        const bool full8 = col + 8 <= N;
-                        if (ep.bias) {
-                            if (full8) {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 4));
-                                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                            } else {
-                                for (int j = 0; j < 8; ++j) if (col + j < N) v[j] += __ldg(ep.bias + col + j);
-                            }
-                        }
-                        if (gelu) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-                        }
-                        if (ep.residual) {
-                            if (res_f32) {
-                                const float* rp = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + col;
-                                if (full8) {
-                                    const float4 a0 = *reinterpret_cast<const float4*>(rp);
-                                    const float4 a1 = *reinterpret_cast<const float4*>(rp + 4);
-                                    v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-                                    v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-                                } else {
-                                    for (int j = 0; j < 8; ++j) if (col + j < N) v[j] += rp[j];
-                                }
-                            } else {
-                                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + col;
-                                if (full8) {
-                                    const uint4 a = *reinterpret_cast<const uint4*>(rp);
-                                    v[0] += bf16lo(a.x); v[1] += bf16hi(a.x); v[2] += bf16lo(a.y); v[3] += bf16hi(a.y);
-                                    v[4] += bf16lo(a.z); v[5] += bf16hi(a.z); v[6] += bf16lo(a.w); v[7] += bf16hi(a.w);
-                                } else {
-                                    for (int j = 0; j < 8; ++j) if (col + j < N) v[j] += __bfloat162float(rp[j]);
-                                }
-                            }
-                        }
-                        if (out_f32) {
-                            float* cp = reinterpret_cast<float*>(ep.C) + (long long)row * ep.ldc + col;
-                            if (full8) {
-                                *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-                                *reinterpret_cast<float4*>(cp + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                            } else {
-                                for (int j = 0; j < 8; ++j) if (col + j < N) cp[j] = v[j];
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
                             }
                         } else {
-                            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(ep.C) + (long long)row * ep.ldc + col;
-                            if (full8) {
-                                uint4 o;
-                                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                                *reinterpret_cast<uint4*>(cp) = o;
-                                if (out_split) {       // lo = bf16(v - hi)
-                                    uint4 l;
-                                    l.x = pack_bf16x2(v[0] - bf16lo(o.x), v[1] - bf16hi(o.x));
-                                    l.y = pack_bf16x2(v[2] - bf16lo(o.y), v[3] - bf16hi(o.y));
-                                    l.z = pack_bf16x2(v[4] - bf16lo(o.z), v[5] - bf16hi(o.z));
-                                    l.w = pack_bf16x2(v[6] - bf16lo(o.w), v[7] - bf16hi(o.w));
-                                    *reinterpret_cast<uint4*>(cp + ep.c_lo_off) = l;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] += __ldg(ep.bias + col0 + j);
+                        }
+                    }
+                    if (gelu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    }
+                    if (ep.residual && row_ok) {
+                        if (res_f32) {
+                            const float* rp = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + col0;
+                            if (full32) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    const float4 a = *reinterpret_cast<const float4*>(rp + j);
+                                    v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
                                 }
                             } else {
-                                for (int j = 0; j < 8; ++j) if (col + j < N) {
-                                    const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
-                                    cp[j] = hi;
-                                    if (out_split) cp[ep.c_lo_off + j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi));
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] += rp[j];
+                            }
+                        } else {
+                            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + col0;
+                            if (full32) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    const uint4 a = *reinterpret_cast<const uint4*>(rp + j);
+                                    v[j] += bf16lo(a.x); v[j + 1] += bf16hi(a.x); v[j + 2] += bf16lo(a.y); v[j + 3] += bf16hi(a.y);
+                                    v[j + 4] += bf16lo(a.z); v[j + 5] += bf16hi(a.z); v[j + 6] += bf16lo(a.w); v[j + 7] += bf16hi(a.w);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] += __bfloat162float(rp[j]);
+                            }
+                        }
+                    }
+                    if (out_f32) {
+                        // one box = 32 rows x 32 fp32 columns; the previous store must have read the box
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            *reinterpret_cast<float4*>(my_row + ((c ^ sw) << 4)) =
+                                make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmC, box, col0, row0);
+                            tma_store_commit();
+                        }
+                    } else {
+                        // one box = 32 rows x 64 bf16 columns = two 32-column chunks
+                        const int hpos = (c0 >> 5) & 1;          // which half of the box this chunk fills
+                        uint32_t hi[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                        if (hpos == 0) {
+                            if (lane == 0) tma_store_wait_read<0>();
+                            __syncwarp();
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            *reinterpret_cast<uint4*>(my_row + (((hpos * 4 + c) ^ sw) << 4)) =
+                                make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                        const bool last_chunk = hpos == 1 || c0 + 32 >= COLS_PER_WARP || col0 + 32 >= N;
+                        if (last_chunk) {
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&tmC, box, col0 - hpos * 32, row0);
+                                tma_store_commit();
+                            }
+                        }
+                        if (out_split) {
+                            // lo = bf16(v - hi), stored ep.c_lo_off columns to the right; 32-column boxes reuse the
+                            // staging box after the hi store has read it (N % 64 == 0 is required by the host)
+                            uint32_t lo[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                lo[j] = pack_bf16x2(v[2 * j] - bf16lo(hi[j]), v[2 * j + 1] - bf16hi(hi[j]));
+                            if (hpos == 0) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) lo_keep[j] = lo[j];
+                            } else {
+                                if (lane == 0) tma_store_wait_read<0>();
+                                __syncwarp();
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    *reinterpret_cast<uint4*>(my_row + ((c ^ sw) << 4)) =
+                                        make_uint4(lo_keep[4 * c], lo_keep[4 * c + 1], lo_keep[4 * c + 2], lo_keep[4 * c + 3]);
+                                    *reinterpret_cast<uint4*>(my_row + (((4 + c) ^ sw) << 4)) =
+                                        make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                                }
+                                fence_proxy_async();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    tma_store_2d(&tmC, box, ep.c_lo_off + col0 - 32, row0);
+                                    tma_store_commit();
                                 }
                             }
                         }
@@ -256,6 +309,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (lane == 0) tma_store_wait_all<0>();      // global writes complete before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -283,27 +337,32 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2D bf16 row-major [rows, cols] with row pitch `ld` elements; box = box_rows x 64, 128B swizzle.
-static int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld,
-                          int box_rows) {
+// 2D row-major [rows, cols] tensor with row pitch `ld` elements; box = box_rows x box_cols (box_cols * esize == 128 B),
+// 128B swizzle.
+static int make_tmap_2d(CUtensorMap* tm, bool f32, const void* ptr, long long rows, long long cols, long long ld,
+                        int box_cols, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point unavailable");
         return T2S_ERR_DRIVER;
     }
+    const int es = f32 ? 4 : 2;
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * es};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed: CUresult %d (ptr %p rows %lld cols %lld ld %lld)", (int)r, ptr, rows,
                   cols, ld);
         return T2S_ERR_DRIVER;
     }
     return T2S_OK;
+}
+static int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+    return make_tmap_2d(tm, false, ptr, rows, cols, ld, GEMM_BK, box_rows);
 }
 
 int num_sms() {
@@ -318,8 +377,8 @@ int num_sms() {
 }
 
 template <int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& ep, int M, int N, int K,
-                       int k_lo_off, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmEpi& ep, int M,
+                       int N, int K, int k_lo_off, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -333,7 +392,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     }
     const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K, k_lo_off);
+    gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, ep, M, N, K, k_lo_off);
     return launch_status("gemm_bf16_tcgen05");
 }
 
@@ -360,7 +419,7 @@ static int gemm_entry(const char* who, bool x3, const void* A, long long lda, co
         set_error("%s: C needs 16-byte aligned base and row pitch (ldc %lld)", who, ldc);
         return T2S_ERR_ALIGN;
     }
-    if (out_split && ((N % 8) || ldc < 2LL * N)) { set_error("%s: OUT_SPLIT needs N %% 8 == 0 and ldc >= 2N", who); return T2S_ERR_SHAPE; }
+    if (out_split && ((N % 64) || ldc < 2LL * N)) { set_error("%s: OUT_SPLIT needs N %% 64 == 0 and ldc >= 2N", who); return T2S_ERR_SHAPE; }
     if (residual && ((ldr % ((flags & T2S_GEMM_RES_F32) ? 4 : 8)) || (reinterpret_cast<uintptr_t>(residual) & 15))) {
         set_error("%s: residual alignment (ldr %lld)", who, ldr);
         return T2S_ERR_ALIGN;
@@ -380,13 +439,17 @@ static int gemm_entry(const char* who, bool x3, const void* A, long long lda, co
     if (rc) return rc;
     rc = make_tmap_bf16(&tb, W, N, kcols, ldw, bn);
     if (rc) return rc;
+    // C is written by TMA stores of 32-row x 128-byte boxes (clipped to [M, N] / [M, 2N] by the map)
+    CUtensorMap tc;
+    rc = make_tmap_2d(&tc, out_f32, C, M, out_split ? 2LL * N : N, ldc, out_f32 ? 32 : 64, 32);
+    if (rc) return rc;
     GemmEpi ep{C, bias, residual, ldc, ldr, flags, N};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int k_lo = x3 ? K : 0;
     switch (bn) {
-        case 256: return launch_gemm<256>(ta, tb, ep, M, N, K, k_lo, st);
-        case 128: return launch_gemm<128>(ta, tb, ep, M, N, K, k_lo, st);
-        case 64: return launch_gemm<64>(ta, tb, ep, M, N, K, k_lo, st);
+        case 256: return launch_gemm<256>(ta, tb, tc, ep, M, N, K, k_lo, st);
+        case 128: return launch_gemm<128>(ta, tb, tc, ep, M, N, K, k_lo, st);
+        case 64: return launch_gemm<64>(ta, tb, tc, ep, M, N, K, k_lo, st);
         default: set_error("%s: block_n must be 0, 64, 128 or 256", who); return T2S_ERR_ARG;
     }
 }
