@@ -68,6 +68,10 @@ int t2s_gemm_f32(const float* A, long long lda, const float* W, long long ldw, c
 int t2s_attn_f32(const float* qkv, long long ld, int B, int L, int H, int heads, const int* key_idx,
                  const int* n_keys, int key_stride, float* out, long long ldo, void* out_split,
                  long long ldo_split, void* stream);   /* out_split: optional bf16 hi|lo copy (lo at column H) */
+/* fp32-class attention on the tensor pipe: q|k|v and the output are bf16 hi|lo pairs (lo_off = column offset of
+ * the lo half of qkv, >= 3H; output lo half at column H).  Same call sites as t2s_attn_f32. */
+int t2s_attn_x3(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads, const int* key_idx,
+                const int* n_keys, int key_stride, void* out_split, long long ldo, void* stream);
 int t2s_attn_bf16(const void* qkv, long long ld, int B, int L, int H, int heads, const int* key_idx,
                   const int* n_keys, int key_stride, void* out, long long ldo, void* stream);
 /* decoder rows t0..t0+nq-1 (nq <= 16): valid encoder keys + causal decoder keys (t2s.py:574-579,609-615) */

@@ -17,6 +17,7 @@ SCORES_MEAN_ABS = 5e-3
 FP32_CHAIN_ATOL = 2e-4     # joint [txt; frames; ocr] features after TextBert / encoders / QTV
 ARGMAX_MARGIN = 1e-1       # answer indices must agree wherever the reference's top1-top2 margin exceeds this
 LOSS_RTOL = 1e-2
+INFO_NCE_ATOL = 1e-2       # on the unweighted InfoNCE (temperature 0.1 amplifies cosine errors 10x)
 
 
 def load_golden(name):

@@ -229,6 +229,27 @@ def test_attn_f32(B, L):
     assert (rec - out).abs().max().item() <= 2 ** -16 * out.abs().max().item()
 
 
+@pytest.mark.parametrize("B,L", [(3, 20), (2, 52), (2, 200), (1, 1044)])
+def test_attn_x3(B, L):
+    """fp32-class attention from bf16 hi|lo operands: three tensor-core products per contraction."""
+    lib = tlib.get_lib()
+    H = 768
+    qkv = rnd(B * L, 3 * H, seed=15)
+    qkv[:, :2 * H] *= 1.7                      # |q.k|/8 up to ~15: exercises the exponent range of real runs
+    mask, keys, nk = _keys(B, L, seed=3 * B + L)
+    qs = _split(qkv)                           # [rows, 2 * 3H], lo at column 3H
+    out = torch.zeros(B * L, 2 * H, device="cuda", dtype=torch.bfloat16)
+    lib.attn_x3(P(qs), 6 * H, 3 * H, B, L, H, 12, P(keys), P(nk), L, P(out), 2 * H, stream())
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv, B, L, H, keys, nk)
+    got = out[:, :H].double() + out[:, H:].double()
+    err = (got - ref).abs().max().item()
+    # scores here reach |q.k|/8 ~ 15 with |q_i k_i| ~ 3: a 2^-17-relative product error moves the exponent by
+    # ~5e-5, hence the probabilities by the same relative amount (real runs have |q_i k_i| ~ 0.2: ~3e-6).
+    # bf16 attention on the same data is ~1e-2.
+    assert err <= 1.5e-4, err
+
+
 @pytest.mark.parametrize("B,L", [(2, 64), (2, 52), (3, 200), (1, 1044)])
 def test_attn_bf16(B, L):
     lib = tlib.get_lib()

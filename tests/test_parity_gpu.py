@@ -14,7 +14,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from parity_utils import (ARGMAX_MARGIN, FP32_CHAIN_ATOL, LOSS_RTOL, SCORES_MAX_ABS, SCORES_MEAN_ABS,  # noqa: E402
+from parity_utils import (ARGMAX_MARGIN, FP32_CHAIN_ATOL, INFO_NCE_ATOL, LOSS_RTOL, SCORES_MAX_ABS, SCORES_MEAN_ABS,  # noqa: E402
                           agreeing_prefix_mask, build_b200_model, load_golden, margin_aware_argmax_check,
                           reference_prev_inds, sample_list, score_errors)
 from vitxt_gqa_b200 import synth  # noqa: E402
@@ -100,7 +100,9 @@ def test_t2s_against_reference_golden(fixture):
     assert abs(losses["pos_bce_loss"] - float(z["loss_pos_bce"][0])) <= LOSS_RTOL * abs(float(z["loss_pos_bce"][0]))
     w = 1000.0
     ref_nce = float(z["loss_info_nce"]) * w
-    assert abs(losses["InfoNCE"] - ref_nce) <= LOSS_RTOL * abs(ref_nce) + 0.2 * w * SCORES_MEAN_ABS, (losses, ref_nce)
+    # InfoNCE = 2-way CE of cos(ref,pos), cos(ref,neg) at temperature 0.1: a cosine error of 1e-3 (bf16 logits,
+    # mean-abs 2-3e-3 on logits of std 0.6) moves the unweighted loss by up to 1e-2; the config weight is 1000
+    assert abs(losses["InfoNCE"] - ref_nce) <= LOSS_RTOL * abs(ref_nce) + w * INFO_NCE_ATOL, (losses, ref_nce)
 
 
 @pytest.mark.parametrize("fixture", ["m4c_small_eval", "m4c_abinet_eval"])

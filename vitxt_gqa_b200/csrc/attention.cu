@@ -10,6 +10,8 @@
 // key list (`key_idx[b, 0..n_keys[b])` = row indices of the valid keys inside the sample).
 //
 //   t2s_attn_f32   fp32 flash-style SIMT kernel (grounding chain: TextBert, QTV)
+//   t2s_attn_x3    fp32-class flash-style kernel on mma.sync with bf16 hi|lo operands (three products per
+//                  contraction): TextBert / QTV of the grounding chain
 //   t2s_attn_bf16  bf16 flash-style kernel on mma.sync m16n8k16, K/V staged in swizzled
 //                  shared memory by cp.async (encoder rows of the answer transformer)
 //   t2s_attn_dec   small-sequence kernel for the <=16 decoder rows: K/V of the valid encoder
@@ -339,6 +341,190 @@ attn_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int L, int
     }
 }
 
+// =============================================================================== bf16x3 mma.sync
+// fp32-class attention for the grounding chain (TextBert / QTV) on the tensor pipe.  q|k|v arrive as
+// bf16 hi|lo pairs (hi at column c, lo at column lo_off + c: the OUT_SPLIT format of t2s_gemm_bf16x3);
+// S = Qh.Kh + Qh.Kl + Ql.Kh and O = Ph.Vh + Ph.Vl + Pl.Vh with P split in registers, everything else
+// (scale, online softmax, accumulators) in fp32.  Per-product error ~2^-17 instead of 2^-8.
+constexpr int AX_SMEM = (2 * AB_BQ + 8 * AB_BK) * 128;     // Q hi/lo + double-buffered K hi/lo, V hi/lo = 80 KB
+
+__global__ void __launch_bounds__(AB_THREADS)
+attn_x3_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, int L, int H,
+               const int* __restrict__ key_idx, const int* __restrict__ n_keys, int key_stride,
+               __nv_bfloat16* __restrict__ out, long long ldo, float scale_log2) {
+    extern __shared__ __align__(128) uint8_t xsm[];
+    uint8_t* Qh = xsm;
+    uint8_t* Ql = Qh + AB_BQ * 128;
+    uint8_t* KV = Ql + AB_BQ * 128;            // [buf][Kh, Kl, Vh, Vl][64 rows x 128 B]
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AB_BQ;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nk = n_keys[b];
+    const int* kidx = key_idx + (long long)b * key_stride;
+    const __nv_bfloat16* base = qkv + (long long)b * L * ld;
+    const int ntiles = (nk + AB_BK - 1) / AB_BK;
+
+    for (int i = tid; i < AB_BQ * 8; i += AB_THREADS) {
+        const int r = i >> 3, c = i & 7;
+        const bool ok = q0 + r < L;
+        const __nv_bfloat16* src = base + (long long)(ok ? q0 + r : 0) * ld + h * DH + c * 8;
+        cp_async16(Qh + sw_off(r, c), src, ok);
+        cp_async16(Ql + sw_off(r, c), src + lo_off, ok);
+    }
+    auto load_kv = [&](int t, int buf) {
+        uint8_t* dst = KV + buf * (4 * AB_BK * 128);
+        for (int i = tid; i < AB_BK * 8; i += AB_THREADS) {
+            const int r = i >> 3, c = i & 7;
+            const bool ok = t * AB_BK + r < nk;
+            const long long row = ok ? kidx[t * AB_BK + r] : 0;
+            const __nv_bfloat16* src = base + row * ld + h * DH + c * 8;
+            const uint32_t o = sw_off(r, c);
+            cp_async16(dst + o, src + H, ok);
+            cp_async16(dst + AB_BK * 128 + o, src + H + lo_off, ok);
+            cp_async16(dst + 2 * AB_BK * 128 + o, src + 2 * H, ok);
+            cp_async16(dst + 3 * AB_BK * 128 + o, src + 2 * H + lo_off, ok);
+        }
+    };
+    if (ntiles > 0) load_kv(0, 0);
+    cp_async_commit();
+
+    float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[n][j] = 0.f;
+    uint32_t qh[4][4], ql[4][4];
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < ntiles) load_kv(t + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const uint8_t* Kh = KV + buf * (4 * AB_BK * 128);
+        const uint8_t* Kl = Kh + AB_BK * 128;
+        const uint8_t* Vh = Kl + AB_BK * 128;
+        const uint8_t* Vl = Vh + AB_BK * 128;
+        if (t == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int row = warp * 16 + (lane & 15);
+                const int chunk = ks * 2 + (lane >> 4);
+                ldmatrix_x4(qh[ks], smem_u32(Qh + sw_off(row, chunk)));
+                ldmatrix_x4(ql[ks], smem_u32(Ql + sw_off(row, chunk)));
+            }
+        }
+        float s[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[n][j] = 0.f;
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t kh[4], kl[4];
+                const int row = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+                const int chunk = ks * 2 + ((lane >> 3) & 1);
+                const uint32_t off = sw_off(row, chunk);
+                ldmatrix_x4(kh, smem_u32(Kh + off));
+                ldmatrix_x4(kl, smem_u32(Kl + off));
+                // small terms first, the dominant hi.hi product last
+                mma_bf16_16816(s[np * 2], ql[ks], kh[0], kh[1]);
+                mma_bf16_16816(s[np * 2 + 1], ql[ks], kh[2], kh[3]);
+                mma_bf16_16816(s[np * 2], qh[ks], kl[0], kl[1]);
+                mma_bf16_16816(s[np * 2 + 1], qh[ks], kl[2], kl[3]);
+                mma_bf16_16816(s[np * 2], qh[ks], kh[0], kh[1]);
+                mma_bf16_16816(s[np * 2 + 1], qh[ks], kh[2], kh[3]);
+            }
+        }
+        const int kbase = t * AB_BK + (lane & 3) * 2;
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int key = kbase + n * 8 + (j & 1);
+                float v = s[n][j] * scale_log2;
+                if (key >= nk) v = -INFINITY;
+                s[n][j] = v;
+                mx[j >> 1] = fmaxf(mx[j >> 1], v);
+            }
+        }
+        float corr[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float m_new = fmaxf(m_i[r], mx[r]);
+            corr[r] = exp2f(m_i[r] - m_new);
+            m_i[r] = m_new;
+        }
+        float rs[2] = {0.f, 0.f};
+        uint32_t ph[4][4], pl[4][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const float p0 = exp2f(s[n][0] - m_i[0]), p1 = exp2f(s[n][1] - m_i[0]);
+            const float p2 = exp2f(s[n][2] - m_i[1]), p3 = exp2f(s[n][3] - m_i[1]);
+            rs[0] += p0 + p1;
+            rs[1] += p2 + p3;
+            const int ks = n >> 1, hi = n & 1;
+            const uint32_t h01 = pack_bf16x2(p0, p1), h23 = pack_bf16x2(p2, p3);
+            ph[ks][hi * 2 + 0] = h01;
+            ph[ks][hi * 2 + 1] = h23;
+            pl[ks][hi * 2 + 0] = pack_bf16x2(p0 - bf16lo(h01), p1 - bf16hi(h01));
+            pl[ks][hi * 2 + 1] = pack_bf16x2(p2 - bf16lo(h23), p3 - bf16hi(h23));
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) l_i[r] = l_i[r] * corr[r] + rs[r];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            o[n][0] *= corr[0]; o[n][1] *= corr[0];
+            o[n][2] *= corr[1]; o[n][3] *= corr[1];
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {
+                uint32_t vh[4], vl[4];
+                const int row = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                const int chunk = dp * 2 + (lane >> 4);
+                const uint32_t off = sw_off(row, chunk);
+                ldmatrix_x4_trans(vh, smem_u32(Vh + off));
+                ldmatrix_x4_trans(vl, smem_u32(Vl + off));
+                mma_bf16_16816(o[dp * 2], pl[ks], vh[0], vh[1]);
+                mma_bf16_16816(o[dp * 2 + 1], pl[ks], vh[2], vh[3]);
+                mma_bf16_16816(o[dp * 2], ph[ks], vl[0], vl[1]);
+                mma_bf16_16816(o[dp * 2 + 1], ph[ks], vl[2], vl[3]);
+                mma_bf16_16816(o[dp * 2], ph[ks], vh[0], vh[1]);
+                mma_bf16_16816(o[dp * 2 + 1], ph[ks], vh[2], vh[3]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 1);
+        l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 2);
+    }
+    const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int row = q0 + warp * 16 + g + r * 8;
+        if (row < L) {
+            const float inv = l_i[r] > 0.f ? 1.0f / l_i[r] : 0.f;
+            __nv_bfloat16* op = out + ((long long)b * L + row) * ldo + h * DH + tq * 2;
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const float a = o[n][r * 2] * inv, c = o[n][r * 2 + 1] * inv;
+                const uint32_t hi = pack_bf16x2(a, c);
+                *reinterpret_cast<uint32_t*>(op + n * 8) = hi;
+                *reinterpret_cast<uint32_t*>(op + n * 8 + H) = pack_bf16x2(a - bf16lo(hi), c - bf16hi(hi));
+            }
+        }
+    }
+}
+
 // =============================================================================== decoder rows
 constexpr int AD_THREADS = 256, AD_MAXQ = 16, AD_WARPS = AD_THREADS / 32;
 
@@ -519,6 +705,26 @@ extern "C" int t2s_attn_bf16(const void* qkv, long long ld, int B, int L, int H,
         reinterpret_cast<const __nv_bfloat16*>(qkv), ld, L, H, key_idx, n_keys, key_stride,
         reinterpret_cast<__nv_bfloat16*>(out), ldo, 0.125f * 1.4426950408889634f);
     return launch_status("attn_bf16");
+}
+
+extern "C" int t2s_attn_x3(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads,
+                           const int* key_idx, const int* n_keys, int key_stride, void* out_split, long long ldo,
+                           void* stream) {
+    if (H != heads * DH || (ld % 8) || (lo_off % 8) || lo_off < 3 * H || ld < lo_off + 3 * H || ldo < 2LL * H || (ldo % 2)) {
+        set_error("attn_x3: bad layout (H %d heads %d ld %lld lo_off %d ldo %lld)", H, heads, ld, lo_off, ldo);
+        return T2S_ERR_SHAPE;
+    }
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(attn_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AX_SMEM);
+        if (e != cudaSuccess) { set_error("attn_x3 attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr = true;
+    }
+    dim3 grid((L + AB_BQ - 1) / AB_BQ, heads, B);
+    attn_x3_kernel<<<grid, AB_THREADS, AX_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), ld, lo_off, L, H, key_idx, n_keys, key_stride,
+        reinterpret_cast<__nv_bfloat16*>(out_split), ldo, 0.125f * 1.4426950408889634f);
+    return launch_status("attn_x3");
 }
 
 extern "C" int t2s_attn_dec(const void* qkv_enc, long long ld_enc, int L_enc, const void* qkv_dec, long long ld_dec,

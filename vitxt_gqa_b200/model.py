@@ -393,6 +393,7 @@ class _FusionModelBase(BaseModel):
         )
         if self.grounding_precision == "bf16x3":    # bf16 hi|lo operand buffers of t2s_gemm_bf16x3
             ws.update(xs=torch.empty(Me, 2 * H, **b16), ctxs=torch.empty(Me, 2 * H, **b16),
+                      qkvs=torch.empty(Me, 6 * H, **b16),
                       x1s=torch.empty(Me, 2 * H, **b16), inters=torch.empty(Me, 8 * H, **b16),
                       a_obj_s=torch.empty(B * F, 2 * dims["k_obj_pad"], **b16),
                       a_ocr_s=torch.empty(B * O, 2 * dims["k_ocr_pad"], **b16))
@@ -415,10 +416,11 @@ class _FusionModelBase(BaseModel):
             xs, ctxs, x1s, inters = ws["xs"], ws["ctxs"], ws["x1s"], ws["inters"]
             if first:
                 L.split_bf16(_ptr(x), H, M, H, H, _ptr(xs), 2 * H, st)
-            L.gemm_bf16x3(_ptr(xs), 2 * H, _ptr(lw["wqkv"]), 2 * H, _ptr(lw["bqkv"]), None, 0, _ptr(qkv), 3 * H,
-                          M, 3 * H, H, F32, 0, st)
-            L.attn_f32(_ptr(qkv), 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride, None, H,
-                       _ptr(ctxs), 2 * H, st)
+            qkvs = ws["qkvs"]      # q|k|v as bf16 hi|lo: [M, 2 * 3H]
+            L.gemm_bf16x3(_ptr(xs), 2 * H, _ptr(lw["wqkv"]), 2 * H, _ptr(lw["bqkv"]), None, 0, _ptr(qkvs), 6 * H,
+                          M, 3 * H, H, SPLIT, 0, st)
+            L.attn_x3(_ptr(qkvs), 6 * H, 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride,
+                      _ptr(ctxs), 2 * H, st)
             L.gemm_bf16x3(_ptr(ctxs), 2 * H, _ptr(lw["wo"]), 2 * H, _ptr(lw["bo"]), _ptr(x), H, _ptr(h), H,
                           M, H, H, F32 | RES, 0, st)
             L.add_ln_split(_ptr(h), 0, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H, None, 0,
