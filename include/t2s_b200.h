@@ -53,7 +53,8 @@ int t2s_gemm_bf16x3(const void* A, long long lda, const void* W, long long ldw, 
 /* fp32 rows [rows,K] -> bf16 hi|lo rows [rows,2K']: hi = bf16(x) at column c, lo = bf16(x - hi) at column
  * lo_off + c; columns K..lo_off of both halves are zero-filled (lo_off >= K, multiple of 8). */
 int t2s_split_bf16(const float* x, long long ldx, int rows, int K, int lo_off, void* out, long long ldo,
-                   void* stream);
+                   int rows_per_group, int in_group_rows, int in_row_off, void* stream);
+/* rows_per_group > 0 gathers input row r from (r / per) * in_group_rows + in_row_off + r % per */
 
 /* K1f same contraction in fp32 on the FMA pipes (grounding chain: TextBert t2s.py:538, obj/OCR
  * encoders t2s.py:211,248, QTV t2s.py:423, Grounding_Module.q_linear t2s.py:472). K % 4 == 0.
@@ -87,7 +88,8 @@ int t2s_bert_embed_ln(const long long* ids, int rows, int L, int H, const float*
  * (F.normalize + nn.Embedding + torch.cat of models/t2s.py:195-207 and 223-244) */
 int t2s_feat_concat(const float* f0, int d0, const float* f1, int d1, const long long* id0, const float* tab0,
                     const long long* id1, const float* tab1, int id_dim, int rows, float* out, long long ldo,
-                    int k_pad, void* stream);
+                    int k_pad, void* out_split, long long ldo_split, void* stream);
+/* out (fp32 rows) and/or out_split (bf16 hi|lo rows, lo at column k_pad: operand of t2s_gemm_bf16x3) */
 /* K4  y = LN(x (+ res)); optional epilogue y = tanh_base + tanh(y) (QTV residual, t2s.py:430-432);
  * fp32 and/or bf16 output; output rows remapped as (r / rows_per_group) * out_group_rows +
  * out_row_off + r % rows_per_group when rows_per_group > 0 (writes straight into the joint

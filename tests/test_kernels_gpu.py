@@ -144,7 +144,7 @@ def test_split_bf16(L):
     rows, K, ldx, lo_off = 1000, 1074, 1076, 1088       # ragged K, 16-byte aligned row pitch
     x = rnd(rows, ldx, seed=31)[:, :K]
     out = torch.full((rows, 2 * lo_off), 7.0, device="cuda", dtype=torch.bfloat16)
-    L.split_bf16(P(x), ldx, rows, K, lo_off, P(out), 2 * lo_off, stream())
+    L.split_bf16(P(x), ldx, rows, K, lo_off, P(out), 2 * lo_off, 0, 0, 0, stream())
     torch.cuda.synchronize()
     assert torch.equal(out[:, :K], x.to(torch.bfloat16))
     assert torch.equal(out[:, lo_off:lo_off + K], (x - x.to(torch.bfloat16).float()).to(torch.bfloat16))
@@ -314,13 +314,24 @@ def test_feat_concat(L):
     id1 = torch.randint(0, 4000, (rows,), device="cuda")
     t0, t1 = rnd(4000, 50, seed=3), rnd(4000, 50, seed=4)
     out = torch.full((rows, kp), float("nan"), device="cuda")
-    L.feat_concat(P(f0), 300, P(f1), 604, P(id0), P(t0), P(id1), P(t1), 50, rows, P(out), kp, kp, stream())
+    osp = torch.full((rows, 2 * kp), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.feat_concat(P(f0), 300, P(f1), 604, P(id0), P(t0), P(id1), P(t1), 50, rows, P(out), kp, kp, P(osp), 2 * kp, stream())
     torch.cuda.synchronize()
     F = torch.nn.functional
     ref = torch.cat([F.normalize(f0, dim=-1), F.normalize(f1, dim=-1), t0[id0], t1[id1],
                      torch.zeros(rows, kp - 1004, device="cuda")], -1)
     assert (out - ref).abs().max().item() <= 1e-6
     assert out[5, 300:904].abs().max().item() == 0
+    assert torch.equal(osp, _split(out))          # fused bf16 hi|lo copy == split of the fp32 rows
+
+
+def test_split_bf16_row_gather(L):
+    B, Le, Lt, H = 5, 52, 20, 768
+    J = rnd(B * Le, H, seed=41)
+    out = torch.zeros(B * Lt, 2 * H, device="cuda", dtype=torch.bfloat16)
+    L.split_bf16(P(J), H, B * Lt, H, H, P(out), 2 * H, Lt, Le, 0, stream())
+    torch.cuda.synchronize()
+    assert torch.equal(out, _split(J.view(B, Le, H)[:, :Lt].reshape(-1, H)))
 
 
 @pytest.mark.parametrize("x_bf16,res_kind,tanh,remap", [(0, None, False, False), (0, "f32", True, False),

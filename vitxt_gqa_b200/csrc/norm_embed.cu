@@ -108,14 +108,22 @@ bert_embed_ln_kernel(const long long* __restrict__ ids, int rows, int L, int H, 
 
 // ------------------------------------------------------------------------------- normalise + concat
 // out[r] = [ f0/max(|f0|,1e-12) | f1/max(|f1|,1e-12) | tab0[id0[r]] | tab1[id1[r]] | 0-pad ]  (fp32)
+__device__ __forceinline__ void put_split(__nv_bfloat16* o, int lo_off, int c, float v) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    o[c] = hi;
+    o[lo_off + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+// out16 != null: write the row as bf16 hi|lo (lo at column k_pad) instead of fp32 -- the operand format of
+// t2s_gemm_bf16x3, saving the fp32 round trip through HBM
 __global__ void __launch_bounds__(NE_THREADS)
 feat_concat_kernel(const float* __restrict__ f0, int d0, const float* __restrict__ f1, int d1,
                    const long long* __restrict__ id0, const float* __restrict__ tab0,
                    const long long* __restrict__ id1, const float* __restrict__ tab1, int id_dim, int rows,
-                   float* __restrict__ out, long long ldo, int k_pad) {
+                   float* __restrict__ out, long long ldo, int k_pad, __nv_bfloat16* __restrict__ out16, long long ldo16) {
     const int row = blockIdx.x * (NE_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
-    float* o = out + (long long)row * ldo;
+    float* o = out ? out + (long long)row * ldo : nullptr;
+    __nv_bfloat16* o16 = out16 ? out16 + (long long)row * ldo16 : nullptr;
     int col = 0;
     for (int seg = 0; seg < 2; ++seg) {
         const float* f = seg == 0 ? f0 : f1;
@@ -125,7 +133,11 @@ feat_concat_kernel(const float* __restrict__ f0, int d0, const float* __restrict
         float ss = 0.f;
         for (int e = lane; e < d; e += 32) { const float v = src[e]; ss = fmaf(v, v, ss); }
         const float denom = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);     // F.normalize: x / max(||x||, eps)
-        for (int e = lane; e < d; e += 32) o[col + e] = src[e] / denom;
+        for (int e = lane; e < d; e += 32) {
+            const float v = src[e] / denom;
+            if (o) o[col + e] = v;
+            if (o16) put_split(o16, k_pad, col + e, v);
+        }
         col += d;
     }
     for (int seg = 0; seg < 2; ++seg) {
@@ -133,10 +145,16 @@ feat_concat_kernel(const float* __restrict__ f0, int d0, const float* __restrict
         const float* tab = seg == 0 ? tab0 : tab1;
         if (!idp) continue;
         const float* src = tab + idp[row] * id_dim;
-        for (int e = lane; e < id_dim; e += 32) o[col + e] = src[e];
+        for (int e = lane; e < id_dim; e += 32) {
+            if (o) o[col + e] = src[e];
+            if (o16) put_split(o16, k_pad, col + e, src[e]);
+        }
         col += id_dim;
     }
-    for (int e = col + lane; e < k_pad; e += 32) o[e] = 0.f;
+    for (int e = col + lane; e < k_pad; e += 32) {
+        if (o) o[e] = 0.f;
+        if (o16) { o16[e] = __float2bfloat16_rn(0.f); o16[k_pad + e] = __float2bfloat16_rn(0.f); }
+    }
 }
 
 // ------------------------------------------------------------------------------- (residual +) LayerNorm
@@ -269,15 +287,16 @@ __global__ void cast_rows_bf16_kernel(const float* __restrict__ x, long long ldx
 
 // fp32 rows -> bf16 hi|lo rows (operand format of t2s_gemm_bf16x3); zero-fills the K..lo_off padding
 __global__ void split_bf16_kernel(const float* __restrict__ x, long long ldx, int rows, int K, int lo_off,
-                                  __nv_bfloat16* __restrict__ out, long long ldo) {
+                                  __nv_bfloat16* __restrict__ out, long long ldo, RowMap in_map) {
     const int c4n = lo_off / 4;
     const long long n4 = (long long)rows * c4n;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const int row = (int)(i / c4n), c = (int)(i % c4n) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c + 4 <= K) v = *reinterpret_cast<const float4*>(x + (long long)row * ldx + c);
+        const long long irow = in_map(row);
+        if (c + 4 <= K) v = *reinterpret_cast<const float4*>(x + irow * ldx + c);
         else if (c < K) {
-            const float* p = x + (long long)row * ldx + c;
+            const float* p = x + irow * ldx + c;
             v.x = p[0];
             if (c + 1 < K) v.y = p[1];
             if (c + 2 < K) v.z = p[2];
@@ -304,11 +323,15 @@ extern "C" int t2s_bert_embed_ln(const long long* ids, int rows, int L, int H, c
 
 extern "C" int t2s_feat_concat(const float* f0, int d0, const float* f1, int d1, const long long* id0, const float* tab0,
                                const long long* id1, const float* tab1, int id_dim, int rows, float* out, long long ldo,
-                               int k_pad, void* stream) {
+                               int k_pad, void* out_split, long long ldo_split, void* stream) {
     const int k = (f0 ? d0 : 0) + (f1 ? d1 : 0) + (id0 ? id_dim : 0) + (id1 ? id_dim : 0);
-    if (rows <= 0 || k > k_pad || k_pad > ldo) { set_error("feat_concat: bad widths k %d k_pad %d ldo %lld", k, k_pad, ldo); return T2S_ERR_SHAPE; }
+    if (rows <= 0 || k > k_pad || (out && k_pad > ldo) || (out_split && 2LL * k_pad > ldo_split) || (!out && !out_split)) {
+        set_error("feat_concat: bad widths k %d k_pad %d ldo %lld ldo_split %lld", k, k_pad, ldo, ldo_split);
+        return T2S_ERR_SHAPE;
+    }
     feat_concat_kernel<<<rows_grid(rows), NE_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        f0, d0, f1, d1, id0, tab0, id1, tab1, id_dim, rows, out, ldo, k_pad);
+        f0, d0, f1, d1, id0, tab0, id1, tab1, id_dim, rows, out, ldo, k_pad, reinterpret_cast<__nv_bfloat16*>(out_split),
+        ldo_split);
     return launch_status("feat_concat");
 }
 
@@ -360,7 +383,7 @@ extern "C" int t2s_add_ln_split(const void* x, int x_bf16, long long ldx, const 
 }
 
 extern "C" int t2s_split_bf16(const float* x, long long ldx, int rows, int K, int lo_off, void* out, long long ldo,
-                              void* stream) {
+                              int rows_per_group, int in_group_rows, int in_row_off, void* stream) {
     if (rows <= 0 || K <= 0 || lo_off < K || (lo_off % 8) || ldo < 2LL * lo_off || (ldx % 4) || (ldo % 8)) {
         set_error("split_bf16: bad shape (K %d lo_off %d ldx %lld ldo %lld)", K, lo_off, ldx, ldo);
         return T2S_ERR_SHAPE;
@@ -369,7 +392,8 @@ extern "C" int t2s_split_bf16(const float* x, long long ldx, int rows, int K, in
     int grid = (int)((n4 + 255) / 256);
     if (grid > num_sms() * 16) grid = num_sms() * 16;
     split_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        x, ldx, rows, K, lo_off, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+        x, ldx, rows, K, lo_off, reinterpret_cast<__nv_bfloat16*>(out), ldo,
+        RowMap{rows_per_group, in_group_rows, in_row_off});
     return launch_status("split_bf16");
 }
 

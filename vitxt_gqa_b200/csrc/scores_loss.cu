@@ -110,15 +110,24 @@ bce_partial_kernel(const float* __restrict__ scores, const float* __restrict__ t
     }
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
-__global__ void bce_final_kernel(const double* __restrict__ partial, int n, const float* __restrict__ loss_mask,
-                                 long long rows, float* __restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < n; ++i) s += partial[i];
-        float c = 0.f;
-        for (long long r = 0; r < rows; ++r) c += loss_mask[r];
-        out[0] = (float)(s / (double)fmaxf(c, 1.f));
+__global__ void __launch_bounds__(256)
+bce_final_kernel(const double* __restrict__ partial, int n, const float* __restrict__ loss_mask, long long rows,
+                 float* __restrict__ out) {
+    // one CTA: fixed-order strided partial sums + a shared-memory tree, so the result is run-to-run identical
+    __shared__ double sd[256];
+    __shared__ float sc[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+    float c = 0.f;
+    for (long long r = threadIdx.x; r < rows; r += 256) c += loss_mask[r];
+    sd[threadIdx.x] = s;
+    sc[threadIdx.x] = c;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) { sd[threadIdx.x] += sd[threadIdx.x + off]; sc[threadIdx.x] += sc[threadIdx.x + off]; }
+        __syncthreads();
     }
+    if (threadIdx.x == 0) out[0] = (float)(sd[0] / (double)fmaxf(sc[0], 1.f));
 }
 
 // ------------------------------------------------------------------------------- InfoNCE (per-sample 2-way)
@@ -170,7 +179,7 @@ using namespace t2s;
 extern "C" int t2s_ptr_score(const void* q, long long ldq, int B, int T, int t0, int nq, const void* keyp,
                              long long key_batch_stride, long long ldk, int O, int H, const float* mask,
                              long long mask_stride, float* scores, long long ld_scores, int V, void* stream) {
-    if (nq < 1 || nq > PS_MAXQ || (H % 256) || (ldk % 8) || t0 < 0 || t0 + nq > T) { set_error("ptr_score: bad arguments"); return T2S_ERR_SHAPE; }
+    if (nq < 1 || nq > PS_MAXQ || (H % 256) || H > 1024 || (ldk % 8) || t0 < 0 || t0 + nq > T) { set_error("ptr_score: bad arguments"); return T2S_ERR_SHAPE; }
     const size_t smem = (size_t)nq * H * sizeof(float);
     static size_t attr = 48 * 1024;
     if (smem > attr) {
@@ -203,7 +212,7 @@ extern "C" int t2s_pos_bce_loss(const float* scores, const float* targets, const
     const long long rows = (long long)B * T;
     const int grid = (int)(rows < 1024 ? rows : 1024);
     bce_partial_kernel<<<grid, 256, 0, st>>>(scores, targets, loss_mask, rows, N, reinterpret_cast<double*>(workspace));
-    bce_final_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const double*>(workspace), grid, loss_mask, rows, out);
+    bce_final_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const double*>(workspace), grid, loss_mask, rows, out);
     return launch_status("pos_bce_loss");
 }
 

@@ -21,14 +21,14 @@ _p, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_flo
 SIGNATURES = {
     "t2s_gemm_bf16": [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p],
     "t2s_gemm_bf16x3": [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p],
-    "t2s_split_bf16": [_p, _ll, _i, _i, _i, _p, _ll, _p],
+    "t2s_split_bf16": [_p, _ll, _i, _i, _i, _p, _ll, _i, _i, _i, _p],
     "t2s_gemm_f32": [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p],
     "t2s_attn_f32": [_p, _ll, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _p, _ll, _p],
     "t2s_attn_x3": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _p],
     "t2s_attn_bf16": [_p, _ll, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _p],
     "t2s_attn_dec": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _ll, _p],
     "t2s_bert_embed_ln": [_p, _i, _i, _i, _p, _p, _p, _p, _p, _f, _p, _ll, _p],
-    "t2s_feat_concat": [_p, _i, _p, _i, _p, _p, _p, _p, _i, _i, _p, _ll, _i, _p],
+    "t2s_feat_concat": [_p, _i, _p, _i, _p, _p, _p, _p, _i, _i, _p, _ll, _i, _p, _ll, _p],
     "t2s_add_ln": [_p, _i, _ll, _p, _i, _ll, _p, _p, _f, _i, _i, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p],
     "t2s_add_ln_split": [_p, _i, _ll, _p, _i, _ll, _p, _p, _f, _i, _i, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p],
     "t2s_ocr_finish": [_p, _ll, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _p, _ll, _i, _i, _i, _p],

@@ -363,8 +363,6 @@ class _FusionModelBase(BaseModel):
         ws = dict(
             # fp32 grounding chain
             xt=torch.empty(B * Lt, H, **f32), xt2=torch.empty(B * Lt, H, **f32),
-            a_obj=torch.empty(B * F, dims["k_obj_pad"], **f32),
-            a_ocr=torch.empty(B * O, dims["k_ocr_pad"], **f32),
             h_obj=torch.empty(B * F, H, **f32), h_ocr=torch.empty(B * O, H, **f32),
             J0=torch.empty(Me, H, **f32), J1=torch.empty(Me, H, **f32),
             fx=torch.empty(Me, H, **f32), fqkv=torch.empty(Me, 3 * H, **f32), fctx=torch.empty(Me, H, **f32),
@@ -398,7 +396,8 @@ class _FusionModelBase(BaseModel):
                       a_obj_s=torch.empty(B * F, 2 * dims["k_obj_pad"], **b16),
                       a_ocr_s=torch.empty(B * O, 2 * dims["k_ocr_pad"], **b16))
         else:
-            ws.update(fint=torch.empty(Me, 4 * H, **f32))
+            ws.update(fint=torch.empty(Me, 4 * H, **f32), a_obj=torch.empty(B * F, dims["k_obj_pad"], **f32),
+                      a_ocr=torch.empty(B * O, dims["k_ocr_pad"], **f32))
         self._ws[key] = ws
         return ws
 
@@ -415,7 +414,7 @@ class _FusionModelBase(BaseModel):
         if self.grounding_precision == "bf16x3":
             xs, ctxs, x1s, inters = ws["xs"], ws["ctxs"], ws["x1s"], ws["inters"]
             if first:
-                L.split_bf16(_ptr(x), H, M, H, H, _ptr(xs), 2 * H, st)
+                L.split_bf16(_ptr(x), H, M, H, H, _ptr(xs), 2 * H, 0, 0, 0, st)
             qkvs = ws["qkvs"]      # q|k|v as bf16 hi|lo: [M, 2 * 3H]
             L.gemm_bf16x3(_ptr(xs), 2 * H, _ptr(lw["wqkv"]), 2 * H, _ptr(lw["bqkv"]), None, 0, _ptr(qkvs), 6 * H,
                           M, 3 * H, H, SPLIT, 0, st)
@@ -449,17 +448,33 @@ class _FusionModelBase(BaseModel):
         L.add_ln(_ptr(h), 0, H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H,
                  _ptr(tanh_base), H, _ptr(out), H, _ptr(out16), H, remap[0], remap[1], remap[2], st)
 
-    def _linear_f32(self, L, P, ws, which, rows, bias, out, st):
-        """obj / OCR input projection (K = 1074 / 1004 padded) in the grounding-chain arithmetic."""
+    def _concat_linear(self, L, P, ws, which, rows, concat_args, bias, out, st):
+        """normalize + id-embedding + concat (t2s.py:195-207 / 223-244) feeding the obj / OCR input projection
+        (K = 1074 / 1004 zero padded) in the grounding-chain arithmetic."""
         H = 768
-        a, kp, w = ws["a_" + which], P["k_%s_pad" % which], P["w_" + which]
+        kp, w = P["k_%s_pad" % which], P["w_" + which]
         if self.grounding_precision == "bf16x3":
-            a_s = ws["a_%s_s" % which]
-            L.split_bf16(_ptr(a), kp, rows, kp, kp, _ptr(a_s), 2 * kp, st)
+            a_s = ws["a_%s_s" % which]      # concat written straight as bf16 hi|lo
+            L.feat_concat(*concat_args, rows, None, 0, kp, _ptr(a_s), 2 * kp, st)
             L.gemm_bf16x3(_ptr(a_s), 2 * kp, _ptr(w), 2 * kp, _ptr(bias), None, 0, _ptr(out), H, rows, H, kp,
                           _lib.GEMM_OUT_F32, 0, st)
         else:
+            a = ws["a_" + which]
+            L.feat_concat(*concat_args, rows, _ptr(a), kp, kp, None, 0, st)
             L.gemm_f32(_ptr(a), kp, _ptr(w), kp, _ptr(bias), None, 0, _ptr(out), H, rows, H, kp, 0, 0, 0, 0, st)
+
+    def _q_linear(self, L, P, ws, w, bias, name, B, Lt, Le, st):
+        """q_proj = q_linear(txt) over the question rows of the joint buffer J1 (reference t2s.py:472, m4c.py:365)."""
+        H = 768
+        if self.grounding_precision == "bf16x3":
+            if name not in P:
+                P[name] = self._split_w(w)
+            L.split_bf16(_ptr(ws["J1"]), H, B * Lt, H, H, _ptr(ws["xs"]), 2 * H, Lt, Le, 0, st)    # gathers the txt rows
+            L.gemm_bf16x3(_ptr(ws["xs"]), 2 * H, _ptr(P[name]), 2 * H, _ptr(bias), None, 0, _ptr(ws["qp"]), H,
+                          B * Lt, H, H, _lib.GEMM_OUT_F32, 0, st)
+        else:
+            L.gemm_f32(_ptr(ws["J1"]), H, _ptr(w), H, _ptr(bias), None, 0, _ptr(ws["qp"]), H, B * Lt, H, H, 0,
+                       Lt, Le, 0, st)
 
     def _text_bert(self, L, P, ws, inp, B, Lt, Le, st):
         """TextBert (reference t2s.py:529-545); last layer's LN lands in rows [b*Le, b*Le+Lt) of J0."""
@@ -483,19 +498,21 @@ class _FusionModelBase(BaseModel):
         H, f = 768, P["f32"]
         n_obj = 1 if m4c else F
         vit = inp["mid_img_feat"] if m4c else inp["video_feat"]
-        L.feat_concat(_ptr(vit), vit.shape[-1], None, 0, None if m4c else _ptr(inp["frame_id"]),
-                      None if m4c else _ptr(f["frame_embeddings.weight"]), None, None, 50, B * n_obj,
-                      _ptr(ws["a_obj"]), P["k_obj_pad"], P["k_obj_pad"], st)
-        self._linear_f32(L, P, ws, "obj", B * n_obj, f["linear_obj_feat_to_mmt_in.bias"], ws["h_obj"], st)
+        self._concat_linear(L, P, ws, "obj", B * n_obj,
+                            (_ptr(vit), vit.shape[-1], None, 0, None if m4c else _ptr(inp["frame_id"]),
+                             None if m4c else _ptr(f["frame_embeddings.weight"]), None, None, 50),
+                            f["linear_obj_feat_to_mmt_in.bias"], ws["h_obj"], st)
         L.add_ln(_ptr(ws["h_obj"]), 0, H, None, 0, 0, _ptr(f["obj_feat_layer_norm.weight"]),
                  _ptr(f["obj_feat_layer_norm.bias"]), LN_EPS_EMBED, B * n_obj, H, None, 0, _ptr(ws["J0"]), H, None, 0,
                  n_obj, Le, Lt, st)
         c0, c1 = inp["context_feature_0"], inp["context_feature_1"]
-        L.feat_concat(_ptr(c0), c0.shape[-1], _ptr(c1), c1.shape[-1],
-                      None if m4c else _ptr(inp["temporal_id"]), None if m4c else _ptr(f["temporal_position_embeddings.weight"]),
-                      None if m4c else _ptr(inp["track_id"]), None if m4c else _ptr(f["track_position_embeddings.weight"]),
-                      50, B * O, _ptr(ws["a_ocr"]), P["k_ocr_pad"], P["k_ocr_pad"], st)
-        self._linear_f32(L, P, ws, "ocr", B * O, f["linear_ocr_feat_to_mmt_in.bias"], ws["h_ocr"], st)
+        self._concat_linear(L, P, ws, "ocr", B * O,
+                            (_ptr(c0), c0.shape[-1], _ptr(c1), c1.shape[-1],
+                             None if m4c else _ptr(inp["temporal_id"]),
+                             None if m4c else _ptr(f["temporal_position_embeddings.weight"]),
+                             None if m4c else _ptr(inp["track_id"]),
+                             None if m4c else _ptr(f["track_position_embeddings.weight"]), 50),
+                            f["linear_ocr_feat_to_mmt_in.bias"], ws["h_ocr"], st)
         L.ocr_finish(_ptr(ws["h_ocr"]), H, _ptr(inp["ocr_bbox_coordinates"]), _ptr(f["linear_ocr_bbox_to_mmt_in.weight"]),
                      _ptr(f["linear_ocr_bbox_to_mmt_in.bias"]), _ptr(f["ocr_feat_layer_norm.weight"]),
                      _ptr(f["ocr_feat_layer_norm.bias"]), _ptr(f["ocr_bbox_layer_norm.weight"]),
@@ -672,8 +689,7 @@ class T2S(_FusionModelBase):
 
         # ---- grounding (K5)
         g = "Grounding_Module."
-        L.gemm_f32(_ptr(ws["J1"]), H, _ptr(f[g + "q_linear.weight"]), H, _ptr(f[g + "q_linear.bias"]), None, 0,
-                   _ptr(ws["qp"]), H, B * Lt, H, H, 0, Lt, Le, 0, st)
+        self._q_linear(L, P, ws, f[g + "q_linear.weight"], f[g + "q_linear.bias"], "q_linear", B, Lt, Le, st)
         L.question_pool(_ptr(ws["qp"]), B, Lt, H, _ptr(f[g + "self_attn.weight"]), _ptr(f[g + "self_attn.bias"]),
                         _ptr(ws["jm_ref"]), Le, _ptr(ws["gq"]), st)
         L.sim_scores(_ptr(ws["gq"]), _ptr(ws["J1"]), Le * H, H, Lt, F + O, H, B, _ptr(ws["sim"]), st)
@@ -771,8 +787,7 @@ class M4C(_FusionModelBase):
         ws["J1"].copy_(ws["J0"])
         L.cast_rows_bf16(_ptr(ws["J0"]), H, B * Le, H, _ptr(ws["X16"]), H, 0, 0, 0, st)
         g = "PostHoc."
-        L.gemm_f32(_ptr(ws["J1"]), H, _ptr(f[g + "q_linear.weight"]), H, _ptr(f[g + "q_linear.bias"]), None, 0,
-                   _ptr(ws["qp"]), H, B * Lt, H, H, 0, Lt, Le, 0, st)
+        self._q_linear(L, P, ws, f[g + "q_linear.weight"], f[g + "q_linear.bias"], "q_linear", B, Lt, Le, st)
         L.question_pool(_ptr(ws["qp"]), B, Lt, H, _ptr(f[g + "self_attn.weight"]), _ptr(f[g + "self_attn.bias"]),
                         _ptr(ws["jm_ref"]), Le, _ptr(ws["gq"]), st)
         L.sim_scores(_ptr(ws["gq"]), _ptr(ws["J1"]), Le * H, H, Lt + 1, O, H, B, _ptr(ws["sim"]), st)
