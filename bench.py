@@ -153,7 +153,7 @@ def kernel_work(name, a):
     if name in ("t2s_gemm_bf16", "t2s_gemm_bf16x3"):     # x3: algorithmic (fp32-equivalent) flops, MMA work is 3x
         M, N, K = a[9], a[10], a[11]
         return 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N)
-    if name == "t2s_attn_x3":
+    if name in ("t2s_attn_x3", "t2s_attn_tc"):
         B, L, Hh = a[3], a[4], a[5]
         return 4.0 * B * L * L * Hh, 16.0 * B * L * Hh
     if name == "t2s_gemm_f32":

@@ -73,6 +73,10 @@ int t2s_attn_f32(const float* qkv, long long ld, int B, int L, int H, int heads,
  * the lo half of qkv, >= 3H; output lo half at column H).  Same call sites as t2s_attn_f32. */
 int t2s_attn_x3(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads, const int* key_idx,
                 const int* n_keys, int key_stride, void* out_split, long long ldo, void* stream);
+/* K2t attention on tcgen05/TMEM (see csrc/attn_tc.cu).  lo_off == 0: bf16 q|k|v [rows, 3H], bf16 output;
+ * lo_off >= 3H: bf16 hi|lo operands (fp32-class, three products per contraction), output hi|lo (lo at column H). */
+int t2s_attn_tc(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads, const int* key_idx,
+                const int* n_keys, int key_stride, void* out, long long ldo, void* stream);
 int t2s_attn_bf16(const void* qkv, long long ld, int B, int L, int H, int heads, const int* key_idx,
                   const int* n_keys, int key_stride, void* out, long long ldo, void* stream);
 /* decoder rows t0..t0+nq-1 (nq <= 16): valid encoder keys + causal decoder keys (t2s.py:574-579,609-615) */

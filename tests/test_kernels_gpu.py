@@ -265,6 +265,60 @@ def test_attn_bf16(B, L):
     assert (out.float() - ref).abs().mean().item() <= 3e-3
 
 
+@pytest.mark.parametrize("B,L,frac", [(2, 64, 0.6), (2, 52, 0.6), (3, 200, 0.6), (1, 1044, 0.6), (2, 300, 1.0),
+                                      (2, 1044, 0.05)])
+def test_attn_tc_bf16(B, L, frac):
+    """tcgen05 attention, bf16 operands: S and O accumulate in TMEM, P goes through shared memory as bf16."""
+    lib = tlib.get_lib()
+    H = 768
+    qkv = rnd(B * L, 3 * H, dtype=torch.bfloat16, seed=16)
+    mask, keys, nk = _keys(B, L, seed=B * 5 + L, frac=frac)
+    out = torch.full((B * L, H), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lib.attn_tc(P(qkv), 3 * H, 0, B, L, H, 12, P(keys), P(nk), L, P(out), H, stream())
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv.float(), B, L, H, keys, nk).float()
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs()
+    assert err.max().item() <= 3e-2, err.max().item()
+    assert err.mean().item() <= 3e-3
+
+
+def test_attn_tc_lazy_rescale():
+    """Keys ordered so that the row maximum keeps rising by more than 2^8 from tile to tile: exercises the
+    in-TMEM rescale of O."""
+    lib = tlib.get_lib()
+    B, L, H = 1, 512, 768
+    qkv = rnd(B * L, 3 * H, dtype=torch.bfloat16, seed=17)
+    ramp = torch.linspace(0.2, 3.0, L, device="cuda")[:, None]
+    qkv[:, H:2 * H] = (qkv[:, H:2 * H].float() * ramp).to(torch.bfloat16)        # later keys score much higher
+    qkv[:, :H] = (qkv[:, :H].float().abs() * 1.5).to(torch.bfloat16)
+    qkv[:, H:2 * H] = qkv[:, H:2 * H].float().abs().to(torch.bfloat16) * torch.sign(ramp - 0.1).to(torch.bfloat16)
+    keys = torch.arange(L, dtype=torch.int32, device="cuda")[None].contiguous()
+    nk = torch.tensor([L], dtype=torch.int32, device="cuda")
+    out = torch.zeros(B * L, H, device="cuda", dtype=torch.bfloat16)
+    lib.attn_tc(P(qkv), 3 * H, 0, B, L, H, 12, P(keys), P(nk), L, P(out), H, stream())
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv.float(), B, L, H, keys, nk).float()
+    assert (out.float() - ref).abs().max().item() <= 4e-2
+
+
+@pytest.mark.parametrize("B,L", [(3, 20), (2, 52), (2, 200), (1, 1044)])
+def test_attn_tc_x3(B, L):
+    """tcgen05 attention with bf16 hi|lo operands: fp32-class."""
+    lib = tlib.get_lib()
+    H = 768
+    qkv = rnd(B * L, 3 * H, seed=18)
+    mask, keys, nk = _keys(B, L, seed=3 * B + L)
+    qs = _split(qkv)
+    out = torch.zeros(B * L, 2 * H, device="cuda", dtype=torch.bfloat16)
+    lib.attn_tc(P(qs), 6 * H, 3 * H, B, L, H, 12, P(keys), P(nk), L, P(out), 2 * H, stream())
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv, B, L, H, keys, nk)
+    got = out[:, :H].double() + out[:, H:].double()
+    err = (got - ref).abs().max().item()
+    assert err <= 5e-5, err
+
+
 @pytest.mark.parametrize("t0,nq", [(0, 1), (5, 1), (11, 1), (0, 12)])
 def test_attn_dec(t0, nq):
     lib = tlib.get_lib()

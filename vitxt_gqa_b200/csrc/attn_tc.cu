@@ -1,0 +1,357 @@
+// K2t: masked multi-head attention on the 5th-gen tensor cores (tcgen05 + TMEM), head size 64.
+//
+// Replaces BertSelfAttention's matmul / +mask / softmax / matmul chain for the encoder rows of the
+// answer transformer (reference pythia/models/t2s.py:622 through pytorch_transformers) and, in its
+// bf16x3 form, for TextBert / QTV of the grounding chain (t2s.py:423,538).  Masked keys are skipped
+// through the compacted per-sample key list (see attention.cu): exp(-10000 - max) == 0 in fp32.
+//
+// One CTA = 128 query rows of one (sample, head); key tiles of 128 gathered rows.
+//   warps 0-3  softmax: thread r owns query row r == TMEM lane r.  Two sweeps over S in TMEM
+//              (row max, then exp2 / row sum), P written as bf16 into a 128B-swizzled shared-memory
+//              tile (the A operand of P.V).  O accumulates in TMEM across key tiles; the online-
+//              softmax correction is LAZY: the running maximum is only raised (and O rescaled in
+//              TMEM by tcgen05.ld / st) when a tile exceeds it by more than 2^8, which keeps the
+//              result exact (the final division uses the same maximum) and the rescale rare.
+//   warps 4-7  loaders: cp.async 16-byte gathers of the K / V rows named by the key list into the
+//              same 128B-swizzled layout a TMA tile load would produce (TMA cannot gather rows),
+//              two stages, fence.proxy.async + mbarrier hand-off to the tensor core.
+//   warp 8     one thread issues tcgen05.mma: S = Q.K^T (M128 N128 K64) into TMEM columns [0,128),
+//              O += P.V (M128 N64 K128, V consumed as an MN-major operand straight from its
+//              row-per-key layout) into columns [128,192); tcgen05.commit drives the mbarriers.
+// S(t+1) is issued right behind P.V(t); two CTAs per SM (112 KB smem, 256 TMEM columns each) overlap
+// one CTA's softmax with the other's tensor work.
+// X3 = true: q|k|v are bf16 hi|lo pairs, S = Ql.Kh + Qh.Kl + Qh.Kh, O = Pl.Vh + Ph.Vl + Ph.Vh
+// (fp32-class; 224 KB smem, one CTA per SM).
+#include "common.cuh"
+#include "../../include/t2s_b200.h"
+
+namespace t2s {
+
+constexpr int TC_BQ = 128, TC_BK = 128, TC_DH = 64;
+constexpr int TC_THREADS = 288;              // 4 softmax + 4 loader + 1 MMA warp
+constexpr int TC_TILE = 128 * 128;           // bytes of a [128 rows x 64 bf16] 128B-swizzled tile
+
+template <bool X3>
+struct TcCfg {
+    static constexpr int NP = X3 ? 2 : 1;                     // hi (+ lo) planes
+    static constexpr int Q_BYTES = NP * TC_TILE;               // Q tile(s)
+    static constexpr int KV_STAGE = NP * 2 * TC_TILE;          // K plane(s) then V plane(s)
+    static constexpr int P_BYTES = NP * 2 * TC_TILE;           // per plane: keys 0-63 tile, keys 64-127 tile
+    // no alignment slack: two CTAs (2 x (114 816 + 1 024 reserved)) must fit the 227 KB of an SM, so the kernel
+    // relies on the dynamic shared-memory window starting 1024-byte aligned (it has no static shared memory)
+    // and traps otherwise
+    static constexpr int SMEM = Q_BYTES + 2 * KV_STAGE + P_BYTES + 128;
+};
+
+// MN-major (rows = K index, 64 contiguous N elements = one 128-byte row) 128B-swizzled operand: 8-row groups
+// 1024 B apart (SBO); a single 64-element atom along N, so LBO is not used.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2)
+attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, int L, int H,
+               const int* __restrict__ key_idx, const int* __restrict__ n_keys, int key_stride,
+               __nv_bfloat16* __restrict__ out, long long ldo, float scale_log2) {
+    using Cfg = TcCfg<X3>;
+    constexpr int NP = Cfg::NP;
+    extern __shared__ __align__(1024) uint8_t tc_raw[];
+    uint8_t* smem = tc_raw;
+    if (smem_u32(smem) & 1023u) __trap();      // 128B-swizzled tiles need 1024-byte alignment
+    uint8_t* sQ = smem;
+    uint8_t* sKV = sQ + Cfg::Q_BYTES;
+    uint8_t* sP = sKV + 2 * Cfg::KV_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+    uint64_t* kv_full = bars;          // [2] count 128 (loader threads)
+    uint64_t* kv_empty = bars + 2;     // [2] count 1   (tcgen05.commit)
+    uint64_t* s_full = bars + 4;       // count 1
+    uint64_t* p_full = bars + 5;       // count 128 (softmax threads)
+    uint64_t* o_done = bars + 6;       // count 1: committed behind the last P.V only
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TC_BQ;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = n_keys[b];
+    const int nt = (nk + TC_BK - 1) / TC_BK;
+    const int* kidx = key_idx + (long long)b * key_stride;
+    const __nv_bfloat16* base = qkv + (long long)b * L * ld + h * TC_DH;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_init(&kv_full[0], 128); mbar_init(&kv_full[1], 128);
+            mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
+            mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_done, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+    if (warp >= 4 && warp < 8) {
+        // ------------------------------------------------------------------ loaders
+        const int lt = threadIdx.x - 128;            // 0..127
+        const int c = lt & 7, r0 = lt >> 3;          // 16-byte chunk / first row; rows r0 + 16 i
+        // Q tile(s): rows q0 .. q0+127 (zero-filled past L)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 16 * i;
+            const bool ok = q0 + r < L;
+            const __nv_bfloat16* src = base + (long long)(ok ? q0 + r : 0) * ld + c * 8;
+            const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+            cp_async16(sQ + off, src, ok);
+            if (X3) cp_async16(sQ + TC_TILE + off, src + lo_off, ok);
+        }
+        auto load_tile = [&](int t, int s) {
+            uint8_t* dst = sKV + s * Cfg::KV_STAGE;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 16 * i;
+                const int k = t * TC_BK + r;
+                const bool ok = k < nk;
+                const long long row = ok ? kidx[k] : 0;
+                const __nv_bfloat16* src = base + row * ld + c * 8;
+                const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+                cp_async16(dst + off, src + H, ok);                                   // K (hi)
+                cp_async16(dst + NP * TC_TILE + off, src + 2 * H, ok);                // V (hi)
+                if (X3) {
+                    cp_async16(dst + TC_TILE + off, src + H + lo_off, ok);            // K lo
+                    cp_async16(dst + 3 * TC_TILE + off, src + 2 * H + lo_off, ok);    // V lo
+                }
+            }
+        };
+        load_tile(0, 0);
+        cp_async_commit();
+        for (int t = 0; t < nt; ++t) {
+            if (t + 1 < nt) {
+                const int s1 = (t + 1) & 1;
+                mbar_wait(&kv_empty[s1], (((t + 1) >> 1) & 1) ^ 1);
+                load_tile(t + 1, s1);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();                  // this thread's share of tile t (and Q) has landed
+            fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&kv_full[t & 1]);
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc_s = make_idesc_bf16(TC_BQ, TC_BK);
+        constexpr uint32_t idesc_o = make_idesc_bf16(TC_BQ, TC_DH) | (1u << 16);     // B operand (V) is MN-major
+        const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+        auto issue_s = [&](int t) {
+            const uint32_t aK = smem_u32(sKV + (t & 1) * Cfg::KV_STAGE);
+            if (lane == 0) {
+                bool first = true;
+                // small terms first (X3): Ql.Kh, Qh.Kl, then Qh.Kh
+#pragma unroll
+                for (int term = X3 ? 0 : 2; term < 3; ++term) {
+                    const uint64_t dq = make_sw128_kmajor_desc(aQ + ((X3 && term == 0) ? TC_TILE : 0));
+                    const uint64_t dk = make_sw128_kmajor_desc(aK + ((X3 && term == 1) ? TC_TILE : 0));
+#pragma unroll
+                    for (int k = 0; k < TC_DH / 16; ++k) {
+                        umma_bf16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, first ? 0u : 1u);
+                        first = false;
+                    }
+                }
+                umma_commit(s_full);
+            }
+            __syncwarp();
+        };
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        issue_s(0);
+        for (int t = 0; t < nt; ++t) {
+            const int s = t & 1;
+            mbar_wait(p_full, t & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t aV = smem_u32(sKV + s * Cfg::KV_STAGE + NP * TC_TILE);
+                bool first = t == 0;         // O accumulates across key tiles
+#pragma unroll
+                for (int term = X3 ? 0 : 2; term < 3; ++term) {      // Pl.Vh, Ph.Vl, Ph.Vh
+                    const uint32_t p_plane = aP + ((X3 && term == 0) ? 2 * TC_TILE : 0);
+                    const uint32_t v_plane = aV + ((X3 && term == 1) ? TC_TILE : 0);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        // P: two [128 x 64-key] K-major tiles side by side; V: 16 keys = 2048 B per k-step
+                        const uint64_t dp = make_sw128_kmajor_desc(p_plane + (k >> 2) * TC_TILE) + 2 * (k & 3);
+                        const uint64_t dv = make_sw128_mnmajor_desc(v_plane + k * 2048);
+                        umma_bf16(tmem_O, dp, dv, idesc_o, first ? 0u : 1u);
+                        first = false;
+                    }
+                }
+                umma_commit(&kv_empty[s]);
+                if (t == nt - 1) umma_commit(o_done);
+            }
+            __syncwarp();
+            if (t + 1 < nt) {
+                mbar_wait(&kv_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
+                tc_fence_after();
+                issue_s(t + 1);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax (thread == query row == TMEM lane)
+        const int r = threadIdx.x;                         // 0..127
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        uint8_t* p_row = sP + r * 128;
+        const int sw = r & 7;
+        constexpr float kRescale = 8.0f;                   // log2 domain: P stays below 2^8
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int t = 0; t < nt; ++t) {
+            const int valid = min(TC_BK, nk - t * TC_BK);          // keys of this tile that exist
+            mbar_wait(s_full, t & 1);       // S(t) done; MMAs retire in order, so P.V(t-1) is done as well
+            tc_fence_after();
+            float mt = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c * 32 + j < valid) mt = fmaxf(mt, __uint_as_float(v[j]));
+            }
+            mt *= scale_log2;
+            const bool raise = mt > m_run + kRescale || t == 0;
+            float corr = 1.0f;
+            if (raise) {
+                corr = exp2f(m_run - mt);                  // exp2(-inf) == 0 on the first tile
+                m_run = mt;
+                l_run *= corr;
+            }
+            if (t > 0 && __any_sync(0xffffffffu, raise)) {
+                // rescale this warp's 32 rows of O in TMEM (rows that keep their maximum use corr == 1)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * corr);
+                    tmem_st_32x32(tmem_O + lane_addr + c * 32, v);
+                }
+                tmem_st_wait();
+            }
+            float sum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
+                tmem_ld_wait();
+                uint32_t ph[16], pl[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float p0 = exp2f(fmaf(__uint_as_float(v[j]), scale_log2, -m_run));
+                    float p1 = exp2f(fmaf(__uint_as_float(v[j + 1]), scale_log2, -m_run));
+                    if (c * 32 + j >= valid) p0 = 0.f;
+                    if (c * 32 + j + 1 >= valid) p1 = 0.f;
+                    sum += p0 + p1;
+                    ph[j >> 1] = pack_bf16x2(p0, p1);
+                    if (X3) pl[j >> 1] = pack_bf16x2(p0 - bf16lo(ph[j >> 1]), p1 - bf16hi(ph[j >> 1]));
+                }
+                // keys c*32 .. c*32+31 -> tile (c >> 1), 16-byte chunks (c & 1) * 4 + 0..3 of row r
+                uint8_t* dst = p_row + (c >> 1) * TC_TILE;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int chunk = (c & 1) * 4 + q;
+                    *reinterpret_cast<uint4*>(dst + ((chunk ^ sw) << 4)) =
+                        make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+                    if (X3)
+                        *reinterpret_cast<uint4*>(dst + 2 * TC_TILE + ((chunk ^ sw) << 4)) =
+                            make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+                }
+            }
+            l_run += sum;
+            tc_fence_before();                   // S reads / O rescale ordered before the issuer's next MMAs
+            fence_proxy_async();                 // P tile visible to the tensor core
+            mbar_arrive(p_full);
+        }
+        mbar_wait(o_done, 0);
+        tc_fence_after();
+        const int row = q0 + r;
+        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+        __nv_bfloat16* op = out + ((long long)b * L + row) * ldo + h * TC_DH;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);      // warp-collective: rows past L load too
+            tmem_ld_wait();
+            if (row < L) {
+#pragma unroll
+                for (int d = 0; d < 32; d += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[d + e]) * inv;
+                    uint4 hi;
+                    hi.x = pack_bf16x2(f[0], f[1]); hi.y = pack_bf16x2(f[2], f[3]);
+                    hi.z = pack_bf16x2(f[4], f[5]); hi.w = pack_bf16x2(f[6], f[7]);
+                    *reinterpret_cast<uint4*>(op + c * 32 + d) = hi;
+                    if (X3) {
+                        uint4 lo;
+                        lo.x = pack_bf16x2(f[0] - bf16lo(hi.x), f[1] - bf16hi(hi.x));
+                        lo.y = pack_bf16x2(f[2] - bf16lo(hi.y), f[3] - bf16hi(hi.y));
+                        lo.z = pack_bf16x2(f[4] - bf16lo(hi.z), f[5] - bf16hi(hi.z));
+                        lo.w = pack_bf16x2(f[6] - bf16lo(hi.w), f[7] - bf16hi(hi.w));
+                        *reinterpret_cast<uint4*>(op + H + c * 32 + d) = lo;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+template <bool X3>
+static int launch_attn_tc(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads,
+                          const int* key_idx, const int* n_keys, int key_stride, void* out, long long ldo,
+                          cudaStream_t st) {
+    using Cfg = TcCfg<X3>;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) { set_error("attn_tc attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr = true;
+    }
+    dim3 grid((L + TC_BQ - 1) / TC_BQ, heads, B);
+    attn_tc_kernel<X3><<<grid, TC_THREADS, Cfg::SMEM, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), ld, lo_off, L, H, key_idx, n_keys, key_stride,
+        reinterpret_cast<__nv_bfloat16*>(out), ldo, 0.125f * 1.4426950408889634f);
+    return launch_status("attn_tc");
+}
+
+}  // namespace t2s
+
+using namespace t2s;
+
+extern "C" int t2s_attn_tc(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads,
+                           const int* key_idx, const int* n_keys, int key_stride, void* out, long long ldo,
+                           void* stream) {
+    if (H != heads * TC_DH || (ld % 8) || (ldo % 8) || (lo_off % 8) || B <= 0 || L <= 0) {
+        set_error("attn_tc: head size must be 64 and pitches multiples of 8 (H %d heads %d ld %lld ldo %lld)", H, heads, ld, ldo);
+        return T2S_ERR_SHAPE;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (lo_off > 0) {
+        if (lo_off < 3 * H || ld < lo_off + 3 * H || ldo < 2LL * H) { set_error("attn_tc: bad hi|lo layout"); return T2S_ERR_SHAPE; }
+        return launch_attn_tc<true>(qkv, ld, lo_off, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st);
+    }
+    return launch_attn_tc<false>(qkv, ld, 0, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st);
+}

@@ -25,6 +25,7 @@ SIGNATURES = {
     "t2s_gemm_f32": [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p],
     "t2s_attn_f32": [_p, _ll, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _p, _ll, _p],
     "t2s_attn_x3": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _p],
+    "t2s_attn_tc": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _p],
     "t2s_attn_bf16": [_p, _ll, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _p],
     "t2s_attn_dec": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _ll, _p],
     "t2s_bert_embed_ln": [_p, _i, _i, _i, _p, _p, _p, _p, _p, _f, _p, _ll, _p],

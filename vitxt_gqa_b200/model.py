@@ -208,6 +208,10 @@ class _FusionModelBase(BaseModel):
         # bf16 hi|lo, three tcgen05 products per contraction (fp32-class, default); "fp32" = FMA-pipe GEMMs
         self.grounding_precision = os.environ.get(
             "T2S_B200_GROUNDING", str(self.config.get("b200_grounding_precision", "bf16x3")))
+        # attention of the encoder rows: "tc" = tcgen05/TMEM kernel (default), "mma" = mma.sync kernels
+        self.attn_impl = os.environ.get("T2S_B200_ATTN", str(self.config.get("b200_attention", "tc")))
+        if self.attn_impl not in ("tc", "mma"):
+            raise ValueError("b200_attention must be 'tc' or 'mma'")
         if self.grounding_precision not in ("bf16x3", "fp32"):
             raise ValueError("b200_grounding_precision must be 'bf16x3' or 'fp32'")
 
@@ -418,8 +422,8 @@ class _FusionModelBase(BaseModel):
             qkvs = ws["qkvs"]      # q|k|v as bf16 hi|lo: [M, 2 * 3H]
             L.gemm_bf16x3(_ptr(xs), 2 * H, _ptr(lw["wqkv"]), 2 * H, _ptr(lw["bqkv"]), None, 0, _ptr(qkvs), 6 * H,
                           M, 3 * H, H, SPLIT, 0, st)
-            L.attn_x3(_ptr(qkvs), 6 * H, 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride,
-                      _ptr(ctxs), 2 * H, st)
+            attn = L.attn_tc if self.attn_impl == "tc" else L.attn_x3
+            attn(_ptr(qkvs), 6 * H, 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride, _ptr(ctxs), 2 * H, st)
             L.gemm_bf16x3(_ptr(ctxs), 2 * H, _ptr(lw["wo"]), 2 * H, _ptr(lw["bo"]), _ptr(x), H, _ptr(h), H,
                           M, H, H, F32 | RES, 0, st)
             L.add_ln_split(_ptr(h), 0, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H, None, 0,
@@ -539,8 +543,12 @@ class _FusionModelBase(BaseModel):
                     qkv = ws["qkv"][v][li]
                     L.gemm_bf16(_ptr(x), H, _ptr(lw["wqkv"]), H, _ptr(lw["bqkv"]), None, 0, _ptr(qkv), 3 * H,
                                 M, 3 * H, H, 0, 0, st)
-                L.attn_bf16(_ptr(qkv), 3 * H, B, Le, H, 12, _ptr(ws["keys"][v]), _ptr(ws["nk"][v]), Le,
-                            _ptr(ws["ctx"]), H, st)
+                if self.attn_impl == "tc":
+                    L.attn_tc(_ptr(qkv), 3 * H, 0, B, Le, H, 12, _ptr(ws["keys"][v]), _ptr(ws["nk"][v]), Le,
+                              _ptr(ws["ctx"]), H, st)
+                else:
+                    L.attn_bf16(_ptr(qkv), 3 * H, B, Le, H, 12, _ptr(ws["keys"][v]), _ptr(ws["nk"][v]), Le,
+                                _ptr(ws["ctx"]), H, st)
                 L.gemm_bf16(_ptr(ws["ctx"]), H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), _ptr(x), H, _ptr(ws["hb"]), H,
                             M, H, H, 0, 0, st)
                 L.add_ln(_ptr(ws["hb"]), 1, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H,
