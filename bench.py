@@ -148,6 +148,38 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ B200 path
+N_SMS = 148
+NCU_NAMES = {"t2s_gemm_bf16<256>": "gemm_bf16_tcgen05_kernel<256>", "t2s_gemm_bf16x3<256>": "gemm_bf16_tcgen05_kernel<256>",
+             "t2s_attn_tc<bf16>": "attn_tc_kernel<0>", "t2s_attn_tc<x3>": "attn_tc_kernel<1>"}
+
+
+def ncu_traffic(key):
+    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py from the launches named there); None if the
+    kernel was not captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        z = json.load(open(p))
+        e = z["kernels"][key]
+        return e["dram_bytes"] / e["launches"], "%s: %s" % (z.get("source", "profiles/ncu_traffic.json"), e.get("note", ""))
+    except Exception:
+        return None, None
+
+
+def kernel_key(name, a):
+    """Launches are grouped the way ncu names them: entry point + the kernel instantiation it selects
+    (tile width of the tcgen05 GEMM as chosen in csrc/gemm_tcgen05.cu gemm_entry; operand mode of attn_tc)."""
+    if name in ("t2s_gemm_bf16", "t2s_gemm_bf16x3"):
+        M, N, bn = a[9], a[10], a[13]
+        if bn == 0:
+            mt = (M + 127) // 128
+            bn = 256 if mt * ((N + 255) // 256) >= N_SMS else 128 if mt * ((N + 127) // 128) >= N_SMS else 64
+        return "%s<%d>" % (name, bn)
+    if name == "t2s_attn_tc":
+        return name + ("<x3>" if a[2] else "<bf16>")
+    return name
+
+
 def kernel_work(name, a):
     """(flops, bytes) one launch is asked to do, from its C-ABI arguments (include/t2s_b200.h)."""
     if name in ("t2s_gemm_bf16", "t2s_gemm_bf16x3"):     # x3: algorithmic (fp32-equivalent) flops, MMA work is 3x
@@ -276,11 +308,16 @@ def run_b200(args):
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
         # ---- leg 3: per-launch CUDA events on the launching stream, same steps again
+        # (the decode / encoder stream overlap is switched off here: per-launch times of kernels that share
+        # the GPU would not be the kernels' own)
         prof_steps = min(args.steps, 3)
+        overlap_sms, model.overlap_sms = model.overlap_sms, 0
+        model(resident)
         L.start_timing()
         for _ in range(prof_steps):
             model(resident)
         rec = L.stop_timing()
+        model.overlap_sms = overlap_sms
 
     if rank != 0:
         if world > 1:
@@ -291,7 +328,7 @@ def run_b200(args):
     per = {}
     for name, a, ms in rec:
         fl, by = kernel_work(name, a)
-        p = per.setdefault(name, dict(ms=0.0, n=0, flops=0.0, bytes=0.0))
+        p = per.setdefault(kernel_key(name, a), dict(ms=0.0, n=0, flops=0.0, bytes=0.0))
         p["ms"] += ms; p["n"] += 1; p["flops"] += fl; p["bytes"] += by
     tot = sum(p["ms"] for p in per.values())
     top = max(per, key=lambda k: per[k]["ms"])
@@ -306,6 +343,7 @@ def run_b200(args):
         ach = tp["bytes"] / (tp["ms"] * 1e-3) / 1e9
         roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"]}
+    roof["traffic"], roof["traffic_source"] = ncu_traffic(top)
     roof.update(launches_per_step=tp["n"] / prof_steps, avg_launch_ms=tp["ms"] / tp["n"],
                 share_of_step=tp["ms"] / tot)
     kernels = {k[4:]: {"share": round(v["ms"] / tot, 4), "ms_per_step": round(v["ms"] / prof_steps, 3),
@@ -335,7 +373,8 @@ def run_b200(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 answer transformer + fp32 grounding chain (fp32 accumulate)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "l2": "inputs (%.0f MB/step) and activations exceed L2"
-                   % (h2d / 1e6), "algorithmic_gflop_per_sample": round(gf, 1)},
+                   % (h2d / 1e6), "algorithmic_gflop_per_sample": round(gf, 1),
+                   "decode_overlap_sms": model.overlap_sms},
         "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,

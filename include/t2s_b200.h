@@ -29,6 +29,8 @@ extern "C" {
 #define T2S_GEMM_OUT_F32 2  /* bf16 GEMM: store C as fp32 instead of bf16                           */
 #define T2S_GEMM_RES_F32 4  /* bf16 GEMM: residual operand is fp32 instead of bf16                  */
 #define T2S_GEMM_OUT_SPLIT 8 /* bf16 GEMM: store C as bf16 hi|lo, hi at [.,0..N), lo at [.,N..2N)       */
+#define T2S_GEMM_SM_CAP_SHIFT 8 /* bits 8..15 of flags: cap the persistent grid at that many CTAs (0 = every SM), so a
+                                 * latency-bound kernel chain on another stream (the greedy decode) finds free SMs    */
 
 int t2s_abi_version(void);
 const char* t2s_last_error(void);

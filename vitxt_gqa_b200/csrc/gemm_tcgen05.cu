@@ -378,7 +378,7 @@ int num_sms() {
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmEpi& ep, int M,
-                       int N, int K, int k_lo_off, cudaStream_t st) {
+                       int N, int K, int k_lo_off, int sm_cap, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -391,7 +391,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
         attr_set = true;
     }
     const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
-    const int grid = tiles < num_sms() ? tiles : num_sms();
+    // T2S_GEMM_SM_CAP: the persistent grid leaves SMs free for latency-bound work on another stream
+    const int sms = (sm_cap > 0 && sm_cap < num_sms()) ? sm_cap : num_sms();
+    const int grid = tiles < sms ? tiles : sms;
     gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, ep, M, N, K, k_lo_off);
     return launch_status("gemm_bf16_tcgen05");
 }
@@ -446,10 +448,11 @@ static int gemm_entry(const char* who, bool x3, const void* A, long long lda, co
     GemmEpi ep{C, bias, residual, ldc, ldr, flags, N};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int k_lo = x3 ? K : 0;
+    const int cap = (flags >> T2S_GEMM_SM_CAP_SHIFT) & 0xff;
     switch (bn) {
-        case 256: return launch_gemm<256>(ta, tb, tc, ep, M, N, K, k_lo, st);
-        case 128: return launch_gemm<128>(ta, tb, tc, ep, M, N, K, k_lo, st);
-        case 64: return launch_gemm<64>(ta, tb, tc, ep, M, N, K, k_lo, st);
+        case 256: return launch_gemm<256>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
+        case 128: return launch_gemm<128>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
+        case 64: return launch_gemm<64>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
         default: set_error("%s: block_n must be 0, 64, 128 or 256", who); return T2S_ERR_ARG;
     }
 }

@@ -15,6 +15,11 @@ namespace t2s {
 // scores[b, t0+i, V+o] = (q[b,t0+i] . keyp[b,o]) / sqrt(H) + mask[b,o]
 constexpr int PS_THREADS = 256, PS_ROWS = 64, PS_MAXQ = 16;
 
+// Each warp scores PS_WROWS key rows at a time so 12 independent 16-byte loads per lane are in flight (one row
+// per iteration left the kernel latency bound at ~1.2 TB/s); MAXQ = 1 is the greedy-decode instantiation.
+constexpr int PS_WROWS = 4;
+
+template <int MAXQ>
 __global__ void __launch_bounds__(PS_THREADS)
 ptr_score_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, int T, int t0, int nq,
                  const __nv_bfloat16* __restrict__ keyp, long long key_batch_stride, long long ldk, int O, int H,
@@ -27,34 +32,60 @@ ptr_score_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, int T, int 
         qs[i] = __bfloat162float(q[((long long)b * T + t0 + r) * ldq + d]);
     }
     __syncthreads();
+    constexpr int NW = PS_THREADS / 32;
     const int o_end = min(O, (int)(blockIdx.x + 1) * PS_ROWS);
-    for (int o = blockIdx.x * PS_ROWS + warp; o < o_end; o += PS_THREADS / 32) {
-        const __nv_bfloat16* kp = keyp + (long long)b * key_batch_stride + (long long)o * ldk;
-        float acc[PS_MAXQ];
+    const __nv_bfloat16* kb = keyp + (long long)b * key_batch_stride;
+    for (int o0 = blockIdx.x * PS_ROWS + warp; o0 < o_end; o0 += NW * PS_WROWS) {
+        uint4 kv[PS_WROWS][4];
 #pragma unroll
-        for (int r = 0; r < PS_MAXQ; ++r) acc[r] = 0.f;
-        for (int d = lane * 8; d < H; d += 256) {
-            const uint4 kv = *reinterpret_cast<const uint4*>(kp + d);
-            const float kf[8] = {bf16lo(kv.x), bf16hi(kv.x), bf16lo(kv.y), bf16hi(kv.y),
-                                 bf16lo(kv.z), bf16hi(kv.z), bf16lo(kv.w), bf16hi(kv.w)};
+        for (int j = 0; j < PS_WROWS; ++j) {
+            const int o = o0 + j * NW;
 #pragma unroll
-            for (int r = 0; r < PS_MAXQ; ++r)
+            for (int c = 0; c < 4; ++c) {
+                const int d = lane * 8 + c * 256;
+                kv[j][c] = (o < o_end && d < H) ? *reinterpret_cast<const uint4*>(kb + (long long)o * ldk + d)
+                                                : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        float acc[PS_WROWS][MAXQ];
+#pragma unroll
+        for (int j = 0; j < PS_WROWS; ++j)
+#pragma unroll
+            for (int r = 0; r < MAXQ; ++r) acc[j][r] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int d = lane * 8 + c * 256;
+            if (d < H) {
+#pragma unroll
+                for (int r = 0; r < MAXQ; ++r)
+                    if (r < nq) {
+                        const float4 q0 = *reinterpret_cast<const float4*>(qs + r * H + d);
+                        const float4 q1 = *reinterpret_cast<const float4*>(qs + r * H + d + 4);
+#pragma unroll
+                        for (int j = 0; j < PS_WROWS; ++j) {
+                            const uint4 k4 = kv[j][c];
+                            float a = acc[j][r];
+                            a = fmaf(q0.x, bf16lo(k4.x), a); a = fmaf(q0.y, bf16hi(k4.x), a);
+                            a = fmaf(q0.z, bf16lo(k4.y), a); a = fmaf(q0.w, bf16hi(k4.y), a);
+                            a = fmaf(q1.x, bf16lo(k4.z), a); a = fmaf(q1.y, bf16hi(k4.z), a);
+                            a = fmaf(q1.z, bf16lo(k4.w), a); a = fmaf(q1.w, bf16hi(k4.w), a);
+                            acc[j][r] = a;
+                        }
+                    }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PS_WROWS; ++j) {
+            const int o = o0 + j * NW;
+            if (o >= o_end) break;        // warp-uniform
+            const float m = mask[(long long)b * mask_stride + o];
+#pragma unroll
+            for (int r = 0; r < MAXQ; ++r)
                 if (r < nq) {
-                    const float4 q0 = *reinterpret_cast<const float4*>(qs + r * H + d);
-                    const float4 q1 = *reinterpret_cast<const float4*>(qs + r * H + d + 4);
-                    acc[r] = fmaf(q0.x, kf[0], acc[r]); acc[r] = fmaf(q0.y, kf[1], acc[r]);
-                    acc[r] = fmaf(q0.z, kf[2], acc[r]); acc[r] = fmaf(q0.w, kf[3], acc[r]);
-                    acc[r] = fmaf(q1.x, kf[4], acc[r]); acc[r] = fmaf(q1.y, kf[5], acc[r]);
-                    acc[r] = fmaf(q1.z, kf[6], acc[r]); acc[r] = fmaf(q1.w, kf[7], acc[r]);
+                    const float sum = warp_sum(acc[j][r]);
+                    if (lane == 0) scores[((long long)b * T + t0 + r) * ld_scores + V + o] = sum / denom + m;
                 }
         }
-        const float m = mask[(long long)b * mask_stride + o];
-#pragma unroll
-        for (int r = 0; r < PS_MAXQ; ++r)
-            if (r < nq) {
-                const float s = warp_sum(acc[r]);
-                if (lane == 0) scores[((long long)b * T + t0 + r) * ld_scores + V + o] = s / denom + m;
-            }
     }
 }
 
@@ -183,14 +214,20 @@ extern "C" int t2s_ptr_score(const void* q, long long ldq, int B, int T, int t0,
     const size_t smem = (size_t)nq * H * sizeof(float);
     static size_t attr = 48 * 1024;
     if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(ptr_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(ptr_score_kernel<PS_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("ptr_score attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr = smem;
     }
     dim3 grid((O + PS_ROWS - 1) / PS_ROWS, B);
-    ptr_score_kernel<<<grid, PS_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(q), ldq, T, t0, nq, reinterpret_cast<const __nv_bfloat16*>(keyp),
-        key_batch_stride, ldk, O, H, mask, mask_stride, scores, ld_scores, V, sqrtf((float)H));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* qp = reinterpret_cast<const __nv_bfloat16*>(q);
+    const __nv_bfloat16* kp = reinterpret_cast<const __nv_bfloat16*>(keyp);
+    if (nq == 1)
+        ptr_score_kernel<1><<<grid, PS_THREADS, smem, st>>>(qp, ldq, T, t0, nq, kp, key_batch_stride, ldk, O, H, mask,
+                                                           mask_stride, scores, ld_scores, V, sqrtf((float)H));
+    else
+        ptr_score_kernel<PS_MAXQ><<<grid, PS_THREADS, smem, st>>>(qp, ldq, T, t0, nq, kp, key_batch_stride, ldk, O, H,
+                                                                 mask, mask_stride, scores, ld_scores, V, sqrtf((float)H));
     return launch_status("ptr_score");
 }
 

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libt2s_sm100.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 GEMM_GELU, GEMM_OUT_F32, GEMM_RES_F32, GEMM_OUT_SPLIT = 1, 2, 4, 8
+GEMM_SM_CAP_SHIFT = 8     # bits 8..15 of the GEMM flags: cap on the persistent grid
 
 _p, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
 

@@ -210,6 +210,11 @@ class _FusionModelBase(BaseModel):
             "T2S_B200_GROUNDING", str(self.config.get("b200_grounding_precision", "bf16x3")))
         # attention of the encoder rows: "tc" = tcgen05/TMEM kernel (default), "mma" = mma.sync kernels
         self.attn_impl = os.environ.get("T2S_B200_ATTN", str(self.config.get("b200_attention", "tc")))
+        # eval only: run the latency-bound greedy decode of the `pos` variant on a second (high-priority) stream
+        # while the throughput-bound encoder passes of `ref` / `neg` run on the caller's stream with their
+        # persistent GEMM grids capped at (SMs - overlap_sms) CTAs.  0 disables the overlap.
+        self.overlap_sms = int(os.environ.get("T2S_B200_OVERLAP_SMS", str(self.config.get("b200_overlap_sms", 16))))
+        self._side_streams = {}
         if self.attn_impl not in ("tc", "mma"):
             raise ValueError("b200_attention must be 'tc' or 'mma'")
         if self.grounding_precision not in ("bf16x3", "fp32"):
@@ -388,7 +393,7 @@ class _FusionModelBase(BaseModel):
             # decoder rows
             xd=torch.empty(Md, H, **b16), xd1=torch.empty(Md, H, **b16), xd2=torch.empty(Md, H, **b16),
             hd=torch.empty(Md, H, **b16), ctxd=torch.empty(Md, H, **b16), interd=torch.empty(Md, 4 * H, **b16),
-            qd=torch.empty(Md, H, **b16),
+            qd=torch.empty(Md, H, **b16), x1d=torch.empty(Md, H, **b16),
             qkvd={v: [torch.empty(Md, 3 * H, **b16) for _ in range(n_mmt)] for v in variants},
             prev=torch.zeros(B, T, device=device, dtype=torch.int64),
             loss_ws=torch.empty(int(_lib.get_lib().loss_workspace_bytes(B, T)), device=device, dtype=torch.uint8),
@@ -523,16 +528,19 @@ class _FusionModelBase(BaseModel):
                      _ptr(f["ocr_bbox_layer_norm.bias"]), LN_EPS_EMBED, B * O, H, _ptr(ws["J0"]), H, O, Le,
                      Lt + n_obj, st)
 
-    def _mmt_encoder(self, L, P, ws, variants, B, Le, st):
+    def _mmt_encoder(self, L, P, ws, variants, B, Le, st, qkv0=True, sm_cap=0):
         """Encoder rows of the answer transformer for each variant; keeps per-layer q|k|v and the
-        pointer-net key projection of the last layer (reference t2s.py:622-631, 659)."""
+        pointer-net key projection of the last layer (reference t2s.py:622-631, 659).  `sm_cap` > 0 caps the
+        persistent GEMM grids (T2S_GEMM_SM_CAP) while the decode chain runs on another stream."""
         H, M = 768, B * Le
         layers = P["mmt"]
         f = P["f32"]
         lw0 = layers[0]
-        # layer-0 q|k|v only depends on the (variant-independent) input rows: compute once
-        L.gemm_bf16(_ptr(ws["X16"]), H, _ptr(lw0["wqkv"]), H, _ptr(lw0["bqkv"]), None, 0, _ptr(ws["qkv0"]), 3 * H,
-                    M, 3 * H, H, 0, 0, st)
+        CAP = (sm_cap & 0xff) << _lib.GEMM_SM_CAP_SHIFT
+        if qkv0:
+            # layer-0 q|k|v only depends on the (variant-independent) input rows: compute once
+            L.gemm_bf16(_ptr(ws["X16"]), H, _ptr(lw0["wqkv"]), H, _ptr(lw0["bqkv"]), None, 0, _ptr(ws["qkv0"]), 3 * H,
+                        M, 3 * H, H, CAP, 0, st)
         for v in variants:
             x = ws["X16"]
             ping = [ws["xa"], ws["xb"]]
@@ -542,7 +550,7 @@ class _FusionModelBase(BaseModel):
                 else:
                     qkv = ws["qkv"][v][li]
                     L.gemm_bf16(_ptr(x), H, _ptr(lw["wqkv"]), H, _ptr(lw["bqkv"]), None, 0, _ptr(qkv), 3 * H,
-                                M, 3 * H, H, 0, 0, st)
+                                M, 3 * H, H, CAP, 0, st)
                 if self.attn_impl == "tc":
                     L.attn_tc(_ptr(qkv), 3 * H, 0, B, Le, H, 12, _ptr(ws["keys"][v]), _ptr(ws["nk"][v]), Le,
                               _ptr(ws["ctx"]), H, st)
@@ -550,19 +558,19 @@ class _FusionModelBase(BaseModel):
                     L.attn_bf16(_ptr(qkv), 3 * H, B, Le, H, 12, _ptr(ws["keys"][v]), _ptr(ws["nk"][v]), Le,
                                 _ptr(ws["ctx"]), H, st)
                 L.gemm_bf16(_ptr(ws["ctx"]), H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), _ptr(x), H, _ptr(ws["hb"]), H,
-                            M, H, H, 0, 0, st)
+                            M, H, H, CAP, 0, st)
                 L.add_ln(_ptr(ws["hb"]), 1, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H,
                          None, 0, None, 0, _ptr(ws["x1"]), H, 0, 0, 0, st)
                 L.gemm_bf16(_ptr(ws["x1"]), H, _ptr(lw["wi"]), H, _ptr(lw["bi"]), None, 0, _ptr(ws["inter"]),
-                            4 * H, M, 4 * H, H, _lib.GEMM_GELU, 0, st)
+                            4 * H, M, 4 * H, H, _lib.GEMM_GELU | CAP, 0, st)
                 L.gemm_bf16(_ptr(ws["inter"]), 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), _ptr(ws["x1"]), H,
-                            _ptr(ws["hb"]), H, M, H, 4 * H, 0, 0, st)
+                            _ptr(ws["hb"]), H, M, H, 4 * H, CAP, 0, st)
                 out = ping[li & 1]
                 L.add_ln(_ptr(ws["hb"]), 1, H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H,
                          None, 0, None, 0, _ptr(out), H, 0, 0, 0, st)
                 x = out
             L.gemm_bf16(_ptr(x), H, _ptr(P["w_ptr_k"]), H, _ptr(f["ocr_ptr_net.key.bias"]), None, 0,
-                        _ptr(ws["keyp"][v]), H, M, H, H, 0, 0, st)
+                        _ptr(ws["keyp"][v]), H, M, H, H, CAP, 0, st)
 
     def _decode_rows(self, L, P, ws, v, jm, scores, B, Le, T, V, O, n_obj, Lt, t0, nq, st):
         """Decoder rows t0..t0+nq-1 of variant `v` through all layers, then both score heads
@@ -598,10 +606,10 @@ class _FusionModelBase(BaseModel):
             L.gemm_bf16(at(ws["ctxd"], H), rs * H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), at(x, H), rs * H,
                         at(ws["hd"], H), rs * H, M, H, H, 0, 0, st)
             L.add_ln(at(ws["hd"], H), 1, rs * H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H,
-                     None, 0, None, 0, at(ws["x1"], H), rs * H, 0, 0, 0, st)
-            L.gemm_bf16(at(ws["x1"], H), rs * H, _ptr(lw["wi"]), H, _ptr(lw["bi"]), None, 0, at(ws["interd"], 4 * H),
+                     None, 0, None, 0, at(ws["x1d"], H), rs * H, 0, 0, 0, st)
+            L.gemm_bf16(at(ws["x1d"], H), rs * H, _ptr(lw["wi"]), H, _ptr(lw["bi"]), None, 0, at(ws["interd"], 4 * H),
                         rs * 4 * H, M, 4 * H, H, _lib.GEMM_GELU, 0, st)
-            L.gemm_bf16(at(ws["interd"], 4 * H), rs * 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), at(ws["x1"], H),
+            L.gemm_bf16(at(ws["interd"], 4 * H), rs * 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), at(ws["x1d"], H),
                         rs * H, at(ws["hd"], H), rs * H, M, H, 4 * H, 0, 0, st)
             out = ping[li & 1]
             L.add_ln(at(ws["hd"], H), 1, rs * H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H,
@@ -731,8 +739,8 @@ class T2S(_FusionModelBase):
         jm = {"ref": ws["jm_ref"], "pos": ws["jm_pos"], "neg": ws["jm_neg"]}
         N = V + O
         scores = {v: torch.empty(B, T, N, device=dev, dtype=torch.float32) for v in variants}
-        self._mmt_encoder(L, P, ws, variants, B, Le, st)
         if self.training:
+            self._mmt_encoder(L, P, ws, variants, B, Le, st)
             ws["prev"].copy_(inp["train_prev_inds"])
             for v in variants:
                 self._decode_rows(L, P, ws, v, jm[v], scores[v], B, Le, T, V, O, F, Lt, 0, T, st)
@@ -741,11 +749,32 @@ class T2S(_FusionModelBase):
             ws["prev"][:, 0] = int(self.answer_processor.BOS_IDX)
             forced = self.parity_hooks.get("force_prev_inds")     # test-only teacher forcing of the feedback
             forced = forced.to(dev) if forced is not None else None
-            for t in range(T):     # greedy decode drives only the `pos` variant (reference t2s.py:353, Q15)
-                self._decode_rows(L, P, ws, "pos", jm["pos"], scores["pos"], B, Le, T, V, O, F, Lt, t, 1, st)
-                L.argmax_feedback(_ptr(scores["pos"]), N, B, T, t, 1, N, _ptr(ws["prev"]), T, None, st)
-                if forced is not None and t + 1 < T:
-                    ws["prev"][:, t + 1].copy_(forced[:, t + 1])
+            self._mmt_encoder(L, P, ws, ("pos",), B, Le, st)
+
+            def greedy(stream_handle):   # drives only the `pos` variant (reference t2s.py:353, Q15)
+                for t in range(T):
+                    self._decode_rows(L, P, ws, "pos", jm["pos"], scores["pos"], B, Le, T, V, O, F, Lt, t, 1,
+                                      stream_handle)
+                    L.argmax_feedback(_ptr(scores["pos"]), N, B, T, t, 1, N, _ptr(ws["prev"]), T, None, stream_handle)
+                    if forced is not None and t + 1 < T:
+                        ws["prev"][:, t + 1].copy_(forced[:, t + 1])
+
+            n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            if 0 < self.overlap_sms < n_sms:
+                # the 12 greedy steps are ~300 small dependent launches that leave most SMs idle; the ref / neg
+                # encoder passes are independent of them and saturate whatever SMs they are given
+                main = torch.cuda.current_stream(dev)
+                side = self._side_streams.get(dev.index)
+                if side is None:
+                    side = self._side_streams[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    greedy(side.cuda_stream)
+                self._mmt_encoder(L, P, ws, ("ref", "neg"), B, Le, st, qkv0=False, sm_cap=n_sms - self.overlap_sms)
+                main.wait_stream(side)
+            else:
+                greedy(st)
+                self._mmt_encoder(L, P, ws, ("ref", "neg"), B, Le, st, qkv0=False)
             for v in ("ref", "neg"):
                 self._decode_rows(L, P, ws, v, jm[v], scores[v], B, Le, T, V, O, F, Lt, 0, T, st)
         if dbg:
