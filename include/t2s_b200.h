@@ -29,6 +29,8 @@ extern "C" {
 #define T2S_GEMM_OUT_F32 2  /* bf16 GEMM: store C as fp32 instead of bf16                           */
 #define T2S_GEMM_RES_F32 4  /* bf16 GEMM: residual operand is fp32 instead of bf16                  */
 #define T2S_GEMM_OUT_SPLIT 8 /* bf16 GEMM: store C as bf16 hi|lo, hi at [.,0..N), lo at [.,N..2N)       */
+#define T2S_GEMM_DGELU 16    /* backward of BertIntermediate: C = (A.W^T) * GELU'(aux), aux = the saved pre-activation passed
+                              * through `residual` / `ldr` (bf16, or fp32 with T2S_GEMM_RES_F32); no bias                  */
 #define T2S_GEMM_SM_CAP_SHIFT 8 /* bits 8..15 of flags: cap the persistent grid at that many CTAs (0 = every SM), so a
                                  * latency-bound kernel chain on another stream (the greedy decode) finds free SMs    */
 
@@ -52,6 +54,15 @@ int t2s_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, co
 int t2s_gemm_bf16x3(const void* A, long long lda, const void* W, long long ldw, const float* bias,
                     const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K,
                     int flags, int block_n, void* stream);
+/* K8b weight gradient: dW[P,Q] += G[rows,P]^T . X[rows,Q] (fp32 accumulate INTO dW: zero it first).  G = gradient of
+ * the layer output, X = the layer input, both bf16 row-major exactly as the forward / backward kernels wrote them
+ * (MN-major tcgen05 operands: no transposed copies).  The rows are split into `splits` ranges (0 = auto) whose
+ * partial tiles are added with TMA reduce-add, so the summation order -- not the value to fp32 rounding -- can vary
+ * from run to run.  Replaces the autograd addmm for every nn.Linear.weight.grad of pythia/models/t2s.py
+ * (loss.backward(), trainers/base_trainer.py:264).  ldg, ldx multiples of 8; ldd multiple of 4. */
+int t2s_gemm_wgrad_bf16(const void* G, long long ldg, const void* X, long long ldx, float* dW, long long ldd,
+                        int rows, int P, int Q, int splits, void* stream);
+
 /* fp32 rows [rows,K] -> bf16 hi|lo rows [rows,2K']: hi = bf16(x) at column c, lo = bf16(x - hi) at column
  * lo_off + c; columns K..lo_off of both halves are zero-filled (lo_off >= K, multiple of 8). */
 int t2s_split_bf16(const float* x, long long ldx, int rows, int K, int lo_off, void* out, long long ldo,
@@ -156,6 +167,78 @@ int t2s_pos_bce_loss(const float* scores, const float* targets, const float* los
                      void* workspace, float* out, void* stream);
 int t2s_info_nce_loss(const float* ref, const float* pos, const float* neg, int B, int T, int N,
                       float temperature, void* workspace, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K8  training step: what autograd runs in the reference for loss.backward(), clip_grad_norm_ and Adam.step()
+ * (pythia/trainers/base_trainer.py:262-270, utils/general.py:32-40).  Gradient accumulators (d*) are fp32 and are
+ * ADDED to: the caller zeroes the flat gradient buffer once per step.  Activations / activation gradients are bf16
+ * unless a *_bf16 flag says otherwise.  The weight-gradient GEMM (t2s_gemm_wgrad_bf16) and T2S_GEMM_DGELU are
+ * declared with K1 above.
+ * --------------------------------------------------------------------------------------------------------------- */
+/* LayerNorm backward: y = LN(h); tanh_out: the forward output was base + tanh(y) (QTV, models/t2s.py:430-432).
+ * dh (row-compact) is the gradient of h = of the residual branch and of the preceding Linear's output; dgamma,
+ * dbeta and (optional) dbias = column sums of dh are accumulated.  dy rows may be gathered from a larger buffer:
+ * row r of dy lives at (r / per) * group + off + r % per when dy_rows_per_group > 0. */
+int t2s_ln_bwd(const void* h, int h_bf16, long long ldh, const void* dy, int dy_bf16, long long lddy,
+               int dy_rows_per_group, int dy_group_rows, int dy_row_off, const float* gamma, const float* beta,
+               float eps, int rows, int H, int tanh_out, void* dh, int dh_bf16, long long lddh, float* dgamma,
+               float* dbeta, float* dbias, void* stream);
+/* dst[c] += sum_r x[r, c] (bias gradients of q|k|v, intermediate, classifier, pointer-net) */
+int t2s_colsum(const void* x, int x_bf16, long long ldx, int rows, int N, float* dst, void* stream);
+/* out[map(r), :] (+)= a[r] + b[r] + c[r]; a, b, c bf16 (b, c optional), out fp32 */
+int t2s_rows_add(const void* a, const void* b, const void* c, long long ldi, int rows, int H, float* out,
+                 long long ldo, int rows_per_group, int out_group_rows, int out_row_off, int accumulate, void* stream);
+/* training-mode forward of BertIntermediate's activation: the GEMM stores the pre-activation u (needed by
+ * T2S_GEMM_DGELU), this writes gelu(u) as bf16, or as bf16 hi|lo (lo at column lo_off) when lo_off > 0 */
+int t2s_gelu_rows(const void* u, int u_bf16, long long ldu, int rows, int N, void* out, long long ldo, int lo_off,
+                  void* stream);
+/* nn.Embedding backward: table[ids[r], 0..d) += src[r, c0..c0+d); rows with ids[r] == pad_id skipped */
+int t2s_embed_scatter_add(const void* src, int src_bf16, long long lds, int c0, int d, const long long* ids, int rows,
+                          long long pad_id, float* table, long long ldt, void* stream);
+/* OcrPtrNet score backward (models/t2s.py:661-666): dq[b,t] and dkeyp[b,o] from dscores[:, :, V:] */
+int t2s_ptr_score_bwd(const float* dscores, long long ld_scores, int B, int T, int V, const void* q, long long ldq,
+                      const void* keyp, long long key_batch_stride, long long ldk, int O, int H, void* dq, long long lddq,
+                      void* dkeyp, long long dkey_batch_stride, long long lddk, void* stream);
+/* PrevPredEmbeddings backward (models/t2s.py:690-723): dx [B*T, H] bf16 -> classifier.weight rows (d_ans_w), OCR rows
+ * of the joint embedding gradient (d_ocr_emb, same strides as ocr_emb), position / token_type tables, three LNs */
+int t2s_prev_embed_bwd(const void* dx, long long lddx, const long long* prev_inds, int ld_prev, int B, int T, int V,
+                       int H, const float* ans_w, const float* ocr_emb, long long ocr_batch_stride, long long ld_ocr,
+                       const float* pos_emb, const float* type_emb, const float* ans_g, const float* ocr_g,
+                       const float* emb_g, float eps, float* d_ans_w, float* d_ocr_emb, float* d_pos, float* d_type,
+                       float* d_ans_g, float* d_ans_b, float* d_ocr_g, float* d_ocr_b, float* d_emb_g, float* d_emb_b,
+                       void* stream);
+/* backward of t2s_ocr_finish: dh (bf16) = gradient of linear_ocr_feat_to_mmt_in's output; dc_ws [rows, H] fp32 scratch
+ * = gradient of linear_ocr_bbox_to_mmt_in's output; accumulates both LayerNorms, both biases and dW2 [H, 4] */
+int t2s_ocr_finish_bwd(const float* h, long long ldh, const float* bbox, const float* w2, const float* b2,
+                       const float* g1, const float* g2, float eps, int rows, int H, const float* dout, long long ldd,
+                       int dy_rows_per_group, int dy_group_rows, int dy_row_off, void* dh, long long lddh, float* dc_ws,
+                       long long lddc, float* dg1, float* db1, float* dg2, float* db2ln, float* dbias1, float* dw2,
+                       float* db2, void* stream);
+/* BertEmbeddings backward: dy [rows, H] bf16 -> word (padding_idx 0 skipped) / position / token_type tables + LN */
+int t2s_bert_embed_bwd(const void* dy, long long lddy, const long long* ids, int rows, int L, int H, const float* word,
+                       const float* pos, const float* type0, const float* gamma, float eps, float* d_word, float* d_pos,
+                       float* d_type, float* dgamma, float* dbeta, void* stream);
+/* attention backward, recompute style (csrc/attn_bwd.cu): encoder rows [B*Le] + optional decoder rows [B*T] with the
+ * prefix-LM mask of models/t2s.py:609-618; q|k|v, context, context gradient in; dq|dk|dv out.  max_keys >= max n_keys. */
+long long t2s_attn_bwd_workspace_bytes(int B, int Le, int T, int heads);
+int t2s_attn_bwd(const void* qkv_enc, long long ld_enc, const void* qkv_dec, long long ld_dec, const void* o_enc,
+                 long long ldo_enc, const void* o_dec, long long ldo_dec, const void* do_enc, long long ldg_enc,
+                 const void* do_dec, long long ldg_dec, void* dqkv_enc, long long ldq_enc, void* dqkv_dec,
+                 long long ldq_dec, int B, int Le, int T, int H, int heads, const int* key_idx, const int* n_keys,
+                 int key_stride, int max_keys, void* workspace, void* stream);
+/* loss backward (modules/losses.py:329-343, 361-385): grad_out = device scalar dL/dloss (carries the loss weight) */
+long long t2s_loss_bwd_workspace_bytes(int B, int T);
+int t2s_nce_rowstats(const float* ref, const float* pos, const float* neg, int rows, int N, float* stats, void* stream);
+int t2s_pos_bce_loss_bwd(const float* scores, const float* targets, const float* loss_mask, int B, int T, int N,
+                         const float* grad_out, float* dscores, int accumulate, void* stream);
+int t2s_info_nce_loss_bwd(const float* ref, const float* pos, const float* neg, int B, int T, int N, float temperature,
+                          void* workspace, const float* grad_out, float* dref, float* dpos, float* dneg, int accumulate,
+                          void* stream);
+/* clip_grad_norm_ + torch.optim.Adam over a flat fp32 range: out[0] = sum g^2 (workspace: 1024 doubles); the step
+ * scales g by grad_scale * min(1, max_norm / (sqrt(sumsq) * grad_scale + 1e-6)) (max_norm <= 0: no clipping) */
+int t2s_sumsq(const float* g, long long n, void* workspace, float* out, void* stream);
+int t2s_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, int step, const float* sumsq, float max_norm, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,464 @@
+// K8c: backward of the masked multi-head attention (head size 64), recompute style -- no probabilities are saved.
+//
+// Replaces what autograd runs for BertSelfAttention's matmul / +mask / softmax / matmul chain (pytorch_transformers
+// modeling_bert, reached from reference pythia/models/t2s.py:423,538,622) under loss.backward()
+// (pythia/trainers/base_trainer.py:264), for both mask shapes of the reference: the key-padding mask of TextBert / QTV
+// (t2s.py:413-419,533-534) and the prefix-LM mask of the answer transformer (t2s.py:609-618).
+//
+// Per (sample, head) the problem is a "virtual sequence": queries i in [0, Le + T) -- Le encoder rows then T decoder
+// rows (T may be 0) -- and keys j in [0, nk + T): the nk valid encoder keys of the compacted key list, then the
+// decoder rows.  allowed(i, j) = j < nk  ||  (i >= Le && j - nk <= i - Le).  Masked keys are skipped exactly as in the
+// forward kernels (exp(-10000 - max) == 0 in fp32).
+//
+// Three kernels, all bf16 mma.sync m16n8k16 with fp32 accumulation, 64 x 64 tiles, K/V (or Q/dO) tiles double
+// buffered with cp.async into XOR-swizzled shared memory:
+//   attn_bwd_stats   lse2[i] = log2 sum_j exp2(s_ij) (s in the exp2 domain) and D[i] = dO_i . O_i
+//   attn_bwd_dq      per 64-query tile, loop over key tiles:  P = exp2(S - lse), dP = dO V^T, dS = P (dP - D) / 8,
+//                    dQ += dS K
+//   attn_bwd_dkv     per 64-key tile, loop over query tiles: the transposed products; dV += P^T dO, dK += dS^T Q
+// No atomics: every dQ / dK / dV row is written by exactly one CTA (rows that are not in a key list keep the zeros
+// the entry point memsets), so the result is run-to-run identical.
+#include "common.cuh"
+#include "../../include/t2s_b200.h"
+
+namespace t2s {
+
+constexpr int XB = 64;               // tile edge (queries and keys)
+constexpr int XB_THREADS = 128;      // 4 warps x 16 rows
+constexpr int XDH = 64;
+
+__device__ __forceinline__ void xb_ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void xb_ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void xb_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t xb_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+struct AttnBwdArgs {
+    const __nv_bfloat16* qkv_enc; long long ld_enc;        // [B*Le, >= 3H]: q | k | v at columns 0, H, 2H
+    const __nv_bfloat16* qkv_dec; long long ld_dec;        // [B*T, >= 3H] (null when T == 0)
+    const __nv_bfloat16* o_enc; long long ldo_enc;         // forward output (context) rows
+    const __nv_bfloat16* o_dec; long long ldo_dec;
+    const __nv_bfloat16* do_enc; long long ldg_enc;        // gradient of the context rows
+    const __nv_bfloat16* do_dec; long long ldg_dec;
+    __nv_bfloat16* dqkv_enc; long long ldq_enc;            // outputs: dq | dk | dv, same column layout
+    __nv_bfloat16* dqkv_dec; long long ldq_dec;
+    const int* key_idx; const int* n_keys; int key_stride;
+    float* stats;                                           // [B, heads, Le + T, 2] = {lse2, D}
+    int Le, T, H, heads;
+    float scale_log2, scale;
+};
+
+// row resolvers of the virtual sequence (sample b); column offset `col` in elements
+__device__ __forceinline__ const __nv_bfloat16* xb_qrow(const AttnBwdArgs& a, const __nv_bfloat16* enc, long long ld_e,
+                                                        const __nv_bfloat16* dec, long long ld_d, int b, int i) {
+    return i < a.Le ? enc + ((long long)b * a.Le + i) * ld_e : dec + ((long long)b * a.T + (i - a.Le)) * ld_d;
+}
+__device__ __forceinline__ long long xb_krow_index(const AttnBwdArgs& a, const int* kidx, int nk, int j, bool& is_dec) {
+    is_dec = j >= nk;
+    return is_dec ? (long long)(j - nk) : (long long)kidx[j];
+}
+
+// load a [64 x 64] bf16 tile of query-side rows i0.. (zero-filled past n_rows) from the (enc | dec) pair of buffers
+__device__ __forceinline__ void xb_load_qtile(uint8_t* dst, const AttnBwdArgs& a, const __nv_bfloat16* enc, long long ld_e,
+                                              const __nv_bfloat16* dec, long long ld_d, int b, int i0, int n_rows, int col) {
+    for (int t = threadIdx.x; t < XB * 8; t += XB_THREADS) {
+        const int r = t >> 3, c = t & 7;
+        const bool ok = i0 + r < n_rows;
+        const __nv_bfloat16* src = xb_qrow(a, enc, ld_e, dec, ld_d, b, ok ? i0 + r : 0) + col + c * 8;
+        cp_async16(dst + xb_off(r, c), src, ok);
+    }
+}
+// load a [64 x 64] tile of key-side rows j0.. of the virtual key list
+__device__ __forceinline__ void xb_load_ktile(uint8_t* dst, const AttnBwdArgs& a, const __nv_bfloat16* enc, long long ld_e,
+                                              const __nv_bfloat16* dec, long long ld_d, int b, const int* kidx, int nk,
+                                              int j0, int n_keys_v, int col) {
+    for (int t = threadIdx.x; t < XB * 8; t += XB_THREADS) {
+        const int r = t >> 3, c = t & 7;
+        const bool ok = j0 + r < n_keys_v;
+        bool is_dec = false;
+        const long long row = ok ? xb_krow_index(a, kidx, nk, j0 + r, is_dec) : 0;
+        const __nv_bfloat16* src = (is_dec ? dec + ((long long)b * a.T + row) * ld_d : enc + ((long long)b * a.Le + row) * ld_e) + col + c * 8;
+        cp_async16(dst + xb_off(r, c), src, ok);
+    }
+}
+__device__ __forceinline__ bool xb_allowed(int i, int j, int Le, int nk) { return j < nk || (i >= Le && (j - nk) <= (i - Le)); }
+
+// A fragments (4 k-steps over the 64 head dims) of this warp's 16 rows of a [64 x 64] tile
+__device__ __forceinline__ void xb_load_afrags(uint32_t (&f)[4][4], const uint8_t* tile, int warp, int lane) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+        xb_ldmatrix_x4(f[ks], smem_u32(tile + xb_off(warp * 16 + (lane & 15), ks * 2 + (lane >> 4))));
+}
+// C[16 x 64] = A[16 x 64(d)] . Bt, Bt tile stored [n][d] (n = 64 rows of the tile): c[n8][4]
+__device__ __forceinline__ void xb_mma_nt(float (&c)[8][4], const uint32_t (&af)[4][4], const uint8_t* tile, int lane) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[n][j] = 0.f;
+#pragma unroll
+    for (int np = 0; np < 4; ++np)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t bf[4];
+            const int row = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+            const int chunk = ks * 2 + ((lane >> 3) & 1);
+            xb_ldmatrix_x4(bf, smem_u32(tile + xb_off(row, chunk)));
+            xb_mma(c[np * 2], af[ks], bf[0], bf[1]);
+            xb_mma(c[np * 2 + 1], af[ks], bf[2], bf[3]);
+        }
+}
+// acc[16 x 64(d)] += P[16 x 64(k)] . B, B tile stored [k][d]: pf = A fragments over the 64 k rows
+__device__ __forceinline__ void xb_mma_nn(float (&acc)[8][4], const uint32_t (&pf)[4][4], const uint8_t* tile, int lane) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+            uint32_t bf[4];
+            const int row = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+            const int chunk = dp * 2 + (lane >> 4);
+            xb_ldmatrix_x4_trans(bf, smem_u32(tile + xb_off(row, chunk)));
+            xb_mma(acc[dp * 2], pf[ks], bf[0], bf[1]);
+            xb_mma(acc[dp * 2 + 1], pf[ks], bf[2], bf[3]);
+        }
+}
+// C tile (fp32, [16 x 64]) -> A fragments for the next product
+__device__ __forceinline__ void xb_c_to_a(uint32_t (&pf)[4][4], const float (&c)[8][4]) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        const int ks = n >> 1, hi = n & 1;
+        pf[ks][hi * 2 + 0] = pack_bf16x2(c[n][0], c[n][1]);
+        pf[ks][hi * 2 + 1] = pack_bf16x2(c[n][2], c[n][3]);
+    }
+}
+
+// ------------------------------------------------------------------------------- stats: lse2 and D per query
+__global__ void __launch_bounds__(XB_THREADS)
+attn_bwd_stats_kernel(AttnBwdArgs a) {
+    __shared__ __align__(128) uint8_t Qs[XB * 128];
+    __shared__ __align__(128) uint8_t Ks[2][XB * 128];
+    const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * XB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const int nq = a.Le + a.T;
+    const int nk = a.n_keys[b];
+    const int* kidx = a.key_idx + (long long)b * a.key_stride;
+    // only tiles that contain decoder rows can see decoder keys
+    const int nkv = (i0 + XB > a.Le) ? nk + a.T : nk;
+    const int ntiles = (nkv + XB - 1) / XB;
+    const int col = h * XDH;
+
+    xb_load_qtile(Qs, a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, i0, nq, col);
+    xb_load_ktile(Ks[0], a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, kidx, nk, 0, nkv, a.H + col);
+    cp_async_commit();
+    float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
+    uint32_t qf[4][4];
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < ntiles)
+            xb_load_ktile(Ks[buf ^ 1], a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, kidx, nk, (t + 1) * XB, nkv, a.H + col);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (t == 0) xb_load_afrags(qf, Qs, warp, lane);
+        float s[8][4];
+        xb_mma_nt(s, qf, Ks[buf], lane);
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int key = t * XB + n * 8 + tq * 2 + (j & 1);
+                const int qi = i0 + warp * 16 + g + (j >> 1) * 8;
+                float v = s[n][j] * a.scale_log2;
+                if (key >= nkv || !xb_allowed(qi, key, a.Le, nk)) v = -INFINITY;
+                s[n][j] = v;
+                mx[j >> 1] = fmaxf(mx[j >> 1], v);
+            }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float m_new = fmaxf(m_i[r], mx[r]);
+            const float corr = m_new == -INFINITY ? 1.f : exp2f(m_i[r] - m_new);
+            float rs = 0.f;
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                if (m_new != -INFINITY) rs += exp2f(s[n][r * 2] - m_new) + exp2f(s[n][r * 2 + 1] - m_new);
+            }
+            l_i[r] = l_i[r] * corr + rs;
+            m_i[r] = m_new;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 1);
+        l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 2);
+    }
+    // D = dO . O: lane quartet shares a row; each lane sums 16 of the 64 dims
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int qi = i0 + warp * 16 + g + r * 8;
+        float d = 0.f;
+        if (qi < nq) {
+            const __nv_bfloat16* op = xb_qrow(a, a.o_enc, a.ldo_enc, a.o_dec, a.ldo_dec, b, qi) + col + tq * 16;
+            const __nv_bfloat16* gp = xb_qrow(a, a.do_enc, a.ldg_enc, a.do_dec, a.ldg_dec, b, qi) + col + tq * 16;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const uint4 ov = *reinterpret_cast<const uint4*>(op + c * 8);
+                const uint4 gv = *reinterpret_cast<const uint4*>(gp + c * 8);
+                d += bf16lo(ov.x) * bf16lo(gv.x) + bf16hi(ov.x) * bf16hi(gv.x) + bf16lo(ov.y) * bf16lo(gv.y) + bf16hi(ov.y) * bf16hi(gv.y)
+                   + bf16lo(ov.z) * bf16lo(gv.z) + bf16hi(ov.z) * bf16hi(gv.z) + bf16lo(ov.w) * bf16lo(gv.w) + bf16hi(ov.w) * bf16hi(gv.w);
+            }
+        }
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        if (qi < nq && tq == 0) {
+            float* st = a.stats + (((long long)b * a.heads + h) * nq + qi) * 2;
+            st[0] = m_i[r] + log2f(l_i[r]);
+            st[1] = d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- dQ
+__global__ void __launch_bounds__(XB_THREADS)
+attn_bwd_dq_kernel(AttnBwdArgs a) {
+    __shared__ __align__(128) uint8_t QG[2][XB * 128];       // Q tile, dO tile (only read at t == 0)
+    __shared__ __align__(128) uint8_t Ks[2][XB * 128];
+    __shared__ __align__(128) uint8_t Vs[2][XB * 128];
+    const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * XB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const int nq = a.Le + a.T;
+    const int nk = a.n_keys[b];
+    const int* kidx = a.key_idx + (long long)b * a.key_stride;
+    const int nkv = (i0 + XB > a.Le) ? nk + a.T : nk;
+    const int ntiles = (nkv + XB - 1) / XB;
+    const int col = h * XDH;
+
+    xb_load_qtile(QG[0], a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, i0, nq, col);
+    xb_load_qtile(QG[1], a, a.do_enc, a.ldg_enc, a.do_dec, a.ldg_dec, b, i0, nq, col);
+    auto load_kv = [&](int t, int buf) {
+        xb_load_ktile(Ks[buf], a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, kidx, nk, t * XB, nkv, a.H + col);
+        xb_load_ktile(Vs[buf], a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, kidx, nk, t * XB, nkv, 2 * a.H + col);
+    };
+    load_kv(0, 0);
+    cp_async_commit();
+    float lse[2], dd[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int qi = i0 + warp * 16 + g + r * 8;
+        const float* st = a.stats + (((long long)b * a.heads + h) * nq + (qi < nq ? qi : 0)) * 2;
+        lse[r] = st[0];
+        dd[r] = st[1];
+    }
+    float dq[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dq[n][j] = 0.f;
+    uint32_t qf[4][4], gf[4][4];
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < ntiles) load_kv(t + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (t == 0) {
+            xb_load_afrags(qf, QG[0], warp, lane);
+            xb_load_afrags(gf, QG[1], warp, lane);
+        }
+        float s[8][4], dp[8][4];
+        xb_mma_nt(s, qf, Ks[buf], lane);
+        xb_mma_nt(dp, gf, Vs[buf], lane);
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int key = t * XB + n * 8 + tq * 2 + (j & 1);
+                const int r = j >> 1;
+                const int qi = i0 + warp * 16 + g + r * 8;
+                const bool ok = key < nkv && xb_allowed(qi, key, a.Le, nk);
+                const float p = ok ? exp2f(s[n][j] * a.scale_log2 - lse[r]) : 0.f;
+                s[n][j] = p * (dp[n][j] - dd[r]) * a.scale;          // dS
+            }
+        uint32_t dsf[4][4];
+        xb_c_to_a(dsf, s);
+        xb_mma_nn(dq, dsf, Ks[buf], lane);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int qi = i0 + warp * 16 + g + r * 8;
+        if (qi < nq) {
+            __nv_bfloat16* op = (qi < a.Le ? a.dqkv_enc + ((long long)b * a.Le + qi) * a.ldq_enc
+                                           : a.dqkv_dec + ((long long)b * a.T + (qi - a.Le)) * a.ldq_dec) + col + tq * 2;
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+                *reinterpret_cast<uint32_t*>(op + n * 8) = pack_bf16x2(dq[n][r * 2], dq[n][r * 2 + 1]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- dK, dV
+constexpr int XB_DKV_SMEM = 2 * XB * 128 /*K,V own tiles*/ + 2 * 2 * XB * 128 /*Q,dO x 2 stages*/ + 2 * 2 * XB * 4 /*stats*/;
+
+__global__ void __launch_bounds__(XB_THREADS)
+attn_bwd_dkv_kernel(AttnBwdArgs a) {
+    extern __shared__ __align__(128) uint8_t xsm[];
+    uint8_t* KV = xsm;                                   // [2][64*128]: this CTA's K tile, V tile
+    uint8_t* Qs = KV + 2 * XB * 128;                     // [2 stages][64*128]
+    uint8_t* Gs = Qs + 2 * XB * 128;                     // [2 stages][64*128] dO
+    float* Ss = reinterpret_cast<float*>(Gs + 2 * XB * 128);     // [2 stages][2][64]: lse2, D
+    const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * XB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const int nq = a.Le + a.T;
+    const int nk = a.n_keys[b];
+    const int nkv = nk + a.T;
+    if (j0 >= nkv) return;
+    const int* kidx = a.key_idx + (long long)b * a.key_stride;
+    const int col = h * XDH;
+    // a key tile made only of decoder keys is seen by decoder queries only
+    const int i_first = (j0 >= nk) ? (a.Le / XB) * XB : 0;
+    const int ntiles = (nq - i_first + XB - 1) / XB;
+
+    xb_load_ktile(KV, a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, kidx, nk, j0, nkv, a.H + col);
+    xb_load_ktile(KV + XB * 128, a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, kidx, nk, j0, nkv, 2 * a.H + col);
+    auto load_q = [&](int t, int buf) {
+        const int i0 = i_first + t * XB;
+        xb_load_qtile(Qs + buf * XB * 128, a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, i0, nq, col);
+        xb_load_qtile(Gs + buf * XB * 128, a, a.do_enc, a.ldg_enc, a.do_dec, a.ldg_dec, b, i0, nq, col);
+        if (threadIdx.x < XB) {
+            const int qi = i0 + threadIdx.x;
+            const float* st = a.stats + (((long long)b * a.heads + h) * nq + (qi < nq ? qi : 0)) * 2;
+            Ss[(buf * 2 + 0) * XB + threadIdx.x] = st[0];
+            Ss[(buf * 2 + 1) * XB + threadIdx.x] = st[1];
+        }
+    };
+    load_q(0, 0);
+    cp_async_commit();
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dk[n][j] = 0.f; dv[n][j] = 0.f; }
+    uint32_t kf[4][4], vf[4][4];
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        const int i0 = i_first + t * XB;
+        if (t + 1 < ntiles) load_q(t + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (t == 0) {
+            xb_load_afrags(kf, KV, warp, lane);
+            xb_load_afrags(vf, KV + XB * 128, warp, lane);
+        }
+        const uint8_t* qt = Qs + buf * XB * 128;
+        const uint8_t* gt = Gs + buf * XB * 128;
+        const float* lse_s = Ss + (buf * 2 + 0) * XB;
+        const float* d_s = Ss + (buf * 2 + 1) * XB;
+        float st[8][4], dpt[8][4];
+        xb_mma_nt(st, kf, qt, lane);          // S^T  [keys x queries]
+        xb_mma_nt(dpt, vf, gt, lane);         // dP^T = V . dO^T
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int qc = n * 8 + tq * 2 + (j & 1);
+                const int qi = i0 + qc;
+                const int key = j0 + warp * 16 + g + (j >> 1) * 8;
+                const bool ok = qi < nq && key < nkv && xb_allowed(qi, key, a.Le, nk);
+                const float p = ok ? exp2f(st[n][j] * a.scale_log2 - lse_s[qc]) : 0.f;
+                st[n][j] = p;                                          // P^T
+                dpt[n][j] = p * (dpt[n][j] - d_s[qc]) * a.scale;       // dS^T
+            }
+        uint32_t pf[4][4];
+        xb_c_to_a(pf, st);
+        xb_mma_nn(dv, pf, gt, lane);          // dV += P^T . dO
+        xb_c_to_a(pf, dpt);
+        xb_mma_nn(dk, pf, qt, lane);          // dK += dS^T . Q
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int key = j0 + warp * 16 + g + r * 8;
+        if (key < nkv) {
+            bool is_dec = false;
+            const long long row = xb_krow_index(a, kidx, nk, key, is_dec);
+            __nv_bfloat16* op = (is_dec ? a.dqkv_dec + ((long long)b * a.T + row) * a.ldq_dec
+                                        : a.dqkv_enc + ((long long)b * a.Le + row) * a.ldq_enc) + col + tq * 2;
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                *reinterpret_cast<uint32_t*>(op + a.H + n * 8) = pack_bf16x2(dk[n][r * 2], dk[n][r * 2 + 1]);
+                *reinterpret_cast<uint32_t*>(op + 2 * a.H + n * 8) = pack_bf16x2(dv[n][r * 2], dv[n][r * 2 + 1]);
+            }
+        }
+    }
+}
+
+}  // namespace t2s
+
+using namespace t2s;
+
+extern "C" long long t2s_attn_bwd_workspace_bytes(int B, int Le, int T, int heads) {
+    return (long long)B * heads * (Le + T) * 2 * sizeof(float);
+}
+
+extern "C" int t2s_attn_bwd(const void* qkv_enc, long long ld_enc, const void* qkv_dec, long long ld_dec,
+                            const void* o_enc, long long ldo_enc, const void* o_dec, long long ldo_dec,
+                            const void* do_enc, long long ldg_enc, const void* do_dec, long long ldg_dec,
+                            void* dqkv_enc, long long ldq_enc, void* dqkv_dec, long long ldq_dec, int B, int Le, int T,
+                            int H, int heads, const int* key_idx, const int* n_keys, int key_stride, int max_keys,
+                            void* workspace, void* stream) {
+    if (H != heads * XDH || B <= 0 || Le <= 0 || T < 0 || max_keys <= 0) {
+        set_error("attn_bwd: head size must be 64 (H %d heads %d B %d Le %d T %d)", H, heads, B, Le, T);
+        return T2S_ERR_SHAPE;
+    }
+    if ((ld_enc % 8) || (ldo_enc % 8) || (ldg_enc % 8) || (ldq_enc % 8) ||
+        (T > 0 && ((ld_dec % 8) || (ldo_dec % 8) || (ldg_dec % 8) || (ldq_dec % 8) || !qkv_dec || !o_dec || !do_dec || !dqkv_dec))) {
+        set_error("attn_bwd: row pitches must be multiples of 8 and the decoder buffers present when T > 0");
+        return T2S_ERR_ALIGN;
+    }
+    typedef __nv_bfloat16 bf;
+    AttnBwdArgs a;
+    a.qkv_enc = reinterpret_cast<const bf*>(qkv_enc); a.ld_enc = ld_enc;
+    a.qkv_dec = reinterpret_cast<const bf*>(qkv_dec); a.ld_dec = ld_dec;
+    a.o_enc = reinterpret_cast<const bf*>(o_enc); a.ldo_enc = ldo_enc;
+    a.o_dec = reinterpret_cast<const bf*>(o_dec); a.ldo_dec = ldo_dec;
+    a.do_enc = reinterpret_cast<const bf*>(do_enc); a.ldg_enc = ldg_enc;
+    a.do_dec = reinterpret_cast<const bf*>(do_dec); a.ldg_dec = ldg_dec;
+    a.dqkv_enc = reinterpret_cast<bf*>(dqkv_enc); a.ldq_enc = ldq_enc;
+    a.dqkv_dec = reinterpret_cast<bf*>(dqkv_dec); a.ldq_dec = ldq_dec;
+    a.key_idx = key_idx; a.n_keys = n_keys; a.key_stride = key_stride;
+    a.stats = reinterpret_cast<float*>(workspace);
+    a.Le = Le; a.T = T; a.H = H; a.heads = heads;
+    a.scale = 0.125f;
+    a.scale_log2 = 0.125f * 1.4426950408889634f;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // rows outside the key list receive no dK / dV: clear the k | v columns (q columns are fully written by dq)
+    cudaError_t e = cudaMemset2DAsync(reinterpret_cast<bf*>(dqkv_enc) + H, ldq_enc * sizeof(bf), 0, 2 * (size_t)H * sizeof(bf),
+                                      (size_t)B * Le, st);
+    if (e != cudaSuccess) { set_error("attn_bwd memset: %s", cudaGetErrorString(e)); return (int)e; }
+    static bool attr = false;
+    if (!attr) {
+        e = cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XB_DKV_SMEM);
+        if (e != cudaSuccess) { set_error("attn_bwd attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr = true;
+    }
+    const int nq = Le + T;
+    dim3 gq((nq + XB - 1) / XB, heads, B);
+    attn_bwd_stats_kernel<<<gq, XB_THREADS, 0, st>>>(a);
+    attn_bwd_dq_kernel<<<gq, XB_THREADS, 0, st>>>(a);
+    dim3 gk((max_keys + T + XB - 1) / XB, heads, B);
+    attn_bwd_dkv_kernel<<<gk, XB_THREADS, XB_DKV_SMEM, st>>>(a);
+    return launch_status("attn_bwd");
+}

@@ -92,6 +92,24 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(-ah, e, h + ah);      // h + |h| erf(t) = h (1 + sign(x) erf(t))
 }
 
+// d/dx of the GELU above: Phi(x) + x phi(x), same erf approximation (used by the dgrad epilogue of the FFN)
+__device__ __forceinline__ float gelu_grad(float x) {
+    const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
+    float q = -8.592197123e-05f;
+    q = fmaf(q, t, 3.653188699e-04f);
+    q = fmaf(q, t, 2.547933478e-03f);
+    q = fmaf(q, t, -2.975212620e-02f);
+    q = fmaf(q, t, 1.491437337e-01f);
+    q = fmaf(q, t, 9.182796953e-01f);
+    q = fmaf(q, t, 1.627918195e+00f);
+    float e, g;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t * q));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(-0.72134752044448170368f * x * x));     // exp(-x^2 / 2)
+    const float erf_abs = 1.0f - e;                                   // erf(|x| / sqrt 2)
+    const float cdf = 0.5f + copysignf(0.5f * erf_abs, x);
+    return fmaf(x * 0.39894228040143267794f, g, cdf);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -159,6 +177,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* desc, ui
 // 2D tiled TMA store of a shared-memory box (bulk-group completion); clips to the tensor bounds
 __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(desc),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// same box, but added into global memory (fp32 red.add performed at L2; used by the split-K weight-gradient GEMM)
+__device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(desc),
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                  : "memory");
 }
@@ -244,6 +268,18 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// MN-major bf16 operand (rows = K index, 64 contiguous M/N elements = one 128-byte row, 128B swizzle -- what a TMA
+// box of [rows x 64 columns] of a row-major matrix produces): 8-row K groups `SBO` = 1024 B apart, 64-element
+// atoms along M/N `lbo_bytes` apart (cute: Swizzle<3,4,3> o ((8,8,m),(8,k)):((1,8,LBO),(64,SBO))).
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;

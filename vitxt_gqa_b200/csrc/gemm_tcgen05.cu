@@ -165,6 +165,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const bool out_f32 = ep.flags & T2S_GEMM_OUT_F32;
         const bool res_f32 = ep.flags & T2S_GEMM_RES_F32;
         const bool out_split = ep.flags & T2S_GEMM_OUT_SPLIT;
+        const bool dgelu = ep.flags & T2S_GEMM_DGELU;
         uint8_t* box = staging + ew * 4096;      // this warp's staging box: 32 rows x 128 B, 128B swizzle
         uint8_t* my_row = box + lane * 128;
         const int sw = lane & 7;
@@ -208,17 +209,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
                     if (ep.residual && row_ok) {
+                        // residual add, or (T2S_GEMM_DGELU) multiply by GELU'(aux) of the saved pre-activation
+                        auto comb = [dgelu](float acc_v, float aux) { return dgelu ? acc_v * gelu_grad(aux) : acc_v + aux; };
                         if (res_f32) {
                             const float* rp = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + col0;
                             if (full32) {
 #pragma unroll
                                 for (int j = 0; j < 32; j += 4) {
                                     const float4 a = *reinterpret_cast<const float4*>(rp + j);
-                                    v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+                                    v[j] = comb(v[j], a.x); v[j + 1] = comb(v[j + 1], a.y);
+                                    v[j + 2] = comb(v[j + 2], a.z); v[j + 3] = comb(v[j + 3], a.w);
                                 }
                             } else {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] += rp[j];
+                                for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] = comb(v[j], rp[j]);
                             }
                         } else {
                             const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + col0;
@@ -226,12 +230,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                                 for (int j = 0; j < 32; j += 8) {
                                     const uint4 a = *reinterpret_cast<const uint4*>(rp + j);
-                                    v[j] += bf16lo(a.x); v[j + 1] += bf16hi(a.x); v[j + 2] += bf16lo(a.y); v[j + 3] += bf16hi(a.y);
-                                    v[j + 4] += bf16lo(a.z); v[j + 5] += bf16hi(a.z); v[j + 6] += bf16lo(a.w); v[j + 7] += bf16hi(a.w);
+                                    v[j] = comb(v[j], bf16lo(a.x)); v[j + 1] = comb(v[j + 1], bf16hi(a.x));
+                                    v[j + 2] = comb(v[j + 2], bf16lo(a.y)); v[j + 3] = comb(v[j + 3], bf16hi(a.y));
+                                    v[j + 4] = comb(v[j + 4], bf16lo(a.z)); v[j + 5] = comb(v[j + 5], bf16hi(a.z));
+                                    v[j + 6] = comb(v[j + 6], bf16lo(a.w)); v[j + 7] = comb(v[j + 7], bf16hi(a.w));
                                 }
                             } else {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] += __bfloat162float(rp[j]);
+                                for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] = comb(v[j], __bfloat162float(rp[j]));
                             }
                         }
                     }
@@ -398,6 +404,204 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     return launch_status("gemm_bf16_tcgen05");
 }
 
+
+// ------------------------------------------------------------------------------------ K8b: weight-gradient GEMM
+// dW[P, Q] += sum_r G[r, P]^T . X[r, Q]      (P = out features, Q = in features, r = the M rows of the layer)
+//
+// Replaces the `addmm` autograd issues for nn.Linear.weight.grad (reference: loss.backward() in
+// pythia/trainers/base_trainer.py:264 over every Linear of pythia/models/t2s.py).  Both operands are read as they
+// lie in HBM (row-major [rows, features], the layout the forward wrote): a TMA box of [64 rows x 64 features] is an
+// MN-major 128B-swizzled operand tile, so no transposed copy of the activations is ever made.  The contraction runs
+// over the rows: split into `splits` row ranges so that tiles x splits fills the SMs; each work item accumulates
+// its range in TMEM and adds its 128 x BN fp32 tile into dW with TMA reduce-add (fp32 red at L2) -- the same
+// instruction also accumulates the contributions of the three grounding variants and of encoder / decoder rows.
+// Warp roles and pipeline as in gemm_bf16_tcgen05_kernel.
+template <int BN>
+struct WgradCfg {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;         // two [64 x 64] boxes
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;              // BN / 64 boxes
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * 4096;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
+                          const __grid_constant__ CUtensorMap tmD, int rows, int P, int Q, int splits,
+                          int kb_per_split) {
+    using Cfg = WgradCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_q = (Q + BN - 1) / BN;
+    const int num_p = (P + GEMM_BM - 1) / GEMM_BM;
+    const int tiles = num_p * num_q;
+    const int items = tiles * splits;             // item = split * tiles + tile: neighbours share a row range in L2
+    const int kb_total = (rows + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmG);
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmD);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(&tfull[a], 1);
+                mbar_init(&tempty[a], GEMM_EPI_WARPS);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int split = item / tiles, tile = item - split * tiles;
+            const int p0 = (tile / num_q) * GEMM_BM, q0 = (tile % num_q) * BN;
+            const int kb0 = split * kb_per_split;
+            const int kb1 = min(kb_total, kb0 + kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                if (lane == 0) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    const int r = kb * GEMM_BK;
+                    tma_load_2d(sa, &tmG, &full[stage], p0, r);
+                    tma_load_2d(sa + 8192, &tmG, &full[stage], p0 + 64, r);
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_load_2d(sa + Cfg::A_BYTES + j * 8192, &tmX, &full[stage], q0 + 64 * j, r);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN) | (1u << 15) | (1u << 16);    // A and B MN-major
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int split = item / tiles;
+            const int kb0 = split * kb_per_split;
+            const int kb1 = min(kb_total, kb0 + kb_per_split);
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        // 16 rows of the contraction = two 8-row groups = 2048 B
+                        const uint64_t da = make_sw128_mnmajor_desc_lbo(sa + k * 2048, 8192);
+                        const uint64_t db = make_sw128_mnmajor_desc_lbo(sa + Cfg::A_BYTES + k * 2048, 8192);
+                        umma_bf16(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (kb == kb1 - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    } else {
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int half = ew >> 2;
+        constexpr int COLS_PER_WARP = BN / 2;
+        uint8_t* box = staging + ew * 4096;
+        uint8_t* my_row = box + lane * 128;
+        const int sw = lane & 7;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int split = item / tiles, tile = item - split * tiles;
+            const int p0 = (tile / num_q) * GEMM_BM, q0 = (tile % num_q) * BN;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const int row0 = p0 + quarter * 32;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
+                uint32_t r[32];
+                const int cw = half * COLS_PER_WARP + c0;
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cw, r);
+                tmem_ld_wait();
+                const int col0 = q0 + cw;
+                if (col0 >= Q || row0 >= P) continue;      // warp-uniform; the tensor map clips partial boxes
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<uint4*>(my_row + ((c ^ sw) << 4)) =
+                        make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_reduce_add_2d(&tmD, box, col0, row0);
+                    tma_store_commit();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensorMap& td, int rows, int P, int Q,
+                        int splits, int kb_per_split, cudaStream_t st) {
+    using Cfg = WgradCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad BN=%d): %s", BN, cudaGetErrorString(e)); return (int)e; }
+        attr_set = true;
+    }
+    const int items = ((P + GEMM_BM - 1) / GEMM_BM) * ((Q + BN - 1) / BN) * splits;
+    const int grid = items < num_sms() ? items : num_sms();
+    gemm_wgrad_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tg, tx, td, rows, P, Q, splits, kb_per_split);
+    return launch_status("gemm_wgrad_tcgen05");
+}
+
 }  // namespace t2s
 
 using namespace t2s;
@@ -467,4 +671,38 @@ extern "C" int t2s_gemm_bf16x3(const void* A, long long lda, const void* W, long
                                const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K,
                                int flags, int block_n, void* stream) {
     return gemm_entry("gemm_bf16x3", true, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, flags, block_n, stream);
+}
+
+extern "C" int t2s_gemm_wgrad_bf16(const void* G, long long ldg, const void* X, long long ldx, float* dW, long long ldd,
+                                   int rows, int P, int Q, int splits, void* stream) {
+    if (rows <= 0 || P <= 0 || Q <= 0) { set_error("gemm_wgrad: bad shape %d %d %d", rows, P, Q); return T2S_ERR_SHAPE; }
+    if ((ldg % 8) || (ldx % 8) || (ldd % 4) || (reinterpret_cast<uintptr_t>(G) & 15) || (reinterpret_cast<uintptr_t>(X) & 15) ||
+        (reinterpret_cast<uintptr_t>(dW) & 15)) {
+        set_error("gemm_wgrad: operands need 16-byte aligned bases and row pitches (ldg %lld ldx %lld ldd %lld)", ldg, ldx, ldd);
+        return T2S_ERR_ALIGN;
+    }
+    const int bn = Q >= 192 ? 256 : 64;
+    const int tiles = ((P + GEMM_BM - 1) / GEMM_BM) * ((Q + bn - 1) / bn);
+    const int kb_total = (rows + GEMM_BK - 1) / GEMM_BK;
+    if (splits <= 0) {
+        // fill the SMs about four times over, but keep >= 16 k-blocks (1024 rows) per item so that the fp32
+        // reduce-add of the 128 x BN tile stays a small part of the item
+        splits = (4 * num_sms()) / tiles;
+        const int max_splits = (kb_total + 15) / 16;
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    }
+    if (splits > kb_total) splits = kb_total;
+    int kb_per_split = (kb_total + splits - 1) / splits;
+    splits = (kb_total + kb_per_split - 1) / kb_per_split;         // no empty items
+    CUtensorMap tg, tx, td;
+    int rc = make_tmap_2d(&tg, false, G, rows, P, ldg, 64, 64);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tx, false, X, rows, Q, ldx, 64, 64);
+    if (rc) return rc;
+    rc = make_tmap_2d(&td, true, dW, P, Q, ldd, 32, 32);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (bn == 256) return launch_wgrad<256>(tg, tx, td, rows, P, Q, splits, kb_per_split, st);
+    return launch_wgrad<64>(tg, tx, td, rows, P, Q, splits, kb_per_split, st);
 }

@@ -253,6 +253,14 @@ extern "C" int t2s_pos_bce_loss(const float* scores, const float* targets, const
     return launch_status("pos_bce_loss");
 }
 
+/* row statistics {|ref|^2, |pos|^2, |neg|^2, ref.pos, ref.neg} shared by the InfoNCE forward and backward */
+extern "C" int t2s_nce_rowstats(const float* ref, const float* pos, const float* neg, int rows, int N, float* stats,
+                                void* stream) {
+    if (rows <= 0 || N <= 0) { set_error("nce_rowstats: bad shape"); return T2S_ERR_SHAPE; }
+    nce_rowstats_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ref, pos, neg, N, stats);
+    return launch_status("nce_rowstats");
+}
+
 extern "C" int t2s_info_nce_loss(const float* ref, const float* pos, const float* neg, int B, int T, int N,
                                  float temperature, void* workspace, float* out, void* stream) {
     if (B <= 0 || T <= 0 || N <= 0) { set_error("info_nce_loss: bad shape"); return T2S_ERR_SHAPE; }

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libt2s_sm100.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 GEMM_GELU, GEMM_OUT_F32, GEMM_RES_F32, GEMM_OUT_SPLIT = 1, 2, 4, 8
+GEMM_DGELU = 16
 GEMM_SM_CAP_SHIFT = 8     # bits 8..15 of the GEMM flags: cap on the persistent grid
 
 _p, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
@@ -22,6 +23,7 @@ _p, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_flo
 SIGNATURES = {
     "t2s_gemm_bf16": [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p],
     "t2s_gemm_bf16x3": [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p],
+    "t2s_gemm_wgrad_bf16": [_p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p],
     "t2s_split_bf16": [_p, _ll, _i, _i, _i, _p, _ll, _i, _i, _i, _p],
     "t2s_gemm_f32": [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p],
     "t2s_attn_f32": [_p, _ll, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _p, _ll, _p],
@@ -48,9 +50,29 @@ SIGNATURES = {
     "t2s_argmax_feedback": [_p, _ll, _i, _i, _i, _i, _i, _p, _i, _p, _p],
     "t2s_pos_bce_loss": [_p, _p, _p, _i, _i, _i, _p, _p, _p],
     "t2s_info_nce_loss": [_p, _p, _p, _i, _i, _i, _f, _p, _p, _p],
+    # K8 training step
+    "t2s_ln_bwd": [_p, _i, _ll, _p, _i, _ll, _i, _i, _i, _p, _p, _f, _i, _i, _i, _p, _i, _ll, _p, _p, _p, _p],
+    "t2s_colsum": [_p, _i, _ll, _i, _i, _p, _p],
+    "t2s_rows_add": [_p, _p, _p, _ll, _i, _i, _p, _ll, _i, _i, _i, _i, _p],
+    "t2s_gelu_rows": [_p, _i, _ll, _i, _i, _p, _ll, _i, _p],
+    "t2s_embed_scatter_add": [_p, _i, _ll, _i, _i, _p, _i, _ll, _p, _ll, _p],
+    "t2s_ptr_score_bwd": [_p, _ll, _i, _i, _i, _p, _ll, _p, _ll, _ll, _i, _i, _p, _ll, _p, _ll, _ll, _p],
+    "t2s_prev_embed_bwd": [_p, _ll, _p, _i, _i, _i, _i, _i, _p, _p, _ll, _ll, _p, _p, _p, _p, _p, _f,
+                           _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "t2s_ocr_finish_bwd": [_p, _ll, _p, _p, _p, _p, _p, _f, _i, _i, _p, _ll, _i, _i, _i, _p, _ll, _p, _ll,
+                           _p, _p, _p, _p, _p, _p, _p, _p],
+    "t2s_bert_embed_bwd": [_p, _ll, _p, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],
+    "t2s_attn_bwd": [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _i,
+                     _p, _p, _i, _i, _p, _p],
+    "t2s_nce_rowstats": [_p, _p, _p, _i, _i, _p, _p],
+    "t2s_pos_bce_loss_bwd": [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p],
+    "t2s_info_nce_loss_bwd": [_p, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p, _i, _p],
+    "t2s_sumsq": [_p, _ll, _p, _p, _p],
+    "t2s_adam_step": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p, _f, _f, _p],
 }
 PLAIN = {"t2s_abi_version": (_i, []), "t2s_last_error": (ctypes.c_char_p, []),
-         "t2s_loss_workspace_bytes": (_ll, [_i, _i])}
+         "t2s_loss_workspace_bytes": (_ll, [_i, _i]), "t2s_loss_bwd_workspace_bytes": (_ll, [_i, _i]),
+         "t2s_attn_bwd_workspace_bytes": (_ll, [_i, _i, _i, _i])}
 
 EXPORTED_SYMBOLS = sorted(list(SIGNATURES) + list(PLAIN))
 

@@ -1,8 +1,9 @@
 """Registered losses `pos_bce_loss` and `InfoNCE` on the fused CUDA kernels (K7).
 
 Drop-in for reference pythia/modules/losses.py:322-385: same registry keys, same
-`forward(sample_list, model_output)` signature, scalar result.  Forward only in
-this round (the training step's backward is SURVEY 8 config 3, next round).
+`forward(sample_list, model_output)` signature, scalar result.  Each loss is a
+`torch.autograd.Function` over its fused forward / backward kernels, so
+`loss.backward()` of the reference trainer reaches the model's backward schedule.
 """
 import torch
 from torch import nn
@@ -20,6 +21,56 @@ def _dev_f32(t, device):
     return t.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
 
 
+class _BCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores, targets, mask):
+        dev = scores.device
+        B, T, N = scores.shape
+        scores = scores.contiguous()
+        out = torch.empty(1, device=dev, dtype=torch.float32)
+        _lib.get_lib().pos_bce_loss(scores.data_ptr(), targets.data_ptr(), mask.data_ptr(), B, T, N,
+                                    _ws(B, T, dev).data_ptr(), out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        ctx.save_for_backward(scores, targets, mask)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        scores, targets, mask = ctx.saved_tensors
+        B, T, N = scores.shape
+        go = grad_out.detach().reshape(1).float().contiguous()
+        d = torch.empty_like(scores)
+        _lib.get_lib().pos_bce_loss_bwd(scores.data_ptr(), targets.data_ptr(), mask.data_ptr(), B, T, N, go.data_ptr(),
+                                        d.data_ptr(), 0, torch.cuda.current_stream(scores.device).cuda_stream)
+        return d, None, None
+
+
+class _NCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ref, pos, neg, temperature):
+        dev = ref.device
+        B, T, N = ref.shape
+        out = torch.empty(1, device=dev, dtype=torch.float32)
+        _lib.get_lib().info_nce_loss(ref.data_ptr(), pos.data_ptr(), neg.data_ptr(), B, T, N, float(temperature),
+                                     _ws(B, T, dev).data_ptr(), out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        ctx.save_for_backward(ref, pos, neg)
+        ctx.temperature = float(temperature)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ref, pos, neg = ctx.saved_tensors
+        B, T, N = ref.shape
+        dev = ref.device
+        L = _lib.get_lib()
+        go = grad_out.detach().reshape(1).float().contiguous()
+        ws = torch.empty(int(L.loss_bwd_workspace_bytes(B, T)), device=dev, dtype=torch.uint8)
+        d = [torch.empty_like(ref) for _ in range(3)]
+        L.info_nce_loss_bwd(ref.data_ptr(), pos.data_ptr(), neg.data_ptr(), B, T, N, ctx.temperature, ws.data_ptr(),
+                            go.data_ptr(), d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), 0,
+                            torch.cuda.current_stream(dev).cuda_stream)
+        return d[0], d[1], d[2], None
+
+
 @registry.register_loss("pos_bce_loss")
 class POSBCEWithMaskLoss(nn.Module):
     """sum(BCEWithLogits(pos_scores, targets) * loss_mask) / max(sum(loss_mask), 1)
@@ -33,11 +84,7 @@ class POSBCEWithMaskLoss(nn.Module):
         targets = _dev_f32(sample_list["targets"], dev)
         mask = _dev_f32(sample_list["train_loss_mask"], dev)
         assert mask.dim() == 2
-        out = torch.empty(1, device=dev, dtype=torch.float32)
-        L = _lib.get_lib()
-        L.pos_bce_loss(scores.contiguous().data_ptr(), targets.data_ptr(), mask.data_ptr(), B, T, N,
-                       _ws(B, T, dev).data_ptr(), out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
-        return out[0]
+        return _BCEFn.apply(scores, targets, mask)
 
 
 @registry.register_loss("InfoNCE")
@@ -52,10 +99,4 @@ class InfoNCE(nn.Module):
     def forward(self, sample_list, model_output, temperature=0.1, reduction="mean", negative_mode="paired"):
         ref, pos, neg = (model_output[k].contiguous() for k in ("ref_scores", "pos_scores", "neg_scores"))
         assert ref.is_cuda and reduction == "mean"
-        dev = ref.device
-        B, T, N = ref.shape
-        out = torch.empty(1, device=dev, dtype=torch.float32)
-        L = _lib.get_lib()
-        L.info_nce_loss(ref.data_ptr(), pos.data_ptr(), neg.data_ptr(), B, T, N, float(temperature),
-                        _ws(B, T, dev).data_ptr(), out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
-        return out[0]
+        return _NCEFn.apply(ref, pos, neg, float(temperature))

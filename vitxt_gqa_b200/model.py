@@ -661,49 +661,19 @@ class T2S(_FusionModelBase):
         self.TransLayer = QTV(h, int(cfg.translayers.num_hidden_layers))
         self.Grounding_Module = GroundingModule(h, int(cfg.encoder.num_hidden_layers))
 
-    def forward(self, sample_list):
-        L = _lib.get_lib()
-        inp = self._gather_inputs(sample_list, self._I64 + self._F32)
-        dev = self._device()
-        B, Lt = inp["text"].shape
-        F = inp["video_feat"].shape[1]
-        O = inp["ocr_mask"].shape[1]
-        T = inp["train_prev_inds"].shape[1]
-        V = self.classifier.module.weight.shape[0]
-        Of = O // F
-        if F != self.frame_num or Of != self.ocr_frame_num or O != F * Of:
-            raise ValueError("inputs have %d frames x %d OCR slots but the config says %d x %d"
-                             % (F, Of, self.frame_num, self.ocr_frame_num))
-        Le, H = Lt + F + O, 768
-        P = self._pack(dev)
-        variants = ("pos", "ref", "neg")
-        ws = self._workspace(B, dev, dict(Lt=Lt, F=F, O=O, T=T, V=V, k_obj_pad=P["k_obj_pad"],
-                                          k_ocr_pad=P["k_ocr_pad"], variants=variants))
-        st = torch.cuda.current_stream(dev).cuda_stream
-        f = P["f32"]
+    def train_engine(self):
+        """The flat-buffer training engine of this model (vitxt_gqa_b200/train.py), created on first use."""
+        eng = getattr(self, "_train_engine", None)
+        if eng is None or eng.dev != self._device():
+            from .train import TrainEngine
+            eng = TrainEngine(self)
+            object.__setattr__(self, "_train_engine", eng)
+        return eng
 
-        # ---- masks and key lists
-        L.mask_prep(_ptr(inp["text_len"]), _ptr(inp["frame_mask"]), _ptr(inp["ocr_mask"]), B, Lt, F, O,
-                    _ptr(ws["jm_ref"]), st)
-        L.mask_prep(_ptr(inp["text_len"]), None, None, B, Lt, 0, 0, _ptr(ws["jm_txt"]), st)
-        L.build_keys(_ptr(ws["jm_txt"]), B, Lt, _ptr(ws["keys_txt"]), _ptr(ws["nk_txt"]), Lt, st)
-        L.build_keys(_ptr(ws["jm_ref"]), B, Le, _ptr(ws["keys"]["ref"]), _ptr(ws["nk"]["ref"]), Le, st)
-
-        # ---- fp32 grounding chain
-        self._text_bert(L, P, ws, inp, B, Lt, Le, st)
-        self._encode_obj_ocr(L, P, ws, inp, B, Lt, F, O, Le, st)
-        x, n = ws["J0"], len(P["qtv"])
-        if n > 2 and "fx2" not in ws:
-            ws["fx2"] = torch.empty_like(ws["fx"])
-        for i, lw in enumerate(P["qtv"]):
-            last = i == n - 1
-            out = ws["J1"] if last else (ws["fx"] if i % 2 == 0 else ws["fx2"])
-            self._layer_f32(L, lw, x, B * Le, Le, ws["keys"]["ref"], ws["nk"]["ref"], Le, ws, st, out=out,
-                            tanh_base=ws["J0"] if last else None, out16=ws["X16"] if last else None,
-                            first=(i == 0), feeds_next=not last)
-            x = out
-
-        # ---- grounding (K5)
+    def _grounding(self, L, P, ws, inp, B, Lt, F, O, Of, Le, dev, st):
+        """Grounding_Module.forward (reference t2s.py:461-518) on the joint features in ws["J1"]: question pooling,
+        similarities, temporal / spatial selection, pos / neg joint masks and their key lists."""
+        H, f = 768, P["f32"]
         g = "Grounding_Module."
         self._q_linear(L, P, ws, f[g + "q_linear.weight"], f[g + "q_linear.bias"], "q_linear", B, Lt, Le, st)
         L.question_pool(_ptr(ws["qp"]), B, Lt, H, _ptr(f[g + "self_attn.weight"]), _ptr(f[g + "self_attn.bias"]),
@@ -734,6 +704,64 @@ class T2S(_FusionModelBase):
                          _ptr(ws["jm_neg"]), _ptr(dbg_o), st)
         L.build_keys(_ptr(ws["jm_pos"]), B, Le, _ptr(ws["keys"]["pos"]), _ptr(ws["nk"]["pos"]), Le, st)
         L.build_keys(_ptr(ws["jm_neg"]), B, Le, _ptr(ws["keys"]["neg"]), _ptr(ws["nk"]["neg"]), Le, st)
+
+        return ground_frame, ground_box, dbg, dbg_f, dbg_o
+
+    def forward(self, sample_list):
+        L = _lib.get_lib()
+        inp = self._gather_inputs(sample_list, self._I64 + self._F32)
+        dev = self._device()
+        B, Lt = inp["text"].shape
+        F = inp["video_feat"].shape[1]
+        O = inp["ocr_mask"].shape[1]
+        T = inp["train_prev_inds"].shape[1]
+        V = self.classifier.module.weight.shape[0]
+        Of = O // F
+        if F != self.frame_num or Of != self.ocr_frame_num or O != F * Of:
+            raise ValueError("inputs have %d frames x %d OCR slots but the config says %d x %d"
+                             % (F, Of, self.frame_num, self.ocr_frame_num))
+        Le, H = Lt + F + O, 768
+        if self.training and torch.is_grad_enabled():
+            # training step: teacher-forced forward that keeps what the backward needs, behind a
+            # torch.autograd.Function so that the reference trainer's loss.backward() drives the backward kernels
+            from . import train as _train
+            eng = self.train_engine()
+            ref, pos, neg = _train._T2STrainFn.apply(eng, inp, *eng.live_params)
+            ground_frame, ground_box = eng.ground
+            return {
+                "ref_scores": ref, "pos_scores": pos, "neg_scores": neg, "ground_box": ground_box,
+                "ground_frame": ground_frame, "frame_topk": torch.tensor(self.frame_topk, device=dev),
+                "ocr_topk": torch.tensor(self.ocr_topk, device=dev),
+            }
+        P = self._pack(dev)
+        variants = ("pos", "ref", "neg")
+        ws = self._workspace(B, dev, dict(Lt=Lt, F=F, O=O, T=T, V=V, k_obj_pad=P["k_obj_pad"],
+                                          k_ocr_pad=P["k_ocr_pad"], variants=variants))
+        st = torch.cuda.current_stream(dev).cuda_stream
+        f = P["f32"]
+
+        # ---- masks and key lists
+        L.mask_prep(_ptr(inp["text_len"]), _ptr(inp["frame_mask"]), _ptr(inp["ocr_mask"]), B, Lt, F, O,
+                    _ptr(ws["jm_ref"]), st)
+        L.mask_prep(_ptr(inp["text_len"]), None, None, B, Lt, 0, 0, _ptr(ws["jm_txt"]), st)
+        L.build_keys(_ptr(ws["jm_txt"]), B, Lt, _ptr(ws["keys_txt"]), _ptr(ws["nk_txt"]), Lt, st)
+        L.build_keys(_ptr(ws["jm_ref"]), B, Le, _ptr(ws["keys"]["ref"]), _ptr(ws["nk"]["ref"]), Le, st)
+
+        # ---- fp32 grounding chain
+        self._text_bert(L, P, ws, inp, B, Lt, Le, st)
+        self._encode_obj_ocr(L, P, ws, inp, B, Lt, F, O, Le, st)
+        x, n = ws["J0"], len(P["qtv"])
+        if n > 2 and "fx2" not in ws:
+            ws["fx2"] = torch.empty_like(ws["fx"])
+        for i, lw in enumerate(P["qtv"]):
+            last = i == n - 1
+            out = ws["J1"] if last else (ws["fx"] if i % 2 == 0 else ws["fx2"])
+            self._layer_f32(L, lw, x, B * Le, Le, ws["keys"]["ref"], ws["nk"]["ref"], Le, ws, st, out=out,
+                            tanh_base=ws["J0"] if last else None, out16=ws["X16"] if last else None,
+                            first=(i == 0), feeds_next=not last)
+            x = out
+
+        ground_frame, ground_box, dbg, dbg_f, dbg_o = self._grounding(L, P, ws, inp, B, Lt, F, O, Of, Le, dev, st)
 
         # ---- bf16 answer transformer
         jm = {"ref": ws["jm_ref"], "pos": ws["jm_pos"], "neg": ws["jm_neg"]}

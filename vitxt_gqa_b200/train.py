@@ -1,0 +1,610 @@
+"""Training step of T2S on the B200 kernels: teacher-forced forward that keeps what the backward needs,
+hand-scheduled backward, flat-buffer gradient all-reduce, fused clip + Adam.
+
+Reference: one training step of pythia/trainers/base_trainer.py:226-270 -- `model(prepared_batch)` in training
+mode (models/t2s.py:288-314: three teacher-forced MMT passes ref / pos / neg), `loss.backward()`,
+`clip_grad_norm_(model.parameters(), 0.25)` (utils/general.py:32-40), `Adam.step()`; under
+DistributedDataParallel the gradients are all-reduced (mean) inside backward (base_trainer.py:134-137).
+
+How it plugs in: `T2S.forward(sample_list)` in training mode with autograd enabled routes through
+`_T2STrainFn`, a `torch.autograd.Function` whose forward enqueues the kernel schedule below and whose backward
+enqueues the backward schedule and returns the parameter gradients, so the reference's trainer
+(`loss.backward(); clip; optimizer.step()`) works unchanged.  `TrainEngine.step()` is the fused alternative to
+clip_grad_norm_ + torch.optim.Adam over the same flat buffers, and `TrainEngine.all_reduce()` the NCCL gradient
+all-reduce of one flat fp32 buffer (live parameters only: the 19.5 M dead parameters of SURVEY Q18 never get a
+gradient and are left out, which is what DDP's find_unused_parameters=True arranges in the reference).
+
+Arithmetic: forward exactly as the eval path (fp32-class bf16x3 grounding chain, bf16 answer transformer) so the
+grounding indices match; backward in bf16 with fp32 accumulation (activation gradients bf16, parameter gradients
+fp32).  Dropout: the reference trains with dropout 0.1; this path implements p = 0 only (parity with autograd is
+checked at p = 0).
+
+Schedule of the backward (per variant v in ref, pos, neg; then the shared front):
+  loss -> dscores (bf16 copy) -> classifier / pointer-net dgrad + wgrad -> for each answer-transformer layer, last to
+  first, decoder rows and encoder rows: LN2 bwd -> FFN-down dgrad (x GELU') + wgrad -> FFN-up dgrad (+ residual)
+  + wgrad -> LN1 bwd -> attention-out dgrad + wgrad -> attention bwd (encoder + decoder rows jointly, prefix-LM
+  mask) -> q|k|v dgrad (+ residual) + wgrad -> PrevPredEmbeddings bwd; encoder-input gradients of the three
+  variants summed into dJ1 -> QTV (tanh residual) -> obj / OCR encoders, TextBert -> embeddings.
+"""
+import torch
+import torch.distributed as dist
+
+from . import lib as _lib
+
+LN_EPS_BERT = 1e-12
+LN_EPS_EMBED = 1e-5
+H = 768
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _ru(x, m):
+    return (x + m - 1) // m * m
+
+
+class _T2STrainFn(torch.autograd.Function):
+    """forward(engine, inputs, *live_params) -> (ref_scores, pos_scores, neg_scores)."""
+
+    @staticmethod
+    def forward(ctx, engine, inp, *params):
+        ctx.engine = engine
+        ref, pos, neg = engine.forward(inp)
+        return ref, pos, neg
+
+    @staticmethod
+    def backward(ctx, d_ref, d_pos, d_neg):
+        eng = ctx.engine
+        grads = eng.backward({"ref": d_ref, "pos": d_pos, "neg": d_neg})
+        return (None, None) + tuple(grads)
+
+
+class TrainEngine:
+    """Flat parameter / gradient / Adam-state buffers of a T2S model + the training kernel schedules."""
+
+    def __init__(self, model):
+        self.model = model
+        self.dev = next(model.parameters()).device
+        if self.dev.type != "cuda":
+            raise _lib.T2SLibraryError("the training step runs only on a CUDA device (sm_100a); there is no CPU fallback")
+        if model.MODEL != "t2s":
+            raise NotImplementedError("the B200 training step is built for T2S (config 3); M4C trains eval-only here")
+        if model.grounding_precision != "bf16x3":
+            raise NotImplementedError("training uses the bf16x3 grounding chain")
+        self._flatten()
+        self.step_count = 0
+        self._ws = {}
+        self._wt = None
+        self._wt_key = None
+        self.saved = None
+
+    # ------------------------------------------------------------------ flat buffers
+    DEAD_PREFIXES = ("Grounding_Module.", "linear_obj_frame_to_mmt_in.", "obj_frame_layer_norm.")
+
+    def _flatten(self):
+        """Re-point every parameter at a view of one flat fp32 buffer, ordered (a) by optimizer group (reference
+        get_optimizer_parameters, t2s.py:356-376: default, text_bert x lr_scale_text_bert, mmt x lr_scale_mmt),
+        dead parameters last, and (b) with query/key/value weights (and biases) adjacent, so the fused q|k|v
+        weight gradient is one [3H, H] view."""
+        m = self.model
+        named = dict(m.named_parameters())
+        text = [n for n in named if n.startswith("text_bert.")]
+        mmt = [n for n in named if n.startswith("mmt.")]
+        dead = [n for n in named if n.startswith(self.DEAD_PREFIXES)]
+        taken = set(text) | set(mmt) | set(dead)
+        default = [n for n in named if n not in taken]
+
+        def order(names):
+            def key(n):
+                # q, k, v of one attention block adjacent and in that order; weights before biases
+                for i, tag in enumerate(("query", "key", "value")):
+                    if ".attention.self." + tag + "." in n:
+                        base = n.split(".attention.self.")[0]
+                        return (base + ".attention.self", 0 if n.endswith("weight") else 1, i)
+                return (n, 2, 0)
+            return sorted(names, key=key)
+
+        finetune_text = any(f["module"] is m.text_bert for f in m.finetune_modules)
+        groups = [("default", order(default + ([] if finetune_text else text))),
+                  ("text_bert", order(text) if finetune_text else []),
+                  ("mmt", order(mmt)), ("dead", order(dead))]
+        total = sum(named[n].numel() for _, ns in groups for n in ns)
+        # every segment starts 16-byte aligned (TMA reduce-add / float4 access): pad each tensor to 4 floats
+        sizes = {n: _ru(named[n].numel(), 4) for n in named}
+        total = sum(sizes.values())
+        flat_p = torch.zeros(total, device=self.dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(total, device=self.dev, dtype=torch.float32)
+        self.adam_m = torch.zeros(total, device=self.dev, dtype=torch.float32)
+        self.adam_v = torch.zeros(total, device=self.dev, dtype=torch.float32)
+        self.offsets, self.group_ranges = {}, {}
+        off = 0
+        for gname, names in groups:
+            start = off
+            for n in names:
+                p = named[n]
+                view = flat_p[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                self.offsets[n] = off
+                off += sizes[n]
+            self.group_ranges[gname] = (start, off)
+        self.flat_param = flat_p
+        self.live_end = self.group_ranges["mmt"][1]
+        self.named = named
+        self.live_names = [n for g, ns in groups[:3] for n in ns]
+        self.live_params = [named[n] for n in self.live_names]
+
+    def grad(self, name):
+        p = self.named[name]
+        o = self.offsets[name]
+        return self.flat_grad[o:o + p.numel()].view_as(p)
+
+    def _g(self, name):
+        return self.flat_grad.data_ptr() + 4 * self.offsets[name]
+
+    # ------------------------------------------------------------------ transposed bf16 weights for the dgrad GEMMs
+    def _wt_pack(self):
+        m = self.model
+        key = m._weights_key()
+        if self._wt is not None and self._wt_key == key:
+            return self._wt
+        bf = lambda w: w.detach().to(torch.bfloat16)
+
+        def layer(l):
+            a = l.attention
+            wqkv = torch.cat([a.self.query.weight, a.self.key.weight, a.self.value.weight], 0)
+            return dict(wqkvT=bf(wqkv).t().contiguous(), woT=bf(a.output.dense.weight).t().contiguous(),
+                        wiT=bf(l.intermediate.dense.weight).t().contiguous(),
+                        wo2T=bf(l.output.dense.weight).t().contiguous())
+
+        W = dict(text=[layer(l) for l in m.text_bert.encoder.layer],
+                 qtv=[layer(l) for l in m.TransLayer.encoder.layer],
+                 mmt=[layer(l) for l in m.mmt.encoder.layer])
+        V = m.classifier.module.weight.shape[0]
+        clsT = torch.zeros(H, _ru(V, 8), device=self.dev, dtype=torch.bfloat16)
+        clsT[:, :V] = bf(m.classifier.module.weight).t()
+        W["clsT"] = clsT
+        W["ptr_qT"] = bf(m.ocr_ptr_net.query.weight).t().contiguous()
+        W["ptr_kT"] = bf(m.ocr_ptr_net.key.weight).t().contiguous()
+        P = m._packed
+        for which, lin in (("obj", m.linear_obj_feat_to_mmt_in), ("ocr", m.linear_ocr_feat_to_mmt_in)):
+            kp = P["k_%s_pad" % which]
+            t = torch.zeros(kp, H, device=self.dev, dtype=torch.bfloat16)
+            t[:lin.weight.shape[1]] = bf(lin.weight).t()
+            W[which + "T"] = t
+        self._wt, self._wt_key = W, key
+        return W
+
+    # ------------------------------------------------------------------ workspaces
+    def _train_ws(self, B, Lt, F, O, T, V, kp_obj, kp_ocr):
+        key = (B, Lt, F, O, T, V)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        dev = self.dev
+        Le = Lt + F + O
+        Me, Md, Mt = B * Le, B * T, B * Lt
+        f32 = dict(device=dev, dtype=torch.float32)
+        b16 = dict(device=dev, dtype=torch.bfloat16)
+        m = self.model
+        n_text, n_qtv, n_mmt = len(m.text_bert.encoder.layer), len(m.TransLayer.encoder.layer), len(m.mmt.encoder.layer)
+        Np = _ru(V + O, 8)
+
+        def x3_layer(M):      # what one grounding-chain layer keeps (bf16 hi|lo operands double as bf16 activations)
+            return dict(xs=torch.empty(M, 2 * H, **b16), qkvs=torch.empty(M, 6 * H, **b16), ctxs=torch.empty(M, 2 * H, **b16),
+                        h1=torch.empty(M, H, **f32), x1=torch.empty(M, H, **f32), x1s=torch.empty(M, 2 * H, **b16),
+                        u=torch.empty(M, 4 * H, **f32), inters=torch.empty(M, 8 * H, **b16), h2=torch.empty(M, H, **f32),
+                        out=torch.empty(M, H, **f32))
+
+        def bf_layer(M, need_qkv=True):
+            d = dict(ctx=torch.empty(M, H, **b16), h1=torch.empty(M, H, **b16), x1=torch.empty(M, H, **b16),
+                     u=torch.empty(M, 4 * H, **b16), inter=torch.empty(M, 4 * H, **b16), h2=torch.empty(M, H, **b16),
+                     out=torch.empty(M, H, **b16))
+            if need_qkv:
+                d["qkv"] = torch.empty(M, 3 * H, **b16)
+            return d
+
+        variants = ("ref", "pos", "neg")
+        ws = dict(
+            text=[x3_layer(Mt) for _ in range(n_text)], qtv=[x3_layer(Me) for _ in range(n_qtv)],
+            xt=torch.empty(Mt, H, **f32),
+            enc={v: [bf_layer(Me, need_qkv=(li > 0)) for li in range(n_mmt)] for v in variants},
+            dec={v: [bf_layer(Md) for _ in range(n_mmt)] for v in variants},
+            xd={v: torch.empty(Md, H, **b16) for v in variants},
+            qd={v: torch.empty(Md, H, **b16) for v in variants},
+            keyp={v: torch.empty(Me, H, **b16) for v in variants},
+            # backward scratch (encoder-row sized; decoder rows use the *_d copies)
+            dy=torch.empty(Me, H, **b16), dy2=torch.empty(Me, H, **b16), dh2=torch.empty(Me, H, **b16),
+            du=torch.empty(Me, 4 * H, **b16), dx1=torch.empty(Me, H, **b16), dh1=torch.empty(Me, H, **b16),
+            dctx=torch.empty(Me, H, **b16), dqkv=torch.empty(Me, 3 * H, **b16),
+            dy_d=torch.empty(Md, H, **b16), dy2_d=torch.empty(Md, H, **b16), dh2_d=torch.empty(Md, H, **b16),
+            du_d=torch.empty(Md, 4 * H, **b16), dx1_d=torch.empty(Md, H, **b16), dh1_d=torch.empty(Md, H, **b16),
+            dctx_d=torch.empty(Md, H, **b16), dqkv_d=torch.empty(Md, 3 * H, **b16),
+            dkeyp=torch.zeros(Me, H, **b16), dq=torch.empty(Md, H, **b16),
+            dS16=torch.zeros(Md, Np, **b16), dJ=torch.empty(Me, H, **f32),
+            dh_obj=torch.empty(B * F, H, **b16), dh_ocr=torch.empty(B * O, H, **b16), dc_ocr=torch.empty(B * O, H, **f32),
+            dw_obj=torch.empty(H, kp_obj, **f32), dw_ocr=torch.empty(H, kp_ocr, **f32),
+            d_id_obj=torch.empty(B * F, 52, **f32), d_id_ocr=torch.empty(B * O, 100, **f32),
+            attn_ws=torch.empty(int(_lib.get_lib().attn_bwd_workspace_bytes(B, Le, T, 12)), device=dev, dtype=torch.uint8),
+            Np=Np,
+        )
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward building blocks
+    def _x3_layer_fwd(self, L, lw, x, sv, M, rows_L, keys, nk, key_stride, st, out, tanh_base=None, out16=None,
+                      remap=(0, 0, 0), next_xs=None):
+        """One grounding-chain BERT layer (as model._layer_f32, bf16x3), keeping its intermediates in `sv`.
+        sv["xs"] already holds the bf16 hi|lo split of the input x."""
+        B = M // rows_L
+        F32, RES, SPLIT = _lib.GEMM_OUT_F32, _lib.GEMM_RES_F32, _lib.GEMM_OUT_SPLIT
+        L.gemm_bf16x3(_ptr(sv["xs"]), 2 * H, _ptr(lw["wqkv"]), 2 * H, _ptr(lw["bqkv"]), None, 0, _ptr(sv["qkvs"]), 6 * H,
+                      M, 3 * H, H, SPLIT, 0, st)
+        L.attn_tc(_ptr(sv["qkvs"]), 6 * H, 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride, _ptr(sv["ctxs"]),
+                  2 * H, st)
+        L.gemm_bf16x3(_ptr(sv["ctxs"]), 2 * H, _ptr(lw["wo"]), 2 * H, _ptr(lw["bo"]), _ptr(x), H, _ptr(sv["h1"]), H,
+                      M, H, H, F32 | RES, 0, st)
+        L.add_ln_split(_ptr(sv["h1"]), 0, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H, None, 0,
+                       _ptr(sv["x1"]), H, _ptr(sv["x1s"]), 2 * H, 0, 0, 0, st)
+        L.gemm_bf16x3(_ptr(sv["x1s"]), 2 * H, _ptr(lw["wi"]), 2 * H, _ptr(lw["bi"]), None, 0, _ptr(sv["u"]), 4 * H,
+                      M, 4 * H, H, F32, 0, st)
+        L.gelu_rows(_ptr(sv["u"]), 0, 4 * H, M, 4 * H, _ptr(sv["inters"]), 8 * H, 4 * H, st)
+        L.gemm_bf16x3(_ptr(sv["inters"]), 8 * H, _ptr(lw["wo2"]), 8 * H, _ptr(lw["bo2"]), _ptr(sv["x1"]), H,
+                      _ptr(sv["h2"]), H, M, H, 4 * H, F32 | RES, 0, st)
+        if next_xs is not None:
+            L.add_ln_split(_ptr(sv["h2"]), 0, H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H,
+                           None, 0, _ptr(out), H, _ptr(next_xs), 2 * H, 0, 0, 0, st)
+        else:
+            L.add_ln(_ptr(sv["h2"]), 0, H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H,
+                     _ptr(tanh_base), H, _ptr(out), H, _ptr(out16), H, remap[0], remap[1], remap[2], st)
+
+    def _bf_layer_fwd(self, L, lw, x, ldx, qkv, sv, M, attn, st):
+        """One answer-transformer layer over M rows; `attn(qkv, ctx)` enqueues the attention of these rows."""
+        if qkv is None:
+            qkv = sv["qkv"]
+            L.gemm_bf16(_ptr(x), ldx, _ptr(lw["wqkv"]), H, _ptr(lw["bqkv"]), None, 0, _ptr(qkv), 3 * H, M, 3 * H, H, 0, 0, st)
+        attn(qkv, sv["ctx"])
+        L.gemm_bf16(_ptr(sv["ctx"]), H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), _ptr(x), ldx, _ptr(sv["h1"]), H, M, H, H, 0, 0, st)
+        L.add_ln(_ptr(sv["h1"]), 1, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H, None, 0, None, 0,
+                 _ptr(sv["x1"]), H, 0, 0, 0, st)
+        L.gemm_bf16(_ptr(sv["x1"]), H, _ptr(lw["wi"]), H, _ptr(lw["bi"]), None, 0, _ptr(sv["u"]), 4 * H, M, 4 * H, H, 0, 0, st)
+        L.gelu_rows(_ptr(sv["u"]), 1, 4 * H, M, 4 * H, _ptr(sv["inter"]), 4 * H, 0, st)
+        L.gemm_bf16(_ptr(sv["inter"]), 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), _ptr(sv["x1"]), H, _ptr(sv["h2"]), H,
+                    M, H, 4 * H, 0, 0, st)
+        L.add_ln(_ptr(sv["h2"]), 1, H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H, None, 0, None, 0,
+                 _ptr(sv["out"]), H, 0, 0, 0, st)
+        return qkv
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, inp):
+        m = self.model
+        L = _lib.get_lib()
+        dev = self.dev
+        B, Lt = inp["text"].shape
+        F = inp["video_feat"].shape[1]
+        O = inp["ocr_mask"].shape[1]
+        T = inp["train_prev_inds"].shape[1]
+        V = m.classifier.module.weight.shape[0]
+        Of = O // F
+        Le = Lt + F + O
+        P = m._pack(dev)
+        variants = ("pos", "ref", "neg")
+        mws = m._workspace(B, dev, dict(Lt=Lt, F=F, O=O, T=T, V=V, k_obj_pad=P["k_obj_pad"], k_ocr_pad=P["k_ocr_pad"],
+                                        variants=variants))
+        ws = self._train_ws(B, Lt, F, O, T, V, P["k_obj_pad"], P["k_ocr_pad"])
+        st = torch.cuda.current_stream(dev).cuda_stream
+        f = P["f32"]
+        Me, Md, Mt = B * Le, B * T, B * Lt
+
+        # ---- masks and key lists (as the eval path)
+        L.mask_prep(_ptr(inp["text_len"]), _ptr(inp["frame_mask"]), _ptr(inp["ocr_mask"]), B, Lt, F, O, _ptr(mws["jm_ref"]), st)
+        L.mask_prep(_ptr(inp["text_len"]), None, None, B, Lt, 0, 0, _ptr(mws["jm_txt"]), st)
+        L.build_keys(_ptr(mws["jm_txt"]), B, Lt, _ptr(mws["keys_txt"]), _ptr(mws["nk_txt"]), Lt, st)
+        L.build_keys(_ptr(mws["jm_ref"]), B, Le, _ptr(mws["keys"]["ref"]), _ptr(mws["nk"]["ref"]), Le, st)
+
+        # ---- TextBert
+        e = "text_bert.embeddings."
+        L.bert_embed_ln(_ptr(inp["text"]), Mt, Lt, H, _ptr(f[e + "word_embeddings.weight"]),
+                        _ptr(f[e + "position_embeddings.weight"]), _ptr(f[e + "token_type_embeddings.weight"]),
+                        _ptr(f[e + "LayerNorm.weight"]), _ptr(f[e + "LayerNorm.bias"]), LN_EPS_BERT, _ptr(ws["xt"]), H, st)
+        x = ws["xt"]
+        n = len(P["text"])
+        L.split_bf16(_ptr(x), H, Mt, H, H, _ptr(ws["text"][0]["xs"]), 2 * H, 0, 0, 0, st)
+        for i, lw in enumerate(P["text"]):
+            sv, last = ws["text"][i], i == n - 1
+            self._x3_layer_fwd(L, lw, x, sv, Mt, Lt, mws["keys_txt"], mws["nk_txt"], Lt, st,
+                               out=mws["J0"] if last else sv["out"], remap=(Lt, Le, 0) if last else (0, 0, 0),
+                               next_xs=None if last else ws["text"][i + 1]["xs"])
+            x = sv["out"]
+        # ---- obj / OCR encoders (model code; h_obj / h_ocr / a_*_s stay in the model workspace until backward)
+        m._encode_obj_ocr(L, P, mws, inp, B, Lt, F, O, Le, st)
+        # ---- QTV
+        x, n = mws["J0"], len(P["qtv"])
+        L.split_bf16(_ptr(x), H, Me, H, H, _ptr(ws["qtv"][0]["xs"]), 2 * H, 0, 0, 0, st)
+        for i, lw in enumerate(P["qtv"]):
+            sv, last = ws["qtv"][i], i == n - 1
+            self._x3_layer_fwd(L, lw, x, sv, Me, Le, mws["keys"]["ref"], mws["nk"]["ref"], Le, st,
+                               out=mws["J1"] if last else sv["out"], tanh_base=mws["J0"] if last else None,
+                               out16=mws["X16"] if last else None, next_xs=None if last else ws["qtv"][i + 1]["xs"])
+            x = sv["out"]
+        # ---- grounding (no gradient: emits constant masks, SURVEY hard part 9)
+        ground_frame, ground_box, _, _, _ = m._grounding(L, P, mws, inp, B, Lt, F, O, Of, Le, dev, st)
+        jm = {"ref": mws["jm_ref"], "pos": mws["jm_pos"], "neg": mws["jm_neg"]}
+
+        # ---- answer transformer, teacher forced (reference t2s.py:288-314)
+        N = V + O
+        scores = {v: torch.empty(B, T, N, device=dev, dtype=torch.float32) for v in variants}
+        layers = P["mmt"]
+        prev = inp["train_prev_inds"].contiguous()
+        pp = "mmt.prev_pred_embeddings."
+        ocr_row0 = Lt + F
+        L.gemm_bf16(_ptr(mws["X16"]), H, _ptr(layers[0]["wqkv"]), H, _ptr(layers[0]["bqkv"]), None, 0, _ptr(mws["qkv0"]),
+                    3 * H, Me, 3 * H, H, 0, 0, st)
+        enc_qkv = {}
+        for v in variants:
+            keys, nk = mws["keys"][v], mws["nk"][v]
+
+            def enc_attn(qkv, ctx, keys=keys, nk=nk):
+                L.attn_tc(_ptr(qkv), 3 * H, 0, B, Le, H, 12, _ptr(keys), _ptr(nk), Le, _ptr(ctx), H, st)
+
+            x = mws["X16"]
+            enc_qkv[v] = []
+            for li, lw in enumerate(layers):
+                sv = ws["enc"][v][li]
+                q = self._bf_layer_fwd(L, lw, x, H, mws["qkv0"] if li == 0 else None, sv, Me, enc_attn, st)
+                enc_qkv[v].append(q)
+                x = sv["out"]
+            L.gemm_bf16(_ptr(x), H, _ptr(P["w_ptr_k"]), H, _ptr(f["ocr_ptr_net.key.bias"]), None, 0, _ptr(ws["keyp"][v]), H,
+                        Me, H, H, 0, 0, st)
+            # decoder rows
+            L.prev_embed(_ptr(prev), T, B, 0, T, T, V, H, _ptr(f["classifier.module.weight"]),
+                         mws["J1"].data_ptr() + ocr_row0 * H * 4, Le * H, H,
+                         _ptr(f[pp + "position_embeddings.weight"]), _ptr(f[pp + "token_type_embeddings.weight"]),
+                         _ptr(f[pp + "ans_layer_norm.weight"]), _ptr(f[pp + "ans_layer_norm.bias"]),
+                         _ptr(f[pp + "ocr_layer_norm.weight"]), _ptr(f[pp + "ocr_layer_norm.bias"]),
+                         _ptr(f[pp + "emb_layer_norm.weight"]), _ptr(f[pp + "emb_layer_norm.bias"]), LN_EPS_BERT,
+                         _ptr(ws["xd"][v]), None, H, st)
+            x = ws["xd"][v]
+            for li, lw in enumerate(layers):
+                sv = ws["dec"][v][li]
+                qe = enc_qkv[v][li]
+
+                def dec_attn(qkv, ctx, qe=qe, keys=keys, nk=nk):
+                    L.attn_dec(_ptr(qe), 3 * H, Le, _ptr(qkv), 3 * H, T, B, H, 12, _ptr(keys), _ptr(nk), Le, 0, T,
+                               _ptr(ctx), H, st)
+
+                self._bf_layer_fwd(L, lw, x, H, None, sv, Md, dec_attn, st)
+                x = sv["out"]
+            sc = scores[v]
+            L.gemm_bf16(_ptr(x), H, _ptr(P["w_cls"]), H, _ptr(f["classifier.module.bias"]), None, 0, _ptr(sc), N,
+                        Md, V, H, _lib.GEMM_OUT_F32, 0, st)
+            L.gemm_bf16(_ptr(x), H, _ptr(P["w_ptr_q"]), H, _ptr(f["ocr_ptr_net.query.bias"]), None, 0, _ptr(ws["qd"][v]), H,
+                        Md, H, H, 0, 0, st)
+            L.ptr_score(_ptr(ws["qd"][v]), H, B, T, 0, T, ws["keyp"][v].data_ptr() + ocr_row0 * H * 2, Le * H, H, O, H,
+                        jm[v].data_ptr() + ocr_row0 * 4, Le, _ptr(sc), N, V, st)
+        self.saved = dict(inp=inp, dims=(B, Lt, F, O, T, V, Le), enc_qkv=enc_qkv, prev=prev)
+        self.ground = (ground_frame, ground_box)
+        return scores["ref"], scores["pos"], scores["neg"]
+
+    # ------------------------------------------------------------------ backward building blocks
+    def _wgrad(self, L, G, ldg, X, ldx, dW_ptr, ldd, rows, Pn, Qn, st):
+        L.gemm_wgrad_bf16(_ptr(G) if torch.is_tensor(G) else G, ldg, _ptr(X) if torch.is_tensor(X) else X, ldx, dW_ptr,
+                          ldd, rows, Pn, Qn, 0, st)
+
+    def _layer_bwd_pre_attn(self, L, wt, lw, pre, sv, M, dy, sc, st, x3):
+        """LN2 -> FFN -> LN1 -> attention-out of one layer over M rows.  dy: gradient of the layer output (bf16, or the
+        (tensor, flags) of the QTV tail); leaves d(context) in sc["dctx"] and the LN1 input gradient in sc["dh1"].
+        `x3`: the layer is a grounding-chain layer (fp32 saved pre-activations, bf16 hi|lo operand buffers)."""
+        g = self._g
+        hb = 0 if x3 else 1                     # saved pre-LayerNorm sums: fp32 in the grounding chain, bf16 in MMT
+        inter, ld_inter = (sv["inters"], 8 * H) if x3 else (sv["inter"], 4 * H)
+        x1, ld_x1 = (sv["x1s"], 2 * H) if x3 else (sv["x1"], H)
+        ctx, ld_ctx = (sv["ctxs"], 2 * H) if x3 else (sv["ctx"], H)
+        dy_t, dy_bf16, dy_map, tanh_out = dy
+        L.ln_bwd(_ptr(sv["h2"]), hb, H, _ptr(dy_t), dy_bf16, H, dy_map[0], dy_map[1], dy_map[2], _ptr(lw["ln2g"]),
+                 _ptr(lw["ln2b"]), LN_EPS_BERT, M, H, tanh_out, _ptr(sc["dh2"]), 1, H,
+                 g(pre + "output.LayerNorm.weight"), g(pre + "output.LayerNorm.bias"), g(pre + "output.dense.bias"), st)
+        L.gemm_bf16(_ptr(sc["dh2"]), H, _ptr(wt["wo2T"]), H, None, _ptr(sv["u"]), 4 * H, _ptr(sc["du"]), 4 * H, M, 4 * H, H,
+                    _lib.GEMM_DGELU | (_lib.GEMM_RES_F32 if x3 else 0), 0, st)
+        self._wgrad(L, sc["dh2"], H, inter, ld_inter, g(pre + "output.dense.weight"), 4 * H, M, H, 4 * H, st)
+        L.colsum(_ptr(sc["du"]), 1, 4 * H, M, 4 * H, g(pre + "intermediate.dense.bias"), st)
+        L.gemm_bf16(_ptr(sc["du"]), 4 * H, _ptr(wt["wiT"]), 4 * H, None, _ptr(sc["dh2"]), H, _ptr(sc["dx1"]), H, M, H, 4 * H,
+                    0, 0, st)
+        self._wgrad(L, sc["du"], 4 * H, x1, ld_x1, g(pre + "intermediate.dense.weight"), H, M, 4 * H, H, st)
+        L.ln_bwd(_ptr(sv["h1"]), hb, H, _ptr(sc["dx1"]), 1, H, 0, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT,
+                 M, H, 0, _ptr(sc["dh1"]), 1, H, g(pre + "attention.output.LayerNorm.weight"),
+                 g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"), st)
+        L.gemm_bf16(_ptr(sc["dh1"]), H, _ptr(wt["woT"]), H, None, None, 0, _ptr(sc["dctx"]), H, M, H, H, 0, 0, st)
+        self._wgrad(L, sc["dh1"], H, ctx, ld_ctx, g(pre + "attention.output.dense.weight"), H, M, H, H, st)
+
+    def _layer_bwd_post_attn(self, L, wt, pre, x, ldx, M, sc, dx_out, st):
+        """q|k|v projection backward: sc["dqkv"] -> dx_out (+ the residual gradient sc["dh1"]); weight / bias grads."""
+        g = self._g
+        L.colsum(_ptr(sc["dqkv"]), 1, 3 * H, M, 3 * H, g(pre + "attention.self.query.bias"), st)
+        L.gemm_bf16(_ptr(sc["dqkv"]), 3 * H, _ptr(wt["wqkvT"]), 3 * H, None, _ptr(sc["dh1"]), H, _ptr(dx_out), H, M, H, 3 * H,
+                    0, 0, st)
+        self._wgrad(L, sc["dqkv"], 3 * H, x, ldx, g(pre + "attention.self.query.weight"), H, M, 3 * H, H, st)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, dscores):
+        m = self.model
+        L = _lib.get_lib()
+        dev = self.dev
+        sv_all = self.saved
+        if sv_all is None:
+            raise RuntimeError("backward called without a training forward")
+        inp = sv_all["inp"]
+        B, Lt, F, O, T, V, Le = sv_all["dims"]
+        P = m._packed
+        W = self._wt_pack()
+        variants = ("pos", "ref", "neg")
+        mws = m._workspace(B, dev, dict(Lt=Lt, F=F, O=O, T=T, V=V, k_obj_pad=P["k_obj_pad"], k_ocr_pad=P["k_ocr_pad"],
+                                        variants=variants))
+        ws = self._train_ws(B, Lt, F, O, T, V, P["k_obj_pad"], P["k_ocr_pad"])
+        st = torch.cuda.current_stream(dev).cuda_stream
+        f = P["f32"]
+        g = self._g
+        Me, Md, Mt = B * Le, B * T, B * Lt
+        N, Np = V + O, ws["Np"]
+        ocr_row0 = Lt + F
+        layers = P["mmt"]
+        n_mmt = len(layers)
+        self.flat_grad[:self.live_end].zero_()
+        enc_sc = dict(dh2=ws["dh2"], du=ws["du"], dx1=ws["dx1"], dh1=ws["dh1"], dctx=ws["dctx"], dqkv=ws["dqkv"])
+        dec_sc = dict(dh2=ws["dh2_d"], du=ws["du_d"], dx1=ws["dx1_d"], dh1=ws["dh1_d"], dctx=ws["dctx_d"], dqkv=ws["dqkv_d"])
+        pp = "mmt.prev_pred_embeddings."
+        first_variant = True
+        for v in variants:
+            dS = dscores[v]
+            if dS is None:
+                continue
+            dS = dS.contiguous()
+            keys, nk = mws["keys"][v], mws["nk"][v]
+            xdec_out = ws["dec"][v][n_mmt - 1]["out"]
+            xenc_out = ws["enc"][v][n_mmt - 1]["out"]
+            # ---- heads
+            L.cast_rows_bf16(_ptr(dS), N, Md, N, _ptr(ws["dS16"]), Np, 0, 0, 0, st)
+            L.colsum(_ptr(dS), 0, N, Md, V, g("classifier.module.bias"), st)
+            L.gemm_bf16(_ptr(ws["dS16"]), Np, _ptr(W["clsT"]), W["clsT"].shape[1], None, None, 0, _ptr(ws["dy_d"]), H,
+                        Md, H, V, 0, 0, st)
+            self._wgrad(L, ws["dS16"], Np, xdec_out, H, g("classifier.module.weight"), H, Md, V, H, st)
+            L.ptr_score_bwd(_ptr(dS), N, B, T, V, _ptr(ws["qd"][v]), H, ws["keyp"][v].data_ptr() + ocr_row0 * H * 2, Le * H, H,
+                            O, H, _ptr(ws["dq"]), H, ws["dkeyp"].data_ptr() + ocr_row0 * H * 2, Le * H, H, st)
+            L.colsum(_ptr(ws["dq"]), 1, H, Md, H, g("ocr_ptr_net.query.bias"), st)
+            L.gemm_bf16(_ptr(ws["dq"]), H, _ptr(W["ptr_qT"]), H, None, _ptr(ws["dy_d"]), H, _ptr(ws["dy_d"]), H, Md, H, H,
+                        0, 0, st)
+            self._wgrad(L, ws["dq"], H, xdec_out, H, g("ocr_ptr_net.query.weight"), H, Md, H, H, st)
+            L.colsum(_ptr(ws["dkeyp"]), 1, H, Me, H, g("ocr_ptr_net.key.bias"), st)
+            L.gemm_bf16(_ptr(ws["dkeyp"]), H, _ptr(W["ptr_kT"]), H, None, None, 0, _ptr(ws["dy"]), H, Me, H, H, 0, 0, st)
+            self._wgrad(L, ws["dkeyp"], H, xenc_out, H, g("ocr_ptr_net.key.weight"), H, Me, H, H, st)
+            # ---- layers, last to first
+            dy_e, dy_d = ws["dy"], ws["dy_d"]
+            alt_e, alt_d = ws["dy2"], ws["dy2_d"]
+            for li in range(n_mmt - 1, -1, -1):
+                lw, wt = layers[li], W["mmt"][li]
+                pre = "mmt.encoder.layer.%d." % li
+                sve, svd = ws["enc"][v][li], ws["dec"][v][li]
+                qkv_e = sv_all["enc_qkv"][v][li]
+                x_e = mws["X16"] if li == 0 else ws["enc"][v][li - 1]["out"]
+                x_d = ws["xd"][v] if li == 0 else ws["dec"][v][li - 1]["out"]
+                self._layer_bwd_pre_attn(L, wt, lw, pre, svd, Md, (dy_d, 1, (0, 0, 0), 0), dec_sc, st, x3=False)
+                self._layer_bwd_pre_attn(L, wt, lw, pre, sve, Me, (dy_e, 1, (0, 0, 0), 0), enc_sc, st, x3=False)
+                L.attn_bwd(_ptr(qkv_e), 3 * H, _ptr(svd["qkv"]), 3 * H, _ptr(sve["ctx"]), H, _ptr(svd["ctx"]), H,
+                           _ptr(enc_sc["dctx"]), H, _ptr(dec_sc["dctx"]), H, _ptr(enc_sc["dqkv"]), 3 * H,
+                           _ptr(dec_sc["dqkv"]), 3 * H, B, Le, T, H, 12, _ptr(keys), _ptr(nk), Le, Le, _ptr(ws["attn_ws"]), st)
+                self._layer_bwd_post_attn(L, wt, pre, x_d, H, Md, dec_sc, alt_d, st)
+                self._layer_bwd_post_attn(L, wt, pre, x_e, H, Me, enc_sc, alt_e, st)
+                dy_e, alt_e = alt_e, dy_e
+                dy_d, alt_d = alt_d, dy_d
+            # ---- encoder-input gradient of this variant into dJ1; decoder input through PrevPredEmbeddings
+            L.rows_add(_ptr(dy_e), None, None, H, Me, H, _ptr(ws["dJ"]), H, 0, 0, 0, 0 if first_variant else 1, st)
+            first_variant = False
+            L.prev_embed_bwd(_ptr(dy_d), H, _ptr(sv_all["prev"]), T, B, T, V, H, _ptr(f["classifier.module.weight"]),
+                             mws["J1"].data_ptr() + ocr_row0 * H * 4, Le * H, H,
+                             _ptr(f[pp + "position_embeddings.weight"]), _ptr(f[pp + "token_type_embeddings.weight"]),
+                             _ptr(f[pp + "ans_layer_norm.weight"]), _ptr(f[pp + "ocr_layer_norm.weight"]),
+                             _ptr(f[pp + "emb_layer_norm.weight"]), LN_EPS_BERT, g("classifier.module.weight"),
+                             ws["dJ"].data_ptr() + ocr_row0 * H * 4, g(pp + "position_embeddings.weight"),
+                             g(pp + "token_type_embeddings.weight"), g(pp + "ans_layer_norm.weight"),
+                             g(pp + "ans_layer_norm.bias"), g(pp + "ocr_layer_norm.weight"), g(pp + "ocr_layer_norm.bias"),
+                             g(pp + "emb_layer_norm.weight"), g(pp + "emb_layer_norm.bias"), st)
+        if first_variant:
+            raise RuntimeError("no score gradient reached the model")
+
+        # ---- QTV: J1 = J0 + tanh(LN2_last(.)): dJ holds dJ1; after the loop dJ += dx(layer 0) = dJ0
+        qtv = P["qtv"]
+        dy = (ws["dJ"], 0, (0, 0, 0), 1)
+        for li in range(len(qtv) - 1, -1, -1):
+            lw, wt, sv = qtv[li], W["qtv"][li], ws["qtv"][li]
+            pre = "TransLayer.encoder.layer.%d." % li
+            self._layer_bwd_pre_attn(L, wt, lw, pre, sv, Me, dy, enc_sc, st, x3=True)
+            L.attn_bwd(_ptr(sv["qkvs"]), 6 * H, None, 0, _ptr(sv["ctxs"]), 2 * H, None, 0, _ptr(enc_sc["dctx"]), H, None, 0,
+                       _ptr(enc_sc["dqkv"]), 3 * H, None, 0, B, Le, 0, H, 12, _ptr(mws["keys"]["ref"]), _ptr(mws["nk"]["ref"]),
+                       Le, Le, _ptr(ws["attn_ws"]), st)
+            self._layer_bwd_post_attn(L, wt, pre, sv["xs"], 2 * H, Me, enc_sc, ws["dy"], st)
+            dy = (ws["dy"], 1, (0, 0, 0), 0)
+        L.rows_add(_ptr(ws["dy"]), None, None, H, Me, H, _ptr(ws["dJ"]), H, 0, 0, 0, 1, st)      # dJ = dJ0
+
+        # ---- obj encoder: J0[obj rows] = LN(W a + b)
+        L.ln_bwd(_ptr(mws["h_obj"]), 0, H, _ptr(ws["dJ"]), 0, H, F, Le, Lt, _ptr(f["obj_feat_layer_norm.weight"]),
+                 _ptr(f["obj_feat_layer_norm.bias"]), LN_EPS_EMBED, B * F, H, 0, _ptr(ws["dh_obj"]), 1, H,
+                 g("obj_feat_layer_norm.weight"), g("obj_feat_layer_norm.bias"), g("linear_obj_feat_to_mmt_in.bias"), st)
+        kpo, kpc = P["k_obj_pad"], P["k_ocr_pad"]
+        ko, kc = P["k_obj"], P["k_ocr"]
+        ws["dw_obj"].zero_()
+        self._wgrad(L, ws["dh_obj"], H, mws["a_obj_s"], 2 * kpo, _ptr(ws["dw_obj"]), kpo, B * F, H, kpo, st)
+        self.grad("linear_obj_feat_to_mmt_in.weight").add_(ws["dw_obj"][:, :ko])
+        L.gemm_bf16(_ptr(ws["dh_obj"]), H, W["objT"].data_ptr() + (ko - 50) * H * 2, H, None, None, 0, _ptr(ws["d_id_obj"]), 52,
+                    B * F, 50, H, _lib.GEMM_OUT_F32, 0, st)
+        L.embed_scatter_add(_ptr(ws["d_id_obj"]), 0, 52, 0, 50, _ptr(inp["frame_id"]), B * F, -1, g("frame_embeddings.weight"),
+                            50, st)
+        # ---- OCR encoder: J0[ocr rows] = LN(W a + b) + LN(W2 bbox + b2)
+        L.ocr_finish_bwd(_ptr(mws["h_ocr"]), H, _ptr(inp["ocr_bbox_coordinates"]), _ptr(f["linear_ocr_bbox_to_mmt_in.weight"]),
+                         _ptr(f["linear_ocr_bbox_to_mmt_in.bias"]), _ptr(f["ocr_feat_layer_norm.weight"]),
+                         _ptr(f["ocr_bbox_layer_norm.weight"]), LN_EPS_EMBED, B * O, H, _ptr(ws["dJ"]), H, O, Le, Lt + F,
+                         _ptr(ws["dh_ocr"]), H, _ptr(ws["dc_ocr"]), H, g("ocr_feat_layer_norm.weight"),
+                         g("ocr_feat_layer_norm.bias"), g("ocr_bbox_layer_norm.weight"), g("ocr_bbox_layer_norm.bias"),
+                         g("linear_ocr_feat_to_mmt_in.bias"), g("linear_ocr_bbox_to_mmt_in.weight"),
+                         g("linear_ocr_bbox_to_mmt_in.bias"), st)
+        ws["dw_ocr"].zero_()
+        self._wgrad(L, ws["dh_ocr"], H, mws["a_ocr_s"], 2 * kpc, _ptr(ws["dw_ocr"]), kpc, B * O, H, kpc, st)
+        self.grad("linear_ocr_feat_to_mmt_in.weight").add_(ws["dw_ocr"][:, :kc])
+        L.gemm_bf16(_ptr(ws["dh_ocr"]), H, W["ocrT"].data_ptr() + (kc - 100) * H * 2, H, None, None, 0, _ptr(ws["d_id_ocr"]), 100,
+                    B * O, 100, H, _lib.GEMM_OUT_F32, 0, st)
+        L.embed_scatter_add(_ptr(ws["d_id_ocr"]), 0, 100, 0, 50, _ptr(inp["temporal_id"]), B * O, -1,
+                            g("temporal_position_embeddings.weight"), 50, st)
+        L.embed_scatter_add(_ptr(ws["d_id_ocr"]), 0, 100, 50, 50, _ptr(inp["track_id"]), B * O, -1,
+                            g("track_position_embeddings.weight"), 50, st)
+        # ---- TextBert
+        text = P["text"]
+        dy = (ws["dJ"], 0, (Lt, Le, 0), 0)
+        txt_sc = {k: t[:Mt] for k, t in enc_sc.items()}
+        dx_t = ws["dy2"][:Mt]
+        for li in range(len(text) - 1, -1, -1):
+            lw, wt, sv = text[li], W["text"][li], ws["text"][li]
+            pre = "text_bert.encoder.layer.%d." % li
+            self._layer_bwd_pre_attn(L, wt, lw, pre, sv, Mt, dy, txt_sc, st, x3=True)
+            L.attn_bwd(_ptr(sv["qkvs"]), 6 * H, None, 0, _ptr(sv["ctxs"]), 2 * H, None, 0, _ptr(txt_sc["dctx"]), H, None, 0,
+                       _ptr(txt_sc["dqkv"]), 3 * H, None, 0, B, Lt, 0, H, 12, _ptr(mws["keys_txt"]), _ptr(mws["nk_txt"]),
+                       Lt, Lt, _ptr(ws["attn_ws"]), st)
+            self._layer_bwd_post_attn(L, wt, pre, sv["xs"], 2 * H, Mt, txt_sc, dx_t, st)
+            dy = (dx_t, 1, (0, 0, 0), 0)
+        e = "text_bert.embeddings."
+        L.bert_embed_bwd(_ptr(dx_t), H, _ptr(inp["text"]), Mt, Lt, H, _ptr(f[e + "word_embeddings.weight"]),
+                         _ptr(f[e + "position_embeddings.weight"]), _ptr(f[e + "token_type_embeddings.weight"]),
+                         _ptr(f[e + "LayerNorm.weight"]), LN_EPS_BERT, g(e + "word_embeddings.weight"),
+                         g(e + "position_embeddings.weight"), g(e + "token_type_embeddings.weight"),
+                         g(e + "LayerNorm.weight"), g(e + "LayerNorm.bias"), st)
+        self.saved = None
+        return [self.grad(n) for n in self.live_names]
+
+    # ------------------------------------------------------------------ collective + optimizer
+    def all_reduce(self):
+        """Gradient all-reduce (mean) of the live range of the flat buffer: one NCCL call over NVLink
+        (reference: DDP, base_trainer.py:134-137)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat_grad[:self.live_end], op=dist.ReduceOp.SUM)
+            return 1.0 / dist.get_world_size()
+        return 1.0
+
+    def step(self, lr, lr_scale_text_bert=0.1, lr_scale_mmt=1.0, max_grad_l2_norm=0.25, betas=(0.9, 0.999), eps=1e-8,
+             grad_scale=1.0):
+        """clip_grad_norm_(all, max_grad_l2_norm) + Adam.step() over the flat buffers (reference
+        base_trainer.py:266-269 with optimizer_attributes of configs/t2s_*.yml)."""
+        L = _lib.get_lib()
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        if not hasattr(self, "_opt_ws"):
+            self._opt_ws = torch.empty(1024, device=self.dev, dtype=torch.float64)
+            self._sumsq = torch.zeros(1, device=self.dev, dtype=torch.float32)
+        self.step_count += 1
+        L.sumsq(_ptr(self.flat_grad), self.live_end, _ptr(self._opt_ws), _ptr(self._sumsq), st)
+        for gname, scale in (("default", 1.0), ("text_bert", lr_scale_text_bert), ("mmt", lr_scale_mmt)):
+            a, b = self.group_ranges[gname]
+            if b > a:
+                L.adam_step(self.flat_param.data_ptr() + 4 * a, self.flat_grad.data_ptr() + 4 * a,
+                            self.adam_m.data_ptr() + 4 * a, self.adam_v.data_ptr() + 4 * a, b - a, lr * scale, betas[0],
+                            betas[1], eps, self.step_count, _ptr(self._sumsq), float(max_grad_l2_norm or 0.0), grad_scale, st)
+        self.model._packed = None      # weights changed: bf16 / split operand copies are stale
+        self._wt = None
+        return self._sumsq
