@@ -30,6 +30,9 @@ FIXTURES = {
     # tiny shapes: fast CPU checks of every code path (ties, pads, short videos)
     "t2s_small_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2), 3, 11, 0, "stress", "eval"),
     "t2s_small_train": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2), 3, 12, 0, "stress", "train"),
+    # same as t2s_small_train, plus loss.backward() through the reference's own modules and loss classes:
+    # parameter-gradient norms and samples that pin the oracle's autograd (and through it the B200 backward)
+    "t2s_small_train_grads": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2), 3, 12, 0, "stress", "train"),
     "t2s_small_default": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2), 2, 13, 1, "default", "eval"),
     # BASELINE config 1: t2s_abinet shapes, batch 1 (+1), eval
     "t2s_abinet_eval": (dict(), 2, 1235, 0, "stress", "eval"),
@@ -141,6 +144,10 @@ def run_fixture(name):
             captured["neg_frame_topk_mask"] = out[2].detach().clone()
         hooks.append(model.Grounding_Module.frame_grounding_indicator.register_forward_hook(cap_temporal))
     noise = {tuple(inp["gumbel_frame"].shape): inp["gumbel_frame"], tuple(inp["gumbel_ocr"].shape): inp["gumbel_ocr"]}
+    if name.endswith("_grads"):
+        return run_grad_fixture(name, model, sl, inp, noise, hooks, captured,
+                                dict(dims=dkw, batch=B, in_seed=in_seed, w_seed=w_seed, variant=variant, mode=mode,
+                                     torch=torch.__version__))
     with torch.no_grad(), InjectGumbel(noise):
         out = model.forward(sl)
     for h in hooks:
@@ -160,6 +167,43 @@ def run_fixture(name):
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **res)
     print(name, {k: getattr(v, "shape", None) for k, v in res.items()}, "%.1f KB" % (os.path.getsize(path) / 1e3))
+
+
+GRAD_LOSS_WEIGHTS = (1.0, 100.0)     # pos_bce_loss, InfoNCE (configs/t2s_clipocr.yml)
+GRAD_SAMPLE = 2048
+
+
+def run_grad_fixture(name, model, sl, inp, noise, hooks, captured, meta):
+    """forward (training mode, dropout 0) + the reference's losses + loss.backward(); stores per-parameter gradient
+    norms and a strided sample of every gradient (index i * stride, stride = max(1, numel // GRAD_SAMPLE))."""
+    from pythia.modules.losses import POSBCEWithMaskLoss, InfoNCE
+    with InjectGumbel(noise):
+        out = model.forward(sl)
+    for h in hooks:
+        h.remove()
+    bce = POSBCEWithMaskLoss()(sl, out)
+    nce = InfoNCE()(sl, out)
+    (GRAD_LOSS_WEIGHTS[0] * bce + GRAD_LOSS_WEIGHTS[1] * nce).backward()
+    res = {"loss_pos_bce": bce.detach().numpy(), "loss_info_nce": nce.detach().numpy(),
+           "ground_frame": out["ground_frame"].numpy()}
+    for k, v in captured.items():
+        res[k] = v.numpy()
+    names, norms = [], []
+    for n, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        g = p.grad.detach().flatten()
+        names.append(n)
+        norms.append(float(g.double().norm()))
+        stride = max(1, g.numel() // GRAD_SAMPLE)
+        res["g:" + n] = g[::stride][:GRAD_SAMPLE].numpy().copy()
+    res["grad_names"] = np.asarray(names)
+    res["grad_norms"] = np.asarray(norms)
+    meta = dict(meta, loss_weights=GRAD_LOSS_WEIGHTS, grad_sample=GRAD_SAMPLE)
+    res["meta"] = np.asarray(repr(meta))
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **res)
+    print(name, len(names), "parameters with gradients", "%.1f KB" % (os.path.getsize(path) / 1e3))
 
 
 if __name__ == "__main__":

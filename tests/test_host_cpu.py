@@ -38,6 +38,30 @@ def test_library_exports_every_header_symbol():
     assert cdll.t2s_abi_version() == 1
 
 
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/t2s_b200.h is bound with the same number and kind of arguments."""
+    import re
+    h = open(os.path.join(ROOT, "include", "t2s_b200.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    bound = dict(tlib.SIGNATURES)
+    bound.update({k: v[1] for k, v in tlib.PLAIN.items()})
+    protos = re.findall(r"\b(t2s_\w+)\s*\(([^;{]*?)\)\s*;", h, flags=re.S)
+    assert {n for n, _ in protos} == set(bound), set(bound) ^ {n for n, _ in protos}
+    for name, params in protos:
+        ps = [p.strip() for p in params.split(",") if p.strip() and p.strip() != "void"]
+        assert len(ps) == len(bound[name]), name
+        for p_, a in zip(ps, bound[name]):
+            if "*" in p_:
+                want = tlib._p
+            elif p_.startswith("long long"):
+                want = tlib._ll
+            elif p_.startswith("float"):
+                want = tlib._f
+            else:
+                want = tlib._i
+            assert a is want, (name, p_)
+
+
 def test_library_is_sm100a_tcgen05_tma():
     """The shipped GEMM really is the Blackwell path: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA)."""
     import subprocess
@@ -172,6 +196,12 @@ def _dp_worker(rank, world, port, q):
             assert float(red["a"]) == pytest.approx(15.0) and float(red["b"]) == pytest.approx(1.5)
         with pytest.raises(RuntimeError):
             dp.per_rank_batch(5)
+        # gradient all-reduce of the training step: flat fp32 buffer, sum + 1/world factor (or mean in place)
+        flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+        scale = dp.all_reduce_flat_(flat)
+        assert scale == pytest.approx(0.5) and torch.equal(flat, torch.arange(1000, dtype=torch.float32) * 3)
+        flat2 = torch.full((7,), float(rank))
+        assert dp.all_reduce_flat_(flat2, mean=True) == 1.0 and torch.allclose(flat2, torch.full((7,), 0.5))
         q.put((rank, "ok"))
     except Exception as e:      # pragma: no cover
         q.put((rank, repr(e)))

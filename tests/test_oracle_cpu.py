@@ -97,3 +97,43 @@ def test_oracle_is_deterministic_and_gumbel_sensitive():
     # the ref variant sees the dataset masks, not the grounded ones: its first decoder row (prev = BOS)
     # cannot depend on the noise; later rows may, through the greedy `pos` decode that feeds prev_inds
     assert torch.equal(a["ref_scores"][:, 0], c["ref_scores"][:, 0])
+
+
+def test_oracle_autograd_matches_reference_backward_golden():
+    """loss.backward() of the REAL reference (training mode, dropout 0, its own loss classes; fixture
+    t2s_small_train_grads) against autograd through the oracle: pins the gradient oracle that the B200 backward is
+    held to in tests/test_train_gpu.py."""
+    z, meta, d, sd, inp = load_golden("t2s_small_train_grads")
+    w_bce, w_nce = meta["loss_weights"]
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    out = O.forward_t2s(sd, d, inp, training=True, neg_frame_override=_neg_override(z))
+    assert np.array_equal(out["ground_frame"].numpy(), z["ground_frame"])
+    bce = O.pos_bce_loss(out["pos_scores"], inp["targets"], inp["train_loss_mask"])
+    nce = O.info_nce(out["ref_scores"], out["pos_scores"], out["neg_scores"])
+    ref_bce, ref_nce = float(z["loss_pos_bce"].reshape(-1)[0]), float(z["loss_info_nce"].reshape(-1)[0])
+    assert abs(float(bce) - ref_bce) <= 1e-5 * max(1.0, abs(ref_bce))
+    assert abs(float(nce) - ref_nce) <= 1e-4
+    (w_bce * bce + w_nce * nce).backward()
+    names = [str(n) for n in z["grad_names"]]
+    norms = dict(zip(names, z["grad_norms"]))
+    scale = max(norms.values())
+    checked = 0
+    for n, p in sd.items():
+        if not p.requires_grad:
+            continue
+        g = p.grad
+        if n not in norms:
+            assert g is None or float(g.abs().max()) == 0.0, n        # no gradient in the reference either
+            continue
+        gref = z["g:" + n]
+        if g is None:
+            assert norms[n] == 0.0, n
+            continue
+        stride = max(1, g.numel() // meta["grad_sample"])
+        got = g.flatten()[::stride][:meta["grad_sample"]].numpy()
+        # fp32 reduction-order noise only; tiny gradients (e.g. key biases, mathematically zero) are compared
+        # against the scale of the whole gradient
+        assert abs(float(g.double().norm()) - norms[n]) <= 2e-3 * norms[n] + 1e-6 * scale, (n, float(g.norm()), norms[n])
+        assert np.abs(got - gref).max() <= 2e-3 * np.abs(gref).max() + 1e-6 * scale, n
+        checked += 1
+    assert checked >= 150

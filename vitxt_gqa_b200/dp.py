@@ -91,3 +91,17 @@ def gather_predictions(model_output, keys=("pos_scores", "ground_frame", "ground
             g = gather_tensor(model_output[k])
             out[k] = g.reshape((-1,) + tuple(model_output[k].shape[1:])) if world() > 1 else g
     return out
+
+
+def all_reduce_flat_(flat, mean=False):
+    """Gradient all-reduce of one flat buffer (reference: DistributedDataParallel's bucketed all-reduce inside
+    backward, pythia/trainers/base_trainer.py:134-137; DDP averages).  Sums in place and returns the factor that
+    turns the sum into the mean (1 / world) so the optimizer kernel can fold it in; mean=True applies it here."""
+    w = world()
+    if w < 2:
+        return 1.0
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if mean:
+        flat.mul_(1.0 / w)
+        return 1.0
+    return 1.0 / w

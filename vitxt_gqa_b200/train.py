@@ -27,7 +27,6 @@ Schedule of the backward (per variant v in ref, pos, neg; then the shared front)
   variants summed into dJ1 -> QTV (tanh residual) -> obj / OCR encoders, TextBert -> embeddings.
 """
 import torch
-import torch.distributed as dist
 
 from . import lib as _lib
 
@@ -583,10 +582,8 @@ class TrainEngine:
     def all_reduce(self):
         """Gradient all-reduce (mean) of the live range of the flat buffer: one NCCL call over NVLink
         (reference: DDP, base_trainer.py:134-137)."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_grad[:self.live_end], op=dist.ReduceOp.SUM)
-            return 1.0 / dist.get_world_size()
-        return 1.0
+        from .dp import all_reduce_flat_
+        return all_reduce_flat_(self.flat_grad[:self.live_end])
 
     def step(self, lr, lr_scale_text_bert=0.1, lr_scale_mmt=1.0, max_grad_l2_norm=0.25, betas=(0.9, 0.999), eps=1e-8,
              grad_scale=1.0):
