@@ -479,18 +479,55 @@ def run_train(args, wl, model, d, inp, dev, world, rank, local):
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
 
-    pinned_loss = None
+    # end to end: every step's inputs come from pinned host memory (H2D on a copy stream, double buffered against the
+    # previous step's compute) and every step's two loss scalars are read back to pinned host memory; the read of
+    # step i is awaited while step i + 1 is being enqueued (as a training loop that logs its loss does), so the
+    # device never waits for the host between steps
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+
+    dev_buf = [host.to(dev), host.to(dev)]          # two resident input slots, overwritten in place
+    slot_free = [None, None]                         # main-stream event: the step that read the slot has finished
+    tensor_keys = [k for k in host.keys() if torch.is_tensor(host[k])]
+
+    def stage_inputs(i):
+        slot = i & 1
+        with torch.cuda.stream(copy_stream):
+            if slot_free[slot] is not None:
+                copy_stream.wait_event(slot_free[slot])
+            for k in tensor_keys:
+                dev_buf[slot][k].copy_(host[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return dev_buf[slot], ev, slot
+
+    pinned_loss = [None, None]
+    loss_host = []
+
     def e2e_steps(n):
-        nonlocal pinned_loss
-        for _ in range(n):
-            sl = host.to(dev, non_blocking=True)
+        nxt = stage_inputs(0)
+        pending = None
+        for i in range(n):
+            sl, ev, slot = nxt
+            main_stream.wait_event(ev)
+            if i + 1 < n:
+                nxt = stage_inputs(i + 1)
             losses = step(sl)
-            if pinned_loss is None:
-                pinned_loss = {k: torch.empty(1).pin_memory() for k in losses}
+            if pinned_loss[slot] is None:
+                pinned_loss[slot] = {k: torch.empty(1).pin_memory() for k in losses}
             for k, v in losses.items():
-                pinned_loss[k].copy_(v.detach(), non_blocking=True)
-            torch.cuda.synchronize()
-    e2e_steps(1)
+                pinned_loss[slot][k].copy_(v.detach(), non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main_stream)
+            slot_free[slot] = done
+            if pending is not None:
+                pending[0].synchronize()
+                loss_host.append({k: float(v) for k, v in pinned_loss[pending[1]].items()})
+            pending = (done, slot)
+        pending[0].synchronize()
+        loss_host.append({k: float(v) for k, v in pinned_loss[pending[1]].items()})
+
+    e2e_steps(2)
     barrier()
     e0.record()
     e2e_steps(args.steps)
@@ -539,7 +576,8 @@ def run_train(args, wl, model, d, inp, dev, world, rank, local):
         "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": None,
-        "model_tflops": round(samples * gf / 1e3 / (ms_dev * 1e-3) / world, 1), "kernels": kernels,
+        "model_tflops": round(samples * gf / 1e3 / (ms_dev * 1e-3) / world, 1),
+        "loss_trace": loss_host[-min(len(loss_host), 4):], "kernels": kernels,
     }))
     if world > 1:
         dist.destroy_process_group()
