@@ -55,6 +55,14 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) 
     return d;
 }
 
+// 2^x by one MUFU.EX2 (flush-to-zero); exp2f() wraps the same instruction in denormal-range scaling (three more
+// issue slots per element) that the softmax never needs: its arguments are <= 8 and results below 2^-126 may vanish
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <bool X3>
 __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2)
 attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, int L, int H,
@@ -210,42 +218,15 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         const int sw = r & 7;
         constexpr float kRescale = 8.0f;                   // log2 domain: P stays below 2^8
         float m_run = -INFINITY, l_run = 0.f;
-        for (int t = 0; t < nt; ++t) {
-            const int valid = min(TC_BK, nk - t * TC_BK);          // keys of this tile that exist
-            mbar_wait(s_full, t & 1);       // S(t) done; MMAs retire in order, so P.V(t-1) is done as well
-            tc_fence_after();
-            float mt = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c * 32 + j < valid) mt = fmaxf(mt, __uint_as_float(v[j]));
-            }
-            mt *= scale_log2;
-            const bool raise = mt > m_run + kRescale || t == 0;
-            float corr = 1.0f;
-            if (raise) {
-                corr = exp2f(m_run - mt);                  // exp2(-inf) == 0 on the first tile
-                m_run = mt;
-                l_run *= corr;
-            }
-            if (t > 0 && __any_sync(0xffffffffu, raise)) {
-                // rescale this warp's 32 rows of O in TMEM (rows that keep their maximum use corr == 1)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * corr);
-                    tmem_st_32x32(tmem_O + lane_addr + c * 32, v);
-                }
-                tmem_st_wait();
-            }
-            float sum = 0.f;
+        // One sweep over S per tile: P = exp2(S * scale - m_run) is formed with the maximum carried from the earlier
+        // tiles while the tile's own maximum is tracked alongside; only when some row of the warp exceeds m_run by
+        // more than 2^8 (or on the first tile, where no maximum exists yet) is the maximum raised, O rescaled in
+        // TMEM and the tile's P recomputed.  (A separate maximum sweep doubled the TMEM reads and cost ~40 % of the
+        // softmax warps' issue slots; ncu showed the tensor pipe waiting on them 85 % of the time.)
+        auto exp_sweep = [&](int valid, float m_use, float& tile_max_raw, float& sum) {
+            tile_max_raw = -INFINITY;
+            sum = 0.f;
+            const bool full = valid == TC_BK;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
@@ -254,10 +235,14 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                 uint32_t ph[16], pl[16];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    float p0 = exp2f(fmaf(__uint_as_float(v[j]), scale_log2, -m_run));
-                    float p1 = exp2f(fmaf(__uint_as_float(v[j + 1]), scale_log2, -m_run));
-                    if (c * 32 + j >= valid) p0 = 0.f;
-                    if (c * 32 + j + 1 >= valid) p1 = 0.f;
+                    float s0 = __uint_as_float(v[j]), s1 = __uint_as_float(v[j + 1]);
+                    if (!full) {                 // warp-uniform: only the last key tile of a sample is ragged
+                        if (c * 32 + j >= valid) s0 = -INFINITY;
+                        if (c * 32 + j + 1 >= valid) s1 = -INFINITY;
+                    }
+                    tile_max_raw = fmaxf(tile_max_raw, fmaxf(s0, s1));
+                    const float p0 = ex2_fast(fmaf(s0, scale_log2, -m_use));
+                    const float p1 = ex2_fast(fmaf(s1, scale_log2, -m_use));
                     sum += p0 + p1;
                     ph[j >> 1] = pack_bf16x2(p0, p1);
                     if (X3) pl[j >> 1] = pack_bf16x2(p0 - bf16lo(ph[j >> 1]), p1 - bf16hi(ph[j >> 1]));
@@ -272,6 +257,51 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                     if (X3)
                         *reinterpret_cast<uint4*>(dst + 2 * TC_TILE + ((chunk ^ sw) << 4)) =
                             make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+                }
+            }
+        };
+        for (int t = 0; t < nt; ++t) {
+            const int valid = min(TC_BK, nk - t * TC_BK);          // keys of this tile that exist
+            mbar_wait(s_full, t & 1);       // S(t) done; MMAs retire in order, so P.V(t-1) is done as well
+            tc_fence_after();
+            float mt_raw, sum;
+            if (t == 0) {
+                // no maximum yet: take it from a maximum-only pass (exp2(-inf - (-inf)) would be NaN)
+                mt_raw = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c * 32 + j < valid) mt_raw = fmaxf(mt_raw, __uint_as_float(v[j]));
+                }
+                m_run = mt_raw * scale_log2;
+                exp_sweep(valid, m_run, mt_raw, sum);
+            } else {
+                exp_sweep(valid, m_run, mt_raw, sum);
+                const float mt = mt_raw * scale_log2;
+                const bool raise = mt > m_run + kRescale;
+                if (__any_sync(0xffffffffu, raise)) {
+                    float corr = 1.0f;
+                    if (raise) {
+                        corr = exp2f(m_run - mt);
+                        m_run = mt;
+                        l_run *= corr;
+                    }
+                    // rescale this warp's 32 rows of O in TMEM (rows that keep their maximum use corr == 1)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * corr);
+                        tmem_st_32x32(tmem_O + lane_addr + c * 32, v);
+                    }
+                    tmem_st_wait();
+                    exp_sweep(valid, m_run, mt_raw, sum);      // P of this tile against the raised maximum
                 }
             }
             l_run += sum;

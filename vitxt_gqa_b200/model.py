@@ -215,6 +215,10 @@ class _FusionModelBase(BaseModel):
         # persistent GEMM grids capped at (SMs - overlap_sms) CTAs.  0 disables the overlap.
         self.overlap_sms = int(os.environ.get("T2S_B200_OVERLAP_SMS", str(self.config.get("b200_overlap_sms", 16))))
         self._side_streams = {}
+        self._phases_on = os.environ.get("T2S_B200_PHASES", "0") == "1"
+        self._phase_events = []
+        # greedy-decode GEMMs (one row per sample) on the weight-streaming kernel instead of the 128-row tcgen05 tile
+        self.skinny_decode = os.environ.get("T2S_B200_SKINNY", str(self.config.get("b200_skinny_decode", 0))) not in ("0", "False")
         if self.attn_impl not in ("tc", "mma"):
             raise ValueError("b200_attention must be 'tc' or 'mma'")
         if self.grounding_precision not in ("bf16x3", "fp32"):
@@ -396,6 +400,9 @@ class _FusionModelBase(BaseModel):
             qd=torch.empty(Md, H, **b16), x1d=torch.empty(Md, H, **b16),
             qkvd={v: [torch.empty(Md, 3 * H, **b16) for _ in range(n_mmt)] for v in variants},
             prev=torch.zeros(B, T, device=device, dtype=torch.int64),
+            skinny_ws=torch.zeros(max(int(_lib.get_lib().gemm_skinny_workspace_bytes(B, n_, k_))
+                                      for n_, k_ in ((3 * H, H), (H, H), (4 * H, H), (H, 4 * H), (V, H))),
+                                  device=device, dtype=torch.uint8),
             loss_ws=torch.empty(int(_lib.get_lib().loss_workspace_bytes(B, T)), device=device, dtype=torch.uint8),
         )
         if self.grounding_precision == "bf16x3":    # bf16 hi|lo operand buffers of t2s_gemm_bf16x3
@@ -594,31 +601,40 @@ class _FusionModelBase(BaseModel):
         def at(t, width, esize=2):            # pointer to row t0 of a [B*T, width] buffer
             return t.data_ptr() + off * width * esize
 
+        if nq == 1 and self.skinny_decode:
+            # one row per sample: weight-streaming kernel spread over all SMs (csrc/gemm_skinny.cu)
+            sk = ws["skinny_ws"]
+
+            def gemm(A, lda, W, ldw, bias, res, ldr, C, ldc, M_, N_, K_, flags, _bn, st_):
+                L.gemm_skinny_bf16(A, lda, W, ldw, bias, res, ldr, C, ldc, M_, N_, K_, flags, _ptr(sk), sk.numel(), st_)
+        else:
+            gemm = L.gemm_bf16
+
         x = ws["xd"]
         ping = [ws["xd1"], ws["xd2"]]
         for li, lw in enumerate(P["mmt"]):
             qkvd = ws["qkvd"][v][li]
             qkve = ws["qkv0"] if li == 0 else ws["qkv"][v][li]
-            L.gemm_bf16(at(x, H), rs * H, _ptr(lw["wqkv"]), H, _ptr(lw["bqkv"]), None, 0, at(qkvd, 3 * H),
+            gemm(at(x, H), rs * H, _ptr(lw["wqkv"]), H, _ptr(lw["bqkv"]), None, 0, at(qkvd, 3 * H),
                         rs * 3 * H, M, 3 * H, H, 0, 0, st)
             L.attn_dec(_ptr(qkve), 3 * H, Le, _ptr(qkvd), 3 * H, T, B, H, 12, _ptr(ws["keys"][v]), _ptr(ws["nk"][v]),
                        Le, t0, nq, _ptr(ws["ctxd"]), H, st)
-            L.gemm_bf16(at(ws["ctxd"], H), rs * H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), at(x, H), rs * H,
+            gemm(at(ws["ctxd"], H), rs * H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), at(x, H), rs * H,
                         at(ws["hd"], H), rs * H, M, H, H, 0, 0, st)
             L.add_ln(at(ws["hd"], H), 1, rs * H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H,
                      None, 0, None, 0, at(ws["x1d"], H), rs * H, 0, 0, 0, st)
-            L.gemm_bf16(at(ws["x1d"], H), rs * H, _ptr(lw["wi"]), H, _ptr(lw["bi"]), None, 0, at(ws["interd"], 4 * H),
+            gemm(at(ws["x1d"], H), rs * H, _ptr(lw["wi"]), H, _ptr(lw["bi"]), None, 0, at(ws["interd"], 4 * H),
                         rs * 4 * H, M, 4 * H, H, _lib.GEMM_GELU, 0, st)
-            L.gemm_bf16(at(ws["interd"], 4 * H), rs * 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), at(ws["x1d"], H),
+            gemm(at(ws["interd"], 4 * H), rs * 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), at(ws["x1d"], H),
                         rs * H, at(ws["hd"], H), rs * H, M, H, 4 * H, 0, 0, st)
             out = ping[li & 1]
             L.add_ln(at(ws["hd"], H), 1, rs * H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H,
                      None, 0, None, 0, at(out, H), rs * H, 0, 0, 0, st)
             x = out
         N = V + O
-        L.gemm_bf16(at(x, H), rs * H, _ptr(P["w_cls"]), H, _ptr(f["classifier.module.bias"]), None, 0,
+        gemm(at(x, H), rs * H, _ptr(P["w_cls"]), H, _ptr(f["classifier.module.bias"]), None, 0,
                     scores.data_ptr() + off * N * 4, rs * N, M, V, H, _lib.GEMM_OUT_F32, 0, st)
-        L.gemm_bf16(at(x, H), rs * H, _ptr(P["w_ptr_q"]), H, _ptr(f["ocr_ptr_net.query.bias"]), None, 0,
+        gemm(at(x, H), rs * H, _ptr(P["w_ptr_q"]), H, _ptr(f["ocr_ptr_net.query.bias"]), None, 0,
                     at(ws["qd"], H), rs * H, M, H, H, 0, 0, st)
         L.ptr_score(_ptr(ws["qd"]), H, B, T, t0, nq, ws["keyp"][v].data_ptr() + ocr_row0 * H * 2, Le * H, H, O, H,
                     jm.data_ptr() + ocr_row0 * 4, Le, _ptr(scores), N, V, st)
@@ -631,6 +647,23 @@ class _FusionModelBase(BaseModel):
 
     def _device(self):
         return next(self.parameters()).device
+
+    # measurement aid (T2S_B200_PHASES=1): CUDA events at the phase boundaries of forward, on the stream that runs
+    # the phase; `phase_report()` synchronises and returns {phase: ms since the start of that forward}
+    def _mark(self, name, stream=None):
+        if not self._phases_on:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream if stream is not None else torch.cuda.current_stream())
+        self._phase_events.append((name, ev))
+
+    def phase_report(self):
+        torch.cuda.synchronize()
+        evs, self._phase_events = self._phase_events, []
+        if not evs:
+            return {}
+        t0 = evs[0][1]
+        return {n: t0.elapsed_time(e) for n, e in evs}
 
     def _gather_inputs(self, sample_list, names):
         dev = self._device()
@@ -740,6 +773,8 @@ class T2S(_FusionModelBase):
         st = torch.cuda.current_stream(dev).cuda_stream
         f = P["f32"]
 
+        self._phase_events = []
+        self._mark("start")
         # ---- masks and key lists
         L.mask_prep(_ptr(inp["text_len"]), _ptr(inp["frame_mask"]), _ptr(inp["ocr_mask"]), B, Lt, F, O,
                     _ptr(ws["jm_ref"]), st)
@@ -761,7 +796,9 @@ class T2S(_FusionModelBase):
                             first=(i == 0), feeds_next=not last)
             x = out
 
+        self._mark("front")
         ground_frame, ground_box, dbg, dbg_f, dbg_o = self._grounding(L, P, ws, inp, B, Lt, F, O, Of, Le, dev, st)
+        self._mark("grounding")
 
         # ---- bf16 answer transformer
         jm = {"ref": ws["jm_ref"], "pos": ws["jm_pos"], "neg": ws["jm_neg"]}
@@ -778,6 +815,7 @@ class T2S(_FusionModelBase):
             forced = self.parity_hooks.get("force_prev_inds")     # test-only teacher forcing of the feedback
             forced = forced.to(dev) if forced is not None else None
             self._mmt_encoder(L, P, ws, ("pos",), B, Le, st)
+            self._mark("enc_pos")
 
             def greedy(stream_handle):   # drives only the `pos` variant (reference t2s.py:353, Q15)
                 for t in range(T):
@@ -795,16 +833,25 @@ class T2S(_FusionModelBase):
                 side = self._side_streams.get(dev.index)
                 if side is None:
                     side = self._side_streams[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
-                side.wait_stream(main)
+                # the host enqueues the ~70 encoder launches first: the ~300 decode launches are host-bound
+                # (~10 us each through ctypes), and issued first they would keep the caller's stream empty meanwhile
+                pos_ready = torch.cuda.Event()
+                pos_ready.record(main)
+                self._mmt_encoder(L, P, ws, ("ref", "neg"), B, Le, st, qkv0=False, sm_cap=n_sms - self.overlap_sms)
+                self._mark("enc_ref_neg")
+                side.wait_event(pos_ready)
                 with torch.cuda.stream(side):
                     greedy(side.cuda_stream)
-                self._mmt_encoder(L, P, ws, ("ref", "neg"), B, Le, st, qkv0=False, sm_cap=n_sms - self.overlap_sms)
+                    self._mark("greedy_side", side)
                 main.wait_stream(side)
             else:
                 greedy(st)
+                self._mark("greedy")
                 self._mmt_encoder(L, P, ws, ("ref", "neg"), B, Le, st, qkv0=False)
+                self._mark("enc_ref_neg")
             for v in ("ref", "neg"):
                 self._decode_rows(L, P, ws, v, jm[v], scores[v], B, Le, T, V, O, F, Lt, 0, T, st)
+            self._mark("dec_ref_neg")
         if dbg:
             self.last_debug = dict(J0=ws["J0"].view(B, Le, H), J1=ws["J1"].view(B, Le, H), sim=ws["sim"],
                                    gq=ws["gq"], frame_score=dbg_f, ocr_score=dbg_o, jm_pos=ws["jm_pos"],
