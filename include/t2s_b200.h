@@ -250,6 +250,14 @@ int t2s_sumsq(const float* g, long long n, void* workspace, float* out, void* st
 int t2s_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, int step, const float* sumsq, float max_norm, float grad_scale, void* stream);
 
+/* Input featurisation, the step before the path.  PHOC descriptor of OCR tokens: replaces the
+ * reference's CPU extension pythia/utils/phoc/src/cphoc.c:12-113 + build_phoc.py:9-14 (lower-case, keep [a-z0-9])
+ * + PhocProcessor, datasets/processors.py:904-928.  bytes = the tokens' UTF-8 bytes back to back (non-ASCII tokens
+ * lower-cased by the caller; ASCII is lower-cased and filtered on the device), offsets[n_tokens + 1] = byte ranges;
+ * out [rows, 604] fp32 0/1 with row stride ldo; rows n_tokens..rows-1 are the processor's zero padding. */
+int t2s_phoc_build(const unsigned char* bytes, const int* offsets, int n_tokens, int rows, float* out, long long ldo,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

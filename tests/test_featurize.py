@@ -1,0 +1,109 @@
+"""PHOC featuriser: oracle vs the reference binary's golden vectors on CPU; the CUDA kernel
+(through the C ABI) vs golden + oracle on the GPU, bit for bit."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import build_ref, phoc_oracle
+from vitxt_gqa_b200 import featurize, lib as tlib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _golden():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "phoc_golden.npz"))
+    tokens = bytes(z["tokens_utf8"]).decode("utf-8").split("\x00")
+    rows = np.unpackbits(z["bits"], axis=1)[:, :604].astype(np.float32)
+    assert len(tokens) == rows.shape[0] == 1500
+    return tokens, rows
+
+
+# ------------------------------------------------------------------------------------------ CPU
+def test_golden_tokens_are_the_seeded_synthetic_ones():
+    tokens, _ = _golden()
+    assert tokens == synth.make_ocr_tokens(1500, seed=2024)
+
+
+def test_phoc_oracle_matches_reference_golden_bit_exact():
+    tokens, rows = _golden()
+    got = np.stack([phoc_oracle.build_phoc(t) for t in tokens])
+    assert np.array_equal(got, rows)
+    # known structure: "<pad>" is the word "pad"; the empty word is all zero; level-2 halves of "ab"
+    assert np.array_equal(phoc_oracle.build_phoc("<pad>"), phoc_oracle.build_phoc("PAD"))
+    assert phoc_oracle.build_phoc("?!").sum() == 0
+    ab = phoc_oracle.build_phoc("ab")
+    assert ab[0] == 1 and ab[36 + 1] == 1 and ab[36] == 0
+
+
+def test_phoc_oracle_matches_compiled_reference_when_present():
+    """oracle/_ref/cphoc.so = the reference's own cphoc.c compiled in place (oracle/build_ref.py)."""
+    ref = build_ref.load()
+    if ref is None:
+        pytest.skip("oracle/_ref/cphoc.so not built (no /root/reference on this box)")
+    for t in synth.make_ocr_tokens(400, seed=7):
+        clean = phoc_oracle.clean_token(t)
+        assert np.array_equal(np.asarray(ref.build_phoc(clean), np.float32), phoc_oracle.phoc_of_clean(clean)), t
+
+
+def test_phoc_processor_oracle_pads_and_truncates():
+    out = phoc_oracle.phoc_processor(["stop", "<pad>", "x"], 5)
+    assert out.shape == (5, 604) and out[3:].sum() == 0 and out[0].sum() > 0
+    assert np.array_equal(phoc_oracle.phoc_processor(["a", "b", "c"], 2), phoc_oracle.phoc_processor(["a", "b"], 2))
+
+
+def test_pack_tokens_and_no_cpu_fallback():
+    data, off = featurize.pack_tokens(["Hello", "<pad>", "", "café", "K"])
+    assert bytes(data.numpy()) == b"Hello<pad>caf\xc3\xa9k" and off.tolist() == [0, 5, 10, 10, 15, 16]
+    data, off = featurize.pack_tokens([])
+    assert data.numel() == 0 and off.tolist() == [0]
+    from vitxt_gqa_b200.pythia_api import registry
+    assert issubclass(registry.mapping["processor_name_mapping"]["phoc"], featurize.PhocProcessor)
+    if not torch.cuda.is_available():
+        with pytest.raises(tlib.T2SLibraryError):
+            featurize.phoc_rows(["abc"])
+        with pytest.raises(tlib.T2SLibraryError):       # argument errors are caught before any launch
+            tlib.get_lib().phoc_build(None, None, 3, 2, None, 604, None)
+
+
+# ------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_phoc_kernel_matches_reference_golden_bit_exact():
+    tokens, rows = _golden()
+    got = featurize.phoc_rows(tokens, rows=len(tokens) + 3)
+    assert torch.equal(got[: len(tokens)].cpu(), torch.from_numpy(rows))
+    assert got[len(tokens):].abs().sum().item() == 0
+
+
+@pytest.mark.gpu
+def test_phoc_kernel_long_and_ragged_tokens_vs_oracle():
+    import random
+    rng = random.Random(3)
+    al = "abcdefghijklmnopqrstuvwxyz0123456789 -.'AZé"
+    tokens = ["", "a" * 31, "b" * 32, "c" * 33, "th" * 100, "z9" * 1000]
+    tokens += ["".join(rng.choice(al) for _ in range(rng.randint(0, 130))) for _ in range(300)]
+    want = np.stack([phoc_oracle.build_phoc(t) for t in tokens])
+    # strided output view (ldo > 604, unaligned for float4) and the contiguous one
+    buf = torch.full((len(tokens), 607), 7.0, device="cuda")
+    got = featurize.phoc_rows(tokens, out=buf[:, 1:605])
+    assert torch.equal(got.cpu(), torch.from_numpy(want))
+    assert torch.all(buf[:, 0] == 7.0) and torch.all(buf[:, 605:] == 7.0)
+    assert torch.equal(featurize.phoc_rows(tokens).cpu(), torch.from_numpy(want))
+    assert featurize.phoc_rows([], rows=0).shape == (0, 604)
+    assert featurize.phoc_rows([], rows=4).abs().sum().item() == 0
+
+
+@pytest.mark.gpu
+def test_phoc_processor_and_batch_match_the_oracle_at_dataset_shape():
+    toks = [synth.make_ocr_tokens(960, seed=s) for s in (1, 2)]
+    toks[1] = toks[1][:700]                                   # short sample: zero rows behind it
+    feat = featurize.phoc_batch(toks, 960)
+    assert feat.shape == (2, 960, 604) and feat.dtype == torch.float32
+    for b in range(2):
+        assert torch.equal(feat[b].cpu(), torch.from_numpy(phoc_oracle.phoc_processor(toks[b], 960)))
+    proc = featurize.PhocProcessor({"max_length": 960})
+    r = proc({"tokens": toks[1]})
+    assert torch.equal(r["text"], feat[1]) and int(r["length"]) == 700 and r["tokens"][700] == "<pad>"
+    r2 = featurize.PhocProcessor({"max_length": 10})({"tokens": toks[0]})
+    assert torch.equal(r2["text"], feat[0, :10]) and int(r2["length"]) == 10

@@ -1,0 +1,122 @@
+"""Input featurisation on the device -- the step immediately before the forward path.
+
+The reference computes the 604-d PHOC descriptor of every OCR token on the CPU inside the DataLoader workers
+(`PhocProcessor`, reference pythia/datasets/processors.py:904-928, calling the C extension
+pythia/utils/phoc/src/cphoc.c through pythia/utils/phoc/build_phoc.py) and ships `context_feature_1`
+([960, 604] fp32 = 2.3 MB per sample, 57 % of all input bytes) to the GPU.  Here the token *bytes* travel
+(~8 B per token) and `t2s_phoc_build` (csrc/featurize.cu) writes the same fp32 rows in HBM, bit-identical to the
+reference binary.  `PhocProcessor` below is the same plugin (registry key "phoc", same call contract and output
+dict); `phoc_batch` builds `context_feature_1` for a whole batch in one launch.
+
+There is no CPU fallback: without the CUDA library / a GPU these calls raise.
+"""
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .pythia_api import registry
+
+PHOC_DIM = 604
+
+
+def pack_tokens(tokens):
+    """tokens (list of str) -> (uint8 bytes back to back, int32 offsets[len + 1]) as pinned-able CPU tensors.
+
+    ASCII tokens go as they are (the kernel lower-cases and filters); a token with non-ASCII characters is
+    lower-cased here with Python's own `str.lower()` (what build_phoc.py:10 applies), because Unicode case
+    mapping can produce ASCII letters (e.g. U+212A KELVIN SIGN -> 'k')."""
+    enc = [(t if t.isascii() else t.lower()).encode("utf-8") for t in tokens]
+    offsets = np.zeros(len(enc) + 1, np.int32)
+    if enc:
+        np.cumsum([len(e) for e in enc], out=offsets[1:])
+    data = np.frombuffer(b"".join(enc), np.uint8) if offsets[-1] else np.zeros(0, np.uint8)
+    return torch.from_numpy(data.copy()), torch.from_numpy(offsets)
+
+
+def phoc_rows(tokens, rows=None, device=None, out=None):
+    """PHOC rows of `tokens` -> fp32 [rows, 604] on `device` (rows >= len(tokens); extra rows are zero, the
+    processor's PAD_INDEX fill).  One H2D copy of the packed bytes + one kernel launch on the current stream."""
+    n = len(tokens)
+    rows = n if rows is None else rows
+    if rows < n:
+        raise ValueError("rows (%d) < number of tokens (%d)" % (rows, n))
+    if not torch.cuda.is_available():
+        raise _lib.T2SLibraryError("phoc_rows needs a CUDA device: the PHOC featuriser has no CPU fallback")
+    if out is None:
+        device = torch.device("cuda" if device is None else device)
+        if device.type != "cuda":
+            raise _lib.T2SLibraryError("phoc_rows runs on a CUDA device only (no CPU fallback); got %s" % device)
+        out = torch.empty(rows, PHOC_DIM, dtype=torch.float32, device=device)
+    else:
+        if not out.is_cuda:
+            raise _lib.T2SLibraryError("phoc_rows: `out` must be a CUDA tensor (no CPU fallback)")
+        assert out.dtype == torch.float32 and out.dim() == 2 and out.shape[0] == rows and out.shape[1] == PHOC_DIM
+        assert out.stride(1) == 1
+    L = _lib.get_lib()
+    data, offsets = pack_tokens(tokens)
+    with torch.cuda.device(out.device):
+        d_data = data.to(out.device, non_blocking=True) if data.numel() else None
+        d_off = offsets.to(out.device, non_blocking=True)
+        L.phoc_build(None if d_data is None else d_data.data_ptr(), d_off.data_ptr(), n, rows, out.data_ptr(),
+                     out.stride(0), torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+def phoc_batch(token_lists, max_length, device=None):
+    """`context_feature_1` of a batch: list (B) of token lists -> fp32 [B, max_length, 604], one launch.
+    Each sample is truncated / zero-padded to max_length exactly like PhocProcessor."""
+    flat, B = [], len(token_lists)
+    for toks in token_lists:
+        toks = list(toks[:max_length])
+        flat.extend(toks + [""] * (max_length - len(toks)))      # the empty word has an all-zero descriptor
+    return phoc_rows(flat, device=device).view(B, max_length, PHOC_DIM)
+
+
+class PhocProcessor:
+    """Drop-in for the reference's `@registry.register_processor("phoc")` (processors.py:904-928 on top of
+    VocabProcessor.__call__, processors.py:237-284): `proc({"tokens": [...]})` ->
+    {"text": fp32 [max_length, 604], "tokens": padded token list, "length": 0-d int64}.  "text" lives on the GPU."""
+    PAD_TOKEN = "<pad>"
+    PAD_INDEX = 0
+    MAX_LENGTH_DEFAULT = 50
+
+    def __init__(self, config, *args, **kwargs):
+        self.config = config
+        ml = getattr(config, "max_length", None) if not isinstance(config, dict) else config.get("max_length")
+        self.max_length = int(ml) if ml is not None else self.MAX_LENGTH_DEFAULT
+        self.device = kwargs.get("device", None)
+
+    def _map_strings_to_indices(self, tokens):
+        return phoc_rows(list(tokens[: self.max_length]), rows=self.max_length, device=self.device)
+
+    def _pad_tokens(self, tokens):
+        padded = [self.PAD_TOKEN] * self.max_length
+        n = min(len(tokens), self.max_length)
+        padded[:n] = tokens[:n]
+        return padded, torch.tensor(n, dtype=torch.long)
+
+    def __call__(self, item):
+        if not isinstance(item, dict):
+            raise TypeError("Argument passed to the processor must be a dict with either 'text' or 'tokens' as keys")
+        if "tokens" not in item:
+            raise AssertionError("A dict with 'tokens' must be passed to the PHOC processor")
+        tokens = item["tokens"]
+        indices = self._map_strings_to_indices(tokens)
+        tokens, length = self._pad_tokens(tokens)
+        return {"text": indices, "tokens": tokens, "length": length}
+
+
+def _register():
+    """Take over the "phoc" processor key.  The real registry asserts a BaseProcessor subclass
+    (registry.py:200-214), so when pythia's processors module is importable the class is mixed with it."""
+    cls = PhocProcessor
+    try:
+        from pythia.datasets.processors import BaseProcessor  # type: ignore
+        cls = type("PhocProcessor", (PhocProcessor, BaseProcessor), {})
+    except Exception:
+        pass
+    registry.mapping.setdefault("processor_name_mapping", {})["phoc"] = cls
+    return cls
+
+
+_register()

@@ -69,6 +69,8 @@ SIGNATURES = {
     "t2s_pos_bce_loss_bwd": [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p],
     "t2s_info_nce_loss_bwd": [_p, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p, _i, _p],
     "t2s_sumsq": [_p, _ll, _p, _p, _p],
+    # input featurisation
+    "t2s_phoc_build": [_p, _p, _i, _i, _p, _ll, _p],
     "t2s_adam_step": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p, _f, _f, _p],
 }
 PLAIN = {"t2s_abi_version": (_i, []), "t2s_last_error": (ctypes.c_char_p, []),

@@ -319,3 +319,37 @@ def make_state_dict(d: Dims, seed: int = 0, variant: str = "default"):
         sd["classifier.module.weight"] *= 0.05
         sd["classifier.module.bias"].zero_()
     return sd
+
+
+# ---------------------------------------------------------------------------------------------
+# OCR token strings (input of the PHOC featuriser)
+# ---------------------------------------------------------------------------------------------
+_OCR_EDGE_TOKENS = [
+    "<pad>", "", "a", "ab", "the", "THE", "he's", "St.", "café", "  x ", "İstanbul", "ﬁne", "K", "Straße",
+    "12345678901234567890", "antidisestablishmentarianism", "ngngng", "ththth", "-", "?!", "q9", "O'Neil",
+    "x" * 200, "th" * 64, "東京tower", "no.7", "A1", "zz9", "\t tab\n",
+]
+
+
+def make_ocr_tokens(n, seed=0, pad_ratio=0.3):
+    """n seeded synthetic OCR token strings: scene-text-like words (mixed case, digits, punctuation, a few
+    non-ASCII code points), the dataset's literal "<pad>" filler (vtextgqa/dataset.py:140) and the edge cases
+    above.  Pure python `random`, so the list is identical everywhere."""
+    import random
+    rng = random.Random(seed)
+    letters = "etaoinshrdlucmfwypvbgkqjxz"
+    out = list(_OCR_EDGE_TOKENS[:n])
+    while len(out) < n:
+        r = rng.random()
+        if r < pad_ratio:
+            out.append("<pad>")
+            continue
+        ln = min(40, max(1, int(rng.expovariate(1 / 5.0)) + 1))
+        w = "".join(rng.choice(letters if rng.random() < 0.85 else "0123456789") for _ in range(ln))
+        if rng.random() < 0.3:
+            w = w.capitalize() if rng.random() < 0.5 else w.upper()
+        if rng.random() < 0.1:
+            p = rng.randrange(len(w) + 1)
+            w = w[:p] + rng.choice(["'", "-", ".", ",", " ", "é", "ß", "&"]) + w[p:]
+        out.append(w)
+    return out
