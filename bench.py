@@ -276,23 +276,43 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    pipelined = bool(args.pipeline) and hasattr(model, "submit") and model.overlap_sms > 0
+
+    def resident_steps(n, pipe):
+        """n forward passes over the HBM-resident batch.  pipe: the serving API (model.submit -> PendingForward):
+        batch i+1 is submitted before batch i's result is collected, so the decode tail of one batch overlaps the
+        front of the next; every submitted batch is collected (joined into the timed stream) before returning."""
+        if not pipe:
+            for _ in range(n):
+                model(resident)
+            return
+        pend = None
+        for _ in range(n):
+            nxt = model.submit(resident)
+            if pend is not None:
+                pend.result()
+            pend = nxt
+        pend.result()
+
     with torch.no_grad():
         # ---- leg 1: inputs resident in HBM
-        for _ in range(args.warmup):
-            model(resident)
+        def timed_resident(pipe):
+            resident_steps(args.warmup, pipe)
+            barrier()
+            l0_ = L.launches
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            resident_steps(args.steps, pipe)
+            b.record()
+            barrier()
+            return max_over_ranks(a.elapsed_time(b)), L.launches - l0_
+
+        ms_pipe = timed_resident(True)[0] if pipelined else None     # serving API, reported next to the headline
         clocks = ClockSampler(local)
         barrier()
         if rank == 0:
             clocks.start()
-        l0 = L.launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            model(resident)
-        e1.record()
-        barrier()
-        launches = L.launches - l0
-        ms_dev = max_over_ranks(e0.elapsed_time(e1))
+        ms_dev, launches = timed_resident(False)         # the drop-in call: model(sample_list), joined every step
         clk = clocks.stop() if rank == 0 else None
 
         # ---- leg 2: end to end from pinned host memory through model(sample_list)
@@ -328,13 +348,47 @@ def run_b200(args):
                     pinned_loss[k].copy_(v, non_blocking=True)
                 torch.cuda.synchronize()      # the caller reads the result of every step
 
-        e2e_steps(min(args.warmup, 3))
-        barrier()
-        e0.record()
-        e2e_steps(args.steps)
-        e1.record()
-        barrier()
-        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        d2h_stream = torch.cuda.Stream(device=dev)
+
+        def e2e_steps_pipelined(n):
+            """Same contract through model.submit(): per step the H2D copy of its pinned inputs (copy stream), the
+            forward, the D2H read of its results (own stream) and the host wait for that read -- one step late, so the
+            next batch is already on the device's queues while the caller reads the previous one."""
+            nxt = stage_inputs()
+            read_done, keep = None, []
+            for i in range(n):
+                sl, ev = nxt
+                main_stream.wait_event(ev)
+                if i + 1 < n:
+                    nxt = stage_inputs()
+                pend = model.submit(sl)
+                keep.append(sl)                   # inputs stay referenced until their step's results were read
+                if read_done is not None:
+                    read_done.synchronize()       # the caller reads the result of step i-1
+                    keep.pop(0)
+                with torch.cuda.stream(d2h_stream):
+                    o = pend.result()
+                    for k in d2h_keys:
+                        pinned_out[k].copy_(o[k], non_blocking=True)
+                    for k, v in o["losses"].items():
+                        pinned_loss[k].copy_(v, non_blocking=True)
+                    read_done = torch.cuda.Event()
+                    read_done.record(d2h_stream)
+            read_done.synchronize()
+            main_stream.wait_stream(d2h_stream)
+
+        def timed_e2e(fn):
+            fn(min(args.warmup, 3))
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(args.steps)
+            b.record()
+            barrier()
+            return max_over_ranks(a.elapsed_time(b))
+
+        ms_e2e = timed_e2e(e2e_steps)
+        ms_e2e_pipe = timed_e2e(e2e_steps_pipelined) if pipelined else None
 
         # ---- leg 3: per-launch CUDA events on the launching stream, same steps again
         # (the decode / encoder stream overlap is switched off here: per-launch times of kernels that share
@@ -404,9 +458,15 @@ def run_b200(args):
         "config": {"workload": wl["text"], "batch_per_gpu": B, "frames": d.frames, "ocr_per_frame": d.ocr_per_frame,
                    "l2": "inputs (%.0f MB/step) and activations exceed L2" % (h2d / 1e6),
                    "algorithmic_gflop_per_sample": round(gf, 1),
-                   "decode_overlap_sms": model.overlap_sms},
+                   "decode_overlap_sms": model.overlap_sms, "api": "model(sample_list)"},
         "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        # the same K steps through the serving API model.submit(sample_list) -> PendingForward.result(): consecutive
+        # batches pipelined (decode tail of batch i overlaps the front of batch i+1), every batch collected inside the
+        # timed region; not the headline
+        "submit_api": None if not pipelined else {
+            "value": samples / (ms_pipe * 1e-3), "ms_per_step": ms_pipe / args.steps,
+            "e2e_value": samples / (ms_e2e_pipe * 1e-3), "e2e_ms_per_step": ms_e2e_pipe / args.steps},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roof,
@@ -596,6 +656,8 @@ def main():
     ap.add_argument("--frames", type=int, default=128)
     ap.add_argument("--ocr-per-frame", type=int, default=15)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pipeline", type=int, default=1,
+                    help="1: also time the serving API model.submit() (consecutive batches pipelined) -> key submit_api")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

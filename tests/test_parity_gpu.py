@@ -181,3 +181,34 @@ def test_t2s_batch_invariance_at_baseline_shape():
         assert torch.equal(a[k][2:3], c[k]), ("batch-dependent result", k)
     # decode really is greedy on pos_scores: prev_inds[t+1] == argmax(pos_scores[t])
     assert a["pos_scores"].shape == (8, d.dec_steps, d.num_outputs)
+
+
+def test_t2s_submit_pipelined_is_bit_identical_to_the_plain_call():
+    """model.submit() (serving API: consecutive batches pipelined over two workspace sets and the side stream)
+    returns exactly what model(sample_list) returns, with three batches in flight and a plain call afterwards."""
+    d = synth.Dims(frames=16, ocr_per_frame=6, vocab=300, frame_topk=4, ocr_topk=3)
+    sd = synth.make_state_dict(d, seed=3, variant="stress")
+    model = build_b200_model(d, sd)
+    batches = [sample_list(synth.make_inputs(d, 5, seed=100 + i)) for i in range(4)]
+    keys = ("pos_scores", "ref_scores", "neg_scores", "ground_frame", "ground_box")
+    with torch.no_grad():
+        want = []
+        for sl in batches:
+            o = model(sl)
+            want.append(({k: o[k].clone() for k in keys}, {k: v.clone() for k, v in o["losses"].items()}))
+        torch.cuda.synchronize()
+        for rep in range(2):
+            pend = [model.submit(sl) for sl in batches]          # all four enqueued before any is collected
+            for i, p in enumerate(pend):
+                o = p.result()
+                for k in keys:
+                    assert torch.equal(o[k], want[i][0][k]), (rep, i, k)
+                for k, v in want[i][1].items():
+                    assert torch.equal(o["losses"][k], v), (rep, i, k)
+            o = model(batches[1])                                # a plain call right behind in-flight tails
+            for k in keys:
+                assert torch.equal(o[k], want[1][0][k]), ("plain after submit", k)
+        with pytest.raises(RuntimeError):
+            model.train()
+            model.submit(batches[0])
+    model.eval()

@@ -104,6 +104,9 @@ class _Lib:
         self.cdll = ctypes.CDLL(LIB_PATH)
         self.launches = 0
         self.timing = None
+        # host-side default for the SM cap bits of the tcgen05 GEMM flags (0 = none): the pipelined eval forward
+        # (model.submit) sets it so that every throughput GEMM leaves SMs to the decode stream
+        self.gemm_cap = 0
         for name, (res, args) in PLAIN.items():
             fn = getattr(self.cdll, name)
             fn.restype, fn.argtypes = res, args
@@ -116,7 +119,11 @@ class _Lib:
             setattr(self, name[4:], self._checked(name, fn))
 
     def _checked(self, name, fn):
+        capped = name in ("t2s_gemm_bf16", "t2s_gemm_bf16x3")     # flags = argument 12 (include/t2s_b200.h)
+
         def call(*args):
+            if capped and self.gemm_cap and not (args[12] >> GEMM_SM_CAP_SHIFT) & 0xff:
+                args = args[:12] + (args[12] | ((self.gemm_cap & 0xff) << GEMM_SM_CAP_SHIFT),) + args[13:]
             rec = self.timing
             if rec is not None:
                 import torch

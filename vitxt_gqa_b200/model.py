@@ -185,6 +185,13 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def _dev_scalar(value, dev):
+    """0-d int64 device tensor like the reference's `torch.tensor(k)` result entries (t2s.py:173-174), made by a fill
+    kernel: torch.tensor(k, device=dev) is a pageable H2D copy that blocks the host until the stream drains, which
+    kept the host from enqueueing the next forward while this one was still running."""
+    return torch.full((), int(value), dtype=torch.int64, device=dev)
+
+
 def _round_up(x, m):
     return (x + m - 1) // m * m
 
@@ -215,6 +222,10 @@ class _FusionModelBase(BaseModel):
         # persistent GEMM grids capped at (SMs - overlap_sms) CTAs.  0 disables the overlap.
         self.overlap_sms = int(os.environ.get("T2S_B200_OVERLAP_SMS", str(self.config.get("b200_overlap_sms", 16))))
         self._side_streams = {}
+        # pipelined eval (submit / PendingForward.result): two workspace sets used alternately; the event that ends
+        # the decode tail of the forward that last used a set gates its reuse
+        self._pipe_slot = 0
+        self._slot_done = [None, None]
         self._phases_on = os.environ.get("T2S_B200_PHASES", "0") == "1"
         self._phase_events = []
         # greedy-decode GEMMs (one row per sample) on the weight-streaming kernel instead of the 128-row tcgen05 tile
@@ -360,8 +371,8 @@ class _FusionModelBase(BaseModel):
         return P
 
     # ---------------------------------------------------------------- workspaces
-    def _workspace(self, B, device, dims):
-        key = (B, str(device), self.grounding_precision) + tuple(sorted(dims.items()))
+    def _workspace(self, B, device, dims, slot=0):
+        key = (B, str(device), self.grounding_precision, slot) + tuple(sorted(dims.items()))
         ws = self._ws.get(key)
         if ws is not None:
             return ws
@@ -684,6 +695,22 @@ class _FusionModelBase(BaseModel):
         raise NotImplementedError
 
 
+class PendingForward:
+    """Handle of a batch submitted with `model.submit(sample_list)`."""
+
+    def __init__(self, out, done, device):
+        self._out, self._done, self._device = out, done, device
+
+    def ready(self):
+        """True once the device has finished this batch (does not block)."""
+        return self._done.query()
+
+    def result(self, stream=None):
+        """Make `stream` (default: the current stream) wait for this batch and return its report dict."""
+        (stream if stream is not None else torch.cuda.current_stream(self._device)).wait_event(self._done)
+        return self._out
+
+
 # =============================================================================== T2S
 @registry.register_model("t2s")
 class T2S(_FusionModelBase):
@@ -740,7 +767,22 @@ class T2S(_FusionModelBase):
 
         return ground_frame, ground_box, dbg, dbg_f, dbg_o
 
-    def forward(self, sample_list):
+    def submit(self, sample_list):
+        """Pipelined eval forward (serving API): enqueue this batch and return a `PendingForward` at once.
+
+        Same kernels and results as `model(sample_list)`; the difference is the tail.  The greedy decode of `pos`, the
+        decoder rows of `ref` / `neg` and the losses run on the side stream and are NOT joined into the caller's
+        stream, so the front of the next submitted batch (caller's stream, GEMM grids capped) overlaps them.
+        `PendingForward.result()` makes the current stream wait for the tail and returns the report dict of
+        `BaseModel.__call__` (scores, grounding, "losses", "metrics").  At most two batches are in flight: the third
+        submit waits (on the device) for the first one's tail before it reuses that workspace set."""
+        if self.training or torch.is_grad_enabled():
+            raise RuntimeError("submit() is the eval path: call model.eval() and use torch.no_grad()")
+        if not 0 < self.overlap_sms:
+            raise RuntimeError("submit() needs the decode side stream (b200_overlap_sms > 0)")
+        return self.forward(sample_list, _pipelined=True)
+
+    def forward(self, sample_list, _pipelined=False):
         L = _lib.get_lib()
         inp = self._gather_inputs(sample_list, self._I64 + self._F32)
         dev = self._device()
@@ -763,14 +805,35 @@ class T2S(_FusionModelBase):
             ground_frame, ground_box = eng.ground
             return {
                 "ref_scores": ref, "pos_scores": pos, "neg_scores": neg, "ground_box": ground_box,
-                "ground_frame": ground_frame, "frame_topk": torch.tensor(self.frame_topk, device=dev),
-                "ocr_topk": torch.tensor(self.ocr_topk, device=dev),
+                "ground_frame": ground_frame, "frame_topk": _dev_scalar(self.frame_topk, dev),
+                "ocr_topk": _dev_scalar(self.ocr_topk, dev),
             }
         P = self._pack(dev)
         variants = ("pos", "ref", "neg")
+        n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        slot = 0
+        if _pipelined:
+            slot, self._pipe_slot = self._pipe_slot, self._pipe_slot ^ 1
+            if self._slot_done[slot] is not None:       # the forward that used this set two submits ago
+                torch.cuda.current_stream(dev).wait_event(self._slot_done[slot])
+            L.gemm_cap = max(1, n_sms - self.overlap_sms)
+        else:
+            for i_, ev_ in enumerate(self._slot_done):     # a plain call after submits: their tails still own set 0 / 1
+                if ev_ is not None:
+                    torch.cuda.current_stream(dev).wait_event(ev_)
+                    self._slot_done[i_] = None
         ws = self._workspace(B, dev, dict(Lt=Lt, F=F, O=O, T=T, V=V, k_obj_pad=P["k_obj_pad"],
-                                          k_ocr_pad=P["k_ocr_pad"], variants=variants))
+                                          k_ocr_pad=P["k_ocr_pad"], variants=variants), slot=slot)
         st = torch.cuda.current_stream(dev).cuda_stream
+        f = P["f32"]
+        try:
+            return self._eval_or_teacher_forced(L, P, ws, inp, sample_list, dev, st, B, Lt, F, O, Of, T, V, Le, H,
+                                                variants, n_sms, slot, _pipelined)
+        finally:
+            L.gemm_cap = 0
+
+    def _eval_or_teacher_forced(self, L, P, ws, inp, sample_list, dev, st, B, Lt, F, O, Of, T, V, Le, H, variants,
+                                n_sms, slot, _pipelined):
         f = P["f32"]
 
         self._phase_events = []
@@ -825,7 +888,40 @@ class T2S(_FusionModelBase):
                     if forced is not None and t + 1 < T:
                         ws["prev"][:, t + 1].copy_(forced[:, t + 1])
 
-            n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            if _pipelined:
+                main = torch.cuda.current_stream(dev)
+                side = self._side_streams.get(dev.index)
+                if side is None:
+                    side = self._side_streams[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
+                pos_ready = torch.cuda.Event()
+                pos_ready.record(main)
+                self._mmt_encoder(L, P, ws, ("ref", "neg"), B, Le, st, qkv0=False)     # capped through L.gemm_cap
+                self._mark("enc_ref_neg")
+                enc_done = torch.cuda.Event()
+                enc_done.record(main)
+                side.wait_event(pos_ready)
+                with torch.cuda.stream(side):
+                    greedy(side.cuda_stream)
+                    self._mark("greedy_side", side)
+                    side.wait_event(enc_done)
+                    for v in ("ref", "neg"):
+                        self._decode_rows(L, P, ws, v, jm[v], scores[v], B, Le, T, V, O, F, Lt, 0, T, side.cuda_stream)
+                    self._mark("dec_ref_neg", side)
+                    out = {
+                        "ref_scores": scores["ref"], "pos_scores": scores["pos"], "neg_scores": scores["neg"],
+                        "ground_box": ground_box, "ground_frame": ground_frame,
+                        "frame_topk": _dev_scalar(self.frame_topk, dev),
+                        "ocr_topk": _dev_scalar(self.ocr_topk, dev),
+                    }
+                    for t_ in list(scores.values()) + [ground_box, ground_frame]:
+                        t_.record_stream(side)
+                    # what BaseModel.__call__ adds (base_model.py:119-149), on the stream that holds the scores
+                    out["losses"] = self.losses(sample_list, out)
+                    out["metrics"] = self.metrics(sample_list, out)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                self._slot_done[slot] = done
+                return PendingForward(out, done, dev)
             if 0 < self.overlap_sms < n_sms:
                 # the 12 greedy steps are ~300 small dependent launches that leave most SMs idle; the ref / neg
                 # encoder passes are independent of them and saturate whatever SMs they are given
@@ -859,7 +955,7 @@ class T2S(_FusionModelBase):
         return {
             "ref_scores": scores["ref"], "pos_scores": scores["pos"], "neg_scores": scores["neg"],
             "ground_box": ground_box, "ground_frame": ground_frame,
-            "frame_topk": torch.tensor(self.frame_topk, device=dev), "ocr_topk": torch.tensor(self.ocr_topk, device=dev),
+            "frame_topk": _dev_scalar(self.frame_topk, dev), "ocr_topk": _dev_scalar(self.ocr_topk, dev),
         }
 
 
@@ -929,5 +1025,5 @@ class M4C(_FusionModelBase):
                     ws["prev"][:, t + 1].copy_(forced[:, t + 1])
         return {
             "pos_scores": scores, "ground_box": ground_box, "ground_frame": inp["middel_frame_id"],
-            "frame_topk": torch.tensor(self.frame_topk, device=dev), "ocr_topk": torch.tensor(self.ocr_topk, device=dev),
+            "frame_topk": _dev_scalar(self.frame_topk, dev), "ocr_topk": _dev_scalar(self.ocr_topk, dev),
         }
