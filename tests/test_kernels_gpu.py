@@ -319,7 +319,7 @@ def test_attn_tc_x3(B, L):
     assert err <= 5e-5, err
 
 
-@pytest.mark.parametrize("t0,nq", [(0, 1), (5, 1), (11, 1), (0, 12)])
+@pytest.mark.parametrize("t0,nq", [(0, 1), (5, 1), (11, 1), (0, 12), (2, 4), (3, 7), (0, 3)])
 def test_attn_dec(t0, nq):
     lib = tlib.get_lib()
     B, Le, T, H = 3, 116, 12, 768

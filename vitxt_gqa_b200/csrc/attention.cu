@@ -18,6 +18,7 @@
 //                  keys + causal decoder keys, scores staged in shared memory, warp-shuffle
 //                  softmax (t2s.py:574-579,609-615 prefix-LM mask)
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/t2s_b200.h"
 
 namespace t2s {
@@ -735,16 +736,22 @@ extern "C" int t2s_attn_dec(const void* qkv_enc, long long ld_enc, int L_enc, co
         return T2S_ERR_SHAPE;
     }
     const int max_keys = ((L_enc + T + 3) / 4) * 4;
-    const int qc = nq == 1 ? 1 : 4;
+    // query chunk: every K / V row is read once per chunk of QC queries.  QC = 12 (all teacher-forced rows in one
+    // pass) was measured SLOWER than three passes of QC = 4 on B200 (195 vs 95 us per launch at 1056 keys: 185
+    // registers and 84 KB of score rows leave one CTA per SM), so it is only used when asked for (T2S_ATTN_DEC_QC=12)
+    static const int qc_big = []() { const char* e = getenv("T2S_ATTN_DEC_QC"); return e && atoi(e) == 12 ? 12 : 4; }();
+    const int qc = nq == 1 ? 1 : (nq <= 4 ? 4 : qc_big);
+    const int slot = qc == 1 ? 0 : (qc == 4 ? 1 : 2);
     const int smem = (AD_MAXQ * DH + qc * max_keys + AD_WARPS * qc * DH + max_keys) * 4;
     if (smem > 200 * 1024) { set_error("attn_dec: %d keys exceed the shared-memory score buffer", max_keys); return T2S_ERR_SHAPE; }
-    static int attr_bytes[2] = {48 * 1024, 48 * 1024};
-    if (smem > attr_bytes[qc == 1 ? 0 : 1]) {
+    static int attr_bytes[3] = {48 * 1024, 48 * 1024, 48 * 1024};
+    if (smem > attr_bytes[slot]) {
         cudaError_t e = qc == 1
             ? cudaFuncSetAttribute(attn_dec_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-            : cudaFuncSetAttribute(attn_dec_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            : qc == 4 ? cudaFuncSetAttribute(attn_dec_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                      : cudaFuncSetAttribute(attn_dec_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { set_error("attn_dec attr: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_bytes[qc == 1 ? 0 : 1] = smem;
+        attr_bytes[slot] = smem;
     }
     dim3 grid(heads, B);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -754,8 +761,11 @@ extern "C" int t2s_attn_dec(const void* qkv_enc, long long ld_enc, int L_enc, co
     if (qc == 1)
         attn_dec_kernel<1><<<grid, AD_THREADS, smem, st>>>(pe, ld_enc, L_enc, pd, ld_dec, T, H, key_idx, n_keys,
                                                            key_stride, t0, nq, po, ldo, 0.125f, max_keys);
-    else
+    else if (qc == 4)
         attn_dec_kernel<4><<<grid, AD_THREADS, smem, st>>>(pe, ld_enc, L_enc, pd, ld_dec, T, H, key_idx, n_keys,
                                                            key_stride, t0, nq, po, ldo, 0.125f, max_keys);
+    else
+        attn_dec_kernel<12><<<grid, AD_THREADS, smem, st>>>(pe, ld_enc, L_enc, pd, ld_dec, T, H, key_idx, n_keys,
+                                                            key_stride, t0, nq, po, ldo, 0.125f, max_keys);
     return launch_status("attn_dec");
 }

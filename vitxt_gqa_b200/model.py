@@ -410,6 +410,10 @@ class _FusionModelBase(BaseModel):
             hd=torch.empty(Md, H, **b16), ctxd=torch.empty(Md, H, **b16), interd=torch.empty(Md, 4 * H, **b16),
             qd=torch.empty(Md, H, **b16), x1d=torch.empty(Md, H, **b16),
             qkvd={v: [torch.empty(Md, 3 * H, **b16) for _ in range(n_mmt)] for v in variants},
+            # teacher-forced decoder rows of several variants in one pass (_decode_rows_multi): [variant][b][t] rows
+            md={k: torch.empty(len(variants) * Md, w * H, **b16)
+                for k, w in (("x", 1), ("x1", 1), ("x2", 1), ("h", 1), ("ctx", 1), ("inter", 4), ("q", 1), ("xa", 1))},
+            md_qkv=[torch.empty(len(variants) * Md, 3 * H, **b16) for _ in range(n_mmt)],
             prev=torch.zeros(B, T, device=device, dtype=torch.int64),
             skinny_ws=torch.zeros(max(int(_lib.get_lib().gemm_skinny_workspace_bytes(B, n_, k_))
                                       for n_, k_ in ((3 * H, H), (H, H), (4 * H, H), (H, 4 * H), (V, H))),
@@ -650,6 +654,61 @@ class _FusionModelBase(BaseModel):
         L.ptr_score(_ptr(ws["qd"]), H, B, T, t0, nq, ws["keyp"][v].data_ptr() + ocr_row0 * H * 2, Le * H, H, O, H,
                     jm.data_ptr() + ocr_row0 * 4, Le, _ptr(scores), N, V, st)
 
+    def _decode_rows_multi(self, L, P, ws, vs, jm, scores, B, Le, T, V, O, n_obj, Lt, st):
+        """All T teacher-forced decoder rows of the variants `vs` in ONE pass: the decoder rows share every weight,
+        so the dense layers, LayerNorms and both score-head projections run over len(vs)*B*T rows at once; only the
+        attention (per-variant encoder K|V and key list) and the pointer scores (per-variant OCR keys / mask) are
+        issued per variant.  `scores`: one fp32 [len(vs), B, T, V+O] buffer (the per-variant results are its slices).
+        Same arithmetic per row as `_decode_rows(..., 0, T)` -- the tcgen05 GEMM is row-independent."""
+        H, f = 768, P["f32"]
+        pp = "mmt.prev_pred_embeddings."
+        ocr_row0 = Lt + n_obj
+        nv, Md = len(vs), B * T
+        M = nv * Md
+        md, N = ws["md"], V + O
+        assert scores.shape == (nv, B, T, N) and scores.is_contiguous()
+
+        def vrow(t, i, width, esize=2):       # pointer to the first row of variant i in a [nv*Md, width] buffer
+            return t.data_ptr() + i * Md * width * esize
+
+        for i in range(nv):                   # identical input rows per variant (prev_inds are shared)
+            L.prev_embed(_ptr(ws["prev"]), T, B, 0, T, T, V, H, _ptr(f["classifier.module.weight"]),
+                         ws["J1"].data_ptr() + ocr_row0 * H * 4, Le * H, H,
+                         _ptr(f[pp + "position_embeddings.weight"]), _ptr(f[pp + "token_type_embeddings.weight"]),
+                         _ptr(f[pp + "ans_layer_norm.weight"]), _ptr(f[pp + "ans_layer_norm.bias"]),
+                         _ptr(f[pp + "ocr_layer_norm.weight"]), _ptr(f[pp + "ocr_layer_norm.bias"]),
+                         _ptr(f[pp + "emb_layer_norm.weight"]), _ptr(f[pp + "emb_layer_norm.bias"]), LN_EPS_BERT,
+                         vrow(md["x"], i, H), None, H, st)
+        x = md["x"]
+        ping = [md["x1"], md["x2"]]
+        for li, lw in enumerate(P["mmt"]):
+            qkvd = ws["md_qkv"][li]
+            L.gemm_bf16(_ptr(x), H, _ptr(lw["wqkv"]), H, _ptr(lw["bqkv"]), None, 0, _ptr(qkvd), 3 * H, M, 3 * H, H,
+                        0, 0, st)
+            for i, v in enumerate(vs):
+                qkve = ws["qkv0"] if li == 0 else ws["qkv"][v][li]
+                L.attn_dec(_ptr(qkve), 3 * H, Le, vrow(qkvd, i, 3 * H), 3 * H, T, B, H, 12, _ptr(ws["keys"][v]),
+                           _ptr(ws["nk"][v]), Le, 0, T, vrow(md["ctx"], i, H), H, st)
+            L.gemm_bf16(_ptr(md["ctx"]), H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), _ptr(x), H, _ptr(md["h"]), H, M, H, H,
+                        0, 0, st)
+            L.add_ln(_ptr(md["h"]), 1, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H,
+                     None, 0, None, 0, _ptr(md["xa"]), H, 0, 0, 0, st)
+            L.gemm_bf16(_ptr(md["xa"]), H, _ptr(lw["wi"]), H, _ptr(lw["bi"]), None, 0, _ptr(md["inter"]), 4 * H,
+                        M, 4 * H, H, _lib.GEMM_GELU, 0, st)
+            L.gemm_bf16(_ptr(md["inter"]), 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), _ptr(md["xa"]), H,
+                        _ptr(md["h"]), H, M, H, 4 * H, 0, 0, st)
+            out = ping[li & 1]
+            L.add_ln(_ptr(md["h"]), 1, H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H,
+                     None, 0, None, 0, _ptr(out), H, 0, 0, 0, st)
+            x = out
+        L.gemm_bf16(_ptr(x), H, _ptr(P["w_cls"]), H, _ptr(f["classifier.module.bias"]), None, 0, _ptr(scores), N,
+                    M, V, H, _lib.GEMM_OUT_F32, 0, st)
+        L.gemm_bf16(_ptr(x), H, _ptr(P["w_ptr_q"]), H, _ptr(f["ocr_ptr_net.query.bias"]), None, 0, _ptr(md["q"]), H,
+                    M, H, H, 0, 0, st)
+        for i, v in enumerate(vs):
+            L.ptr_score(vrow(md["q"], i, H), H, B, T, 0, T, ws["keyp"][v].data_ptr() + ocr_row0 * H * 2, Le * H, H, O, H,
+                        jm[v].data_ptr() + ocr_row0 * 4, Le, scores[i].data_ptr(), N, V, st)
+
     # ---------------------------------------------------------------- input plumbing
     _I64 = ("text", "text_len", "frame_id", "frame_mask", "temporal_id", "track_id", "ocr_mask", "train_prev_inds",
             "middel_frame_id", "middel_frame_idx")
@@ -866,13 +925,16 @@ class T2S(_FusionModelBase):
         # ---- bf16 answer transformer
         jm = {"ref": ws["jm_ref"], "pos": ws["jm_pos"], "neg": ws["jm_neg"]}
         N = V + O
-        scores = {v: torch.empty(B, T, N, device=dev, dtype=torch.float32) for v in variants}
         if self.training:
+            scores_all = torch.empty(3, B, T, N, device=dev, dtype=torch.float32)
+            scores = {v: scores_all[i] for i, v in enumerate(variants)}
             self._mmt_encoder(L, P, ws, variants, B, Le, st)
             ws["prev"].copy_(inp["train_prev_inds"])
-            for v in variants:
-                self._decode_rows(L, P, ws, v, jm[v], scores[v], B, Le, T, V, O, F, Lt, 0, T, st)
+            self._decode_rows_multi(L, P, ws, variants, jm, scores_all, B, Le, T, V, O, F, Lt, st)
         else:
+            scores_rn = torch.empty(2, B, T, N, device=dev, dtype=torch.float32)
+            scores = {"pos": torch.empty(B, T, N, device=dev, dtype=torch.float32),
+                      "ref": scores_rn[0], "neg": scores_rn[1]}
             ws["prev"].zero_()
             ws["prev"][:, 0] = int(self.answer_processor.BOS_IDX)
             forced = self.parity_hooks.get("force_prev_inds")     # test-only teacher forcing of the feedback
@@ -904,8 +966,8 @@ class T2S(_FusionModelBase):
                     greedy(side.cuda_stream)
                     self._mark("greedy_side", side)
                     side.wait_event(enc_done)
-                    for v in ("ref", "neg"):
-                        self._decode_rows(L, P, ws, v, jm[v], scores[v], B, Le, T, V, O, F, Lt, 0, T, side.cuda_stream)
+                    self._decode_rows_multi(L, P, ws, ("ref", "neg"), jm, scores_rn, B, Le, T, V, O, F, Lt,
+                                            side.cuda_stream)
                     self._mark("dec_ref_neg", side)
                     out = {
                         "ref_scores": scores["ref"], "pos_scores": scores["pos"], "neg_scores": scores["neg"],
@@ -913,7 +975,7 @@ class T2S(_FusionModelBase):
                         "frame_topk": _dev_scalar(self.frame_topk, dev),
                         "ocr_topk": _dev_scalar(self.ocr_topk, dev),
                     }
-                    for t_ in list(scores.values()) + [ground_box, ground_frame]:
+                    for t_ in (scores["pos"], scores_rn, ground_box, ground_frame):
                         t_.record_stream(side)
                     # what BaseModel.__call__ adds (base_model.py:119-149), on the stream that holds the scores
                     out["losses"] = self.losses(sample_list, out)
@@ -945,8 +1007,7 @@ class T2S(_FusionModelBase):
                 self._mark("greedy")
                 self._mmt_encoder(L, P, ws, ("ref", "neg"), B, Le, st, qkv0=False)
                 self._mark("enc_ref_neg")
-            for v in ("ref", "neg"):
-                self._decode_rows(L, P, ws, v, jm[v], scores[v], B, Le, T, V, O, F, Lt, 0, T, st)
+            self._decode_rows_multi(L, P, ws, ("ref", "neg"), jm, scores_rn, B, Le, T, V, O, F, Lt, st)
             self._mark("dec_ref_neg")
         if dbg:
             self.last_debug = dict(J0=ws["J0"].view(B, Le, H), J1=ws["J1"].view(B, Le, H), sim=ws["sim"],

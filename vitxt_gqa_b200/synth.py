@@ -353,3 +353,73 @@ def make_ocr_tokens(n, seed=0, pad_ratio=0.3):
             w = w[:p] + rng.choice(["'", "-", ".", ",", " ", "é", "ß", "&"]) + w[p:]
         out.append(w)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Grounding annotations + predictions (input of the grounding metrics)
+# ---------------------------------------------------------------------------------------------
+def make_ground_info(n, seed=0, max_spans=3):
+    """n synthetic entries shaped like the reference's ground-annotation file (a list of dicts, loaded at
+    modules/metrics.py:260 and read at metrics.py:269-272, m4c_evaluators.py:378-393): question_id, fps, width,
+    height, spatial_temporal_gt = [{temporal_gt: [t0, t1] seconds, bbox_gt: {"<frame index>": [x1, y1, x2, y2]}}].
+    Pure python `random`: identical everywhere."""
+    import random
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        fps = rng.choice([10, 10, 25, 29.97, 30])
+        width, height = rng.choice([(1280, 720), (1920, 1080), (640, 360), (720, 1280)])
+        spans = []
+        for _ in range(rng.randint(1, max_spans)):
+            t0 = round(rng.uniform(0.0, 20.0), 2)
+            t1 = round(t0 + rng.uniform(0.1, 6.0), 2)
+            st, ed = int(t0 * fps) + 1, int(t1 * fps) + 1
+            boxes = {}
+            for fr in range(max(0, st - 2), ed + 1):
+                if rng.random() < 0.7:
+                    x1, y1 = rng.uniform(0, width * 0.8), rng.uniform(0, height * 0.8)
+                    bw, bh = rng.uniform(8, width * 0.2), rng.uniform(6, height * 0.2)
+                    box = [x1, y1, min(x1 + bw, width - 1.0), min(y1 + bh, height - 1.0)]
+                    boxes[str(fr)] = [round(v, 1) for v in box] if rng.random() < 0.5 else [int(v) for v in box]
+            spans.append({"temporal_gt": [t0, t1], "bbox_gt": boxes})
+        out.append({"question_id": 1000 + i, "fps": fps, "width": width, "height": height,
+                    "spatial_temporal_gt": spans})
+    return out
+
+
+def make_ground_predictions(ground_info, frame_topk, ocr_topk, n_boxes, seed=0):
+    """Seeded model outputs for the entries of `ground_info`: ground_frame [B, frame_topk] int64 (ascending, about
+    half of them inside an annotated span), ground_box [B, n_boxes, 4] fp32 normalised boxes (sorted corners; about a
+    third of the first frame_topk*ocr_topk ones jittered copies of an annotated box, so every IoU regime occurs)."""
+    import random
+    import torch
+    rng = random.Random(seed)
+    B = len(ground_info)
+    frames = torch.zeros(B, frame_topk, dtype=torch.int64)
+    boxes = torch.zeros(B, n_boxes, 4, dtype=torch.float32)
+    for b, g in enumerate(ground_info):
+        fr = []
+        for _ in range(frame_topk):
+            sp = rng.choice(g["spatial_temporal_gt"])
+            st = int(sp["temporal_gt"][0] * g["fps"]) + 1
+            ed = int(sp["temporal_gt"][1] * g["fps"]) + 1
+            fr.append(rng.randint(st, ed) if rng.random() < 0.5 else rng.randint(1, 700))
+        fr.sort()
+        frames[b] = torch.tensor(fr)
+        for j in range(n_boxes):
+            if rng.random() < 0.1:
+                continue                                          # a padding slot: all zeros
+            x = sorted(rng.random() for _ in range(2))
+            y = sorted(rng.random() for _ in range(2))
+            box = [x[0], y[0], x[1], y[1]]
+            if j < frame_topk * ocr_topk and rng.random() < 0.35:
+                sp = rng.choice(g["spatial_temporal_gt"])
+                if sp["bbox_gt"]:
+                    gt = rng.choice(list(sp["bbox_gt"].values()))
+                    jit = lambda: rng.uniform(-0.02, 0.02)        # noqa: E731
+                    box = [gt[0] / g["width"] + jit(), gt[1] / g["height"] + jit(),
+                           gt[2] / g["width"] + jit(), gt[3] / g["height"] + jit()]
+                    box = [min(max(v, 0.0), 1.0) for v in box]
+                    box = [min(box[0], box[2]), min(box[1], box[3]), max(box[0], box[2]), max(box[1], box[3])]
+            boxes[b, j] = torch.tensor(box)
+    return frames, boxes
