@@ -52,8 +52,11 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// MODE >= 0: the epilogue flags (low 5 bits of ep.flags) and "has a residual operand" (bit 5) are compile-time
+// constants -- the hot epilogues of the fusion transformer get their own lean instantiation; MODE < 0: read at run time.
+constexpr int GEMM_MODE_RES = 32;
+template <int BN, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)     // 10 warps = 3 on two of the four 16 K-register partitions: 168 registers at most
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, GemmEpi ep, int M, int N, int K, int k_lo_off) {
     using Cfg = GemmCfg<BN>;
@@ -161,11 +164,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         constexpr int COLS_PER_WARP = BN / (ACTIVE / 4);
         const bool active = ew < ACTIVE;
         const int half = ew >> 2;
-        const bool gelu = ep.flags & T2S_GEMM_GELU;
-        const bool out_f32 = ep.flags & T2S_GEMM_OUT_F32;
-        const bool res_f32 = ep.flags & T2S_GEMM_RES_F32;
-        const bool out_split = ep.flags & T2S_GEMM_OUT_SPLIT;
-        const bool dgelu = ep.flags & T2S_GEMM_DGELU;
+        const int fl = MODE >= 0 ? (MODE & 31) : ep.flags;
+        const bool has_res = MODE >= 0 ? (MODE & GEMM_MODE_RES) != 0 : ep.residual != nullptr;
+        const bool gelu = fl & T2S_GEMM_GELU;
+        const bool out_f32 = fl & T2S_GEMM_OUT_F32;
+        const bool res_f32 = fl & T2S_GEMM_RES_F32;
+        const bool out_split = fl & T2S_GEMM_OUT_SPLIT;
+        const bool dgelu = fl & T2S_GEMM_DGELU;
         uint8_t* box = staging + ew * 4096;      // this warp's staging box: 32 rows x 128 B, 128B swizzle
         uint8_t* my_row = box + lane * 128;
         const int sw = lane & 7;
@@ -180,14 +185,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const bool row_ok = row < M;
             if (active) {
                 uint32_t lo_keep[16];            // OUT_SPLIT: lo half of the first chunk of a box
-#pragma unroll 1
-                for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
-                    uint32_t r[32];
-                    const int cw = half * COLS_PER_WARP + c0;
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cw, r);
-                    tmem_ld_wait();
-                    const int col0 = n_blk * BN + cw;
-                    if (col0 >= N) break;        // warp-uniform: the whole 32-column chunk is outside the matrix
+                // Software pipeline over the 32-column chunks: the tcgen05.ld of chunk i+1 (and the load of its
+                // bf16 residual / GELU' operand) is in flight while chunk i goes through bias / GELU / pack / store,
+                // and the accumulator is handed back to the MMA warp as soon as its last chunk sits in registers.
+                constexpr int NCH = COLS_PER_WARP / 32;
+                const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * COLS_PER_WARP;
+                const int col_w = n_blk * BN + half * COLS_PER_WARP;
+                const bool pre_res = has_res && !res_f32 && row_ok;
+                const __nv_bfloat16* res16 =
+                    reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + col_w;
+                uint32_t rbuf[2][32];
+                uint4 qbuf[2][4];
+                tmem_ld_32x32(t_acc, rbuf[0]);
+                if (pre_res && col_w + 32 <= N) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) qbuf[0][j] = *reinterpret_cast<const uint4*>(res16 + 8 * j);
+                }
+#pragma unroll
+                for (int ci = 0; ci < NCH; ++ci) {
+                    const int c0 = ci * 32;
+                    uint32_t (&r)[32] = rbuf[ci & 1];
+                    const uint4 (&q)[4] = qbuf[ci & 1];
+                    tmem_ld_wait_on(r);
+                    if (ci + 1 == NCH) {             // the accumulator is in registers: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
+                    }
+                    const int col0 = col_w + c0;
+                    if (col0 >= N) continue;     // warp-uniform: the whole 32-column chunk is outside the matrix
                     const bool full32 = col0 + 32 <= N;
                     float v[32];
 #pragma unroll
@@ -208,7 +234,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
-                    if (ep.residual && row_ok) {
+                    if (has_res && row_ok) {
                         // residual add, or (T2S_GEMM_DGELU) multiply by GELU'(aux) of the saved pre-activation
                         auto comb = [dgelu](float acc_v, float aux) { return dgelu ? acc_v * gelu_grad(aux) : acc_v + aux; };
                         if (res_f32) {
@@ -229,7 +255,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             if (full32) {
 #pragma unroll
                                 for (int j = 0; j < 32; j += 8) {
-                                    const uint4 a = *reinterpret_cast<const uint4*>(rp + j);
+                                    const uint4 a = q[j >> 3];       // prefetched one chunk ahead
                                     v[j] = comb(v[j], bf16lo(a.x)); v[j + 1] = comb(v[j + 1], bf16hi(a.x));
                                     v[j + 2] = comb(v[j + 2], bf16lo(a.y)); v[j + 3] = comb(v[j + 3], bf16hi(a.y));
                                     v[j + 4] = comb(v[j + 4], bf16lo(a.z)); v[j + 5] = comb(v[j + 5], bf16hi(a.z));
@@ -239,6 +265,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] = comb(v[j], __bfloat162float(rp[j]));
                             }
+                        }
+                    }
+                    if (ci + 1 < NCH) {
+                        // chunk i + 1: TMEM load and bf16 residual load fly while this chunk is packed and stored
+                        tmem_ld_32x32(t_acc + c0 + 32, rbuf[(ci + 1) & 1]);
+                        if (pre_res && col0 + 64 <= N) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                qbuf[(ci + 1) & 1][j] = *reinterpret_cast<const uint4*>(res16 + c0 + 32 + 8 * j);
                         }
                     }
                     if (out_f32) {
@@ -309,9 +344,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (!active) {                           // BN == 64: warps 4..7 hold no columns
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -382,14 +419,14 @@ int num_sms() {
     return n;
 }
 
-template <int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmEpi& ep, int M,
-                       int N, int K, int k_lo_off, int sm_cap, cudaStream_t st) {
+template <int BN, int MODE>
+static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmEpi& ep,
+                            int M, int N, int K, int k_lo_off, int sm_cap, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, MODE>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
             return (int)e;
@@ -400,8 +437,35 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     // T2S_GEMM_SM_CAP: the persistent grid leaves SMs free for latency-bound work on another stream
     const int sms = (sm_cap > 0 && sm_cap < num_sms()) ? sm_cap : num_sms();
     const int grid = tiles < sms ? tiles : sms;
-    gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, ep, M, N, K, k_lo_off);
+    gemm_bf16_tcgen05_kernel<BN, MODE><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, ep, M, N, K, k_lo_off);
     return launch_status("gemm_bf16_tcgen05");
+}
+
+// The epilogues of the eval forward (qkv / ptr-net plain, +residual, GELU, fp32 out, fp32 out + fp32 residual,
+// GELU + hi|lo out, hi|lo out) and the GELU' dgrad of the training step are compiled with constant flags for the
+// throughput tiles; everything else (BN = 64 decode tiles, rare combinations) takes the run-time-flag instantiation.
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmEpi& ep, int M,
+                       int N, int K, int k_lo_off, int sm_cap, cudaStream_t st) {
+    if (BN >= 128) {
+        const int mode = (ep.flags & 31) | (ep.residual ? GEMM_MODE_RES : 0);
+#define T2S_GEMM_MODE_CASE(m) \
+        case (m): return launch_gemm_mode<(BN >= 128 ? BN : 128), (m)>(ta, tb, tc, ep, M, N, K, k_lo_off, sm_cap, st);
+        switch (mode) {
+            T2S_GEMM_MODE_CASE(0)
+            T2S_GEMM_MODE_CASE(GEMM_MODE_RES)
+            T2S_GEMM_MODE_CASE(T2S_GEMM_GELU)
+            T2S_GEMM_MODE_CASE(T2S_GEMM_OUT_F32)
+            T2S_GEMM_MODE_CASE(T2S_GEMM_OUT_F32 | T2S_GEMM_RES_F32 | GEMM_MODE_RES)
+            T2S_GEMM_MODE_CASE(T2S_GEMM_GELU | T2S_GEMM_OUT_SPLIT)
+            T2S_GEMM_MODE_CASE(T2S_GEMM_OUT_SPLIT)
+            T2S_GEMM_MODE_CASE(T2S_GEMM_DGELU | GEMM_MODE_RES)
+            T2S_GEMM_MODE_CASE(T2S_GEMM_DGELU | T2S_GEMM_RES_F32 | GEMM_MODE_RES)
+            default: break;
+        }
+#undef T2S_GEMM_MODE_CASE
+    }
+    return launch_gemm_mode<BN, -1>(ta, tb, tc, ep, M, N, K, k_lo_off, sm_cap, st);
 }
 
 
