@@ -258,6 +258,29 @@ int t2s_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
 int t2s_phoc_build(const unsigned char* bytes, const int* offsets, int n_tokens, int rows, float* out, long long ldo,
                    void* stream);
 
+/* K9  Evaluation step that consumes the forward's outputs.
+ * t2s_answer_decode: `pos_scores.argmax(-1)` and the EOS cut of the python loop in modules/metrics.py:186-207 (= 395-416,
+ * 498-519).  ans_ids [B, T] int32 = argmax of every decoding row (lowest index on ties); ans_len [B] = number of ids
+ * before the first VOCABULARY id equal to eos_idx (ids >= V are OCR copies and never end the answer), T if none. */
+int t2s_answer_decode(const float* scores, long long ld_scores, int B, int T, int N, int V, int eos_idx,
+                      int* ans_ids, int* ans_len, void* stream);
+/* t2s_ground_metrics: BoxGroundAccuracyEvaluator.eval_pred_list at two IoU thresholds and
+ * TempGroundAccuracyEvaluator.eval_pred_list (utils/m4c_evaluators.py:301-405; callers modules/metrics.py:233-546) on
+ * ground_frame [B, kf] int64 / ground_box [B, n_box, 4] fp32 as the forward returns them.  The ground-truth
+ * annotation file is packed once on the host (vitxt_gqa_b200/metrics.py GroundAnnotations): record r owns spans
+ * span_ptr[r] .. span_ptr[r+1]; span s = frames [span_st[s], span_ed[s]] (= int(t*fps)+1, computed in python) and the
+ * labelled boxes box_ptr[s] .. box_ptr[s+1] (box_frame = int of the dict key, box_xyxy binary64); rec_wh [R, 2] =
+ * (width, height); rec_index [B] = record of each sample's question (-1: none).  Outputs: ones / tail_zero [2, B] = per
+ * sample and threshold the number of 1s and (0 | 1) trailing 0 the evaluator appends to its score list; t_hit [B];
+ * status [B] bit 0 / 1 = the evaluator's box-order assertions on the labelled / predicted box would fail, bit 2 = no
+ * annotation; acc [3] = IOU@thr_a, IOU@thr_b, temporal accuracy (sum / len in binary64, then float32);
+ * head [2, B] = the first B entries of each concatenated score list (what GQA@x indexes by sample). */
+int t2s_ground_metrics(const long long* ground_frame, int kf, const float* ground_box, int n_box, int ocr_topk,
+                       const int* rec_index, const int* span_ptr, const long long* span_st, const long long* span_ed,
+                       const int* box_ptr, const long long* box_frame, const double* box_xyxy, const double* rec_wh,
+                       int B, double thr_a, double thr_b, int* ones, int* tail_zero, int* t_hit, int* status,
+                       float* acc, int* head, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

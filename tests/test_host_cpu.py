@@ -57,6 +57,8 @@ def test_ctypes_signatures_match_the_header():
                 want = tlib._ll
             elif p_.startswith("float"):
                 want = tlib._f
+            elif p_.startswith("double"):
+                want = tlib._d
             else:
                 want = tlib._i
             assert a is want, (name, p_)

@@ -12,7 +12,8 @@ import torch  # noqa: E402
 from vitxt_gqa_b200 import model as tmodel, synth  # noqa: E402
 from vitxt_gqa_b200.pythia_api import SampleList, load_yaml_config, register_defaults  # noqa: E402
 
-cfg = load_yaml_config("t2s_abinet.yml", {"model_attributes.t2s.text_bert_init_from_bert_base": False})
+cfg = load_yaml_config("t2s_abinet.yml", {"model_attributes.t2s.text_bert_init_from_bert_base": False,
+                             "model_attributes.t2s.metrics": []})
 mcfg = cfg.model_attributes.t2s
 d = synth.dims_from_config(mcfg, vocab=5000)
 register_defaults(vocab_size=d.vocab, ocr_max_num=d.ocr)

@@ -18,6 +18,7 @@ GEMM_DGELU = 16
 GEMM_SM_CAP_SHIFT = 8     # bits 8..15 of the GEMM flags: cap on the persistent grid
 
 _p, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+_d = ctypes.c_double
 
 # name -> argtypes, in the order of include/t2s_b200.h
 SIGNATURES = {
@@ -71,6 +72,9 @@ SIGNATURES = {
     "t2s_sumsq": [_p, _ll, _p, _p, _p],
     # input featurisation
     "t2s_phoc_build": [_p, _p, _i, _i, _p, _ll, _p],
+    # evaluation step
+    "t2s_answer_decode": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _p],
+    "t2s_ground_metrics": [_p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p],
     "t2s_adam_step": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p, _f, _f, _p],
 }
 PLAIN = {"t2s_abi_version": (_i, []), "t2s_last_error": (ctypes.c_char_p, []),

@@ -60,6 +60,17 @@ class _Registry:
         return wrap
 
     @classmethod
+    def register_metric(cls, name):
+        def wrap(metric_cls):
+            cls.mapping["metric_name_mapping"][name] = metric_cls
+            return metric_cls
+        return wrap
+
+    @classmethod
+    def get_metric_class(cls, name):
+        return cls.mapping["metric_name_mapping"].get(name, None)
+
+    @classmethod
     def register(cls, name, obj):
         path = name.split(".")
         cur = cls.mapping["state"]
@@ -266,9 +277,9 @@ class _Losses(nn.Module):
 
 
 class _BaseModel(nn.Module):
-    """Stand-in for reference `BaseModel` (base_model.py:52-149).  Metrics are
-    host-side python in the reference (out of scope): the
-    stand-in returns an empty metrics dict."""
+    """Stand-in for reference `BaseModel` (base_model.py:52-149): forward, then
+    `Losses`, then `Metrics` (vitxt_gqa_b200/metrics.py, the evaluation step on
+    the device) built from `config.losses` / `config.metrics`."""
 
     def __init__(self, config):
         super().__init__()
@@ -283,7 +294,8 @@ class _BaseModel(nn.Module):
         if len(losses) == 0:
             warnings.warn("No losses are defined in model configuration.")
         self.losses = _Losses(losses)
-        self.metrics = lambda sample_list, model_output: {}
+        from .metrics import Metrics      # late: metrics.py imports this module's registry
+        self.metrics = Metrics(list(self.config.get("metrics", []) or []))
 
     def __call__(self, sample_list, *args, **kwargs):
         model_output = super().__call__(sample_list, *args, **kwargs)

@@ -388,9 +388,12 @@ def make_ground_info(n, seed=0, max_spans=3):
 
 
 def make_ground_predictions(ground_info, frame_topk, ocr_topk, n_boxes, seed=0):
-    """Seeded model outputs for the entries of `ground_info`: ground_frame [B, frame_topk] int64 (ascending, about
-    half of them inside an annotated span), ground_box [B, n_boxes, 4] fp32 normalised boxes (sorted corners; about a
-    third of the first frame_topk*ocr_topk ones jittered copies of an annotated box, so every IoU regime occurs)."""
+    """Seeded model outputs for the entries of `ground_info`: ground_frame [B, frame_topk] int64 and ground_box
+    [B, n_boxes, 4] fp32 normalised boxes (sorted corners, a few all-zero padding slots).  About 60 % of the grounded
+    frames are frames whose predecessor carries a labelled box inside an annotated span (what the evaluator looks up,
+    m4c_evaluators.py:389-391); the boxes the evaluator pairs with such a frame (slice i*ocr_topk .. of the list, E3
+    in csrc/metrics.cu) are then tight, loose or unrelated copies of that label, so IoU lands on both sides of 0.3 and
+    0.5, samples score several hits, and the last check of a sample fails after earlier ones passed."""
     import random
     import torch
     rng = random.Random(seed)
@@ -398,28 +401,176 @@ def make_ground_predictions(ground_info, frame_topk, ocr_topk, n_boxes, seed=0):
     frames = torch.zeros(B, frame_topk, dtype=torch.int64)
     boxes = torch.zeros(B, n_boxes, 4, dtype=torch.float32)
     for b, g in enumerate(ground_info):
-        fr = []
-        for _ in range(frame_topk):
-            sp = rng.choice(g["spatial_temporal_gt"])
-            st = int(sp["temporal_gt"][0] * g["fps"]) + 1
-            ed = int(sp["temporal_gt"][1] * g["fps"]) + 1
-            fr.append(rng.randint(st, ed) if rng.random() < 0.5 else rng.randint(1, 700))
-        fr.sort()
-        frames[b] = torch.tensor(fr)
+        W, H = float(g["width"]), float(g["height"])
         for j in range(n_boxes):
             if rng.random() < 0.1:
                 continue                                          # a padding slot: all zeros
             x = sorted(rng.random() for _ in range(2))
             y = sorted(rng.random() for _ in range(2))
-            box = [x[0], y[0], x[1], y[1]]
-            if j < frame_topk * ocr_topk and rng.random() < 0.35:
-                sp = rng.choice(g["spatial_temporal_gt"])
-                if sp["bbox_gt"]:
-                    gt = rng.choice(list(sp["bbox_gt"].values()))
-                    jit = lambda: rng.uniform(-0.02, 0.02)        # noqa: E731
-                    box = [gt[0] / g["width"] + jit(), gt[1] / g["height"] + jit(),
-                           gt[2] / g["width"] + jit(), gt[3] / g["height"] + jit()]
+            boxes[b, j] = torch.tensor([x[0], y[0], x[1], y[1]])
+        for i in range(frame_topk):
+            sp = rng.choice(g["spatial_temporal_gt"])
+            st = int(sp["temporal_gt"][0] * g["fps"]) + 1
+            ed = int(sp["temporal_gt"][1] * g["fps"]) + 1
+            labelled = [int(k) + 1 for k in sp["bbox_gt"] if st <= int(k) + 1 <= ed]
+            r = rng.random()
+            if r < 0.6 and labelled:
+                fr = rng.choice(labelled)
+                gt = sp["bbox_gt"][str(fr - 1)]
+                for j in range(i * ocr_topk, min(n_boxes, (i + 1) * ocr_topk)):
+                    mode = rng.random()
+                    if mode < 0.35:
+                        amp = 0.004                               # tight: IoU well above 0.5
+                    elif mode < 0.7:
+                        amp = 0.03                                # loose: IoU around 0.3 .. 0.6
+                    else:
+                        continue                                  # keep the unrelated box
+                    jit = lambda: rng.uniform(-amp, amp)          # noqa: E731
+                    box = [gt[0] / W + jit(), gt[1] / H + jit(), gt[2] / W + jit(), gt[3] / H + jit()]
                     box = [min(max(v, 0.0), 1.0) for v in box]
                     box = [min(box[0], box[2]), min(box[1], box[3]), max(box[0], box[2]), max(box[1], box[3])]
-            boxes[b, j] = torch.tensor(box)
+                    boxes[b, j] = torch.tensor(box)
+            elif r < 0.8:
+                fr = rng.randint(st, ed)                          # inside the span, label or not
+            else:
+                fr = rng.randint(1, 700)
+            frames[b, i] = fr
     return frames, boxes
+
+
+# ---------------------------------------------------------------------------------------------
+# Answer side of the metrics: scores whose argmax spells an answer, OCR token lists, 10 human answers
+# ---------------------------------------------------------------------------------------------
+_ANSWER_WORDS = (
+    "stop exit 7 seven the a an open closed coca cola coca-cola dont don't youre can't cant let's she's its "
+    "o'clock oclock none zero ten 10 1,000 1,000,000 3.5 u.s.a. a.m. hello! yes? [sale] {50%} (off) a/b c\\d e_f "
+    "g-h >> << @home `q` semi;colon plus+minus equal=s \"quoted\" mc'donalds somebody'd yall'd've wouldn'tve "
+    "Id've main st. blvd 42nd new york taxi").split()
+
+
+def make_answer_vocab(V, seed=0):
+    """V answer-vocabulary words: the four specials of the answer processor (`<pad>` 0, `<s>` 1, `</s>` 2, `<unk>` 3;
+    reference datasets/processors.py:994-1005) followed by seeded picks that exercise every branch of the EvalAI
+    normaliser (articles, number words, contractions, each punctuation mark, commas inside numbers, periods)."""
+    import random
+    rng = random.Random(seed)
+    words = ["<pad>", "<s>", "</s>", "<unk>"] + list(_ANSWER_WORDS)
+    while len(words) < V:
+        words.append(rng.choice(_ANSWER_WORDS) if rng.random() < 0.2 else "w%d" % len(words))
+    return words[:V]
+
+
+def make_answer_batch(B, T, V, O, seed=0):
+    """Seeded inputs of the answer metrics: pos_scores [B, T, V + O] fp32 whose row-wise argmax spells a planted id
+    sequence (vocabulary ids, OCR copies, EOS anywhere from step 0 to never, exact ties so that the lowest-index rule
+    is visible), `ocr_tokens` (B lists of O strings), `gt_answers` (B lists of 10 strings: a seeded number of them
+    agree with the planted answer so that every soft-accuracy level occurs) and the planted ids.  Pure python
+    `random` + torch fills: identical everywhere."""
+    import random
+    import torch
+    rng = random.Random(seed)
+    vocab = make_answer_vocab(V, seed)
+    N = V + O
+    g = torch.Generator().manual_seed(seed)
+    scores = torch.randn(B, T, N, generator=g)
+    planted, ocr_tokens, gt_answers = [], [], []
+    for b in range(B):
+        toks = make_ocr_tokens(O, seed=seed * 131 + b, pad_ratio=0.2)
+        ocr_tokens.append(toks)
+        n_words = rng.choice([0, 1, 1, 2, 2, 3, 5, T])
+        ids = []
+        for t in range(T):
+            if t == n_words:
+                ids.append(2)                                        # EOS
+            elif rng.random() < 0.4:
+                ids.append(V + rng.randrange(O))                     # copy an OCR token
+            else:
+                ids.append(rng.randrange(4, V) if t < n_words else rng.randrange(0, N))
+        planted.append(ids)
+        for t, i in enumerate(ids):
+            scores[b, t, i] = 9.0 + rng.random()
+            if rng.random() < 0.3:                                   # an exact tie at a HIGHER index must lose
+                j = rng.randrange(N)
+                if j > i:
+                    scores[b, t, j] = scores[b, t, i]
+        words = []
+        for i in ids:
+            if i >= V:
+                words.append(toks[i - V])
+            elif i == 2:
+                break
+            else:
+                words.append(vocab[i])
+        answer = " ".join(words)
+        agree = rng.choice([0, 1, 2, 3, 4, 10]) if answer.strip() else 0     # ANLS of '' against '' divides by zero
+        pool = [" ".join(rng.choice(_ANSWER_WORDS) for _ in range(rng.randint(1, 3))) for _ in range(3)]
+        gts = [answer if k < agree else rng.choice(pool) for k in range(10)]
+        rng.shuffle(gts)
+        gt_answers.append(gts)
+    return {"pos_scores": scores, "ocr_tokens": ocr_tokens, "gt_answers": gt_answers, "vocab": vocab,
+            "planted_ids": torch.tensor(planted, dtype=torch.int64)}
+
+
+def encode_object(obj, max_size=16384):
+    """The dataset's byte-tensor encoding of a python object (reference pythia/utils/objects_to_byte_tensor.py:11-31:
+    two size bytes, then the pickle, zero padded to max_size)."""
+    import pickle
+    import torch
+    raw = pickle.dumps(obj)
+    if len(raw) > max_size - 2:
+        raise ValueError("object too large for the byte tensor: %d bytes" % len(raw))
+    out = torch.zeros(max_size, dtype=torch.uint8)
+    out[0], out[1] = len(raw) // 256, len(raw) % 256
+    out[2:2 + len(raw)] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    return out
+
+
+class SynthAnswerProcessor:
+    """The members of the reference answer processor the metrics read (datasets/processors.py:994-1063):
+    `EOS_IDX`, `BOS_IDX`, `PAD_IDX`, `get_true_vocab_size()`, `answer_vocab.idx2word(i)`."""
+    PAD_IDX, BOS_IDX, EOS_IDX = 0, 1, 2
+
+    def __init__(self, words):
+        self.words = list(words)
+        self.answer_vocab = self
+
+    def idx2word(self, i):
+        return self.words[i]
+
+    def get_true_vocab_size(self):
+        return len(self.words)
+
+
+def make_metrics_case(B=6, T=12, V=120, O=24, frame_topk=3, ocr_topk=2, n_boxes=None, seed=0):
+    """One seeded evaluation batch: annotation records (B + 3 of them, so lookups skip entries), the batch's
+    question ids, the grounding outputs and the answer-side tensors / strings."""
+    import random
+    info = make_ground_info(B + 3, seed=seed)
+    order = list(range(len(info)))
+    random.Random(seed + 7).shuffle(order)
+    chosen = [info[i] for i in order[:B]]
+    n_boxes = frame_topk * ocr_topk + 4 if n_boxes is None else n_boxes
+    gf, gb = make_ground_predictions(chosen, frame_topk, ocr_topk, n_boxes, seed=seed)
+    case = make_answer_batch(B, T, V, O, seed=seed)
+    case.update(records=info, question_id=[c["question_id"] for c in chosen], ground_frame=gf, ground_box=gb,
+                frame_topk=frame_topk, ocr_topk=ocr_topk, V=V, O=O)
+    return case
+
+
+def metrics_sample_list(case, sample_list_cls, dataset_type="val", dataset_name="vtextgqa"):
+    """(sample_list, model_output) of a `make_metrics_case` batch, with the fields the reference metrics read
+    (modules/metrics.py:181-214, 256-275): context_tokens_enc, gt_answers_enc, frame_num, question_id, targets."""
+    import torch
+    B = len(case["question_id"])
+    sl = sample_list_cls()
+    sl.add_field("context_tokens_enc", torch.stack([encode_object(t) for t in case["ocr_tokens"]]))
+    sl.add_field("gt_answers_enc", torch.stack([encode_object(a) for a in case["gt_answers"]]))
+    sl.add_field("frame_num", torch.full((B,), 64, dtype=torch.int64))
+    sl.add_field("question_id", torch.tensor(case["question_id"], dtype=torch.int64))
+    sl.add_field("targets", torch.zeros(B, 1))
+    sl.add_field("dataset_type", dataset_type)
+    sl.add_field("dataset_name", dataset_name)
+    out = {"pos_scores": case["pos_scores"].clone(), "ground_frame": case["ground_frame"].clone(),
+           "ground_box": case["ground_box"].clone(), "frame_topk": torch.tensor(case["frame_topk"]),
+           "ocr_topk": torch.tensor(case["ocr_topk"])}
+    return sl, out
