@@ -163,6 +163,17 @@ int t2s_spatial_select(const float* sim, int sim_stride, int sim_off, const floa
                        float* pos_joint, float* neg_joint, float* dbg_score, void* stream);
 int t2s_middle_frame_slots(const long long* mid_id, const long long* temporal_id, int B, int O,
                            float* slot_mask, void* stream);
+/* Ablation variants (models/t2s_wo_sg.py:496-506, models/t2s_wo_tg.py:483-535).  t2s_spatial_select modes: 0 = T2S,
+ * 1 = M4C post-hoc, 2 = "w/o SG" (pos = slot mask, neg = 1 - slot mask, ground_box [B, topk * Of, 4] = boxes of the
+ * positive slots, `topk` = number of grounded frames, buffer zeroed by the caller), 3 = "w/o TG" (mode 0, both masks
+ * also multiplied by the OCR part of joint_mask).  t2s_frame_slots: slot_mask [B, O] = 1 where temporal_id equals one
+ * of the n_ids ids of the sample (id 0 read as 1).  t2s_frames_from_ocr: frame part of pos / neg joint masks = the
+ * first n_pick frames that own a positive / negative OCR slot (fewer: the last frame is set, the reference's index
+ * -1), ground_frame [B, n_pick] = positive frame positions, -1 padded; copies the question part from joint_mask. */
+int t2s_frame_slots(const long long* ids, int n_ids, const long long* temporal_id, int B, int O, float* slot_mask,
+                    void* stream);
+int t2s_frames_from_ocr(const float* joint_mask, float* pos_joint, float* neg_joint, int B, int Lt, int F, int Of,
+                        int n_pick, long long* ground_frame, void* stream);
 
 /* K6  pointer scores written into scores[:, :, V:], argmax feedback (models/t2s.py:661-666,285,353-354) */
 int t2s_ptr_score(const void* q, long long ldq, int B, int T, int t0, int nq, const void* keyp,

@@ -220,22 +220,53 @@ def spatial_indicator(q, ocr, boxes, attn_mask, o_topk, frame_num, o_frame_num, 
 
 
 def grounding_t2s(sd, d, inp, txt, txt_mask, frames, ocr, neg_frame_override=None):
-    """Grounding_Module.forward (models/t2s.py:461-518)."""
+    """Grounding_Module.forward (models/t2s.py:461-518); d.ablation selects the two ablation models, which differ
+    from it only here: "wo_sg" (models/t2s_wo_sg.py:496-506) and "wo_tg" (models/t2s_wo_tg.py:477-537)."""
     B = ocr.size(0)
     frame_mask = inp["frame_mask"]
+    ablation = getattr(d, "ablation", "")
     gq = question_pool(sd, "Grounding_Module", txt, txt_mask)
-    ground_frame, gf_mask, nf_mask, dbg = temporal_indicator(
-        gq, frames, frame_mask, inp["frame_id"], d.frame_topk, inp["gumbel_frame"], neg_frame_override)
-    gf_mask = gf_mask * frame_mask
-    nf_mask = nf_mask * frame_mask
+    dbg = {}
+    if ablation == "wo_tg":
+        ground_frame = inp["frame_id"]                                           # t2s_wo_tg.py:483
+    else:
+        ground_frame, gf_mask, nf_mask, dbg = temporal_indicator(
+            gq, frames, frame_mask, inp["frame_id"], d.frame_topk, inp["gumbel_frame"], neg_frame_override)
+        gf_mask = gf_mask * frame_mask
+        nf_mask = nf_mask * frame_mask
     t1 = torch.where(ground_frame == 0, torch.tensor(1), ground_frame)           # Q9
     eq = torch.eq(inp["temporal_id"].unsqueeze(1), t1.unsqueeze(-1))
     new_idx = torch.nonzero(eq, as_tuple=True)[2].view(B, -1)
     new_ocr_mask = torch.zeros((B, ocr.size(1))).scatter_(1, new_idx, 1)
-    gbox, go_mask, no_mask, dbg2 = spatial_indicator(
-        gq, ocr, inp["ocr_bbox_coordinates"], new_ocr_mask, d.ocr_topk, d.frames, d.ocr_per_frame,
-        inp["gumbel_ocr"])
-    dbg.update(dbg2)
+    boxes = inp["ocr_bbox_coordinates"]
+    if ablation == "wo_sg":
+        go_mask = new_ocr_mask                                                   # t2s_wo_sg.py:503
+        no_mask = torch.ones_like(go_mask) - go_mask
+        gbox = torch.masked_select(boxes, new_ocr_mask.unsqueeze(-1).expand(B, -1, 4).bool()).view(B, -1, 4)
+    else:
+        o_topk = d.frame_topk * d.ocr_topk if ablation == "wo_tg" else d.ocr_topk     # t2s_wo_tg.py:504
+        gbox, go_mask, no_mask, dbg2 = spatial_indicator(
+            gq, ocr, boxes, new_ocr_mask, o_topk, d.frames, d.ocr_per_frame, inp["gumbel_ocr"])
+        dbg.update(dbg2)
+    if ablation == "wo_tg":
+        ocr_mask = inp["ocr_mask"]
+        go_mask = go_mask * ocr_mask                                             # t2s_wo_tg.py:506-507
+        no_mask = no_mask * ocr_mask
+
+        def frames_of(mask):                                                     # t2s_wo_tg.py:511-535 (the 5 is literal)
+            any_f = mask.view(B, d.frames, -1).any(dim=2)
+            rows = []
+            for i in range(B):
+                idx = torch.where(any_f[i])[0]
+                if len(idx) < 5:
+                    idx = torch.cat([idx, torch.full((5 - len(idx),), -1, dtype=torch.long)])
+                rows.append(idx[:5])
+            idx = torch.stack(rows)
+            fm = torch.zeros((B, d.frames), dtype=torch.long)
+            fm[torch.arange(B).unsqueeze(1), idx] = 1
+            return idx, fm
+        ground_frame, gf_mask = frames_of(go_mask)
+        _, nf_mask = frames_of(no_mask)
     dbg.update(global_q=gq, new_ocr_mask=new_ocr_mask)
     return dict(ground_frame=ground_frame, ground_bbox=gbox, pos_obj_mask=gf_mask, pos_ocr_mask=go_mask,
                 neg_obj_mask=nf_mask, neg_ocr_mask=no_mask, debug=dbg)

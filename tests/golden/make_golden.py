@@ -37,6 +37,12 @@ FIXTURES = {
     # BASELINE config 1: t2s_abinet shapes, batch 1 (+1), eval
     "t2s_abinet_eval": (dict(), 2, 1235, 0, "stress", "eval"),
     "t2s_clipocr_train": (dict(frame_topk=1, ocr_topk=1), 2, 1237, 0, "stress", "train"),
+    # ablation models: same weights and inputs, different Grounding_Module wiring
+    "t2s_wo_sg_small_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2, ablation="wo_sg"), 3, 15, 0, "stress", "eval"),
+    "t2s_wo_sg_small_train": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2, ablation="wo_sg"), 3, 16, 0, "stress", "train"),
+    # w/o TG selects frame_topk * ocr_topk OCR tokens per frame: 2 < 4 slots here, 6 >= 4 (everything, as in the shipped configs) below
+    "t2s_wo_tg_small_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=1, ocr_topk=2, ablation="wo_tg"), 3, 17, 0, "stress", "eval"),
+    "t2s_wo_tg_all_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2, ablation="wo_tg"), 3, 18, 0, "stress", "eval"),
     "m4c_small_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=1, ocr_topk=1, model="m4c"), 3, 14, 0, "stress", "eval"),
     "m4c_abinet_eval": (dict(frame_topk=1, ocr_topk=1, model="m4c"), 2, 1238, 0, "stress", "eval"),
 }
@@ -83,7 +89,11 @@ def build_reference_model(d, sd):
     registry.register("vtextgqa_num_final_outputs", d.num_outputs)
     registry.register("vtextgqa_answer_processor", AttrDict(BOS_IDX=1, EOS_IDX=2, PAD_IDX=0))
     cfg = AttrDict.wrap(synth.model_config_for_dims(d))
-    if d.model == "t2s":
+    if d.model == "t2s" and d.ablation == "wo_sg":
+        from pythia.models.t2s_wo_sg import T2S as Model        # registered as "t2s_wo_sg"
+    elif d.model == "t2s" and d.ablation == "wo_tg":
+        from pythia.models.t2s_wo_tg import T2S as Model        # registered as "t2s_wo_tg"
+    elif d.model == "t2s":
         from pythia.models.t2s import T2S as Model
     else:
         from pythia.models.m4c import M4C as Model
@@ -138,7 +148,7 @@ def run_fixture(name):
     sl = synth.to_sample_list(inp, SampleList, with_noise=False)
     captured = {}
     hooks = []
-    if d.model == "t2s":
+    if d.model == "t2s" and d.ablation != "wo_tg":
         def cap_temporal(mod, args, out):
             captured["pos_frame_topk_mask"] = out[1].detach().clone()
             captured["neg_frame_topk_mask"] = out[2].detach().clone()

@@ -33,7 +33,8 @@ def build_b200_model(d, sd, train=False):
     from vitxt_gqa_b200 import model as tmodel
     register_defaults(vocab_size=d.vocab, ocr_max_num=d.ocr)
     cfg = ConfigNode(synth.model_config_for_dims(d))
-    m = (tmodel.T2S if d.model == "t2s" else tmodel.M4C)(cfg)
+    cls = {"": tmodel.T2S, "wo_sg": tmodel.T2SWithoutSG, "wo_tg": tmodel.T2SWithoutTG}[d.ablation]
+    m = (cls if d.model == "t2s" else tmodel.M4C)(cfg)
     m.build()
     m.init_losses_and_metrics()
     m.load_state_dict(sd, strict=True)

@@ -23,7 +23,10 @@ def _neg_override(z):
 
 
 @pytest.mark.parametrize("fixture,schedule", [("t2s_small_eval", "literal"), ("t2s_small_eval", "dedup"),
-                                              ("t2s_small_default", "literal"), ("t2s_small_train", "literal")])
+                                              ("t2s_small_default", "literal"), ("t2s_small_train", "literal"),
+                                              # ablation models (reference models/t2s_wo_sg.py, t2s_wo_tg.py)
+                                              ("t2s_wo_sg_small_eval", "dedup"), ("t2s_wo_sg_small_train", "literal"),
+                                              ("t2s_wo_tg_small_eval", "dedup"), ("t2s_wo_tg_all_eval", "dedup")])
 def test_oracle_t2s_matches_reference_golden(fixture, schedule):
     z, meta, d, sd, inp = load_golden(fixture)
     train = meta["mode"] == "train"
@@ -32,7 +35,8 @@ def test_oracle_t2s_matches_reference_golden(fixture, schedule):
                             return_debug=True)
     assert np.array_equal(out["ground_frame"].numpy(), z["ground_frame"])
     assert np.array_equal(out["ground_box"].numpy(), z["ground_box"])
-    assert np.array_equal(out["debug"]["frame_pos_topk"].numpy(), z["pos_frame_topk_mask"])
+    if "pos_frame_topk_mask" in z.files:          # the w/o TG ablation has no temporal indicator
+        assert np.array_equal(out["debug"]["frame_pos_topk"].numpy(), z["pos_frame_topk_mask"])
     for k in ("ref_scores", "pos_scores", "neg_scores"):
         err = np.abs(out[k].numpy() - z[k]).max()
         assert err <= FP32_ATOL, (fixture, k, err)

@@ -105,6 +105,41 @@ def test_t2s_against_reference_golden(fixture):
     assert abs(losses["InfoNCE"] - ref_nce) <= LOSS_RTOL * abs(ref_nce) + w * INFO_NCE_ATOL, (losses, ref_nce)
 
 
+@pytest.mark.parametrize("fixture", ["t2s_wo_sg_small_eval", "t2s_wo_sg_small_train", "t2s_wo_tg_small_eval",
+                                     "t2s_wo_tg_all_eval"])
+def test_ablation_models_against_reference_golden(fixture):
+    """`t2s_wo_sg` / `t2s_wo_tg` (reference models/t2s_wo_sg.py, t2s_wo_tg.py): same weights, inputs
+    and kernels, different Grounding_Module wiring; goldens come from the real ablation models."""
+    from vitxt_gqa_b200.pythia_api import registry
+    z, meta, d, sd, inp = load_golden(fixture)
+    train = meta["mode"] == "train"
+    model = build_b200_model(d, sd, train=train)
+    assert type(model) is registry.get_model_class("t2s_" + d.ablation)
+    sl = sample_list(inp)
+    if "pos_frame_topk_mask" in z.files:        # w/o SG keeps the temporal indicator and its tie-order freedom
+        model.parity_hooks = {"pos_frame_topk": torch.from_numpy(z["pos_frame_topk_mask"]),
+                              "neg_frame_topk": torch.from_numpy(z["neg_frame_topk_mask"])}
+    with torch.no_grad():
+        out = model(sl)
+    torch.cuda.synchronize()
+    assert out["ground_frame"].shape == z["ground_frame"].shape and out["ground_box"].shape == z["ground_box"].shape
+    assert np.array_equal(out["ground_frame"].cpu().numpy(), z["ground_frame"])
+    assert np.array_equal(out["ground_box"].cpu().numpy(), z["ground_box"]), "grounded OCR boxes differ"
+    keys = ("pos_scores", "ref_scores", "neg_scores")
+    if train:
+        for key in keys:
+            _check_scores(fixture + ":" + key, z[key], out[key], True)
+    elif _check_eval_scores(fixture, z, out, model, sl, keys):
+        model.parity_hooks["force_prev_inds"] = reference_prev_inds(z["pos_scores"])
+        with torch.no_grad():
+            out = model(sl)
+        torch.cuda.synchronize()
+    losses = {k_.split("/")[-1]: float(v) for k_, v in out["losses"].items()}
+    assert abs(losses["pos_bce_loss"] - float(z["loss_pos_bce"][0])) <= LOSS_RTOL * abs(float(z["loss_pos_bce"][0]))
+    ref_nce = float(z["loss_info_nce"]) * 1000.0
+    assert abs(losses["InfoNCE"] - ref_nce) <= LOSS_RTOL * abs(ref_nce) + 1000.0 * INFO_NCE_ATOL, (losses, ref_nce)
+
+
 @pytest.mark.parametrize("fixture", ["m4c_small_eval", "m4c_abinet_eval"])
 def test_m4c_against_reference_golden(fixture):
     z, meta, d, sd, inp = load_golden(fixture)

@@ -245,12 +245,12 @@ spatial_select_kernel(const float* __restrict__ sim, int sim_stride, int sim_off
     const int kk = topk < Of ? topk : Of;
     for (int o = tid; o < O; o += blockDim.x) {
         att[o] = sim[(long long)b * sim_stride + sim_off + o];
-        msk[o] = mode == 0 ? slot_mask[(long long)b * O + o] : joint_mask[(long long)b * L + ocr_off + o];
+        msk[o] = mode != 1 ? slot_mask[(long long)b * O + o] : joint_mask[(long long)b * L + ocr_off + o];
     }
     __syncthreads();
     masked_attention(att, msk, O, red);
     for (int o = tid; o < O; o += blockDim.x) {
-        if (mode == 0) {
+        if (mode == 0 || mode == 3) {
             const Split s = gumbel_split(att[o], msk[o], gumbel[((long long)b * 2) * O + o], gumbel[((long long)b * 2 + 1) * O + o]);
             pos[o] = s.pos_score;
             neg[o] = s.neg_score;
@@ -270,9 +270,23 @@ spatial_select_kernel(const float* __restrict__ sim, int sim_stride, int sim_off
             rn += (neg[base + j] < nv) || (neg[base + j] == nv && j < i);   // stable ascending sort rank
         }
         const bool psel = rp < kk;
-        if (mode == 0) {
-            pos_joint[(long long)b * L + ocr_off + o] = psel ? 1.f : 0.f;
-            neg_joint[(long long)b * L + ocr_off + o] = (rn < kk ? 1.f : 0.f) * msk[o];
+        if (mode == 2) {
+            // ablation "w/o SG" (models/t2s_wo_sg.py:503-506): every slot of the grounded frames is positive, every
+            // other slot negative (pads included), ground_box = the boxes of the positive slots in slot order
+            const float slot = msk[o];
+            pos_joint[(long long)b * L + ocr_off + o] = slot;
+            neg_joint[(long long)b * L + ocr_off + o] = 1.f - slot;
+            if (slot != 0.f) {
+                for (int j = 0; j < o; ++j) before += msk[j] != 0.f;
+                if (before < topk * Of)
+                    *reinterpret_cast<float4*>(ground_box + ((long long)b * topk * Of + before) * 4) =
+                        *reinterpret_cast<const float4*>(boxes + ((long long)b * O + o) * 4);
+            }
+        } else if (mode == 0 || mode == 3) {
+            // mode 3 = ablation "w/o TG" (models/t2s_wo_tg.py:503-507): both masks are also multiplied by ocr_mask
+            const float om = mode == 3 ? joint_mask[(long long)b * L + ocr_off + o] : 1.f;
+            pos_joint[(long long)b * L + ocr_off + o] = (psel ? 1.f : 0.f) * om;
+            neg_joint[(long long)b * L + ocr_off + o] = (rn < kk ? 1.f : 0.f) * msk[o] * om;
             if (psel) {
                 // masked_select keeps slot order: index inside the frame = #selected slots before this one
                 for (int j = 0; j < i; ++j) {
@@ -300,6 +314,63 @@ spatial_select_kernel(const float* __restrict__ sim, int sim_stride, int sim_off
                 *reinterpret_cast<float4*>(ground_box + ((long long)b * kk + before) * 4) = bx;
             }
         }
+    }
+}
+
+// OCR slots whose temporal id equals one of n_ids frame ids per sample, id 0 (padding) read as 1
+// (models/t2s.py:486-494 with `tensor1` = any id list; models/t2s_wo_tg.py:483-495 passes sample_list.frame_id)
+__global__ void frame_slots_kernel(const long long* __restrict__ ids, int n_ids, const long long* __restrict__ temporal_id,
+                                   int B, int O, float* __restrict__ slot_mask) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * O) return;
+    const int b = (int)(i / O);
+    const long long t = temporal_id[i];
+    bool hit = false;
+    for (int k = 0; k < n_ids; ++k) {
+        const long long id = ids[(long long)b * n_ids + k];
+        hit |= t == (id == 0 ? 1 : id);
+    }
+    slot_mask[i] = hit ? 1.f : 0.f;
+}
+
+// ablation "w/o TG" (models/t2s_wo_tg.py:511-535): the frame masks are derived from the OCR masks -- the first n_pick
+// frames that own a positive (negative) OCR slot; a sample with fewer gets index -1, which the reference's advanced
+// indexing reads as the LAST frame.  ground_frame = the picked positive frame POSITIONS (not ids), -1 padded.
+// One CTA per sample; also copies the question part of the joint mask like temporal_select does.
+__global__ void __launch_bounds__(128)
+frames_from_ocr_kernel(const float* __restrict__ joint_mask, float* __restrict__ pos_joint, float* __restrict__ neg_joint,
+                       int L, int Lt, int F, int Of, int n_pick, long long* __restrict__ ground_frame) {
+    extern __shared__ unsigned char s_any[];     // [2][F]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    float* jm[2] = {pos_joint + (long long)b * L, neg_joint + (long long)b * L};
+    for (int f = tid; f < 2 * F; f += blockDim.x) {
+        const int which = f / F, fr = f % F;
+        const float* row = jm[which] + Lt + F + fr * Of;
+        bool any = false;
+        for (int j = 0; j < Of; ++j) any |= row[j] != 0.f;
+        s_any[f] = any;
+    }
+    __syncthreads();
+    for (int f = tid; f < 2 * F; f += blockDim.x) {
+        const int which = f / F, fr = f % F;
+        int before = 0, total = 0;
+        for (int j = 0; j < F; ++j) {
+            total += s_any[which * F + j];
+            if (j < fr) before += s_any[which * F + j];
+        }
+        bool on = s_any[f] && before < n_pick;
+        if (fr == F - 1 && total < n_pick) on = true;                 // index -1
+        jm[which][Lt + fr] = on ? 1.f : 0.f;
+        if (which == 0) {
+            if (s_any[f] && before < n_pick) ground_frame[(long long)b * n_pick + before] = fr;
+            if (fr == 0)
+                for (int k = total; k < n_pick; ++k) ground_frame[(long long)b * n_pick + k] = -1;
+        }
+    }
+    for (int i = tid; i < Lt; i += blockDim.x) {
+        const float v = joint_mask[(long long)b * L + i];
+        jm[0][i] = v;
+        jm[1][i] = v;
     }
 }
 
@@ -388,4 +459,21 @@ extern "C" int t2s_middle_frame_slots(const long long* mid_id, const long long* 
     if (n <= 0) { set_error("middle_frame_slots: empty"); return T2S_ERR_SHAPE; }
     middle_frame_slots_kernel<<<(int)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(mid_id, temporal_id, B, O, slot_mask);
     return launch_status("middle_frame_slots");
+}
+
+extern "C" int t2s_frame_slots(const long long* ids, int n_ids, const long long* temporal_id, int B, int O,
+                               float* slot_mask, void* stream) {
+    const long long n = (long long)B * O;
+    if (n <= 0 || n_ids <= 0) { set_error("frame_slots: empty"); return T2S_ERR_SHAPE; }
+    frame_slots_kernel<<<(int)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids, n_ids, temporal_id, B, O, slot_mask);
+    return launch_status("frame_slots");
+}
+
+extern "C" int t2s_frames_from_ocr(const float* joint_mask, float* pos_joint, float* neg_joint, int B, int Lt, int F,
+                                   int Of, int n_pick, long long* ground_frame, void* stream) {
+    if (B <= 0 || F <= 0 || Of <= 0 || n_pick <= 0) { set_error("frames_from_ocr: bad shape"); return T2S_ERR_SHAPE; }
+    const int L = Lt + F + F * Of;
+    frames_from_ocr_kernel<<<B, 128, 2 * F, reinterpret_cast<cudaStream_t>(stream)>>>(joint_mask, pos_joint, neg_joint, L, Lt,
+                                                                                   F, Of, n_pick, ground_frame);
+    return launch_status("frames_from_ocr");
 }

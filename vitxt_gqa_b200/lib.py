@@ -48,6 +48,8 @@ SIGNATURES = {
     "t2s_temporal_select": [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "t2s_spatial_select": [_p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "t2s_middle_frame_slots": [_p, _p, _i, _i, _p, _p],
+    "t2s_frame_slots": [_p, _i, _p, _i, _i, _p, _p],
+    "t2s_frames_from_ocr": [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
     "t2s_ptr_score": [_p, _ll, _i, _i, _i, _i, _p, _ll, _ll, _i, _i, _p, _ll, _p, _ll, _i, _p],
     "t2s_argmax_feedback": [_p, _ll, _i, _i, _i, _i, _i, _p, _i, _p, _p],
     "t2s_pos_bce_loss": [_p, _p, _p, _i, _i, _i, _p, _p, _p],

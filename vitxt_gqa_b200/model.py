@@ -774,6 +774,7 @@ class PendingForward:
 @registry.register_model("t2s")
 class T2S(_FusionModelBase):
     MODEL = "t2s"
+    ABLATION = ""       # "" | "wo_sg" | "wo_tg": the Grounding_Module wiring of the reference's ablation models
 
     def _build_grounding(self):
         cfg, h = self.config, self.hidden
@@ -803,9 +804,6 @@ class T2S(_FusionModelBase):
         else:   # F.gumbel_softmax draws -log(Exp(1)) noise (reference stg.py:41,89); torch RNG is plumbing here
             gf = -torch.empty(B, 2, F, device=dev).exponential_().log()
             go = -torch.empty(B, 2, O, device=dev).exponential_().log()
-        ground_frame = torch.empty(B, self.frame_topk, device=dev, dtype=torch.int64)
-        kk = min(self.ocr_topk, Of)
-        ground_box = torch.empty(B, F * kk, 4, device=dev, dtype=torch.float32)
         # test-only overrides; the device copies must stay referenced until the launch is enqueued
         pos_ovr = self.parity_hooks.get("pos_frame_topk")
         neg_ovr = self.parity_hooks.get("neg_frame_topk")
@@ -814,13 +812,36 @@ class T2S(_FusionModelBase):
         dbg = self.parity_hooks.get("debug", False)
         dbg_f = torch.empty(B, F, device=dev) if dbg else None
         dbg_o = torch.empty(B, O, device=dev) if dbg else None
-        L.temporal_select(_ptr(ws["sim"]), F + O, _ptr(ws["jm_ref"]), B, Lt, F, Of, _ptr(gf), _ptr(inp["frame_id"]),
-                          _ptr(inp["temporal_id"]), self.frame_topk,
-                          _ptr(pos_ovr), _ptr(neg_ovr),
-                          _ptr(ground_frame), _ptr(ws["jm_pos"]), _ptr(ws["jm_neg"]), _ptr(ws["slot"]), _ptr(dbg_f), st)
-        L.spatial_select(_ptr(ws["sim"]), F + O, F, _ptr(ws["slot"]), _ptr(ws["jm_ref"]), B, Le, Lt + F, F, Of, _ptr(go),
-                         _ptr(inp["ocr_bbox_coordinates"]), self.ocr_topk, 0, _ptr(ground_box), _ptr(ws["jm_pos"]),
-                         _ptr(ws["jm_neg"]), _ptr(dbg_o), st)
+        boxes = inp["ocr_bbox_coordinates"]
+        if self.ABLATION == "wo_tg":
+            # reference models/t2s_wo_tg.py:483-535: no temporal stage -- the slots of every frame id compete, the
+            # spatial stage keeps frame_topk * ocr_topk tokens per frame, and the frame masks follow from the OCR masks
+            k_o = self.frame_topk * self.ocr_topk
+            ground_frame = torch.empty(B, 5, device=dev, dtype=torch.int64)          # the 5 is literal in the reference
+            ground_box = torch.empty(B, F * min(k_o, Of), 4, device=dev, dtype=torch.float32)
+            L.frame_slots(_ptr(inp["frame_id"]), F, _ptr(inp["temporal_id"]), B, O, _ptr(ws["slot"]), st)
+            L.spatial_select(_ptr(ws["sim"]), F + O, F, _ptr(ws["slot"]), _ptr(ws["jm_ref"]), B, Le, Lt + F, F, Of,
+                             _ptr(go), _ptr(boxes), k_o, 3, _ptr(ground_box), _ptr(ws["jm_pos"]), _ptr(ws["jm_neg"]),
+                             _ptr(dbg_o), st)
+            L.frames_from_ocr(_ptr(ws["jm_ref"]), _ptr(ws["jm_pos"]), _ptr(ws["jm_neg"]), B, Lt, F, Of, 5,
+                              _ptr(ground_frame), st)
+        else:
+            ground_frame = torch.empty(B, self.frame_topk, device=dev, dtype=torch.int64)
+            L.temporal_select(_ptr(ws["sim"]), F + O, _ptr(ws["jm_ref"]), B, Lt, F, Of, _ptr(gf), _ptr(inp["frame_id"]),
+                              _ptr(inp["temporal_id"]), self.frame_topk,
+                              _ptr(pos_ovr), _ptr(neg_ovr),
+                              _ptr(ground_frame), _ptr(ws["jm_pos"]), _ptr(ws["jm_neg"]), _ptr(ws["slot"]), _ptr(dbg_f), st)
+            if self.ABLATION == "wo_sg":
+                # reference models/t2s_wo_sg.py:496-506: all slots of the grounded frames / all the other slots
+                ground_box = torch.zeros(B, self.frame_topk * Of, 4, device=dev, dtype=torch.float32)
+                L.spatial_select(_ptr(ws["sim"]), F + O, F, _ptr(ws["slot"]), _ptr(ws["jm_ref"]), B, Le, Lt + F, F, Of,
+                                 _ptr(go), _ptr(boxes), self.frame_topk, 2, _ptr(ground_box), _ptr(ws["jm_pos"]),
+                                 _ptr(ws["jm_neg"]), _ptr(dbg_o), st)
+            else:
+                ground_box = torch.empty(B, F * min(self.ocr_topk, Of), 4, device=dev, dtype=torch.float32)
+                L.spatial_select(_ptr(ws["sim"]), F + O, F, _ptr(ws["slot"]), _ptr(ws["jm_ref"]), B, Le, Lt + F, F, Of,
+                                 _ptr(go), _ptr(boxes), self.ocr_topk, 0, _ptr(ground_box), _ptr(ws["jm_pos"]),
+                                 _ptr(ws["jm_neg"]), _ptr(dbg_o), st)
         L.build_keys(_ptr(ws["jm_pos"]), B, Le, _ptr(ws["keys"]["pos"]), _ptr(ws["nk"]["pos"]), Le, st)
         L.build_keys(_ptr(ws["jm_neg"]), B, Le, _ptr(ws["keys"]["neg"]), _ptr(ws["nk"]["neg"]), Le, st)
 
@@ -1018,6 +1039,22 @@ class T2S(_FusionModelBase):
             "ground_box": ground_box, "ground_frame": ground_frame,
             "frame_topk": _dev_scalar(self.frame_topk, dev), "ocr_topk": _dev_scalar(self.ocr_topk, dev),
         }
+
+
+@registry.register_model("t2s_wo_sg")
+class T2SWithoutSG(T2S):
+    """Ablation "w/o spatial grounding" (reference pythia/models/t2s_wo_sg.py, registry key `t2s_wo_sg`): identical
+    modules and state_dict; the positive / negative OCR sets are all slots of the grounded / the other frames."""
+    MODEL = "t2s_wo_sg"
+    ABLATION = "wo_sg"
+
+
+@registry.register_model("t2s_wo_tg")
+class T2SWithoutTG(T2S):
+    """Ablation "w/o temporal grounding" (reference pythia/models/t2s_wo_tg.py, registry key `t2s_wo_tg`): the spatial
+    indicator runs over the slots of every frame and the frame masks are derived from its OCR masks."""
+    MODEL = "t2s_wo_tg"
+    ABLATION = "wo_tg"
 
 
 # =============================================================================== M4C

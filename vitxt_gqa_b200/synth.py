@@ -35,6 +35,7 @@ class Dims:
     ground_enc_layers: int = 2   # Grounding_Module.encoder: dead weights
     word_vocab: int = 30522
     model: str = "t2s"           # "t2s" | "m4c"
+    ablation: str = ""           # t2s only: "" | "wo_sg" | "wo_tg" (reference models/t2s_wo_sg.py, t2s_wo_tg.py)
 
     @property
     def ocr(self):

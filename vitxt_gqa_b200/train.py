@@ -67,7 +67,7 @@ class TrainEngine:
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
             raise _lib.T2SLibraryError("the training step runs only on a CUDA device (sm_100a); there is no CPU fallback")
-        if model.MODEL != "t2s":
+        if not model.MODEL.startswith("t2s"):
             raise NotImplementedError("the B200 training step is built for T2S (config 3); M4C trains eval-only here")
         if model.grounding_precision != "bf16x3":
             raise NotImplementedError("training uses the bf16x3 grounding chain")
