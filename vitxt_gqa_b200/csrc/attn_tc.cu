@@ -6,8 +6,8 @@
 // through the compacted per-sample key list (see attention.cu): exp(-10000 - max) == 0 in fp32.
 //
 // One CTA = 128 query rows of one (sample, head); key tiles of 128 gathered rows.
-//   warps 0-3  softmax: thread r owns query row r == TMEM lane r.  Two sweeps over S in TMEM
-//              (row max, then exp2 / row sum), P written as bf16 into a 128B-swizzled shared-memory
+//   warps 0-3  softmax: thread r owns query row r == TMEM lane r.  One software-pipelined sweep over S in TMEM
+//              (exp2 against the carried maximum, row sum), P written as bf16 into a 128B-swizzled shared-memory
 //              tile (the A operand of P.V).  O accumulates in TMEM across key tiles; the online-
 //              softmax correction is LAZY: the running maximum is only raised (and O rescaled in
 //              TMEM by tcgen05.ld / st) when a tile exceeds it by more than 2^8, which keeps the
@@ -30,6 +30,12 @@ namespace t2s {
 constexpr int TC_BQ = 128, TC_BK = 128, TC_DH = 64;
 constexpr int TC_THREADS = 288;              // 4 softmax + 4 loader + 1 MMA warp
 constexpr int TC_TILE = 128 * 128;           // bytes of a [128 rows x 64 bf16] 128B-swizzled tile
+// Query tiles per CTA.  A CTA that lives for one 128-row query tile spends ~4 us on things that are not attention
+// (launch, barrier + TMEM set-up, the dependent index -> row gathers of Q and the first K/V tile, the drain of the last
+// P.V, the O read-out) -- 35 % of the bf16 launches' time at the short `pos` / `neg` key lists.  With TC_NQ consecutive
+// query tiles of one (sample, head) per CTA the set-up is paid once and Q / K / V of tile i + 1 are gathered while tile
+// i is in its last softmax, P.V and read-out.
+constexpr int TC_NQ = 3;
 
 template <bool X3>
 struct TcCfg {
@@ -81,10 +87,13 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
     uint64_t* kv_empty = bars + 2;     // [2] count 1   (tcgen05.commit)
     uint64_t* s_full = bars + 4;       // count 1
     uint64_t* p_full = bars + 5;       // count 128 (softmax threads)
-    uint64_t* o_done = bars + 6;       // count 1: committed behind the last P.V only
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint64_t* o_done = bars + 6;       // count 1: committed behind the last P.V of a query tile
+    uint64_t* q_empty = bars + 7;      // count 1: committed behind the last S of a query tile (Q may be overwritten)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TC_BQ;
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int it0 = blockIdx.x * TC_NQ;                                    // first query tile of this CTA
+    const int n_items = min(TC_NQ, (L + TC_BQ - 1) / TC_BQ - it0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = n_keys[b];
     const int nt = (nk + TC_BK - 1) / TC_BK;
@@ -95,7 +104,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         if (lane == 0) {
             mbar_init(&kv_full[0], 128); mbar_init(&kv_full[1], 128);
             mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
-            mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_done, 1);
+            mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_done, 1); mbar_init(q_empty, 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -112,16 +121,17 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         // ------------------------------------------------------------------ loaders
         const int lt = threadIdx.x - 128;            // 0..127
         const int c = lt & 7, r0 = lt >> 3;          // 16-byte chunk / first row; rows r0 + 16 i
-        // Q tile(s): rows q0 .. q0+127 (zero-filled past L)
+        auto load_q = [&](int q0) {              // Q tile(s): rows q0 .. q0+127 (zero-filled past L)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = r0 + 16 * i;
-            const bool ok = q0 + r < L;
-            const __nv_bfloat16* src = base + (long long)(ok ? q0 + r : 0) * ld + c * 8;
-            const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
-            cp_async16(sQ + off, src, ok);
-            if (X3) cp_async16(sQ + TC_TILE + off, src + lo_off, ok);
-        }
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 16 * i;
+                const bool ok = q0 + r < L;
+                const __nv_bfloat16* src = base + (long long)(ok ? q0 + r : 0) * ld + c * 8;
+                const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+                cp_async16(sQ + off, src, ok);
+                if (X3) cp_async16(sQ + TC_TILE + off, src + lo_off, ok);
+            }
+        };
         auto load_tile = [&](int t, int s) {
             uint8_t* dst = sKV + s * Cfg::KV_STAGE;
 #pragma unroll
@@ -140,18 +150,26 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                 }
             }
         };
-        load_tile(0, 0);
-        cp_async_commit();
-        for (int t = 0; t < nt; ++t) {
-            if (t + 1 < nt) {
-                const int s1 = (t + 1) & 1;
-                mbar_wait(&kv_empty[s1], (((t + 1) >> 1) & 1) ^ 1);
-                load_tile(t + 1, s1);
-            }
+        int g = 0;                               // key tiles handled so far by this CTA: stage g & 1, phase (g >> 1) & 1
+        for (int it = 0; it < n_items; ++it) {
+            // Q of this query tile may land once every S of the previous one has retired; its first K/V tile goes to
+            // the stage the tile before last has left.  Both waits pass at once for the first query tile.
+            mbar_wait(q_empty, (it & 1) ^ 1);
+            mbar_wait(&kv_empty[g & 1], ((g >> 1) & 1) ^ 1);
+            load_q((it0 + it) * TC_BQ);
+            load_tile(0, g & 1);
             cp_async_commit();
-            cp_async_wait<1>();                  // this thread's share of tile t (and Q) has landed
-            fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
-            mbar_arrive(&kv_full[t & 1]);
+            for (int t = 0; t < nt; ++t, ++g) {
+                if (t + 1 < nt) {
+                    const int s1 = (g + 1) & 1;
+                    mbar_wait(&kv_empty[s1], (((g + 1) >> 1) & 1) ^ 1);
+                    load_tile(t + 1, s1);
+                }
+                cp_async_commit();
+                cp_async_wait<1>();                  // this thread's share of tile t (and Q) has landed
+                fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
+                mbar_arrive(&kv_full[g & 1]);
+            }
         }
     } else if (warp == 8) {
         // ------------------------------------------------------------------ MMA issuer
@@ -177,37 +195,45 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
             }
             __syncwarp();
         };
-        mbar_wait(&kv_full[0], 0);
-        tc_fence_after();
-        issue_s(0);
-        for (int t = 0; t < nt; ++t) {
-            const int s = t & 1;
-            mbar_wait(p_full, t & 1);
+        int g = 0;                               // key tiles issued so far by this CTA (all query tiles)
+        for (int it = 0; it < n_items; ++it) {
+            // S of the first key tile goes out right behind the previous query tile's last P.V: S in TMEM is free (its
+            // softmax has arrived on p_full), and O is only overwritten by this tile's first P.V, which waits for a
+            // p_full that the softmax warps raise after they have read the previous O out
+            mbar_wait(&kv_full[g & 1], (g >> 1) & 1);
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t aV = smem_u32(sKV + s * Cfg::KV_STAGE + NP * TC_TILE);
-                bool first = t == 0;         // O accumulates across key tiles
-#pragma unroll
-                for (int term = X3 ? 0 : 2; term < 3; ++term) {      // Pl.Vh, Ph.Vl, Ph.Vh
-                    const uint32_t p_plane = aP + ((X3 && term == 0) ? 2 * TC_TILE : 0);
-                    const uint32_t v_plane = aV + ((X3 && term == 1) ? TC_TILE : 0);
-#pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k) {
-                        // P: two [128 x 64-key] K-major tiles side by side; V: 16 keys = 2048 B per k-step
-                        const uint64_t dp = make_sw128_kmajor_desc(p_plane + (k >> 2) * TC_TILE) + 2 * (k & 3);
-                        const uint64_t dv = make_sw128_mnmajor_desc(v_plane + k * 2048);
-                        umma_bf16(tmem_O, dp, dv, idesc_o, first ? 0u : 1u);
-                        first = false;
-                    }
-                }
-                umma_commit(&kv_empty[s]);
-                if (t == nt - 1) umma_commit(o_done);
-            }
-            __syncwarp();
-            if (t + 1 < nt) {
-                mbar_wait(&kv_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
+            issue_s(g);
+            if (nt == 1 && lane == 0) umma_commit(q_empty);
+            for (int t = 0; t < nt; ++t, ++g) {
+                const int s = g & 1;
+                mbar_wait(p_full, g & 1);
                 tc_fence_after();
-                issue_s(t + 1);
+                if (lane == 0) {
+                    const uint32_t aV = smem_u32(sKV + s * Cfg::KV_STAGE + NP * TC_TILE);
+                    bool first = t == 0;         // O accumulates across the key tiles of one query tile
+#pragma unroll
+                    for (int term = X3 ? 0 : 2; term < 3; ++term) {      // Pl.Vh, Ph.Vl, Ph.Vh
+                        const uint32_t p_plane = aP + ((X3 && term == 0) ? 2 * TC_TILE : 0);
+                        const uint32_t v_plane = aV + ((X3 && term == 1) ? TC_TILE : 0);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k) {
+                            // P: two [128 x 64-key] K-major tiles side by side; V: 16 keys = 2048 B per k-step
+                            const uint64_t dp = make_sw128_kmajor_desc(p_plane + (k >> 2) * TC_TILE) + 2 * (k & 3);
+                            const uint64_t dv = make_sw128_mnmajor_desc(v_plane + k * 2048);
+                            umma_bf16(tmem_O, dp, dv, idesc_o, first ? 0u : 1u);
+                            first = false;
+                        }
+                    }
+                    umma_commit(&kv_empty[s]);
+                    if (t == nt - 1) umma_commit(o_done);
+                }
+                __syncwarp();
+                if (t + 1 < nt) {
+                    mbar_wait(&kv_full[(g + 1) & 1], ((g + 1) >> 1) & 1);
+                    tc_fence_after();
+                    issue_s(g + 1);
+                    if (t + 2 == nt && lane == 0) umma_commit(q_empty);     // last S of this query tile
+                }
             }
         }
     } else {
@@ -218,27 +244,29 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         const int sw = r & 7;
         constexpr float kRescale = 8.0f;                   // log2 domain: P stays below 2^8
         float m_run = -INFINITY, l_run = 0.f;
+        int g = 0;                                         // key tiles consumed so far by this CTA
         // One sweep over S per tile: P = exp2(S * scale - m_run) is formed with the maximum carried from the earlier
         // tiles while the tile's own maximum is tracked alongside; only when some row of the warp exceeds m_run by
         // more than 2^8 (or on the first tile, where no maximum exists yet) is the maximum raised, O rescaled in
         // TMEM and the tile's P recomputed.  (A separate maximum sweep doubled the TMEM reads and cost ~40 % of the
         // softmax warps' issue slots; ncu showed the tensor pipe waiting on them 85 % of the time.)
-        auto exp_sweep = [&](int valid, float m_use, float& tile_max_raw, float& sum) {
+        // The eight 16-column TMEM loads of a sweep are software pipelined (chunk c + 1 is in flight while chunk c goes
+        // through exp2 / pack / store).  On the first tile no maximum exists yet: it is seeded from the first 16 keys
+        // of the row (already in registers) instead of a separate maximum sweep over S -- any value within 2^8 of the
+        // true maximum is exact, and the rare larger excess takes the same raise-and-recompute path as later tiles.
+        auto exp_sweep = [&](int valid, float& m_use, bool seed, float& tile_max_raw, float& sum) {
             tile_max_raw = -INFINITY;
             sum = 0.f;
             const bool full = valid == TC_BK;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
-                tmem_ld_wait();
-                uint32_t ph[16], pl[16];
+            uint32_t va[16], vb[16];
+            auto step = [&](uint32_t (&v)[16], int c) {       // 16 keys: columns c*16 .. c*16+15
+                uint32_t ph[8], pl[8];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
+                for (int j = 0; j < 16; j += 2) {
                     float s0 = __uint_as_float(v[j]), s1 = __uint_as_float(v[j + 1]);
                     if (!full) {                 // warp-uniform: only the last key tile of a sample is ragged
-                        if (c * 32 + j >= valid) s0 = -INFINITY;
-                        if (c * 32 + j + 1 >= valid) s1 = -INFINITY;
+                        if (c * 16 + j >= valid) s0 = -INFINITY;
+                        if (c * 16 + j + 1 >= valid) s1 = -INFINITY;
                     }
                     tile_max_raw = fmaxf(tile_max_raw, fmaxf(s0, s1));
                     const float p0 = ex2_fast(fmaf(s0, scale_log2, -m_use));
@@ -247,49 +275,56 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                     ph[j >> 1] = pack_bf16x2(p0, p1);
                     if (X3) pl[j >> 1] = pack_bf16x2(p0 - bf16lo(ph[j >> 1]), p1 - bf16hi(ph[j >> 1]));
                 }
-                // keys c*32 .. c*32+31 -> tile (c >> 1), 16-byte chunks (c & 1) * 4 + 0..3 of row r
-                uint8_t* dst = p_row + (c >> 1) * TC_TILE;
+                // -> tile (c >> 2), 16-byte chunks (c & 3) * 2 + 0..1 of row r
+                uint8_t* dst = p_row + (c >> 2) * TC_TILE;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int chunk = (c & 1) * 4 + q;
+                for (int q = 0; q < 2; ++q) {
+                    const int chunk = (c & 3) * 2 + q;
                     *reinterpret_cast<uint4*>(dst + ((chunk ^ sw) << 4)) =
                         make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
                     if (X3)
                         *reinterpret_cast<uint4*>(dst + 2 * TC_TILE + ((chunk ^ sw) << 4)) =
                             make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
                 }
+            };
+            tmem_ld_32x16(tmem_S + lane_addr, va);
+#pragma unroll 1
+            for (int c = 0; c < 8; c += 2) {
+                tmem_ld_wait_on(va);
+                tmem_ld_32x16(tmem_S + lane_addr + (c + 1) * 16, vb);
+                if (c == 0 && seed) {
+                    float m0 = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (full || j < valid) m0 = fmaxf(m0, __uint_as_float(va[j]));
+                    m_use = m0 * scale_log2;         // key lists are compacted: column 0 always exists
+                }
+                step(va, c);
+                tmem_ld_wait_on(vb);
+                if (c + 2 < 8) tmem_ld_32x16(tmem_S + lane_addr + (c + 2) * 16, va);
+                step(vb, c + 1);
             }
         };
-        for (int t = 0; t < nt; ++t) {
+        for (int it = 0; it < n_items; ++it) {
+        const int q0 = (it0 + it) * TC_BQ;
+        m_run = -INFINITY;
+        l_run = 0.f;
+        for (int t = 0; t < nt; ++t, ++g) {
             const int valid = min(TC_BK, nk - t * TC_BK);          // keys of this tile that exist
-            mbar_wait(s_full, t & 1);       // S(t) done; MMAs retire in order, so P.V(t-1) is done as well
+            mbar_wait(s_full, g & 1);       // S(t) done; MMAs retire in order, so P.V(t-1) is done as well
             tc_fence_after();
             float mt_raw, sum;
-            if (t == 0) {
-                // no maximum yet: take it from a maximum-only pass (exp2(-inf - (-inf)) would be NaN)
-                mt_raw = -INFINITY;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c * 32 + j < valid) mt_raw = fmaxf(mt_raw, __uint_as_float(v[j]));
+            exp_sweep(valid, m_run, t == 0, mt_raw, sum);
+            const float mt = mt_raw * scale_log2;
+            const bool raise = mt > m_run + kRescale;
+            if (__any_sync(0xffffffffu, raise)) {
+                float corr = 1.0f;
+                if (raise) {
+                    corr = exp2f(m_run - mt);
+                    m_run = mt;
+                    l_run *= corr;
                 }
-                m_run = mt_raw * scale_log2;
-                exp_sweep(valid, m_run, mt_raw, sum);
-            } else {
-                exp_sweep(valid, m_run, mt_raw, sum);
-                const float mt = mt_raw * scale_log2;
-                const bool raise = mt > m_run + kRescale;
-                if (__any_sync(0xffffffffu, raise)) {
-                    float corr = 1.0f;
-                    if (raise) {
-                        corr = exp2f(m_run - mt);
-                        m_run = mt;
-                        l_run *= corr;
-                    }
+                if (t > 0) {
                     // rescale this warp's 32 rows of O in TMEM (rows that keep their maximum use corr == 1)
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -301,15 +336,15 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                         tmem_st_32x32(tmem_O + lane_addr + c * 32, v);
                     }
                     tmem_st_wait();
-                    exp_sweep(valid, m_run, mt_raw, sum);      // P of this tile against the raised maximum
                 }
+                exp_sweep(valid, m_run, false, mt_raw, sum);      // P of this tile against the raised maximum
             }
             l_run += sum;
             tc_fence_before();                   // S reads / O rescale ordered before the issuer's next MMAs
             fence_proxy_async();                 // P tile visible to the tensor core
             mbar_arrive(p_full);
         }
-        mbar_wait(o_done, 0);
+        mbar_wait(o_done, it & 1);
         tc_fence_after();
         const int row = q0 + r;
         const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
@@ -340,6 +375,8 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                 }
             }
         }
+        tc_fence_before();                       // O read-out ordered before the next query tile's first P.V
+        }   // query tiles of this CTA
     }
     tc_fence_before();
     __syncthreads();
@@ -360,7 +397,8 @@ static int launch_attn_tc(const void* qkv, long long ld, int lo_off, int B, int 
         if (e != cudaSuccess) { set_error("attn_tc attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr = true;
     }
-    dim3 grid((L + TC_BQ - 1) / TC_BQ, heads, B);
+    const int n_qt = (L + TC_BQ - 1) / TC_BQ;
+    dim3 grid((n_qt + TC_NQ - 1) / TC_NQ, heads, B);
     attn_tc_kernel<X3><<<grid, TC_THREADS, Cfg::SMEM, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(qkv), ld, lo_off, L, H, key_idx, n_keys, key_stride,
         reinterpret_cast<__nv_bfloat16*>(out), ldo, 0.125f * 1.4426950408889634f);

@@ -41,14 +41,21 @@ struct GemmEpi {
     int c_lo_off;   // T2S_GEMM_OUT_SPLIT: column offset of the `lo` half of the bf16 hi|lo output
 };
 
+// BN = 64 is the latency tile of the greedy decode (M = batch rows, a few dozen CTAs per launch, run next to the capped
+// throughput GEMMs of the other stream): 4 epilogue warps (one per TMEM lane quarter), 3 stages and 192 threads, so that
+// TWO CTAs fit one SM (91 KB shared memory, 32 K registers, 128 TMEM columns each) and the SMs the big grids leave
+// free hold twice as many decode tiles.
 template <int BN>
 struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 3);
     static constexpr int TMEM_COLS = 2 * BN;     // 512 / 256 / 128: powers of two >= 32
-    static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * 4096;    // one 32-row x 128-byte box per epilogue warp
+    static constexpr int EPI_WARPS = BN == 64 ? 4 : GEMM_EPI_WARPS;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int MIN_CTAS = BN == 64 ? 2 : 1;
+    static constexpr int STAGING_BYTES = EPI_WARPS * 4096;    // one 32-row x 128-byte box per epilogue warp
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -56,7 +63,7 @@ struct GemmCfg {
 // constants -- the hot epilogues of the fusion transformer get their own lean instantiation; MODE < 0: read at run time.
 constexpr int GEMM_MODE_RES = 32;
 template <int BN, int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)     // 10 warps = 3 on two of the four 16 K-register partitions: 168 registers at most
+__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, GemmCfg<BN>::MIN_CTAS)     // 10 warps = 3 on two of the four 16 K-register partitions: 168 registers at most
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, GemmEpi ep, int M, int N, int K, int k_lo_off) {
     using Cfg = GemmCfg<BN>;
@@ -93,7 +100,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&tfull[a], 1);
-                mbar_init(&tempty[a], GEMM_EPI_WARPS);
+                mbar_init(&tempty[a], Cfg::EPI_WARPS);
             }
             fence_barrier_init();
         }
@@ -159,10 +166,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ------------------------------------------------ epilogue (8 warps)
         const int ew = warp - 2;
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-        // BN >= 128: two warps per lane quarter split the columns; BN == 64: warps 0..3 take all 64 columns
-        constexpr int ACTIVE = BN >= 128 ? 8 : 4;
-        constexpr int COLS_PER_WARP = BN / (ACTIVE / 4);
-        const bool active = ew < ACTIVE;
+        // BN >= 128: two warps per lane quarter split the columns; BN == 64: four warps take all 64 columns
+        constexpr int COLS_PER_WARP = BN / (Cfg::EPI_WARPS / 4);
+        constexpr bool active = true;
         const int half = ew >> 2;
         const int fl = MODE >= 0 ? (MODE & 31) : ep.flags;
         const bool has_res = MODE >= 0 ? (MODE & GEMM_MODE_RES) != 0 : ep.residual != nullptr;
@@ -344,11 +350,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     }
                 }
             }
-            if (!active) {                           // BN == 64: warps 4..7 hold no columns
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
-            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -437,7 +438,7 @@ static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const 
     // T2S_GEMM_SM_CAP: the persistent grid leaves SMs free for latency-bound work on another stream
     const int sms = (sm_cap > 0 && sm_cap < num_sms()) ? sm_cap : num_sms();
     const int grid = tiles < sms ? tiles : sms;
-    gemm_bf16_tcgen05_kernel<BN, MODE><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, ep, M, N, K, k_lo_off);
+    gemm_bf16_tcgen05_kernel<BN, MODE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, ep, M, N, K, k_lo_off);
     return launch_status("gemm_bf16_tcgen05");
 }
 

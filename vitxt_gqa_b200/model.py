@@ -220,7 +220,7 @@ class _FusionModelBase(BaseModel):
         # eval only: run the latency-bound greedy decode of the `pos` variant on a second (high-priority) stream
         # while the throughput-bound encoder passes of `ref` / `neg` run on the caller's stream with their
         # persistent GEMM grids capped at (SMs - overlap_sms) CTAs.  0 disables the overlap.
-        self.overlap_sms = int(os.environ.get("T2S_B200_OVERLAP_SMS", str(self.config.get("b200_overlap_sms", 16))))
+        self.overlap_sms = int(os.environ.get("T2S_B200_OVERLAP_SMS", str(self.config.get("b200_overlap_sms", 24))))
         self._side_streams = {}
         # pipelined eval (submit / PendingForward.result): two workspace sets used alternately; the event that ends
         # the decode tail of the forward that last used a set gates its reuse
