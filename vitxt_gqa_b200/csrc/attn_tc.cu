@@ -28,7 +28,7 @@
 namespace t2s {
 
 constexpr int TC_BQ = 128, TC_BK = 128, TC_DH = 64;
-constexpr int TC_THREADS = 288;              // 4 softmax + 4 loader + 1 MMA warp
+// warps: NSW softmax, then 4 loaders, then 1 MMA issuer (NSW = 4, or 8 in the bf16x3 form)
 constexpr int TC_TILE = 128 * 128;           // bytes of a [128 rows x 64 bf16] 128B-swizzled tile
 // Query tiles per CTA.  A CTA that lives for one 128-row query tile spends ~4 us on things that are not attention
 // (launch, barrier + TMEM set-up, the dependent index -> row gathers of Q and the first K/V tile, the drain of the last
@@ -46,7 +46,15 @@ struct TcCfg {
     // no alignment slack: two CTAs (2 x (114 816 + 1 024 reserved)) must fit the 227 KB of an SM, so the kernel
     // relies on the dynamic shared-memory window starting 1024-byte aligned (it has no static shared memory)
     // and traps otherwise
-    static constexpr int SMEM = Q_BYTES + 2 * KV_STAGE + P_BYTES + 128;
+    // X3 runs one CTA per SM (shared memory), i.e. one softmax warp per scheduler if a thread owned a whole row; its
+    // softmax also does twice the conversions (hi and lo planes).  So each row is split between two threads (columns
+    // 0-63 / 64-127, warps w and w + 4 reach the same TMEM lane quarter): 8 softmax warps, two per scheduler, which
+    // exchange the tile maximum (per tile) and the row sum (per query tile) through shared memory.
+    static constexpr int HS = X3 ? 2 : 1;                     // threads per query row
+    static constexpr int NSW = 4 * HS;                        // softmax warps
+    static constexpr int THREADS = 32 * (NSW + 5);
+    static constexpr int XCH_BYTES = X3 ? 2 * 2 * 128 * 4 : 0; // [tile parity][half][row] floats
+    static constexpr int SMEM = Q_BYTES + 2 * KV_STAGE + P_BYTES + 128 + XCH_BYTES;
 };
 
 // MN-major (rows = K index, 64 contiguous N elements = one 128-byte row) 128B-swizzled operand: 8-row groups
@@ -70,7 +78,7 @@ __device__ __forceinline__ float ex2_fast(float x) {
 }
 
 template <bool X3>
-__global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2)
+__global__ void __launch_bounds__(TcCfg<X3>::THREADS, X3 ? 1 : 2)
 attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, int L, int H,
                const int* __restrict__ key_idx, const int* __restrict__ n_keys, int key_stride,
                __nv_bfloat16* __restrict__ out, long long ldo, float scale_log2) {
@@ -90,6 +98,8 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
     uint64_t* o_done = bars + 6;       // count 1: committed behind the last P.V of a query tile
     uint64_t* q_empty = bars + 7;      // count 1: committed behind the last S of a query tile (Q may be overwritten)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    float* xch = reinterpret_cast<float*>(sP + Cfg::P_BYTES + 128);
+    constexpr int HS = Cfg::HS, NSW = Cfg::NSW;
 
     const int b = blockIdx.z, h = blockIdx.y;
     const int it0 = blockIdx.x * TC_NQ;                                    // first query tile of this CTA
@@ -100,11 +110,11 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
     const int* kidx = key_idx + (long long)b * key_stride;
     const __nv_bfloat16* base = qkv + (long long)b * L * ld + h * TC_DH;
 
-    if (warp == 8) {
+    if (warp == NSW + 4) {
         if (lane == 0) {
             mbar_init(&kv_full[0], 128); mbar_init(&kv_full[1], 128);
             mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
-            mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_done, 1); mbar_init(q_empty, 1);
+            mbar_init(s_full, 1); mbar_init(p_full, 128 * HS); mbar_init(o_done, 1); mbar_init(q_empty, 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -117,9 +127,9 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= NSW && warp < NSW + 4) {
         // ------------------------------------------------------------------ loaders
-        const int lt = threadIdx.x - 128;            // 0..127
+        const int lt = threadIdx.x - 32 * NSW;       // 0..127
         const int c = lt & 7, r0 = lt >> 3;          // 16-byte chunk / first row; rows r0 + 16 i
         auto load_q = [&](int q0) {              // Q tile(s): rows q0 .. q0+127 (zero-filled past L)
 #pragma unroll
@@ -171,7 +181,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                 mbar_arrive(&kv_full[g & 1]);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == NSW + 4) {
         // ------------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc_s = make_idesc_bf16(TC_BQ, TC_BK);
         constexpr uint32_t idesc_o = make_idesc_bf16(TC_BQ, TC_DH) | (1u << 16);     // B operand (V) is MN-major
@@ -238,8 +248,10 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         }
     } else {
         // ------------------------------------------------------------------ softmax (thread == query row == TMEM lane)
-        const int r = threadIdx.x;                         // 0..127
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        const int r = threadIdx.x & 127;                   // query row of this thread
+        const int half = threadIdx.x >> 7;                 // HS == 2: which 64 key columns of the row (0 otherwise)
+        constexpr int NC = 8 / HS;                         // 16-column steps per sweep of this thread
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         uint8_t* p_row = sP + r * 128;
         const int sw = r & 7;
         constexpr float kRescale = 8.0f;                   // log2 domain: P stays below 2^8
@@ -265,7 +277,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                 for (int j = 0; j < 16; j += 2) {
                     float s0 = __uint_as_float(v[j]), s1 = __uint_as_float(v[j + 1]);
                     if (!full) {                 // warp-uniform: only the last key tile of a sample is ragged
-                        if (c * 16 + j >= valid) s0 = -INFINITY;
+                        if (c * 16 + j >= valid) s0 = -INFINITY;        // c = global 16-column step
                         if (c * 16 + j + 1 >= valid) s1 = -INFINITY;
                     }
                     tile_max_raw = fmaxf(tile_max_raw, fmaxf(s0, s1));
@@ -287,23 +299,40 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                             make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
                 }
             };
-            tmem_ld_32x16(tmem_S + lane_addr, va);
+            const int c0 = half * NC;                // first global 16-column step of this thread
+            if (seed) {
+                // the seed must be the same for both threads of a row: both read the row's first 16 keys
+                if (HS == 2 && half == 1) {
+                    tmem_ld_32x16(tmem_S + lane_addr, vb);
+                    tmem_ld_wait_on(vb);
+                }
+            }
+            tmem_ld_32x16(tmem_S + lane_addr + c0 * 16, va);
 #pragma unroll 1
-            for (int c = 0; c < 8; c += 2) {
+            for (int c = 0; c < NC; c += 2) {
                 tmem_ld_wait_on(va);
-                tmem_ld_32x16(tmem_S + lane_addr + (c + 1) * 16, vb);
                 if (c == 0 && seed) {
                     float m0 = -INFINITY;
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (full || j < valid) m0 = fmaxf(m0, __uint_as_float(va[j]));
+                        if (full || j < valid)
+                            m0 = fmaxf(m0, __uint_as_float((HS == 2 && half == 1) ? vb[j] : va[j]));
                     m_use = m0 * scale_log2;         // key lists are compacted: column 0 always exists
                 }
-                step(va, c);
+                tmem_ld_32x16(tmem_S + lane_addr + (c0 + c + 1) * 16, vb);
+                step(va, c0 + c);
                 tmem_ld_wait_on(vb);
-                if (c + 2 < 8) tmem_ld_32x16(tmem_S + lane_addr + (c + 2) * 16, va);
-                step(vb, c + 1);
+                if (c + 2 < NC) tmem_ld_32x16(tmem_S + lane_addr + (c0 + c + 2) * 16, va);
+                step(vb, c0 + c + 1);
             }
+        };
+        // HS == 2: the two threads of a row agree on the tile maximum through shared memory (slot = tile parity, so the
+        // next tile's write cannot overtake a slow reader); named barrier 1 covers the 256 softmax threads
+        auto joint_max = [&](float mine, int slot) {
+            if (HS == 1) return mine;
+            xch[(slot * 2 + half) * 128 + r] = mine;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            return fmaxf(mine, xch[(slot * 2 + (half ^ 1)) * 128 + r]);
         };
         for (int it = 0; it < n_items; ++it) {
         const int q0 = (it0 + it) * TC_BQ;
@@ -315,6 +344,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
             tc_fence_after();
             float mt_raw, sum;
             exp_sweep(valid, m_run, t == 0, mt_raw, sum);
+            mt_raw = joint_max(mt_raw, g & 1);
             const float mt = mt_raw * scale_log2;
             const bool raise = mt > m_run + kRescale;
             if (__any_sync(0xffffffffu, raise)) {
@@ -325,15 +355,17 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                     l_run *= corr;
                 }
                 if (t > 0) {
-                    // rescale this warp's 32 rows of O in TMEM (rows that keep their maximum use corr == 1)
+                    // rescale this warp's 32 rows of O in TMEM (rows that keep their maximum use corr == 1);
+                    // HS == 2: each thread of a row takes 32 of the 64 columns
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
+                    for (int c = 0; c < 2 / HS; ++c) {
                         uint32_t v[32];
-                        tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
+                        const uint32_t oc = (uint32_t)(HS == 2 ? half : c) * 32;
+                        tmem_ld_32x32(tmem_O + lane_addr + oc, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * corr);
-                        tmem_st_32x32(tmem_O + lane_addr + c * 32, v);
+                        tmem_st_32x32(tmem_O + lane_addr + oc, v);
                     }
                     tmem_st_wait();
                 }
@@ -347,10 +379,18 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         mbar_wait(o_done, it & 1);
         tc_fence_after();
         const int row = q0 + r;
-        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+        float l_row = l_run;
+        if (HS == 2) {                           // row sum = the two threads' partial sums (slots are free: the last
+            xch[half * 128 + r] = l_run;         // joint_max of this query tile lies behind a barrier both have passed)
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            l_row += xch[(half ^ 1) * 128 + r];
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // reads done before the next query tile writes
+        }
+        const float inv = l_row > 0.f ? 1.0f / l_row : 0.f;
         __nv_bfloat16* op = out + ((long long)b * L + row) * ldo + h * TC_DH;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int cc = 0; cc < 2 / HS; ++cc) {
+            const int c = HS == 2 ? half : cc;   // 32-column half of O this thread writes out
             uint32_t v[32];
             tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);      // warp-collective: rows past L load too
             tmem_ld_wait();
@@ -380,7 +420,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == NSW + 4) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 256);
     }
@@ -399,7 +439,7 @@ static int launch_attn_tc(const void* qkv, long long ld, int lo_off, int B, int 
     }
     const int n_qt = (L + TC_BQ - 1) / TC_BQ;
     dim3 grid((n_qt + TC_NQ - 1) / TC_NQ, heads, B);
-    attn_tc_kernel<X3><<<grid, TC_THREADS, Cfg::SMEM, st>>>(
+    attn_tc_kernel<X3><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(qkv), ld, lo_off, L, H, key_idx, n_keys, key_stride,
         reinterpret_cast<__nv_bfloat16*>(out), ldo, 0.125f * 1.4426950408889634f);
     return launch_status("attn_tc");
