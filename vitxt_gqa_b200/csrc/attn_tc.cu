@@ -170,15 +170,17 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
             load_tile(0, g & 1);
             cp_async_commit();
             for (int t = 0; t < nt; ++t, ++g) {
+                // publish tile t BEFORE gathering tile t + 1: the other stage only frees when P.V(t-1) retires, and a
+                // clock trace showed S(t) waiting ~1500 cycles behind that wait and the issue of the next gathers
+                cp_async_wait<0>();                  // this thread's share of tile t (and Q) has landed
+                fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
+                mbar_arrive(&kv_full[g & 1]);
                 if (t + 1 < nt) {
                     const int s1 = (g + 1) & 1;
                     mbar_wait(&kv_empty[s1], (((g + 1) >> 1) & 1) ^ 1);
                     load_tile(t + 1, s1);
+                    cp_async_commit();
                 }
-                cp_async_commit();
-                cp_async_wait<1>();                  // this thread's share of tile t (and Q) has landed
-                fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
-                mbar_arrive(&kv_full[g & 1]);
             }
         }
     } else if (warp == NSW + 4) {
