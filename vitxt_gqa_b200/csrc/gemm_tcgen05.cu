@@ -23,6 +23,7 @@
 // Tiles are walked n-fastest so the CTAs running concurrently share one A row-block
 // through L2 and A streams from HBM once.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/t2s_b200.h"
 
 namespace t2s {
@@ -62,7 +63,11 @@ struct GemmCfg {
 // MODE >= 0: the epilogue flags (low 5 bits of ep.flags) and "has a residual operand" (bit 5) are compile-time
 // constants -- the hot epilogues of the fusion transformer get their own lean instantiation; MODE < 0: read at run time.
 constexpr int GEMM_MODE_RES = 32;
-template <int BN, int MODE>
+// PAIR: the CTAs of a 2-CTA cluster work on vertically adjacent tiles (rows 2p and 2p + 1 of the same n block) in step.
+// Each loads its own A tile and HALF of the shared W tile, multicast into both CTAs' shared memory, so a k-block costs
+// each SM 32 KB of L2 reads instead of 48 KB; a stage is refilled only when BOTH tensor cores have released it (the
+// MMA commits are multicast to the `empty` barriers of both CTAs).
+template <int BN, int MODE, bool PAIR>
 __global__ void __launch_bounds__(GemmCfg<BN>::THREADS, GemmCfg<BN>::MIN_CTAS)     // 10 warps = 3 on two of the four 16 K-register partitions: 168 registers at most
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, GemmEpi ep, int M, int N, int K, int k_lo_off) {
@@ -80,7 +85,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_n = (N + BN - 1) / BN;
     const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
-    const int tiles = num_m * num_n;
+    // PAIR: "tiles" counts pair tiles (two row blocks x one n block); work item w of this CTA is pair tile
+    // first_tile + w * tile_step, of which it takes row block 2 * (pair tile / num_n) + rank
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const int tiles = (PAIR ? (num_m + 1) / 2 : num_m) * num_n;
+    const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     // k_lo_off > 0: "bf16x3" mode.  A and W hold fp32 values split as bf16 hi|lo (lo at column k_lo_off) and
     // the k loop runs three segments -- hi.hi, hi.lo, lo.hi -- into the same fp32 accumulator (the lo.lo
     // term is below 2^-16 relative and is dropped), giving fp32-class products on the bf16 tensor pipe.
@@ -96,7 +106,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) {
                 mbar_init(&full[s], 1);
-                mbar_init(&empty[s], 1);
+                mbar_init(&empty[s], PAIR ? 2 : 1);
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&tfull[a], 1);
@@ -110,6 +120,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();        // the peer's barriers are initialised before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -117,8 +128,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ------------------------------------------------ TMA producer
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int tile = first_tile; tile < tiles; tile += tile_step) {
+            const int m_blk = PAIR ? 2 * (tile / num_n) + rank : tile / num_n, n_blk = tile % num_n;
             for (int kb = 0; kb < kblocks; ++kb) {
                 if (lane == 0) {
                     const int seg = kb / kseg, kk = (kb - seg * kseg) * GEMM_BK;
@@ -126,7 +137,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                     tma_load_2d(sa, &tmA, &full[stage], kk + (seg == 2 ? k_lo_off : 0), m_blk * GEMM_BM);
-                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kk + (seg == 1 ? k_lo_off : 0), n_blk * BN);
+                    if (PAIR)       // this CTA's half of the W tile (tmB box = BN / 2 rows), to both CTAs
+                        tma_load_2d_multicast(sa + Cfg::A_BYTES + rank * (Cfg::B_BYTES / 2), &tmB, &full[stage],
+                                              kk + (seg == 1 ? k_lo_off : 0), n_blk * BN + rank * (BN / 2), 3);
+                    else
+                        tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kk + (seg == 1 ? k_lo_off : 0), n_blk * BN);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -137,7 +152,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int tile = first_tile; tile < tiles; tile += tile_step) {
             mbar_wait(&tempty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
@@ -153,7 +168,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         // +32 B per K=16 step inside the swizzle atom == +2 in the (addr >> 4) field
                         umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty[stage]);
+                    if (PAIR) umma_commit_multicast(&empty[stage], 3); else umma_commit(&empty[stage]);
                     if (kb == kblocks - 1) umma_commit(&tfull[acc]);
                 }
                 __syncwarp();
@@ -182,8 +197,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int sw = lane & 7;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int tile = first_tile; tile < tiles; tile += tile_step) {
+            const int m_blk = PAIR ? 2 * (tile / num_n) + rank : tile / num_n, n_blk = tile % num_n;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const int row0 = m_blk * GEMM_BM + quarter * 32;
@@ -357,6 +372,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     tc_fence_before();
     __syncthreads();
+    // PAIR: every MMA commit of this CTA has been delivered once its last accumulator was published, and every multicast
+    // load aimed at it has been consumed; the peer may still be behind, so neither leaves before the other is done
+    if (PAIR) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -420,13 +438,13 @@ int num_sms() {
     return n;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool PAIR>
 static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmEpi& ep,
                             int M, int N, int K, int k_lo_off, int sm_cap, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, MODE>,
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, MODE, PAIR>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
@@ -437,21 +455,43 @@ static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const 
     const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
     // T2S_GEMM_SM_CAP: the persistent grid leaves SMs free for latency-bound work on another stream
     const int sms = (sm_cap > 0 && sm_cap < num_sms()) ? sm_cap : num_sms();
+    if (PAIR) {
+        const int pair_tiles = (((M + GEMM_BM - 1) / GEMM_BM + 1) / 2) * ((N + BN - 1) / BN);
+        const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(Cfg::THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, MODE, PAIR>, ta, tb, tc, ep, M, N, K, k_lo_off);
+        if (e != cudaSuccess) {
+            set_error("gemm_bf16_tcgen05 (pair): %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        return launch_status("gemm_bf16_tcgen05 (pair)");
+    }
     const int grid = tiles < sms ? tiles : sms;
-    gemm_bf16_tcgen05_kernel<BN, MODE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, ep, M, N, K, k_lo_off);
+    gemm_bf16_tcgen05_kernel<BN, MODE, PAIR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, ep, M, N, K, k_lo_off);
     return launch_status("gemm_bf16_tcgen05");
 }
 
 // The epilogues of the eval forward (qkv / ptr-net plain, +residual, GELU, fp32 out, fp32 out + fp32 residual,
 // GELU + hi|lo out, hi|lo out) and the GELU' dgrad of the training step are compiled with constant flags for the
 // throughput tiles; everything else (BN = 64 decode tiles, rare combinations) takes the run-time-flag instantiation.
-template <int BN>
+template <int BN, bool PAIR>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmEpi& ep, int M,
                        int N, int K, int k_lo_off, int sm_cap, cudaStream_t st) {
     if (BN >= 128) {
         const int mode = (ep.flags & 31) | (ep.residual ? GEMM_MODE_RES : 0);
 #define T2S_GEMM_MODE_CASE(m) \
-        case (m): return launch_gemm_mode<(BN >= 128 ? BN : 128), (m)>(ta, tb, tc, ep, M, N, K, k_lo_off, sm_cap, st);
+        case (m): return launch_gemm_mode<(BN >= 128 ? BN : 128), (m), PAIR>(ta, tb, tc, ep, M, N, K, k_lo_off, sm_cap, st);
         switch (mode) {
             T2S_GEMM_MODE_CASE(0)
             T2S_GEMM_MODE_CASE(GEMM_MODE_RES)
@@ -466,7 +506,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
         }
 #undef T2S_GEMM_MODE_CASE
     }
-    return launch_gemm_mode<BN, -1>(ta, tb, tc, ep, M, N, K, k_lo_off, sm_cap, st);
+    return launch_gemm_mode<BN, -1, PAIR>(ta, tb, tc, ep, M, N, K, k_lo_off, sm_cap, st);
 }
 
 
@@ -708,7 +748,14 @@ static int gemm_entry(const char* who, bool x3, const void* A, long long lda, co
     CUtensorMap ta, tb;
     int rc = make_tmap_bf16(&ta, A, M, kcols, lda, GEMM_BM);
     if (rc) return rc;
-    rc = make_tmap_bf16(&tb, W, N, kcols, ldw, bn);
+    // CTA pairs for the throughput tile (see the kernel); T2S_GEMM_PAIR=0 in the environment turns them off
+    static int pair_env = -1;
+    if (pair_env < 0) {
+        const char* e = getenv("T2S_GEMM_PAIR");
+        pair_env = (e && e[0] == '0') ? 0 : 1;
+    }
+    const bool pair = pair_env && bn == 256 && M >= 2 * GEMM_BM;
+    rc = make_tmap_bf16(&tb, W, N, kcols, ldw, pair ? bn / 2 : bn);
     if (rc) return rc;
     // C is written by TMA stores of 32-row x 128-byte boxes (clipped to [M, N] / [M, 2N] by the map)
     CUtensorMap tc;
@@ -719,9 +766,10 @@ static int gemm_entry(const char* who, bool x3, const void* A, long long lda, co
     const int k_lo = x3 ? K : 0;
     const int cap = (flags >> T2S_GEMM_SM_CAP_SHIFT) & 0xff;
     switch (bn) {
-        case 256: return launch_gemm<256>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
-        case 128: return launch_gemm<128>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
-        case 64: return launch_gemm<64>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
+        case 256: return pair ? launch_gemm<256, true>(ta, tb, tc, ep, M, N, K, k_lo, cap, st)
+                              : launch_gemm<256, false>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
+        case 128: return launch_gemm<128, false>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
+        case 64: return launch_gemm<64, false>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
         default: set_error("%s: block_n must be 0, 64, 128 or 256", who); return T2S_ERR_ARG;
     }
 }
