@@ -85,6 +85,24 @@ def test_gemm_bf16_epilogues(L, flags, res_kind):
     assert err <= tol, (err, tol)
 
 
+@pytest.mark.parametrize("M,cap", [(5000, 0), (5000, 37), (3 * 128, 2), (66816, 124)])
+def test_gemm_bf16_cta_pairs(L, M, cap):
+    """The 128 x 256 throughput tile runs as 2-CTA clusters (W tile halves multicast into both CTAs): odd numbers of
+    row blocks (the second CTA of the last pair gets an out-of-range tile), odd / tiny SM caps, many tiles per pair."""
+    N, K = 2304, 768
+    A = rnd(M, K, dtype=torch.bfloat16, seed=31)
+    W = rnd(N, K, scale=0.05, dtype=torch.bfloat16, seed=32)
+    bias = rnd(N, seed=33)
+    R = rnd(M, N, dtype=torch.bfloat16, seed=34)
+    C = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.gemm_bf16(P(A), K, P(W), K, P(bias), P(R), N, P(C), N, M, N, K, cap << tlib.GEMM_SM_CAP_SHIFT, 256, stream())
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias + R.float()
+    assert torch.isfinite(C.float()).all(), "unwritten or non-finite outputs"
+    err = (C.float() - ref).abs().max().item()
+    assert err <= 2 ** -8 * ref.abs().max().item() + 1e-3, err
+
+
 def test_gemm_bf16_strided_rows(L):
     """Decoder-step addressing: one row per sample, T rows apart, fp32 output with a wide pitch."""
     B, T, H, V, N = 64, 12, 768, 5000, 5960
