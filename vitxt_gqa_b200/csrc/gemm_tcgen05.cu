@@ -43,20 +43,25 @@ struct GemmEpi {
 };
 
 // BN = 64 is the latency tile of the greedy decode (M = batch rows, a few dozen CTAs per launch, run next to the capped
-// throughput GEMMs of the other stream): 4 epilogue warps (one per TMEM lane quarter), 3 stages and 192 threads, so that
-// TWO CTAs fit one SM (91 KB shared memory, 32 K registers, 128 TMEM columns each) and the SMs the big grids leave
-// free hold twice as many decode tiles.
+// throughput GEMMs of the other stream).  A clock trace of one decode launch (M = 64, K = 768) showed the kernel spending
+// its time on round trips, not on data: with 3 stages a k-block arrived every ~700 cycles (three loads per ~2000-cycle
+// TMA latency) and half of every A stage was zero fill.  So this tile is 64 rows x 64 columns: the A box is 64 rows
+// (8 KB; the M = 128 MMA reads the W tile behind it as rows 64..127, whose accumulator rows are never read), a stage is
+// 16 KB and six of them fit next to a second CTA on the same SM (105 KB shared memory, 192 threads, 128 TMEM columns
+// each).  Epilogue: the two warps that own TMEM lane quarters 0 and 1.
 template <int BN>
 struct GemmCfg {
-    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int BM = BN == 64 ? 64 : GEMM_BM;          // rows of an output tile (and of the A box)
+    static constexpr int A_BYTES = BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 3);
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
     static constexpr int TMEM_COLS = 2 * BN;     // 512 / 256 / 128: powers of two >= 32
     static constexpr int EPI_WARPS = BN == 64 ? 4 : GEMM_EPI_WARPS;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
     static constexpr int MIN_CTAS = BN == 64 ? 2 : 1;
-    static constexpr int STAGING_BYTES = EPI_WARPS * 4096;    // one 32-row x 128-byte box per epilogue warp
+    static constexpr int ROW_WARPS = BM / 32;                 // epilogue warps per column group that own tile rows
+    static constexpr int STAGING_BYTES = (BN == 64 ? 2 : EPI_WARPS) * 4096;    // one 32-row x 128-byte box per active epilogue warp
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -84,7 +89,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_n = (N + BN - 1) / BN;
-    const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
+    const int num_m = (M + Cfg::BM - 1) / Cfg::BM;
     // PAIR: "tiles" counts pair tiles (two row blocks x one n block); work item w of this CTA is pair tile
     // first_tile + w * tile_step, of which it takes row block 2 * (pair tile / num_n) + rank
     const int rank = PAIR ? (int)cluster_ctarank() : 0;
@@ -136,7 +141,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(sa, &tmA, &full[stage], kk + (seg == 2 ? k_lo_off : 0), m_blk * GEMM_BM);
+                    tma_load_2d(sa, &tmA, &full[stage], kk + (seg == 2 ? k_lo_off : 0), m_blk * Cfg::BM);
                     if (PAIR)       // this CTA's half of the W tile (tmB box = BN / 2 rows), to both CTAs
                         tma_load_2d_multicast(sa + Cfg::A_BYTES + rank * (Cfg::B_BYTES / 2), &tmB, &full[stage],
                                               kk + (seg == 1 ? k_lo_off : 0), n_blk * BN + rank * (BN / 2), 3);
@@ -183,7 +188,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
         // BN >= 128: two warps per lane quarter split the columns; BN == 64: four warps take all 64 columns
         constexpr int COLS_PER_WARP = BN / (Cfg::EPI_WARPS / 4);
-        constexpr bool active = true;
+        const bool active = quarter < Cfg::ROW_WARPS;       // BN == 64: TMEM lanes 64..127 hold no tile rows
         const int half = ew >> 2;
         const int fl = MODE >= 0 ? (MODE & 31) : ep.flags;
         const bool has_res = MODE >= 0 ? (MODE & GEMM_MODE_RES) != 0 : ep.residual != nullptr;
@@ -192,16 +197,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const bool res_f32 = fl & T2S_GEMM_RES_F32;
         const bool out_split = fl & T2S_GEMM_OUT_SPLIT;
         const bool dgelu = fl & T2S_GEMM_DGELU;
-        uint8_t* box = staging + ew * 4096;      // this warp's staging box: 32 rows x 128 B, 128B swizzle
+        uint8_t* box = staging + (BN == 64 ? quarter & 1 : ew) * 4096;      // this warp's staging box: 32 rows x 128 B, 128B swizzle
         uint8_t* my_row = box + lane * 128;
         const int sw = lane & 7;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = first_tile; tile < tiles; tile += tile_step) {
             const int m_blk = PAIR ? 2 * (tile / num_n) + rank : tile / num_n, n_blk = tile % num_n;
+            // the bias slice of this warp (first touched here by the whole grid at once) comes in under the main loop
+            if (ep.bias && lane * 32 < COLS_PER_WARP && n_blk * BN + (ew >> 2) * COLS_PER_WARP + lane * 32 < N)
+                prefetch_l1(ep.bias + n_blk * BN + (ew >> 2) * COLS_PER_WARP + lane * 32);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const int row0 = m_blk * GEMM_BM + quarter * 32;
+            const int row0 = m_blk * Cfg::BM + quarter * 32;
             const int row = row0 + lane;
             const bool row_ok = row < M;
             if (active) {
@@ -365,6 +373,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     }
                 }
             }
+            if (!active) {                           // BN == 64: the warps of lane quarters 2 and 3
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -452,9 +465,9 @@ static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const 
         }
         attr_set = true;
     }
-    const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+    const int tiles = ((M + Cfg::BM - 1) / Cfg::BM) * ((N + BN - 1) / BN);
     // T2S_GEMM_SM_CAP: the persistent grid leaves SMs free for latency-bound work on another stream
-    const int sms = (sm_cap > 0 && sm_cap < num_sms()) ? sm_cap : num_sms();
+    const int sms = ((sm_cap > 0 && sm_cap < num_sms()) ? sm_cap : num_sms()) * Cfg::MIN_CTAS;
     if (PAIR) {
         const int pair_tiles = (((M + GEMM_BM - 1) / GEMM_BM + 1) / 2) * ((N + BN - 1) / BN);
         const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
@@ -746,7 +759,7 @@ static int gemm_entry(const char* who, bool x3, const void* A, long long lda, co
     }
     const int kcols = x3 ? 2 * K : K;      // columns the tensor maps may touch
     CUtensorMap ta, tb;
-    int rc = make_tmap_bf16(&ta, A, M, kcols, lda, GEMM_BM);
+    int rc = make_tmap_bf16(&ta, A, M, kcols, lda, bn == 64 ? 64 : GEMM_BM);
     if (rc) return rc;
     // CTA pairs for the throughput tile (see the kernel); T2S_GEMM_PAIR=0 in the environment turns them off
     static int pair_env = -1;
