@@ -56,6 +56,24 @@ def test_soft_accuracy_and_anls_match_the_reference():
     assert M.edit_distance("flaw", "lawn") == 2 and M.edit_distance("same", "same") == 0
 
 
+def test_edit_distance_bit_parallel_equals_the_textbook_recurrence():
+    import random
+
+    def dp(a, b):
+        prev = list(range(len(b) + 1))
+        for i, ca in enumerate(a, 1):
+            cur = [i]
+            for j, cb in enumerate(b, 1):
+                cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+            prev = cur
+        return prev[-1]
+    rng = random.Random(5)
+    for _ in range(1500):
+        a = "".join(rng.choice("abcd '") for _ in range(rng.randint(0, 70)))
+        b = "".join(rng.choice("abcd '") for _ in range(rng.randint(0, 70)))
+        assert M.edit_distance(a, b) == dp(a, b), (a, b)
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_oracle_box_and_temporal_scores_match_the_reference(name):
     g, case = _case(name)

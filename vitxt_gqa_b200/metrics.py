@@ -88,17 +88,35 @@ class EvalAIAnswerProcessor:
 
 
 def edit_distance(a, b):
-    """Levenshtein distance of two sequences: the published algorithm of the absent third-party dependency
-    `editdistance` (unpinned in the reference; imported at m4c_evaluators.py:268)."""
-    if len(a) < len(b):
+    """Levenshtein distance of two sequences: the published definition of the absent third-party dependency
+    `editdistance` (unpinned in the reference; imported at m4c_evaluators.py:268), computed with the bit-parallel
+    recurrence of Myers / Hyyro on python integers (one step per element of the longer sequence)."""
+    if len(a) > len(b):
         a, b = b, a
-    prev = list(range(len(b) + 1))
-    for i, ca in enumerate(a, 1):
-        cur = [i]
-        for j, cb in enumerate(b, 1):
-            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
-        prev = cur
-    return prev[-1]
+    m = len(a)
+    if m == 0:
+        return len(b)
+    full = (1 << m) - 1
+    top = 1 << (m - 1)
+    peq = {}
+    for i, ch in enumerate(a):
+        peq[ch] = peq.get(ch, 0) | (1 << i)
+    pv, mv, score = full, 0, m
+    for ch in b:
+        eq = peq.get(ch, 0)
+        xv = eq | mv
+        xh = (((eq & pv) + pv) ^ pv) | eq
+        ph = mv | (~(xh | pv) & full)
+        mh = pv & xh
+        if ph & top:
+            score += 1
+        elif mh & top:
+            score -= 1
+        ph = ((ph << 1) | 1) & full
+        mh = (mh << 1) & full
+        pv = mh | (~(xv | ph) & full)
+        mv = ph & xv
+    return score
 
 
 class TextVQAAccuracyEvaluator:
@@ -241,7 +259,7 @@ class BatchEval:
 
     def __init__(self, sample_list, model_output):
         self.sample_list, self.out = sample_list, model_output
-        self._answers = self._qa = self._ground = None
+        self._answers = self._qa = self._ground = self._qa_scores = None
 
     # ---- answers
     def answer_ids(self):
@@ -280,6 +298,12 @@ class BatchEval:
                               "gt_answers": decode_object(gts[b])})
             self._qa = preds
         return self._qa
+
+    def qa_soft_scores(self, evaluator):
+        """per-sample soft VQA accuracy of the predictions (shared by textvqa_accuracy and the two GQA metrics)"""
+        if self._qa_scores is None:
+            self._qa_scores = evaluator.eval_pred_list([], self.qa_predictions())[0]
+        return self._qa_scores
 
     # ---- grounding
     def grounding(self):
@@ -359,8 +383,12 @@ class TextVQAAccuracy(BaseMetric):
         self.evaluator = TextVQAAccuracyEvaluator()
 
     def calculate(self, sample_list, model_output, *args, **kwargs):
-        preds = _batch_eval(sample_list, model_output, kwargs).qa_predictions()
-        _, accuracy = self.evaluator.eval_pred_list([], preds)
+        ctx = _batch_eval(sample_list, model_output, kwargs)
+        if isinstance(self.evaluator, TextVQAAccuracyEvaluator):
+            scores = ctx.qa_soft_scores(self.evaluator)
+            accuracy = sum(scores) / len(scores)
+        else:
+            _, accuracy = self.evaluator.eval_pred_list([], ctx.qa_predictions())
         return torch.tensor(accuracy).to(sample_list.context_tokens_enc.device)
 
 
@@ -395,7 +423,7 @@ class _GroundedQAAccuracy(BaseMetric):
     def calculate(self, sample_list, model_output, *args, **kwargs):
         ctx = _batch_eval(sample_list, model_output, kwargs)
         head = ctx.grounding()["head"][self.SLOT].tolist()
-        qa, _ = self.qa_evaluator.eval_pred_list([], ctx.qa_predictions())
+        qa = ctx.qa_soft_scores(self.qa_evaluator)
         both = [1 if head[i] == 1 and qa[i] == 1 else 0 for i in range(len(qa))]
         return torch.tensor(sum(both) / len(both)).to(sample_list.frame_num.device)
 
