@@ -226,6 +226,12 @@ class _FusionModelBase(BaseModel):
         # the decode tail of the forward that last used a set gates its reuse
         self._pipe_slot = 0
         self._slot_done = [None, None]
+        # eval only: the 12 greedy steps are ~310 launches of 3-10 us kernels; enqueued one by one through ctypes
+        # (~15 us of host time each, tensor-map encodes included) the chain is HOST-bound (4.7 ms alone, 8.7 ms next to
+        # the encoder launches).  So the chain is captured once per (workspace, weights) into a CUDA graph and replayed.
+        self.greedy_graph = os.environ.get("T2S_B200_GREEDY_GRAPH", str(self.config.get("b200_greedy_graph", 1))) not in ("0", "False")
+        self._greedy_graphs = {}
+        self._greedy_warm = set()
         self._phases_on = os.environ.get("T2S_B200_PHASES", "0") == "1"
         self._phase_events = []
         # greedy-decode GEMMs (one row per sample) on the weight-streaming kernel instead of the 128-row tcgen05 tile
@@ -954,22 +960,56 @@ class T2S(_FusionModelBase):
             self._decode_rows_multi(L, P, ws, variants, jm, scores_all, B, Le, T, V, O, F, Lt, st)
         else:
             scores_rn = torch.empty(2, B, T, N, device=dev, dtype=torch.float32)
-            scores = {"pos": torch.empty(B, T, N, device=dev, dtype=torch.float32),
-                      "ref": scores_rn[0], "neg": scores_rn[1]}
-            ws["prev"].zero_()
-            ws["prev"][:, 0] = int(self.answer_processor.BOS_IDX)
             forced = self.parity_hooks.get("force_prev_inds")     # test-only teacher forcing of the feedback
             forced = forced.to(dev) if forced is not None else None
+            # graph replay needs fixed addresses: the chain writes a workspace buffer, the result is a copy of it
+            use_graph = self.greedy_graph and forced is None and L.timing is None
+            pos_out = torch.empty(B, T, N, device=dev, dtype=torch.float32)
+            if use_graph:
+                pos_buf = ws.get("scores_pos")
+                if pos_buf is None or pos_buf.shape != (B, T, N):
+                    pos_buf = ws["scores_pos"] = torch.empty(B, T, N, device=dev, dtype=torch.float32)
+            else:
+                pos_buf = pos_out
+            scores = {"pos": pos_out, "ref": scores_rn[0], "neg": scores_rn[1]}
+            ws["prev"].zero_()
+            ws["prev"][:, 0] = int(self.answer_processor.BOS_IDX)
             self._mmt_encoder(L, P, ws, ("pos",), B, Le, st)
             self._mark("enc_pos")
 
             def greedy(stream_handle):   # drives only the `pos` variant (reference t2s.py:353, Q15)
                 for t in range(T):
-                    self._decode_rows(L, P, ws, "pos", jm["pos"], scores["pos"], B, Le, T, V, O, F, Lt, t, 1,
+                    self._decode_rows(L, P, ws, "pos", jm["pos"], pos_buf, B, Le, T, V, O, F, Lt, t, 1,
                                       stream_handle)
-                    L.argmax_feedback(_ptr(scores["pos"]), N, B, T, t, 1, N, _ptr(ws["prev"]), T, None, stream_handle)
+                    L.argmax_feedback(_ptr(pos_buf), N, B, T, t, 1, N, _ptr(ws["prev"]), T, None, stream_handle)
                     if forced is not None and t + 1 < T:
                         ws["prev"][:, t + 1].copy_(forced[:, t + 1])
+
+            def run_greedy(stream):      # `stream` is torch's current stream here
+                if not use_graph:
+                    greedy(stream.cuda_stream)
+                    return
+                gkey = (id(ws), id(P), B, T, V, O)
+                graph = self._greedy_graphs.get(gkey)
+                if graph is None:
+                    if gkey not in self._greedy_warm:       # first forward: eager (one-time attribute calls, lazy init)
+                        self._greedy_warm.add(gkey)
+                        greedy(stream.cuda_stream)
+                        pos_out.copy_(pos_buf)
+                        return
+                    try:
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph):
+                            greedy(torch.cuda.current_stream(dev).cuda_stream)
+                    except RuntimeError as e:       # e.g. another thread touched the CUDA API during the capture
+                        self.greedy_graph = False   # same kernels, launched one by one from now on
+                        self.writer.write("greedy-decode graph capture failed (%s): eager launches" % e, "warning")
+                        greedy(stream.cuda_stream)
+                        pos_out.copy_(pos_buf)
+                        return
+                    self._greedy_graphs[gkey] = graph
+                graph.replay()
+                pos_out.copy_(pos_buf)
 
             if _pipelined:
                 main = torch.cuda.current_stream(dev)
@@ -984,7 +1024,7 @@ class T2S(_FusionModelBase):
                 enc_done.record(main)
                 side.wait_event(pos_ready)
                 with torch.cuda.stream(side):
-                    greedy(side.cuda_stream)
+                    run_greedy(side)
                     self._mark("greedy_side", side)
                     side.wait_event(enc_done)
                     self._decode_rows_multi(L, P, ws, ("ref", "neg"), jm, scores_rn, B, Le, T, V, O, F, Lt,
@@ -1020,11 +1060,11 @@ class T2S(_FusionModelBase):
                 self._mark("enc_ref_neg")
                 side.wait_event(pos_ready)
                 with torch.cuda.stream(side):
-                    greedy(side.cuda_stream)
+                    run_greedy(side)
                     self._mark("greedy_side", side)
                 main.wait_stream(side)
             else:
-                greedy(st)
+                run_greedy(torch.cuda.current_stream(dev))
                 self._mark("greedy")
                 self._mmt_encoder(L, P, ws, ("ref", "neg"), B, Le, st, qkv0=False)
                 self._mark("enc_ref_neg")
