@@ -166,7 +166,9 @@ int t2s_middle_frame_slots(const long long* mid_id, const long long* temporal_id
 /* Ablation variants (models/t2s_wo_sg.py:496-506, models/t2s_wo_tg.py:483-535).  t2s_spatial_select modes: 0 = T2S,
  * 1 = M4C post-hoc, 2 = "w/o SG" (pos = slot mask, neg = 1 - slot mask, ground_box [B, topk * Of, 4] = boxes of the
  * positive slots, `topk` = number of grounded frames, buffer zeroed by the caller), 3 = "w/o TG" (mode 0, both masks
- * also multiplied by the OCR part of joint_mask).  t2s_frame_slots: slot_mask [B, O] = 1 where temporal_id equals one
+ * also multiplied by the OCR part of joint_mask), 4 = T5-ViteVQA post-hoc (models/t5vitevqa.py:396-408: the `topk` OCR
+ * tokens with the largest masked attention over all frames, ground_box [B, topk, 4] in slot order, padding slots zeroed;
+ * joint masks untouched).  t2s_frame_slots: slot_mask [B, O] = 1 where temporal_id equals one
  * of the n_ids ids of the sample (id 0 read as 1).  t2s_frames_from_ocr: frame part of pos / neg joint masks = the
  * first n_pick frames that own a positive / negative OCR slot (fewer: the last frame is set, the reference's index
  * -1), ground_frame [B, n_pick] = positive frame positions, -1 padded; copies the question part from joint_mask. */

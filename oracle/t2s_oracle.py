@@ -443,6 +443,51 @@ def forward_m4c(sd, d, inp, training=False, ln_eps_embed=1e-5, bos_idx=1, return
     return out
 
 
+def posthoc_t5vitevqa(sd, d, inp, txt, txt_mask, frames, ocr):
+    """PostHoc_Attention.forward of the T5-ViteVQA baseline (models/t5vitevqa.py:357-416): the frame_topk * ocr_topk OCR
+    tokens with the largest post-hoc attention over ALL frames; the answer transformer sees the dataset masks."""
+    B = frames.size(0)
+    ocr_mask = inp["ocr_mask"]
+    gq = question_pool(sd, "PostHoc", txt, txt_mask)
+    score = attention_score(gq, ocr, ocr_mask)
+    _, si = torch.sort(score, descending=True, dim=-1, stable=True)
+    topk_mask = torch.zeros_like(score).scatter_(1, si[:, :d.ocr_topk * d.frame_topk], 1)
+    gbox = torch.masked_select(inp["ocr_bbox_coordinates"], topk_mask.unsqueeze(-1).expand(B, -1, 4).bool()).view(B, -1, 4)
+    g_ocr_mask = torch.masked_select(ocr_mask, topk_mask.bool()).view(B, -1)
+    gbox = gbox * g_ocr_mask.unsqueeze(-1).expand(B, -1, 4)
+    return dict(ground_frame=inp["frame_id"], ground_bbox=gbox, obj_mask=inp["frame_mask"], ocr_mask=ocr_mask,
+                debug=dict(global_q=gq, ocr_score=score))
+
+
+def forward_t5vitevqa(sd, d, inp, training=False, ln_eps_embed=1e-5, bos_idx=1, return_debug=False):
+    """T5VITEVQA.forward (models/t5vitevqa.py:151-169): M4C's single-variant answer transformer over the question,
+    all frames (ViT + frame-id embedding) and all OCR tokens (FastText + PHOC + temporal / track ids)."""
+    txt_mask = get_mask(inp["text_len"], inp["text"].size(1))
+    txt = text_bert(sd, d, inp["text"], txt_mask)
+    obj = encode_obj(sd, d, inp, ln_eps_embed)
+    ocr = encode_ocr(sd, d, inp, ln_eps_embed)
+    g = posthoc_t5vitevqa(sd, d, inp, txt, txt_mask, obj, ocr)
+
+    def one_pass(prev):
+        ocr_out, dec_out = mmt(sd, d, txt, txt_mask, obj, g["obj_mask"], ocr, g["ocr_mask"], prev)
+        return forward_output(sd, ocr_out, dec_out, g["ocr_mask"])
+
+    if training:
+        scores = one_pass(inp["train_prev_inds"].clone())
+    else:
+        T = inp["train_prev_inds"].size(1)
+        prev = torch.zeros_like(inp["train_prev_inds"])
+        prev[:, 0] = bos_idx
+        for _ in range(T):
+            scores = one_pass(prev)
+            prev[:, 1:] = scores.argmax(dim=-1)[:, :-1]
+    out = {"pos_scores": scores, "ground_box": g["ground_bbox"], "ground_frame": g["ground_frame"],
+           "frame_topk": torch.tensor(d.frame_topk), "ocr_topk": torch.tensor(d.ocr_topk)}
+    if return_debug:
+        out["debug"] = dict(txt=txt, obj=obj, ocr=ocr, ocr_mask=g["ocr_mask"], **g["debug"])
+    return out
+
+
 # ------------------------------------------------------------------ losses
 def pos_bce_loss(pos_scores, targets, loss_mask):
     """POSBCEWithMaskLoss.forward (modules/losses.py:329-343)."""

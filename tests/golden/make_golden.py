@@ -43,6 +43,9 @@ FIXTURES = {
     # w/o TG selects frame_topk * ocr_topk OCR tokens per frame: 2 < 4 slots here, 6 >= 4 (everything, as in the shipped configs) below
     "t2s_wo_tg_small_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=1, ocr_topk=2, ablation="wo_tg"), 3, 17, 0, "stress", "eval"),
     "t2s_wo_tg_all_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2, ablation="wo_tg"), 3, 18, 0, "stress", "eval"),
+    # T5-ViteVQA baseline (reference models/t5vitevqa.py): single variant over all frames, global post-hoc OCR top-k
+    "t5vitevqa_small_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=2, ocr_topk=3, model="t5vitevqa"), 3, 19, 0, "stress", "eval"),
+    "t5vitevqa_small_train": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=1, ocr_topk=1, model="t5vitevqa"), 3, 20, 0, "stress", "train"),
     "m4c_small_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=1, ocr_topk=1, model="m4c"), 3, 14, 0, "stress", "eval"),
     "m4c_abinet_eval": (dict(frame_topk=1, ocr_topk=1, model="m4c"), 2, 1238, 0, "stress", "eval"),
 }
@@ -95,6 +98,8 @@ def build_reference_model(d, sd):
         from pythia.models.t2s_wo_tg import T2S as Model        # registered as "t2s_wo_tg"
     elif d.model == "t2s":
         from pythia.models.t2s import T2S as Model
+    elif d.model == "t5vitevqa":
+        from pythia.models.t5vitevqa import T5VITEVQA as Model
     else:
         from pythia.models.m4c import M4C as Model
     torch.manual_seed(0)

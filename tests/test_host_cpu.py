@@ -88,12 +88,15 @@ def test_registered_models_and_losses():
     import vitxt_gqa_b200.model  # noqa: F401
     for key in ("t2s", "m4c"):
         assert registry.get_model_class(key) is not None
+    for key in ("t2s_wo_sg", "t2s_wo_tg", "t5vitevqa"):
+        assert registry.get_model_class(key) is not None
     for key in ("pos_bce_loss", "InfoNCE"):
         assert registry.get_loss_class(key) is not None
 
 
 @pytest.mark.parametrize("name,model,topk,w", [("t2s_abinet.yml", "t2s", 5, 1000), ("t2s_clipocr.yml", "t2s", 1, 100),
-                                              ("m4c_abinet.yml", "m4c", None, None)])
+                                              ("m4c_abinet.yml", "m4c", None, None),
+                                              ("t5vitevqa_abinet.yml", "t5vitevqa", 1, None)])
 def test_packaged_configs_load(name, model, topk, w):
     cfg = load_yaml_config(name, {"model_attributes.%s.text_bert_init_from_bert_base" % model: False})
     m = cfg.model_attributes[model]
@@ -103,6 +106,8 @@ def test_packaged_configs_load(name, model, topk, w):
         assert m.obj.mmt_in_dim == 1074 and m.ocr.mmt_in_dim == 1004
         assert m.grounding.frame_topk == topk and m.grounding.frame_num == 64 and m.grounding.ocr_frame_num == 15
         assert [l["weight"] for l in m.losses if l["type"] == "InfoNCE"] == [w]
+    elif model == "t5vitevqa":
+        assert m.obj.mmt_in_dim == 1074 and m.ocr.mmt_in_dim == 1004 and m.grounding.frame_topk == topk
     else:
         assert m.obj.mmt_in_dim == 1024 and m.ocr.mmt_in_dim == 904
 
@@ -122,13 +127,14 @@ def test_sample_list_semantics():
 def _build(d):
     from vitxt_gqa_b200 import model as tmodel
     register_defaults(vocab_size=d.vocab, ocr_max_num=d.ocr)
-    m = (tmodel.T2S if d.model == "t2s" else tmodel.M4C)(ConfigNode(synth.model_config_for_dims(d)))
+    m = {"t2s": tmodel.T2S, "m4c": tmodel.M4C, "t5vitevqa": tmodel.T5ViteVQA}[d.model](
+        ConfigNode(synth.model_config_for_dims(d)))
     m.build()
     m.init_losses_and_metrics()
     return m
 
 
-@pytest.mark.parametrize("kind", ["t2s", "m4c"])
+@pytest.mark.parametrize("kind", ["t2s", "m4c", "t5vitevqa"])
 def test_state_dict_names_and_shapes_match_the_reference(kind):
     """synth.param_shapes is the reference's state_dict (tests/golden/make_golden.py loads it strict into the
     real reference model); ours must be identical, dead weights included."""

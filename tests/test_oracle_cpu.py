@@ -62,6 +62,22 @@ def test_oracle_m4c_matches_reference_golden():
     assert abs(float(bce) - float(z["loss_pos_bce"][0])) <= 1e-5 * max(1.0, abs(float(z["loss_pos_bce"][0])))
 
 
+@pytest.mark.parametrize("fixture", ["t5vitevqa_small_eval", "t5vitevqa_small_train"])
+def test_oracle_t5vitevqa_matches_reference_golden(fixture):
+    """The T5-ViteVQA baseline (reference models/t5vitevqa.py), golden from the real class."""
+    z, meta, d, sd, inp = load_golden(fixture)
+    with torch.no_grad():
+        out = O.forward_t5vitevqa(sd, d, inp, training=meta["mode"] == "train")
+    assert np.array_equal(out["ground_frame"].numpy(), z["ground_frame"])
+    assert np.array_equal(out["ground_box"].numpy(), z["ground_box"])
+    err = np.abs(out["pos_scores"].numpy() - z["pos_scores"]).max()
+    assert err <= FP32_ATOL, err
+    if meta["mode"] != "train":
+        assert np.array_equal(out["pos_scores"].numpy().argmax(-1), z["pos_scores"].argmax(-1))
+    bce = O.pos_bce_loss(out["pos_scores"], inp["targets"], inp["train_loss_mask"])
+    assert abs(float(bce) - float(z["loss_pos_bce"][0])) <= 1e-5 * max(1.0, abs(float(z["loss_pos_bce"][0])))
+
+
 def test_oracle_front_matches_reference_golden_at_baseline_shape():
     """t2s_abinet shapes (F=64, 15 OCR/frame, V=5000): the grounding front end is cheap enough on CPU;
     the full 36-pass decode at this shape is covered on the GPU box and by the dedup schedule below."""

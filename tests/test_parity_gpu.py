@@ -140,6 +140,31 @@ def test_ablation_models_against_reference_golden(fixture):
     assert abs(losses["InfoNCE"] - ref_nce) <= LOSS_RTOL * abs(ref_nce) + 1000.0 * INFO_NCE_ATOL, (losses, ref_nce)
 
 
+@pytest.mark.parametrize("fixture", ["t5vitevqa_small_eval", "t5vitevqa_small_train"])
+def test_t5vitevqa_against_reference_golden(fixture):
+    """The T5-ViteVQA baseline (reference models/t5vitevqa.py, registry key `t5vitevqa`)."""
+    from vitxt_gqa_b200.pythia_api import registry
+    z, meta, d, sd, inp = load_golden(fixture)
+    train = meta["mode"] == "train"
+    model = build_b200_model(d, sd, train=train)
+    assert type(model) is registry.get_model_class("t5vitevqa")
+    sl = sample_list(inp)
+    with torch.no_grad():
+        out = model(sl)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["ground_frame"].cpu().numpy(), z["ground_frame"])
+    assert np.array_equal(out["ground_box"].cpu().numpy(), z["ground_box"])
+    if train:
+        _check_scores(fixture, z["pos_scores"], out["pos_scores"], True)
+    elif _check_eval_scores(fixture, z, out, model, sl, ("pos_scores",)):
+        model.parity_hooks["force_prev_inds"] = reference_prev_inds(z["pos_scores"])
+        with torch.no_grad():
+            out = model(sl)
+        torch.cuda.synchronize()
+    losses = {k_.split("/")[-1]: float(v) for k_, v in out["losses"].items()}
+    assert abs(losses["pos_bce_loss"] - float(z["loss_pos_bce"][0])) <= LOSS_RTOL * abs(float(z["loss_pos_bce"][0]))
+
+
 @pytest.mark.parametrize("fixture", ["m4c_small_eval", "m4c_abinet_eval"])
 def test_m4c_against_reference_golden(fixture):
     z, meta, d, sd, inp = load_golden(fixture)

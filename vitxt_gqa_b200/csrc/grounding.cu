@@ -245,7 +245,7 @@ spatial_select_kernel(const float* __restrict__ sim, int sim_stride, int sim_off
     const int kk = topk < Of ? topk : Of;
     for (int o = tid; o < O; o += blockDim.x) {
         att[o] = sim[(long long)b * sim_stride + sim_off + o];
-        msk[o] = mode != 1 ? slot_mask[(long long)b * O + o] : joint_mask[(long long)b * L + ocr_off + o];
+        msk[o] = (mode != 1 && mode != 4) ? slot_mask[(long long)b * O + o] : joint_mask[(long long)b * L + ocr_off + o];
     }
     __syncthreads();
     masked_attention(att, msk, O, red);
@@ -261,6 +261,29 @@ spatial_select_kernel(const float* __restrict__ sim, int sim_stride, int sim_off
         if (dbg_score) dbg_score[(long long)b * O + o] = pos[o];
     }
     __syncthreads();
+    if (mode == 4) {
+        // T5-ViteVQA post-hoc attention (models/t5vitevqa.py:396-408): the `topk` OCR tokens with the largest score over
+        // ALL frames (stable order: lowest index first among equals); ground_box [B, topk, 4] = their boxes in slot
+        // order, zeroed where the slot is padding.  The joint masks are not touched (the answer transformer sees the
+        // dataset masks).
+        for (int o = tid; o < O; o += blockDim.x) {
+            const float pv = pos[o];
+            int r = 0;
+            for (int j = 0; j < O; ++j) r += (pos[j] > pv) || (pos[j] == pv && j < o);
+            neg[o] = r < topk ? 1.f : 0.f;
+        }
+        __syncthreads();
+        for (int o = tid; o < O; o += blockDim.x) {
+            if (neg[o] == 0.f) continue;
+            int before = 0;
+            for (int j = 0; j < o; ++j) before += neg[j] != 0.f;
+            const float om = msk[o];
+            float4 bx = *reinterpret_cast<const float4*>(boxes + ((long long)b * O + o) * 4);
+            bx.x *= om; bx.y *= om; bx.z *= om; bx.w *= om;
+            *reinterpret_cast<float4*>(ground_box + ((long long)b * topk + before) * 4) = bx;
+        }
+        return;
+    }
     for (int o = tid; o < O; o += blockDim.x) {
         const int f = o / Of, i = o % Of, base = f * Of;
         const float pv = pos[o], nv = neg[o];

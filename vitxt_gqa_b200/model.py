@@ -139,11 +139,13 @@ class GroundingModule(nn.Module):    # reference t2s.py:434-451 (frame_attn / en
         self.encoder = _BertEncoder(h, n_enc_layers)
 
 
-class PostHocAttention(nn.Module):   # reference m4c.py:334-346
-    def __init__(self, h):
+class PostHocAttention(nn.Module):   # reference m4c.py:334-346; t5vitevqa.py:334-347 adds the (unused) frame_att
+    def __init__(self, h, frame_att=False):
         super().__init__()
         self.q_linear = nn.Linear(h, h)
         self.self_attn = nn.Linear(h, 1)
+        if frame_att:
+            self.frame_att = _AttentionScore(h)
         self.ocr_att = _AttentionScore(h)
 
 
@@ -660,6 +662,35 @@ class _FusionModelBase(BaseModel):
         L.ptr_score(_ptr(ws["qd"]), H, B, T, t0, nq, ws["keyp"][v].data_ptr() + ocr_row0 * H * 2, Le * H, H, O, H,
                     jm.data_ptr() + ocr_row0 * 4, Le, _ptr(scores), N, V, st)
 
+    def _run_greedy(self, greedy, use_graph, gkey, pos_buf, pos_out, stream, dev):
+        """Run the greedy-decode launch chain `greedy(stream_handle)` on torch's current stream `stream`: eagerly, or --
+        from the third forward with the same workspace and packed weights on -- as one CUDA-graph replay (the chain
+        only touches workspace / weight buffers, whose addresses are fixed; its scores land in `pos_buf` and are
+        copied to this forward's `pos_out`)."""
+        if not use_graph:
+            greedy(stream.cuda_stream)
+            return
+        graph = self._greedy_graphs.get(gkey)
+        if graph is None:
+            if gkey not in self._greedy_warm:       # first forward: eager (one-time attribute calls, lazy init)
+                self._greedy_warm.add(gkey)
+                greedy(stream.cuda_stream)
+                pos_out.copy_(pos_buf)
+                return
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    greedy(torch.cuda.current_stream(dev).cuda_stream)
+            except RuntimeError as e:       # e.g. another thread touched the CUDA API during the capture
+                self.greedy_graph = False   # same kernels, launched one by one from now on
+                self.writer.write("greedy-decode graph capture failed (%s): eager launches" % e, "warning")
+                greedy(stream.cuda_stream)
+                pos_out.copy_(pos_buf)
+                return
+            self._greedy_graphs[gkey] = graph
+        graph.replay()
+        pos_out.copy_(pos_buf)
+
     def _decode_rows_multi(self, L, P, ws, vs, jm, scores, B, Le, T, V, O, n_obj, Lt, st):
         """All T teacher-forced decoder rows of the variants `vs` in ONE pass: the decoder rows share every weight,
         so the dense layers, LayerNorms and both score-head projections run over len(vs)*B*T rows at once; only the
@@ -986,30 +1017,7 @@ class T2S(_FusionModelBase):
                         ws["prev"][:, t + 1].copy_(forced[:, t + 1])
 
             def run_greedy(stream):      # `stream` is torch's current stream here
-                if not use_graph:
-                    greedy(stream.cuda_stream)
-                    return
-                gkey = (id(ws), id(P), B, T, V, O)
-                graph = self._greedy_graphs.get(gkey)
-                if graph is None:
-                    if gkey not in self._greedy_warm:       # first forward: eager (one-time attribute calls, lazy init)
-                        self._greedy_warm.add(gkey)
-                        greedy(stream.cuda_stream)
-                        pos_out.copy_(pos_buf)
-                        return
-                    try:
-                        graph = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(graph):
-                            greedy(torch.cuda.current_stream(dev).cuda_stream)
-                    except RuntimeError as e:       # e.g. another thread touched the CUDA API during the capture
-                        self.greedy_graph = False   # same kernels, launched one by one from now on
-                        self.writer.write("greedy-decode graph capture failed (%s): eager launches" % e, "warning")
-                        greedy(stream.cuda_stream)
-                        pos_out.copy_(pos_buf)
-                        return
-                    self._greedy_graphs[gkey] = graph
-                graph.replay()
-                pos_out.copy_(pos_buf)
+                self._run_greedy(greedy, use_graph, (id(ws), id(P), B, T, V, O), pos_buf, pos_out, stream, dev)
 
             if _pipelined:
                 main = torch.cuda.current_stream(dev)
@@ -1156,12 +1164,105 @@ class M4C(_FusionModelBase):
             ws["prev"][:, 0] = int(self.answer_processor.BOS_IDX)
             forced = self.parity_hooks.get("force_prev_inds")
             forced = forced.to(dev) if forced is not None else None
-            for t in range(T):
-                self._decode_rows(L, P, ws, "pos", ws["jm_pos"], scores, B, Le, T, V, O, 1, Lt, t, 1, st)
-                L.argmax_feedback(_ptr(scores), N, B, T, t, 1, N, _ptr(ws["prev"]), T, None, st)
-                if forced is not None and t + 1 < T:
-                    ws["prev"][:, t + 1].copy_(forced[:, t + 1])
+            use_graph = self.greedy_graph and forced is None and L.timing is None
+            pos_buf = scores
+            if use_graph:
+                pos_buf = ws.get("scores_pos")
+                if pos_buf is None or pos_buf.shape != (B, T, N):
+                    pos_buf = ws["scores_pos"] = torch.empty(B, T, N, device=dev, dtype=torch.float32)
+
+            def greedy(stream_handle):
+                for t in range(T):
+                    self._decode_rows(L, P, ws, "pos", ws["jm_pos"], pos_buf, B, Le, T, V, O, 1, Lt, t, 1, stream_handle)
+                    L.argmax_feedback(_ptr(pos_buf), N, B, T, t, 1, N, _ptr(ws["prev"]), T, None, stream_handle)
+                    if forced is not None and t + 1 < T:
+                        ws["prev"][:, t + 1].copy_(forced[:, t + 1])
+
+            self._run_greedy(greedy, use_graph, (id(ws), id(P), B, T, V, O), pos_buf, scores,
+                             torch.cuda.current_stream(dev), dev)
         return {
             "pos_scores": scores, "ground_box": ground_box, "ground_frame": inp["middel_frame_id"],
+            "frame_topk": _dev_scalar(self.frame_topk, dev), "ocr_topk": _dev_scalar(self.ocr_topk, dev),
+        }
+
+
+# =============================================================================== T5-ViteVQA baseline
+@registry.register_model("t5vitevqa")
+class T5ViteVQA(_FusionModelBase):
+    """The T5-ViteVQA baseline of the reference (pythia/models/t5vitevqa.py, registry key `t5vitevqa`,
+    configs/t5vitevqa_abinet.yml): M4C's single answer transformer over the question, ALL sampled frames (ViT feature +
+    frame-id embedding) and all OCR tokens (FastText + PHOC + temporal / track id embeddings), with a post-hoc attention
+    that reports the frame_topk * ocr_topk OCR boxes the pooled question attends to most.  Same kernels as T2S / M4C."""
+    MODEL = "t5vitevqa"
+
+    def _build_grounding(self):
+        self.PostHoc = PostHocAttention(self.hidden, frame_att=True)
+
+    def forward(self, sample_list):
+        L = _lib.get_lib()
+        inp = self._gather_inputs(sample_list, self._I64 + self._F32)
+        dev = self._device()
+        B, Lt = inp["text"].shape
+        F, Of = self.frame_num, self.ocr_frame_num
+        O = inp["ocr_mask"].shape[1]
+        T = inp["train_prev_inds"].shape[1]
+        V = self.classifier.module.weight.shape[0]
+        if inp["video_feat"].shape[1] != F or O != F * Of:
+            raise ValueError("inputs have %d frames / %d OCR slots but the config says %d x %d"
+                             % (inp["video_feat"].shape[1], O, F, Of))
+        Le, H = Lt + F + O, 768
+        P = self._pack(dev)
+        variants = ("ref",)          # one variant, keyed by the dataset masks (t5vitevqa.py:411-415)
+        ws = self._workspace(B, dev, dict(Lt=Lt, F=F, O=O, T=T, V=V, k_obj_pad=P["k_obj_pad"],
+                                          k_ocr_pad=P["k_ocr_pad"], variants=variants))
+        st = torch.cuda.current_stream(dev).cuda_stream
+        f = P["f32"]
+        L.mask_prep(_ptr(inp["text_len"]), _ptr(inp["frame_mask"]), _ptr(inp["ocr_mask"]), B, Lt, F, O,
+                    _ptr(ws["jm_ref"]), st)
+        L.mask_prep(_ptr(inp["text_len"]), None, None, B, Lt, 0, 0, _ptr(ws["jm_txt"]), st)
+        L.build_keys(_ptr(ws["jm_txt"]), B, Lt, _ptr(ws["keys_txt"]), _ptr(ws["nk_txt"]), Lt, st)
+        L.build_keys(_ptr(ws["jm_ref"]), B, Le, _ptr(ws["keys"]["ref"]), _ptr(ws["nk"]["ref"]), Le, st)
+        self._text_bert(L, P, ws, inp, B, Lt, Le, st)
+        self._encode_obj_ocr(L, P, ws, inp, B, Lt, F, O, Le, st)
+        ws["J1"].copy_(ws["J0"])          # no QTV: the joint buffer feeds the answer transformer directly
+        L.cast_rows_bf16(_ptr(ws["J0"]), H, B * Le, H, _ptr(ws["X16"]), H, 0, 0, 0, st)
+        g = "PostHoc."
+        self._q_linear(L, P, ws, f[g + "q_linear.weight"], f[g + "q_linear.bias"], "q_linear", B, Lt, Le, st)
+        L.question_pool(_ptr(ws["qp"]), B, Lt, H, _ptr(f[g + "self_attn.weight"]), _ptr(f[g + "self_attn.bias"]),
+                        _ptr(ws["jm_ref"]), Le, _ptr(ws["gq"]), st)
+        L.sim_scores(_ptr(ws["gq"]), _ptr(ws["J1"]), Le * H, H, Lt + F, O, H, B, _ptr(ws["sim"]), st)
+        K = min(self.frame_topk * self.ocr_topk, O)
+        ground_box = torch.zeros(B, K, 4, device=dev, dtype=torch.float32)
+        L.spatial_select(_ptr(ws["sim"]), O, 0, None, _ptr(ws["jm_ref"]), B, Le, Lt + F, F, Of, None,
+                         _ptr(inp["ocr_bbox_coordinates"]), K, 4, _ptr(ground_box), None, None, None, st)
+        N = V + O
+        scores = torch.empty(B, T, N, device=dev, dtype=torch.float32)
+        self._mmt_encoder(L, P, ws, variants, B, Le, st)
+        if self.training:
+            ws["prev"].copy_(inp["train_prev_inds"])
+            self._decode_rows(L, P, ws, "ref", ws["jm_ref"], scores, B, Le, T, V, O, F, Lt, 0, T, st)
+        else:
+            ws["prev"].zero_()
+            ws["prev"][:, 0] = int(self.answer_processor.BOS_IDX)
+            forced = self.parity_hooks.get("force_prev_inds")
+            forced = forced.to(dev) if forced is not None else None
+            use_graph = self.greedy_graph and forced is None and L.timing is None
+            pos_buf = scores
+            if use_graph:
+                pos_buf = ws.get("scores_pos")
+                if pos_buf is None or pos_buf.shape != (B, T, N):
+                    pos_buf = ws["scores_pos"] = torch.empty(B, T, N, device=dev, dtype=torch.float32)
+
+            def greedy(stream_handle):
+                for t in range(T):
+                    self._decode_rows(L, P, ws, "ref", ws["jm_ref"], pos_buf, B, Le, T, V, O, F, Lt, t, 1, stream_handle)
+                    L.argmax_feedback(_ptr(pos_buf), N, B, T, t, 1, N, _ptr(ws["prev"]), T, None, stream_handle)
+                    if forced is not None and t + 1 < T:
+                        ws["prev"][:, t + 1].copy_(forced[:, t + 1])
+
+            self._run_greedy(greedy, use_graph, (id(ws), id(P), B, T, V, O), pos_buf, scores,
+                             torch.cuda.current_stream(dev), dev)
+        return {
+            "pos_scores": scores, "ground_box": ground_box, "ground_frame": inp["frame_id"],
             "frame_topk": _dev_scalar(self.frame_topk, dev), "ocr_topk": _dev_scalar(self.ocr_topk, dev),
         }

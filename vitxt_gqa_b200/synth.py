@@ -34,7 +34,7 @@ class Dims:
     mmt_layers: int = 3
     ground_enc_layers: int = 2   # Grounding_Module.encoder: dead weights
     word_vocab: int = 30522
-    model: str = "t2s"           # "t2s" | "m4c"
+    model: str = "t2s"           # "t2s" | "m4c" | "t5vitevqa" (M4C over all frames with T2S's encoders, reference models/t5vitevqa.py)
     ablation: str = ""           # t2s only: "" | "wo_sg" | "wo_tg" (reference models/t2s_wo_sg.py, t2s_wo_tg.py)
 
     @property
@@ -62,12 +62,13 @@ def dims_from_config(model_cfg, vocab=5000, model="t2s"):
 def model_config_for_dims(d: Dims):
     """`model_attributes.<model>` dict for arbitrary dims (stress sweep / small tests)."""
     t2s = d.model == "t2s"
+    ids = d.model != "m4c"
     return {
         "lr_scale_frcn": 0.1, "lr_scale_text_bert": 0.1, "lr_scale_mmt": 1.0,
         "text_bert_init_from_bert_base": False,
         "text_bert": {"num_hidden_layers": d.text_layers},
-        "obj": {"mmt_in_dim": d.vit_dim + (d.id_dim if t2s else 0), "dropout_prob": 0.1},
-        "ocr": {"mmt_in_dim": d.ft_dim + d.phoc_dim + (2 * d.id_dim if t2s else 0), "dropout_prob": 0.1},
+        "obj": {"mmt_in_dim": d.vit_dim + (d.id_dim if ids else 0), "dropout_prob": 0.1},
+        "ocr": {"mmt_in_dim": d.ft_dim + d.phoc_dim + (2 * d.id_dim if ids else 0), "dropout_prob": 0.1},
         "translayers": {"hidden_size": d.hidden, "num_hidden_layers": d.qtv_layers},
         "grounding": {"frame_topk": d.frame_topk, "ocr_topk": d.ocr_topk, "max_ocr_num": d.ocr,
                       "frame_num": d.frames, "ocr_frame_num": d.ocr_per_frame, "hidden_size": d.hidden},
@@ -201,6 +202,7 @@ def param_shapes(d: Dims):
     548-554,636-646,673-687; m4c.py equivalents)."""
     H, I = d.hidden, 4 * d.hidden
     t2s = d.model == "t2s"
+    ids = d.model != "m4c"             # frame / temporal / track id embeddings are part of the encoder inputs
     s = {}
     s["text_bert.embeddings.word_embeddings.weight"] = (d.word_vocab, H)
     s["text_bert.embeddings.position_embeddings.weight"] = (512, H)
@@ -210,8 +212,8 @@ def param_shapes(d: Dims):
     for i in range(d.text_layers):
         s.update(_bert_layer_shapes(f"text_bert.encoder.layer.{i}", H, I))
     s["frame_embeddings.weight"] = (4000, d.id_dim)
-    obj_in = d.vit_dim + (d.id_dim if t2s else 0)
-    ocr_in = d.ft_dim + d.phoc_dim + (2 * d.id_dim if t2s else 0)
+    obj_in = d.vit_dim + (d.id_dim if ids else 0)
+    ocr_in = d.ft_dim + d.phoc_dim + (2 * d.id_dim if ids else 0)
     s["linear_obj_feat_to_mmt_in.weight"] = (H, obj_in)
     s["linear_obj_feat_to_mmt_in.bias"] = (H,)
     s["obj_feat_layer_norm.weight"] = (H,)
@@ -254,9 +256,10 @@ def param_shapes(d: Dims):
         s[f"{g}.q_linear.bias"] = (H,)
         s[f"{g}.self_attn.weight"] = (1, H)
         s[f"{g}.self_attn.bias"] = (1,)
-        for lin in ("linear_q", "linear_k"):
-            s[f"{g}.ocr_att.{lin}.weight"] = (H, H)
-            s[f"{g}.ocr_att.{lin}.bias"] = (H,)
+        for att in (("frame_att", "ocr_att") if d.model == "t5vitevqa" else ("ocr_att",)):
+            for lin in ("linear_q", "linear_k"):
+                s[f"{g}.{att}.{lin}.weight"] = (H, H)
+                s[f"{g}.{att}.{lin}.bias"] = (H,)
     p = "mmt.prev_pred_embeddings"
     s[f"{p}.position_embeddings.weight"] = (100, H)
     s[f"{p}.token_type_embeddings.weight"] = (5, H)
