@@ -488,6 +488,36 @@ def forward_t5vitevqa(sd, d, inp, training=False, ln_eps_embed=1e-5, bos_idx=1, 
     return out
 
 
+def forward_gt_box(sd, d, inp, training=False, ln_eps_embed=1e-5, bos_idx=1):
+    """GTBOX.forward (models/gt_box.py:158-175): the upper-bound model that is GIVEN the annotated frames / OCR boxes.
+    OCR encoder over the annotated fields (gt_box.py:262-288), no QTV, no grounding computation (gt_box.py:474-488:
+    outputs = the annotation, frame_topk / ocr_topk = the literals 64 / 15), one answer-transformer pass masked by
+    frame_mask_embedding / ocr_mask_embedding."""
+    txt_mask = get_mask(inp["text_len"], inp["text"].size(1))
+    txt = text_bert(sd, d, inp["text"], txt_mask)
+    obj = encode_obj(sd, d, inp, ln_eps_embed)
+    gt_inp = dict(inp, temporal_id=inp["ocr_temporal_id"], track_id=inp["ocr_track_id"],
+                  ocr_bbox_coordinates=inp["ocr_bbox_list"])
+    ocr = encode_ocr(sd, d, gt_inp, ln_eps_embed)
+    om, cm = inp["frame_mask_embedding"], inp["ocr_mask_embedding"]
+
+    def one_pass(prev):
+        ocr_out, dec_out = mmt(sd, d, txt, txt_mask, obj, om, ocr, cm, prev)
+        return forward_output(sd, ocr_out, dec_out, cm)
+
+    if training:
+        scores = one_pass(inp["train_prev_inds"].clone())
+    else:
+        T = inp["train_prev_inds"].size(1)
+        prev = torch.zeros_like(inp["train_prev_inds"])
+        prev[:, 0] = bos_idx
+        for _ in range(T):
+            scores = one_pass(prev)
+            prev[:, 1:] = scores.argmax(dim=-1)[:, :-1]
+    return {"pos_scores": scores, "ground_box": inp["ocr_bbox_list"], "ground_frame": inp["frame_list"],
+            "frame_topk": torch.tensor(64), "ocr_topk": torch.tensor(15)}
+
+
 # ------------------------------------------------------------------ losses
 def pos_bce_loss(pos_scores, targets, loss_mask):
     """POSBCEWithMaskLoss.forward (modules/losses.py:329-343)."""

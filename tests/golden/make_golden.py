@@ -46,6 +46,9 @@ FIXTURES = {
     # T5-ViteVQA baseline (reference models/t5vitevqa.py): single variant over all frames, global post-hoc OCR top-k
     "t5vitevqa_small_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=2, ocr_topk=3, model="t5vitevqa"), 3, 19, 0, "stress", "eval"),
     "t5vitevqa_small_train": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=1, ocr_topk=1, model="t5vitevqa"), 3, 20, 0, "stress", "train"),
+    # upper bound with the annotated frames / OCR as input (reference models/gt_box.py)
+    "gt_box_small_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=4, ocr_topk=4, model="gt_box"), 3, 21, 0, "stress", "eval"),
+    "gt_box_small_train": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=4, ocr_topk=4, model="gt_box"), 3, 22, 0, "stress", "train"),
     "m4c_small_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=1, ocr_topk=1, model="m4c"), 3, 14, 0, "stress", "eval"),
     "m4c_abinet_eval": (dict(frame_topk=1, ocr_topk=1, model="m4c"), 2, 1238, 0, "stress", "eval"),
 }
@@ -100,6 +103,8 @@ def build_reference_model(d, sd):
         from pythia.models.t2s import T2S as Model
     elif d.model == "t5vitevqa":
         from pythia.models.t5vitevqa import T5VITEVQA as Model
+    elif d.model == "gt_box":
+        from pythia.models.gt_box import GTBOX as Model
     else:
         from pythia.models.m4c import M4C as Model
     torch.manual_seed(0)

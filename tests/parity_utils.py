@@ -34,7 +34,7 @@ def build_b200_model(d, sd, train=False):
     register_defaults(vocab_size=d.vocab, ocr_max_num=d.ocr)
     cfg = ConfigNode(synth.model_config_for_dims(d))
     cls = {"": tmodel.T2S, "wo_sg": tmodel.T2SWithoutSG, "wo_tg": tmodel.T2SWithoutTG}[d.ablation]
-    m = {"t2s": cls, "m4c": tmodel.M4C, "t5vitevqa": tmodel.T5ViteVQA}[d.model](cfg)
+    m = {"t2s": cls, "m4c": tmodel.M4C, "t5vitevqa": tmodel.T5ViteVQA, "gt_box": tmodel.GTBox}[d.model](cfg)
     m.build()
     m.init_losses_and_metrics()
     m.load_state_dict(sd, strict=True)

@@ -88,7 +88,7 @@ def test_registered_models_and_losses():
     import vitxt_gqa_b200.model  # noqa: F401
     for key in ("t2s", "m4c"):
         assert registry.get_model_class(key) is not None
-    for key in ("t2s_wo_sg", "t2s_wo_tg", "t5vitevqa"):
+    for key in ("t2s_wo_sg", "t2s_wo_tg", "t5vitevqa", "gt_box"):
         assert registry.get_model_class(key) is not None
     for key in ("pos_bce_loss", "InfoNCE"):
         assert registry.get_loss_class(key) is not None
@@ -127,14 +127,14 @@ def test_sample_list_semantics():
 def _build(d):
     from vitxt_gqa_b200 import model as tmodel
     register_defaults(vocab_size=d.vocab, ocr_max_num=d.ocr)
-    m = {"t2s": tmodel.T2S, "m4c": tmodel.M4C, "t5vitevqa": tmodel.T5ViteVQA}[d.model](
+    m = {"t2s": tmodel.T2S, "m4c": tmodel.M4C, "t5vitevqa": tmodel.T5ViteVQA, "gt_box": tmodel.GTBox}[d.model](
         ConfigNode(synth.model_config_for_dims(d)))
     m.build()
     m.init_losses_and_metrics()
     return m
 
 
-@pytest.mark.parametrize("kind", ["t2s", "m4c", "t5vitevqa"])
+@pytest.mark.parametrize("kind", ["t2s", "m4c", "t5vitevqa", "gt_box"])
 def test_state_dict_names_and_shapes_match_the_reference(kind):
     """synth.param_shapes is the reference's state_dict (tests/golden/make_golden.py loads it strict into the
     real reference model); ours must be identical, dead weights included."""

@@ -78,6 +78,20 @@ def test_oracle_t5vitevqa_matches_reference_golden(fixture):
     assert abs(float(bce) - float(z["loss_pos_bce"][0])) <= 1e-5 * max(1.0, abs(float(z["loss_pos_bce"][0])))
 
 
+@pytest.mark.parametrize("fixture", ["gt_box_small_eval", "gt_box_small_train"])
+def test_oracle_gt_box_matches_reference_golden(fixture):
+    """The GT-box upper bound (reference models/gt_box.py), golden from the real class."""
+    z, meta, d, sd, inp = load_golden(fixture)
+    with torch.no_grad():
+        out = O.forward_gt_box(sd, d, inp, training=meta["mode"] == "train")
+    assert np.array_equal(out["ground_frame"].numpy(), z["ground_frame"])
+    assert np.array_equal(out["ground_box"].numpy(), z["ground_box"])
+    assert int(out["frame_topk"]) == int(z["frame_topk"]) == 64 and int(out["ocr_topk"]) == int(z["ocr_topk"]) == 15
+    assert np.abs(out["pos_scores"].numpy() - z["pos_scores"]).max() <= FP32_ATOL
+    if meta["mode"] != "train":
+        assert np.array_equal(out["pos_scores"].numpy().argmax(-1), z["pos_scores"].argmax(-1))
+
+
 def test_oracle_front_matches_reference_golden_at_baseline_shape():
     """t2s_abinet shapes (F=64, 15 OCR/frame, V=5000): the grounding front end is cheap enough on CPU;
     the full 36-pass decode at this shape is covered on the GPU box and by the dedup schedule below."""

@@ -140,20 +140,23 @@ def test_ablation_models_against_reference_golden(fixture):
     assert abs(losses["InfoNCE"] - ref_nce) <= LOSS_RTOL * abs(ref_nce) + 1000.0 * INFO_NCE_ATOL, (losses, ref_nce)
 
 
-@pytest.mark.parametrize("fixture", ["t5vitevqa_small_eval", "t5vitevqa_small_train"])
-def test_t5vitevqa_against_reference_golden(fixture):
-    """The T5-ViteVQA baseline (reference models/t5vitevqa.py, registry key `t5vitevqa`)."""
+@pytest.mark.parametrize("fixture", ["t5vitevqa_small_eval", "t5vitevqa_small_train", "gt_box_small_eval",
+                                     "gt_box_small_train"])
+def test_single_variant_baselines_against_reference_golden(fixture):
+    """The T5-ViteVQA baseline and the GT-box upper bound (reference models/t5vitevqa.py, gt_box.py; registry keys
+    `t5vitevqa`, `gt_box`)."""
     from vitxt_gqa_b200.pythia_api import registry
     z, meta, d, sd, inp = load_golden(fixture)
     train = meta["mode"] == "train"
     model = build_b200_model(d, sd, train=train)
-    assert type(model) is registry.get_model_class("t5vitevqa")
+    assert type(model) is registry.get_model_class(d.model)
     sl = sample_list(inp)
     with torch.no_grad():
         out = model(sl)
     torch.cuda.synchronize()
     assert np.array_equal(out["ground_frame"].cpu().numpy(), z["ground_frame"])
     assert np.array_equal(out["ground_box"].cpu().numpy(), z["ground_box"])
+    assert int(out["frame_topk"]) == int(z["frame_topk"]) and int(out["ocr_topk"]) == int(z["ocr_topk"])
     if train:
         _check_scores(fixture, z["pos_scores"], out["pos_scores"], True)
     elif _check_eval_scores(fixture, z, out, model, sl, ("pos_scores",)):

@@ -748,9 +748,10 @@ class _FusionModelBase(BaseModel):
 
     # ---------------------------------------------------------------- input plumbing
     _I64 = ("text", "text_len", "frame_id", "frame_mask", "temporal_id", "track_id", "ocr_mask", "train_prev_inds",
-            "middel_frame_id", "middel_frame_idx")
+            "middel_frame_id", "middel_frame_idx",
+            "ocr_temporal_id", "ocr_track_id", "ocr_mask_embedding", "frame_mask_embedding", "frame_list")
     _F32 = ("video_feat", "context_feature_0", "context_feature_1", "ocr_bbox_coordinates", "mid_img_feat",
-            "gumbel_frame", "gumbel_ocr")
+            "gumbel_frame", "gumbel_ocr", "ocr_bbox_list")
 
     def _device(self):
         return next(self.parameters()).device
@@ -1265,4 +1266,81 @@ class T5ViteVQA(_FusionModelBase):
         return {
             "pos_scores": scores, "ground_box": ground_box, "ground_frame": inp["frame_id"],
             "frame_topk": _dev_scalar(self.frame_topk, dev), "ocr_topk": _dev_scalar(self.ocr_topk, dev),
+        }
+
+
+# =============================================================================== GT-box upper bound
+@registry.register_model("gt_box")
+class GTBox(_FusionModelBase):
+    """The upper-bound model of the reference that is GIVEN the annotated frames and OCR boxes
+    (pythia/models/gt_box.py, registry key `gt_box`, configs/gt_box_clipocr.yml): T2S's text / frame / OCR encoders over
+    the annotated OCR fields (`ocr_temporal_id`, `ocr_track_id`, `ocr_bbox_list`), no QTV, no grounding computation
+    (outputs = the annotation; `frame_topk` / `ocr_topk` are the literals 64 / 15 of gt_box.py:480-481) and one
+    answer-transformer pass masked by `frame_mask_embedding` / `ocr_mask_embedding`.  Every T2S module still exists
+    (TransLayer, Grounding_Module) plus a never-called LSTM, so that checkpoints interchange."""
+    MODEL = "gt_box"
+
+    def _build_grounding(self):
+        cfg, h = self.config, self.hidden
+        self.spatial_enhance = nn.LSTM(num_layers=2, input_size=300, hidden_size=300, batch_first=True,
+                                       bidirectional=True)        # dead weights (gt_box.py:104)
+        self.TransLayer = QTV(h, int(cfg.translayers.num_hidden_layers))
+        self.Grounding_Module = GroundingModule(h, int(cfg.encoder.num_hidden_layers))
+
+    def forward(self, sample_list):
+        L = _lib.get_lib()
+        inp = self._gather_inputs(sample_list, self._I64 + self._F32)
+        dev = self._device()
+        B, Lt = inp["text"].shape
+        F = inp["video_feat"].shape[1]
+        O = inp["ocr_mask_embedding"].shape[1]
+        T = inp["train_prev_inds"].shape[1]
+        V = self.classifier.module.weight.shape[0]
+        Le, H = Lt + F + O, 768
+        P = self._pack(dev)
+        variants = ("pos",)
+        ws = self._workspace(B, dev, dict(Lt=Lt, F=F, O=O, T=T, V=V, k_obj_pad=P["k_obj_pad"],
+                                          k_ocr_pad=P["k_ocr_pad"], variants=variants))
+        st = torch.cuda.current_stream(dev).cuda_stream
+        L.mask_prep(_ptr(inp["text_len"]), _ptr(inp["frame_mask_embedding"]), _ptr(inp["ocr_mask_embedding"]), B, Lt, F, O,
+                    _ptr(ws["jm_pos"]), st)
+        L.mask_prep(_ptr(inp["text_len"]), None, None, B, Lt, 0, 0, _ptr(ws["jm_txt"]), st)
+        L.build_keys(_ptr(ws["jm_txt"]), B, Lt, _ptr(ws["keys_txt"]), _ptr(ws["nk_txt"]), Lt, st)
+        L.build_keys(_ptr(ws["jm_pos"]), B, Le, _ptr(ws["keys"]["pos"]), _ptr(ws["nk"]["pos"]), Le, st)
+        self._text_bert(L, P, ws, inp, B, Lt, Le, st)
+        gt_inp = dict(inp, temporal_id=inp["ocr_temporal_id"], track_id=inp["ocr_track_id"],
+                      ocr_bbox_coordinates=inp["ocr_bbox_list"])
+        self._encode_obj_ocr(L, P, ws, gt_inp, B, Lt, F, O, Le, st)
+        ws["J1"].copy_(ws["J0"])          # no QTV (gt_box.py:298-299)
+        L.cast_rows_bf16(_ptr(ws["J0"]), H, B * Le, H, _ptr(ws["X16"]), H, 0, 0, 0, st)
+        N = V + O
+        scores = torch.empty(B, T, N, device=dev, dtype=torch.float32)
+        self._mmt_encoder(L, P, ws, variants, B, Le, st)
+        if self.training:
+            ws["prev"].copy_(inp["train_prev_inds"])
+            self._decode_rows(L, P, ws, "pos", ws["jm_pos"], scores, B, Le, T, V, O, F, Lt, 0, T, st)
+        else:
+            ws["prev"].zero_()
+            ws["prev"][:, 0] = int(self.answer_processor.BOS_IDX)
+            forced = self.parity_hooks.get("force_prev_inds")
+            forced = forced.to(dev) if forced is not None else None
+            use_graph = self.greedy_graph and forced is None and L.timing is None
+            pos_buf = scores
+            if use_graph:
+                pos_buf = ws.get("scores_pos")
+                if pos_buf is None or pos_buf.shape != (B, T, N):
+                    pos_buf = ws["scores_pos"] = torch.empty(B, T, N, device=dev, dtype=torch.float32)
+
+            def greedy(stream_handle):
+                for t in range(T):
+                    self._decode_rows(L, P, ws, "pos", ws["jm_pos"], pos_buf, B, Le, T, V, O, F, Lt, t, 1, stream_handle)
+                    L.argmax_feedback(_ptr(pos_buf), N, B, T, t, 1, N, _ptr(ws["prev"]), T, None, stream_handle)
+                    if forced is not None and t + 1 < T:
+                        ws["prev"][:, t + 1].copy_(forced[:, t + 1])
+
+            self._run_greedy(greedy, use_graph, (id(ws), id(P), B, T, V, O), pos_buf, scores,
+                             torch.cuda.current_stream(dev), dev)
+        return {
+            "pos_scores": scores, "ground_box": inp["ocr_bbox_list"], "ground_frame": inp["frame_list"],
+            "frame_topk": _dev_scalar(64, dev), "ocr_topk": _dev_scalar(15, dev),
         }

@@ -34,7 +34,7 @@ class Dims:
     mmt_layers: int = 3
     ground_enc_layers: int = 2   # Grounding_Module.encoder: dead weights
     word_vocab: int = 30522
-    model: str = "t2s"           # "t2s" | "m4c" | "t5vitevqa" (M4C over all frames with T2S's encoders, reference models/t5vitevqa.py)
+    model: str = "t2s"           # "t2s" | "m4c" | "t5vitevqa" (M4C over all frames with T2S's encoders, reference models/t5vitevqa.py) | "gt_box" (annotated OCR as input, reference models/gt_box.py)
     ablation: str = ""           # t2s only: "" | "wo_sg" | "wo_tg" (reference models/t2s_wo_sg.py, t2s_wo_tg.py)
 
     @property
@@ -145,6 +145,21 @@ def make_inputs(d: Dims, batch: int, seed: int = 1234, full_frames: bool = False
     targets.scatter_(2, tgt_idx, 1.0)
     out["targets"] = targets * out["train_loss_mask"][:, :, None]
 
+    if d.model == "gt_box":
+        # the dataset's human-annotated OCR fields (gt_box.py:268-274,478-486): own ids / boxes / masks, so that reading
+        # the detector's fields instead would show
+        keep = torch.rand(B, O, generator=g) < 0.6
+        gt_valid = ovalid & keep
+        out["ocr_mask_embedding"] = gt_valid.to(torch.int64)
+        out["ocr_temporal_id"] = out["temporal_id"] * gt_valid
+        out["ocr_track_id"] = randint(1, 200, (B, O)) * gt_valid
+        c2 = torch.rand(B, O, 2, 2, generator=g).sort(dim=2).values
+        box2 = torch.stack([c2[:, :, 0, 0], c2[:, :, 0, 1], c2[:, :, 1, 0], c2[:, :, 1, 1]], -1)
+        out["ocr_bbox_list"] = box2 * gt_valid[:, :, None]
+        fkeep = torch.rand(B, F, generator=g) < 0.7
+        fkeep[:, 0] = True
+        out["frame_mask_embedding"] = (fvalid & fkeep).to(torch.int64)
+        out["frame_list"] = out["frame_id"] * out["frame_mask_embedding"]
     if d.model == "m4c":
         mid = (n_frames - 1) // 2
         out["middel_frame_idx"] = (mid + 1)[:, None]                      # 1-based position
@@ -161,7 +176,9 @@ def make_inputs(d: Dims, batch: int, seed: int = 1234, full_frames: bool = False
 SAMPLE_FIELDS = ("text", "text_len", "video_feat", "frame_id", "frame_mask", "context_feature_0",
                  "context_feature_1", "temporal_id", "track_id", "ocr_bbox_coordinates", "ocr_mask",
                  "train_prev_inds", "targets", "train_loss_mask",
-                 "mid_img_feat", "middel_frame_id", "middel_frame_idx")
+                 "mid_img_feat", "middel_frame_id", "middel_frame_idx",
+                 "ocr_mask_embedding", "ocr_temporal_id", "ocr_track_id", "ocr_bbox_list", "frame_mask_embedding",
+                 "frame_list")
 
 
 def to_sample_list(inputs, sample_list_cls, with_noise=True, dataset_name="vtextgqa", dataset_type="val"):
@@ -201,7 +218,7 @@ def param_shapes(d: Dims):
     (SURVEY 8b 'Parameter naming'; reference t2s.py:43-151,378-451,521-527,
     548-554,636-646,673-687; m4c.py equivalents)."""
     H, I = d.hidden, 4 * d.hidden
-    t2s = d.model == "t2s"
+    t2s = d.model in ("t2s", "gt_box")      # gt_box keeps every T2S module (most of them unused) ...
     ids = d.model != "m4c"             # frame / temporal / track id embeddings are part of the encoder inputs
     s = {}
     s["text_bert.embeddings.word_embeddings.weight"] = (d.word_vocab, H)
@@ -232,6 +249,14 @@ def param_shapes(d: Dims):
     s["ocr_feat_layer_norm.bias"] = (H,)
     s["ocr_bbox_layer_norm.weight"] = (H,)
     s["ocr_bbox_layer_norm.bias"] = (H,)
+    if d.model == "gt_box":                 # ... plus an LSTM that forward never calls (gt_box.py:104)
+        for layer in range(2):
+            for sfx in ("", "_reverse"):
+                i = 300 if layer == 0 else 600
+                s[f"spatial_enhance.weight_ih_l{layer}{sfx}"] = (1200, i)
+                s[f"spatial_enhance.weight_hh_l{layer}{sfx}"] = (1200, 300)
+                s[f"spatial_enhance.bias_ih_l{layer}{sfx}"] = (1200,)
+                s[f"spatial_enhance.bias_hh_l{layer}{sfx}"] = (1200,)
     if t2s:
         for i in range(d.qtv_layers):
             s.update(_bert_layer_shapes(f"TransLayer.encoder.layer.{i}", H, I))
@@ -298,7 +323,9 @@ def make_state_dict(d: Dims, seed: int = 0, variant: str = "default"):
     for k, shape in shapes.items():
         is_ln = "LayerNorm" in k or "layer_norm" in k
         in_bert = k.startswith(_BERT_PREFIXES)
-        if is_ln:
+        if k.startswith("spatial_enhance."):        # nn.LSTM default: U(+-1/sqrt(hidden_size)) for every tensor
+            t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(300)
+        elif is_ln:
             base = torch.ones(shape) if k.endswith("weight") else torch.zeros(shape)
             if variant == "stress":
                 base = base + 0.1 * torch.randn(shape, generator=g)
