@@ -491,3 +491,76 @@ def test_training_step_fused_adam_matches_torch_adam():
     m.eval()
     with torch.no_grad():
         m(sl)
+
+
+def test_lr_schedule_is_the_references():
+    """general.py:20-30 with the training_parameters of configs/t2s_clipocr.yml."""
+    from vitxt_gqa_b200.train import lr_lambda_update
+    cfg = {"training_parameters": {"use_warmup": True, "warmup_iterations": 1000, "warmup_factor": 0.2,
+                                   "lr_steps": [10000, 20000], "lr_ratio": 0.1}}
+    assert lr_lambda_update(0, cfg) == pytest.approx(0.2) and lr_lambda_update(500, cfg) == pytest.approx(0.6)
+    assert lr_lambda_update(1000, cfg) == pytest.approx(1.0) and lr_lambda_update(1001, cfg) == 1.0
+    assert lr_lambda_update(10000, cfg) == pytest.approx(0.1) and lr_lambda_update(25000, cfg) == pytest.approx(0.01)
+
+
+def test_optimizer_state_and_checkpoint_interchange_with_torch_adam(tmp_path):
+    """The fused Adam's state exported in torch.optim.Adam's format (what the reference's checkpoint stores,
+    checkpoint.py:226-232): a torch Adam that loads it takes the SAME next step as the engine, and a checkpoint
+    round trip restores parameters, moments and step count."""
+    from parity_utils import build_b200_model, sample_list
+    from vitxt_gqa_b200 import synth
+    from vitxt_gqa_b200.pythia_api import ConfigNode
+    d = synth.Dims(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2)
+    m = build_b200_model(d, synth.make_state_dict(d, seed=0, variant="stress"), train=True)
+    cfg = ConfigNode({"optimizer_attributes": {"params": {"lr": 1e-4}}})
+    eng = m.train_engine()
+
+    def fwd_bwd(seed):
+        for p in m.parameters():
+            p.grad = None
+        out = m(sample_list(synth.make_inputs(d, 2, seed=seed, train=True)))
+        sum(out["losses"].values()).backward()
+
+    for it in range(2):                       # two engine steps build non-trivial moments
+        fwd_bwd(30 + it)
+        eng.step(lr=1e-4, max_grad_l2_norm=0.25)
+    sd = eng.optimizer_state_dict(cfg)
+    assert len(sd["state"]) == len(eng.live_names) and all(int(s["step"]) == 2 for s in sd["state"].values())
+    path = str(tmp_path / "ckpt.pth")
+    eng.save_checkpoint(path, cfg, best_iteration=2, best_metric_value=0.5)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"model", "optimizer", "best_iteration", "best_metric_value", "config"}
+    assert set(ck["model"]) == set(m.state_dict())
+
+    # third step, two ways from the same parameters / gradients / moments
+    fwd_bwd(40)
+    p0 = {n: p.detach().clone() for n, p in m.named_parameters()}
+    g0 = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+    opt = torch.optim.Adam(m.get_optimizer_parameters(cfg), lr=1e-4, eps=1e-8)
+    opt.load_state_dict(sd)
+    torch.nn.utils.clip_grad_norm_([p for p in m.parameters() if p.grad is not None], 0.25)
+    opt.step()
+    torch.cuda.synchronize()
+    p_torch = {n: p.detach().clone() for n, p in m.named_parameters()}
+    with torch.no_grad():                     # back to the state before the step
+        for n, p in m.named_parameters():
+            p.copy_(p0[n])
+            if n in g0:
+                p.grad.copy_(g0[n])
+    eng.step(lr=1e-4, max_grad_l2_norm=0.25)
+    torch.cuda.synchronize()
+    for n, p in m.named_parameters():
+        assert (p.detach() - p_torch[n]).abs().max().item() <= 1e-6, n
+
+    # checkpoint round trip into a fresh model / engine
+    m2 = build_b200_model(d, synth.make_state_dict(d, seed=3, variant="default"), train=True)
+    eng2 = m2.train_engine()
+    eng2.load_checkpoint(path, cfg)
+    assert eng2.step_count == 2
+    for (n, a), (_, b) in zip(m2.state_dict().items(), ck["model"].items()):
+        assert torch.equal(a.cpu(), b), n
+    sd2 = eng2.optimizer_state_dict(cfg)          # (torch's load_state_dict aliased `sd`'s tensors: compare with the file)
+    assert set(sd2["state"]) == set(ck["optimizer"]["state"])
+    for i, s in ck["optimizer"]["state"].items():
+        assert torch.equal(sd2["state"][i]["exp_avg"].cpu(), s["exp_avg"].cpu())
+        assert torch.equal(sd2["state"][i]["exp_avg_sq"].cpu(), s["exp_avg_sq"].cpu())

@@ -43,6 +43,18 @@ def _ru(x, m):
     return (x + m - 1) // m * m
 
 
+def lr_lambda_update(i_iter, cfg):
+    """The reference's learning-rate multiplier (pythia/utils/general.py:20-30): linear warm-up from `warmup_factor`
+    to 1 over `warmup_iterations`, then `lr_ratio` ** (number of `lr_steps` passed).  `TrainEngine.step(lr=base_lr *
+    lr_lambda_update(i, cfg), ...)` is what `LambdaLR` does for the reference's optimizer."""
+    from bisect import bisect
+    tp = cfg["training_parameters"]
+    if tp["use_warmup"] is True and i_iter <= tp["warmup_iterations"]:
+        alpha = float(i_iter) / float(tp["warmup_iterations"])
+        return tp["warmup_factor"] * (1.0 - alpha) + alpha
+    return pow(tp["lr_ratio"], bisect(tp["lr_steps"], i_iter))
+
+
 class _T2STrainFn(torch.autograd.Function):
     """forward(engine, inputs, *live_params) -> (ref_scores, pos_scores, neg_scores)."""
 
@@ -605,3 +617,70 @@ class TrainEngine:
         self.model._packed = None      # weights changed: bf16 / split operand copies are stale
         self._wt = None
         return self._sumsq
+
+    # ------------------------------------------------------------------ optimizer state / checkpoints in the reference's format
+    def _adam_template(self, config, lr):
+        """An (empty-state) torch.optim.Adam over the reference's parameter groups (t2s.py:356-376) -- used only as the
+        source of a state_dict layout that `Optimizer.load_state_dict` of this torch accepts."""
+        groups = self.model.get_optimizer_parameters(config)
+        return groups, torch.optim.Adam(groups, lr=lr, eps=1e-8, weight_decay=0)
+
+    def optimizer_state_dict(self, config, lr=None):
+        """The fused Adam state as a `torch.optim.Adam.state_dict()` over `model.get_optimizer_parameters(config)`:
+        what the reference's checkpoint stores under "optimizer" (pythia/utils/checkpoint.py:226-232) and restores
+        with `optimizer.load_state_dict` (checkpoint.py:114), so a run can move between the two optimizers."""
+        lr = float(config.optimizer_attributes.params.lr) if lr is None else lr
+        groups, opt = self._adam_template(config, lr)
+        sd = opt.state_dict()
+        name_of = {id(p): n for n, p in self.named.items()}
+        live = set(self.live_names)
+        idx = 0
+        for g in groups:
+            for p in g["params"]:
+                n = name_of[id(p)]
+                if n in live and self.step_count > 0:
+                    o = self.offsets[n]
+                    sd["state"][idx] = {"step": torch.tensor(float(self.step_count)),
+                                        "exp_avg": self.adam_m[o:o + p.numel()].view_as(p).clone(),
+                                        "exp_avg_sq": self.adam_v[o:o + p.numel()].view_as(p).clone()}
+                idx += 1
+        return sd
+
+    def load_optimizer_state_dict(self, sd, config):
+        """Inverse of `optimizer_state_dict` (also accepts the state of a torch.optim.Adam the reference trained)."""
+        groups = self.model.get_optimizer_parameters(config)
+        name_of = {id(p): n for n, p in self.named.items()}
+        self.adam_m.zero_()
+        self.adam_v.zero_()
+        steps = set()
+        idx = 0
+        for g in groups:
+            for p in g["params"]:
+                st = sd["state"].get(idx)
+                if st is not None:
+                    o = self.offsets[name_of[id(p)]]
+                    self.adam_m[o:o + p.numel()].copy_(st["exp_avg"].reshape(-1))
+                    self.adam_v[o:o + p.numel()].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.add(int(st["step"]))
+                idx += 1
+        if len(steps) > 1:
+            raise ValueError("the fused Adam keeps one step count; the state has %s" % sorted(steps))
+        self.step_count = steps.pop() if steps else 0
+
+    def save_checkpoint(self, path, config, best_iteration=0, best_metric_value=None, lr=None):
+        """Same keys as the reference's checkpoint file (checkpoint.py:226-240, minus the git metadata)."""
+        torch.save({"model": self.model.state_dict(), "optimizer": self.optimizer_state_dict(config, lr),
+                    "best_iteration": best_iteration, "best_metric_value": best_metric_value, "config": config}, path)
+
+    def load_checkpoint(self, path, config):
+        """Restore model + optimizer from a checkpoint in the reference's format (checkpoint.py:98-116; a DataParallel
+        "module." prefix is stripped like there)."""
+        ckpt = torch.load(path, map_location=self.dev, weights_only=False)
+        model_sd = ckpt["model"] if "model" in ckpt else ckpt
+        model_sd = {(k[7:] if k.startswith("module.") else k): v for k, v in model_sd.items()}
+        self.model.load_state_dict(model_sd)           # copies into the views of the flat buffer
+        if "optimizer" in ckpt:
+            self.load_optimizer_state_dict(ckpt["optimizer"], config)
+        self.model._packed = None
+        self._wt = None
+        return ckpt
