@@ -670,25 +670,30 @@ class _FusionModelBase(BaseModel):
         if not use_graph:
             greedy(stream.cuda_stream)
             return
-        graph = self._greedy_graphs.get(gkey)
-        if graph is None:
+        lib = _lib.get_lib()
+        entry = self._greedy_graphs.get(gkey)
+        if entry is None:
             if gkey not in self._greedy_warm:       # first forward: eager (one-time attribute calls, lazy init)
                 self._greedy_warm.add(gkey)
                 greedy(stream.cuda_stream)
                 pos_out.copy_(pos_buf)
                 return
+            n0 = lib.launches
             try:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     greedy(torch.cuda.current_stream(dev).cuda_stream)
             except RuntimeError as e:       # e.g. another thread touched the CUDA API during the capture
+                lib.launches = n0
                 self.greedy_graph = False   # same kernels, launched one by one from now on
                 self.writer.write("greedy-decode graph capture failed (%s): eager launches" % e, "warning")
                 greedy(stream.cuda_stream)
                 pos_out.copy_(pos_buf)
                 return
-            self._greedy_graphs[gkey] = graph
-        graph.replay()
+            entry = self._greedy_graphs[gkey] = (graph, lib.launches - n0)
+            lib.launches = n0               # recorded, not run: the replay below is what executes (and counts) them
+        entry[0].replay()
+        lib.launches += entry[1]            # kernels of ours inside the replayed graph (bench.py's gpu_launches)
         pos_out.copy_(pos_buf)
 
     def _decode_rows_multi(self, L, P, ws, vs, jm, scores, B, Le, T, V, O, n_obj, Lt, st):
