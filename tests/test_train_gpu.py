@@ -564,3 +564,59 @@ def test_optimizer_state_and_checkpoint_interchange_with_torch_adam(tmp_path):
     for i, s in ck["optimizer"]["state"].items():
         assert torch.equal(sd2["state"][i]["exp_avg"].cpu(), s["exp_avg"].cpu())
         assert torch.equal(sd2["state"][i]["exp_avg_sq"].cpu(), s["exp_avg_sq"].cpu())
+
+
+@pytest.mark.parametrize("kind", ["m4c", "t5vitevqa", "gt_box"])
+def test_single_variant_training_gradients_match_oracle_autograd(kind):
+    """The training step of the single-variant models (M4C, the T5-ViteVQA baseline, the GT-box upper bound): one
+    answer-transformer variant straight on the encoders' output, masked BCE only; gradients against autograd through the
+    oracle (whose forward is pinned to the real classes' goldens)."""
+    from oracle import t2s_oracle as O
+    from parity_utils import build_b200_model, sample_list
+    from vitxt_gqa_b200 import synth
+    d = synth.Dims(frames=8, ocr_per_frame=4, vocab=200, frame_topk=1 if kind == "m4c" else 2, ocr_topk=1 if kind == "m4c" else 3,
+                   model=kind)
+    sd = synth.make_state_dict(d, seed=0, variant="stress")
+    inp = synth.make_inputs(d, 3, seed=13, train=True)
+    sdg = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    fwd = {"m4c": O.forward_m4c, "t5vitevqa": O.forward_t5vitevqa, "gt_box": O.forward_gt_box}[kind]
+    ref_out = fwd(sdg, d, inp, training=True)
+    bce = O.pos_bce_loss(ref_out["pos_scores"], inp["targets"], inp["train_loss_mask"])
+    bce.backward()
+    ref_g = {k: v.grad for k, v in sdg.items() if v.requires_grad}
+    m = build_b200_model(d, sd, train=True)
+    out = m(sample_list(inp))
+    assert torch.equal(out["ground_frame"].cpu(), ref_out["ground_frame"])
+    assert torch.equal(out["ground_box"].cpu(), ref_out["ground_box"].detach())
+    assert (out["pos_scores"].detach().cpu() - ref_out["pos_scores"].detach()).abs().max().item() <= 5e-2
+    (loss,) = out["losses"].values()
+    assert abs(loss.item() - bce.item()) <= 1e-2 * abs(bce.item()) + 1e-4
+    loss.sum().backward()
+    torch.cuda.synchronize()
+    eng = m.train_engine()
+    worst = {}
+    for name, p in m.named_parameters():
+        ref = ref_g.get(name)
+        if name.startswith(eng.DEAD_PREFIXES):
+            assert p.grad is None or p.grad.abs().max().item() == 0, name
+            assert ref is None or ref.abs().max().item() == 0, name
+            continue
+        assert p.grad is not None, name
+        if ref is None or ref.norm().item() == 0:
+            assert p.grad.abs().max().item() <= 1e-6, name
+            continue
+        if name.endswith("attention.self.key.bias"):
+            qref = ref_g[name.replace(".key.", ".query.")].abs().max().item()
+            assert p.grad.abs().max().item() <= 2e-2 * qref + 1e-6, (name, p.grad.abs().max().item(), qref)
+            continue
+        worst[name] = rel_l2(p.grad.cpu(), ref)
+    bad = {k: v for k, v in worst.items() if v > 5e-2}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:12]
+    a = torch.cat([m.get_parameter(k).grad.flatten().cpu().double() for k in worst])
+    b = torch.cat([ref_g[k].flatten().double() for k in worst])
+    assert F.cosine_similarity(a, b, dim=0).item() >= 0.999
+    # and the fused optimizer steps it
+    eng.step(lr=1e-4, max_grad_l2_norm=0.25)
+    m.eval()
+    with torch.no_grad():
+        m(sample_list(inp))

@@ -662,6 +662,27 @@ class _FusionModelBase(BaseModel):
         L.ptr_score(_ptr(ws["qd"]), H, B, T, t0, nq, ws["keyp"][v].data_ptr() + ocr_row0 * H * 2, Le * H, H, O, H,
                     jm.data_ptr() + ocr_row0 * 4, Le, _ptr(scores), N, V, st)
 
+    # ---------------------------------------------------------------- training step (vitxt_gqa_b200/train.py)
+    TRAIN_VARIANT = None        # single-variant models: name of the one answer-transformer variant
+    TRAIN_DEAD = ("Grounding_Module.", "linear_obj_frame_to_mmt_in.", "obj_frame_layer_norm.")   # never get a gradient
+
+    def train_engine(self):
+        """The flat-buffer training engine of this model (vitxt_gqa_b200/train.py), created on first use."""
+        eng = getattr(self, "_train_engine", None)
+        if eng is None or eng.dev != self._device():
+            from .train import TrainEngine
+            eng = TrainEngine(self)
+            object.__setattr__(self, "_train_engine", eng)
+        return eng
+
+    def _train_forward_single(self, inp, dev):
+        """Training-mode forward of a single-variant model behind the engine's autograd Function."""
+        from . import train as _train
+        eng = self.train_engine()
+        (scores,) = _train._T2STrainFn.apply(eng, inp, *eng.live_params)
+        ground_frame, ground_box = eng.ground
+        return scores, ground_frame, ground_box
+
     def _run_greedy(self, greedy, use_graph, gkey, pos_buf, pos_out, stream, dev):
         """Run the greedy-decode launch chain `greedy(stream_handle)` on torch's current stream `stream`: eagerly, or --
         from the third forward with the same workspace and packed weights on -- as one CUDA-graph replay (the chain
@@ -823,15 +844,6 @@ class T2S(_FusionModelBase):
         cfg, h = self.config, self.hidden
         self.TransLayer = QTV(h, int(cfg.translayers.num_hidden_layers))
         self.Grounding_Module = GroundingModule(h, int(cfg.encoder.num_hidden_layers))
-
-    def train_engine(self):
-        """The flat-buffer training engine of this model (vitxt_gqa_b200/train.py), created on first use."""
-        eng = getattr(self, "_train_engine", None)
-        if eng is None or eng.dev != self._device():
-            from .train import TrainEngine
-            eng = TrainEngine(self)
-            object.__setattr__(self, "_train_engine", eng)
-        return eng
 
     def _grounding(self, L, P, ws, inp, B, Lt, F, O, Of, Le, dev, st):
         """Grounding_Module.forward (reference t2s.py:461-518) on the joint features in ws["J1"]: question pooling,
@@ -1119,6 +1131,41 @@ class M4C(_FusionModelBase):
     def _build_grounding(self):
         self.PostHoc = PostHocAttention(self.hidden)
 
+    # hooks of the training engine (single answer-transformer variant; vitxt_gqa_b200/train.py)
+    TRAIN_VARIANT = "pos"
+    TRAIN_DEAD = ("PostHoc.", "frame_embeddings.", "temporal_position_embeddings.", "track_position_embeddings.",
+                  "linear_obj_frame_to_mmt_in.", "obj_frame_layer_norm.")
+
+    def _sv_dims(self, inp):
+        return 1, inp["ocr_mask"].shape[1]
+
+    def _sv_masks(self, L, ws, inp, B, Lt, n_obj, O, st):
+        ones = torch.ones(B, 1, device=inp["text"].device, dtype=torch.int64)
+        L.mask_prep(_ptr(inp["text_len"]), _ptr(ones), _ptr(inp["ocr_mask"]), B, Lt, 1, O, _ptr(ws["jm_ref"]), st)
+        L.mask_prep(_ptr(inp["text_len"]), None, None, B, Lt, 0, 0, _ptr(ws["jm_txt"]), st)
+        L.build_keys(_ptr(ws["jm_txt"]), B, Lt, _ptr(ws["keys_txt"]), _ptr(ws["nk_txt"]), Lt, st)
+
+    def _sv_encoder_inputs(self, inp):
+        return inp, True
+
+    def _sv_ground(self, L, P, ws, inp, B, Lt, n_obj, O, Le, dev, st):
+        """PostHoc_Attention (m4c.py:356-422) on ws["J1"]; leaves the variant's joint mask / key list in ws."""
+        H, f, g = 768, P["f32"], "PostHoc."
+        F, Of = self.frame_num, self.ocr_frame_num
+        self._q_linear(L, P, ws, f[g + "q_linear.weight"], f[g + "q_linear.bias"], "q_linear", B, Lt, Le, st)
+        L.question_pool(_ptr(ws["qp"]), B, Lt, H, _ptr(f[g + "self_attn.weight"]), _ptr(f[g + "self_attn.bias"]),
+                        _ptr(ws["jm_ref"]), Le, _ptr(ws["gq"]), st)
+        L.sim_scores(_ptr(ws["gq"]), _ptr(ws["J1"]), Le * H, H, Lt + 1, O, H, B, _ptr(ws["sim"]), st)
+        L.middle_frame_slots(_ptr(inp["middel_frame_id"]), _ptr(inp["temporal_id"]), B, O, _ptr(ws["slot"]), st)
+        kk = min(self.ocr_topk, Of)
+        ground_box = torch.zeros(B, kk, 4, device=dev, dtype=torch.float32)
+        ws["jm_pos"].copy_(ws["jm_ref"])
+        L.spatial_select(_ptr(ws["sim"]), O, 0, _ptr(ws["slot"]), _ptr(ws["jm_ref"]), B, Le, Lt + 1, F, Of, None,
+                         _ptr(inp["ocr_bbox_coordinates"]), self.ocr_topk, 1, _ptr(ground_box), _ptr(ws["jm_pos"]),
+                         None, None, st)
+        L.build_keys(_ptr(ws["jm_pos"]), B, Le, _ptr(ws["keys"]["pos"]), _ptr(ws["nk"]["pos"]), Le, st)
+        return inp["middel_frame_id"], ground_box
+
     def forward(self, sample_list):
         L = _lib.get_lib()
         inp = self._gather_inputs(sample_list, self._I64 + self._F32)
@@ -1130,6 +1177,10 @@ class M4C(_FusionModelBase):
         V = self.classifier.module.weight.shape[0]
         if O != F * Of:
             raise ValueError("inputs have %d OCR slots but the config says %d x %d" % (O, F, Of))
+        if self.training and torch.is_grad_enabled():
+            scores, ground_frame, ground_box = self._train_forward_single(inp, dev)
+            return {"pos_scores": scores, "ground_box": ground_box, "ground_frame": ground_frame,
+                    "frame_topk": _dev_scalar(self.frame_topk, dev), "ocr_topk": _dev_scalar(self.ocr_topk, dev)}
         Le, H = Lt + 1 + O, 768      # one object token: the middle frame (reference m4c.py:188,420)
         P = self._pack(dev)
         variants = ("pos",)
@@ -1204,6 +1255,36 @@ class T5ViteVQA(_FusionModelBase):
     def _build_grounding(self):
         self.PostHoc = PostHocAttention(self.hidden, frame_att=True)
 
+    # hooks of the training engine (vitxt_gqa_b200/train.py)
+    TRAIN_VARIANT = "ref"
+    TRAIN_DEAD = ("PostHoc.", "linear_obj_frame_to_mmt_in.", "obj_frame_layer_norm.")
+
+    def _sv_dims(self, inp):
+        return inp["video_feat"].shape[1], inp["ocr_mask"].shape[1]
+
+    def _sv_masks(self, L, ws, inp, B, Lt, F, O, st):
+        L.mask_prep(_ptr(inp["text_len"]), _ptr(inp["frame_mask"]), _ptr(inp["ocr_mask"]), B, Lt, F, O,
+                    _ptr(ws["jm_ref"]), st)
+        L.mask_prep(_ptr(inp["text_len"]), None, None, B, Lt, 0, 0, _ptr(ws["jm_txt"]), st)
+        L.build_keys(_ptr(ws["jm_txt"]), B, Lt, _ptr(ws["keys_txt"]), _ptr(ws["nk_txt"]), Lt, st)
+        L.build_keys(_ptr(ws["jm_ref"]), B, Lt + F + O, _ptr(ws["keys"]["ref"]), _ptr(ws["nk"]["ref"]), Lt + F + O, st)
+
+    def _sv_encoder_inputs(self, inp):
+        return inp, False
+
+    def _sv_ground(self, L, P, ws, inp, B, Lt, F, O, Le, dev, st):
+        """Post-hoc attention of t5vitevqa.py:357-416 on ws["J1"] (reports boxes only; masks stay the dataset's)."""
+        H, f, g = 768, P["f32"], "PostHoc."
+        self._q_linear(L, P, ws, f[g + "q_linear.weight"], f[g + "q_linear.bias"], "q_linear", B, Lt, Le, st)
+        L.question_pool(_ptr(ws["qp"]), B, Lt, H, _ptr(f[g + "self_attn.weight"]), _ptr(f[g + "self_attn.bias"]),
+                        _ptr(ws["jm_ref"]), Le, _ptr(ws["gq"]), st)
+        L.sim_scores(_ptr(ws["gq"]), _ptr(ws["J1"]), Le * H, H, Lt + F, O, H, B, _ptr(ws["sim"]), st)
+        K = min(self.frame_topk * self.ocr_topk, O)
+        ground_box = torch.zeros(B, K, 4, device=dev, dtype=torch.float32)
+        L.spatial_select(_ptr(ws["sim"]), O, 0, None, _ptr(ws["jm_ref"]), B, Le, Lt + F, F, self.ocr_frame_num, None,
+                         _ptr(inp["ocr_bbox_coordinates"]), K, 4, _ptr(ground_box), None, None, None, st)
+        return inp["frame_id"], ground_box
+
     def forward(self, sample_list):
         L = _lib.get_lib()
         inp = self._gather_inputs(sample_list, self._I64 + self._F32)
@@ -1216,6 +1297,10 @@ class T5ViteVQA(_FusionModelBase):
         if inp["video_feat"].shape[1] != F or O != F * Of:
             raise ValueError("inputs have %d frames / %d OCR slots but the config says %d x %d"
                              % (inp["video_feat"].shape[1], O, F, Of))
+        if self.training and torch.is_grad_enabled():
+            scores, ground_frame, ground_box = self._train_forward_single(inp, dev)
+            return {"pos_scores": scores, "ground_box": ground_box, "ground_frame": ground_frame,
+                    "frame_topk": _dev_scalar(self.frame_topk, dev), "ocr_topk": _dev_scalar(self.ocr_topk, dev)}
         Le, H = Lt + F + O, 768
         P = self._pack(dev)
         variants = ("ref",)          # one variant, keyed by the dataset masks (t5vitevqa.py:411-415)
@@ -1292,6 +1377,28 @@ class GTBox(_FusionModelBase):
         self.TransLayer = QTV(h, int(cfg.translayers.num_hidden_layers))
         self.Grounding_Module = GroundingModule(h, int(cfg.encoder.num_hidden_layers))
 
+    # hooks of the training engine (vitxt_gqa_b200/train.py)
+    TRAIN_VARIANT = "pos"
+    TRAIN_DEAD = ("Grounding_Module.", "TransLayer.", "spatial_enhance.", "linear_obj_frame_to_mmt_in.",
+                  "obj_frame_layer_norm.")
+
+    def _sv_dims(self, inp):
+        return inp["video_feat"].shape[1], inp["ocr_mask_embedding"].shape[1]
+
+    def _sv_masks(self, L, ws, inp, B, Lt, F, O, st):
+        L.mask_prep(_ptr(inp["text_len"]), _ptr(inp["frame_mask_embedding"]), _ptr(inp["ocr_mask_embedding"]), B, Lt, F, O,
+                    _ptr(ws["jm_pos"]), st)
+        L.mask_prep(_ptr(inp["text_len"]), None, None, B, Lt, 0, 0, _ptr(ws["jm_txt"]), st)
+        L.build_keys(_ptr(ws["jm_txt"]), B, Lt, _ptr(ws["keys_txt"]), _ptr(ws["nk_txt"]), Lt, st)
+        L.build_keys(_ptr(ws["jm_pos"]), B, Lt + F + O, _ptr(ws["keys"]["pos"]), _ptr(ws["nk"]["pos"]), Lt + F + O, st)
+
+    def _sv_encoder_inputs(self, inp):
+        return dict(inp, temporal_id=inp["ocr_temporal_id"], track_id=inp["ocr_track_id"],
+                    ocr_bbox_coordinates=inp["ocr_bbox_list"]), False
+
+    def _sv_ground(self, L, P, ws, inp, B, Lt, F, O, Le, dev, st):
+        return inp["frame_list"], inp["ocr_bbox_list"]          # the annotation itself (gt_box.py:478-479)
+
     def forward(self, sample_list):
         L = _lib.get_lib()
         inp = self._gather_inputs(sample_list, self._I64 + self._F32)
@@ -1301,6 +1408,10 @@ class GTBox(_FusionModelBase):
         O = inp["ocr_mask_embedding"].shape[1]
         T = inp["train_prev_inds"].shape[1]
         V = self.classifier.module.weight.shape[0]
+        if self.training and torch.is_grad_enabled():
+            scores, ground_frame, ground_box = self._train_forward_single(inp, dev)
+            return {"pos_scores": scores, "ground_box": ground_box, "ground_frame": ground_frame,
+                    "frame_topk": _dev_scalar(64, dev), "ocr_topk": _dev_scalar(15, dev)}
         Le, H = Lt + F + O, 768
         P = self._pack(dev)
         variants = ("pos",)

@@ -56,18 +56,18 @@ def lr_lambda_update(i_iter, cfg):
 
 
 class _T2STrainFn(torch.autograd.Function):
-    """forward(engine, inputs, *live_params) -> (ref_scores, pos_scores, neg_scores)."""
+    """forward(engine, inputs, *live_params) -> one score tensor per entry of `engine.out_variants`
+    (T2S: ref, pos, neg; the single-variant models: one)."""
 
     @staticmethod
     def forward(ctx, engine, inp, *params):
         ctx.engine = engine
-        ref, pos, neg = engine.forward(inp)
-        return ref, pos, neg
+        return tuple(engine.forward(inp))
 
     @staticmethod
-    def backward(ctx, d_ref, d_pos, d_neg):
+    def backward(ctx, *dscores):
         eng = ctx.engine
-        grads = eng.backward({"ref": d_ref, "pos": d_pos, "neg": d_neg})
+        grads = eng.backward(dict(zip(eng.out_variants, dscores)))
         return (None, None) + tuple(grads)
 
 
@@ -79,10 +79,19 @@ class TrainEngine:
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
             raise _lib.T2SLibraryError("the training step runs only on a CUDA device (sm_100a); there is no CPU fallback")
-        if not model.MODEL.startswith("t2s"):
-            raise NotImplementedError("the B200 training step is built for T2S (config 3); M4C trains eval-only here")
         if model.grounding_precision != "bf16x3":
             raise NotImplementedError("training uses the bf16x3 grounding chain")
+        # T2S and its ablations: three variants behind the QTV layers; M4C / T5-ViteVQA / GT-box: ONE answer-transformer
+        # variant straight on the encoders' output (no QTV, no grounding gradient), driven through the model's _sv_* hooks
+        self.is_t2s = model.MODEL.startswith("t2s")
+        if self.is_t2s:
+            self.variants = ("pos", "ref", "neg")
+            self.out_variants = ("ref", "pos", "neg")
+        else:
+            if getattr(model, "TRAIN_VARIANT", None) is None:
+                raise NotImplementedError("no training schedule for model '%s'" % model.MODEL)
+            self.variants = self.out_variants = (model.TRAIN_VARIANT,)
+        self.DEAD_PREFIXES = tuple(getattr(model, "TRAIN_DEAD", self.DEAD_PREFIXES))
         self._flatten()
         self.step_count = 0
         self._ws = {}
@@ -170,7 +179,7 @@ class TrainEngine:
                         wo2T=bf(l.output.dense.weight).t().contiguous())
 
         W = dict(text=[layer(l) for l in m.text_bert.encoder.layer],
-                 qtv=[layer(l) for l in m.TransLayer.encoder.layer],
+                 qtv=[layer(l) for l in m.TransLayer.encoder.layer] if self.is_t2s else [],
                  mmt=[layer(l) for l in m.mmt.encoder.layer])
         V = m.classifier.module.weight.shape[0]
         clsT = torch.zeros(H, _ru(V, 8), device=self.dev, dtype=torch.bfloat16)
@@ -189,6 +198,7 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ workspaces
     def _train_ws(self, B, Lt, F, O, T, V, kp_obj, kp_ocr):
+        """`F` = rows of the object part of the joint sequence (frames; 1 for M4C)."""
         key = (B, Lt, F, O, T, V)
         ws = self._ws.get(key)
         if ws is not None:
@@ -199,7 +209,8 @@ class TrainEngine:
         f32 = dict(device=dev, dtype=torch.float32)
         b16 = dict(device=dev, dtype=torch.bfloat16)
         m = self.model
-        n_text, n_qtv, n_mmt = len(m.text_bert.encoder.layer), len(m.TransLayer.encoder.layer), len(m.mmt.encoder.layer)
+        n_text, n_mmt = len(m.text_bert.encoder.layer), len(m.mmt.encoder.layer)
+        n_qtv = len(m.TransLayer.encoder.layer) if self.is_t2s else 0
         Np = _ru(V + O, 8)
 
         def x3_layer(M):      # what one grounding-chain layer keeps (bf16 hi|lo operands double as bf16 activations)
@@ -216,7 +227,7 @@ class TrainEngine:
                 d["qkv"] = torch.empty(M, 3 * H, **b16)
             return d
 
-        variants = ("ref", "pos", "neg")
+        variants = self.variants
         ws = dict(
             text=[x3_layer(Mt) for _ in range(n_text)], qtv=[x3_layer(Me) for _ in range(n_qtv)],
             xt=torch.empty(Mt, H, **f32),
@@ -293,14 +304,15 @@ class TrainEngine:
         L = _lib.get_lib()
         dev = self.dev
         B, Lt = inp["text"].shape
-        F = inp["video_feat"].shape[1]
-        O = inp["ocr_mask"].shape[1]
+        if self.is_t2s:
+            F, O = inp["video_feat"].shape[1], inp["ocr_mask"].shape[1]
+        else:
+            F, O = m._sv_dims(inp)            # rows of the object part (1 for M4C), OCR slots
         T = inp["train_prev_inds"].shape[1]
         V = m.classifier.module.weight.shape[0]
-        Of = O // F
         Le = Lt + F + O
         P = m._pack(dev)
-        variants = ("pos", "ref", "neg")
+        variants = self.variants
         mws = m._workspace(B, dev, dict(Lt=Lt, F=F, O=O, T=T, V=V, k_obj_pad=P["k_obj_pad"], k_ocr_pad=P["k_ocr_pad"],
                                         variants=variants))
         ws = self._train_ws(B, Lt, F, O, T, V, P["k_obj_pad"], P["k_ocr_pad"])
@@ -309,10 +321,13 @@ class TrainEngine:
         Me, Md, Mt = B * Le, B * T, B * Lt
 
         # ---- masks and key lists (as the eval path)
-        L.mask_prep(_ptr(inp["text_len"]), _ptr(inp["frame_mask"]), _ptr(inp["ocr_mask"]), B, Lt, F, O, _ptr(mws["jm_ref"]), st)
-        L.mask_prep(_ptr(inp["text_len"]), None, None, B, Lt, 0, 0, _ptr(mws["jm_txt"]), st)
-        L.build_keys(_ptr(mws["jm_txt"]), B, Lt, _ptr(mws["keys_txt"]), _ptr(mws["nk_txt"]), Lt, st)
-        L.build_keys(_ptr(mws["jm_ref"]), B, Le, _ptr(mws["keys"]["ref"]), _ptr(mws["nk"]["ref"]), Le, st)
+        if self.is_t2s:
+            L.mask_prep(_ptr(inp["text_len"]), _ptr(inp["frame_mask"]), _ptr(inp["ocr_mask"]), B, Lt, F, O, _ptr(mws["jm_ref"]), st)
+            L.mask_prep(_ptr(inp["text_len"]), None, None, B, Lt, 0, 0, _ptr(mws["jm_txt"]), st)
+            L.build_keys(_ptr(mws["jm_txt"]), B, Lt, _ptr(mws["keys_txt"]), _ptr(mws["nk_txt"]), Lt, st)
+            L.build_keys(_ptr(mws["jm_ref"]), B, Le, _ptr(mws["keys"]["ref"]), _ptr(mws["nk"]["ref"]), Le, st)
+        else:
+            m._sv_masks(L, mws, inp, B, Lt, F, O, st)
 
         # ---- TextBert
         e = "text_bert.embeddings."
@@ -329,19 +344,33 @@ class TrainEngine:
                                next_xs=None if last else ws["text"][i + 1]["xs"])
             x = sv["out"]
         # ---- obj / OCR encoders (model code; h_obj / h_ocr / a_*_s stay in the model workspace until backward)
-        m._encode_obj_ocr(L, P, mws, inp, B, Lt, F, O, Le, st)
-        # ---- QTV
-        x, n = mws["J0"], len(P["qtv"])
-        L.split_bf16(_ptr(x), H, Me, H, H, _ptr(ws["qtv"][0]["xs"]), 2 * H, 0, 0, 0, st)
-        for i, lw in enumerate(P["qtv"]):
-            sv, last = ws["qtv"][i], i == n - 1
-            self._x3_layer_fwd(L, lw, x, sv, Me, Le, mws["keys"]["ref"], mws["nk"]["ref"], Le, st,
-                               out=mws["J1"] if last else sv["out"], tanh_base=mws["J0"] if last else None,
-                               out16=mws["X16"] if last else None, next_xs=None if last else ws["qtv"][i + 1]["xs"])
-            x = sv["out"]
-        # ---- grounding (no gradient: emits constant masks, SURVEY hard part 9)
-        ground_frame, ground_box, _, _, _ = m._grounding(L, P, mws, inp, B, Lt, F, O, Of, Le, dev, st)
-        jm = {"ref": mws["jm_ref"], "pos": mws["jm_pos"], "neg": mws["jm_neg"]}
+        if self.is_t2s:
+            enc_inp, has_ids = inp, True
+            m._encode_obj_ocr(L, P, mws, inp, B, Lt, F, O, Le, st)
+        else:
+            enc_inp, m4c = m._sv_encoder_inputs(inp)
+            has_ids = not m4c
+            m._encode_obj_ocr(L, P, mws, enc_inp, B, Lt, F, O, Le, st, m4c=m4c)
+        if self.is_t2s:
+            # ---- QTV
+            x, n = mws["J0"], len(P["qtv"])
+            L.split_bf16(_ptr(x), H, Me, H, H, _ptr(ws["qtv"][0]["xs"]), 2 * H, 0, 0, 0, st)
+            for i, lw in enumerate(P["qtv"]):
+                sv, last = ws["qtv"][i], i == n - 1
+                self._x3_layer_fwd(L, lw, x, sv, Me, Le, mws["keys"]["ref"], mws["nk"]["ref"], Le, st,
+                                   out=mws["J1"] if last else sv["out"], tanh_base=mws["J0"] if last else None,
+                                   out16=mws["X16"] if last else None, next_xs=None if last else ws["qtv"][i + 1]["xs"])
+                x = sv["out"]
+            # ---- grounding (no gradient: emits constant masks, SURVEY hard part 9)
+            ground_frame, ground_box, _, _, _ = m._grounding(L, P, mws, inp, B, Lt, F, O, O // F, Le, dev, st)
+            jm = {"ref": mws["jm_ref"], "pos": mws["jm_pos"], "neg": mws["jm_neg"]}
+        else:
+            # no QTV: the encoders' output feeds the answer transformer (m4c.py:255-273, t5vitevqa.py, gt_box.py:298-299);
+            # the model's grounding hook (post-hoc attention, no gradient) fixes the variant's key list
+            mws["J1"].copy_(mws["J0"])
+            L.cast_rows_bf16(_ptr(mws["J0"]), H, Me, H, _ptr(mws["X16"]), H, 0, 0, 0, st)
+            ground_frame, ground_box = m._sv_ground(L, P, mws, inp, B, Lt, F, O, Le, dev, st)
+            jm = {variants[0]: mws["jm_" + variants[0]]}
 
         # ---- answer transformer, teacher forced (reference t2s.py:288-314)
         N = V + O
@@ -394,9 +423,9 @@ class TrainEngine:
                         Md, H, H, 0, 0, st)
             L.ptr_score(_ptr(ws["qd"][v]), H, B, T, 0, T, ws["keyp"][v].data_ptr() + ocr_row0 * H * 2, Le * H, H, O, H,
                         jm[v].data_ptr() + ocr_row0 * 4, Le, _ptr(sc), N, V, st)
-        self.saved = dict(inp=inp, dims=(B, Lt, F, O, T, V, Le), enc_qkv=enc_qkv, prev=prev)
+        self.saved = dict(inp=inp, enc_inp=enc_inp, has_ids=has_ids, dims=(B, Lt, F, O, T, V, Le), enc_qkv=enc_qkv, prev=prev)
         self.ground = (ground_frame, ground_box)
-        return scores["ref"], scores["pos"], scores["neg"]
+        return [scores[v] for v in self.out_variants]
 
     # ------------------------------------------------------------------ backward building blocks
     def _wgrad(self, L, G, ldg, X, ldx, dW_ptr, ldd, rows, Pn, Qn, st):
@@ -446,10 +475,11 @@ class TrainEngine:
         if sv_all is None:
             raise RuntimeError("backward called without a training forward")
         inp = sv_all["inp"]
+        enc_inp, has_ids = sv_all["enc_inp"], sv_all["has_ids"]
         B, Lt, F, O, T, V, Le = sv_all["dims"]
         P = m._packed
         W = self._wt_pack()
-        variants = ("pos", "ref", "neg")
+        variants = self.variants
         mws = m._workspace(B, dev, dict(Lt=Lt, F=F, O=O, T=T, V=V, k_obj_pad=P["k_obj_pad"], k_ocr_pad=P["k_ocr_pad"],
                                         variants=variants))
         ws = self._train_ws(B, Lt, F, O, T, V, P["k_obj_pad"], P["k_ocr_pad"])
@@ -467,7 +497,7 @@ class TrainEngine:
         pp = "mmt.prev_pred_embeddings."
         first_variant = True
         for v in variants:
-            dS = dscores[v]
+            dS = dscores.get(v)
             if dS is None:
                 continue
             dS = dS.contiguous()
@@ -524,7 +554,8 @@ class TrainEngine:
             raise RuntimeError("no score gradient reached the model")
 
         # ---- QTV: J1 = J0 + tanh(LN2_last(.)): dJ holds dJ1; after the loop dJ += dx(layer 0) = dJ0
-        qtv = P["qtv"]
+        # (single-variant models have no QTV: dJ already is dJ0)
+        qtv = P["qtv"] if self.is_t2s else []
         dy = (ws["dJ"], 0, (0, 0, 0), 1)
         for li in range(len(qtv) - 1, -1, -1):
             lw, wt, sv = qtv[li], W["qtv"][li], ws["qtv"][li]
@@ -535,7 +566,8 @@ class TrainEngine:
                        Le, Le, _ptr(ws["attn_ws"]), st)
             self._layer_bwd_post_attn(L, wt, pre, sv["xs"], 2 * H, Me, enc_sc, ws["dy"], st)
             dy = (ws["dy"], 1, (0, 0, 0), 0)
-        L.rows_add(_ptr(ws["dy"]), None, None, H, Me, H, _ptr(ws["dJ"]), H, 0, 0, 0, 1, st)      # dJ = dJ0
+        if qtv:
+            L.rows_add(_ptr(ws["dy"]), None, None, H, Me, H, _ptr(ws["dJ"]), H, 0, 0, 0, 1, st)      # dJ = dJ0
 
         # ---- obj encoder: J0[obj rows] = LN(W a + b)
         L.ln_bwd(_ptr(mws["h_obj"]), 0, H, _ptr(ws["dJ"]), 0, H, F, Le, Lt, _ptr(f["obj_feat_layer_norm.weight"]),
@@ -546,12 +578,13 @@ class TrainEngine:
         ws["dw_obj"].zero_()
         self._wgrad(L, ws["dh_obj"], H, mws["a_obj_s"], 2 * kpo, _ptr(ws["dw_obj"]), kpo, B * F, H, kpo, st)
         self.grad("linear_obj_feat_to_mmt_in.weight").add_(ws["dw_obj"][:, :ko])
-        L.gemm_bf16(_ptr(ws["dh_obj"]), H, W["objT"].data_ptr() + (ko - 50) * H * 2, H, None, None, 0, _ptr(ws["d_id_obj"]), 52,
-                    B * F, 50, H, _lib.GEMM_OUT_F32, 0, st)
-        L.embed_scatter_add(_ptr(ws["d_id_obj"]), 0, 52, 0, 50, _ptr(inp["frame_id"]), B * F, -1, g("frame_embeddings.weight"),
-                            50, st)
+        if has_ids:         # gradient of the frame-id embedding (M4C's object token has none)
+            L.gemm_bf16(_ptr(ws["dh_obj"]), H, W["objT"].data_ptr() + (ko - 50) * H * 2, H, None, None, 0, _ptr(ws["d_id_obj"]), 52,
+                        B * F, 50, H, _lib.GEMM_OUT_F32, 0, st)
+            L.embed_scatter_add(_ptr(ws["d_id_obj"]), 0, 52, 0, 50, _ptr(enc_inp["frame_id"]), B * F, -1,
+                                g("frame_embeddings.weight"), 50, st)
         # ---- OCR encoder: J0[ocr rows] = LN(W a + b) + LN(W2 bbox + b2)
-        L.ocr_finish_bwd(_ptr(mws["h_ocr"]), H, _ptr(inp["ocr_bbox_coordinates"]), _ptr(f["linear_ocr_bbox_to_mmt_in.weight"]),
+        L.ocr_finish_bwd(_ptr(mws["h_ocr"]), H, _ptr(enc_inp["ocr_bbox_coordinates"]), _ptr(f["linear_ocr_bbox_to_mmt_in.weight"]),
                          _ptr(f["linear_ocr_bbox_to_mmt_in.bias"]), _ptr(f["ocr_feat_layer_norm.weight"]),
                          _ptr(f["ocr_bbox_layer_norm.weight"]), LN_EPS_EMBED, B * O, H, _ptr(ws["dJ"]), H, O, Le, Lt + F,
                          _ptr(ws["dh_ocr"]), H, _ptr(ws["dc_ocr"]), H, g("ocr_feat_layer_norm.weight"),
@@ -561,12 +594,13 @@ class TrainEngine:
         ws["dw_ocr"].zero_()
         self._wgrad(L, ws["dh_ocr"], H, mws["a_ocr_s"], 2 * kpc, _ptr(ws["dw_ocr"]), kpc, B * O, H, kpc, st)
         self.grad("linear_ocr_feat_to_mmt_in.weight").add_(ws["dw_ocr"][:, :kc])
-        L.gemm_bf16(_ptr(ws["dh_ocr"]), H, W["ocrT"].data_ptr() + (kc - 100) * H * 2, H, None, None, 0, _ptr(ws["d_id_ocr"]), 100,
-                    B * O, 100, H, _lib.GEMM_OUT_F32, 0, st)
-        L.embed_scatter_add(_ptr(ws["d_id_ocr"]), 0, 100, 0, 50, _ptr(inp["temporal_id"]), B * O, -1,
-                            g("temporal_position_embeddings.weight"), 50, st)
-        L.embed_scatter_add(_ptr(ws["d_id_ocr"]), 0, 100, 50, 50, _ptr(inp["track_id"]), B * O, -1,
-                            g("track_position_embeddings.weight"), 50, st)
+        if has_ids:
+            L.gemm_bf16(_ptr(ws["dh_ocr"]), H, W["ocrT"].data_ptr() + (kc - 100) * H * 2, H, None, None, 0, _ptr(ws["d_id_ocr"]), 100,
+                        B * O, 100, H, _lib.GEMM_OUT_F32, 0, st)
+            L.embed_scatter_add(_ptr(ws["d_id_ocr"]), 0, 100, 0, 50, _ptr(enc_inp["temporal_id"]), B * O, -1,
+                                g("temporal_position_embeddings.weight"), 50, st)
+            L.embed_scatter_add(_ptr(ws["d_id_ocr"]), 0, 100, 50, 50, _ptr(enc_inp["track_id"]), B * O, -1,
+                                g("track_position_embeddings.weight"), 50, st)
         # ---- TextBert
         text = P["text"]
         dy = (ws["dJ"], 0, (Lt, Le, 0), 0)
