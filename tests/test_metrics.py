@@ -222,3 +222,32 @@ def test_evaluator_errors_surface_like_the_reference():
     sl["question_id"] = sl["question_id"] + 100000                  # no annotation: `None['spatial_temporal_gt']`
     with pytest.raises(TypeError):
         M.BatchEval(sl, out).grounding()
+
+
+@pytest.mark.gpu
+def test_prediction_dump_matches_the_reference_loop():
+    """`format_for_evalai` (vtextgqa/dataset.py:315-362) restated as the plain python loop over the same report."""
+    g, case = _case("t2s")
+    sl, out = _on_gpu(case)
+    proc = synth.SynthAnswerProcessor(case["vocab"])
+    B, T, N = out["pos_scores"].shape
+    report = {"question_id": sl["question_id"], "image_id": ["vid%d" % i for i in range(B)],
+              "context_tokens": case["ocr_tokens"], "scores": out["pos_scores"].view(-1, N),
+              "ground_frame": out["ground_frame"], "ground_box": out["ground_box"]}
+    got = M.format_for_evalai(report, proc)
+    V = case["V"]
+    pred = out["pos_scores"].argmax(dim=-1).view(B, -1).cpu()
+    for b in range(B):
+        words, src = [], []
+        for a in pred[b].tolist():
+            if a >= V:
+                words.append(M.ocr_word(case["ocr_tokens"][b][a - V])); src.append("OCR")
+            else:
+                if a == proc.EOS_IDX:
+                    break
+                words.append(proc.idx2word(a)); src.append("VOCAB")
+        assert got[b] == {"question_id": int(sl["question_id"][b]), "video_id": "vid%d" % b,
+                          "answer": " ".join(words).replace(" 's", "'s"),
+                          "grounded frame": out["ground_frame"][b].tolist(), "grounded box": out["ground_box"][b].tolist(),
+                          "pred_source": src}
+        assert got[b]["answer"] == g["pred_answers"][b]

@@ -508,3 +508,45 @@ class Metrics:
                 values[key] = value.view(1) if value.dim() == 0 else value
         registry.register("{}.{}.{}".format("metrics", dataset_name, dataset_type), values)
         return values
+
+
+# ------------------------------------------------------------------------------------------------ prediction dump
+def format_for_evalai(report, answer_processor):
+    """The prediction entries the reference's test reporter writes (`format_for_evalai`, reference
+    pythia/datasets/videoqa/vtextgqa/dataset.py:315-362, fed by pythia/common/test_reporter.py:134-150 with
+    `report.scores` = `pos_scores` flattened to [B * T, V + O]): answer string, grounded frames / boxes and the source of
+    every answer token.  The argmax and the EOS cut run on the device (`t2s_answer_decode`); `report` needs
+    `question_id`, `image_id`, `context_tokens`, `scores`, `ground_frame`, `ground_box`."""
+    scores = report["scores"] if isinstance(report, collections.abc.Mapping) else report.scores
+    get = (lambda k: report[k]) if isinstance(report, collections.abc.Mapping) else (lambda k: getattr(report, k))
+    qids = get("question_id")
+    B = len(qids)
+    V = int(answer_processor.get_true_vocab_size())
+    if not scores.is_cuda:
+        raise _lib.T2SLibraryError("format_for_evalai decodes on the CUDA device that holds the scores (no CPU fallback)")
+    scores = scores.reshape(B, -1, scores.shape[-1])
+    T, N = scores.shape[1], scores.shape[2]
+    scores = scores.contiguous()
+    buf = torch.empty(B * T + B, dtype=torch.int32, device=scores.device)
+    with torch.cuda.device(scores.device):
+        _lib.get_lib().answer_decode(scores.data_ptr(), N, B, T, N, V, int(answer_processor.EOS_IDX), buf.data_ptr(),
+                                     buf[B * T:].data_ptr(), torch.cuda.current_stream().cuda_stream)
+    host = buf.cpu()
+    ids, lens = host[:B * T].view(B, T), host[B * T:]
+    frames, boxes = get("ground_frame").tolist(), get("ground_box").tolist()
+    out = []
+    for b in range(B):
+        tokens = get("context_tokens")[b]
+        words, source = [], []
+        for a in ids[b, :int(lens[b])].tolist():
+            if a >= V:
+                words.append(ocr_word(tokens[a - V]))
+                source.append("OCR")
+            else:
+                words.append(answer_processor.answer_vocab.idx2word(a))
+                source.append("VOCAB")
+        q = qids[b]
+        out.append({"question_id": q.item() if hasattr(q, "item") else q, "video_id": get("image_id")[b],
+                    "answer": " ".join(words).replace(" 's", "'s"), "grounded frame": frames[b],
+                    "grounded box": boxes[b], "pred_source": source})
+    return out
