@@ -702,7 +702,8 @@ class _FusionModelBase(BaseModel):
             n0 = lib.launches
             try:
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                # thread_local: other host threads (NCCL watchdog, pin-memory workers) keep using the CUDA API
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     greedy(torch.cuda.current_stream(dev).cuda_stream)
             except RuntimeError as e:       # e.g. another thread touched the CUDA API during the capture
                 lib.launches = n0
