@@ -228,3 +228,25 @@ def test_data_parallel_helpers_two_ranks_gloo():
     for p in procs:
         p.join(60)
     assert res == [(0, "ok"), (1, "ok")], res
+
+
+def test_lr_schedule_matches_the_reference_formula():
+    """`lr_lambda_update` (vitxt_gqa_b200/train.py) against the closed form of pythia/utils/general.py:20-30."""
+    from bisect import bisect
+    from vitxt_gqa_b200.train import lr_lambda_update
+    tp = {"use_warmup": True, "warmup_iterations": 1000, "warmup_factor": 0.2, "lr_steps": [10000, 20000], "lr_ratio": 0.1}
+    cfg = {"training_parameters": tp}
+    for i in (0, 1, 250, 999, 1000, 1001, 9999, 10000, 19999, 20000, 30000):
+        want = (0.2 * (1 - i / 1000) + i / 1000) if i <= 1000 else 0.1 ** bisect([10000, 20000], i)
+        assert lr_lambda_update(i, cfg) == pytest.approx(want)
+    tp["use_warmup"] = False
+    assert lr_lambda_update(10, cfg) == 1.0
+
+
+def test_prediction_dump_refuses_cpu_scores():
+    from vitxt_gqa_b200 import metrics as M
+    proc = synth.SynthAnswerProcessor(["<pad>", "<s>", "</s>", "<unk>", "a", "b"])
+    report = {"question_id": torch.tensor([1]), "image_id": ["v"], "context_tokens": [["x"] * 4],
+              "scores": torch.zeros(3, 10), "ground_frame": torch.zeros(1, 2), "ground_box": torch.zeros(1, 2, 4)}
+    with pytest.raises(tlib.T2SLibraryError):
+        M.format_for_evalai(report, proc)
