@@ -140,7 +140,7 @@ int t2s_prev_embed(const long long* prev_inds, int ld_prev, int B, int t0, int n
                    const float* ans_w, const float* ocr_emb, long long ocr_batch_stride, long long ld_ocr,
                    const float* pos_emb, const float* type_emb, const float* ans_g, const float* ans_b,
                    const float* ocr_g, const float* ocr_b, const float* emb_g, const float* emb_b, float eps,
-                   void* out16, float* out32, long long ldo, void* stream);
+                   void* out16, float* out32, long long ldo, int n_ocr, void* stream);
 int t2s_cast_rows_bf16(const float* x, long long ldx, int rows, int H, void* out, long long ldo,
                        int rows_per_group, int out_group_rows, int out_row_off, void* stream);
 
@@ -229,7 +229,7 @@ int t2s_prev_embed_bwd(const void* dx, long long lddx, const long long* prev_ind
                        const float* pos_emb, const float* type_emb, const float* ans_g, const float* ocr_g,
                        const float* emb_g, float eps, float* d_ans_w, float* d_ocr_emb, float* d_pos, float* d_type,
                        float* d_ans_g, float* d_ans_b, float* d_ocr_g, float* d_ocr_b, float* d_emb_g, float* d_emb_b,
-                       void* stream);
+                       int n_ocr, void* stream);
 /* backward of t2s_ocr_finish: dh (bf16) = gradient of linear_ocr_feat_to_mmt_in's output; dc_ws [rows, H] fp32 scratch
  * = gradient of linear_ocr_bbox_to_mmt_in's output; accumulates both LayerNorms, both biases and dW2 [H, 4] */
 int t2s_ocr_finish_bwd(const float* h, long long ldh, const float* bbox, const float* w2, const float* b2,

@@ -20,6 +20,15 @@ LOSS_RTOL = 1e-2
 INFO_NCE_ATOL = 1e-2       # on the unweighted InfoNCE (temperature 0.1 amplifies cosine errors 10x)
 
 
+# Flip / low-margin counts of every margin-aware comparison of a test session; tests/conftest.py prints them in the
+# terminal summary so that tolerated flips are REPORTED, not swallowed (SURVEY hard part 8).
+PARITY_REPORT = []
+
+
+def report_parity(name, **fields):
+    PARITY_REPORT.append((name, fields))
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     meta = ast.literal_eval(str(z["meta"]))

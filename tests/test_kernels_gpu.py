@@ -456,7 +456,7 @@ def test_prev_embed(L):
     out = torch.zeros(B * T, H, device="cuda", dtype=torch.bfloat16)
     o32 = torch.zeros(B * T, H, device="cuda")
     L.prev_embed(P(prev), T, B, 0, T, T, V, H, P(ans), J.data_ptr() + ocr_row0 * H * 4, Le * H, H, P(pos), P(typ),
-                 P(ln[0]), P(ln[1]), P(ln[2]), P(ln[3]), P(ln[4]), P(ln[5]), 1e-12, P(out), P(o32), H, stream())
+                 P(ln[0]), P(ln[1]), P(ln[2]), P(ln[3]), P(ln[4]), P(ln[5]), 1e-12, P(out), P(o32), H, O, stream())
     torch.cuda.synchronize()
     F = torch.nn.functional
     ocr = J.view(B, Le, H)[:, ocr_row0:]

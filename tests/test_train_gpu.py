@@ -282,7 +282,7 @@ def test_prev_embed_bwd(L):
     row0 = 28
     L.prev_embed_bwd(P(dx), H, P(prev), T, B, T, V, H, P(ans_w), ocr.data_ptr() + row0 * H * 4, Le * H, H, P(pos_emb),
                      P(type_emb), P(gs[0]), P(gs[1]), P(gs[2]), 1e-12, P(d["ans"]), d["ocr"].data_ptr() + row0 * H * 4,
-                     P(d["pos"]), P(d["type"]), P(dg[0]), P(dg[1]), P(dg[2]), P(dg[3]), P(dg[4]), P(dg[5]), stream())
+                     P(d["pos"]), P(d["type"]), P(dg[0]), P(dg[1]), P(dg[2]), P(dg[3]), P(dg[4]), P(dg[5]), O, stream())
     torch.cuda.synchronize()
     t64 = [t.double().requires_grad_(True) for t in (ans_w, ocr, pos_emb, type_emb)]
     g64 = [t.double().requires_grad_(True) for t in gs]

@@ -369,7 +369,7 @@ prev_embed_bwd_kernel(const __nv_bfloat16* __restrict__ dx, long long lddx, cons
                       float eps, float* __restrict__ d_ans_w, float* __restrict__ d_ocr_emb,
                       float* __restrict__ d_pos, float* __restrict__ d_type, float* __restrict__ d_ans_g,
                       float* __restrict__ d_ans_b, float* __restrict__ d_ocr_g, float* __restrict__ d_ocr_b,
-                      float* __restrict__ d_emb_g, float* __restrict__ d_emb_b) {
+                      float* __restrict__ d_emb_g, float* __restrict__ d_emb_b, int n_ocr) {
     extern __shared__ float red[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = H / 128;
@@ -377,7 +377,7 @@ prev_embed_bwd_kernel(const __nv_bfloat16* __restrict__ dx, long long lddx, cons
     zero_acc(g_ans); zero_acc(b_ans); zero_acc(g_ocr); zero_acc(b_ocr); zero_acc(g_emb); zero_acc(b_emb);
     for (int w = blockIdx.x * (BW_THREADS / 32) + warp; w < B * T; w += gridDim.x * (BW_THREADS / 32)) {
         const int b = w / T, t = w % T;
-        const long long idx = prev_inds[(long long)b * ld_prev + t];
+        const long long idx = clamp_index(prev_inds[(long long)b * ld_prev + t], (long long)V + n_ocr);   // as prev_embed
         const bool is_ocr = idx >= V;
         const float* src = is_ocr ? ocr_emb + (long long)b * ocr_batch_stride + (idx - V) * ld_ocr : ans_w + idx * H;
         const float* ty = type_emb + (is_ocr ? H : 0);
@@ -807,13 +807,13 @@ extern "C" int t2s_prev_embed_bwd(const void* dx, long long lddx, const long lon
                                   long long ld_ocr, const float* pos_emb, const float* type_emb, const float* ans_g,
                                   const float* ocr_g, const float* emb_g, float eps, float* d_ans_w, float* d_ocr_emb,
                                   float* d_pos, float* d_type, float* d_ans_g, float* d_ans_b, float* d_ocr_g,
-                                  float* d_ocr_b, float* d_emb_g, float* d_emb_b, void* stream) {
-    if (!bw_h_ok(H) || B <= 0 || T <= 0) { set_error("prev_embed_bwd: bad shape"); return T2S_ERR_SHAPE; }
+                                  float* d_ocr_b, float* d_emb_g, float* d_emb_b, int n_ocr, void* stream) {
+    if (!bw_h_ok(H) || B <= 0 || T <= 0 || n_ocr < 0) { set_error("prev_embed_bwd: bad shape"); return T2S_ERR_SHAPE; }
     const size_t smem = (size_t)(BW_THREADS / 32) * H * sizeof(float);
     prev_embed_bwd_kernel<<<bw_row_grid(B * T), BW_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(dx), lddx, prev_inds, ld_prev, B, T, V, H, ans_w, ocr_emb, ocr_batch_stride,
         ld_ocr, pos_emb, type_emb, ans_g, ocr_g, emb_g, eps, d_ans_w, d_ocr_emb, d_pos, d_type, d_ans_g, d_ans_b, d_ocr_g,
-        d_ocr_b, d_emb_g, d_emb_b);
+        d_ocr_b, d_emb_g, d_emb_b, n_ocr);
     return launch_status("prev_embed_bwd");
 }
 

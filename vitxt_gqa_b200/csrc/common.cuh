@@ -30,6 +30,11 @@ inline int launch_status(const char* what) {
 
 constexpr int kWarp = 32;
 
+// index into a table of `n` rows, forced into range (bad feedback / teacher-forcing indices must not read out of bounds)
+__device__ __forceinline__ long long clamp_index(long long i, long long n) {
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+
 // ---------------------------------------------------------------- warp / block reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

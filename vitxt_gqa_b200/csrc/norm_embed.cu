@@ -242,12 +242,14 @@ prev_embed_kernel(const long long* __restrict__ prev_inds, int ld_prev, int B, i
                   long long ld_ocr, const float* __restrict__ pos_emb, const float* __restrict__ type_emb,
                   const float* __restrict__ ans_g, const float* __restrict__ ans_b, const float* __restrict__ ocr_g,
                   const float* __restrict__ ocr_b, const float* __restrict__ emb_g, const float* __restrict__ emb_b,
-                  float eps, __nv_bfloat16* __restrict__ out16, float* __restrict__ out32, long long ldo, int T) {
+                  float eps, __nv_bfloat16* __restrict__ out16, float* __restrict__ out32, long long ldo, int T,
+                  int n_ocr) {
     const int w = blockIdx.x * (NE_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (w >= B * nt) return;
     const int b = w / nt, t = t0 + w % nt;
     const int nv = H / 128;
-    const long long idx = prev_inds[(long long)b * ld_prev + t];
+    // indices outside [0, V + n_ocr) cannot come from an argmax over the score row; clamp instead of reading out of bounds
+    const long long idx = clamp_index(prev_inds[(long long)b * ld_prev + t], (long long)V + n_ocr);
     const bool is_ocr = idx >= V;
     const float* src = is_ocr ? ocr_emb + (long long)b * ocr_batch_stride + (idx - V) * ld_ocr : ans_w + idx * H;
     const float* ty = type_emb + (is_ocr ? H : 0);
@@ -412,11 +414,11 @@ extern "C" int t2s_prev_embed(const long long* prev_inds, int ld_prev, int B, in
                               const float* ans_w, const float* ocr_emb, long long ocr_batch_stride, long long ld_ocr,
                               const float* pos_emb, const float* type_emb, const float* ans_g, const float* ans_b,
                               const float* ocr_g, const float* ocr_b, const float* emb_g, const float* emb_b, float eps,
-                              void* out16, float* out32, long long ldo, void* stream) {
-    if (!h_ok(H) || B <= 0 || nt <= 0 || t0 < 0 || t0 + nt > T) { set_error("prev_embed: bad arguments"); return T2S_ERR_SHAPE; }
+                              void* out16, float* out32, long long ldo, int n_ocr, void* stream) {
+    if (!h_ok(H) || B <= 0 || nt <= 0 || t0 < 0 || t0 + nt > T || n_ocr < 0 || V <= 0) { set_error("prev_embed: bad arguments"); return T2S_ERR_SHAPE; }
     prev_embed_kernel<<<rows_grid(B * nt), NE_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         prev_inds, ld_prev, B, t0, nt, V, H, ans_w, ocr_emb, ocr_batch_stride, ld_ocr, pos_emb, type_emb, ans_g, ans_b,
-        ocr_g, ocr_b, emb_g, emb_b, eps, reinterpret_cast<__nv_bfloat16*>(out16), out32, ldo, T);
+        ocr_g, ocr_b, emb_g, emb_b, eps, reinterpret_cast<__nv_bfloat16*>(out16), out32, ldo, T, n_ocr);
     return launch_status("prev_embed");
 }
 

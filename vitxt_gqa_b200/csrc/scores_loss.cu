@@ -114,6 +114,7 @@ argmax_feedback_kernel(const float* __restrict__ scores, long long ld_scores, in
     if (threadIdx.x == 0) {
         for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
             if (sv[k] > best || (sv[k] == best && si[k] < bi)) { best = sv[k]; bi = si[k]; }
+        if (bi == 0x7fffffff) bi = 0;      // row of NaN / -inf only: no element compared greater (t2s_answer_decode maps it to 0 too)
         if (argmax_out) argmax_out[(long long)b * T + t] = bi;
         if (prev_inds && t + 1 < T) prev_inds[(long long)b * ld_prev + t + 1] = bi;
     }

@@ -39,7 +39,7 @@ SIGNATURES = {
     "t2s_add_ln_split": [_p, _i, _ll, _p, _i, _ll, _p, _p, _f, _i, _i, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p],
     "t2s_ocr_finish": [_p, _ll, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _p, _ll, _i, _i, _i, _p],
     "t2s_prev_embed": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _ll, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _f,
-                       _p, _p, _ll, _p],
+                       _p, _p, _ll, _i, _p],
     "t2s_cast_rows_bf16": [_p, _ll, _i, _i, _p, _ll, _i, _i, _i, _p],
     "t2s_mask_prep": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
     "t2s_build_keys": [_p, _i, _i, _p, _p, _i, _p],
@@ -62,7 +62,7 @@ SIGNATURES = {
     "t2s_embed_scatter_add": [_p, _i, _ll, _i, _i, _p, _i, _ll, _p, _ll, _p],
     "t2s_ptr_score_bwd": [_p, _ll, _i, _i, _i, _p, _ll, _p, _ll, _ll, _i, _i, _p, _ll, _p, _ll, _ll, _p],
     "t2s_prev_embed_bwd": [_p, _ll, _p, _i, _i, _i, _i, _i, _p, _p, _ll, _ll, _p, _p, _p, _p, _p, _f,
-                           _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+                           _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "t2s_ocr_finish_bwd": [_p, _ll, _p, _p, _p, _p, _p, _f, _i, _i, _p, _ll, _i, _i, _i, _p, _ll, _p, _ll,
                            _p, _p, _p, _p, _p, _p, _p, _p],
     "t2s_bert_embed_bwd": [_p, _ll, _p, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],

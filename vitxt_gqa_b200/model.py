@@ -234,6 +234,7 @@ class _FusionModelBase(BaseModel):
         self.greedy_graph = os.environ.get("T2S_B200_GREEDY_GRAPH", str(self.config.get("b200_greedy_graph", 1))) not in ("0", "False")
         self._greedy_graphs = {}
         self._greedy_warm = set()
+        self._pack_gen = 0
         self._phases_on = os.environ.get("T2S_B200_PHASES", "0") == "1"
         self._phase_events = []
         # greedy-decode GEMMs (one row per sample) on the weight-streaming kernel instead of the 128-row tcgen05 tile
@@ -376,6 +377,11 @@ class _FusionModelBase(BaseModel):
         P["w_ptr_k"] = self.ocr_ptr_net.key.weight.detach().to(torch.bfloat16).contiguous()
         P["f32"] = {n: f32(p) for n, p in self.named_parameters()}
         self._packed, self._packed_key = P, key
+        # captured greedy-decode graphs hold raw pointers / tensor maps of the PREVIOUS packed weights: drop them, and key
+        # new captures on a generation counter (id() of a freed dict can be handed to the next one)
+        self._pack_gen += 1
+        self._greedy_graphs.clear()
+        self._greedy_warm.clear()
         return P
 
     # ---------------------------------------------------------------- workspaces
@@ -614,7 +620,7 @@ class _FusionModelBase(BaseModel):
                      _ptr(f[pp + "ans_layer_norm.weight"]), _ptr(f[pp + "ans_layer_norm.bias"]),
                      _ptr(f[pp + "ocr_layer_norm.weight"]), _ptr(f[pp + "ocr_layer_norm.bias"]),
                      _ptr(f[pp + "emb_layer_norm.weight"]), _ptr(f[pp + "emb_layer_norm.bias"]), LN_EPS_BERT,
-                     _ptr(ws["xd"]), None, H, st)
+                     _ptr(ws["xd"]), None, H, O, st)
         if nq == T:
             M, rs, off = B * T, 1, 0          # all decoder rows, contiguous
         else:
@@ -742,7 +748,7 @@ class _FusionModelBase(BaseModel):
                          _ptr(f[pp + "ans_layer_norm.weight"]), _ptr(f[pp + "ans_layer_norm.bias"]),
                          _ptr(f[pp + "ocr_layer_norm.weight"]), _ptr(f[pp + "ocr_layer_norm.bias"]),
                          _ptr(f[pp + "emb_layer_norm.weight"]), _ptr(f[pp + "emb_layer_norm.bias"]), LN_EPS_BERT,
-                         vrow(md["x"], i, H), None, H, st)
+                         vrow(md["x"], i, H), None, H, O, st)
         x = md["x"]
         ping = [md["x1"], md["x2"]]
         for li, lw in enumerate(P["mmt"]):
@@ -1036,7 +1042,7 @@ class T2S(_FusionModelBase):
                         ws["prev"][:, t + 1].copy_(forced[:, t + 1])
 
             def run_greedy(stream):      # `stream` is torch's current stream here
-                self._run_greedy(greedy, use_graph, (id(ws), id(P), B, T, V, O), pos_buf, pos_out, stream, dev)
+                self._run_greedy(greedy, use_graph, (id(ws), self._pack_gen, B, T, V, O), pos_buf, pos_out, stream, dev)
 
             if _pipelined:
                 main = torch.cuda.current_stream(dev)
@@ -1236,7 +1242,7 @@ class M4C(_FusionModelBase):
                     if forced is not None and t + 1 < T:
                         ws["prev"][:, t + 1].copy_(forced[:, t + 1])
 
-            self._run_greedy(greedy, use_graph, (id(ws), id(P), B, T, V, O), pos_buf, scores,
+            self._run_greedy(greedy, use_graph, (id(ws), self._pack_gen, B, T, V, O), pos_buf, scores,
                              torch.cuda.current_stream(dev), dev)
         return {
             "pos_scores": scores, "ground_box": ground_box, "ground_frame": inp["middel_frame_id"],
@@ -1352,7 +1358,7 @@ class T5ViteVQA(_FusionModelBase):
                     if forced is not None and t + 1 < T:
                         ws["prev"][:, t + 1].copy_(forced[:, t + 1])
 
-            self._run_greedy(greedy, use_graph, (id(ws), id(P), B, T, V, O), pos_buf, scores,
+            self._run_greedy(greedy, use_graph, (id(ws), self._pack_gen, B, T, V, O), pos_buf, scores,
                              torch.cuda.current_stream(dev), dev)
         return {
             "pos_scores": scores, "ground_box": ground_box, "ground_frame": inp["frame_id"],
@@ -1455,7 +1461,7 @@ class GTBox(_FusionModelBase):
                     if forced is not None and t + 1 < T:
                         ws["prev"][:, t + 1].copy_(forced[:, t + 1])
 
-            self._run_greedy(greedy, use_graph, (id(ws), id(P), B, T, V, O), pos_buf, scores,
+            self._run_greedy(greedy, use_graph, (id(ws), self._pack_gen, B, T, V, O), pos_buf, scores,
                              torch.cuda.current_stream(dev), dev)
         return {
             "pos_scores": scores, "ground_box": inp["ocr_bbox_list"], "ground_frame": inp["frame_list"],

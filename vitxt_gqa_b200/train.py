@@ -62,13 +62,22 @@ class _T2STrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, inp, *params):
         ctx.engine = engine
-        return tuple(engine.forward(inp))
+        out = tuple(engine.forward(inp))
+        ctx.fwd_gen = engine.fwd_gen        # the engine keeps ONE set of saved activations: this forward's
+        return out
 
     @staticmethod
     def backward(ctx, *dscores):
         eng = ctx.engine
-        grads = eng.backward(dict(zip(eng.out_variants, dscores)))
-        return (None, None) + tuple(grads)
+        if eng.saved is None or ctx.fwd_gen != eng.fwd_gen:
+            raise RuntimeError(
+                "T2S training backward: the saved activations belong to a different forward (the engine keeps one "
+                "forward's activations; run forward -> backward pairs, not two training forwards before one backward)")
+        eng.backward(dict(zip(eng.out_variants, dscores)))
+        # autograd owns what is returned here (AccumulateGrad steals it as p.grad or adds it to an existing p.grad), so
+        # it must not alias the engine's flat buffer, which the next backward zeroes and refills: hand out views of ONE
+        # copy of the live range (351 MB, ~0.1 ms).  TrainEngine.all_reduce() / .step() keep using the flat buffer.
+        return (None, None) + tuple(eng.grad_copies())
 
 
 class TrainEngine:
@@ -98,6 +107,8 @@ class TrainEngine:
         self._wt = None
         self._wt_key = None
         self.saved = None
+        self.fwd_gen = 0
+        self.grad_scale = 1.0      # set by all_reduce(): the factor that turns the summed gradients into their mean
 
     # ------------------------------------------------------------------ flat buffers
     DEAD_PREFIXES = ("Grounding_Module.", "linear_obj_frame_to_mmt_in.", "obj_frame_layer_norm.")
@@ -162,6 +173,12 @@ class TrainEngine:
 
     def _g(self, name):
         return self.flat_grad.data_ptr() + 4 * self.offsets[name]
+
+    def grad_copies(self):
+        """Per-parameter views of one fresh copy of the live gradient range, in `live_names` order."""
+        flat = self.flat_grad[:self.live_end].clone()
+        return [flat[self.offsets[n]:self.offsets[n] + self.named[n].numel()].view_as(self.named[n])
+                for n in self.live_names]
 
     # ------------------------------------------------------------------ transposed bf16 weights for the dgrad GEMMs
     def _wt_pack(self):
@@ -404,7 +421,7 @@ class TrainEngine:
                          _ptr(f[pp + "ans_layer_norm.weight"]), _ptr(f[pp + "ans_layer_norm.bias"]),
                          _ptr(f[pp + "ocr_layer_norm.weight"]), _ptr(f[pp + "ocr_layer_norm.bias"]),
                          _ptr(f[pp + "emb_layer_norm.weight"]), _ptr(f[pp + "emb_layer_norm.bias"]), LN_EPS_BERT,
-                         _ptr(ws["xd"][v]), None, H, st)
+                         _ptr(ws["xd"][v]), None, H, O, st)
             x = ws["xd"][v]
             for li, lw in enumerate(layers):
                 sv = ws["dec"][v][li]
@@ -424,6 +441,7 @@ class TrainEngine:
             L.ptr_score(_ptr(ws["qd"][v]), H, B, T, 0, T, ws["keyp"][v].data_ptr() + ocr_row0 * H * 2, Le * H, H, O, H,
                         jm[v].data_ptr() + ocr_row0 * 4, Le, _ptr(sc), N, V, st)
         self.saved = dict(inp=inp, enc_inp=enc_inp, has_ids=has_ids, dims=(B, Lt, F, O, T, V, Le), enc_qkv=enc_qkv, prev=prev)
+        self.fwd_gen += 1
         self.ground = (ground_frame, ground_box)
         return [scores[v] for v in self.out_variants]
 
@@ -549,7 +567,7 @@ class TrainEngine:
                              ws["dJ"].data_ptr() + ocr_row0 * H * 4, g(pp + "position_embeddings.weight"),
                              g(pp + "token_type_embeddings.weight"), g(pp + "ans_layer_norm.weight"),
                              g(pp + "ans_layer_norm.bias"), g(pp + "ocr_layer_norm.weight"), g(pp + "ocr_layer_norm.bias"),
-                             g(pp + "emb_layer_norm.weight"), g(pp + "emb_layer_norm.bias"), st)
+                             g(pp + "emb_layer_norm.weight"), g(pp + "emb_layer_norm.bias"), O, st)
         if first_variant:
             raise RuntimeError("no score gradient reached the model")
 
@@ -626,15 +644,21 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ collective + optimizer
     def all_reduce(self):
-        """Gradient all-reduce (mean) of the live range of the flat buffer: one NCCL call over NVLink
-        (reference: DDP, base_trainer.py:134-137)."""
+        """Gradient all-reduce of the live range of the flat buffer over NCCL / NVLink (reference: DDP,
+        base_trainer.py:134-137, which averages).  The buffer is SUMMED in place; the factor that makes it the mean
+        (1 / world) is returned and remembered in `self.grad_scale`, which `step()` folds into the clip + Adam kernel,
+        so `eng.all_reduce(); eng.step(lr)` trains on the mean gradient like DDP does."""
         from .dp import all_reduce_flat_
-        return all_reduce_flat_(self.flat_grad[:self.live_end])
+        self.grad_scale = all_reduce_flat_(self.flat_grad[:self.live_end])
+        return self.grad_scale
 
     def step(self, lr, lr_scale_text_bert=0.1, lr_scale_mmt=1.0, max_grad_l2_norm=0.25, betas=(0.9, 0.999), eps=1e-8,
-             grad_scale=1.0):
+             grad_scale=None):
         """clip_grad_norm_(all, max_grad_l2_norm) + Adam.step() over the flat buffers (reference
-        base_trainer.py:266-269 with optimizer_attributes of configs/t2s_*.yml)."""
+        base_trainer.py:266-269 with optimizer_attributes of configs/t2s_*.yml).  `grad_scale` multiplies the
+        gradients before the clip (default: what the last `all_reduce()` returned, 1 on a single rank)."""
+        if grad_scale is None:
+            grad_scale = self.grad_scale
         L = _lib.get_lib()
         st = torch.cuda.current_stream(self.dev).cuda_stream
         if not hasattr(self, "_opt_ws"):
