@@ -1,0 +1,116 @@
+"""Run under torchrun on N >= 2 GPUs (spawned by tests/test_train_multi_gpu.py; also usable by hand:
+`python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/ddp_grad_check.py`).
+
+Data-parallel training step of the B200 path == the single-GPU step on the concatenated batch:
+every rank runs forward + losses + backward on ITS shard of one seeded global batch; the backward all-reduces the flat
+gradient buffer bucket by bucket on a side stream (vitxt_gqa_b200/train.py).  The mean over ranks must equal the
+gradient of  (1 / world) * sum_r loss(shard r)  computed in ONE process on the whole batch -- the reference's
+semantics: each DDP rank normalises pos_bce_loss by ITS OWN mask count (pythia/modules/losses.py:341-342) and DDP
+averages the per-rank gradients (pythia/trainers/base_trainer.py:134-137).  Also checked: p.grad holds the mean (as
+DDP leaves it), the un-overlapped single-call all-reduce gives the same numbers, and clip + Adam on the reduced buffer
+leaves every rank with identical parameters.
+"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def main():
+    from parity_utils import build_b200_model, sample_list
+    from vitxt_gqa_b200 import dp, synth
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=dev)
+    report = {}
+    for tag, dkw, b in (("small", dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=1, ocr_topk=1), 3),
+                        ("clipocr", dict(frame_topk=1, ocr_topk=1), 2)):
+        d = synth.Dims(**dkw)
+        sd = synth.make_state_dict(d, seed=0, variant="stress")
+        full = synth.make_inputs(d, world * b, seed=31, train=True)
+        # unequal loss-mask counts per rank: the per-rank normaliser then differs from a global one
+        full["train_loss_mask"][:b, 2:] = 0
+        m = build_b200_model(d, sd, train=True)
+        eng = m.train_engine()
+        eng.dropout = 0.0 if hasattr(eng, "dropout") else None
+        sl_full = sample_list(full)
+        shard = dp.shard_sample_list(sl_full, rank, world)
+
+        def local_step(overlap):
+            eng.overlap_allreduce = overlap
+            for p in m.parameters():
+                p.grad = None
+            out = m(shard)
+            sum(out["losses"].values()).backward()
+            scale = eng.all_reduce()
+            torch.cuda.synchronize()
+            return (eng.flat_grad[:eng.live_end] * scale).clone(), out
+
+        g_ovl, _ = local_step(True)
+        pg = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+        for n, g in pg.items():           # autograd received the MEAN over ranks (what DDP leaves in p.grad)
+            o = eng.offsets[n]
+            assert torch.equal(g.flatten(), g_ovl[o:o + g.numel()]), (tag, "p.grad is not the reduced mean", n)
+        g_one, _ = local_step(False)      # one flat NCCL call after backward
+        r_modes = rel_l2(g_ovl, g_one)
+        # every rank: the whole batch in one process, loss = mean over shards of the shard's own losses
+        eng.overlap_allreduce = False
+        was_init = dist.is_initialized
+        for p in m.parameters():
+            p.grad = None
+        scores = m.forward(sl_full)
+        total = 0
+        for r in range(world):
+            sl_r = dp.shard_sample_list(sl_full, r, world)
+            out_r = {k: (v[r * b:(r + 1) * b] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == world * b else v)
+                     for k, v in scores.items()}
+            total = total + sum(m.losses(sl_r, out_r).values())
+        (total / world).backward()
+        torch.cuda.synchronize()
+        g_ref = eng.flat_grad[:eng.live_end].clone()       # no all-reduce: this is a single-process gradient
+        worst, worst_name = 0.0, None
+        for n in eng.live_names:
+            o, k = eng.offsets[n], eng.named[n].numel()
+            ref = g_ref[o:o + k]
+            if ref.norm().item() < 1e-12 or n.endswith("attention.self.key.bias"):
+                continue
+            e = rel_l2(g_ovl[o:o + k], ref)
+            if e > worst:
+                worst, worst_name = e, n
+        r_all = rel_l2(g_ovl, g_ref)
+        # ranks agree bit for bit on the reduced buffer, hence on the parameters after clip + Adam
+        g_ovl2, _ = local_step(True)
+        eng.step(lr=1e-4, max_grad_l2_norm=0.25)
+        torch.cuda.synchronize()
+        chk = torch.stack([eng.flat_param[:eng.live_end].double().sum(), g_ovl2.double().sum()])
+        gathered = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(gathered, chk)
+        same = all(torch.equal(gathered[0], g) for g in gathered)
+        report[tag] = dict(rel_l2_vs_single_process=r_all, worst_param_rel_l2=worst, worst_param=worst_name,
+                           rel_l2_overlapped_vs_single_call=r_modes, ranks_identical_after_step=bool(same),
+                           allreduce_bytes=int(eng.live_end) * 4, world=world)
+        assert r_all <= 2e-3, (tag, r_all)
+        assert worst <= 2e-2, (tag, worst, worst_name)
+        assert r_modes <= 1e-5, (tag, r_modes)
+        assert same, tag
+        del m, eng
+        torch.cuda.empty_cache()
+    if rank == 0:
+        print("DDP-GRAD-OK " + json.dumps(report))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

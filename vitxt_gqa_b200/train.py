@@ -26,6 +26,8 @@ Schedule of the backward (per variant v in ref, pos, neg; then the shared front)
   mask) -> q|k|v dgrad (+ residual) + wgrad -> PrevPredEmbeddings bwd; encoder-input gradients of the three
   variants summed into dJ1 -> QTV (tanh residual) -> obj / OCR encoders, TextBert -> embeddings.
 """
+import os
+
 import torch
 
 from . import lib as _lib
@@ -108,7 +110,17 @@ class TrainEngine:
         self._wt_key = None
         self.saved = None
         self.fwd_gen = 0
+        self.dropout_p = 0.0
         self.grad_scale = 1.0      # set by all_reduce(): the factor that turns the summed gradients into their mean
+        # gradient all-reduce overlapped with the backward (reference: DDP's bucketed all-reduce inside autograd,
+        # base_trainer.py:134-137): as soon as a contiguous range of the flat gradient buffer is final, its NCCL
+        # all-reduce is enqueued on a side stream behind an event of the compute stream.  0 = one call after backward.
+        self.overlap_allreduce = os.environ.get("T2S_B200_OVERLAP_ALLREDUCE", "1") not in ("0", "False")
+        self._comm_stream = None
+        self._buckets_pending = []     # [(lo, hi)] of this backward, in launch order
+        self._reduced_upto = None      # None: nothing reduced by the current backward
+        self.comm_events = []          # measurement aid: [(bytes, start_event, end_event)] of the last backward
+        self.time_comm = False
 
     # ------------------------------------------------------------------ flat buffers
     DEAD_PREFIXES = ("Grounding_Module.", "linear_obj_frame_to_mmt_in.", "obj_frame_layer_norm.")
@@ -177,6 +189,8 @@ class TrainEngine:
     def grad_copies(self):
         """Per-parameter views of one fresh copy of the live gradient range, in `live_names` order."""
         flat = self.flat_grad[:self.live_end].clone()
+        if self._reduced_upto == self.live_end and self.grad_scale != 1.0:
+            flat.mul_(self.grad_scale)        # DDP leaves the MEAN over ranks in p.grad
         return [flat[self.offsets[n]:self.offsets[n] + self.named[n].numel()].view_as(self.named[n])
                 for n in self.live_names]
 
@@ -510,6 +524,8 @@ class TrainEngine:
         layers = P["mmt"]
         n_mmt = len(layers)
         self.flat_grad[:self.live_end].zero_()
+        self._begin_overlapped_reduce()
+        live_v = [v for v in variants if dscores.get(v) is not None]
         enc_sc = dict(dh2=ws["dh2"], du=ws["du"], dx1=ws["dx1"], dh1=ws["dh1"], dctx=ws["dctx"], dqkv=ws["dqkv"])
         dec_sc = dict(dh2=ws["dh2_d"], du=ws["du_d"], dx1=ws["dx1_d"], dh1=ws["dh1_d"], dctx=ws["dctx_d"], dqkv=ws["dqkv_d"])
         pp = "mmt.prev_pred_embeddings."
@@ -556,6 +572,8 @@ class TrainEngine:
                 self._layer_bwd_post_attn(L, wt, pre, x_e, H, Me, enc_sc, alt_e, st)
                 dy_e, alt_e = alt_e, dy_e
                 dy_d, alt_d = alt_d, dy_d
+                if v == live_v[-1]:        # the last variant's pass over this layer: its weight gradients are final
+                    self._bucket_ready(pre)
             # ---- encoder-input gradient of this variant into dJ1; decoder input through PrevPredEmbeddings
             L.rows_add(_ptr(dy_e), None, None, H, Me, H, _ptr(ws["dJ"]), H, 0, 0, 0, 0 if first_variant else 1, st)
             first_variant = False
@@ -570,6 +588,9 @@ class TrainEngine:
                              g(pp + "emb_layer_norm.weight"), g(pp + "emb_layer_norm.bias"), O, st)
         if first_variant:
             raise RuntimeError("no score gradient reached the model")
+        self._bucket_ready("mmt.prev_pred_embeddings.")
+        self._bucket_ready("classifier.")
+        self._bucket_ready("ocr_ptr_net.")
 
         # ---- QTV: J1 = J0 + tanh(LN2_last(.)): dJ holds dJ1; after the loop dJ += dx(layer 0) = dJ0
         # (single-variant models have no QTV: dJ already is dJ0)
@@ -584,6 +605,7 @@ class TrainEngine:
                        Le, Le, _ptr(ws["attn_ws"]), st)
             self._layer_bwd_post_attn(L, wt, pre, sv["xs"], 2 * H, Me, enc_sc, ws["dy"], st)
             dy = (ws["dy"], 1, (0, 0, 0), 0)
+            self._bucket_ready(pre)
         if qtv:
             L.rows_add(_ptr(ws["dy"]), None, None, H, Me, H, _ptr(ws["dJ"]), H, 0, 0, 0, 1, st)      # dJ = dJ0
 
@@ -633,6 +655,7 @@ class TrainEngine:
                        Lt, Lt, _ptr(ws["attn_ws"]), st)
             self._layer_bwd_post_attn(L, wt, pre, sv["xs"], 2 * H, Mt, txt_sc, dx_t, st)
             dy = (dx_t, 1, (0, 0, 0), 0)
+            self._bucket_ready(pre)
         e = "text_bert.embeddings."
         L.bert_embed_bwd(_ptr(dx_t), H, _ptr(inp["text"]), Mt, Lt, H, _ptr(f[e + "word_embeddings.weight"]),
                          _ptr(f[e + "position_embeddings.weight"]), _ptr(f[e + "token_type_embeddings.weight"]),
@@ -640,7 +663,109 @@ class TrainEngine:
                          g(e + "position_embeddings.weight"), g(e + "token_type_embeddings.weight"),
                          g(e + "LayerNorm.weight"), g(e + "LayerNorm.bias"), st)
         self.saved = None
+        self._finish_overlapped_reduce()      # remaining ranges (encoders' linears / id tables, embeddings) + join
         return [self.grad(n) for n in self.live_names]
+
+    # ------------------------------------------------------------------ bucketed gradient all-reduce (SURVEY K9)
+    def _range_of(self, prefixes):
+        """[lo, hi) of the flat buffer covered by the live parameters whose names start with one of `prefixes`;
+        they must be contiguous there (they are: `_flatten` sorts by name inside each optimizer group)."""
+        key = tuple(prefixes)
+        cache = self.__dict__.setdefault("_range_cache", {})
+        if key in cache:
+            return cache[key]
+        names = [n for n in self.live_names if n.startswith(key)]
+        if not names:
+            cache[key] = None
+            return None
+        lo = min(self.offsets[n] for n in names)
+        hi = max(self.offsets[n] + _ru(self.named[n].numel(), 4) for n in names)
+        inside = [n for n in self.live_names if lo <= self.offsets[n] < hi]
+        if sorted(inside) != sorted(names):
+            raise AssertionError("gradient bucket %s is not contiguous in the flat buffer" % (key,))
+        cache[key] = (lo, hi)
+        return cache[key]
+
+    def _dist_world(self):
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _bucket_ready(self, *prefixes):
+        """The gradients of the parameters under `prefixes` are final on the compute stream: all-reduce that range on
+        the communication stream, overlapping whatever the backward still has to do."""
+        if self._reduced_upto is None:            # not a distributed, overlapped backward
+            return
+        r = self._range_of(prefixes)
+        if r is None:
+            return
+        import torch.distributed as dist
+        lo, hi = r
+        main = torch.cuda.current_stream(self.dev)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        comm = self._comm_stream
+        comm.wait_event(ready)
+        with torch.cuda.stream(comm):
+            if self.time_comm:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(comm)
+            dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM)
+            if self.time_comm:
+                e1.record(comm)
+                self.comm_events.append(((hi - lo) * 4, e0, e1))
+        self._buckets_pending.append((lo, hi))
+
+    def _begin_overlapped_reduce(self):
+        self._buckets_pending = []
+        self.comm_events = []
+        self._reduced_upto = None
+        if not self.overlap_allreduce or self._dist_world() < 2:
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.dev)
+        self._reduced_upto = 0
+
+    def _finish_overlapped_reduce(self):
+        """End of backward: every live range not yet handed to NCCL goes out now, then the compute stream waits for
+        the communication stream.  Leaves the flat buffer holding the SUM over ranks and `grad_scale` = 1 / world."""
+        if self._reduced_upto is None:
+            return
+        import torch.distributed as dist
+        done = sorted(self._buckets_pending)
+        gaps, cur = [], 0
+        for lo, hi in done:
+            if lo > cur:
+                gaps.append((cur, lo))
+            cur = max(cur, hi)
+        if cur < self.live_end:
+            gaps.append((cur, self.live_end))
+        main = torch.cuda.current_stream(self.dev)
+        comm = self._comm_stream
+        if gaps:
+            ready = torch.cuda.Event()
+            ready.record(main)
+            comm.wait_event(ready)
+            with torch.cuda.stream(comm):
+                for lo, hi in gaps:
+                    dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM)
+        if self.time_comm:
+            self._join_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self._join_events[0].record(main)
+        main.wait_stream(comm)
+        if self.time_comm:
+            self._join_events[1].record(main)
+        self.grad_scale = 1.0 / self._dist_world()
+        self._reduced_upto = self.live_end
+
+    def comm_report(self):
+        """(after a synchronize) {"allreduce_ms": NCCL time on the communication stream, "exposed_ms": how long the
+        compute stream waited for it at the end of backward, "bytes", "buckets"} of the last timed backward."""
+        if not self.comm_events:
+            return None
+        tot = sum(e0.elapsed_time(e1) for _, e0, e1 in self.comm_events)
+        exposed = self._join_events[0].elapsed_time(self._join_events[1])
+        return {"allreduce_ms": tot, "exposed_ms": exposed, "hidden_ms": max(tot - exposed, 0.0),
+                "bytes": sum(b for b, _, _ in self.comm_events), "buckets": len(self.comm_events)}
 
     # ------------------------------------------------------------------ collective + optimizer
     def all_reduce(self):
@@ -648,8 +773,11 @@ class TrainEngine:
         base_trainer.py:134-137, which averages).  The buffer is SUMMED in place; the factor that makes it the mean
         (1 / world) is returned and remembered in `self.grad_scale`, which `step()` folds into the clip + Adam kernel,
         so `eng.all_reduce(); eng.step(lr)` trains on the mean gradient like DDP does."""
+        if self._reduced_upto == self.live_end:     # the backward already all-reduced bucket by bucket (overlapped)
+            return self.grad_scale
         from .dp import all_reduce_flat_
         self.grad_scale = all_reduce_flat_(self.flat_grad[:self.live_end])
+        self._reduced_upto = self.live_end
         return self.grad_scale
 
     def step(self, lr, lr_scale_text_bert=0.1, lr_scale_mmt=1.0, max_grad_l2_norm=0.25, betas=(0.9, 0.999), eps=1e-8,
