@@ -263,6 +263,48 @@ int t2s_sumsq(const float* g, long long n, void* workspace, float* out, void* st
 int t2s_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, int step, const float* sumsq, float max_norm, float grad_scale, void* stream);
 
+/* Dropout of the training step.  The reference trains with p = 0.1 at every site below (configs/t2s_*.yml obj / ocr
+ * dropout_prob; BertConfig hidden_dropout_prob / attention_probs_dropout_prob defaults, models/t2s.py:25-28):
+ *   BertEmbeddings: LN -> dropout                                  (via t2s.py:530)        t2s_dropout_rows
+ *   obj_drop / ocr_drop on the encoded frames / OCR tokens          (t2s.py:95,118,214,253) t2s_dropout_rows
+ *   PrevPredEmbeddings.emb_dropout                                  (t2s.py:688,720)        t2s_dropout_rows
+ *   BertSelfOutput / BertOutput: LN(dropout(Linear(x)) + input)     (via t2s.py:423,538,622) t2s_add_ln_dropout
+ *   BertSelfAttention: dropout(softmax(scores)) . V                 (same)                  t2s_attn_tc_dropout / _dec_
+ * No mask is stored: a mask is a pure function of (seed, site, element) -- one 32-bit counter hash per element pair,
+ * csrc/common.cuh -- and the backward entry points recompute it from the same (p, seed, site).  p is applied as
+ * thr = round(p * 65536) on 16-bit draws; kept values are scaled by 65536 / (65536 - thr).  `site` < 4096.
+ * t2s_dropout_rows works in place on rows (r / per) * group + off + r % per (per == 0: r) and is its own backward
+ * (apply it to the gradient rows).  t2s_add_ln_dropout = t2s_add_ln / _split with dropout on x before + res; the
+ * pre-LayerNorm sum is written to h_out (dtype of x, may alias x) for t2s_ln_bwd_dropout, which returns dh (residual
+ * branch) and dh_drop = dh * mask (Linear output; dbias sums it).  t2s_dropout_mask writes a site's multipliers as
+ * fp32 (mode 0: [rows, H]; mode 1: attention [BH, n_query, n_key]) -- for tests. */
+int t2s_add_ln_dropout(const void* x, int x_bf16, long long ldx, const void* res, int res_bf16, long long ldr,
+                       const float* gamma, const float* beta, float eps, int rows, int H, const float* tanh_base,
+                       long long ld_base, float* out32, long long ldo32, void* out16, long long ldo16, int split,
+                       int rows_per_group, int out_group_rows, int out_row_off, void* h_out, float p,
+                       unsigned long long seed, unsigned site, void* stream);
+int t2s_dropout_rows(void* x, int x_bf16, long long ldx, int rows, int H, int rows_per_group, int group_rows,
+                     int row_off, float p, unsigned long long seed, unsigned site, void* stream);
+int t2s_dropout_mask(float* out, int mode, int rows_or_bh, int H, int n_query, int n_key, float p,
+                     unsigned long long seed, unsigned site, void* stream);
+int t2s_ln_bwd_dropout(const void* h, int h_bf16, long long ldh, const void* dy, int dy_bf16, long long lddy,
+                       int dy_rows_per_group, int dy_group_rows, int dy_row_off, const float* gamma, const float* beta,
+                       float eps, int rows, int H, int tanh_out, void* dh, int dh_bf16, long long lddh, float* dgamma,
+                       float* dbeta, float* dbias, void* dh_drop, float p, unsigned long long seed, unsigned site,
+                       void* stream);
+int t2s_attn_tc_dropout(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads, const int* key_idx,
+                        const int* n_keys, int key_stride, void* out, long long ldo, float p, unsigned long long seed,
+                        unsigned site, void* stream);
+int t2s_attn_dec_dropout(const void* qkv_enc, long long ld_enc, int L_enc, const void* qkv_dec, long long ld_dec, int T,
+                         int B, int H, int heads, const int* key_idx, const int* n_keys, int key_stride, int t0, int nq,
+                         void* out, long long ldo, float p, unsigned long long seed, unsigned site, void* stream);
+int t2s_attn_bwd_dropout(const void* qkv_enc, long long ld_enc, const void* qkv_dec, long long ld_dec, const void* o_enc,
+                         long long ldo_enc, const void* o_dec, long long ldo_dec, const void* do_enc, long long ldg_enc,
+                         const void* do_dec, long long ldg_dec, void* dqkv_enc, long long ldq_enc, void* dqkv_dec,
+                         long long ldq_dec, int B, int Le, int T, int H, int heads, const int* key_idx,
+                         const int* n_keys, int key_stride, int max_keys, void* workspace, float p,
+                         unsigned long long seed, unsigned site, void* stream);
+
 /* Input featurisation, the step before the path.  PHOC descriptor of OCR tokens: replaces the
  * reference's CPU extension pythia/utils/phoc/src/cphoc.c:12-113 + build_phoc.py:9-14 (lower-case, keep [a-z0-9])
  * + PhocProcessor, datasets/processors.py:904-928.  bytes = the tokens' UTF-8 bytes back to back (non-ASCII tokens

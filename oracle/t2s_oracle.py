@@ -25,6 +25,18 @@ import torch.nn.functional as F
 
 NEG = -10000.0
 
+# Training-step tests at dropout p > 0 inject the masks here: DROPOUT_HOOK(site, tensor) -> tensor stands in for every
+# nn.Dropout of the reference's training forward (BertEmbeddings, BertSelfAttention probabilities, BertSelfOutput /
+# BertOutput, obj_drop / ocr_drop t2s.py:214,253, PrevPredEmbeddings.emb_dropout t2s.py:720).  `site` = the module's
+# state-dict prefix + ".emb" / ".attn" / ".h1" / ".h2" (or "obj" / "ocr" / "prev"), prefixed by DROPOUT_CONTEXT + "|"
+# inside the answer transformer (the variant name: ref / pos / neg).  None (default) = dropout off, as in eval.
+DROPOUT_HOOK = None
+DROPOUT_CONTEXT = ""
+
+
+def _drop(site, x):
+    return x if DROPOUT_HOOK is None else DROPOUT_HOOK(DROPOUT_CONTEXT + "|" + site if DROPOUT_CONTEXT else site, x)
+
 
 def _ln(x, sd, prefix, eps):
     return F.layer_norm(x, (x.shape[-1],), sd[prefix + ".weight"], sd[prefix + ".bias"], eps)
@@ -55,7 +67,7 @@ def bert_self_attention(sd, prefix, x, ext_mask, heads=12):
     v = split(_lin(x, sd, prefix + ".value"))
     scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(dh)
     scores = scores + ext_mask
-    probs = F.softmax(scores, dim=-1)
+    probs = _drop(prefix[:-len(".attention.self")] + ".attn", F.softmax(scores, dim=-1))
     ctx = torch.matmul(probs, v).permute(0, 2, 1, 3).contiguous()
     return ctx.view(B, L, H)
 
@@ -64,10 +76,10 @@ def bert_layer(sd, prefix, x, ext_mask, eps=1e-12):
     """BertLayer = BertAttention(self + output: dense, LN(x+res)) ->
     BertIntermediate(dense, gelu) -> BertOutput(dense, LN(x+res))."""
     ctx = bert_self_attention(sd, prefix + ".attention.self", x, ext_mask)
-    a = _ln(_lin(ctx, sd, prefix + ".attention.output.dense") + x, sd,
+    a = _ln(_drop(prefix + ".h1", _lin(ctx, sd, prefix + ".attention.output.dense")) + x, sd,
             prefix + ".attention.output.LayerNorm", eps)
     inter = gelu(_lin(a, sd, prefix + ".intermediate.dense"))
-    return _ln(_lin(inter, sd, prefix + ".output.dense") + a, sd, prefix + ".output.LayerNorm", eps)
+    return _ln(_drop(prefix + ".h2", _lin(inter, sd, prefix + ".output.dense")) + a, sd, prefix + ".output.LayerNorm", eps)
 
 
 def bert_encoder(sd, prefix, x, ext_mask, n_layers):
@@ -90,7 +102,7 @@ def text_bert(sd, d, text, txt_mask):
     e = (F.embedding(text, sd[p + ".word_embeddings.weight"])
          + F.embedding(pos, sd[p + ".position_embeddings.weight"])
          + F.embedding(torch.zeros_like(text), sd[p + ".token_type_embeddings.weight"]))
-    e = _ln(e, sd, p + ".LayerNorm", 1e-12)
+    e = _drop("text_bert.emb", _ln(e, sd, p + ".LayerNorm", 1e-12))
     ext = (1.0 - txt_mask.unsqueeze(1).unsqueeze(2)) * NEG
     return bert_encoder(sd, "text_bert.encoder", e, ext, d.text_layers)
 
@@ -104,7 +116,7 @@ def encode_obj(sd, d, inp, ln_eps):
     else:
         x = F.normalize(inp["video_feat"], dim=-1)
         x = torch.cat([x, F.embedding(inp["frame_id"], sd["frame_embeddings.weight"])], dim=-1)
-    return _ln(_lin(x, sd, "linear_obj_feat_to_mmt_in"), sd, "obj_feat_layer_norm", ln_eps)
+    return _drop("obj", _ln(_lin(x, sd, "linear_obj_feat_to_mmt_in"), sd, "obj_feat_layer_norm", ln_eps))
 
 
 def encode_ocr(sd, d, inp, ln_eps):
@@ -116,9 +128,9 @@ def encode_ocr(sd, d, inp, ln_eps):
         parts.append(F.embedding(inp["temporal_id"], sd["temporal_position_embeddings.weight"]))
         parts.append(F.embedding(inp["track_id"], sd["track_position_embeddings.weight"]))
     feat = torch.cat(parts, dim=-1)
-    return (_ln(_lin(feat, sd, "linear_ocr_feat_to_mmt_in"), sd, "ocr_feat_layer_norm", ln_eps)
-            + _ln(_lin(inp["ocr_bbox_coordinates"], sd, "linear_ocr_bbox_to_mmt_in"), sd,
-                  "ocr_bbox_layer_norm", ln_eps))
+    return _drop("ocr", _ln(_lin(feat, sd, "linear_ocr_feat_to_mmt_in"), sd, "ocr_feat_layer_norm", ln_eps)
+                 + _ln(_lin(inp["ocr_bbox_coordinates"], sd, "linear_ocr_bbox_to_mmt_in"), sd,
+                       "ocr_bbox_layer_norm", ln_eps))
 
 
 def qtv(sd, d, txt, txt_mask, obj, obj_mask, ocr, ocr_mask):
@@ -309,7 +321,7 @@ def prev_pred_embeddings(sd, ans_emb, ocr_emb, prev_inds):
     pos_ids = torch.arange(T, dtype=torch.long).unsqueeze(0).expand(B, T)
     emb = (F.embedding(pos_ids, sd[p + ".position_embeddings.weight"])
            + F.embedding(prev_inds.ge(ans_num).long(), sd[p + ".token_type_embeddings.weight"]))
-    return raw + _ln(emb, sd, p + ".emb_layer_norm", 1e-12)
+    return _drop("prev", raw + _ln(emb, sd, p + ".emb_layer_norm", 1e-12))
 
 
 def causal_mask(n):
@@ -377,8 +389,13 @@ def forward_t2s(sd, d, inp, training=False, schedule="literal", ln_eps_embed=1e-
     }
 
     def one_pass(name, prev):
+        global DROPOUT_CONTEXT
         om, cm = variants[name]
-        ocr_out, dec_out = mmt(sd, d, txt, txt_mask, obj, om, ocr, cm, prev)
+        DROPOUT_CONTEXT = name
+        try:
+            ocr_out, dec_out = mmt(sd, d, txt, txt_mask, obj, om, ocr, cm, prev)
+        finally:
+            DROPOUT_CONTEXT = ""
         return forward_output(sd, ocr_out, dec_out, cm)
 
     scores = {}

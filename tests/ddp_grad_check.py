@@ -43,7 +43,6 @@ def main():
         full["train_loss_mask"][:b, 2:] = 0
         m = build_b200_model(d, sd, train=True)
         eng = m.train_engine()
-        eng.dropout = 0.0 if hasattr(eng, "dropout") else None
         sl_full = sample_list(full)
         shard = dp.shard_sample_list(sl_full, rank, world)
 
@@ -66,7 +65,6 @@ def main():
         r_modes = rel_l2(g_ovl, g_one)
         # every rank: the whole batch in one process, loss = mean over shards of the shard's own losses
         eng.overlap_allreduce = False
-        was_init = dist.is_initialized
         for p in m.parameters():
             p.grad = None
         scores = m.forward(sl_full)

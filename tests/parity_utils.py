@@ -38,7 +38,9 @@ def load_golden(name):
     return z, meta, d, sd, inp
 
 
-def build_b200_model(d, sd, train=False):
+def build_b200_model(d, sd, train=False, dropout=False):
+    """`dropout=False` (default): the training step runs at p = 0, where parity with autograd is defined; True keeps the
+    configured probabilities (obj / ocr dropout_prob 0.1, BERT defaults 0.1) like the reference's training."""
     from vitxt_gqa_b200 import model as tmodel
     register_defaults(vocab_size=d.vocab, ocr_max_num=d.ocr)
     cfg = ConfigNode(synth.model_config_for_dims(d))
@@ -49,6 +51,7 @@ def build_b200_model(d, sd, train=False):
     m.load_state_dict(sd, strict=True)
     m = m.cuda()
     m.train(train)
+    m.train_dropout = bool(dropout)
     return m
 
 

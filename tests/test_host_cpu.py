@@ -53,6 +53,10 @@ def test_ctypes_signatures_match_the_header():
         for p_, a in zip(ps, bound[name]):
             if "*" in p_:
                 want = tlib._p
+            elif p_.startswith("unsigned long long"):
+                want = tlib._ull
+            elif p_.startswith("unsigned"):
+                want = tlib._u
             elif p_.startswith("long long"):
                 want = tlib._ll
             elif p_.startswith("float"):

@@ -543,7 +543,8 @@ __global__ void __launch_bounds__(AD_THREADS)
 attn_dec_kernel(const __nv_bfloat16* __restrict__ qkv_enc, long long ld_enc, int L_enc,
                 const __nv_bfloat16* __restrict__ qkv_dec, long long ld_dec, int T, int H,
                 const int* __restrict__ key_idx, const int* __restrict__ n_keys, int key_stride,
-                int t0, int nq, __nv_bfloat16* __restrict__ out, long long ldo, float scale, int max_keys) {
+                int t0, int nq, __nv_bfloat16* __restrict__ out, long long ldo, float scale, int max_keys,
+                DropCfg drop) {
     extern __shared__ __align__(16) float dsm[];
     float* Qs = dsm;                                   // [AD_MAXQ][64], pre-scaled
     float* Ss = Qs + AD_MAXQ * DH;                     // [QC][max_keys]
@@ -618,7 +619,19 @@ attn_dec_kernel(const __nv_bfloat16* __restrict__ qkv_enc, long long ld_enc, int
                 sum += p;
             }
             const float inv = 1.0f / warp_sum(sum);
-            for (int k = lane; k < nk; k += 32) srow[k] *= inv;
+            if (drop.thr) {
+                // attention_probs dropout (training step): query = decoder position L_enc + t of the virtual sequence,
+                // key k = position in [compacted encoder keys; decoder keys] -- as t2s_attn_bwd_dropout recomputes it
+                const uint32_t y = drop_attn_y(drop, b * gridDim.x + h);
+                const int qi = L_enc + t0 + q0 + q;
+                for (int k = lane; k < nk; k += 32) {
+                    const uint32_t hsh = drop_hash(drop.s0, drop.s1, drop_attn_x(qi, k), y);
+                    const uint32_t u = (k & 1) ? (hsh >> 16) : (hsh & 0xffffu);
+                    srow[k] = u >= drop.thr ? srow[k] * inv * drop.scale : 0.f;
+                }
+            } else {
+                for (int k = lane; k < nk; k += 32) srow[k] *= inv;
+            }
         }
         __syncthreads();
         // ---- O[q] = sum_k P[q][k] V[k]; this thread: dims c*8..c*8+7 of key slice (warp*4+sub) mod 32
@@ -728,9 +741,9 @@ extern "C" int t2s_attn_x3(const void* qkv, long long ld, int lo_off, int B, int
     return launch_status("attn_x3");
 }
 
-extern "C" int t2s_attn_dec(const void* qkv_enc, long long ld_enc, int L_enc, const void* qkv_dec, long long ld_dec,
-                            int T, int B, int H, int heads, const int* key_idx, const int* n_keys, int key_stride,
-                            int t0, int nq, void* out, long long ldo, void* stream) {
+static int attn_dec_entry(const void* qkv_enc, long long ld_enc, int L_enc, const void* qkv_dec, long long ld_dec,
+                          int T, int B, int H, int heads, const int* key_idx, const int* n_keys, int key_stride,
+                          int t0, int nq, void* out, long long ldo, void* stream, DropCfg drop) {
     if (H != heads * DH || nq < 1 || nq > AD_MAXQ || t0 < 0 || t0 + nq > T || (ld_enc % 8) || (ld_dec % 8)) {
         set_error("attn_dec: bad arguments (H %d heads %d t0 %d nq %d T %d)", H, heads, t0, nq, T);
         return T2S_ERR_SHAPE;
@@ -740,9 +753,13 @@ extern "C" int t2s_attn_dec(const void* qkv_enc, long long ld_enc, int L_enc, co
     // pass) was measured SLOWER than three passes of QC = 4 on B200 (195 vs 95 us per launch at 1056 keys: 185
     // registers and 84 KB of score rows leave one CTA per SM), so it is only used when asked for (T2S_ATTN_DEC_QC=12)
     static const int qc_big = []() { const char* e = getenv("T2S_ATTN_DEC_QC"); return e && atoi(e) == 12 ? 12 : 4; }();
-    const int qc = nq == 1 ? 1 : (nq <= 4 ? 4 : qc_big);
+    int qc = nq == 1 ? 1 : (nq <= 4 ? 4 : qc_big);
+    auto smem_for = [&](int q) { return (AD_MAXQ * DH + q * max_keys + AD_WARPS * q * DH + max_keys) * 4; };
+    // long videos (stress sweep: up to 256 frames x 60 OCR slots = 15.6 k keys): the score rows of a 4-query chunk no
+    // longer fit shared memory -> one query per chunk (K / V are re-read per query; the rows stay L2-resident)
+    while (qc > 1 && smem_for(qc) > 200 * 1024) qc = qc == 12 ? 4 : 1;
     const int slot = qc == 1 ? 0 : (qc == 4 ? 1 : 2);
-    const int smem = (AD_MAXQ * DH + qc * max_keys + AD_WARPS * qc * DH + max_keys) * 4;
+    const int smem = smem_for(qc);
     if (smem > 200 * 1024) { set_error("attn_dec: %d keys exceed the shared-memory score buffer", max_keys); return T2S_ERR_SHAPE; }
     static int attr_bytes[3] = {48 * 1024, 48 * 1024, 48 * 1024};
     if (smem > attr_bytes[slot]) {
@@ -760,12 +777,29 @@ extern "C" int t2s_attn_dec(const void* qkv_enc, long long ld_enc, int L_enc, co
     __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(out);
     if (qc == 1)
         attn_dec_kernel<1><<<grid, AD_THREADS, smem, st>>>(pe, ld_enc, L_enc, pd, ld_dec, T, H, key_idx, n_keys,
-                                                           key_stride, t0, nq, po, ldo, 0.125f, max_keys);
+                                                           key_stride, t0, nq, po, ldo, 0.125f, max_keys, drop);
     else if (qc == 4)
         attn_dec_kernel<4><<<grid, AD_THREADS, smem, st>>>(pe, ld_enc, L_enc, pd, ld_dec, T, H, key_idx, n_keys,
-                                                           key_stride, t0, nq, po, ldo, 0.125f, max_keys);
+                                                           key_stride, t0, nq, po, ldo, 0.125f, max_keys, drop);
     else
         attn_dec_kernel<12><<<grid, AD_THREADS, smem, st>>>(pe, ld_enc, L_enc, pd, ld_dec, T, H, key_idx, n_keys,
-                                                            key_stride, t0, nq, po, ldo, 0.125f, max_keys);
+                                                            key_stride, t0, nq, po, ldo, 0.125f, max_keys, drop);
     return launch_status("attn_dec");
+}
+
+extern "C" int t2s_attn_dec(const void* qkv_enc, long long ld_enc, int L_enc, const void* qkv_dec, long long ld_dec,
+                            int T, int B, int H, int heads, const int* key_idx, const int* n_keys, int key_stride,
+                            int t0, int nq, void* out, long long ldo, void* stream) {
+    return attn_dec_entry(qkv_enc, ld_enc, L_enc, qkv_dec, ld_dec, T, B, H, heads, key_idx, n_keys, key_stride, t0, nq,
+                          out, ldo, stream, DropCfg{0, 0, 0, 0, 1.f});
+}
+
+/* t2s_attn_dec with attention_probs dropout (training step; decoder rows = positions L_enc + t of the virtual sequence) */
+extern "C" int t2s_attn_dec_dropout(const void* qkv_enc, long long ld_enc, int L_enc, const void* qkv_dec,
+                                    long long ld_dec, int T, int B, int H, int heads, const int* key_idx,
+                                    const int* n_keys, int key_stride, int t0, int nq, void* out, long long ldo, float p,
+                                    unsigned long long seed, unsigned site, void* stream) {
+    if (p <= 0.f || p >= 1.f || L_enc + T > 65535) { set_error("attn_dec_dropout: p in (0, 1), L < 65536"); return T2S_ERR_ARG; }
+    return attn_dec_entry(qkv_enc, ld_enc, L_enc, qkv_dec, ld_dec, T, B, H, heads, key_idx, n_keys, key_stride, t0, nq,
+                          out, ldo, stream, make_drop(p, seed, site));
 }

@@ -55,6 +55,7 @@ struct AttnBwdArgs {
     float* stats;                                           // [B, heads, Le + T, 2] = {lse2, D}
     int Le, T, H, heads;
     float scale_log2, scale;
+    DropCfg drop;                                           // attention_probs dropout of the forward (thr == 0: none)
 };
 
 // row resolvers of the virtual sequence (sample b); column offset `col` in elements
@@ -288,7 +289,13 @@ attn_bwd_dq_kernel(AttnBwdArgs a) {
                 const int qi = i0 + warp * 16 + g + r * 8;
                 const bool ok = key < nkv && xb_allowed(qi, key, a.Le, nk);
                 const float p = ok ? exp2f(s[n][j] * a.scale_log2 - lse[r]) : 0.f;
-                s[n][j] = p * (dp[n][j] - dd[r]) * a.scale;          // dS
+                float dpj = dp[n][j];
+                if (a.drop.thr) {               // O = sum_j p_j m_j v_j: dL/dp_j = m_j (dO . v_j); D = dO . O is unchanged
+                    const uint32_t hsh = drop_hash(a.drop.s0, a.drop.s1, drop_attn_x(qi, key), drop_attn_y(a.drop, b * a.heads + h));
+                    const uint32_t u = (key & 1) ? (hsh >> 16) : (hsh & 0xffffu);
+                    dpj = u >= a.drop.thr ? dpj * a.drop.scale : 0.f;
+                }
+                s[n][j] = p * (dpj - dd[r]) * a.scale;          // dS
             }
         uint32_t dsf[4][4];
         xb_c_to_a(dsf, s);
@@ -378,8 +385,14 @@ attn_bwd_dkv_kernel(AttnBwdArgs a) {
                 const int key = j0 + warp * 16 + g + (j >> 1) * 8;
                 const bool ok = qi < nq && key < nkv && xb_allowed(qi, key, a.Le, nk);
                 const float p = ok ? exp2f(st[n][j] * a.scale_log2 - lse_s[qc]) : 0.f;
-                st[n][j] = p;                                          // P^T
-                dpt[n][j] = p * (dpt[n][j] - d_s[qc]) * a.scale;       // dS^T
+                float m = 1.f;
+                if (a.drop.thr) {
+                    const uint32_t hsh = drop_hash(a.drop.s0, a.drop.s1, drop_attn_x(qi, key), drop_attn_y(a.drop, b * a.heads + h));
+                    const uint32_t u = (key & 1) ? (hsh >> 16) : (hsh & 0xffffu);
+                    m = u >= a.drop.thr ? a.drop.scale : 0.f;
+                }
+                st[n][j] = p * m;                                      // (P o M)^T: what multiplied V in the forward
+                dpt[n][j] = p * (dpt[n][j] * m - d_s[qc]) * a.scale;   // dS^T
             }
         uint32_t pf[4][4];
         xb_c_to_a(pf, st);
@@ -413,12 +426,12 @@ extern "C" long long t2s_attn_bwd_workspace_bytes(int B, int Le, int T, int head
     return (long long)B * heads * (Le + T) * 2 * sizeof(float);
 }
 
-extern "C" int t2s_attn_bwd(const void* qkv_enc, long long ld_enc, const void* qkv_dec, long long ld_dec,
-                            const void* o_enc, long long ldo_enc, const void* o_dec, long long ldo_dec,
-                            const void* do_enc, long long ldg_enc, const void* do_dec, long long ldg_dec,
-                            void* dqkv_enc, long long ldq_enc, void* dqkv_dec, long long ldq_dec, int B, int Le, int T,
-                            int H, int heads, const int* key_idx, const int* n_keys, int key_stride, int max_keys,
-                            void* workspace, void* stream) {
+static int attn_bwd_entry(const void* qkv_enc, long long ld_enc, const void* qkv_dec, long long ld_dec,
+                          const void* o_enc, long long ldo_enc, const void* o_dec, long long ldo_dec,
+                          const void* do_enc, long long ldg_enc, const void* do_dec, long long ldg_dec,
+                          void* dqkv_enc, long long ldq_enc, void* dqkv_dec, long long ldq_dec, int B, int Le, int T,
+                          int H, int heads, const int* key_idx, const int* n_keys, int key_stride, int max_keys,
+                          void* workspace, void* stream, DropCfg drop) {
     if (H != heads * XDH || B <= 0 || Le <= 0 || T < 0 || max_keys <= 0) {
         set_error("attn_bwd: head size must be 64 (H %d heads %d B %d Le %d T %d)", H, heads, B, Le, T);
         return T2S_ERR_SHAPE;
@@ -443,6 +456,7 @@ extern "C" int t2s_attn_bwd(const void* qkv_enc, long long ld_enc, const void* q
     a.Le = Le; a.T = T; a.H = H; a.heads = heads;
     a.scale = 0.125f;
     a.scale_log2 = 0.125f * 1.4426950408889634f;
+    a.drop = drop;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // rows outside the key list receive no dK / dV: clear the k | v columns (q columns are fully written by dq)
     cudaError_t e = cudaMemset2DAsync(reinterpret_cast<bf*>(dqkv_enc) + H, ldq_enc * sizeof(bf), 0, 2 * (size_t)H * sizeof(bf),
@@ -461,4 +475,29 @@ extern "C" int t2s_attn_bwd(const void* qkv_enc, long long ld_enc, const void* q
     dim3 gk((max_keys + T + XB - 1) / XB, heads, B);
     attn_bwd_dkv_kernel<<<gk, XB_THREADS, XB_DKV_SMEM, st>>>(a);
     return launch_status("attn_bwd");
+}
+
+extern "C" int t2s_attn_bwd(const void* qkv_enc, long long ld_enc, const void* qkv_dec, long long ld_dec,
+                            const void* o_enc, long long ldo_enc, const void* o_dec, long long ldo_dec,
+                            const void* do_enc, long long ldg_enc, const void* do_dec, long long ldg_dec,
+                            void* dqkv_enc, long long ldq_enc, void* dqkv_dec, long long ldq_dec, int B, int Le, int T,
+                            int H, int heads, const int* key_idx, const int* n_keys, int key_stride, int max_keys,
+                            void* workspace, void* stream) {
+    return attn_bwd_entry(qkv_enc, ld_enc, qkv_dec, ld_dec, o_enc, ldo_enc, o_dec, ldo_dec, do_enc, ldg_enc, do_dec, ldg_dec,
+                          dqkv_enc, ldq_enc, dqkv_dec, ldq_dec, B, Le, T, H, heads, key_idx, n_keys, key_stride, max_keys,
+                          workspace, stream, DropCfg{0, 0, 0, 0, 1.f});
+}
+
+/* backward of t2s_attn_tc_dropout (encoder rows) + t2s_attn_dec_dropout (decoder rows) of one layer: same (p, seed, site) */
+extern "C" int t2s_attn_bwd_dropout(const void* qkv_enc, long long ld_enc, const void* qkv_dec, long long ld_dec,
+                                    const void* o_enc, long long ldo_enc, const void* o_dec, long long ldo_dec,
+                                    const void* do_enc, long long ldg_enc, const void* do_dec, long long ldg_dec,
+                                    void* dqkv_enc, long long ldq_enc, void* dqkv_dec, long long ldq_dec, int B, int Le,
+                                    int T, int H, int heads, const int* key_idx, const int* n_keys, int key_stride,
+                                    int max_keys, void* workspace, float p, unsigned long long seed, unsigned site,
+                                    void* stream) {
+    if (p <= 0.f || p >= 1.f || Le + T > 65535) { set_error("attn_bwd_dropout: p in (0, 1), L < 65536"); return T2S_ERR_ARG; }
+    return attn_bwd_entry(qkv_enc, ld_enc, qkv_dec, ld_dec, o_enc, ldo_enc, o_dec, ldo_dec, do_enc, ldg_enc, do_dec, ldg_dec,
+                          dqkv_enc, ldq_enc, dqkv_dec, ldq_dec, B, Le, T, H, heads, key_idx, n_keys, key_stride, max_keys,
+                          workspace, stream, make_drop(p, seed, site));
 }

@@ -77,11 +77,14 @@ __device__ __forceinline__ float ex2_fast(float x) {
     return y;
 }
 
-template <bool X3>
+// DROP (training step): attention_probs dropout of BertSelfAttention -- the normalised probabilities are masked before
+// P.V, i.e. O = (1/l) sum_j p_j m_j v_j with the row sum l over the UNMASKED p: P is masked where it is written for
+// the tensor core, the row sum is not, and the keep scale goes into the final 1/l.  Mask addressing: common.cuh.
+template <bool X3, bool DROP>
 __global__ void __launch_bounds__(TcCfg<X3>::THREADS, X3 ? 1 : 2)
 attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, int L, int H,
                const int* __restrict__ key_idx, const int* __restrict__ n_keys, int key_stride,
-               __nv_bfloat16* __restrict__ out, long long ldo, float scale_log2) {
+               __nv_bfloat16* __restrict__ out, long long ldo, float scale_log2, DropCfg drop) {
     using Cfg = TcCfg<X3>;
     constexpr int NP = Cfg::NP;
     extern __shared__ __align__(1024) uint8_t tc_raw[];
@@ -268,6 +271,8 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         // through exp2 / pack / store).  On the first tile no maximum exists yet: it is seeded from the first 16 keys
         // of the row (already in registers) instead of a separate maximum sweep over S -- any value within 2^8 of the
         // true maximum is exact, and the rare larger excess takes the same raise-and-recompute path as later tiles.
+        uint32_t drop_x0 = 0;                              // DROP: (query << 16) | (first key of the tile >> 1)
+        const uint32_t drop_y = drop_attn_y(drop, b * (H / TC_DH) + h);
         auto exp_sweep = [&](int valid, float& m_use, bool seed, float& tile_max_raw, float& sum) {
             tile_max_raw = -INFINITY;
             sum = 0.f;
@@ -283,9 +288,14 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                         if (c * 16 + j + 1 >= valid) s1 = -INFINITY;
                     }
                     tile_max_raw = fmaxf(tile_max_raw, fmaxf(s0, s1));
-                    const float p0 = ex2_fast(fmaf(s0, scale_log2, -m_use));
-                    const float p1 = ex2_fast(fmaf(s1, scale_log2, -m_use));
+                    float p0 = ex2_fast(fmaf(s0, scale_log2, -m_use));
+                    float p1 = ex2_fast(fmaf(s1, scale_log2, -m_use));
                     sum += p0 + p1;
+                    if (DROP) {
+                        const uint32_t hsh = drop_hash(drop.s0, drop.s1, drop_x0 + (uint32_t)(c * 8 + (j >> 1)), drop_y);
+                        if ((hsh & 0xffffu) < drop.thr) p0 = 0.f;
+                        if ((hsh >> 16) < drop.thr) p1 = 0.f;
+                    }
                     ph[j >> 1] = pack_bf16x2(p0, p1);
                     if (X3) pl[j >> 1] = pack_bf16x2(p0 - bf16lo(ph[j >> 1]), p1 - bf16hi(ph[j >> 1]));
                 }
@@ -342,6 +352,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         l_run = 0.f;
         for (int t = 0; t < nt; ++t, ++g) {
             const int valid = min(TC_BK, nk - t * TC_BK);          // keys of this tile that exist
+            if (DROP) drop_x0 = drop_attn_x(q0 + r, t * TC_BK);
             mbar_wait(s_full, g & 1);       // S(t) done; MMAs retire in order, so P.V(t-1) is done as well
             tc_fence_after();
             float mt_raw, sum;
@@ -388,7 +399,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
             l_row += xch[(half ^ 1) * 128 + r];
             asm volatile("bar.sync 1, 256;" ::: "memory");      // reads done before the next query tile writes
         }
-        const float inv = l_row > 0.f ? 1.0f / l_row : 0.f;
+        const float inv = l_row > 0.f ? (DROP ? drop.scale : 1.0f) / l_row : 0.f;
         __nv_bfloat16* op = out + ((long long)b * L + row) * ldo + h * TC_DH;
 #pragma unroll
         for (int cc = 0; cc < 2 / HS; ++cc) {
@@ -428,22 +439,22 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
     }
 }
 
-template <bool X3>
+template <bool X3, bool DROP>
 static int launch_attn_tc(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads,
                           const int* key_idx, const int* n_keys, int key_stride, void* out, long long ldo,
-                          cudaStream_t st) {
+                          cudaStream_t st, DropCfg drop = DropCfg{0, 0, 0, 0, 1.f}) {
     using Cfg = TcCfg<X3>;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<X3, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) { set_error("attn_tc attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr = true;
     }
     const int n_qt = (L + TC_BQ - 1) / TC_BQ;
     dim3 grid((n_qt + TC_NQ - 1) / TC_NQ, heads, B);
-    attn_tc_kernel<X3><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(
+    attn_tc_kernel<X3, DROP><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(qkv), ld, lo_off, L, H, key_idx, n_keys, key_stride,
-        reinterpret_cast<__nv_bfloat16*>(out), ldo, 0.125f * 1.4426950408889634f);
+        reinterpret_cast<__nv_bfloat16*>(out), ldo, 0.125f * 1.4426950408889634f, drop);
     return launch_status("attn_tc");
 }
 
@@ -451,9 +462,9 @@ static int launch_attn_tc(const void* qkv, long long ld, int lo_off, int B, int 
 
 using namespace t2s;
 
-extern "C" int t2s_attn_tc(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads,
-                           const int* key_idx, const int* n_keys, int key_stride, void* out, long long ldo,
-                           void* stream) {
+static int attn_tc_entry(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads,
+                         const int* key_idx, const int* n_keys, int key_stride, void* out, long long ldo,
+                         void* stream, bool train, DropCfg drop) {
     if (H != heads * TC_DH || (ld % 8) || (ldo % 8) || (lo_off % 8) || B <= 0 || L <= 0) {
         set_error("attn_tc: head size must be 64 and pitches multiples of 8 (H %d heads %d ld %lld ldo %lld)", H, heads, ld, ldo);
         return T2S_ERR_SHAPE;
@@ -461,7 +472,26 @@ extern "C" int t2s_attn_tc(const void* qkv, long long ld, int lo_off, int B, int
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (lo_off > 0) {
         if (lo_off < 3 * H || ld < lo_off + 3 * H || ldo < 2LL * H) { set_error("attn_tc: bad hi|lo layout"); return T2S_ERR_SHAPE; }
-        return launch_attn_tc<true>(qkv, ld, lo_off, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st);
+        if (train) return launch_attn_tc<true, true>(qkv, ld, lo_off, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st, drop);
+        return launch_attn_tc<true, false>(qkv, ld, lo_off, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st);
     }
-    return launch_attn_tc<false>(qkv, ld, 0, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st);
+    if (train) return launch_attn_tc<false, true>(qkv, ld, 0, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st, drop);
+    return launch_attn_tc<false, false>(qkv, ld, 0, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st);
+}
+
+extern "C" int t2s_attn_tc(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads,
+                           const int* key_idx, const int* n_keys, int key_stride, void* out, long long ldo,
+                           void* stream) {
+    return attn_tc_entry(qkv, ld, lo_off, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, stream, false,
+                         DropCfg{0, 0, 0, 0, 1.f});
+}
+
+/* t2s_attn_tc with attention_probs dropout (training step); the query rows are positions 0..L-1 of the virtual
+ * sequence of t2s_attn_bwd_dropout, which recomputes the same mask from (seed, site) */
+extern "C" int t2s_attn_tc_dropout(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads,
+                                   const int* key_idx, const int* n_keys, int key_stride, void* out, long long ldo,
+                                   float p, unsigned long long seed, unsigned site, void* stream) {
+    if (p <= 0.f || p >= 1.f || L > 65535 || B * heads >= (1 << 20)) { set_error("attn_tc_dropout: p in (0, 1), L < 65536"); return T2S_ERR_ARG; }
+    return attn_tc_entry(qkv, ld, lo_off, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, stream, true,
+                         make_drop(p, seed, site));
 }

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(BW_THREADS)
 ln_bwd_kernel(const TH* __restrict__ h, long long ldh, const TD* __restrict__ dy, long long lddy, BwRowMap dy_map,
               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int rows, int H, int tanh_out,
               TO* __restrict__ dh, long long lddh, float* __restrict__ dgamma, float* __restrict__ dbeta,
-              float* __restrict__ dbias) {
+              float* __restrict__ dbias, TO* __restrict__ dh_drop, DropCfg drop) {
     extern __shared__ float red[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = H / 128;
@@ -161,8 +161,15 @@ ln_bwd_kernel(const TH* __restrict__ h, long long ldh, const TD* __restrict__ dy
         for (int i = 0; i < BW_MAXV; ++i)
             if (i < nv) {
                 const int e = (i * 32 + lane) * 4;
-                ac[i].x += d[i].x; ac[i].y += d[i].y; ac[i].z += d[i].z; ac[i].w += d[i].w;
                 bw_store4(dh + (long long)row * lddh + e, d[i]);
+                if (dh_drop) {
+                    // the forward was LN(dropout(Linear(.)) + residual): `dh` is the residual branch's gradient, the
+                    // Linear's output (and its bias) get the masked one
+                    const float4 m = drop_mask4(drop, row, H, e);
+                    d[i].x *= m.x; d[i].y *= m.y; d[i].z *= m.z; d[i].w *= m.w;
+                    bw_store4(dh_drop + (long long)row * lddh + e, d[i]);
+                }
+                ac[i].x += d[i].x; ac[i].y += d[i].y; ac[i].z += d[i].z; ac[i].w += d[i].w;
             }
     }
     bw_flush_cols(ag, nv, H, red, dgamma);
@@ -694,10 +701,11 @@ using namespace t2s;
 extern "C" int t2s_nce_rowstats(const float* ref, const float* pos, const float* neg, int rows, int N, float* stats,
                                 void* stream);      // scores_loss.cu
 
-extern "C" int t2s_ln_bwd(const void* h, int h_bf16, long long ldh, const void* dy, int dy_bf16, long long lddy,
-                          int dy_rows_per_group, int dy_group_rows, int dy_row_off, const float* gamma,
-                          const float* beta, float eps, int rows, int H, int tanh_out, void* dh, int dh_bf16,
-                          long long lddh, float* dgamma, float* dbeta, float* dbias, void* stream) {
+static int ln_bwd_entry(const void* h, int h_bf16, long long ldh, const void* dy, int dy_bf16, long long lddy,
+                        int dy_rows_per_group, int dy_group_rows, int dy_row_off, const float* gamma,
+                        const float* beta, float eps, int rows, int H, int tanh_out, void* dh, int dh_bf16,
+                        long long lddh, float* dgamma, float* dbeta, float* dbias, void* dh_drop, DropCfg drop,
+                        void* stream) {
     if (!bw_h_ok(H) || rows <= 0) { set_error("ln_bwd: H %d must be a multiple of 128 <= 1024", H); return T2S_ERR_SHAPE; }
     if (!dgamma || !dbeta || !dh) { set_error("ln_bwd: missing output"); return T2S_ERR_ARG; }
     BwRowMap map{dy_rows_per_group, dy_group_rows, dy_row_off};
@@ -707,7 +715,7 @@ extern "C" int t2s_ln_bwd(const void* h, int h_bf16, long long ldh, const void* 
 #define T2S_LNB(TH, TD, TO)                                                                                          \
     ln_bwd_kernel<TH, TD, TO><<<grid, BW_THREADS, smem, st>>>(reinterpret_cast<const TH*>(h), ldh,                  \
         reinterpret_cast<const TD*>(dy), lddy, map, gamma, beta, eps, rows, H, tanh_out, reinterpret_cast<TO*>(dh), \
-        lddh, dgamma, dbeta, dbias)
+        lddh, dgamma, dbeta, dbias, reinterpret_cast<TO*>(dh_drop), drop)
     typedef __nv_bfloat16 bf;
     const int key = (h_bf16 ? 4 : 0) | (dy_bf16 ? 2 : 0) | (dh_bf16 ? 1 : 0);
     switch (key) {
@@ -722,6 +730,26 @@ extern "C" int t2s_ln_bwd(const void* h, int h_bf16, long long ldh, const void* 
     }
 #undef T2S_LNB
     return launch_status("ln_bwd");
+}
+
+extern "C" int t2s_ln_bwd(const void* h, int h_bf16, long long ldh, const void* dy, int dy_bf16, long long lddy,
+                          int dy_rows_per_group, int dy_group_rows, int dy_row_off, const float* gamma,
+                          const float* beta, float eps, int rows, int H, int tanh_out, void* dh, int dh_bf16,
+                          long long lddh, float* dgamma, float* dbeta, float* dbias, void* stream) {
+    return ln_bwd_entry(h, h_bf16, ldh, dy, dy_bf16, lddy, dy_rows_per_group, dy_group_rows, dy_row_off, gamma, beta, eps,
+                        rows, H, tanh_out, dh, dh_bf16, lddh, dgamma, dbeta, dbias, nullptr, DropCfg{0, 0, 0, 0, 1.f}, stream);
+}
+
+/* backward of t2s_add_ln_dropout: dh = gradient of the pre-LayerNorm sum (the residual branch), dh_drop = dh * mask
+ * (same site / seed as the forward) = gradient of the Linear's output; dbias sums dh_drop */
+extern "C" int t2s_ln_bwd_dropout(const void* h, int h_bf16, long long ldh, const void* dy, int dy_bf16, long long lddy,
+                                  int dy_rows_per_group, int dy_group_rows, int dy_row_off, const float* gamma,
+                                  const float* beta, float eps, int rows, int H, int tanh_out, void* dh, int dh_bf16,
+                                  long long lddh, float* dgamma, float* dbeta, float* dbias, void* dh_drop, float p,
+                                  unsigned long long seed, unsigned site, void* stream) {
+    if (p < 0.f || p >= 1.f || !dh_drop) { set_error("ln_bwd_dropout: bad arguments"); return T2S_ERR_ARG; }
+    return ln_bwd_entry(h, h_bf16, ldh, dy, dy_bf16, lddy, dy_rows_per_group, dy_group_rows, dy_row_off, gamma, beta, eps,
+                        rows, H, tanh_out, dh, dh_bf16, lddh, dgamma, dbeta, dbias, dh_drop, make_drop(p, seed, site), stream);
 }
 
 extern "C" int t2s_colsum(const void* x, int x_bf16, long long ldx, int rows, int N, float* dst, void* stream) {

@@ -35,6 +35,61 @@ __device__ __forceinline__ long long clamp_index(long long i, long long n) {
     return i < 0 ? 0 : (i >= n ? n - 1 : i);
 }
 
+// ---------------------------------------------------------------- dropout (training step only)
+// Counter-based masks: nothing is stored, the backward recomputes the mask of a site from (seed, site, element).
+// One 32-bit hash serves TWO adjacent elements (its 16-bit halves against thr = round(p * 65536)), the pair being
+// (even column, odd column) of a row -- the accumulator layout of mma.sync and the per-row sweeps of the softmax both
+// own such pairs.  Kept values are scaled by 65536 / (65536 - thr), the inverse of the exact keep probability.
+//   row-major [rows, H] sites:    x = row * (H / 2) + col / 2          y = site << 20
+//   attention probabilities:      x = (query << 16) | (key >> 1)       y = (site << 20) | (sample * heads + head)
+// (query / key = positions in the virtual sequence of csrc/attn_bwd.cu: encoder rows then decoder rows; keys by their
+// position in the compacted key list, then the decoder keys).
+struct DropCfg {
+    uint32_t s0, s1;      // seed
+    uint32_t site;        // < 4096
+    uint32_t thr;         // 0 = dropout off
+    float scale;
+};
+inline DropCfg make_drop(float p, unsigned long long seed, unsigned site) {
+    DropCfg d;
+    d.s0 = (uint32_t)seed;
+    d.s1 = (uint32_t)(seed >> 32);
+    d.site = site & 0xfffu;
+    long t = lrintf(p * 65536.0f);
+    d.thr = p > 0.f ? (uint32_t)(t < 1 ? 1 : (t > 65535 ? 65535 : t)) : 0u;
+    d.scale = 65536.0f / (65536.0f - (float)d.thr);
+    return d;
+}
+__device__ __forceinline__ uint32_t drop_hash(uint32_t s0, uint32_t s1, uint32_t x, uint32_t y) {
+    uint32_t h = x ^ s0;
+    h *= 0x9E3779B1u;
+    h ^= h >> 15;
+    h += y * 0x85EBCA6Bu + s1;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 13;
+    h *= 0x27D4EB2Fu;
+    h ^= h >> 16;
+    h *= 0x165667B1u;
+    h ^= h >> 15;
+    return h;
+}
+// multipliers (0 or scale) of the element pair (x, y)
+__device__ __forceinline__ void drop_pair(const DropCfg& d, uint32_t x, uint32_t y, float& m0, float& m1) {
+    const uint32_t h = drop_hash(d.s0, d.s1, x, y);
+    m0 = (h & 0xffffu) >= d.thr ? d.scale : 0.f;
+    m1 = (h >> 16) >= d.thr ? d.scale : 0.f;
+}
+// four consecutive elements starting at the even column `col` of row `row` of a [rows, H] site
+__device__ __forceinline__ float4 drop_mask4(const DropCfg& d, int row, int H, int col) {
+    const uint32_t x = (uint32_t)row * (uint32_t)(H >> 1) + (uint32_t)(col >> 1);
+    float4 m;
+    drop_pair(d, x, d.site << 20, m.x, m.y);
+    drop_pair(d, x + 1, d.site << 20, m.z, m.w);
+    return m;
+}
+__device__ __forceinline__ uint32_t drop_attn_y(const DropCfg& d, int bh) { return (d.site << 20) | (uint32_t)bh; }
+__device__ __forceinline__ uint32_t drop_attn_x(int query, int key) { return ((uint32_t)query << 16) | ((uint32_t)key >> 1); }
+
 // ---------------------------------------------------------------- warp / block reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

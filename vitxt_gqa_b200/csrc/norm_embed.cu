@@ -39,6 +39,8 @@ __device__ __forceinline__ void store4_bf16(__nv_bfloat16* p, float4 v) {
     o.y = pack_bf16x2(v.z, v.w);
     *reinterpret_cast<uint2*>(p) = o;
 }
+__device__ __forceinline__ void store4_any(__nv_bfloat16* p, float4 v) { store4_bf16(p, v); }
+__device__ __forceinline__ void store4_any(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 // bf16 hi|lo split of 4 fp32 values: hi = bf16(v) at p, lo = bf16(v - hi) at p + lo_off
 __device__ __forceinline__ void store4_split(__nv_bfloat16* p, long long lo_off, float4 v) {
     uint2 o, l;
@@ -158,12 +160,15 @@ feat_concat_kernel(const float* __restrict__ f0, int d0, const float* __restrict
 }
 
 // ------------------------------------------------------------------------------- (residual +) LayerNorm
-template <typename TX, typename TR, bool SPLIT>
+// DROP (training step): y = LN(dropout(x) + res) as BertSelfOutput / BertOutput compute it (Linear -> dropout ->
+// LN(. + input)); the pre-LayerNorm sum is written back to `h_out` (may alias x) because the backward's LayerNorm
+// needs it.  x and h_out are not __restrict__ in that form.
+template <typename TX, typename TR, bool SPLIT, bool DROP>
 __global__ void __launch_bounds__(NE_THREADS)
-add_ln_kernel(const TX* __restrict__ x, long long ldx, const TR* __restrict__ res, long long ldr,
+add_ln_kernel(const TX* x, long long ldx, const TR* __restrict__ res, long long ldr,
               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int rows, int H,
               const float* __restrict__ tanh_base, long long ld_base, float* __restrict__ out32, long long ldo32,
-              __nv_bfloat16* __restrict__ out16, long long ldo16, RowMap map) {
+              __nv_bfloat16* __restrict__ out16, long long ldo16, RowMap map, TX* h_out, DropCfg drop) {
     const int row = blockIdx.x * (NE_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     const int nv = H / 128;
@@ -173,10 +178,15 @@ add_ln_kernel(const TX* __restrict__ x, long long ldx, const TR* __restrict__ re
         if (i < nv) {
             const int e = (i * 32 + lane) * 4;
             v[i] = load4<TX>(x + (long long)row * ldx + e);
+            if (DROP && drop.thr) {
+                const float4 m = drop_mask4(drop, row, H, e);
+                v[i].x *= m.x; v[i].y *= m.y; v[i].z *= m.z; v[i].w *= m.w;
+            }
             if (res) {
                 const float4 r = load4<TR>(res + (long long)row * ldr + e);
                 v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
             }
+            if (DROP && h_out) store4_any(h_out + (long long)row * ldx + e, v[i]);
         }
     warp_layernorm(v, nv, H, gamma, beta, eps, lane);
     const long long orow = map(row);
@@ -307,6 +317,43 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, long long ldx, in
     }
 }
 
+// in place: x[map(r), :] *= mask(r, :) * scale  (nn.Dropout on embedding rows: BertEmbeddings, obj_drop / ocr_drop of
+// t2s.py:95,118,214,253, PrevPredEmbeddings.emb_dropout t2s.py:720 -- and, in the backward, the same mask on the
+// gradient rows).  `r` is the compact row index: forward and backward address a site the same way.
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_rows_kernel(T* __restrict__ x, long long ldx, int rows, int H, RowMap map, DropCfg drop) {
+    const long long n4 = (long long)rows * (H / 4);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / (H / 4)), c = (int)(i % (H / 4)) * 4;
+        T* p = x + map(row) * ldx + c;
+        float4 v = load4<T>(p);
+        const float4 m = drop_mask4(drop, row, H, c);
+        v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+        store4_any(p, v);
+    }
+}
+// test / inspection helper: the multipliers (0 or scale) of a site, as fp32
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(float* __restrict__ out, long long n_pairs, int mode, int H, int n_query, int n_key, DropCfg drop) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pairs; i += (long long)gridDim.x * blockDim.x) {
+        float m0, m1;
+        if (mode == 0) {                       // [rows, H]: pair i = row * H/2 + col/2
+            drop_pair(drop, (uint32_t)i, drop.site << 20, m0, m1);
+            out[2 * i] = m0;
+            out[2 * i + 1] = m1;
+        } else {                               // [BH, n_query, n_key] attention probabilities
+            const int kp = (n_key + 1) / 2;
+            const int bh = (int)(i / ((long long)n_query * kp));
+            const int q = (int)((i / kp) % n_query), jp = (int)(i % kp);
+            drop_pair(drop, drop_attn_x(q, 2 * jp), drop_attn_y(drop, bh), m0, m1);
+            float* o = out + ((long long)bh * n_query + q) * n_key;
+            o[2 * jp] = m0;
+            if (2 * jp + 1 < n_key) o[2 * jp + 1] = m1;
+        }
+    }
+}
+
 static inline int rows_grid(int rows) { return (rows + NE_THREADS / 32 - 1) / (NE_THREADS / 32); }
 static inline bool h_ok(int H) { return H % 128 == 0 && H / 128 <= NE_MAXV && H > 0; }
 
@@ -340,19 +387,27 @@ extern "C" int t2s_feat_concat(const float* f0, int d0, const float* f1, int d1,
 static int add_ln_entry(bool split, const void* x, int x_bf16, long long ldx, const void* res, int res_bf16,
                         long long ldr, const float* gamma, const float* beta, float eps, int rows, int H,
                         const float* tanh_base, long long ld_base, float* out32, long long ldo32, void* out16,
-                        long long ldo16, int rows_per_group, int out_group_rows, int out_row_off, void* stream) {
+                        long long ldo16, int rows_per_group, int out_group_rows, int out_row_off, void* stream,
+                        bool train = false, void* h_out = nullptr, DropCfg drop = DropCfg{0, 0, 0, 0, 1.f}) {
     if (!h_ok(H) || rows <= 0) { set_error("add_ln: H %d must be a multiple of 128 <= 1024", H); return T2S_ERR_SHAPE; }
     if (!out32 && !out16) { set_error("add_ln: no output"); return T2S_ERR_ARG; }
+    if (train && (H % 2)) { set_error("add_ln_dropout: H must be even"); return T2S_ERR_SHAPE; }
     if (split && (!out16 || ldo16 < 2LL * H)) { set_error("add_ln_split: needs out16 with row pitch >= 2H"); return T2S_ERR_ARG; }
     RowMap map{rows_per_group, out_group_rows, out_row_off};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = rows_grid(rows);
     __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(out16);
 #define T2S_LN_LAUNCH(TX, TR, SP)                                                                                 \
-    add_ln_kernel<TX, TR, SP><<<grid, NE_THREADS, 0, st>>>(reinterpret_cast<const TX*>(x), ldx,                   \
-                                                           reinterpret_cast<const TR*>(res), ldr, gamma, beta,    \
-                                                           eps, rows, H, tanh_base, ld_base, out32, ldo32, o16,   \
-                                                           ldo16, map)
+    do {                                                                                                          \
+        if (train)                                                                                                \
+            add_ln_kernel<TX, TR, SP, true><<<grid, NE_THREADS, 0, st>>>(                                         \
+                reinterpret_cast<const TX*>(x), ldx, reinterpret_cast<const TR*>(res), ldr, gamma, beta, eps,     \
+                rows, H, tanh_base, ld_base, out32, ldo32, o16, ldo16, map, reinterpret_cast<TX*>(h_out), drop);  \
+        else                                                                                                      \
+            add_ln_kernel<TX, TR, SP, false><<<grid, NE_THREADS, 0, st>>>(                                        \
+                reinterpret_cast<const TX*>(x), ldx, reinterpret_cast<const TR*>(res), ldr, gamma, beta, eps,     \
+                rows, H, tanh_base, ld_base, out32, ldo32, o16, ldo16, map, nullptr, drop);                       \
+    } while (0)
     if (split) {
         if (x_bf16) { set_error("add_ln_split: fp32 input only"); return T2S_ERR_ARG; }
         if (res_bf16 && res) T2S_LN_LAUNCH(float, __nv_bfloat16, true);
@@ -382,6 +437,43 @@ extern "C" int t2s_add_ln_split(const void* x, int x_bf16, long long ldx, const 
                                 long long ldo16, int rows_per_group, int out_group_rows, int out_row_off, void* stream) {
     return add_ln_entry(true, x, x_bf16, ldx, res, res_bf16, ldr, gamma, beta, eps, rows, H, tanh_base, ld_base, out32,
                         ldo32, out16, ldo16, rows_per_group, out_group_rows, out_row_off, stream);
+}
+
+extern "C" int t2s_add_ln_dropout(const void* x, int x_bf16, long long ldx, const void* res, int res_bf16, long long ldr,
+                                  const float* gamma, const float* beta, float eps, int rows, int H,
+                                  const float* tanh_base, long long ld_base, float* out32, long long ldo32, void* out16,
+                                  long long ldo16, int split, int rows_per_group, int out_group_rows, int out_row_off,
+                                  void* h_out, float p, unsigned long long seed, unsigned site, void* stream) {
+    if (p < 0.f || p >= 1.f) { set_error("add_ln_dropout: p %f outside [0, 1)", p); return T2S_ERR_ARG; }
+    return add_ln_entry(split != 0, x, x_bf16, ldx, res, res_bf16, ldr, gamma, beta, eps, rows, H, tanh_base, ld_base,
+                        out32, ldo32, out16, ldo16, rows_per_group, out_group_rows, out_row_off, stream, true, h_out,
+                        make_drop(p, seed, site));
+}
+
+extern "C" int t2s_dropout_rows(void* x, int x_bf16, long long ldx, int rows, int H, int rows_per_group, int group_rows,
+                                int row_off, float p, unsigned long long seed, unsigned site, void* stream) {
+    if (rows <= 0 || H <= 0 || (H % 4) || (ldx % 4) || p < 0.f || p >= 1.f) { set_error("dropout_rows: bad arguments"); return T2S_ERR_ARG; }
+    if (p == 0.f) return T2S_OK;
+    const long long n4 = (long long)rows * (H / 4);
+    int grid = (int)((n4 + 255) / 256);
+    if (grid > num_sms() * 16) grid = num_sms() * 16;
+    RowMap map{rows_per_group, group_rows, row_off};
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (x_bf16) dropout_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(x), ldx, rows, H, map, make_drop(p, seed, site));
+    else dropout_rows_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<float*>(x), ldx, rows, H, map, make_drop(p, seed, site));
+    return launch_status("dropout_rows");
+}
+
+extern "C" int t2s_dropout_mask(float* out, int mode, int rows_or_bh, int H, int n_query, int n_key, float p,
+                                unsigned long long seed, unsigned site, void* stream) {
+    if (!out || rows_or_bh <= 0 || p < 0.f || p >= 1.f || (mode == 0 && (H <= 0 || (H % 2))) ||
+        (mode != 0 && (n_query <= 0 || n_key <= 0 || n_query > 65535))) { set_error("dropout_mask: bad arguments"); return T2S_ERR_ARG; }
+    const long long n_pairs = mode == 0 ? (long long)rows_or_bh * (H / 2) : (long long)rows_or_bh * n_query * ((n_key + 1) / 2);
+    int grid = (int)((n_pairs + 255) / 256);
+    if (grid > num_sms() * 16) grid = num_sms() * 16;
+    dropout_mask_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, n_pairs, mode, H, n_query, n_key,
+                                                                                  make_drop(p, seed, site));
+    return launch_status("dropout_mask");
 }
 
 extern "C" int t2s_split_bf16(const float* x, long long ldx, int rows, int K, int lo_off, void* out, long long ldo,

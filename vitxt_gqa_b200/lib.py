@@ -19,6 +19,7 @@ GEMM_SM_CAP_SHIFT = 8     # bits 8..15 of the GEMM flags: cap on the persistent 
 
 _p, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
 _d = ctypes.c_double
+_ull, _u = ctypes.c_ulonglong, ctypes.c_uint
 
 # name -> argtypes, in the order of include/t2s_b200.h
 SIGNATURES = {
@@ -78,6 +79,17 @@ SIGNATURES = {
     "t2s_answer_decode": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _p],
     "t2s_ground_metrics": [_p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p],
     "t2s_adam_step": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p, _f, _f, _p],
+    # dropout of the training step (masks recomputed from (p, seed, site))
+    "t2s_add_ln_dropout": [_p, _i, _ll, _p, _i, _ll, _p, _p, _f, _i, _i, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p,
+                           _f, _ull, _u, _p],
+    "t2s_dropout_rows": [_p, _i, _ll, _i, _i, _i, _i, _i, _f, _ull, _u, _p],
+    "t2s_dropout_mask": [_p, _i, _i, _i, _i, _i, _f, _ull, _u, _p],
+    "t2s_ln_bwd_dropout": [_p, _i, _ll, _p, _i, _ll, _i, _i, _i, _p, _p, _f, _i, _i, _i, _p, _i, _ll, _p, _p, _p, _p,
+                           _f, _ull, _u, _p],
+    "t2s_attn_tc_dropout": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _f, _ull, _u, _p],
+    "t2s_attn_dec_dropout": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _ll, _f, _ull, _u, _p],
+    "t2s_attn_bwd_dropout": [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _i,
+                             _p, _p, _i, _i, _p, _f, _ull, _u, _p],
 }
 PLAIN = {"t2s_abi_version": (_i, []), "t2s_last_error": (ctypes.c_char_p, []),
          "t2s_loss_workspace_bytes": (_ll, [_i, _i]), "t2s_loss_bwd_workspace_bytes": (_ll, [_i, _i]),

@@ -16,8 +16,12 @@ gradient and are left out, which is what DDP's find_unused_parameters=True arran
 
 Arithmetic: forward exactly as the eval path (fp32-class bf16x3 grounding chain, bf16 answer transformer) so the
 grounding indices match; backward in bf16 with fp32 accumulation (activation gradients bf16, parameter gradients
-fp32).  Dropout: the reference trains with dropout 0.1; this path implements p = 0 only (parity with autograd is
-checked at p = 0).
+fp32).  Dropout: the reference trains with p = 0.1 at BertEmbeddings, every BertSelfOutput / BertOutput, the attention
+probabilities, obj_drop / ocr_drop and PrevPredEmbeddings.emb_dropout (models/t2s.py:95,118,688,720 and the BertConfig
+defaults behind t2s.py:25-28); the engine reads the same probabilities from the model config and applies them with
+counter-based masks that the backward recomputes from (seed, site) -- nothing is stored (include/t2s_b200.h,
+"Dropout of the training step").  Parity with autograd is defined at p = 0 (`eng.set_dropout(False)`, or zero
+probabilities in the config); at p > 0 the masks are checked statistically and forward against backward.
 
 Schedule of the backward (per variant v in ref, pos, neg; then the shared front):
   loss -> dscores (bf16 copy) -> classifier / pointer-net dgrad + wgrad -> for each answer-transformer layer, last to
@@ -110,7 +114,7 @@ class TrainEngine:
         self._wt_key = None
         self.saved = None
         self.fwd_gen = 0
-        self.dropout_p = 0.0
+        self._read_dropout_config()
         self.grad_scale = 1.0      # set by all_reduce(): the factor that turns the summed gradients into their mean
         # gradient all-reduce overlapped with the backward (reference: DDP's bucketed all-reduce inside autograd,
         # base_trainer.py:134-137): as soon as a contiguous range of the flat gradient buffer is final, its NCCL
@@ -121,6 +125,68 @@ class TrainEngine:
         self._reduced_upto = None      # None: nothing reduced by the current backward
         self.comm_events = []          # measurement aid: [(bytes, start_event, end_event)] of the last backward
         self.time_comm = False
+
+    # ------------------------------------------------------------------ dropout
+    def _read_dropout_config(self):
+        """Dropout probabilities exactly where the reference reads them: `config.obj.dropout_prob`,
+        `config.ocr.dropout_prob` (t2s.py:95,118) and the BertConfig built from `config.text_bert` / `translayers` /
+        `mmt` (t2s.py:25-28,46), whose `hidden_dropout_prob` / `attention_probs_dropout_prob` default to 0.1."""
+        cfg = self.model.config
+
+        def bert(key):
+            node = cfg.get(key, None) if hasattr(cfg, "get") else None
+            node = dict(node) if node is not None else {}
+            return float(node.get("hidden_dropout_prob", 0.1)), float(node.get("attention_probs_dropout_prob", 0.1))
+
+        def prob(key):
+            node = cfg.get(key, None) if hasattr(cfg, "get") else None
+            return float(dict(node).get("dropout_prob", 0.0)) if node is not None else 0.0
+
+        self.drop_cfg = dict(obj=prob("obj"), ocr=prob("ocr"), text=bert("text_bert"), qtv=bert("translayers"),
+                             mmt=bert("mmt"))
+        self.dropout_enabled = True
+        self._site_ids = {}
+        self.base_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+
+    def set_dropout(self, enabled, seed=None):
+        """Switch the training-step dropout on / off (off = the p = 0 step the autograd parity tests are defined
+        at); `seed` re-bases the mask sequence."""
+        self.dropout_enabled = bool(enabled)
+        if seed is not None:
+            self.base_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+
+    @property
+    def dropout_p(self):
+        """The largest dropout probability in effect (0.0 when dropout is off) -- what bench.py reports."""
+        if not (self.dropout_enabled and getattr(self.model, "train_dropout", True)):
+            return 0.0
+        d = self.drop_cfg
+        return max(d["obj"], d["ocr"], *d["text"], *(d["qtv"] if self.is_t2s else (0.0,)), *d["mmt"])
+
+    def _p(self, key, which=None):
+        if not (self.dropout_enabled and getattr(self.model, "train_dropout", True)):
+            return 0.0
+        v = self.drop_cfg[key]
+        return v if which is None else v[which]
+
+    def _site(self, name):
+        """Small integer id of a dropout site (stable across steps; forward and backward name sites identically)."""
+        i = self._site_ids.get(name)
+        if i is None:
+            i = self._site_ids[name] = len(self._site_ids) + 1
+            if i >= 4096:
+                raise RuntimeError("too many dropout sites")
+        return i
+
+    def _step_seed(self):
+        r = 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                r = dist.get_rank()
+        except Exception:
+            pass
+        return (self.base_seed + self.fwd_gen * 0x9E3779B97F4A7C15 + r * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
 
     # ------------------------------------------------------------------ flat buffers
     DEAD_PREFIXES = ("Grounding_Module.", "linear_obj_frame_to_mmt_in.", "obj_frame_layer_norm.")
@@ -274,6 +340,9 @@ class TrainEngine:
             dy_d=torch.empty(Md, H, **b16), dy2_d=torch.empty(Md, H, **b16), dh2_d=torch.empty(Md, H, **b16),
             du_d=torch.empty(Md, 4 * H, **b16), dx1_d=torch.empty(Md, H, **b16), dh1_d=torch.empty(Md, H, **b16),
             dctx_d=torch.empty(Md, H, **b16), dqkv_d=torch.empty(Md, 3 * H, **b16),
+            # dropout: gradients of the Linear outputs behind the hidden dropouts (masked copies of dh2 / dh1)
+            dh2m=torch.empty(Me, H, **b16), dh1m=torch.empty(Me, H, **b16),
+            dh2m_d=torch.empty(Md, H, **b16), dh1m_d=torch.empty(Md, H, **b16),
             dkeyp=torch.zeros(Me, H, **b16), dq=torch.empty(Md, H, **b16),
             dS16=torch.zeros(Md, Np, **b16), dJ=torch.empty(Me, H, **f32),
             dh_obj=torch.empty(B * F, H, **b16), dh_ocr=torch.empty(B * O, H, **b16), dc_ocr=torch.empty(B * O, H, **f32),
@@ -287,22 +356,49 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ forward building blocks
     def _x3_layer_fwd(self, L, lw, x, sv, M, rows_L, keys, nk, key_stride, st, out, tanh_base=None, out16=None,
-                      remap=(0, 0, 0), next_xs=None):
+                      remap=(0, 0, 0), next_xs=None, drop=None):
         """One grounding-chain BERT layer (as model._layer_f32, bf16x3), keeping its intermediates in `sv`.
-        sv["xs"] already holds the bf16 hi|lo split of the input x."""
+        sv["xs"] already holds the bf16 hi|lo split of the input x.  drop = (p_hidden, p_attn, seed, site name)."""
         B = M // rows_L
         F32, RES, SPLIT = _lib.GEMM_OUT_F32, _lib.GEMM_RES_F32, _lib.GEMM_OUT_SPLIT
+        p_h, p_a, seed, sname = drop if drop is not None else (0.0, 0.0, 0, "")
         L.gemm_bf16x3(_ptr(sv["xs"]), 2 * H, _ptr(lw["wqkv"]), 2 * H, _ptr(lw["bqkv"]), None, 0, _ptr(sv["qkvs"]), 6 * H,
                       M, 3 * H, H, SPLIT, 0, st)
-        L.attn_tc(_ptr(sv["qkvs"]), 6 * H, 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride, _ptr(sv["ctxs"]),
-                  2 * H, st)
-        L.gemm_bf16x3(_ptr(sv["ctxs"]), 2 * H, _ptr(lw["wo"]), 2 * H, _ptr(lw["bo"]), _ptr(x), H, _ptr(sv["h1"]), H,
-                      M, H, H, F32 | RES, 0, st)
-        L.add_ln_split(_ptr(sv["h1"]), 0, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H, None, 0,
-                       _ptr(sv["x1"]), H, _ptr(sv["x1s"]), 2 * H, 0, 0, 0, st)
+        if p_a > 0:
+            L.attn_tc_dropout(_ptr(sv["qkvs"]), 6 * H, 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride,
+                              _ptr(sv["ctxs"]), 2 * H, p_a, seed, self._site(sname + ".attn"), st)
+        else:
+            L.attn_tc(_ptr(sv["qkvs"]), 6 * H, 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride, _ptr(sv["ctxs"]),
+                      2 * H, st)
+        if p_h > 0:
+            # BertSelfOutput / BertOutput with dropout: the GEMM leaves Linear(x) + bias, the LayerNorm kernel does
+            # LN(dropout(.) + input) and writes the pre-LayerNorm sum back for the backward
+            L.gemm_bf16x3(_ptr(sv["ctxs"]), 2 * H, _ptr(lw["wo"]), 2 * H, _ptr(lw["bo"]), None, 0, _ptr(sv["h1"]), H,
+                          M, H, H, F32, 0, st)
+            L.add_ln_dropout(_ptr(sv["h1"]), 0, H, _ptr(x), 0, H, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H,
+                             None, 0, _ptr(sv["x1"]), H, _ptr(sv["x1s"]), 2 * H, 1, 0, 0, 0, _ptr(sv["h1"]), p_h, seed,
+                             self._site(sname + ".h1"), st)
+        else:
+            L.gemm_bf16x3(_ptr(sv["ctxs"]), 2 * H, _ptr(lw["wo"]), 2 * H, _ptr(lw["bo"]), _ptr(x), H, _ptr(sv["h1"]), H,
+                          M, H, H, F32 | RES, 0, st)
+            L.add_ln_split(_ptr(sv["h1"]), 0, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H, None, 0,
+                           _ptr(sv["x1"]), H, _ptr(sv["x1s"]), 2 * H, 0, 0, 0, st)
         L.gemm_bf16x3(_ptr(sv["x1s"]), 2 * H, _ptr(lw["wi"]), 2 * H, _ptr(lw["bi"]), None, 0, _ptr(sv["u"]), 4 * H,
                       M, 4 * H, H, F32, 0, st)
         L.gelu_rows(_ptr(sv["u"]), 0, 4 * H, M, 4 * H, _ptr(sv["inters"]), 8 * H, 4 * H, st)
+        if p_h > 0:
+            L.gemm_bf16x3(_ptr(sv["inters"]), 8 * H, _ptr(lw["wo2"]), 8 * H, _ptr(lw["bo2"]), None, 0,
+                          _ptr(sv["h2"]), H, M, H, 4 * H, F32, 0, st)
+            site2 = self._site(sname + ".h2")
+            if next_xs is not None:
+                L.add_ln_dropout(_ptr(sv["h2"]), 0, H, _ptr(sv["x1"]), 0, H, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]),
+                                 LN_EPS_BERT, M, H, None, 0, _ptr(out), H, _ptr(next_xs), 2 * H, 1, 0, 0, 0,
+                                 _ptr(sv["h2"]), p_h, seed, site2, st)
+            else:
+                L.add_ln_dropout(_ptr(sv["h2"]), 0, H, _ptr(sv["x1"]), 0, H, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]),
+                                 LN_EPS_BERT, M, H, _ptr(tanh_base), H, _ptr(out), H, _ptr(out16), H, 0, remap[0],
+                                 remap[1], remap[2], _ptr(sv["h2"]), p_h, seed, site2, st)
+            return
         L.gemm_bf16x3(_ptr(sv["inters"]), 8 * H, _ptr(lw["wo2"]), 8 * H, _ptr(lw["bo2"]), _ptr(sv["x1"]), H,
                       _ptr(sv["h2"]), H, M, H, 4 * H, F32 | RES, 0, st)
         if next_xs is not None:
@@ -312,21 +408,36 @@ class TrainEngine:
             L.add_ln(_ptr(sv["h2"]), 0, H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H,
                      _ptr(tanh_base), H, _ptr(out), H, _ptr(out16), H, remap[0], remap[1], remap[2], st)
 
-    def _bf_layer_fwd(self, L, lw, x, ldx, qkv, sv, M, attn, st):
-        """One answer-transformer layer over M rows; `attn(qkv, ctx)` enqueues the attention of these rows."""
+    def _bf_layer_fwd(self, L, lw, x, ldx, qkv, sv, M, attn, st, drop=None):
+        """One answer-transformer layer over M rows; `attn(qkv, ctx)` enqueues the attention of these rows.
+        drop = (p_hidden, seed, site name) of the two hidden dropouts (the attention's is inside `attn`)."""
+        p_h, seed, sname = drop if drop is not None else (0.0, 0, "")
         if qkv is None:
             qkv = sv["qkv"]
             L.gemm_bf16(_ptr(x), ldx, _ptr(lw["wqkv"]), H, _ptr(lw["bqkv"]), None, 0, _ptr(qkv), 3 * H, M, 3 * H, H, 0, 0, st)
         attn(qkv, sv["ctx"])
-        L.gemm_bf16(_ptr(sv["ctx"]), H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), _ptr(x), ldx, _ptr(sv["h1"]), H, M, H, H, 0, 0, st)
-        L.add_ln(_ptr(sv["h1"]), 1, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H, None, 0, None, 0,
-                 _ptr(sv["x1"]), H, 0, 0, 0, st)
+        if p_h > 0:
+            L.gemm_bf16(_ptr(sv["ctx"]), H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), None, 0, _ptr(sv["h1"]), H, M, H, H, 0, 0, st)
+            L.add_ln_dropout(_ptr(sv["h1"]), 1, H, _ptr(x), 1, ldx, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H,
+                             None, 0, None, 0, _ptr(sv["x1"]), H, 0, 0, 0, 0, _ptr(sv["h1"]), p_h, seed,
+                             self._site(sname + ".h1"), st)
+        else:
+            L.gemm_bf16(_ptr(sv["ctx"]), H, _ptr(lw["wo"]), H, _ptr(lw["bo"]), _ptr(x), ldx, _ptr(sv["h1"]), H, M, H, H, 0, 0, st)
+            L.add_ln(_ptr(sv["h1"]), 1, H, None, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT, M, H, None, 0, None, 0,
+                     _ptr(sv["x1"]), H, 0, 0, 0, st)
         L.gemm_bf16(_ptr(sv["x1"]), H, _ptr(lw["wi"]), H, _ptr(lw["bi"]), None, 0, _ptr(sv["u"]), 4 * H, M, 4 * H, H, 0, 0, st)
         L.gelu_rows(_ptr(sv["u"]), 1, 4 * H, M, 4 * H, _ptr(sv["inter"]), 4 * H, 0, st)
-        L.gemm_bf16(_ptr(sv["inter"]), 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), _ptr(sv["x1"]), H, _ptr(sv["h2"]), H,
-                    M, H, 4 * H, 0, 0, st)
-        L.add_ln(_ptr(sv["h2"]), 1, H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H, None, 0, None, 0,
-                 _ptr(sv["out"]), H, 0, 0, 0, st)
+        if p_h > 0:
+            L.gemm_bf16(_ptr(sv["inter"]), 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), None, 0, _ptr(sv["h2"]), H,
+                        M, H, 4 * H, 0, 0, st)
+            L.add_ln_dropout(_ptr(sv["h2"]), 1, H, _ptr(sv["x1"]), 1, H, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT,
+                             M, H, None, 0, None, 0, _ptr(sv["out"]), H, 0, 0, 0, 0, _ptr(sv["h2"]), p_h, seed,
+                             self._site(sname + ".h2"), st)
+        else:
+            L.gemm_bf16(_ptr(sv["inter"]), 4 * H, _ptr(lw["wo2"]), 4 * H, _ptr(lw["bo2"]), _ptr(sv["x1"]), H, _ptr(sv["h2"]), H,
+                        M, H, 4 * H, 0, 0, st)
+            L.add_ln(_ptr(sv["h2"]), 1, H, None, 0, 0, _ptr(lw["ln2g"]), _ptr(lw["ln2b"]), LN_EPS_BERT, M, H, None, 0, None, 0,
+                     _ptr(sv["out"]), H, 0, 0, 0, st)
         return qkv
 
     # ------------------------------------------------------------------ forward
@@ -350,6 +461,11 @@ class TrainEngine:
         st = torch.cuda.current_stream(dev).cuda_stream
         f = P["f32"]
         Me, Md, Mt = B * Le, B * T, B * Lt
+        seed = self._step_seed()
+        pt_h, pt_a = self._p("text", 0), self._p("text", 1)
+        pq_h, pq_a = (self._p("qtv", 0), self._p("qtv", 1)) if self.is_t2s else (0.0, 0.0)
+        pm_h, pm_a = self._p("mmt", 0), self._p("mmt", 1)
+        p_obj, p_ocr = self._p("obj"), self._p("ocr")
 
         # ---- masks and key lists (as the eval path)
         if self.is_t2s:
@@ -367,12 +483,15 @@ class TrainEngine:
                         _ptr(f[e + "LayerNorm.weight"]), _ptr(f[e + "LayerNorm.bias"]), LN_EPS_BERT, _ptr(ws["xt"]), H, st)
         x = ws["xt"]
         n = len(P["text"])
+        if pt_h > 0:       # BertEmbeddings: LayerNorm -> dropout
+            L.dropout_rows(_ptr(x), 0, H, Mt, H, 0, 0, 0, pt_h, seed, self._site("text.emb"), st)
         L.split_bf16(_ptr(x), H, Mt, H, H, _ptr(ws["text"][0]["xs"]), 2 * H, 0, 0, 0, st)
         for i, lw in enumerate(P["text"]):
             sv, last = ws["text"][i], i == n - 1
             self._x3_layer_fwd(L, lw, x, sv, Mt, Lt, mws["keys_txt"], mws["nk_txt"], Lt, st,
                                out=mws["J0"] if last else sv["out"], remap=(Lt, Le, 0) if last else (0, 0, 0),
-                               next_xs=None if last else ws["text"][i + 1]["xs"])
+                               next_xs=None if last else ws["text"][i + 1]["xs"],
+                               drop=(pt_h, pt_a, seed, "text.%d" % i))
             x = sv["out"]
         # ---- obj / OCR encoders (model code; h_obj / h_ocr / a_*_s stay in the model workspace until backward)
         if self.is_t2s:
@@ -382,6 +501,11 @@ class TrainEngine:
             enc_inp, m4c = m._sv_encoder_inputs(inp)
             has_ids = not m4c
             m._encode_obj_ocr(L, P, mws, enc_inp, B, Lt, F, O, Le, st, m4c=m4c)
+        # obj_drop / ocr_drop (t2s.py:214,253; m4c.py:206,247) on the encoded rows of the joint buffer
+        if p_obj > 0:
+            L.dropout_rows(_ptr(mws["J0"]), 0, H, B * F, H, F, Le, Lt, p_obj, seed, self._site("obj"), st)
+        if p_ocr > 0:
+            L.dropout_rows(_ptr(mws["J0"]), 0, H, B * O, H, O, Le, Lt + F, p_ocr, seed, self._site("ocr"), st)
         if self.is_t2s:
             # ---- QTV
             x, n = mws["J0"], len(P["qtv"])
@@ -390,7 +514,8 @@ class TrainEngine:
                 sv, last = ws["qtv"][i], i == n - 1
                 self._x3_layer_fwd(L, lw, x, sv, Me, Le, mws["keys"]["ref"], mws["nk"]["ref"], Le, st,
                                    out=mws["J1"] if last else sv["out"], tanh_base=mws["J0"] if last else None,
-                                   out16=mws["X16"] if last else None, next_xs=None if last else ws["qtv"][i + 1]["xs"])
+                                   out16=mws["X16"] if last else None, next_xs=None if last else ws["qtv"][i + 1]["xs"],
+                                   drop=(pq_h, pq_a, seed, "qtv.%d" % i))
                 x = sv["out"]
             # ---- grounding (no gradient: emits constant masks, SURVEY hard part 9)
             ground_frame, ground_box, _, _, _ = m._grounding(L, P, mws, inp, B, Lt, F, O, O // F, Le, dev, st)
@@ -416,14 +541,20 @@ class TrainEngine:
         for v in variants:
             keys, nk = mws["keys"][v], mws["nk"][v]
 
-            def enc_attn(qkv, ctx, keys=keys, nk=nk):
-                L.attn_tc(_ptr(qkv), 3 * H, 0, B, Le, H, 12, _ptr(keys), _ptr(nk), Le, _ptr(ctx), H, st)
+            def enc_attn(qkv, ctx, li, keys=keys, nk=nk, v=v):
+                if pm_a > 0:        # one site per (variant, layer): encoder and decoder rows are one virtual sequence
+                    L.attn_tc_dropout(_ptr(qkv), 3 * H, 0, B, Le, H, 12, _ptr(keys), _ptr(nk), Le, _ptr(ctx), H, pm_a,
+                                      seed, self._site("mmt.%s.%d.attn" % (v, li)), st)
+                else:
+                    L.attn_tc(_ptr(qkv), 3 * H, 0, B, Le, H, 12, _ptr(keys), _ptr(nk), Le, _ptr(ctx), H, st)
 
             x = mws["X16"]
             enc_qkv[v] = []
             for li, lw in enumerate(layers):
                 sv = ws["enc"][v][li]
-                q = self._bf_layer_fwd(L, lw, x, H, mws["qkv0"] if li == 0 else None, sv, Me, enc_attn, st)
+                q = self._bf_layer_fwd(L, lw, x, H, mws["qkv0"] if li == 0 else None, sv, Me,
+                                       lambda qkv, ctx, li=li: enc_attn(qkv, ctx, li), st,
+                                       drop=(pm_h, seed, "mmt.%s.%d.enc" % (v, li)))
                 enc_qkv[v].append(q)
                 x = sv["out"]
             L.gemm_bf16(_ptr(x), H, _ptr(P["w_ptr_k"]), H, _ptr(f["ocr_ptr_net.key.bias"]), None, 0, _ptr(ws["keyp"][v]), H,
@@ -436,16 +567,22 @@ class TrainEngine:
                          _ptr(f[pp + "ocr_layer_norm.weight"]), _ptr(f[pp + "ocr_layer_norm.bias"]),
                          _ptr(f[pp + "emb_layer_norm.weight"]), _ptr(f[pp + "emb_layer_norm.bias"]), LN_EPS_BERT,
                          _ptr(ws["xd"][v]), None, H, O, st)
+            if pm_h > 0:       # PrevPredEmbeddings.emb_dropout (t2s.py:720)
+                L.dropout_rows(_ptr(ws["xd"][v]), 1, H, Md, H, 0, 0, 0, pm_h, seed, self._site("mmt.%s.prev" % v), st)
             x = ws["xd"][v]
             for li, lw in enumerate(layers):
                 sv = ws["dec"][v][li]
                 qe = enc_qkv[v][li]
 
-                def dec_attn(qkv, ctx, qe=qe, keys=keys, nk=nk):
-                    L.attn_dec(_ptr(qe), 3 * H, Le, _ptr(qkv), 3 * H, T, B, H, 12, _ptr(keys), _ptr(nk), Le, 0, T,
-                               _ptr(ctx), H, st)
+                def dec_attn(qkv, ctx, qe=qe, keys=keys, nk=nk, li=li, v=v):
+                    if pm_a > 0:
+                        L.attn_dec_dropout(_ptr(qe), 3 * H, Le, _ptr(qkv), 3 * H, T, B, H, 12, _ptr(keys), _ptr(nk), Le,
+                                           0, T, _ptr(ctx), H, pm_a, seed, self._site("mmt.%s.%d.attn" % (v, li)), st)
+                    else:
+                        L.attn_dec(_ptr(qe), 3 * H, Le, _ptr(qkv), 3 * H, T, B, H, 12, _ptr(keys), _ptr(nk), Le, 0, T,
+                                   _ptr(ctx), H, st)
 
-                self._bf_layer_fwd(L, lw, x, H, None, sv, Md, dec_attn, st)
+                self._bf_layer_fwd(L, lw, x, H, None, sv, Md, dec_attn, st, drop=(pm_h, seed, "mmt.%s.%d.dec" % (v, li)))
                 x = sv["out"]
             sc = scores[v]
             L.gemm_bf16(_ptr(x), H, _ptr(P["w_cls"]), H, _ptr(f["classifier.module.bias"]), None, 0, _ptr(sc), N,
@@ -454,7 +591,8 @@ class TrainEngine:
                         Md, H, H, 0, 0, st)
             L.ptr_score(_ptr(ws["qd"][v]), H, B, T, 0, T, ws["keyp"][v].data_ptr() + ocr_row0 * H * 2, Le * H, H, O, H,
                         jm[v].data_ptr() + ocr_row0 * 4, Le, _ptr(sc), N, V, st)
-        self.saved = dict(inp=inp, enc_inp=enc_inp, has_ids=has_ids, dims=(B, Lt, F, O, T, V, Le), enc_qkv=enc_qkv, prev=prev)
+        self.saved = dict(inp=inp, enc_inp=enc_inp, has_ids=has_ids, dims=(B, Lt, F, O, T, V, Le), enc_qkv=enc_qkv, prev=prev,
+                          seed=seed, p=dict(text=(pt_h, pt_a), qtv=(pq_h, pq_a), mmt=(pm_h, pm_a), obj=p_obj, ocr=p_ocr))
         self.fwd_gen += 1
         self.ground = (ground_frame, ground_box)
         return [scores[v] for v in self.out_variants]
@@ -464,31 +602,55 @@ class TrainEngine:
         L.gemm_wgrad_bf16(_ptr(G) if torch.is_tensor(G) else G, ldg, _ptr(X) if torch.is_tensor(X) else X, ldx, dW_ptr,
                           ldd, rows, Pn, Qn, 0, st)
 
-    def _layer_bwd_pre_attn(self, L, wt, lw, pre, sv, M, dy, sc, st, x3):
+    def _layer_bwd_pre_attn(self, L, wt, lw, pre, sv, M, dy, sc, st, x3, drop=None):
         """LN2 -> FFN -> LN1 -> attention-out of one layer over M rows.  dy: gradient of the layer output (bf16, or the
         (tensor, flags) of the QTV tail); leaves d(context) in sc["dctx"] and the LN1 input gradient in sc["dh1"].
-        `x3`: the layer is a grounding-chain layer (fp32 saved pre-activations, bf16 hi|lo operand buffers)."""
+        `x3`: the layer is a grounding-chain layer (fp32 saved pre-activations, bf16 hi|lo operand buffers).
+        drop = (p_hidden, seed, site name) of the forward's hidden dropouts: the Linear outputs (dgrad, wgrad, bias) get
+        the masked gradient sc["dh*m"], the residual branches the unmasked sc["dh*"]."""
         g = self._g
         hb = 0 if x3 else 1                     # saved pre-LayerNorm sums: fp32 in the grounding chain, bf16 in MMT
         inter, ld_inter = (sv["inters"], 8 * H) if x3 else (sv["inter"], 4 * H)
         x1, ld_x1 = (sv["x1s"], 2 * H) if x3 else (sv["x1"], H)
         ctx, ld_ctx = (sv["ctxs"], 2 * H) if x3 else (sv["ctx"], H)
         dy_t, dy_bf16, dy_map, tanh_out = dy
-        L.ln_bwd(_ptr(sv["h2"]), hb, H, _ptr(dy_t), dy_bf16, H, dy_map[0], dy_map[1], dy_map[2], _ptr(lw["ln2g"]),
-                 _ptr(lw["ln2b"]), LN_EPS_BERT, M, H, tanh_out, _ptr(sc["dh2"]), 1, H,
-                 g(pre + "output.LayerNorm.weight"), g(pre + "output.LayerNorm.bias"), g(pre + "output.dense.bias"), st)
-        L.gemm_bf16(_ptr(sc["dh2"]), H, _ptr(wt["wo2T"]), H, None, _ptr(sv["u"]), 4 * H, _ptr(sc["du"]), 4 * H, M, 4 * H, H,
+        p_h, seed, sname = drop if drop is not None else (0.0, 0, "")
+        if p_h > 0:
+            g2, g1 = sc["dh2m"], sc["dh1m"]
+            L.ln_bwd_dropout(_ptr(sv["h2"]), hb, H, _ptr(dy_t), dy_bf16, H, dy_map[0], dy_map[1], dy_map[2], _ptr(lw["ln2g"]),
+                             _ptr(lw["ln2b"]), LN_EPS_BERT, M, H, tanh_out, _ptr(sc["dh2"]), 1, H,
+                             g(pre + "output.LayerNorm.weight"), g(pre + "output.LayerNorm.bias"),
+                             g(pre + "output.dense.bias"), _ptr(g2), p_h, seed, self._site(sname + ".h2"), st)
+        else:
+            g2, g1 = sc["dh2"], sc["dh1"]
+            L.ln_bwd(_ptr(sv["h2"]), hb, H, _ptr(dy_t), dy_bf16, H, dy_map[0], dy_map[1], dy_map[2], _ptr(lw["ln2g"]),
+                     _ptr(lw["ln2b"]), LN_EPS_BERT, M, H, tanh_out, _ptr(sc["dh2"]), 1, H,
+                     g(pre + "output.LayerNorm.weight"), g(pre + "output.LayerNorm.bias"), g(pre + "output.dense.bias"), st)
+        L.gemm_bf16(_ptr(g2), H, _ptr(wt["wo2T"]), H, None, _ptr(sv["u"]), 4 * H, _ptr(sc["du"]), 4 * H, M, 4 * H, H,
                     _lib.GEMM_DGELU | (_lib.GEMM_RES_F32 if x3 else 0), 0, st)
-        self._wgrad(L, sc["dh2"], H, inter, ld_inter, g(pre + "output.dense.weight"), 4 * H, M, H, 4 * H, st)
+        self._wgrad(L, g2, H, inter, ld_inter, g(pre + "output.dense.weight"), 4 * H, M, H, 4 * H, st)
         L.colsum(_ptr(sc["du"]), 1, 4 * H, M, 4 * H, g(pre + "intermediate.dense.bias"), st)
         L.gemm_bf16(_ptr(sc["du"]), 4 * H, _ptr(wt["wiT"]), 4 * H, None, _ptr(sc["dh2"]), H, _ptr(sc["dx1"]), H, M, H, 4 * H,
                     0, 0, st)
         self._wgrad(L, sc["du"], 4 * H, x1, ld_x1, g(pre + "intermediate.dense.weight"), H, M, 4 * H, H, st)
-        L.ln_bwd(_ptr(sv["h1"]), hb, H, _ptr(sc["dx1"]), 1, H, 0, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT,
-                 M, H, 0, _ptr(sc["dh1"]), 1, H, g(pre + "attention.output.LayerNorm.weight"),
-                 g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"), st)
-        L.gemm_bf16(_ptr(sc["dh1"]), H, _ptr(wt["woT"]), H, None, None, 0, _ptr(sc["dctx"]), H, M, H, H, 0, 0, st)
-        self._wgrad(L, sc["dh1"], H, ctx, ld_ctx, g(pre + "attention.output.dense.weight"), H, M, H, H, st)
+        if p_h > 0:
+            L.ln_bwd_dropout(_ptr(sv["h1"]), hb, H, _ptr(sc["dx1"]), 1, H, 0, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]),
+                             LN_EPS_BERT, M, H, 0, _ptr(sc["dh1"]), 1, H, g(pre + "attention.output.LayerNorm.weight"),
+                             g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"),
+                             _ptr(g1), p_h, seed, self._site(sname + ".h1"), st)
+        else:
+            L.ln_bwd(_ptr(sv["h1"]), hb, H, _ptr(sc["dx1"]), 1, H, 0, 0, 0, _ptr(lw["ln1g"]), _ptr(lw["ln1b"]), LN_EPS_BERT,
+                     M, H, 0, _ptr(sc["dh1"]), 1, H, g(pre + "attention.output.LayerNorm.weight"),
+                     g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"), st)
+        L.gemm_bf16(_ptr(g1), H, _ptr(wt["woT"]), H, None, None, 0, _ptr(sc["dctx"]), H, M, H, H, 0, 0, st)
+        self._wgrad(L, g1, H, ctx, ld_ctx, g(pre + "attention.output.dense.weight"), H, M, H, H, st)
+
+    def _attn_bwd(self, L, args, p_a, seed, sname, st):
+        """t2s_attn_bwd(*args, stream), with the forward's attention-probability dropout recomputed when p_a > 0."""
+        if p_a > 0:
+            L.attn_bwd_dropout(*args, p_a, seed, self._site(sname + ".attn"), st)
+        else:
+            L.attn_bwd(*args, st)
 
     def _layer_bwd_post_attn(self, L, wt, pre, x, ldx, M, sc, dx_out, st):
         """q|k|v projection backward: sc["dqkv"] -> dx_out (+ the residual gradient sc["dh1"]); weight / bias grads."""
@@ -526,8 +688,15 @@ class TrainEngine:
         self.flat_grad[:self.live_end].zero_()
         self._begin_overlapped_reduce()
         live_v = [v for v in variants if dscores.get(v) is not None]
-        enc_sc = dict(dh2=ws["dh2"], du=ws["du"], dx1=ws["dx1"], dh1=ws["dh1"], dctx=ws["dctx"], dqkv=ws["dqkv"])
-        dec_sc = dict(dh2=ws["dh2_d"], du=ws["du_d"], dx1=ws["dx1_d"], dh1=ws["dh1_d"], dctx=ws["dctx_d"], dqkv=ws["dqkv_d"])
+        enc_sc = dict(dh2=ws["dh2"], du=ws["du"], dx1=ws["dx1"], dh1=ws["dh1"], dctx=ws["dctx"], dqkv=ws["dqkv"],
+                      dh2m=ws["dh2m"], dh1m=ws["dh1m"])
+        dec_sc = dict(dh2=ws["dh2_d"], du=ws["du_d"], dx1=ws["dx1_d"], dh1=ws["dh1_d"], dctx=ws["dctx_d"], dqkv=ws["dqkv_d"],
+                      dh2m=ws["dh2m_d"], dh1m=ws["dh1m_d"])
+        seed = sv_all["seed"]
+        pt_h, pt_a = sv_all["p"]["text"]
+        pq_h, pq_a = sv_all["p"]["qtv"]
+        pm_h, pm_a = sv_all["p"]["mmt"]
+        p_obj, p_ocr = sv_all["p"]["obj"], sv_all["p"]["ocr"]
         pp = "mmt.prev_pred_embeddings."
         first_variant = True
         for v in variants:
@@ -563,11 +732,14 @@ class TrainEngine:
                 qkv_e = sv_all["enc_qkv"][v][li]
                 x_e = mws["X16"] if li == 0 else ws["enc"][v][li - 1]["out"]
                 x_d = ws["xd"][v] if li == 0 else ws["dec"][v][li - 1]["out"]
-                self._layer_bwd_pre_attn(L, wt, lw, pre, svd, Md, (dy_d, 1, (0, 0, 0), 0), dec_sc, st, x3=False)
-                self._layer_bwd_pre_attn(L, wt, lw, pre, sve, Me, (dy_e, 1, (0, 0, 0), 0), enc_sc, st, x3=False)
-                L.attn_bwd(_ptr(qkv_e), 3 * H, _ptr(svd["qkv"]), 3 * H, _ptr(sve["ctx"]), H, _ptr(svd["ctx"]), H,
-                           _ptr(enc_sc["dctx"]), H, _ptr(dec_sc["dctx"]), H, _ptr(enc_sc["dqkv"]), 3 * H,
-                           _ptr(dec_sc["dqkv"]), 3 * H, B, Le, T, H, 12, _ptr(keys), _ptr(nk), Le, Le, _ptr(ws["attn_ws"]), st)
+                self._layer_bwd_pre_attn(L, wt, lw, pre, svd, Md, (dy_d, 1, (0, 0, 0), 0), dec_sc, st, x3=False,
+                                         drop=(pm_h, seed, "mmt.%s.%d.dec" % (v, li)))
+                self._layer_bwd_pre_attn(L, wt, lw, pre, sve, Me, (dy_e, 1, (0, 0, 0), 0), enc_sc, st, x3=False,
+                                         drop=(pm_h, seed, "mmt.%s.%d.enc" % (v, li)))
+                self._attn_bwd(L, (_ptr(qkv_e), 3 * H, _ptr(svd["qkv"]), 3 * H, _ptr(sve["ctx"]), H, _ptr(svd["ctx"]), H,
+                                   _ptr(enc_sc["dctx"]), H, _ptr(dec_sc["dctx"]), H, _ptr(enc_sc["dqkv"]), 3 * H,
+                                   _ptr(dec_sc["dqkv"]), 3 * H, B, Le, T, H, 12, _ptr(keys), _ptr(nk), Le, Le,
+                                   _ptr(ws["attn_ws"])), pm_a, seed, "mmt.%s.%d" % (v, li), st)
                 self._layer_bwd_post_attn(L, wt, pre, x_d, H, Md, dec_sc, alt_d, st)
                 self._layer_bwd_post_attn(L, wt, pre, x_e, H, Me, enc_sc, alt_e, st)
                 dy_e, alt_e = alt_e, dy_e
@@ -577,6 +749,8 @@ class TrainEngine:
             # ---- encoder-input gradient of this variant into dJ1; decoder input through PrevPredEmbeddings
             L.rows_add(_ptr(dy_e), None, None, H, Me, H, _ptr(ws["dJ"]), H, 0, 0, 0, 0 if first_variant else 1, st)
             first_variant = False
+            if pm_h > 0:       # emb_dropout of the forward: the same mask on the gradient of the decoder input rows
+                L.dropout_rows(_ptr(dy_d), 1, H, Md, H, 0, 0, 0, pm_h, seed, self._site("mmt.%s.prev" % v), st)
             L.prev_embed_bwd(_ptr(dy_d), H, _ptr(sv_all["prev"]), T, B, T, V, H, _ptr(f["classifier.module.weight"]),
                              mws["J1"].data_ptr() + ocr_row0 * H * 4, Le * H, H,
                              _ptr(f[pp + "position_embeddings.weight"]), _ptr(f[pp + "token_type_embeddings.weight"]),
@@ -599,16 +773,21 @@ class TrainEngine:
         for li in range(len(qtv) - 1, -1, -1):
             lw, wt, sv = qtv[li], W["qtv"][li], ws["qtv"][li]
             pre = "TransLayer.encoder.layer.%d." % li
-            self._layer_bwd_pre_attn(L, wt, lw, pre, sv, Me, dy, enc_sc, st, x3=True)
-            L.attn_bwd(_ptr(sv["qkvs"]), 6 * H, None, 0, _ptr(sv["ctxs"]), 2 * H, None, 0, _ptr(enc_sc["dctx"]), H, None, 0,
-                       _ptr(enc_sc["dqkv"]), 3 * H, None, 0, B, Le, 0, H, 12, _ptr(mws["keys"]["ref"]), _ptr(mws["nk"]["ref"]),
-                       Le, Le, _ptr(ws["attn_ws"]), st)
+            self._layer_bwd_pre_attn(L, wt, lw, pre, sv, Me, dy, enc_sc, st, x3=True, drop=(pq_h, seed, "qtv.%d" % li))
+            self._attn_bwd(L, (_ptr(sv["qkvs"]), 6 * H, None, 0, _ptr(sv["ctxs"]), 2 * H, None, 0, _ptr(enc_sc["dctx"]), H,
+                               None, 0, _ptr(enc_sc["dqkv"]), 3 * H, None, 0, B, Le, 0, H, 12, _ptr(mws["keys"]["ref"]),
+                               _ptr(mws["nk"]["ref"]), Le, Le, _ptr(ws["attn_ws"])), pq_a, seed, "qtv.%d" % li, st)
             self._layer_bwd_post_attn(L, wt, pre, sv["xs"], 2 * H, Me, enc_sc, ws["dy"], st)
             dy = (ws["dy"], 1, (0, 0, 0), 0)
             self._bucket_ready(pre)
         if qtv:
             L.rows_add(_ptr(ws["dy"]), None, None, H, Me, H, _ptr(ws["dJ"]), H, 0, 0, 0, 1, st)      # dJ = dJ0
 
+        # ---- obj_drop / ocr_drop of the forward: the same masks on the gradient rows of the joint buffer
+        if p_obj > 0:
+            L.dropout_rows(_ptr(ws["dJ"]), 0, H, B * F, H, F, Le, Lt, p_obj, seed, self._site("obj"), st)
+        if p_ocr > 0:
+            L.dropout_rows(_ptr(ws["dJ"]), 0, H, B * O, H, O, Le, Lt + F, p_ocr, seed, self._site("ocr"), st)
         # ---- obj encoder: J0[obj rows] = LN(W a + b)
         L.ln_bwd(_ptr(mws["h_obj"]), 0, H, _ptr(ws["dJ"]), 0, H, F, Le, Lt, _ptr(f["obj_feat_layer_norm.weight"]),
                  _ptr(f["obj_feat_layer_norm.bias"]), LN_EPS_EMBED, B * F, H, 0, _ptr(ws["dh_obj"]), 1, H,
@@ -649,13 +828,15 @@ class TrainEngine:
         for li in range(len(text) - 1, -1, -1):
             lw, wt, sv = text[li], W["text"][li], ws["text"][li]
             pre = "text_bert.encoder.layer.%d." % li
-            self._layer_bwd_pre_attn(L, wt, lw, pre, sv, Mt, dy, txt_sc, st, x3=True)
-            L.attn_bwd(_ptr(sv["qkvs"]), 6 * H, None, 0, _ptr(sv["ctxs"]), 2 * H, None, 0, _ptr(txt_sc["dctx"]), H, None, 0,
-                       _ptr(txt_sc["dqkv"]), 3 * H, None, 0, B, Lt, 0, H, 12, _ptr(mws["keys_txt"]), _ptr(mws["nk_txt"]),
-                       Lt, Lt, _ptr(ws["attn_ws"]), st)
+            self._layer_bwd_pre_attn(L, wt, lw, pre, sv, Mt, dy, txt_sc, st, x3=True, drop=(pt_h, seed, "text.%d" % li))
+            self._attn_bwd(L, (_ptr(sv["qkvs"]), 6 * H, None, 0, _ptr(sv["ctxs"]), 2 * H, None, 0, _ptr(txt_sc["dctx"]), H,
+                               None, 0, _ptr(txt_sc["dqkv"]), 3 * H, None, 0, B, Lt, 0, H, 12, _ptr(mws["keys_txt"]),
+                               _ptr(mws["nk_txt"]), Lt, Lt, _ptr(ws["attn_ws"])), pt_a, seed, "text.%d" % li, st)
             self._layer_bwd_post_attn(L, wt, pre, sv["xs"], 2 * H, Mt, txt_sc, dx_t, st)
             dy = (dx_t, 1, (0, 0, 0), 0)
             self._bucket_ready(pre)
+        if pt_h > 0:           # BertEmbeddings' dropout
+            L.dropout_rows(_ptr(dx_t), 1, H, Mt, H, 0, 0, 0, pt_h, seed, self._site("text.emb"), st)
         e = "text_bert.embeddings."
         L.bert_embed_bwd(_ptr(dx_t), H, _ptr(inp["text"]), Mt, Lt, H, _ptr(f[e + "word_embeddings.weight"]),
                          _ptr(f[e + "position_embeddings.weight"]), _ptr(f[e + "token_type_embeddings.weight"]),
