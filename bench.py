@@ -269,19 +269,36 @@ def kernel_key(name, a):
             mt = (M + 127) // 128
             bn = 256 if mt * ((N + 255) // 256) >= N_SMS else 128 if mt * ((N + 127) // 128) >= N_SMS else 64
         return "%s<%d>" % (name, bn)
-    if name == "t2s_attn_tc":
+    if name in ("t2s_attn_tc", "t2s_attn_tc_dropout"):
         return name + ("<x3>" if a[2] else "<bf16>")
     return name
 
 
-def kernel_work(name, a):
+def key_counts(model):
+    """{device pointer of an n_keys vector: sum of its entries} for every key list in the model's workspaces: the
+    attention kernels skip masked keys through compacted key lists, so their algorithmic work is 4 L sum(n_keys) H,
+    not 4 L^2 H (the `pos` / `neg` variants keep a fraction of the keys)."""
+    out = {}
+    for ws in getattr(model, "_ws", {}).values():
+        for k in ("nk", ):
+            for t in (ws.get(k) or {}).values():
+                out[t.data_ptr()] = float(t.sum().item())
+        if "nk_txt" in ws:
+            out[ws["nk_txt"].data_ptr()] = float(ws["nk_txt"].sum().item())
+    return out
+
+
+def kernel_work(name, a, nk=None):
     """(flops, bytes) one launch is asked to do, from its C-ABI arguments (include/t2s_b200.h)."""
     if name in ("t2s_gemm_bf16", "t2s_gemm_bf16x3"):     # x3: algorithmic (fp32-equivalent) flops, MMA work is 3x
         M, N, K = a[9], a[10], a[11]
         return 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N)
-    if name in ("t2s_attn_x3", "t2s_attn_tc"):
+    if name in ("t2s_attn_x3", "t2s_attn_tc", "t2s_attn_tc_dropout"):
         B, L, Hh = a[3], a[4], a[5]
-        return 4.0 * B * L * L * Hh, 16.0 * B * L * Hh
+        keys = (nk or {}).get(a[8])          # sum over the batch of the compacted key counts
+        if keys is None:
+            keys = float(B * L)              # dense upper bound when the key list is unknown
+        return 4.0 * L * keys * Hh, 16.0 * B * L * Hh
     if name == "t2s_gemm_f32":
         M, N, K = a[9], a[10], a[11]
         return 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)
@@ -336,6 +353,10 @@ def run_b200(args):
     model.train(wl["train"])
     B = args.batch or wl["batch"]
     inp = synth.make_inputs(d, B, seed=1235 + rank, full_frames=True, train=wl["train"])
+    if args.phoc == "device" and mname == "t2s":
+        # the OCR token TEXT travels (64 B per slot) and the PHOC rows are built on the device in front of the OCR
+        # encoder, instead of 604 fp32 per slot computed by CPU workers (reference processors.py:904-928)
+        synth.attach_ocr_tokens(inp, seed=77 + rank)
     if wl["train"]:
         return run_train(args, wl, model, d, inp, dev, world, rank, local)
     host = synth.to_sample_list(inp, SampleList)
@@ -483,6 +504,7 @@ def run_b200(args):
             model(resident)
         rec = L.stop_timing()
         model.overlap_sms = overlap_sms
+        nk_by_ptr = key_counts(model)
 
     parity = None
     if args.workload == "eval" and rank == 0 and mname == "t2s":
@@ -511,7 +533,7 @@ def run_b200(args):
     peaks = load_peaks()
     per = {}
     for name, a, ms in rec:
-        fl, by = kernel_work(name, a)
+        fl, by = kernel_work(name, a, nk_by_ptr)
         p = per.setdefault(kernel_key(name, a), dict(ms=0.0, n=0, flops=0.0, bytes=0.0))
         p["ms"] += ms; p["n"] += 1; p["flops"] += fl; p["bytes"] += by
     tot = sum(p["ms"] for p in per.values())
@@ -559,7 +581,8 @@ def run_b200(args):
         "config": {"workload": wl["text"], "batch_per_gpu": B, "frames": d.frames, "ocr_per_frame": d.ocr_per_frame,
                    "l2": "inputs (%.0f MB/step) and activations exceed L2" % (h2d / 1e6),
                    "algorithmic_gflop_per_sample": round(gf, 1),
-                   "decode_overlap_sms": model.overlap_sms, "api": "model(sample_list)"},
+                   "decode_overlap_sms": model.overlap_sms, "api": "model(sample_list)",
+                   "ocr_phoc": "built on the device from ocr_token_bytes" if args.phoc == "device" else "context_feature_1 from the host"},
         "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         # the same K steps through the serving API model.submit(sample_list) -> PendingForward.result(): consecutive
@@ -620,6 +643,8 @@ def train_sub_record(args, dev, world, rank, batch, steps=5, warmup=2, label="we
     model.load_state_dict(synth.make_state_dict(d, seed=0, variant="stress"))
     model = model.to(dev).train()
     inp = synth.make_inputs(d, batch, seed=2235 + rank, full_frames=True, train=True)
+    if args.phoc == "device":
+        synth.attach_ocr_tokens(inp, seed=177 + rank)
     resident = synth.to_sample_list(inp, SampleList).to(dev)
     eng = model.train_engine()
     step = train_step_fn(model, eng)
@@ -832,6 +857,9 @@ def main():
                          "stress = configs[4] (t2s_abinet with --frames x --ocr-per-frame)")
     ap.add_argument("--frames", type=int, default=128)
     ap.add_argument("--ocr-per-frame", type=int, default=15)
+    ap.add_argument("--phoc", default="device", choices=["device", "host"],
+                    help="device: the batch carries ocr_token_bytes and the PHOC rows are built on the GPU; host: it carries "
+                         "context_feature_1 (604 fp32 per OCR slot) as the reference's DataLoader produces it")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--train-steps", type=int, default=5,
                     help="eval workload: also time this many t2s_clipocr training steps -> key train_step (0 = skip)")

@@ -312,6 +312,10 @@ int t2s_attn_bwd_dropout(const void* qkv_enc, long long ld_enc, const void* qkv_
  * out [rows, 604] fp32 0/1 with row stride ldo; rows n_tokens..rows-1 are the processor's zero padding. */
 int t2s_phoc_build(const unsigned char* bytes, const int* offsets, int n_tokens, int rows, float* out, long long ldo,
                    void* stream);
+/* same descriptor from fixed-width records: token i = bytes[i * width, (i + 1) * width), zero padded (byte 0 is outside
+ * the alphabet) -- the batched `ocr_token_bytes` [B, O, width] field of a SampleList, so that the forward takes the OCR
+ * token TEXT instead of the 604 fp32 of `context_feature_1` per token (vtextgqa/dataset.py:237, processors.py:904-928) */
+int t2s_phoc_build_fixed(const unsigned char* bytes, int width, int n_tokens, float* out, long long ldo, void* stream);
 
 /* K9  Evaluation step that consumes the forward's outputs.
  * t2s_answer_decode: `pos_scores.argmax(-1)` and the EOS cut of the python loop in modules/metrics.py:186-207 (= 395-416,

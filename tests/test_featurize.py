@@ -107,3 +107,37 @@ def test_phoc_processor_and_batch_match_the_oracle_at_dataset_shape():
     assert torch.equal(r["text"], feat[1]) and int(r["length"]) == 700 and r["tokens"][700] == "<pad>"
     r2 = featurize.PhocProcessor({"max_length": 10})({"tokens": toks[0]})
     assert torch.equal(r2["text"], feat[0, :10]) and int(r2["length"]) == 10
+
+
+@pytest.mark.gpu
+def test_forward_takes_ocr_token_text_instead_of_phoc_rows():
+    """SURVEY 8f rank 2, wired: a SampleList that carries `ocr_token_bytes` (the OCR token text, 64 B per slot) instead
+    of `context_feature_1` (604 fp32 per slot) gives bit-identical outputs to one that carries the PHOC rows the
+    reference's CPU processor would have produced for the same tokens (checked against the compiled-reference golden
+    rows elsewhere in this file), in eval and in the training step."""
+    import torch
+    from parity_utils import build_b200_model, sample_list
+    from vitxt_gqa_b200 import featurize, synth
+    from oracle import phoc_oracle
+    d = synth.Dims(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2)
+    sd = synth.make_state_dict(d, seed=0, variant="stress")
+    for train in (False, True):
+        a = synth.make_inputs(d, 3, seed=41, train=train)
+        b = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in a.items()}
+        tokens = synth.attach_ocr_tokens(b, seed=7)
+        assert "context_feature_1" not in b and b["ocr_token_bytes"].shape == (3, d.ocr, 64)
+        # the float path gets the rows of the CPU restatement of cphoc.c for the same tokens
+        a["context_feature_1"] = torch.from_numpy(np.stack(
+            [np.stack([phoc_oracle.build_phoc(t) for t in toks]) for toks in tokens])).float()
+        m = build_b200_model(d, sd, train=train)
+        with torch.no_grad():
+            oa = m(sample_list(a))
+            ob = m(sample_list(b))
+        torch.cuda.synchronize()
+        for k in ("pos_scores", "ref_scores", "neg_scores", "ground_frame", "ground_box"):
+            assert torch.equal(oa[k], ob[k]), (train, k)
+    rec = featurize.pack_tokens_fixed(["Hello", "<pad>", "naïve-42"]).cuda()
+    rows = featurize.phoc_from_records(rec)
+    assert torch.equal(rows.cpu(), featurize.phoc_rows(["Hello", "<pad>", "naïve-42"]).cpu())
+    with pytest.raises(ValueError):
+        featurize.pack_tokens_fixed(["x" * 65])

@@ -456,3 +456,55 @@ def test_eval_after_weight_update_does_not_replay_a_stale_graph():
                 assert torch.equal(o, eager), "a graph captured for older weights was replayed"
             assert not torch.equal(eager, before)
             assert len(model._greedy_graphs) <= 1, "graphs of dead weight versions are kept alive"
+
+
+@pytest.mark.parametrize("frames,ocr_per_frame,with_oracle", [(256, 30, True), (256, 60, False)])
+def test_t2s_stress_sweep_corner(frames, ocr_per_frame, with_oracle):
+    """BASELINE configs[4], the far corners of the sweep: 256 frames x 30 / 60 OCR slots (L_mmt = 7 968 / 15 648; the
+    decoder attention falls back to one query per chunk, the spatial indicator keeps 15 360 slots in shared memory).
+    256 x 30, batch 1: against the CPU oracle (pinned to the real reference at 64 x 15 and 128 x 15) run on this box.
+    256 x 60: the oracle would materialise 12 x 15 648^2 fp32 probabilities per layer (11.7 GB each) -- there the checks
+    are the size-independent ones: finite scores, grounded indices inside the valid frames, decode feedback consistent
+    with the scores.  Both: the same sample inside a batch of 2 is bit-identical to the sample alone."""
+    d = synth.Dims(frames=frames, ocr_per_frame=ocr_per_frame)
+    sd = synth.make_state_dict(d, seed=0, variant="stress")
+    inp = synth.make_inputs(d, 1, seed=1300 + ocr_per_frame)
+    model = build_b200_model(d, sd)
+    sl = sample_list(inp)
+    ovr1 = {}
+    if with_oracle:
+        from oracle import t2s_oracle as O
+        with torch.no_grad():
+            ref = O.forward_t2s(sd, d, inp, schedule="dedup", return_debug=True)
+        dbg = ref["debug"]
+        ovr1 = {"pos_frame_topk": dbg["frame_pos_topk"].float(), "neg_frame_topk": dbg["frame_neg_topk"].float()}
+    model.parity_hooks = dict(ovr1, debug=True)
+    with torch.no_grad():
+        out = model(sl)
+    torch.cuda.synchronize()
+    if with_oracle:
+        assert torch.equal(out["ground_frame"].cpu(), ref["ground_frame"])
+        assert torch.equal(out["ground_box"].cpu(), ref["ground_box"])
+        _check_eval_scores("stress_f%dx%d" % (frames, ocr_per_frame), ref, out, model, sl,
+                           ("pos_scores", "ref_scores", "neg_scores"))
+    else:
+        for k in ("pos_scores", "ref_scores", "neg_scores"):
+            assert torch.isfinite(out[k]).all(), k
+        valid_ids = set(inp["frame_id"][0][inp["frame_mask"][0] > 0].tolist())
+        assert set(out["ground_frame"][0].tolist()) <= valid_ids | {0}
+        prev = model.last_debug["prev_inds"].cpu()
+        assert torch.equal(prev[:, 1:], out["pos_scores"].argmax(-1)[:, :-1].cpu())
+        jm = model.last_debug["jm_pos"].cpu()
+        assert int(jm[0, d.txt_len + frames:].sum()) == frames * min(d.ocr_topk, ocr_per_frame)      # Q3
+    two = synth.make_inputs(d, 2, seed=77, full_frames=True)
+    for k, v in two.items():
+        if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == 2:
+            v[1] = inp[k][0]
+    ovr = {k: -torch.ones(2, frames) for k in ("pos_frame_topk", "neg_frame_topk")}
+    for k, v in ovr1.items():
+        ovr[k][1] = v[0]
+    model.parity_hooks = ovr
+    with torch.no_grad():
+        out2 = model(sample_list(two))
+    for k in ("ground_frame", "ground_box", "pos_scores", "ref_scores", "neg_scores"):
+        assert torch.equal(out2[k][1:2], out[k]), ("batch-dependent result", k)

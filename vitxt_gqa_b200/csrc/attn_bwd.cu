@@ -280,6 +280,7 @@ attn_bwd_dq_kernel(AttnBwdArgs a) {
         float s[8][4], dp[8][4];
         xb_mma_nt(s, qf, Ks[buf], lane);
         xb_mma_nt(dp, gf, Vs[buf], lane);
+        uint32_t hsh = 0;
 #pragma unroll
         for (int n = 0; n < 8; ++n)
 #pragma unroll
@@ -291,8 +292,10 @@ attn_bwd_dq_kernel(AttnBwdArgs a) {
                 const float p = ok ? exp2f(s[n][j] * a.scale_log2 - lse[r]) : 0.f;
                 float dpj = dp[n][j];
                 if (a.drop.thr) {               // O = sum_j p_j m_j v_j: dL/dp_j = m_j (dO . v_j); D = dO . O is unchanged
-                    const uint32_t hsh = drop_hash(a.drop.s0, a.drop.s1, drop_attn_x(qi, key), drop_attn_y(a.drop, b * a.heads + h));
-                    const uint32_t u = (key & 1) ? (hsh >> 16) : (hsh & 0xffffu);
+                    // accumulator columns j = 0|1 (2|3) are the two keys of one mask pair: one hash serves both
+                    if ((j & 1) == 0)
+                        hsh = drop_hash(a.drop.s0, a.drop.s1, drop_attn_x(qi, key), drop_attn_y(a.drop, b * a.heads + h));
+                    const uint32_t u = (j & 1) ? (hsh >> 16) : (hsh & 0xffffu);
                     dpj = u >= a.drop.thr ? dpj * a.drop.scale : 0.f;
                 }
                 s[n][j] = p * (dpj - dd[r]) * a.scale;          // dS
@@ -387,7 +390,13 @@ attn_bwd_dkv_kernel(AttnBwdArgs a) {
                 const float p = ok ? exp2f(st[n][j] * a.scale_log2 - lse_s[qc]) : 0.f;
                 float m = 1.f;
                 if (a.drop.thr) {
-                    const uint32_t hsh = drop_hash(a.drop.s0, a.drop.s1, drop_attn_x(qi, key), drop_attn_y(a.drop, b * a.heads + h));
+                    // rows of this accumulator are keys: key and key ^ 1 (one mask pair) sit in lanes g and g ^ 1, i.e.
+                    // lane ^ 4 -- the even-g lane hashes j = 0, 1 and the odd-g lane j = 2, 3 of both, then they swap
+                    const bool mine = ((g & 1) == 0) == (j < 2);
+                    uint32_t hsh = 0;          // (the pair index key >> 1 is the same in both lanes)
+                    if (mine) hsh = drop_hash(a.drop.s0, a.drop.s1, drop_attn_x(qi, key), drop_attn_y(a.drop, b * a.heads + h));
+                    const uint32_t other = __shfl_xor_sync(0xffffffffu, hsh, 4);
+                    if (!mine) hsh = other;
                     const uint32_t u = (key & 1) ? (hsh >> 16) : (hsh & 0xffffu);
                     m = u >= a.drop.thr ? a.drop.scale : 0.f;
                 }

@@ -43,7 +43,7 @@ __device__ __forceinline__ bool phoc_hit(float a0, float a1, int region, int lev
 }
 
 __global__ void __launch_bounds__(kPhocWarps * 32)
-phoc_build_kernel(const unsigned char* __restrict__ bytes, const int* __restrict__ offsets, int n_tokens,
+phoc_build_kernel(const unsigned char* __restrict__ bytes, const int* __restrict__ offsets, int width, int n_tokens,
                   int rows, float* __restrict__ out, long long ldo) {
     __shared__ unsigned s_bits[kPhocWarps][kPhocWords + 1];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -53,7 +53,8 @@ phoc_build_kernel(const unsigned char* __restrict__ bytes, const int* __restrict
     if (lane < kPhocWords + 1) bits[lane] = 0u;
     __syncwarp();
     if (row < n_tokens) {
-        const int beg = offsets[row], end = offsets[row + 1];
+        // offsets == null: fixed-width records (`width` bytes per token, zero padded: byte 0 is outside the alphabet)
+        const int beg = offsets ? offsets[row] : row * width, end = offsets ? offsets[row + 1] : beg + width;
         // pass 1: length of the filtered word (cphoc.c:32 strlen)
         int n = 0;
         for (int p = beg; p < end; p += 32) {
@@ -125,15 +126,15 @@ static int upload_bigram_table() {
 
 }  // namespace t2s
 
-extern "C" int t2s_phoc_build(const unsigned char* bytes, const int* offsets, int n_tokens, int rows, float* out,
-                              long long ldo, void* stream) {
+static int phoc_entry(const unsigned char* bytes, const int* offsets, int width, int n_tokens, int rows, float* out,
+                      long long ldo, void* stream) {
     using namespace t2s;
-    if (n_tokens < 0 || rows < n_tokens || ldo < kPhocDim) {
+    if (n_tokens < 0 || rows < n_tokens || ldo < kPhocDim || (!offsets && (width <= 0 || (long long)rows * width > 0x7fffffffLL))) {
         set_error("t2s_phoc_build: need 0 <= n_tokens <= rows and ldo >= 604 (got %d, %d, %lld)", n_tokens, rows, ldo);
         return T2S_ERR_SHAPE;
     }
     if (rows == 0) return T2S_OK;
-    if (!out || (n_tokens > 0 && (!bytes || !offsets))) {
+    if (!out || (n_tokens > 0 && !bytes)) {
         set_error("t2s_phoc_build: null pointer");
         return T2S_ERR_ARG;
     }
@@ -149,6 +150,17 @@ extern "C" int t2s_phoc_build(const unsigned char* bytes, const int* offsets, in
         table_dev = dev;
     }
     const int grid = (rows + kPhocWarps - 1) / kPhocWarps;
-    phoc_build_kernel<<<grid, kPhocWarps * 32, 0, (cudaStream_t)stream>>>(bytes, offsets, n_tokens, rows, out, ldo);
+    phoc_build_kernel<<<grid, kPhocWarps * 32, 0, (cudaStream_t)stream>>>(bytes, offsets, width, n_tokens, rows, out, ldo);
     return launch_status("t2s_phoc_build");
+}
+
+extern "C" int t2s_phoc_build(const unsigned char* bytes, const int* offsets, int n_tokens, int rows, float* out,
+                              long long ldo, void* stream) {
+    if (n_tokens > 0 && !offsets) { t2s::set_error("t2s_phoc_build: null offsets"); return T2S_ERR_ARG; }
+    return phoc_entry(bytes, offsets, 0, n_tokens, rows, out, ldo, stream);
+}
+
+extern "C" int t2s_phoc_build_fixed(const unsigned char* bytes, int width, int n_tokens, float* out, long long ldo,
+                                    void* stream) {
+    return phoc_entry(bytes, nullptr, width, n_tokens, n_tokens, out, ldo, stream);
 }

@@ -132,7 +132,8 @@ __device__ __forceinline__ Split gumbel_split(float att, float m, float g0, floa
 }
 
 // softmax over n logits in shared memory followed by mask-renormalise; in place -> att (with -10000 on masked)
-__device__ void masked_attention(float* s, const float* m, int n, float* red) {
+template <typename TM>
+__device__ void masked_attention(float* s, const TM* m, int n, float* red) {
     float mx = -INFINITY;
     for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, s[i]);
     mx = block_max(mx, red);
@@ -141,12 +142,12 @@ __device__ void masked_attention(float* s, const float* m, int n, float* red) {
     sum = block_sum(sum, red);
     float ms = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float a = (expf(s[i] - mx) / sum) * m[i];
+        const float a = (expf(s[i] - mx) / sum) * (float)m[i];
         s[i] = a;
         ms += a;
     }
     ms = block_sum(ms, red) + 1e-12f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = m[i] == 0.f ? kMasked : s[i] / ms;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = (float)m[i] == 0.f ? kMasked : s[i] / ms;
     __syncthreads();
 }
 
@@ -237,21 +238,24 @@ spatial_select_kernel(const float* __restrict__ sim, int sim_stride, int sim_off
                       float* __restrict__ dbg_score) {
     extern __shared__ float sm[];
     float* att = sm;           // [O]
-    float* msk = att + O;      // [O]
-    float* pos = msk + O;      // [O]
+    float* pos = att + O;      // [O]
     float* neg = pos + O;      // [O]
+    // the attention mask is 0 / 1: one byte per slot, so that the long-video shapes of the stress sweep (256 frames x 60
+    // OCR slots = 15 360 slots, 13 B each) still fit the 227 KB of shared memory
+    unsigned char* msk = reinterpret_cast<unsigned char*>(neg + O);      // [O]
     __shared__ float red[33];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int kk = topk < Of ? topk : Of;
     for (int o = tid; o < O; o += blockDim.x) {
         att[o] = sim[(long long)b * sim_stride + sim_off + o];
-        msk[o] = (mode != 1 && mode != 4) ? slot_mask[(long long)b * O + o] : joint_mask[(long long)b * L + ocr_off + o];
+        const float mv = (mode != 1 && mode != 4) ? slot_mask[(long long)b * O + o] : joint_mask[(long long)b * L + ocr_off + o];
+        msk[o] = mv != 0.f ? 1 : 0;
     }
     __syncthreads();
     masked_attention(att, msk, O, red);
     for (int o = tid; o < O; o += blockDim.x) {
         if (mode == 0 || mode == 3) {
-            const Split s = gumbel_split(att[o], msk[o], gumbel[((long long)b * 2) * O + o], gumbel[((long long)b * 2 + 1) * O + o]);
+            const Split s = gumbel_split(att[o], (float)msk[o], gumbel[((long long)b * 2) * O + o], gumbel[((long long)b * 2 + 1) * O + o]);
             pos[o] = s.pos_score;
             neg[o] = s.neg_score;
         } else {
@@ -277,7 +281,7 @@ spatial_select_kernel(const float* __restrict__ sim, int sim_stride, int sim_off
             if (neg[o] == 0.f) continue;
             int before = 0;
             for (int j = 0; j < o; ++j) before += neg[j] != 0.f;
-            const float om = msk[o];
+            const float om = (float)msk[o];
             float4 bx = *reinterpret_cast<const float4*>(boxes + ((long long)b * O + o) * 4);
             bx.x *= om; bx.y *= om; bx.z *= om; bx.w *= om;
             *reinterpret_cast<float4*>(ground_box + ((long long)b * topk + before) * 4) = bx;
@@ -296,11 +300,11 @@ spatial_select_kernel(const float* __restrict__ sim, int sim_stride, int sim_off
         if (mode == 2) {
             // ablation "w/o SG" (models/t2s_wo_sg.py:503-506): every slot of the grounded frames is positive, every
             // other slot negative (pads included), ground_box = the boxes of the positive slots in slot order
-            const float slot = msk[o];
+            const float slot = (float)msk[o];
             pos_joint[(long long)b * L + ocr_off + o] = slot;
             neg_joint[(long long)b * L + ocr_off + o] = 1.f - slot;
             if (slot != 0.f) {
-                for (int j = 0; j < o; ++j) before += msk[j] != 0.f;
+                for (int j = 0; j < o; ++j) before += msk[j] != 0;
                 if (before < topk * Of)
                     *reinterpret_cast<float4*>(ground_box + ((long long)b * topk * Of + before) * 4) =
                         *reinterpret_cast<const float4*>(boxes + ((long long)b * O + o) * 4);
@@ -309,7 +313,7 @@ spatial_select_kernel(const float* __restrict__ sim, int sim_stride, int sim_off
             // mode 3 = ablation "w/o TG" (models/t2s_wo_tg.py:503-507): both masks are also multiplied by ocr_mask
             const float om = mode == 3 ? joint_mask[(long long)b * L + ocr_off + o] : 1.f;
             pos_joint[(long long)b * L + ocr_off + o] = (psel ? 1.f : 0.f) * om;
-            neg_joint[(long long)b * L + ocr_off + o] = (rn < kk ? 1.f : 0.f) * msk[o] * om;
+            neg_joint[(long long)b * L + ocr_off + o] = (rn < kk ? 1.f : 0.f) * (float)msk[o] * om;
             if (psel) {
                 // masked_select keeps slot order: index inside the frame = #selected slots before this one
                 for (int j = 0; j < i; ++j) {
@@ -462,10 +466,10 @@ extern "C" int t2s_spatial_select(const float* sim, int sim_stride, int sim_off,
     if (B <= 0 || F <= 0 || Of <= 0 || topk <= 0) { set_error("spatial_select: bad shape"); return T2S_ERR_SHAPE; }
     const int O = F * Of, L = L_joint;
     if (ocr_off < 0 || ocr_off + O > L) { set_error("spatial_select: OCR part outside the joint mask"); return T2S_ERR_SHAPE; }
-    const size_t smem = 4 * (size_t)O * sizeof(float);
+    const size_t smem = 3 * (size_t)O * sizeof(float) + (((size_t)O + 15) & ~(size_t)15);
     static size_t attr = 48 * 1024;
     if (smem > attr) {
-        if (smem > 200 * 1024) { set_error("spatial_select: %d OCR slots exceed shared memory", O); return T2S_ERR_SHAPE; }
+        if (smem > 227 * 1024) { set_error("spatial_select: %d OCR slots exceed shared memory", O); return T2S_ERR_SHAPE; }
         cudaError_t e = cudaFuncSetAttribute(spatial_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("spatial_select attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr = smem;

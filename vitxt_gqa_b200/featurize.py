@@ -33,6 +33,38 @@ def pack_tokens(tokens):
     return torch.from_numpy(data.copy()), torch.from_numpy(offsets)
 
 
+OCR_TOKEN_WIDTH = 64      # bytes per record of the `ocr_token_bytes` field (UTF-8, zero padded)
+
+
+def pack_tokens_fixed(tokens, width=OCR_TOKEN_WIDTH):
+    """tokens (list of str) -> uint8 [len(tokens), width], one zero-padded UTF-8 record per token: the per-sample
+    `ocr_token_bytes` field ([O, width]; the batch collator stacks it to [B, O, width]) that `T2S.forward` accepts
+    INSTEAD of `context_feature_1` -- the PHOC rows are then built on the device (`t2s_phoc_build_fixed`) in front of
+    the OCR encoder.  Same lower-casing rule as `pack_tokens`.  A token longer than `width` bytes raises (its
+    descriptor depends on every kept symbol): choose the width for the dataset."""
+    out = np.zeros((len(tokens), width), np.uint8)
+    for i, t in enumerate(tokens):
+        e = (t if t.isascii() else t.lower()).encode("utf-8")
+        if len(e) > width:
+            raise ValueError("OCR token of %d bytes does not fit the %d-byte record: raise `width`" % (len(e), width))
+        out[i, :len(e)] = np.frombuffer(e, np.uint8)
+    return torch.from_numpy(out)
+
+
+def phoc_from_records(records, out=None):
+    """uint8 CUDA tensor [..., width] of token records -> fp32 [n, 604] PHOC rows (n = product of the leading dims)."""
+    if not records.is_cuda or records.dtype != torch.uint8:
+        raise _lib.T2SLibraryError("phoc_from_records needs a uint8 CUDA tensor (no CPU fallback)")
+    records = records.contiguous()
+    width = records.shape[-1]
+    n = records.numel() // width
+    if out is None:
+        out = torch.empty(n, PHOC_DIM, dtype=torch.float32, device=records.device)
+    _lib.get_lib().phoc_build_fixed(records.data_ptr(), width, n, out.data_ptr(), out.stride(0),
+                                    torch.cuda.current_stream(records.device).cuda_stream)
+    return out
+
+
 def phoc_rows(tokens, rows=None, device=None, out=None):
     """PHOC rows of `tokens` -> fp32 [rows, 604] on `device` (rows >= len(tokens); extra rows are zero, the
     processor's PAD_INDEX fill).  One H2D copy of the packed bytes + one kernel launch on the current stream."""

@@ -75,6 +75,7 @@ SIGNATURES = {
     "t2s_sumsq": [_p, _ll, _p, _p, _p],
     # input featurisation
     "t2s_phoc_build": [_p, _p, _i, _i, _p, _ll, _p],
+    "t2s_phoc_build_fixed": [_p, _i, _i, _p, _ll, _p],
     # evaluation step
     "t2s_answer_decode": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _p],
     "t2s_ground_metrics": [_p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p],

@@ -550,7 +550,20 @@ class _FusionModelBase(BaseModel):
         L.add_ln(_ptr(ws["h_obj"]), 0, H, None, 0, 0, _ptr(f["obj_feat_layer_norm.weight"]),
                  _ptr(f["obj_feat_layer_norm.bias"]), LN_EPS_EMBED, B * n_obj, H, None, 0, _ptr(ws["J0"]), H, None, 0,
                  n_obj, Le, Lt, st)
-        c0, c1 = inp["context_feature_0"], inp["context_feature_1"]
+        c0 = inp["context_feature_0"]
+        if "context_feature_1" in inp:
+            c1 = inp["context_feature_1"]
+        elif "ocr_token_bytes" in inp:
+            # the OCR token TEXT came instead of its PHOC rows (vitxt_gqa_b200/featurize.py pack_tokens_fixed): build the
+            # rows here, in front of the OCR encoder -- what the reference's DataLoader workers do on the CPU
+            # (processors.py:904-928 over utils/phoc/src/cphoc.c), bit-identical
+            rec = inp["ocr_token_bytes"]
+            c1 = ws.get("phoc")
+            if c1 is None or c1.shape[0] != B * O:
+                c1 = ws["phoc"] = torch.empty(B * O, 604, device=rec.device, dtype=torch.float32)
+            L.phoc_build_fixed(_ptr(rec), rec.shape[-1], B * O, _ptr(c1), 604, st)
+        else:
+            raise KeyError("the sample list carries neither `context_feature_1` nor `ocr_token_bytes`")
         self._concat_linear(L, P, ws, "ocr", B * O,
                             (_ptr(c0), c0.shape[-1], _ptr(c1), c1.shape[-1],
                              None if m4c else _ptr(inp["temporal_id"]),
@@ -806,6 +819,8 @@ class _FusionModelBase(BaseModel):
         t0 = evs[0][1]
         return {n: t0.elapsed_time(e) for n, e in evs}
 
+    _U8 = ("ocr_token_bytes",)
+
     def _gather_inputs(self, sample_list, names):
         dev = self._device()
         if dev.type != "cuda":
@@ -813,11 +828,11 @@ class _FusionModelBase(BaseModel):
                 "the %s forward path runs only on a CUDA device (sm_100a); move the model with .to('cuda'). "
                 "There is no CPU fallback." % self.MODEL)
         out = {}
-        for n in names:
+        for n in tuple(names) + self._U8:
             if n not in sample_list:
                 continue
             t = sample_list[n]
-            want = torch.int64 if n in self._I64 else torch.float32
+            want = torch.int64 if n in self._I64 else (torch.uint8 if n in self._U8 else torch.float32)
             out[n] = t.to(device=dev, dtype=want, non_blocking=True).contiguous()
         return out
 

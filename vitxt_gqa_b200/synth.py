@@ -178,7 +178,7 @@ SAMPLE_FIELDS = ("text", "text_len", "video_feat", "frame_id", "frame_mask", "co
                  "train_prev_inds", "targets", "train_loss_mask",
                  "mid_img_feat", "middel_frame_id", "middel_frame_idx",
                  "ocr_mask_embedding", "ocr_temporal_id", "ocr_track_id", "ocr_bbox_list", "frame_mask_embedding",
-                 "frame_list")
+                 "frame_list", "ocr_token_bytes")
 
 
 def to_sample_list(inputs, sample_list_cls, with_noise=True, dataset_name="vtextgqa", dataset_type="val"):
@@ -384,6 +384,21 @@ def make_ocr_tokens(n, seed=0, pad_ratio=0.3):
             w = w[:p] + rng.choice(["'", "-", ".", ",", " ", "é", "ß", "&"]) + w[p:]
         out.append(w)
     return out
+
+
+def attach_ocr_tokens(inputs, seed=0, width=64):
+    """Replace `context_feature_1` (the PHOC rows, 604 fp32 per OCR slot) of a synthetic batch by `ocr_token_bytes`
+    (uint8 [B, O, width]): seeded scene-text-like words on the valid slots, the dataset's literal "<pad>" on the padded
+    ones (vtextgqa/dataset.py:140).  The forward then builds the PHOC rows on the device.  Returns the token lists."""
+    from .featurize import pack_tokens_fixed
+    valid = inputs["ocr_mask"].bool()
+    B, O = valid.shape
+    words = [w for w in make_ocr_tokens(B * O + 64, seed=seed, pad_ratio=0.0) if w != "<pad>" and len(w.encode()) <= width]
+    tokens = [[words[b * O + o] if valid[b, o] else "<pad>" for o in range(O)] for b in range(B)]
+    import torch as _torch
+    inputs["ocr_token_bytes"] = _torch.stack([pack_tokens_fixed(t, width) for t in tokens])
+    inputs.pop("context_feature_1", None)
+    return tokens
 
 
 # ---------------------------------------------------------------------------------------------
