@@ -37,6 +37,9 @@ extern "C" {
 int t2s_abi_version(void);
 const char* t2s_last_error(void);
 
+/* TMA tensor maps of the GEMM operands are cached per (pointer, geometry, box, device) inside the library;
+ * which = 0: hits, 1: misses (encodes) since load */
+long long t2s_tmap_cache_stats(int which);
 /* K1  C[M,N] = epi(A[M,K] . W[N,K]^T + bias (+ residual)); A, W bf16; tcgen05 + TMA + TMEM.
  * Replaces nn.Linear/addmm of BertSelfAttention.query/key/value, BertSelfOutput.dense,
  * BertIntermediate.dense(+gelu), BertOutput.dense (via models/t2s.py:622), ClassifierLayer
@@ -54,16 +57,6 @@ int t2s_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, co
 int t2s_gemm_bf16x3(const void* A, long long lda, const void* W, long long ldw, const float* bias,
                     const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K,
                     int flags, int block_n, void* stream);
-/* K1s the same contraction for the greedy-decode rows (M <= ~128, one decoder row per sample): (N/64) x splits CTAs of
- * one 64 x 64 tile each so every SM streams a slice of W; K-split partial tiles meet in `workspace`
- * (t2s_gemm_skinny_workspace_bytes; zero it ONCE before the first use -- the kernel leaves its counters zeroed) and
- * are summed in split order by the last CTA to arrive, so results are deterministic.  flags: GELU, OUT_F32,
- * RES_F32.  K, lda, ldw multiples of 8.  One workspace serves consecutive launches of one stream. */
-long long t2s_gemm_skinny_workspace_bytes(int M, int N, int K);
-int t2s_gemm_skinny_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
-                         const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K, int flags,
-                         void* workspace, long long workspace_bytes, void* stream);
-
 /* K8b weight gradient: dW[P,Q] += G[rows,P]^T . X[rows,Q] (fp32 accumulate INTO dW: zero it first).  G = gradient of
  * the layer output, X = the layer input, both bf16 row-major exactly as the forward / backward kernels wrote them
  * (MN-major tcgen05 operands: no transposed copies).  The rows are split into `splits` ranges (0 = auto) whose

@@ -532,43 +532,3 @@ def test_losses(L):
     nce = F.cross_entropy(logits, torch.zeros(B, dtype=torch.long, device="cuda"))
     assert abs(o1.item() - bce.item()) <= 1e-5 * abs(bce.item())      # rtol: fp32 elementwise, fp64 reduction
     assert abs(o2.item() - nce.item()) <= 1e-5
-
-
-# ------------------------------------------------------------------------------- K1s skinny GEMM (decode rows)
-@pytest.mark.parametrize("M,N,K,flags,res,row_stride", [
-    (64, 2304, 768, 0, False, 1), (64, 768, 768, 0, True, 12), (64, 3072, 768, tlib.GEMM_GELU, False, 12),
-    (64, 768, 3072, 0, True, 12), (64, 5000, 768, tlib.GEMM_OUT_F32, False, 12), (48, 768, 768, 0, False, 1),
-    (100, 2304, 768, 0, True, 1), (3, 200, 768, tlib.GEMM_OUT_F32, False, 1), (64, 768, 72, 0, False, 1),
-])
-def test_gemm_skinny(L, M, N, K, flags, res, row_stride):
-    rs = row_stride
-    A = rnd(M * rs, K, dtype=torch.bfloat16, seed=1)
-    W = rnd(N, K, scale=0.05, dtype=torch.bfloat16, seed=2)
-    bias = rnd(N, seed=3)
-    R = rnd(M * rs, N, dtype=torch.bfloat16, seed=4) if res else None
-    f32 = bool(flags & tlib.GEMM_OUT_F32)
-    ldc = N + (8 if f32 else 0)
-    C = torch.full((M * rs, ldc), float("nan"), device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
-    wsz = int(L.gemm_skinny_workspace_bytes(M, N, K))
-    ws = torch.zeros(wsz, device="cuda", dtype=torch.uint8)
-    outs = []
-    for _ in range(2):       # second call reuses the workspace (counters must have been left at zero)
-        C.fill_(float("nan"))
-        L.gemm_skinny_bf16(P(A), rs * K, P(W), K, P(bias), P(R), rs * N, P(C), rs * ldc, M, N, K, flags, P(ws), wsz, stream())
-        torch.cuda.synchronize()
-        outs.append(C.clone())
-    rows = torch.arange(M, device="cuda") * rs
-    ref = A[rows].float() @ W.float().t() + bias
-    if flags & tlib.GEMM_GELU:
-        ref = gelu(ref)
-    if res:
-        ref = ref + R[rows].float()
-    got = outs[0][rows][:, :N].float()
-    assert torch.isfinite(got).all()
-    tol = (2e-5 if f32 else 2 ** -8) * ref.abs().max().item() + 1e-3
-    assert (got - ref).abs().max().item() <= tol
-    assert torch.equal(outs[0][rows], outs[1][rows]) or f32 and torch.equal(outs[0][rows][:, :N], outs[1][rows][:, :N])
-    if rs > 1:       # rows between the strided ones are untouched
-        other = torch.ones(M * rs, dtype=torch.bool, device="cuda")
-        other[rows] = False
-        assert torch.isnan(outs[0][other].float()).all()

@@ -31,5 +31,5 @@ with torch.no_grad():
         if i >= 3:
             reps.append(r)
 keys = list(reps[0])
-print(json.dumps({"overlap_sms": m.overlap_sms, "skinny": m.skinny_decode,
+print(json.dumps({"overlap_sms": m.overlap_sms, 
                   "ms_since_start": {k: round(sum(r[k] for r in reps) / len(reps), 3) for k in keys}}))

@@ -24,6 +24,7 @@
 // through L2 and A streams from HBM once.
 #include "common.cuh"
 #include <stdlib.h>
+#include <mutex>
 #include "../../include/t2s_b200.h"
 
 namespace t2s {
@@ -412,10 +413,68 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// Descriptor cache: a tensor map is a pure function of (type, base pointer, rows, cols, pitch, box), and the
+// forward enqueues the same ~150 GEMMs over the same workspace / weight buffers every step, so the encoded maps are kept
+// in a small direct-mapped table instead of calling cuTensorMapEncodeTiled (a driver call, ~1 us) three times per launch.
+// A map holds no reference to the memory: a recycled pointer with the same geometry encodes to the same 128 bytes, so
+// stale entries are harmless.  One mutex: the library serves one host thread per GPU, contention is nil.
+struct TmapKey {
+    const void* ptr;
+    long long rows, cols, ld;
+    int box_cols, box_rows, f32, dev;
+    bool operator==(const TmapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols &&
+               box_rows == o.box_rows && f32 == o.f32 && dev == o.dev;
+    }
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool used; };
+constexpr int kTmapSlots = 4096;
+static TmapSlot* g_tmap_cache = nullptr;
+static std::mutex g_tmap_mutex;
+static long long g_tmap_hits = 0, g_tmap_misses = 0;
+
+static inline unsigned tmap_hash(const TmapKey& k) {
+    unsigned long long h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= (unsigned long long)k.rows * 0xC2B2AE3D27D4EB4Full + (unsigned long long)k.cols * 0x165667B19E3779F9ull;
+    h ^= (unsigned long long)k.ld * 0x27D4EB2F165667C5ull + (unsigned)(k.box_rows * 131 + k.box_cols * 7 + k.f32 + k.dev * 1009);
+    h ^= h >> 29;
+    return (unsigned)(h * 0xBF58476D1CE4E5B9ull >> 40) % kTmapSlots;
+}
+
+static int encode_tmap_2d(CUtensorMap* tm, bool f32, const void* ptr, long long rows, long long cols, long long ld,
+                          int box_cols, int box_rows);
+
 // 2D row-major [rows, cols] tensor with row pitch `ld` elements; box = box_rows x box_cols (box_cols * esize == 128 B),
 // 128B swizzle.
 static int make_tmap_2d(CUtensorMap* tm, bool f32, const void* ptr, long long rows, long long cols, long long ld,
                         int box_cols, int box_rows) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const TmapKey key{ptr, rows, cols, ld, box_cols, box_rows, f32 ? 1 : 0, dev};
+    const unsigned slot = tmap_hash(key);
+    {
+        std::lock_guard<std::mutex> lock(g_tmap_mutex);
+        if (!g_tmap_cache) g_tmap_cache = new TmapSlot[kTmapSlots]();
+        TmapSlot& s = g_tmap_cache[slot];
+        if (s.used && s.key == key) {
+            *tm = s.map;
+            ++g_tmap_hits;
+            return T2S_OK;
+        }
+    }
+    const int rc = encode_tmap_2d(tm, f32, ptr, rows, cols, ld, box_cols, box_rows);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    TmapSlot& s = g_tmap_cache[slot];
+    s.key = key;
+    s.map = *tm;
+    s.used = true;
+    ++g_tmap_misses;
+    return T2S_OK;
+}
+
+static int encode_tmap_2d(CUtensorMap* tm, bool f32, const void* ptr, long long rows, long long cols, long long ld,
+                          int box_cols, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -785,6 +844,12 @@ static int gemm_entry(const char* who, bool x3, const void* A, long long lda, co
         case 64: return launch_gemm<64, false>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
         default: set_error("%s: block_n must be 0, 64, 128 or 256", who); return T2S_ERR_ARG;
     }
+}
+
+/* hits / misses of the tensor-map descriptor cache since the library was loaded (diagnostics, tests) */
+extern "C" long long t2s_tmap_cache_stats(int which) {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    return which == 0 ? g_tmap_hits : g_tmap_misses;
 }
 
 extern "C" int t2s_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,

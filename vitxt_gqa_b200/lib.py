@@ -25,7 +25,6 @@ _ull, _u = ctypes.c_ulonglong, ctypes.c_uint
 SIGNATURES = {
     "t2s_gemm_bf16": [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p],
     "t2s_gemm_bf16x3": [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p],
-    "t2s_gemm_skinny_bf16": [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _p, _ll, _p],
     "t2s_gemm_wgrad_bf16": [_p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _p],
     "t2s_split_bf16": [_p, _ll, _i, _i, _i, _p, _ll, _i, _i, _i, _p],
     "t2s_gemm_f32": [_p, _ll, _p, _ll, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p],
@@ -95,7 +94,7 @@ SIGNATURES = {
 PLAIN = {"t2s_abi_version": (_i, []), "t2s_last_error": (ctypes.c_char_p, []),
          "t2s_loss_workspace_bytes": (_ll, [_i, _i]), "t2s_loss_bwd_workspace_bytes": (_ll, [_i, _i]),
          "t2s_attn_bwd_workspace_bytes": (_ll, [_i, _i, _i, _i]),
-         "t2s_gemm_skinny_workspace_bytes": (_ll, [_i, _i, _i])}
+         "t2s_tmap_cache_stats": (_ll, [_i])}
 
 EXPORTED_SYMBOLS = sorted(list(SIGNATURES) + list(PLAIN))
 

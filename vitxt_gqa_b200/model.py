@@ -237,8 +237,6 @@ class _FusionModelBase(BaseModel):
         self._pack_gen = 0
         self._phases_on = os.environ.get("T2S_B200_PHASES", "0") == "1"
         self._phase_events = []
-        # greedy-decode GEMMs (one row per sample) on the weight-streaming kernel instead of the 128-row tcgen05 tile
-        self.skinny_decode = os.environ.get("T2S_B200_SKINNY", str(self.config.get("b200_skinny_decode", 0))) not in ("0", "False")
         if self.attn_impl not in ("tc", "mma"):
             raise ValueError("b200_attention must be 'tc' or 'mma'")
         if self.grounding_precision not in ("bf16x3", "fp32"):
@@ -429,9 +427,6 @@ class _FusionModelBase(BaseModel):
                 for k, w in (("x", 1), ("x1", 1), ("x2", 1), ("h", 1), ("ctx", 1), ("inter", 4), ("q", 1), ("xa", 1))},
             md_qkv=[torch.empty(len(variants) * Md, 3 * H, **b16) for _ in range(n_mmt)],
             prev=torch.zeros(B, T, device=device, dtype=torch.int64),
-            skinny_ws=torch.zeros(max(int(_lib.get_lib().gemm_skinny_workspace_bytes(B, n_, k_))
-                                      for n_, k_ in ((3 * H, H), (H, H), (4 * H, H), (H, 4 * H), (V, H))),
-                                  device=device, dtype=torch.uint8),
             loss_ws=torch.empty(int(_lib.get_lib().loss_workspace_bytes(B, T)), device=device, dtype=torch.uint8),
         )
         if self.grounding_precision == "bf16x3":    # bf16 hi|lo operand buffers of t2s_gemm_bf16x3
@@ -643,14 +638,7 @@ class _FusionModelBase(BaseModel):
         def at(t, width, esize=2):            # pointer to row t0 of a [B*T, width] buffer
             return t.data_ptr() + off * width * esize
 
-        if nq == 1 and self.skinny_decode:
-            # one row per sample: weight-streaming kernel spread over all SMs (csrc/gemm_skinny.cu)
-            sk = ws["skinny_ws"]
-
-            def gemm(A, lda, W, ldw, bias, res, ldr, C, ldc, M_, N_, K_, flags, _bn, st_):
-                L.gemm_skinny_bf16(A, lda, W, ldw, bias, res, ldr, C, ldc, M_, N_, K_, flags, _ptr(sk), sk.numel(), st_)
-        else:
-            gemm = L.gemm_bf16
+        gemm = L.gemm_bf16
 
         x = ws["xd"]
         ping = [ws["xd1"], ws["xd2"]]

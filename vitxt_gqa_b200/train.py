@@ -928,7 +928,13 @@ class TrainEngine:
             comm.wait_event(ready)
             with torch.cuda.stream(comm):
                 for lo, hi in gaps:
+                    if self.time_comm:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(comm)
                     dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM)
+                    if self.time_comm:
+                        e1.record(comm)
+                        self.comm_events.append(((hi - lo) * 4, e0, e1))
         if self.time_comm:
             self._join_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             self._join_events[0].record(main)
