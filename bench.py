@@ -381,6 +381,22 @@ def run_b200(args):
 
     pipelined = bool(args.pipeline) and hasattr(model, "submit") and model.overlap_sms > 0
 
+    if args.ncu_window:
+        # profiling aid: `ncu --profile-from-start off ... bench.py --ncu-window` captures exactly ONE warmed-up forward
+        # (decode overlap off, so the launches of one stream are not interleaved with the other's)
+        model.overlap_sms = 0
+        with torch.no_grad():
+            for _ in range(3):
+                model(resident)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            model(resident)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     def resident_steps(n, pipe):
         """n forward passes over the HBM-resident batch.  pipe: the serving API (model.submit -> PendingForward):
         batch i+1 is submitted before batch i's result is collected, so the decode tail of one batch overlaps the
@@ -860,6 +876,8 @@ def main():
     ap.add_argument("--phoc", default="device", choices=["device", "host"],
                     help="device: the batch carries ocr_token_bytes and the PHOC rows are built on the GPU; host: it carries "
                          "context_feature_1 (604 fp32 per OCR slot) as the reference's DataLoader produces it")
+    ap.add_argument("--ncu-window", action="store_true",
+                    help="run three warm-up forwards, then ONE forward between cudaProfilerStart/Stop, and exit")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--train-steps", type=int, default=5,
                     help="eval workload: also time this many t2s_clipocr training steps -> key train_step (0 = skip)")

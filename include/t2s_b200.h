@@ -285,18 +285,23 @@ int t2s_ln_bwd_dropout(const void* h, int h_bf16, long long ldh, const void* dy,
                        float eps, int rows, int H, int tanh_out, void* dh, int dh_bf16, long long lddh, float* dgamma,
                        float* dbeta, float* dbias, void* dh_drop, float p, unsigned long long seed, unsigned site,
                        void* stream);
+/* The attention kernels of the training step also hand the backward what it would otherwise recompute: lse_out != null
+ * receives the log2-sum-exp of every query row, at lse_out[((b * heads + h) * rows + i) * 2] with i the row's position in
+ * the virtual sequence [encoder rows; decoder rows] (rows = lse_rows for t2s_attn_tc_dropout, L_enc + T for
+ * t2s_attn_dec_dropout) -- the {lse2, D} layout t2s_attn_bwd_dropout takes as `stats_lse`.  p = 0 is allowed. */
 int t2s_attn_tc_dropout(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads, const int* key_idx,
                         const int* n_keys, int key_stride, void* out, long long ldo, float p, unsigned long long seed,
-                        unsigned site, void* stream);
+                        unsigned site, float* lse_out, int lse_rows, void* stream);
 int t2s_attn_dec_dropout(const void* qkv_enc, long long ld_enc, int L_enc, const void* qkv_dec, long long ld_dec, int T,
                          int B, int H, int heads, const int* key_idx, const int* n_keys, int key_stride, int t0, int nq,
-                         void* out, long long ldo, float p, unsigned long long seed, unsigned site, void* stream);
+                         void* out, long long ldo, float p, unsigned long long seed, unsigned site, float* lse_out,
+                         void* stream);
 int t2s_attn_bwd_dropout(const void* qkv_enc, long long ld_enc, const void* qkv_dec, long long ld_dec, const void* o_enc,
                          long long ldo_enc, const void* o_dec, long long ldo_dec, const void* do_enc, long long ldg_enc,
                          const void* do_dec, long long ldg_dec, void* dqkv_enc, long long ldq_enc, void* dqkv_dec,
                          long long ldq_dec, int B, int Le, int T, int H, int heads, const int* key_idx,
                          const int* n_keys, int key_stride, int max_keys, void* workspace, float p,
-                         unsigned long long seed, unsigned site, void* stream);
+                         unsigned long long seed, unsigned site, float* stats_lse, void* stream);
 
 /* Input featurisation, the step before the path.  PHOC descriptor of OCR tokens: replaces the
  * reference's CPU extension pythia/utils/phoc/src/cphoc.c:12-113 + build_phoc.py:9-14 (lower-case, keep [a-z0-9])

@@ -213,24 +213,29 @@ def test_attention_dropout_forward_and_backward(L, B, Le, T, x3):
     key_idx, n_keys, lists = _keys(B, Le, 0.7, seed=Le + T)
     nkv_max = int(n_keys.max()) + T
     ms = attn_mask(L, B * heads, Le + T, nkv_max, p, seed, site)
+    # {log2-sum-exp, dO . O} per (sample, head, row): the forward kernels fill slot 0 for the backward
+    stats = torch.full((B * heads * (Le + T) * 2,), float("nan"), device="cuda")
     # ---- forward: encoder rows through the tcgen05 kernel (bf16 or bf16 hi|lo), decoder rows through attn_dec
     if x3:
         hi = qkv_e32.to(torch.bfloat16)
         qs = torch.cat([hi, (qkv_e32 - hi.float()).to(torch.bfloat16)], 1).contiguous()
         o_e = torch.empty(B * Le, 2 * H, device="cuda", dtype=torch.bfloat16)
-        L.attn_tc_dropout(P(qs), 6 * H, 3 * H, B, Le, H, heads, P(key_idx), P(n_keys), Le, P(o_e), 2 * H, p, seed, site, stream())
+        L.attn_tc_dropout(P(qs), 6 * H, 3 * H, B, Le, H, heads, P(key_idx), P(n_keys), Le, P(o_e), 2 * H, p, seed, site,
+                          P(stats), Le + T, stream())
         qkv_e = qkv_e32
     else:
         qkv_e16 = qkv_e32.to(torch.bfloat16)
         o_e = torch.empty(B * Le, H, device="cuda", dtype=torch.bfloat16)
-        L.attn_tc_dropout(P(qkv_e16), 3 * H, 0, B, Le, H, heads, P(key_idx), P(n_keys), Le, P(o_e), H, p, seed, site, stream())
+        L.attn_tc_dropout(P(qkv_e16), 3 * H, 0, B, Le, H, heads, P(key_idx), P(n_keys), Le, P(o_e), H, p, seed, site,
+                          P(stats), Le + T, stream())
         qkv_e = qkv_e16.float()
     o_d = torch.zeros(max(B * T, 1), H, device="cuda", dtype=torch.bfloat16)
     if T:
         src = qs if x3 else qkv_e16
         L.attn_dec_dropout(P(src), src.shape[1], Le, P(qkv_d), 3 * H, T, B, H, heads, P(key_idx), P(n_keys), Le, 0, T,
-                           P(o_d), H, p, seed, site, stream())
+                           P(o_d), H, p, seed, site, P(stats), stream())
     torch.cuda.synchronize()
+    assert torch.isfinite(stats.view(-1, 2)[:, 0]).all(), "a forward kernel left a row's log-sum-exp unwritten"
 
     def joint(e, d, width):
         e = e.view(B, Le, -1)[..., :width]
@@ -257,20 +262,23 @@ def test_attention_dropout_forward_and_backward(L, B, Le, T, x3):
     dqkv_e = torch.full((B * Le, 3 * H), float("nan"), device="cuda", dtype=torch.bfloat16)
     dqkv_d = torch.full((max(B * T, 1), 3 * H), float("nan"), device="cuda", dtype=torch.bfloat16)
     ws = torch.empty(int(L.attn_bwd_workspace_bytes(B, Le, T, heads)), device="cuda", dtype=torch.uint8)
-    L.attn_bwd_dropout(P(qe16), 3 * H, P(qkv_d) if T else None, 3 * H, P(oe16), H, P(od16), H, P(do_e), H,
-                       P(do_d) if T else None, H, P(dqkv_e), 3 * H, P(dqkv_d) if T else None, 3 * H, B, Le, T, H, heads,
-                       P(key_idx), P(n_keys), Le, Le, P(ws), p, seed, site, stream())
-    torch.cuda.synchronize()
     ref = torch.cat([t.grad.reshape(B, Le + T, H) for t in (q, k, v)], -1)
-    got = joint(dqkv_e.float(), dqkv_d.float(), 3 * H)
-    assert torch.isfinite(got).all()
-    for i, name in enumerate(("dq", "dk", "dv")):
-        e = rel_l2(got[..., i * H:(i + 1) * H], ref[..., i * H:(i + 1) * H])
-        assert e <= 3e-2, (name, e)
+    for stats_arg in (None, stats):       # statistics recomputed by the backward / taken from the forward kernels
+        dqkv_e.fill_(float("nan"))
+        dqkv_d.fill_(float("nan"))
+        L.attn_bwd_dropout(P(qe16), 3 * H, P(qkv_d) if T else None, 3 * H, P(oe16), H, P(od16), H, P(do_e), H,
+                           P(do_d) if T else None, H, P(dqkv_e), 3 * H, P(dqkv_d) if T else None, 3 * H, B, Le, T, H, heads,
+                           P(key_idx), P(n_keys), Le, Le, P(ws), p, seed, site, P(stats_arg), stream())
+        torch.cuda.synchronize()
+        got = joint(dqkv_e.float(), dqkv_d.float(), 3 * H)
+        assert torch.isfinite(got).all()
+        for i, name in enumerate(("dq", "dk", "dv")):
+            e = rel_l2(got[..., i * H:(i + 1) * H], ref[..., i * H:(i + 1) * H])
+            assert e <= 3e-2, (name, e, stats_arg is not None)
     # a backward with ANOTHER site's mask is measurably wrong: the test can tell the masks apart
     L.attn_bwd_dropout(P(qe16), 3 * H, P(qkv_d) if T else None, 3 * H, P(oe16), H, P(od16), H, P(do_e), H,
                        P(do_d) if T else None, H, P(dqkv_e), 3 * H, P(dqkv_d) if T else None, 3 * H, B, Le, T, H, heads,
-                       P(key_idx), P(n_keys), Le, Le, P(ws), p, seed, site + 1, stream())
+                       P(key_idx), P(n_keys), Le, Le, P(ws), p, seed, site + 1, None, stream())
     torch.cuda.synchronize()
     assert rel_l2(joint(dqkv_e.float(), dqkv_d.float(), 3 * H)[..., 2 * H:], ref[..., 2 * H:]) > 0.1
 

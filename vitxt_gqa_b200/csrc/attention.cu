@@ -544,7 +544,7 @@ attn_dec_kernel(const __nv_bfloat16* __restrict__ qkv_enc, long long ld_enc, int
                 const __nv_bfloat16* __restrict__ qkv_dec, long long ld_dec, int T, int H,
                 const int* __restrict__ key_idx, const int* __restrict__ n_keys, int key_stride,
                 int t0, int nq, __nv_bfloat16* __restrict__ out, long long ldo, float scale, int max_keys,
-                DropCfg drop) {
+                DropCfg drop, float* __restrict__ lse_out) {
     extern __shared__ __align__(16) float dsm[];
     float* Qs = dsm;                                   // [AD_MAXQ][64], pre-scaled
     float* Ss = Qs + AD_MAXQ * DH;                     // [QC][max_keys]
@@ -618,7 +618,12 @@ attn_dec_kernel(const __nv_bfloat16* __restrict__ qkv_enc, long long ld_enc, int
                 srow[k] = p;
                 sum += p;
             }
-            const float inv = 1.0f / warp_sum(sum);
+            sum = warp_sum(sum);
+            const float inv = 1.0f / sum;
+            // training step: the row's log2-sum-exp in the {lse2, D} layout of t2s_attn_bwd's statistics buffer
+            if (lse_out && lane == 0)
+                lse_out[(((long long)b * gridDim.x + h) * (L_enc + T) + L_enc + t0 + q0 + q) * 2] =
+                    (mx + logf(sum)) * 1.4426950408889634f;
             if (drop.thr) {
                 // attention_probs dropout (training step): query = decoder position L_enc + t of the virtual sequence,
                 // key k = position in [compacted encoder keys; decoder keys] -- as t2s_attn_bwd_dropout recomputes it
@@ -743,7 +748,7 @@ extern "C" int t2s_attn_x3(const void* qkv, long long ld, int lo_off, int B, int
 
 static int attn_dec_entry(const void* qkv_enc, long long ld_enc, int L_enc, const void* qkv_dec, long long ld_dec,
                           int T, int B, int H, int heads, const int* key_idx, const int* n_keys, int key_stride,
-                          int t0, int nq, void* out, long long ldo, void* stream, DropCfg drop) {
+                          int t0, int nq, void* out, long long ldo, void* stream, DropCfg drop, float* lse_out = nullptr) {
     if (H != heads * DH || nq < 1 || nq > AD_MAXQ || t0 < 0 || t0 + nq > T || (ld_enc % 8) || (ld_dec % 8)) {
         set_error("attn_dec: bad arguments (H %d heads %d t0 %d nq %d T %d)", H, heads, t0, nq, T);
         return T2S_ERR_SHAPE;
@@ -777,13 +782,13 @@ static int attn_dec_entry(const void* qkv_enc, long long ld_enc, int L_enc, cons
     __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(out);
     if (qc == 1)
         attn_dec_kernel<1><<<grid, AD_THREADS, smem, st>>>(pe, ld_enc, L_enc, pd, ld_dec, T, H, key_idx, n_keys,
-                                                           key_stride, t0, nq, po, ldo, 0.125f, max_keys, drop);
+                                                           key_stride, t0, nq, po, ldo, 0.125f, max_keys, drop, lse_out);
     else if (qc == 4)
         attn_dec_kernel<4><<<grid, AD_THREADS, smem, st>>>(pe, ld_enc, L_enc, pd, ld_dec, T, H, key_idx, n_keys,
-                                                           key_stride, t0, nq, po, ldo, 0.125f, max_keys, drop);
+                                                           key_stride, t0, nq, po, ldo, 0.125f, max_keys, drop, lse_out);
     else
         attn_dec_kernel<12><<<grid, AD_THREADS, smem, st>>>(pe, ld_enc, L_enc, pd, ld_dec, T, H, key_idx, n_keys,
-                                                            key_stride, t0, nq, po, ldo, 0.125f, max_keys, drop);
+                                                            key_stride, t0, nq, po, ldo, 0.125f, max_keys, drop, lse_out);
     return launch_status("attn_dec");
 }
 
@@ -794,12 +799,14 @@ extern "C" int t2s_attn_dec(const void* qkv_enc, long long ld_enc, int L_enc, co
                           out, ldo, stream, DropCfg{0, 0, 0, 0, 1.f});
 }
 
-/* t2s_attn_dec with attention_probs dropout (training step; decoder rows = positions L_enc + t of the virtual sequence) */
+/* t2s_attn_dec of the training step (decoder rows = positions L_enc + t of the virtual sequence): attention_probs
+ * dropout (p may be 0) and, when lse_out != null, the rows' log2-sum-exp at
+ * lse_out[((b * heads + h) * (L_enc + T) + L_enc + t) * 2] */
 extern "C" int t2s_attn_dec_dropout(const void* qkv_enc, long long ld_enc, int L_enc, const void* qkv_dec,
                                     long long ld_dec, int T, int B, int H, int heads, const int* key_idx,
                                     const int* n_keys, int key_stride, int t0, int nq, void* out, long long ldo, float p,
-                                    unsigned long long seed, unsigned site, void* stream) {
-    if (p <= 0.f || p >= 1.f || L_enc + T > 65535) { set_error("attn_dec_dropout: p in (0, 1), L < 65536"); return T2S_ERR_ARG; }
+                                    unsigned long long seed, unsigned site, float* lse_out, void* stream) {
+    if (p < 0.f || p >= 1.f || L_enc + T > 65535) { set_error("attn_dec_dropout: p in [0, 1), L < 65536"); return T2S_ERR_ARG; }
     return attn_dec_entry(qkv_enc, ld_enc, L_enc, qkv_dec, ld_dec, T, B, H, heads, key_idx, n_keys, key_stride, t0, nq,
-                          out, ldo, stream, make_drop(p, seed, site));
+                          out, ldo, stream, make_drop(p, seed, site), lse_out);
 }

@@ -10,15 +10,20 @@
 // decoder rows.  allowed(i, j) = j < nk  ||  (i >= Le && j - nk <= i - Le).  Masked keys are skipped exactly as in the
 // forward kernels (exp(-10000 - max) == 0 in fp32).
 //
-// Three kernels, all bf16 mma.sync m16n8k16 with fp32 accumulation, 64 x 64 tiles, K/V (or Q/dO) tiles double
-// buffered with cp.async into XOR-swizzled shared memory:
+// Kernels, all bf16 mma.sync m16n8k16 with fp32 accumulation, 64 x 64 tiles, K/V (or Q/dO) tiles double buffered with
+// cp.async into XOR-swizzled shared memory:
 //   attn_bwd_stats   lse2[i] = log2 sum_j exp2(s_ij) (s in the exp2 domain) and D[i] = dO_i . O_i
-//   attn_bwd_dq      per 64-query tile, loop over key tiles:  P = exp2(S - lse), dP = dO V^T, dS = P (dP - D) / 8,
-//                    dQ += dS K
-//   attn_bwd_dkv     per 64-key tile, loop over query tiles: the transposed products; dV += P^T dO, dK += dS^T Q
-// No atomics: every dQ / dK / dV row is written by exactly one CTA (rows that are not in a key list keep the zeros
-// the entry point memsets), so the result is run-to-run identical.
+//   attn_bwd_dkv     per 64-key tile, loop over query tiles: S^T = K Q^T, dP^T = V dO^T, P^T = exp2(S^T - lse),
+//                    dS^T = P^T (dP^T - D) / 8; dV += P^T dO, dK += dS^T Q -- and, from the same dS^T (transposed through
+//                    shared memory), this key tile's share of dQ = dS K, added into an fp32 buffer with red.global.add
+//                    (the key tiles of a query row run in different CTAs); attn_bwd_dq_store converts it to bf16.
+//                    Five products per tile pair instead of the seven of a separate dQ pass (S and dP were recomputed).
+//   attn_bwd_dq      the separate, atomic-free dQ pass (per 64-query tile, loop over key tiles); kept for
+//                    T2S_ATTN_BWD_FUSED=0 (run-to-run identical results; the fp32 adds of the fused form commute only
+//                    up to rounding).
+// dK / dV rows are written by exactly one CTA (rows that are not in a key list keep the zeros the entry point memsets).
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/t2s_b200.h"
 
 namespace t2s {
@@ -53,6 +58,8 @@ struct AttnBwdArgs {
     __nv_bfloat16* dqkv_dec; long long ldq_dec;
     const int* key_idx; const int* n_keys; int key_stride;
     float* stats;                                           // [B, heads, Le + T, 2] = {lse2, D}
+    float* dq32;                                            // fused form: [B * (Le + T), H] fp32 dQ accumulator (zeroed)
+    int have_lse;                                           // stats[..][0] was written by the forward kernels
     int Le, T, H, heads;
     float scale_log2, scale;
     DropCfg drop;                                           // attention_probs dropout of the forward (thr == 0: none)
@@ -156,12 +163,14 @@ attn_bwd_stats_kernel(AttnBwdArgs a) {
     const int ntiles = (nkv + XB - 1) / XB;
     const int col = h * XDH;
 
-    xb_load_qtile(Qs, a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, i0, nq, col);
-    xb_load_ktile(Ks[0], a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, kidx, nk, 0, nkv, a.H + col);
-    cp_async_commit();
     float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
     uint32_t qf[4][4];
-    for (int t = 0; t < ntiles; ++t) {
+    if (!a.have_lse) {
+        xb_load_qtile(Qs, a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, i0, nq, col);
+        xb_load_ktile(Ks[0], a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, kidx, nk, 0, nkv, a.H + col);
+        cp_async_commit();
+    }
+    for (int t = 0; t < (a.have_lse ? 0 : ntiles); ++t) {
         const int buf = t & 1;
         if (t + 1 < ntiles)
             xb_load_ktile(Ks[buf ^ 1], a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, kidx, nk, (t + 1) * XB, nkv, a.H + col);
@@ -224,7 +233,7 @@ attn_bwd_stats_kernel(AttnBwdArgs a) {
         d += __shfl_xor_sync(0xffffffffu, d, 2);
         if (qi < nq && tq == 0) {
             float* st = a.stats + (((long long)b * a.heads + h) * nq + qi) * 2;
-            st[0] = m_i[r] + log2f(l_i[r]);
+            if (!a.have_lse) st[0] = m_i[r] + log2f(l_i[r]);
             st[1] = d;
         }
     }
@@ -319,7 +328,8 @@ attn_bwd_dq_kernel(AttnBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------- dK, dV
-constexpr int XB_DKV_SMEM = 2 * XB * 128 /*K,V own tiles*/ + 2 * 2 * XB * 128 /*Q,dO x 2 stages*/ + 2 * 2 * XB * 4 /*stats*/;
+constexpr int XB_DKV_SMEM = 2 * XB * 128 /*K,V own tiles*/ + 2 * 2 * XB * 128 /*Q,dO x 2 stages*/ + 2 * 2 * XB * 4 /*stats*/
+                            + XB * 128 /*dS^T tile of the fused dQ product*/;
 
 __global__ void __launch_bounds__(XB_THREADS)
 attn_bwd_dkv_kernel(AttnBwdArgs a) {
@@ -328,6 +338,7 @@ attn_bwd_dkv_kernel(AttnBwdArgs a) {
     uint8_t* Qs = KV + 2 * XB * 128;                     // [2 stages][64*128]
     uint8_t* Gs = Qs + 2 * XB * 128;                     // [2 stages][64*128] dO
     float* Ss = reinterpret_cast<float*>(Gs + 2 * XB * 128);     // [2 stages][2][64]: lse2, D
+    uint8_t* Ts = reinterpret_cast<uint8_t*>(Ss + 2 * 2 * XB);   // [64 keys][64 queries] bf16: dS^T of this iteration
     const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * XB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const int nq = a.Le + a.T;
@@ -408,6 +419,48 @@ attn_bwd_dkv_kernel(AttnBwdArgs a) {
         xb_mma_nn(dv, pf, gt, lane);          // dV += P^T . dO
         xb_c_to_a(pf, dpt);
         xb_mma_nn(dk, pf, qt, lane);          // dK += dS^T . Q
+        if (a.dq32) {
+            // dQ[q tile] += dS . K[this key tile]: dS^T goes through shared memory ([key][query], this warp's 16 key rows),
+            // each warp then takes 16 QUERY rows over all 64 keys as A fragments (ldmatrix.trans) against the K tile
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                    *reinterpret_cast<uint32_t*>(Ts + xb_off(warp * 16 + g + r * 8, n) + tq * 4) =
+                        pack_bf16x2(dpt[n][r * 2], dpt[n][r * 2 + 1]);
+            __syncthreads();
+            float dq[8][4];
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dq[n][j] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t af[4];
+                // matrices (query 0-7 | 8-15) x (key 0-7 | 8-15) of this warp's 16 queries, stored [key][query]
+                xb_ldmatrix_x4_trans(af, smem_u32(Ts + xb_off(ks * 16 + ((lane >> 4) & 1) * 8 + (lane & 7),
+                                                               warp * 2 + ((lane >> 3) & 1))));
+#pragma unroll
+                for (int dp = 0; dp < 4; ++dp) {
+                    uint32_t bf[4];
+                    const int row = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                    xb_ldmatrix_x4_trans(bf, smem_u32(KV + xb_off(row, dp * 2 + (lane >> 4))));
+                    xb_mma(dq[dp * 2], af, bf[0], bf[1]);
+                    xb_mma(dq[dp * 2 + 1], af, bf[2], bf[3]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int qi = i0 + warp * 16 + g + r * 8;
+                if (qi < nq) {
+                    float* op = a.dq32 + ((long long)b * nq + qi) * a.H + col + tq * 2;
+#pragma unroll
+                    for (int n = 0; n < 8; ++n)
+                        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(op + n * 8), "f"(dq[n][r * 2]),
+                                     "f"(dq[n][r * 2 + 1]) : "memory");
+                }
+            }
+        }
         __syncthreads();
     }
 #pragma unroll
@@ -427,12 +480,35 @@ attn_bwd_dkv_kernel(AttnBwdArgs a) {
     }
 }
 
+// fused form: fp32 dQ accumulator -> the q columns of the bf16 dq|dk|dv rows
+__global__ void __launch_bounds__(256)
+attn_bwd_dq_store_kernel(const float* __restrict__ dq32, int B, int Le, int T, int H, __nv_bfloat16* __restrict__ enc,
+                         long long ld_e, __nv_bfloat16* __restrict__ dec, long long ld_d) {
+    const int nq = Le + T, h4 = H / 4;
+    const long long n = (long long)B * nq * h4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / h4;
+        const int c = (int)(i % h4) * 4, b = (int)(row / nq), qi = (int)(row % nq);
+        const float4 v = *reinterpret_cast<const float4*>(dq32 + row * H + c);
+        __nv_bfloat16* o = qi < Le ? enc + ((long long)b * Le + qi) * ld_e + c : dec + ((long long)b * T + (qi - Le)) * ld_d + c;
+        uint2 w;
+        w.x = pack_bf16x2(v.x, v.y);
+        w.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(o) = w;
+    }
+}
+
 }  // namespace t2s
 
 using namespace t2s;
 
+static inline long long attn_bwd_stats_bytes(int B, int Le, int T, int heads) {
+    return (((long long)B * heads * (Le + T) * 2 * sizeof(float)) + 255) & ~255LL;
+}
+
 extern "C" long long t2s_attn_bwd_workspace_bytes(int B, int Le, int T, int heads) {
-    return (long long)B * heads * (Le + T) * 2 * sizeof(float);
+    // {lse2, D} per (sample, head, query) + the fp32 dQ accumulator of the fused dK / dV / dQ pass (head size 64)
+    return attn_bwd_stats_bytes(B, Le, T, heads) + (long long)B * (Le + T) * heads * XDH * sizeof(float);
 }
 
 static int attn_bwd_entry(const void* qkv_enc, long long ld_enc, const void* qkv_dec, long long ld_dec,
@@ -440,7 +516,7 @@ static int attn_bwd_entry(const void* qkv_enc, long long ld_enc, const void* qkv
                           const void* do_enc, long long ldg_enc, const void* do_dec, long long ldg_dec,
                           void* dqkv_enc, long long ldq_enc, void* dqkv_dec, long long ldq_dec, int B, int Le, int T,
                           int H, int heads, const int* key_idx, const int* n_keys, int key_stride, int max_keys,
-                          void* workspace, void* stream, DropCfg drop) {
+                          void* workspace, void* stream, DropCfg drop, float* stats_lse = nullptr) {
     if (H != heads * XDH || B <= 0 || Le <= 0 || T < 0 || max_keys <= 0) {
         set_error("attn_bwd: head size must be 64 (H %d heads %d B %d Le %d T %d)", H, heads, B, Le, T);
         return T2S_ERR_SHAPE;
@@ -461,7 +537,10 @@ static int attn_bwd_entry(const void* qkv_enc, long long ld_enc, const void* qkv
     a.dqkv_enc = reinterpret_cast<bf*>(dqkv_enc); a.ldq_enc = ldq_enc;
     a.dqkv_dec = reinterpret_cast<bf*>(dqkv_dec); a.ldq_dec = ldq_dec;
     a.key_idx = key_idx; a.n_keys = n_keys; a.key_stride = key_stride;
-    a.stats = reinterpret_cast<float*>(workspace);
+    a.stats = stats_lse ? stats_lse : reinterpret_cast<float*>(workspace);
+    a.have_lse = stats_lse ? 1 : 0;
+    static const int fused = []() { const char* e = getenv("T2S_ATTN_BWD_FUSED"); return (e && e[0] == '0') ? 0 : 1; }();
+    a.dq32 = fused ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + attn_bwd_stats_bytes(B, Le, T, heads)) : nullptr;
     a.Le = Le; a.T = T; a.H = H; a.heads = heads;
     a.scale = 0.125f;
     a.scale_log2 = 0.125f * 1.4426950408889634f;
@@ -480,9 +559,19 @@ static int attn_bwd_entry(const void* qkv_enc, long long ld_enc, const void* qkv
     const int nq = Le + T;
     dim3 gq((nq + XB - 1) / XB, heads, B);
     attn_bwd_stats_kernel<<<gq, XB_THREADS, 0, st>>>(a);
-    attn_bwd_dq_kernel<<<gq, XB_THREADS, 0, st>>>(a);
     dim3 gk((max_keys + T + XB - 1) / XB, heads, B);
-    attn_bwd_dkv_kernel<<<gk, XB_THREADS, XB_DKV_SMEM, st>>>(a);
+    if (a.dq32) {
+        e = cudaMemsetAsync(a.dq32, 0, (size_t)B * nq * H * sizeof(float), st);
+        if (e != cudaSuccess) { set_error("attn_bwd memset dq: %s", cudaGetErrorString(e)); return (int)e; }
+        attn_bwd_dkv_kernel<<<gk, XB_THREADS, XB_DKV_SMEM, st>>>(a);
+        const long long n4 = (long long)B * nq * (H / 4);
+        int grid = (int)((n4 + 255) / 256);
+        if (grid > num_sms() * 16) grid = num_sms() * 16;
+        attn_bwd_dq_store_kernel<<<grid, 256, 0, st>>>(a.dq32, B, Le, T, H, a.dqkv_enc, a.ldq_enc, a.dqkv_dec, a.ldq_dec);
+    } else {
+        attn_bwd_dq_kernel<<<gq, XB_THREADS, 0, st>>>(a);
+        attn_bwd_dkv_kernel<<<gk, XB_THREADS, XB_DKV_SMEM, st>>>(a);
+    }
     return launch_status("attn_bwd");
 }
 
@@ -497,16 +586,18 @@ extern "C" int t2s_attn_bwd(const void* qkv_enc, long long ld_enc, const void* q
                           workspace, stream, DropCfg{0, 0, 0, 0, 1.f});
 }
 
-/* backward of t2s_attn_tc_dropout (encoder rows) + t2s_attn_dec_dropout (decoder rows) of one layer: same (p, seed, site) */
+/* backward of t2s_attn_tc_dropout (encoder rows) + t2s_attn_dec_dropout (decoder rows) of one layer: same (p, seed,
+ * site), p may be 0.  stats_lse != null: the [B, heads, Le + T, 2] fp32 buffer those kernels wrote the rows' log2-sum-exp
+ * into (slot 0; slot 1 is filled here with D = dO . O) -- the S recomputation of the statistics pass is skipped */
 extern "C" int t2s_attn_bwd_dropout(const void* qkv_enc, long long ld_enc, const void* qkv_dec, long long ld_dec,
                                     const void* o_enc, long long ldo_enc, const void* o_dec, long long ldo_dec,
                                     const void* do_enc, long long ldg_enc, const void* do_dec, long long ldg_dec,
                                     void* dqkv_enc, long long ldq_enc, void* dqkv_dec, long long ldq_dec, int B, int Le,
                                     int T, int H, int heads, const int* key_idx, const int* n_keys, int key_stride,
                                     int max_keys, void* workspace, float p, unsigned long long seed, unsigned site,
-                                    void* stream) {
-    if (p <= 0.f || p >= 1.f || Le + T > 65535) { set_error("attn_bwd_dropout: p in (0, 1), L < 65536"); return T2S_ERR_ARG; }
+                                    float* stats_lse, void* stream) {
+    if (p < 0.f || p >= 1.f || Le + T > 65535) { set_error("attn_bwd_dropout: p in [0, 1), L < 65536"); return T2S_ERR_ARG; }
     return attn_bwd_entry(qkv_enc, ld_enc, qkv_dec, ld_dec, o_enc, ldo_enc, o_dec, ldo_dec, do_enc, ldg_enc, do_dec, ldg_dec,
                           dqkv_enc, ldq_enc, dqkv_dec, ldq_dec, B, Le, T, H, heads, key_idx, n_keys, key_stride, max_keys,
-                          workspace, stream, make_drop(p, seed, site));
+                          workspace, stream, make_drop(p, seed, site), stats_lse);
 }

@@ -84,7 +84,8 @@ template <bool X3, bool DROP>
 __global__ void __launch_bounds__(TcCfg<X3>::THREADS, X3 ? 1 : 2)
 attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, int L, int H,
                const int* __restrict__ key_idx, const int* __restrict__ n_keys, int key_stride,
-               __nv_bfloat16* __restrict__ out, long long ldo, float scale_log2, DropCfg drop) {
+               __nv_bfloat16* __restrict__ out, long long ldo, float scale_log2, DropCfg drop,
+               float* __restrict__ lse_out, int lse_rows) {
     using Cfg = TcCfg<X3>;
     constexpr int NP = Cfg::NP;
     extern __shared__ __align__(1024) uint8_t tc_raw[];
@@ -291,7 +292,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                     float p0 = ex2_fast(fmaf(s0, scale_log2, -m_use));
                     float p1 = ex2_fast(fmaf(s1, scale_log2, -m_use));
                     sum += p0 + p1;
-                    if (DROP) {
+                    if (DROP && drop.thr) {
                         const uint32_t hsh = drop_hash(drop.s0, drop.s1, drop_x0 + (uint32_t)(c * 8 + (j >> 1)), drop_y);
                         if ((hsh & 0xffffu) < drop.thr) p0 = 0.f;
                         if ((hsh >> 16) < drop.thr) p1 = 0.f;
@@ -400,6 +401,10 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
             asm volatile("bar.sync 1, 256;" ::: "memory");      // reads done before the next query tile writes
         }
         const float inv = l_row > 0.f ? (DROP ? drop.scale : 1.0f) / l_row : 0.f;
+        // training step: log2-sum-exp of the row (exp2 domain of the scaled scores) in the {lse2, D} layout of the
+        // backward's statistics buffer, so that t2s_attn_bwd does not have to recompute S for it
+        if (DROP && lse_out && row < L && (HS == 1 || half == 0))
+            lse_out[(((long long)b * (H / TC_DH) + h) * lse_rows + row) * 2] = m_run + log2f(l_row);
         __nv_bfloat16* op = out + ((long long)b * L + row) * ldo + h * TC_DH;
 #pragma unroll
         for (int cc = 0; cc < 2 / HS; ++cc) {
@@ -442,7 +447,8 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
 template <bool X3, bool DROP>
 static int launch_attn_tc(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads,
                           const int* key_idx, const int* n_keys, int key_stride, void* out, long long ldo,
-                          cudaStream_t st, DropCfg drop = DropCfg{0, 0, 0, 0, 1.f}) {
+                          cudaStream_t st, DropCfg drop = DropCfg{0, 0, 0, 0, 1.f}, float* lse_out = nullptr,
+                          int lse_rows = 0) {
     using Cfg = TcCfg<X3>;
     static bool attr = false;
     if (!attr) {
@@ -454,7 +460,7 @@ static int launch_attn_tc(const void* qkv, long long ld, int lo_off, int B, int 
     dim3 grid((n_qt + TC_NQ - 1) / TC_NQ, heads, B);
     attn_tc_kernel<X3, DROP><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(qkv), ld, lo_off, L, H, key_idx, n_keys, key_stride,
-        reinterpret_cast<__nv_bfloat16*>(out), ldo, 0.125f * 1.4426950408889634f, drop);
+        reinterpret_cast<__nv_bfloat16*>(out), ldo, 0.125f * 1.4426950408889634f, drop, lse_out, lse_rows);
     return launch_status("attn_tc");
 }
 
@@ -464,7 +470,7 @@ using namespace t2s;
 
 static int attn_tc_entry(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads,
                          const int* key_idx, const int* n_keys, int key_stride, void* out, long long ldo,
-                         void* stream, bool train, DropCfg drop) {
+                         void* stream, bool train, DropCfg drop, float* lse_out = nullptr, int lse_rows = 0) {
     if (H != heads * TC_DH || (ld % 8) || (ldo % 8) || (lo_off % 8) || B <= 0 || L <= 0) {
         set_error("attn_tc: head size must be 64 and pitches multiples of 8 (H %d heads %d ld %lld ldo %lld)", H, heads, ld, ldo);
         return T2S_ERR_SHAPE;
@@ -472,10 +478,10 @@ static int attn_tc_entry(const void* qkv, long long ld, int lo_off, int B, int L
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (lo_off > 0) {
         if (lo_off < 3 * H || ld < lo_off + 3 * H || ldo < 2LL * H) { set_error("attn_tc: bad hi|lo layout"); return T2S_ERR_SHAPE; }
-        if (train) return launch_attn_tc<true, true>(qkv, ld, lo_off, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st, drop);
+        if (train) return launch_attn_tc<true, true>(qkv, ld, lo_off, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st, drop, lse_out, lse_rows);
         return launch_attn_tc<true, false>(qkv, ld, lo_off, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st);
     }
-    if (train) return launch_attn_tc<false, true>(qkv, ld, 0, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st, drop);
+    if (train) return launch_attn_tc<false, true>(qkv, ld, 0, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st, drop, lse_out, lse_rows);
     return launch_attn_tc<false, false>(qkv, ld, 0, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, st);
 }
 
@@ -486,12 +492,17 @@ extern "C" int t2s_attn_tc(const void* qkv, long long ld, int lo_off, int B, int
                          DropCfg{0, 0, 0, 0, 1.f});
 }
 
-/* t2s_attn_tc with attention_probs dropout (training step); the query rows are positions 0..L-1 of the virtual
- * sequence of t2s_attn_bwd_dropout, which recomputes the same mask from (seed, site) */
+/* t2s_attn_tc of the training step: attention_probs dropout (p may be 0) whose mask t2s_attn_bwd_dropout recomputes
+ * from (seed, site) -- the query rows are positions 0..L-1 of its virtual sequence -- and, when lse_out != null, the
+ * rows' log2-sum-exp written to lse_out[((b * heads + h) * lse_rows + row) * 2] (the backward's statistics layout) */
 extern "C" int t2s_attn_tc_dropout(const void* qkv, long long ld, int lo_off, int B, int L, int H, int heads,
                                    const int* key_idx, const int* n_keys, int key_stride, void* out, long long ldo,
-                                   float p, unsigned long long seed, unsigned site, void* stream) {
-    if (p <= 0.f || p >= 1.f || L > 65535 || B * heads >= (1 << 20)) { set_error("attn_tc_dropout: p in (0, 1), L < 65536"); return T2S_ERR_ARG; }
+                                   float p, unsigned long long seed, unsigned site, float* lse_out, int lse_rows,
+                                   void* stream) {
+    if (p < 0.f || p >= 1.f || L > 65535 || B * heads >= (1 << 20) || (lse_out && lse_rows < L)) {
+        set_error("attn_tc_dropout: p in [0, 1), L < 65536, lse_rows >= L");
+        return T2S_ERR_ARG;
+    }
     return attn_tc_entry(qkv, ld, lo_off, B, L, H, heads, key_idx, n_keys, key_stride, out, ldo, stream, true,
-                         make_drop(p, seed, site));
+                         make_drop(p, seed, site), lse_out, lse_rows);
 }

@@ -86,10 +86,10 @@ SIGNATURES = {
     "t2s_dropout_mask": [_p, _i, _i, _i, _i, _i, _f, _ull, _u, _p],
     "t2s_ln_bwd_dropout": [_p, _i, _ll, _p, _i, _ll, _i, _i, _i, _p, _p, _f, _i, _i, _i, _p, _i, _ll, _p, _p, _p, _p,
                            _f, _ull, _u, _p],
-    "t2s_attn_tc_dropout": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _f, _ull, _u, _p],
-    "t2s_attn_dec_dropout": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _ll, _f, _ull, _u, _p],
+    "t2s_attn_tc_dropout": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _f, _ull, _u, _p, _i, _p],
+    "t2s_attn_dec_dropout": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _ll, _f, _ull, _u, _p, _p],
     "t2s_attn_bwd_dropout": [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _i,
-                             _p, _p, _i, _i, _p, _f, _ull, _u, _p],
+                             _p, _p, _i, _i, _p, _f, _ull, _u, _p, _p],
 }
 PLAIN = {"t2s_abi_version": (_i, []), "t2s_last_error": (ctypes.c_char_p, []),
          "t2s_loss_workspace_bytes": (_ll, [_i, _i]), "t2s_loss_bwd_workspace_bytes": (_ll, [_i, _i]),

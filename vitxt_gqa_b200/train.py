@@ -311,7 +311,8 @@ class TrainEngine:
         Np = _ru(V + O, 8)
 
         def x3_layer(M):      # what one grounding-chain layer keeps (bf16 hi|lo operands double as bf16 activations)
-            return dict(xs=torch.empty(M, 2 * H, **b16), qkvs=torch.empty(M, 6 * H, **b16), ctxs=torch.empty(M, 2 * H, **b16),
+            return dict(stats=torch.empty(M * 12 * 2, **f32),      # {log2-sum-exp, dO . O} per (sample, head, row)
+                        xs=torch.empty(M, 2 * H, **b16), qkvs=torch.empty(M, 6 * H, **b16), ctxs=torch.empty(M, 2 * H, **b16),
                         h1=torch.empty(M, H, **f32), x1=torch.empty(M, H, **f32), x1s=torch.empty(M, 2 * H, **b16),
                         u=torch.empty(M, 4 * H, **f32), inters=torch.empty(M, 8 * H, **b16), h2=torch.empty(M, H, **f32),
                         out=torch.empty(M, H, **f32))
@@ -328,7 +329,8 @@ class TrainEngine:
         ws = dict(
             text=[x3_layer(Mt) for _ in range(n_text)], qtv=[x3_layer(Me) for _ in range(n_qtv)],
             xt=torch.empty(Mt, H, **f32),
-            enc={v: [bf_layer(Me, need_qkv=(li > 0)) for li in range(n_mmt)] for v in variants},
+            enc={v: [dict(bf_layer(Me, need_qkv=(li > 0)), stats=torch.empty((Me + Md) * 12 * 2, **f32))
+                     for li in range(n_mmt)] for v in variants},
             dec={v: [bf_layer(Md) for _ in range(n_mmt)] for v in variants},
             xd={v: torch.empty(Md, H, **b16) for v in variants},
             qd={v: torch.empty(Md, H, **b16) for v in variants},
@@ -364,12 +366,10 @@ class TrainEngine:
         p_h, p_a, seed, sname = drop if drop is not None else (0.0, 0.0, 0, "")
         L.gemm_bf16x3(_ptr(sv["xs"]), 2 * H, _ptr(lw["wqkv"]), 2 * H, _ptr(lw["bqkv"]), None, 0, _ptr(sv["qkvs"]), 6 * H,
                       M, 3 * H, H, SPLIT, 0, st)
-        if p_a > 0:
-            L.attn_tc_dropout(_ptr(sv["qkvs"]), 6 * H, 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride,
-                              _ptr(sv["ctxs"]), 2 * H, p_a, seed, self._site(sname + ".attn"), st)
-        else:
-            L.attn_tc(_ptr(sv["qkvs"]), 6 * H, 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride, _ptr(sv["ctxs"]),
-                      2 * H, st)
+        # the training form of the attention kernel: dropout on the probabilities (p_a may be 0) and the rows'
+        # log2-sum-exp saved for the backward
+        L.attn_tc_dropout(_ptr(sv["qkvs"]), 6 * H, 3 * H, B, rows_L, H, 12, _ptr(keys), _ptr(nk), key_stride,
+                          _ptr(sv["ctxs"]), 2 * H, p_a, seed, self._site(sname + ".attn"), _ptr(sv["stats"]), rows_L, st)
         if p_h > 0:
             # BertSelfOutput / BertOutput with dropout: the GEMM leaves Linear(x) + bias, the LayerNorm kernel does
             # LN(dropout(.) + input) and writes the pre-LayerNorm sum back for the backward
@@ -542,11 +542,10 @@ class TrainEngine:
             keys, nk = mws["keys"][v], mws["nk"][v]
 
             def enc_attn(qkv, ctx, li, keys=keys, nk=nk, v=v):
-                if pm_a > 0:        # one site per (variant, layer): encoder and decoder rows are one virtual sequence
-                    L.attn_tc_dropout(_ptr(qkv), 3 * H, 0, B, Le, H, 12, _ptr(keys), _ptr(nk), Le, _ptr(ctx), H, pm_a,
-                                      seed, self._site("mmt.%s.%d.attn" % (v, li)), st)
-                else:
-                    L.attn_tc(_ptr(qkv), 3 * H, 0, B, Le, H, 12, _ptr(keys), _ptr(nk), Le, _ptr(ctx), H, st)
+                # one dropout site and one statistics buffer per (variant, layer): encoder and decoder rows are one
+                # virtual sequence of Le + T query rows in the backward
+                L.attn_tc_dropout(_ptr(qkv), 3 * H, 0, B, Le, H, 12, _ptr(keys), _ptr(nk), Le, _ptr(ctx), H, pm_a,
+                                  seed, self._site("mmt.%s.%d.attn" % (v, li)), _ptr(ws["enc"][v][li]["stats"]), Le + T, st)
 
             x = mws["X16"]
             enc_qkv[v] = []
@@ -575,12 +574,9 @@ class TrainEngine:
                 qe = enc_qkv[v][li]
 
                 def dec_attn(qkv, ctx, qe=qe, keys=keys, nk=nk, li=li, v=v):
-                    if pm_a > 0:
-                        L.attn_dec_dropout(_ptr(qe), 3 * H, Le, _ptr(qkv), 3 * H, T, B, H, 12, _ptr(keys), _ptr(nk), Le,
-                                           0, T, _ptr(ctx), H, pm_a, seed, self._site("mmt.%s.%d.attn" % (v, li)), st)
-                    else:
-                        L.attn_dec(_ptr(qe), 3 * H, Le, _ptr(qkv), 3 * H, T, B, H, 12, _ptr(keys), _ptr(nk), Le, 0, T,
-                                   _ptr(ctx), H, st)
+                    L.attn_dec_dropout(_ptr(qe), 3 * H, Le, _ptr(qkv), 3 * H, T, B, H, 12, _ptr(keys), _ptr(nk), Le,
+                                       0, T, _ptr(ctx), H, pm_a, seed, self._site("mmt.%s.%d.attn" % (v, li)),
+                                       _ptr(ws["enc"][v][li]["stats"]), st)
 
                 self._bf_layer_fwd(L, lw, x, H, None, sv, Md, dec_attn, st, drop=(pm_h, seed, "mmt.%s.%d.dec" % (v, li)))
                 x = sv["out"]
@@ -645,12 +641,10 @@ class TrainEngine:
         L.gemm_bf16(_ptr(g1), H, _ptr(wt["woT"]), H, None, None, 0, _ptr(sc["dctx"]), H, M, H, H, 0, 0, st)
         self._wgrad(L, g1, H, ctx, ld_ctx, g(pre + "attention.output.dense.weight"), H, M, H, H, st)
 
-    def _attn_bwd(self, L, args, p_a, seed, sname, st):
-        """t2s_attn_bwd(*args, stream), with the forward's attention-probability dropout recomputed when p_a > 0."""
-        if p_a > 0:
-            L.attn_bwd_dropout(*args, p_a, seed, self._site(sname + ".attn"), st)
-        else:
-            L.attn_bwd(*args, st)
+    def _attn_bwd(self, L, args, p_a, seed, sname, st, stats):
+        """Attention backward of one layer: the forward's attention-probability dropout recomputed from (seed, site)
+        (p_a may be 0), the rows' log2-sum-exp taken from `stats`, where the forward kernels left it."""
+        L.attn_bwd_dropout(*args, p_a, seed, self._site(sname + ".attn"), _ptr(stats), st)
 
     def _layer_bwd_post_attn(self, L, wt, pre, x, ldx, M, sc, dx_out, st):
         """q|k|v projection backward: sc["dqkv"] -> dx_out (+ the residual gradient sc["dh1"]); weight / bias grads."""
@@ -739,7 +733,7 @@ class TrainEngine:
                 self._attn_bwd(L, (_ptr(qkv_e), 3 * H, _ptr(svd["qkv"]), 3 * H, _ptr(sve["ctx"]), H, _ptr(svd["ctx"]), H,
                                    _ptr(enc_sc["dctx"]), H, _ptr(dec_sc["dctx"]), H, _ptr(enc_sc["dqkv"]), 3 * H,
                                    _ptr(dec_sc["dqkv"]), 3 * H, B, Le, T, H, 12, _ptr(keys), _ptr(nk), Le, Le,
-                                   _ptr(ws["attn_ws"])), pm_a, seed, "mmt.%s.%d" % (v, li), st)
+                                   _ptr(ws["attn_ws"])), pm_a, seed, "mmt.%s.%d" % (v, li), st, sve["stats"])
                 self._layer_bwd_post_attn(L, wt, pre, x_d, H, Md, dec_sc, alt_d, st)
                 self._layer_bwd_post_attn(L, wt, pre, x_e, H, Me, enc_sc, alt_e, st)
                 dy_e, alt_e = alt_e, dy_e
@@ -776,7 +770,7 @@ class TrainEngine:
             self._layer_bwd_pre_attn(L, wt, lw, pre, sv, Me, dy, enc_sc, st, x3=True, drop=(pq_h, seed, "qtv.%d" % li))
             self._attn_bwd(L, (_ptr(sv["qkvs"]), 6 * H, None, 0, _ptr(sv["ctxs"]), 2 * H, None, 0, _ptr(enc_sc["dctx"]), H,
                                None, 0, _ptr(enc_sc["dqkv"]), 3 * H, None, 0, B, Le, 0, H, 12, _ptr(mws["keys"]["ref"]),
-                               _ptr(mws["nk"]["ref"]), Le, Le, _ptr(ws["attn_ws"])), pq_a, seed, "qtv.%d" % li, st)
+                               _ptr(mws["nk"]["ref"]), Le, Le, _ptr(ws["attn_ws"])), pq_a, seed, "qtv.%d" % li, st, sv["stats"])
             self._layer_bwd_post_attn(L, wt, pre, sv["xs"], 2 * H, Me, enc_sc, ws["dy"], st)
             dy = (ws["dy"], 1, (0, 0, 0), 0)
             self._bucket_ready(pre)
@@ -831,7 +825,7 @@ class TrainEngine:
             self._layer_bwd_pre_attn(L, wt, lw, pre, sv, Mt, dy, txt_sc, st, x3=True, drop=(pt_h, seed, "text.%d" % li))
             self._attn_bwd(L, (_ptr(sv["qkvs"]), 6 * H, None, 0, _ptr(sv["ctxs"]), 2 * H, None, 0, _ptr(txt_sc["dctx"]), H,
                                None, 0, _ptr(txt_sc["dqkv"]), 3 * H, None, 0, B, Lt, 0, H, 12, _ptr(mws["keys_txt"]),
-                               _ptr(mws["nk_txt"]), Lt, Lt, _ptr(ws["attn_ws"])), pt_a, seed, "text.%d" % li, st)
+                               _ptr(mws["nk_txt"]), Lt, Lt, _ptr(ws["attn_ws"])), pt_a, seed, "text.%d" % li, st, sv["stats"])
             self._layer_bwd_post_attn(L, wt, pre, sv["xs"], 2 * H, Mt, txt_sc, dx_t, st)
             dy = (dx_t, 1, (0, 0, 0), 0)
             self._bucket_ready(pre)
