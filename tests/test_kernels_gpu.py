@@ -514,6 +514,32 @@ def test_ptr_score_and_argmax(L):
     assert torch.equal(prev[:, 1:], am[:, :-1]) and prev[:, 0].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("O,t0,nq", [(960, 0, 12), (50, 2, 4), (77, 0, 16), (960, 5, 2)])
+def test_ptr_score_several_rows_tensor_core_kernel(L, O, t0, nq):
+    """nq > 1 decoder rows go through the mma.sync kernel (keys = M, queries = N), one row through the scalar kernel:
+    both against torch, ragged key counts, row offsets, and untouched neighbours."""
+    B, T, V, H = 3, 16, 40, 768
+    Le, N = 20 + O, V + O
+    q = rnd(B * T, H, dtype=torch.bfloat16, seed=1)
+    keyp = rnd(B * Le, H, dtype=torch.bfloat16, seed=2)
+    jm = (torch.rand(B, Le, device="cuda") < 0.5).float()
+    off = Le - O
+    S = torch.full((B, T, N), float("nan"), device="cuda")
+    L.ptr_score(P(q), H, B, T, t0, nq, keyp.data_ptr() + off * H * 2, Le * H, H, O, H, jm.data_ptr() + off * 4, Le,
+                P(S), N, V, stream())
+    torch.cuda.synchronize()
+    ref = torch.einsum("btd,bod->bto", q.view(B, T, H).float(), keyp.view(B, Le, H)[:, off:].float()) / math.sqrt(H) \
+        + jm[:, None, off:]
+    assert (S[:, t0:t0 + nq, V:] - ref[:, t0:t0 + nq]).abs().max().item() <= 1e-4
+    assert torch.isnan(S[:, :, :V]).all() and torch.isnan(S[:, :t0]).all() and torch.isnan(S[:, t0 + nq:]).all()
+    one = torch.full((B, T, N), float("nan"), device="cuda")
+    for t in range(t0, t0 + nq):      # the one-row (greedy) kernel gives the same numbers to fp32 summation order
+        L.ptr_score(P(q), H, B, T, t, 1, keyp.data_ptr() + off * H * 2, Le * H, H, O, H, jm.data_ptr() + off * 4, Le,
+                    P(one), N, V, stream())
+    torch.cuda.synchronize()
+    assert (one[:, t0:t0 + nq, V:] - S[:, t0:t0 + nq, V:]).abs().max().item() <= 2e-5
+
+
 def test_losses(L):
     B, T, N = 5, 12, 5960
     ref_s, pos_s, neg_s = rnd(B, T, N, seed=1), rnd(B, T, N, seed=2), rnd(B, T, N, seed=3)

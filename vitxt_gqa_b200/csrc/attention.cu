@@ -746,6 +746,13 @@ extern "C" int t2s_attn_x3(const void* qkv, long long ld, int lo_off, int B, int
     return launch_status("attn_x3");
 }
 
+namespace t2s {
+// csrc/attn_bwd.cu: mma.sync flash kernel for several decoder rows per sample
+int launch_attn_dec_mma(const void* qkv_enc, long long ld_enc, int L_enc, const void* qkv_dec, long long ld_dec, int T,
+                        int B, int H, int heads, const int* key_idx, const int* n_keys, int key_stride, int t0, int nq,
+                        void* out, long long ldo, cudaStream_t st, DropCfg drop, float* lse_out);
+}
+
 static int attn_dec_entry(const void* qkv_enc, long long ld_enc, int L_enc, const void* qkv_dec, long long ld_dec,
                           int T, int B, int H, int heads, const int* key_idx, const int* n_keys, int key_stride,
                           int t0, int nq, void* out, long long ldo, void* stream, DropCfg drop, float* lse_out = nullptr) {
@@ -753,6 +760,11 @@ static int attn_dec_entry(const void* qkv_enc, long long ld_enc, int L_enc, cons
         set_error("attn_dec: bad arguments (H %d heads %d t0 %d nq %d T %d)", H, heads, t0, nq, T);
         return T2S_ERR_SHAPE;
     }
+    static const int use_mma = []() { const char* e = getenv("T2S_ATTN_DEC_MMA"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (nq > 1 && use_mma && (ldo % 2) == 0)
+        // several decoder rows of a sample (teacher-forced passes): tensor-core kernel, K / V read once
+        return launch_attn_dec_mma(qkv_enc, ld_enc, L_enc, qkv_dec, ld_dec, T, B, H, heads, key_idx, n_keys, key_stride, t0,
+                                   nq, out, ldo, reinterpret_cast<cudaStream_t>(stream), drop, lse_out);
     const int max_keys = ((L_enc + T + 3) / 4) * 4;
     // query chunk: every K / V row is read once per chunk of QC queries.  QC = 12 (all teacher-forced rows in one
     // pass) was measured SLOWER than three passes of QC = 4 on B200 (195 vs 95 us per launch at 1056 keys: 185

@@ -480,6 +480,210 @@ attn_bwd_dkv_kernel(AttnBwdArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------- decoder rows, forward (nq > 1)
+// The teacher-forced passes score several decoder rows of a sample at once (all T of them in the `ref` / `neg` tail of
+// the eval forward and in every pass of the training step).  The scalar kernel of csrc/attention.cu reads K / V once
+// per chunk of four queries and is latency bound (ncu: 97 us per launch, 0.10 of the HBM rate, on the critical path
+// behind the greedy decode); this one is a small flash attention on mma.sync built from the tile helpers above: one
+// CTA per (head, sample), the <= 16 query rows are ONE m16 tile, 64-key tiles of the virtual key list (compacted
+// encoder keys, then the causal decoder keys) are double buffered with cp.async, each of the four warps takes 16 keys
+// of a tile (S = Q K^T, online softmax, O += P V with P as bf16 A fragments), and the four partial (max, sum, O) sets
+// meet in shared memory.  K and V are read exactly once.  `drop` / `lse_out`: the training form (see attn_bwd above).
+struct AttnDecArgs {
+    const __nv_bfloat16* qkv_enc; long long ld_enc; int L_enc;
+    const __nv_bfloat16* qkv_dec; long long ld_dec; int T, H;
+    const int* key_idx; const int* n_keys; int key_stride;
+    int t0, nq;
+    __nv_bfloat16* out; long long ldo;
+    float scale_log2;
+    DropCfg drop;
+    float* lse_out;
+};
+
+__global__ void __launch_bounds__(XB_THREADS)
+attn_dec_mma_kernel(AttnDecArgs a) {
+    __shared__ __align__(128) uint8_t Qs[16 * 128];
+    __shared__ __align__(128) uint8_t KVs[2][2][XB * 128];        // [stage][K | V]; reused for the final reduction
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const int heads = gridDim.x;
+    const int nk = a.n_keys[b];
+    const int nkv = nk + a.t0 + a.nq;                              // the last query sees decoder keys 0 .. t0 + nq - 1
+    const int ntiles = (nkv + XB - 1) / XB;
+    const int* kidx = a.key_idx + (long long)b * a.key_stride;
+    const int col = h * XDH;
+    const __nv_bfloat16* enc = a.qkv_enc + (long long)b * a.L_enc * a.ld_enc;
+    const __nv_bfloat16* dec = a.qkv_dec + (long long)b * a.T * a.ld_dec;
+
+    auto load_kv = [&](int t, int buf) {
+        for (int i = threadIdx.x; i < XB * 8; i += XB_THREADS) {
+            const int r = i >> 3, c = i & 7;
+            const int j = t * XB + r;
+            const bool ok = j < nkv;
+            const __nv_bfloat16* src = (!ok ? enc : (j < nk ? enc + (long long)kidx[j] * a.ld_enc
+                                                            : dec + (long long)(j - nk) * a.ld_dec)) + col + c * 8;
+            cp_async16(KVs[buf][0] + xb_off(r, c), src + a.H, ok);
+            cp_async16(KVs[buf][1] + xb_off(r, c), src + 2 * a.H, ok);
+        }
+    };
+    for (int i = threadIdx.x; i < 16 * 8; i += XB_THREADS) {
+        const int r = i >> 3, c = i & 7;
+        const bool ok = r < a.nq;
+        cp_async16(Qs + xb_off(r, c), dec + (long long)(a.t0 + (ok ? r : 0)) * a.ld_dec + col + c * 8, ok);
+    }
+    load_kv(0, 0);
+    cp_async_commit();
+
+    float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
+    float acc[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[n][j] = 0.f;
+    uint32_t qf[4][4];
+    const uint32_t drop_y = drop_attn_y(a.drop, b * heads + h);
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < ntiles) load_kv(t + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (t == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)       // the 16 query rows as A fragments (all four warps hold the same ones)
+                xb_ldmatrix_x4(qf[ks], smem_u32(Qs + xb_off(lane & 15, ks * 2 + (lane >> 4))));
+        }
+        if (t * XB + warp * 16 < nkv) {          // warp-uniform: this warp's 16 keys of the tile exist
+            const uint8_t* Kt = KVs[buf][0];
+            const uint8_t* Vt = KVs[buf][1];
+            float c[2][4];
+#pragma unroll
+            for (int n = 0; n < 2; ++n)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c[n][j] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t bf[4];
+                xb_ldmatrix_x4(bf, smem_u32(Kt + xb_off(warp * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1))));
+                xb_mma(c[0], qf[ks], bf[0], bf[1]);
+                xb_mma(c[1], qf[ks], bf[2], bf[3]);
+            }
+            float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+            for (int n = 0; n < 2; ++n)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int key = t * XB + warp * 16 + n * 8 + tq * 2 + (j & 1);
+                    const int qpos = a.t0 + g + (j >> 1) * 8;            // decoder position of this query row
+                    float v = c[n][j] * a.scale_log2;
+                    if (key >= nkv || (key >= nk && key - nk > qpos)) v = -INFINITY;
+                    c[n][j] = v;
+                    mx[j >> 1] = fmaxf(mx[j >> 1], v);
+                }
+            float corr[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+                const float m_new = fmaxf(m_i[r], mx[r]);
+                corr[r] = m_new == -INFINITY ? 1.f : exp2f(m_i[r] - m_new);
+                float rs = 0.f;
+#pragma unroll
+                for (int n = 0; n < 2; ++n)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float p = m_new == -INFINITY ? 0.f : exp2f(c[n][r * 2 + e] - m_new);
+                        c[n][r * 2 + e] = p;
+                        rs += p;
+                    }
+                l_i[r] = l_i[r] * corr[r] + rs;        // this lane's share of the row sum (the quad is summed at the end)
+                m_i[r] = m_new;
+            }
+            if (a.drop.thr) {                           // training: mask the probabilities that multiply V (not the row sum)
+#pragma unroll
+                for (int n = 0; n < 2; ++n)
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int key = t * XB + warp * 16 + n * 8 + tq * 2;
+                        const uint32_t hsh = drop_hash(a.drop.s0, a.drop.s1, drop_attn_x(a.L_enc + a.t0 + g + r * 8, key), drop_y);
+                        if ((hsh & 0xffffu) < a.drop.thr) c[n][r * 2] = 0.f;
+                        if ((hsh >> 16) < a.drop.thr) c[n][r * 2 + 1] = 0.f;
+                    }
+            }
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                acc[n][0] *= corr[0]; acc[n][1] *= corr[0];
+                acc[n][2] *= corr[1]; acc[n][3] *= corr[1];
+            }
+            uint32_t pf[4];
+            pf[0] = pack_bf16x2(c[0][0], c[0][1]);
+            pf[1] = pack_bf16x2(c[0][2], c[0][3]);
+            pf[2] = pack_bf16x2(c[1][0], c[1][1]);
+            pf[3] = pack_bf16x2(c[1][2], c[1][3]);
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {
+                uint32_t bf[4];
+                xb_ldmatrix_x4_trans(bf, smem_u32(Vt + xb_off(warp * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dp * 2 + (lane >> 4))));
+                xb_mma(acc[dp * 2], pf, bf[0], bf[1]);
+                xb_mma(acc[dp * 2 + 1], pf, bf[2], bf[3]);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- combine the four warps' partial results through shared memory (the K / V stages are free now)
+    float* red = reinterpret_cast<float*>(&KVs[0][0][0]);       // [4 warps][16 rows][64 + 2]: O, max, sum
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 1);
+        l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 2);
+        float* row = red + (warp * 16 + g + r * 8) * 66;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            row[n * 8 + tq * 2] = acc[n][r * 2];
+            row[n * 8 + tq * 2 + 1] = acc[n][r * 2 + 1];
+        }
+        if (tq == 0) { row[64] = m_i[r]; row[65] = l_i[r]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16 * 32; i += XB_THREADS) {
+        const int r = i >> 5, d = (i & 31) * 2;
+        if (r >= a.nq) continue;
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) M = fmaxf(M, red[(w * 16 + r) * 66 + 64]);
+        float Lsum = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float* row = red + (w * 16 + r) * 66;
+            const float f = row[64] == -INFINITY ? 0.f : exp2f(row[64] - M);
+            Lsum += row[65] * f;
+            o0 += row[d] * f;
+            o1 += row[d + 1] * f;
+        }
+        const float inv = Lsum > 0.f ? a.drop.scale / Lsum : 0.f;
+        *reinterpret_cast<uint32_t*>(a.out + ((long long)b * a.T + a.t0 + r) * a.ldo + col + d) = pack_bf16x2(o0 * inv, o1 * inv);
+        if (a.lse_out && d == 0)
+            a.lse_out[(((long long)b * heads + h) * (a.L_enc + a.T) + a.L_enc + a.t0 + r) * 2] = M + log2f(Lsum);
+    }
+}
+
+// declared in csrc/attention.cu (t2s_attn_dec dispatches here when nq > 1)
+int launch_attn_dec_mma(const void* qkv_enc, long long ld_enc, int L_enc, const void* qkv_dec, long long ld_dec, int T,
+                        int B, int H, int heads, const int* key_idx, const int* n_keys, int key_stride, int t0, int nq,
+                        void* out, long long ldo, cudaStream_t st, DropCfg drop, float* lse_out) {
+    AttnDecArgs a;
+    a.qkv_enc = reinterpret_cast<const __nv_bfloat16*>(qkv_enc); a.ld_enc = ld_enc; a.L_enc = L_enc;
+    a.qkv_dec = reinterpret_cast<const __nv_bfloat16*>(qkv_dec); a.ld_dec = ld_dec; a.T = T; a.H = H;
+    a.key_idx = key_idx; a.n_keys = n_keys; a.key_stride = key_stride;
+    a.t0 = t0; a.nq = nq;
+    a.out = reinterpret_cast<__nv_bfloat16*>(out); a.ldo = ldo;
+    a.scale_log2 = 0.125f * 1.4426950408889634f;
+    a.drop = drop;
+    a.lse_out = lse_out;
+    attn_dec_mma_kernel<<<dim3(heads, B), XB_THREADS, 0, st>>>(a);
+    return launch_status("attn_dec");
+}
+
 // fused form: fp32 dQ accumulator -> the q columns of the bf16 dq|dk|dv rows
 __global__ void __launch_bounds__(256)
 attn_bwd_dq_store_kernel(const float* __restrict__ dq32, int B, int Le, int T, int H, __nv_bfloat16* __restrict__ enc,

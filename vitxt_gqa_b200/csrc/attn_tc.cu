@@ -292,7 +292,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                     float p0 = ex2_fast(fmaf(s0, scale_log2, -m_use));
                     float p1 = ex2_fast(fmaf(s1, scale_log2, -m_use));
                     sum += p0 + p1;
-                    if (DROP && drop.thr) {
+                    if (DROP) {      // thr == 0 (p = 0) drops nothing; no run-time test inside the pipelined sweep
                         const uint32_t hsh = drop_hash(drop.s0, drop.s1, drop_x0 + (uint32_t)(c * 8 + (j >> 1)), drop_y);
                         if ((hsh & 0xffffu) < drop.thr) p0 = 0.f;
                         if ((hsh >> 16) < drop.thr) p1 = 0.f;

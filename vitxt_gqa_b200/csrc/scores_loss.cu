@@ -120,6 +120,67 @@ argmax_feedback_kernel(const float* __restrict__ scores, long long ld_scores, in
     }
 }
 
+// Teacher-forced passes (2 <= nq <= 16 decoder rows at once: the `ref` / `neg` tail of the eval forward, every pass of
+// the training step): scores^T[16 keys x 16 queries] per warp on the tensor cores (mma.sync m16n8k16, fp32 accumulate).
+// The SIMT kernel above re-did the bf16 unpack of every key row once per query and ran at 0.4 TB/s (231 us per launch
+// for the 94 MB of pointer keys at batch 64); here a key row is read once (4-byte fragment loads straight from global
+// memory, L1 turns the four k-steps of a 128-byte line into one fetch) and costs two MMAs per 16 hidden dims.
+// A = key rows (M = keys), B = the queries (N), staged once per CTA in shared memory with padded rows.
+constexpr int PM_THREADS = 128, PM_KEYS = 64, PM_QPAD = 8;     // 4 warps x 16 keys; Q rows padded by 8 bf16 (bank spread)
+
+__global__ void __launch_bounds__(PM_THREADS)
+ptr_score_mma_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, int T, int t0, int nq,
+                     const __nv_bfloat16* __restrict__ keyp, long long key_batch_stride, long long ldk, int O, int H,
+                     const float* __restrict__ mask, long long mask_stride, float* __restrict__ scores,
+                     long long ld_scores, int V, float inv_denom) {
+    extern __shared__ __align__(16) uint8_t pm_raw[];
+    __nv_bfloat16* qs = reinterpret_cast<__nv_bfloat16*>(pm_raw);         // [16][H + PM_QPAD], rows >= nq zero
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+    const int ldqs = H + PM_QPAD;
+    for (int i = tid; i < 16 * (H / 8); i += PM_THREADS) {
+        const int r = i / (H / 8), c = (i % (H / 8)) * 8;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < nq) v = *reinterpret_cast<const uint4*>(q + ((long long)b * T + t0 + r) * ldq + c);
+        *reinterpret_cast<uint4*>(qs + r * ldqs + c) = v;
+    }
+    __syncthreads();
+    const int o0 = blockIdx.x * PM_KEYS + warp * 16;
+    if (o0 >= O) return;
+    const __nv_bfloat16* kb = keyp + (long long)b * key_batch_stride;
+    const int r0 = min(o0 + g, O - 1), r1 = min(o0 + g + 8, O - 1);      // clamped: rows past O are computed, not stored
+    const __nv_bfloat16* k0 = kb + (long long)r0 * ldk + tq * 2;
+    const __nv_bfloat16* k1 = kb + (long long)r1 * ldk + tq * 2;
+    const __nv_bfloat16* q0 = qs + g * ldqs + tq * 2;                      // queries 0-7 (n tile 0), 8-15 (n tile 1)
+    const __nv_bfloat16* q1 = qs + (g + 8) * ldqs + tq * 2;
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k = 0; k < H; k += 16) {
+        uint32_t a[4];
+        a[0] = *reinterpret_cast<const uint32_t*>(k0 + k);
+        a[1] = *reinterpret_cast<const uint32_t*>(k1 + k);
+        a[2] = *reinterpret_cast<const uint32_t*>(k0 + k + 8);
+        a[3] = *reinterpret_cast<const uint32_t*>(k1 + k + 8);
+        const uint32_t b00 = *reinterpret_cast<const uint32_t*>(q0 + k), b01 = *reinterpret_cast<const uint32_t*>(q0 + k + 8);
+        const uint32_t b10 = *reinterpret_cast<const uint32_t*>(q1 + k), b11 = *reinterpret_cast<const uint32_t*>(q1 + k + 8);
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c0[0]), "+f"(c0[1]), "+f"(c0[2]), "+f"(c0[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b00), "r"(b01));
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c1[0]), "+f"(c1[1]), "+f"(c1[2]), "+f"(c1[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b10), "r"(b11));
+    }
+    // c[j]: key row g (j < 2) or g + 8, query 2 tq + (j & 1) (+ 8 for the second n tile)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int o = o0 + g + (j >> 1) * 8;
+        if (o >= O) continue;
+        const float m = mask[(long long)b * mask_stride + o];
+        const int qa = 2 * tq + (j & 1), qb = qa + 8;
+        if (qa < nq) scores[((long long)b * T + t0 + qa) * ld_scores + V + o] = c0[j] * inv_denom + m;
+        if (qb < nq) scores[((long long)b * T + t0 + qb) * ld_scores + V + o] = c1[j] * inv_denom + m;
+    }
+}
+
 // ------------------------------------------------------------------------------- masked BCE-with-logits
 __global__ void __launch_bounds__(256)
 bce_partial_kernel(const float* __restrict__ scores, const float* __restrict__ targets, const float* __restrict__ loss_mask,
@@ -212,6 +273,16 @@ extern "C" int t2s_ptr_score(const void* q, long long ldq, int B, int T, int t0,
                              long long key_batch_stride, long long ldk, int O, int H, const float* mask,
                              long long mask_stride, float* scores, long long ld_scores, int V, void* stream) {
     if (nq < 1 || nq > PS_MAXQ || (H % 256) || H > 1024 || (ldk % 8) || t0 < 0 || t0 + nq > T) { set_error("ptr_score: bad arguments"); return T2S_ERR_SHAPE; }
+    if (nq > 1 && (ldq % 8) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(keyp) & 3) == 0 &&
+        (ldk % 2) == 0 && (key_batch_stride % 2) == 0) {
+        // several decoder rows per sample: tensor-core kernel (the scalar kernel stays for the one-row greedy step)
+        const size_t sm = (size_t)16 * (H + PM_QPAD) * sizeof(__nv_bfloat16);
+        dim3 grid((O + PM_KEYS - 1) / PM_KEYS, B);
+        ptr_score_mma_kernel<<<grid, PM_THREADS, sm, reinterpret_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const __nv_bfloat16*>(q), ldq, T, t0, nq, reinterpret_cast<const __nv_bfloat16*>(keyp),
+            key_batch_stride, ldk, O, H, mask, mask_stride, scores, ld_scores, V, 1.0f / sqrtf((float)H));
+        return launch_status("ptr_score");
+    }
     const size_t smem = (size_t)nq * H * sizeof(float);
     static size_t attr = 48 * 1024;
     if (smem > attr) {
