@@ -39,9 +39,12 @@ FIXTURES = {
     "t2s_clipocr_train": (dict(frame_topk=1, ocr_topk=1), 2, 1237, 0, "stress", "train"),
     # BASELINE config 5 (shape stress sweep): a long video, 128 sampled frames x 15 OCR slots (L_mmt = 2080), batch 1
     "t2s_stress_f128_eval": (dict(frames=128, ocr_per_frame=15), 1, 1240, 0, "stress", "eval"),
-    # the sweep's long-video / dense-OCR corner that one CPU reference run can still afford: 256 frames x 30 OCR slots
-    # (L_mmt = 7968)
-    "t2s_stress_f256x30_eval": (dict(frames=256, ocr_per_frame=30), 1, 1241, 0, "stress", "eval"),
+    # ... and 256 frames x 15 OCR slots (L_mmt = 4108).  Denser OCR (30 / 60 slots per frame) has no reference golden: the
+    # reference's per-frame `torch.sort` (stg.py:102-117) is not stable beyond 16 elements on CPU, every non-grounded frame
+    # is 30 exact ties at -10000, and which five of them land in pos_ocr_mask (Q3) -- hence every score -- is then an
+    # accident of the sort implementation (seen: 154 of 1280 ground_box rows differ from the lowest-index rule while
+    # TextBert / encoders / QTV agree to 0.0).  Those shapes are checked against the oracle (stable, lowest index first).
+    "t2s_stress_f256_eval": (dict(frames=256, ocr_per_frame=15), 1, 1242, 0, "stress", "eval"),
     # ablation models: same weights and inputs, different Grounding_Module wiring
     "t2s_wo_sg_small_eval": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2, ablation="wo_sg"), 3, 15, 0, "stress", "eval"),
     "t2s_wo_sg_small_train": (dict(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2, ablation="wo_sg"), 3, 16, 0, "stress", "train"),

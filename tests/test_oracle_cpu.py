@@ -28,7 +28,8 @@ def _neg_override(z):
                                               ("t2s_wo_sg_small_eval", "dedup"), ("t2s_wo_sg_small_train", "literal"),
                                               ("t2s_wo_tg_small_eval", "dedup"), ("t2s_wo_tg_all_eval", "dedup"),
                                               # BASELINE configs[4]: 128 frames x 15 OCR slots, batch 1
-                                              ("t2s_stress_f128_eval", "dedup")])
+                                              ("t2s_stress_f128_eval", "dedup"),
+                                              ("t2s_stress_f256_eval", "dedup")])
 def test_oracle_t2s_matches_reference_golden(fixture, schedule):
     z, meta, d, sd, inp = load_golden(fixture)
     train = meta["mode"] == "train"
