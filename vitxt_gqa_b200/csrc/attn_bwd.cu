@@ -480,6 +480,307 @@ attn_bwd_dkv_kernel(AttnBwdArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------- dK / dV / dQ on tcgen05 + TMEM
+// The same fused backward as attn_bwd_dkv_kernel above, on the 5th-gen tensor cores.  One CTA = one 128-key tile of the
+// virtual key list of one (sample, head); it loops over the 128-row query tiles that can see it.  Per tile pair:
+//   MMA 1   S^T  = K_j Q_i^T   (M 128 keys, N 128 queries, K 64)  -> TMEM columns [0, 128)
+//           dP^T = V_j dO_i^T                                     -> TMEM columns [128, 256)
+//   warps 0-3 (thread r == key row r == TMEM lane r): P^T = exp2(S^T scale - lse[q]) (mask, validity), dropout
+//           multiplier m(q, key) recomputed, P^T m and dS^T = P^T (dP^T m - D[q]) / 8 written as bf16 into two 128B-
+//           swizzled [128 keys x 64 queries] shared-memory tiles each
+//   MMA 2   dV += (P^T m) dO_i   (M 128 keys, N 64, K 128 queries; dO_i read as an MN-major B operand from the tile
+//                                  MMA 1 read K-major)            -> TMEM columns [256, 320), accumulated over i
+//           dK += dS^T Q_i                                         -> [320, 384), accumulated over i
+//           dQ_i = dS K_j         (M 128 queries: dS^T read as an MN-major A operand, i.e. transposed by the
+//                                  descriptor; K_j as MN-major B)  -> [384, 448), read out per tile and added into the
+//                                  fp32 dQ buffer with red.global.add (other key tiles add to the same rows)
+// Roles: warps 0-15 softmax / read-out (warp w owns TMEM lanes 32 (w % 4) .. + 31 = 32 key rows and the 32 query
+// columns of quarter w / 4: one CTA per SM leaves these warps alone with their latencies -- a first version with four
+// such warps ran the element-wise pass at ~0.2 instructions per cycle per scheduler and was slower than mma.sync),
+// warps 16-19 loaders (cp.async row gathers of K_j, V_j once and of Q_i, dO_i, {lse, D} per query tile, two stages),
+// warp 20 issues the MMAs.  162 KB of shared memory, 512 TMEM columns: one CTA per SM; MMA 1 of tile i + 1 runs under
+// the dQ read-out of tile i.
+constexpr int BT_SW = 16;                          // softmax warps
+constexpr int BT_THREADS = 32 * (BT_SW + 5);
+constexpr int BT_TILE = 128 * 128;                 // bytes of a [128 rows x 64 bf16] 128B-swizzled tile
+constexpr int BT_SMEM = 2 * BT_TILE /*K, V*/ + 2 * 2 * BT_TILE /*Q, dO x 2 stages*/ + 2 * BT_TILE /*P^T*/ + 2 * BT_TILE /*dS^T*/
+                        + 2 * 2 * 128 * 4 /*lse, D x 2 stages*/ + 128 /*barriers*/;
+
+__device__ __forceinline__ uint64_t bt_mnmajor_desc(uint32_t smem_addr) { return make_sw128_mnmajor_desc_lbo(smem_addr, 1024); }
+
+__global__ void __launch_bounds__(BT_THREADS, 1)
+attn_bwd_tc_kernel(AttnBwdArgs a) {
+    extern __shared__ __align__(1024) uint8_t bt_raw[];
+    uint8_t* smem = bt_raw;
+    const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * 128;
+    const int nq = a.Le + a.T;
+    const int nk = a.n_keys[b];
+    const int nkv = nk + a.T;
+    if (j0 >= nkv) return;                          // uniform per CTA, before any barrier / TMEM set-up
+    if (smem_u32(smem) & 1023u) __trap();
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + BT_TILE;
+    uint8_t* sQ = sV + BT_TILE;                     // [2 stages]
+    uint8_t* sG = sQ + 2 * BT_TILE;                 // [2 stages] dO
+    uint8_t* sPT = sG + 2 * BT_TILE;                // two tiles: queries 0-63 | 64-127
+    uint8_t* sDS = sPT + 2 * BT_TILE;
+    float* sStat = reinterpret_cast<float*>(sDS + 2 * BT_TILE);      // [stage][lse | D][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 2 * 128);
+    uint64_t* kv_ready = bars;          // count 128
+    uint64_t* q_full = bars + 1;        // [2] count 128
+    uint64_t* q_empty = bars + 3;       // [2] count 1 (commit behind MMA 2)
+    uint64_t* s_full = bars + 5;        // count 1 (commit behind MMA 1)
+    uint64_t* p_full = bars + 6;        // count 32 * BT_SW (softmax threads)
+    uint64_t* dq_full = bars + 7;       // count 1 (commit behind MMA 2)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int* kidx = a.key_idx + (long long)b * a.key_stride;
+    const int col = h * XDH;
+    // a key tile made only of decoder keys is seen by decoder queries only
+    const int i_first = (j0 >= nk) ? a.Le / 128 : 0;
+    const int n_tiles = (nq + 127) / 128 - i_first;
+
+    if (warp == BT_SW + 4) {
+        if (lane == 0) {
+            mbar_init(kv_ready, 128);
+            mbar_init(&q_full[0], 128); mbar_init(&q_full[1], 128);
+            mbar_init(&q_empty[0], 1); mbar_init(&q_empty[1], 1);
+            mbar_init(s_full, 1); mbar_init(p_full, 32 * BT_SW); mbar_init(dq_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
+
+    if (warp >= BT_SW && warp < BT_SW + 4) {
+        // ------------------------------------------------------------------ loaders
+        const int lt = threadIdx.x - 32 * BT_SW;     // 0..127
+        const int c = lt & 7, r0 = lt >> 3;          // 16-byte chunk / first row; rows r0 + 16 i
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 16 * i;
+            const int j = j0 + r;
+            const bool ok = j < nkv;
+            bool is_dec = false;
+            const long long row = ok ? xb_krow_index(a, kidx, nk, j, is_dec) : 0;
+            const __nv_bfloat16* src = (is_dec ? a.qkv_dec + ((long long)b * a.T + row) * a.ld_dec
+                                               : a.qkv_enc + ((long long)b * a.Le + row) * a.ld_enc) + col + c * 8;
+            const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+            cp_async16(sK + off, src + a.H, ok);
+            cp_async16(sV + off, src + 2 * a.H, ok);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async();
+        mbar_arrive(kv_ready);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int s = t & 1;
+            const int i0 = (i_first + t) * 128;
+            mbar_wait(&q_empty[s], ((t >> 1) & 1) ^ 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 16 * i;
+                const int qi = i0 + r;
+                const bool ok = qi < nq;
+                const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+                cp_async16(sQ + s * BT_TILE + off,
+                           xb_qrow(a, a.qkv_enc, a.ld_enc, a.qkv_dec, a.ld_dec, b, ok ? qi : 0) + col + c * 8, ok);
+                cp_async16(sG + s * BT_TILE + off,
+                           xb_qrow(a, a.do_enc, a.ldg_enc, a.do_dec, a.ldg_dec, b, ok ? qi : 0) + col + c * 8, ok);
+            }
+            cp_async_commit();
+            {
+                const int qi = i0 + lt;
+                const float* st = a.stats + (((long long)b * a.heads + h) * nq + (qi < nq ? qi : 0)) * 2;
+                // rows past the sequence: lse = +inf makes every probability of the column exp2(-inf) = 0
+                sStat[(s * 2 + 0) * 128 + lt] = qi < nq ? st[0] : INFINITY;
+                sStat[(s * 2 + 1) * 128 + lt] = qi < nq ? st[1] : 0.f;
+            }
+            cp_async_wait<0>();
+            fence_proxy_async();                     // cp.async tiles -> visible to the tensor core
+            mbar_arrive(&q_full[s]);                 // (release: the plain stores of the statistics, for the softmax warps)
+        }
+    } else if (warp == BT_SW + 4) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);                               // A, B K-major
+        constexpr uint32_t idesc_kv = make_idesc_bf16(128, 64) | (1u << 16);                  // B MN-major
+        constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);     // A and B MN-major
+        const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aPT = smem_u32(sPT), aDS = smem_u32(sDS);
+        mbar_wait(kv_ready, 0);
+        tc_fence_after();
+        for (int t = 0; t < n_tiles; ++t) {
+            const int s = t & 1;
+            const uint32_t aQ = smem_u32(sQ + s * BT_TILE), aG = smem_u32(sG + s * BT_TILE);
+            mbar_wait(&q_full[s], (t >> 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tS, make_sw128_kmajor_desc(aK) + 2 * k, make_sw128_kmajor_desc(aQ) + 2 * k, idesc_s, k ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tDP, make_sw128_kmajor_desc(aV) + 2 * k, make_sw128_kmajor_desc(aG) + 2 * k, idesc_s, k ? 1u : 0u);
+                umma_commit(s_full);
+            }
+            __syncwarp();
+            mbar_wait(p_full, t & 1);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {        // 16 queries per step: A = P^T / dS^T (K-major), B = dO / Q (MN-major)
+                    const uint32_t a_off = (k >> 2) * BT_TILE;
+                    umma_bf16(tDV, make_sw128_kmajor_desc(aPT + a_off) + 2 * (k & 3), bt_mnmajor_desc(aG + k * 2048), idesc_kv,
+                              (t | k) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t a_off = (k >> 2) * BT_TILE;
+                    umma_bf16(tDK, make_sw128_kmajor_desc(aDS + a_off) + 2 * (k & 3), bt_mnmajor_desc(aQ + k * 2048), idesc_kv,
+                              (t | k) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)          // 16 keys per step: A = dS (dS^T tiles read MN-major: M = queries)
+                    umma_bf16(tDQ, make_sw128_mnmajor_desc_lbo(aDS + k * 2048, BT_TILE), bt_mnmajor_desc(aK + k * 2048), idesc_dq,
+                              k ? 1u : 0u);
+                umma_commit(&q_empty[s]);
+                umma_commit(dq_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax / read-out
+        const int quarter = warp & 3, cq = warp >> 2;
+        const int r = quarter * 32 + lane;           // key row of the tile (S^T, dP^T, dV, dK) / query row (dQ) = TMEM lane
+        const int key = j0 + r;
+        const bool key_ok = key < nkv;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const int sw = r & 7;
+        const uint32_t drop_y = drop_attn_y(a.drop, b * a.heads + h);
+        const float row_bias = key_ok ? 0.f : -INFINITY;               // rows past the key list: every probability 0
+        // decoder keys are causal: key nk + j is seen by queries Le + j, Le + j + 1, ...; encoder keys by every query
+        const bool has_dec = j0 + 127 >= nk;                            // tile-uniform
+        const int q_min = key >= nk ? a.Le + (key - nk) : 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int s = t & 1;
+            const int i0 = (i_first + t) * 128;
+            const float* lse_s = sStat + (s * 2 + 0) * 128 + cq * 32;
+            const float* d_s = sStat + (s * 2 + 1) * 128 + cq * 32;
+            mbar_wait(&q_full[s], (t >> 1) & 1);     // acquire the loaders' {lse, D} stores of this stage
+            mbar_wait(s_full, t & 1);                // S^T / dP^T of this tile (and every earlier MMA) done
+            tc_fence_after();
+#pragma unroll 1
+            for (int hc = 0; hc < 2; ++hc) {         // two 16-column halves (register budget: 96 per thread)
+            uint32_t vs[16], vd[16];
+            tmem_ld_32x16(tS + lane_addr + cq * 32 + hc * 16, vs);
+            tmem_ld_32x16(tDP + lane_addr + cq * 32 + hc * 16, vd);
+            tmem_ld_wait_on(vs);
+            tmem_ld_wait_on(vd);
+            uint32_t pp[8], dd[8];
+#pragma unroll
+            for (int j2 = 0; j2 < 16; j2 += 2) {
+                const int jj = hc * 16 + j2;
+                const float2 l2 = *reinterpret_cast<const float2*>(lse_s + jj);
+                const float2 d2 = *reinterpret_cast<const float2*>(d_s + jj);
+                float p0, p1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(vs[j2]), a.scale_log2, row_bias) - l2.x));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(vs[j2 + 1]), a.scale_log2, row_bias) - l2.y));
+                if (has_dec) {
+                    const int qi = i0 + cq * 32 + jj;
+                    if (qi < q_min) p0 = 0.f;
+                    if (qi + 1 < q_min) p1 = 0.f;
+                }
+                float m0 = 1.f, m1 = 1.f;
+                if (a.drop.thr) {
+                    // one hash serves the key pair (key, key ^ 1) = this lane and lane ^ 1: the even lane hashes query column
+                    // jj, the odd lane column jj + 1, and they swap
+                    const uint32_t mine = drop_hash(a.drop.s0, a.drop.s1, drop_attn_x(i0 + cq * 32 + jj + (r & 1), key), drop_y);
+                    const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                    const uint32_t h0 = (r & 1) ? other : mine, h1 = (r & 1) ? mine : other;
+                    const uint32_t u0 = (r & 1) ? (h0 >> 16) : (h0 & 0xffffu), u1 = (r & 1) ? (h1 >> 16) : (h1 & 0xffffu);
+                    m0 = u0 >= a.drop.thr ? a.drop.scale : 0.f;
+                    m1 = u1 >= a.drop.thr ? a.drop.scale : 0.f;
+                }
+                pp[j2 >> 1] = pack_bf16x2(p0 * m0, p1 * m1);
+                dd[j2 >> 1] = pack_bf16x2(p0 * (__uint_as_float(vd[j2]) * m0 - d2.x) * a.scale,
+                                          p1 * (__uint_as_float(vd[j2 + 1]) * m1 - d2.y) * a.scale);
+            }
+            {
+                // 16 query columns = 32 bytes of row r: tile cq >> 1, 16-byte chunks (cq & 1) * 4 + hc * 2 + 0..1
+                uint8_t* pdst = sPT + (cq >> 1) * BT_TILE + r * 128;
+                uint8_t* ddst = sDS + (cq >> 1) * BT_TILE + r * 128;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int chunk = (cq & 1) * 4 + hc * 2 + q;
+                    *reinterpret_cast<uint4*>(pdst + ((chunk ^ sw) << 4)) = make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]);
+                    *reinterpret_cast<uint4*>(ddst + ((chunk ^ sw) << 4)) = make_uint4(dd[4 * q], dd[4 * q + 1], dd[4 * q + 2], dd[4 * q + 3]);
+                }
+            }
+            }
+            tc_fence_before();                       // TMEM reads ordered before the issuer's next MMAs
+            fence_proxy_async();                     // P^T / dS^T tiles visible to the tensor core
+            mbar_arrive(p_full);
+            // ---- dQ of this tile pair: row r = query i0 + r, columns cq * 16 .. + 15
+            mbar_wait(dq_full, t & 1);
+            tc_fence_after();
+            {
+                const int qi = i0 + r;
+                uint32_t v[16];
+                tmem_ld_32x16(tDQ + lane_addr + cq * 16, v);           // warp-collective: rows past nq load too
+                tmem_ld_wait_on(v);
+                if (qi < nq) {
+                    float* op = a.dq32 + ((long long)b * nq + qi) * a.H + col + cq * 16;
+#pragma unroll
+                    for (int d = 0; d < 16; d += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + d),
+                                     "f"(__uint_as_float(v[d])), "f"(__uint_as_float(v[d + 1])),
+                                     "f"(__uint_as_float(v[d + 2])), "f"(__uint_as_float(v[d + 3])) : "memory");
+                }
+            }
+            tc_fence_before();
+        }
+        // ---- dV, dK of this key tile (complete behind the last dq_full): columns cq * 16 .. + 15 of row r.  tcgen05.ld is
+        // warp-collective: every lane loads, only the rows inside the key list store
+        {
+            bool is_dec = false;
+            const long long row = key_ok ? xb_krow_index(a, kidx, nk, key, is_dec) : 0;
+            __nv_bfloat16* op = (is_dec ? a.dqkv_dec + ((long long)b * a.T + row) * a.ldq_dec
+                                        : a.dqkv_enc + ((long long)b * a.Le + row) * a.ldq_enc) + col + cq * 16;
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                uint32_t v[16];
+                tmem_ld_32x16((which ? tDV : tDK) + lane_addr + cq * 16, v);
+                tmem_ld_wait_on(v);
+                if (key_ok) {
+#pragma unroll
+                    for (int d = 0; d < 16; d += 8) {
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(v[d]), __uint_as_float(v[d + 1]));
+                        o.y = pack_bf16x2(__uint_as_float(v[d + 2]), __uint_as_float(v[d + 3]));
+                        o.z = pack_bf16x2(__uint_as_float(v[d + 4]), __uint_as_float(v[d + 5]));
+                        o.w = pack_bf16x2(__uint_as_float(v[d + 6]), __uint_as_float(v[d + 7]));
+                        *reinterpret_cast<uint4*>(op + (which ? 2 : 1) * a.H + d) = o;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == BT_SW + 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // ------------------------------------------------------------------------------- decoder rows, forward (nq > 1)
 // The teacher-forced passes score several decoder rows of a sample at once (all T of them in the `ref` / `neg` tail of
 // the eval forward and in every pass of the training step).  The scalar kernel of csrc/attention.cu reads K / V once
@@ -767,6 +1068,18 @@ static int attn_bwd_entry(const void* qkv_enc, long long ld_enc, const void* qkv
     if (a.dq32) {
         e = cudaMemsetAsync(a.dq32, 0, (size_t)B * nq * H * sizeof(float), st);
         if (e != cudaSuccess) { set_error("attn_bwd memset dq: %s", cudaGetErrorString(e)); return (int)e; }
+        // T2S_ATTN_BWD_TC=0: the mma.sync form of the fused pass
+        static const int use_tc = []() { const char* ev = getenv("T2S_ATTN_BWD_TC"); return (ev && ev[0] == '0') ? 0 : 1; }();
+        if (use_tc) {
+            static bool tc_attr = false;
+            if (!tc_attr) {
+                e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM);
+                if (e != cudaSuccess) { set_error("attn_bwd_tc attr: %s", cudaGetErrorString(e)); return (int)e; }
+                tc_attr = true;
+            }
+            dim3 gt((max_keys + T + 127) / 128, heads, B);
+            attn_bwd_tc_kernel<<<gt, BT_THREADS, BT_SMEM, st>>>(a);
+        } else
         attn_bwd_dkv_kernel<<<gk, XB_THREADS, XB_DKV_SMEM, st>>>(a);
         const long long n4 = (long long)B * nq * (H / 4);
         int grid = (int)((n4 + 255) / 256);
