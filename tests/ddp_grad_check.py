@@ -100,7 +100,9 @@ def main():
                            allreduce_bytes=int(eng.live_end) * 4, world=world)
         assert r_all <= 2e-3, (tag, r_all)
         assert worst <= 2e-2, (tag, worst, worst_name)
-        assert r_modes <= 1e-5, (tag, r_modes)
+        # two separate backward passes: the fp32 red.add order of the attention backward / weight-gradient GEMMs differs run
+        # to run, and a gradient that lands on a bf16 rounding boundary moves by a bf16 ulp -- 6e-5 relative L2 observed
+        assert r_modes <= 5e-4, (tag, r_modes)
         assert same, tag
         del m, eng
         torch.cuda.empty_cache()
