@@ -3,7 +3,8 @@
 
 Data-parallel training step of the B200 path == the single-GPU step on the concatenated batch:
 every rank runs forward + losses + backward on ITS shard of one seeded global batch; the backward all-reduces the flat
-gradient buffer bucket by bucket on a side stream (vitxt_gqa_b200/train.py).  The mean over ranks must equal the
+gradient buffer before it returns -- one flat NCCL call (default) or bucket by bucket on a side stream
+(T2S_B200_OVERLAP_ALLREDUCE=1); both are run here (vitxt_gqa_b200/train.py).  The mean over ranks must equal the
 gradient of  (1 / world) * sum_r loss(shard r)  computed in ONE process on the whole batch -- the reference's
 semantics: each DDP rank normalises pos_bce_loss by ITS OWN mask count (pythia/modules/losses.py:341-342) and DDP
 averages the per-rank gradients (pythia/trainers/base_trainer.py:134-137).  Also checked: p.grad holds the mean (as
@@ -65,6 +66,7 @@ def main():
         r_modes = rel_l2(g_ovl, g_one)
         # every rank: the whole batch in one process, loss = mean over shards of the shard's own losses
         eng.overlap_allreduce = False
+        eng.reduce_in_backward = False            # this IS the single-process reference: no collective
         for p in m.parameters():
             p.grad = None
         scores = m.forward(sl_full)
@@ -88,6 +90,7 @@ def main():
                 worst, worst_name = e, n
         r_all = rel_l2(g_ovl, g_ref)
         # ranks agree bit for bit on the reduced buffer, hence on the parameters after clip + Adam
+        eng.reduce_in_backward = True
         g_ovl2, _ = local_step(True)
         eng.step(lr=1e-4, max_grad_l2_norm=0.25)
         torch.cuda.synchronize()

@@ -118,8 +118,19 @@ class TrainEngine:
         self.grad_scale = 1.0      # set by all_reduce(): the factor that turns the summed gradients into their mean
         # gradient all-reduce overlapped with the backward (reference: DDP's bucketed all-reduce inside autograd,
         # base_trainer.py:134-137): as soon as a contiguous range of the flat gradient buffer is final, its NCCL
-        # all-reduce is enqueued on a side stream behind an event of the compute stream.  0 = one call after backward.
-        self.overlap_allreduce = os.environ.get("T2S_B200_OVERLAP_ALLREDUCE", "1") not in ("0", "False")
+        # all-reduce is enqueued on a side stream behind an event of the compute stream.  Built, tested (gradient parity
+        # at N = 2 and 8) and measured on one 8 x B200 NVSwitch box -- where it LOSES to one flat all-reduce after the
+        # backward: NCCL's CTAs compete with the persistent tcgen05 grids of the backward for SMs, so the "hidden"
+        # transfers slow the backward by more than the < 1 ms a 351 MB NVLS all-reduce costs on its own (batch 48 / GPU:
+        # 55.5 / 55.1 ms per step with 64 / 128 MB buckets, 54.8 ms with the flat call; batch 6 / GPU: 17.35 vs 16.94 ms).
+        # Default therefore: the flat call (T2S_B200_OVERLAP_ALLREDUCE=1 turns the overlap on, e.g. for PCIe / multi-node).
+        self.overlap_allreduce = os.environ.get("T2S_B200_OVERLAP_ALLREDUCE", "0") not in ("0", "False")
+        # final ranges are collected until this many bytes are pending, then go out as one group of NCCL calls: on
+        # NVSwitch a 351 MB all-reduce alone takes < 1 ms, while many small all-reduces under the backward are SM-starved by
+        # the persistent GEMM grids and slow the backward down more than they hide (measured at N = 8)
+        self.bucket_bytes = int(float(os.environ.get("T2S_B200_ALLREDUCE_BUCKET_MB", "64")) * (1 << 20))
+        self._ready_ranges = []
+        self.reduce_in_backward = True     # False: leave the local gradients alone (a caller that reduces by itself)
         self._comm_stream = None
         self._buckets_pending = []     # [(lo, hi)] of this backward, in launch order
         self._reduced_upto = None      # None: nothing reduced by the current backward
@@ -838,7 +849,10 @@ class TrainEngine:
                          g(e + "position_embeddings.weight"), g(e + "token_type_embeddings.weight"),
                          g(e + "LayerNorm.weight"), g(e + "LayerNorm.bias"), st)
         self.saved = None
-        self._finish_overlapped_reduce()      # remaining ranges (encoders' linears / id tables, embeddings) + join
+        if self._reduced_upto is not None:
+            self._finish_overlapped_reduce()  # remaining ranges (encoders' linears / id tables, embeddings) + join
+        elif self._dist_world() > 1 and self.reduce_in_backward:
+            self.all_reduce()                 # one flat NCCL call, still inside loss.backward(): p.grad gets the mean
         return [self.grad(n) for n in self.live_names]
 
     # ------------------------------------------------------------------ bucketed gradient all-reduce
@@ -873,28 +887,45 @@ class TrainEngine:
         r = self._range_of(prefixes)
         if r is None:
             return
+        self._ready_ranges.append(r)
+        if sum(hi - lo for lo, hi in self._ready_ranges) * 4 >= self.bucket_bytes:
+            self._flush_ready()
+
+    def _flush_ready(self):
+        """All-reduce the collected final ranges (adjacent ones merged) on the communication stream, behind an event of
+        the compute stream."""
+        if not self._ready_ranges:
+            return
         import torch.distributed as dist
-        lo, hi = r
+        merged = []
+        for lo, hi in sorted(self._ready_ranges):
+            if merged and lo <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], hi)
+            else:
+                merged.append([lo, hi])
+        self._ready_ranges = []
         main = torch.cuda.current_stream(self.dev)
         ready = torch.cuda.Event()
         ready.record(main)
         comm = self._comm_stream
         comm.wait_event(ready)
         with torch.cuda.stream(comm):
-            if self.time_comm:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(comm)
-            dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM)
-            if self.time_comm:
-                e1.record(comm)
-                self.comm_events.append(((hi - lo) * 4, e0, e1))
-        self._buckets_pending.append((lo, hi))
+            for lo, hi in merged:
+                if self.time_comm:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(comm)
+                dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM)
+                if self.time_comm:
+                    e1.record(comm)
+                    self.comm_events.append(((hi - lo) * 4, e0, e1))
+                self._buckets_pending.append((lo, hi))
 
     def _begin_overlapped_reduce(self):
         self._buckets_pending = []
+        self._ready_ranges = []
         self.comm_events = []
         self._reduced_upto = None
-        if not self.overlap_allreduce or self._dist_world() < 2:
+        if not self.overlap_allreduce or not self.reduce_in_backward or self._dist_world() < 2:
             return
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=self.dev)
@@ -906,6 +937,7 @@ class TrainEngine:
         if self._reduced_upto is None:
             return
         import torch.distributed as dist
+        self._ready_ranges = []        # whatever is still collected goes out with the remaining ranges below
         done = sorted(self._buckets_pending)
         gaps, cur = [], 0
         for lo, hi in done:
@@ -953,11 +985,22 @@ class TrainEngine:
         """Gradient all-reduce of the live range of the flat buffer over NCCL / NVLink (reference: DDP,
         base_trainer.py:134-137, which averages).  The buffer is SUMMED in place; the factor that makes it the mean
         (1 / world) is returned and remembered in `self.grad_scale`, which `step()` folds into the clip + Adam kernel,
-        so `eng.all_reduce(); eng.step(lr)` trains on the mean gradient like DDP does."""
+        so `eng.all_reduce(); eng.step(lr)` trains on the mean gradient like DDP does.  Under torch.distributed the
+        backward already calls this (or its overlapped form) before it returns, so that `p.grad` holds the mean as
+        DistributedDataParallel leaves it; a second call is a no-op that returns the factor."""
         if self._reduced_upto == self.live_end:     # the backward already all-reduced bucket by bucket (overlapped)
             return self.grad_scale
         from .dp import all_reduce_flat_
+        timed = self.time_comm and self._dist_world() > 1
+        if timed:
+            main = torch.cuda.current_stream(self.dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(main)
         self.grad_scale = all_reduce_flat_(self.flat_grad[:self.live_end])
+        if timed:
+            e1.record(main)
+            self.comm_events = [(int(self.live_end) * 4, e0, e1)]
+            self._join_events = (e0, e1)            # one flat call on the compute stream: all of it is exposed
         self._reduced_upto = self.live_end
         return self.grad_scale
 
