@@ -253,6 +253,12 @@ int t2s_info_nce_loss_bwd(const float* ref, const float* pos, const float* neg, 
 /* clip_grad_norm_ + torch.optim.Adam over a flat fp32 range: out[0] = sum g^2 (workspace: 1024 doubles); the step
  * scales g by grad_scale * min(1, max_norm / (sqrt(sumsq) * grad_scale + 1e-6)) (max_norm <= 0: no clipping) */
 int t2s_sumsq(const float* g, long long n, void* workspace, float* out, void* stream);
+/* after the optimizer step: rewrite, in place, every GEMM operand derived from the fp32 parameters (bf16 copies, bf16
+ * hi|lo splits, transposed bf16 copies for the dgrad GEMMs) from a device-resident job table of 48-byte records
+ * {long long src_off, dst, ld_dst; int rows, cols, mode (0 bf16, 1 hi|lo split, 2 bf16 transposed, 3 fp32), k_pad,
+ * tile0, tiles_x}; n_tiles = total 32 x 32 tiles.  Replaces ~300 tensor ops per step (what torch's `.to(bfloat16)`,
+ * `torch.cat`, `.t().contiguous()` did after `Adam.step()`, base_trainer.py:269). */
+int t2s_repack_weights(const float* flat_param, const void* jobs, int n_jobs, int n_tiles, void* stream);
 int t2s_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, int step, const float* sumsq, float max_norm, float grad_scale, void* stream);
 

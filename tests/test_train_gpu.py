@@ -620,3 +620,50 @@ def test_single_variant_training_gradients_match_oracle_autograd(kind):
     m.eval()
     with torch.no_grad():
         m(sample_list(inp))
+
+
+def test_operand_copies_are_rewritten_in_place_after_the_step():
+    """After `eng.step()` the bf16 / hi|lo / transposed weight copies are refreshed by ONE kernel from a job table
+    (t2s_repack_weights) instead of ~300 tensor ops: every copy must equal, bit for bit, what packing from scratch
+    through torch produces from the updated parameters -- and the tensors must be the same objects (pointers stable)."""
+    from parity_utils import build_b200_model, sample_list
+    from vitxt_gqa_b200 import synth
+    d = synth.Dims(frames=8, ocr_per_frame=4, vocab=200, frame_topk=3, ocr_topk=2)
+    sd = synth.make_state_dict(d, seed=0, variant="stress")
+    m = build_b200_model(d, sd, train=True)
+    sl = sample_list(synth.make_inputs(d, 2, seed=12, train=True))
+    eng = m.train_engine()
+    for _ in range(2):
+        sum(m(sl)["losses"].values()).backward()
+        eng.step(lr=1e-2, max_grad_l2_norm=0.25)          # a large step: every weight moves
+    torch.cuda.synchronize()
+    tab = eng._repack_tab
+    assert tab is not None and tab["jobs"] is not None and tab["n_jobs"] > 40, "the in-place path was not taken"
+    P, W = m._packed, eng._wt
+    assert P is tab["P"] and W is tab["W"]
+
+    def flat(x, pre=""):
+        out = {}
+        if torch.is_tensor(x):
+            out[pre] = x
+        elif isinstance(x, dict):
+            for k, v in x.items():
+                out.update(flat(v, pre + "/" + str(k)))
+        elif isinstance(x, (list, tuple)):
+            for i, v in enumerate(x):
+                out.update(flat(v, pre + "/%d" % i))
+        return out
+
+    got = {k: v.clone() for k, v in {**flat(P, "P"), **flat(W, "W")}.items()}
+    m._packed, eng._wt = None, None
+    want = {**flat(m._pack(eng.dev), "P"), **flat(eng._wt_pack(), "W")}
+    assert set(want) <= set(got) and set(got) - set(want) <= {"P/q_linear"}    # (the lazily split dead weight of the grounding module)
+    for k in want:
+        assert got[k].shape == want[k].shape and torch.equal(got[k], want[k]), "stale or wrong operand copy: " + k
+    # and a forward on the refreshed copies equals a forward on freshly packed ones
+    m.eval()
+    with torch.no_grad():
+        a = m(sl)["pos_scores"].clone()
+        m._packed = None
+        b = m(sl)["pos_scores"].clone()
+    assert torch.equal(a, b)

@@ -231,6 +231,71 @@ colsum_f32_kernel(const float* __restrict__ x, long long ldx, int rows, int N, f
     atomicAdd(dst + c, s);
 }
 
+// ------------------------------------------------------------------------------- operand copies of the weights
+// After an optimizer step every GEMM operand derived from the fp32 parameters is stale: the bf16 copies (answer
+// transformer, heads), the bf16 hi|lo splits (grounding chain), the transposed bf16 copies the dgrad GEMMs read.  The
+// host used to rebuild them with ~300 small tensor ops (3.3 ms per step, host bound); this kernel rewrites them all in
+// place from a job table: job = one parameter matrix -> one destination.  One CTA per 32 x 32 tile of a source matrix.
+struct RepackJob {          // 48 bytes; mirrored by vitxt_gqa_b200/train.py (struct format "qqqiiiiii4x")
+    long long src_off;      // first element of the fp32 [rows, cols] matrix in the flat parameter buffer
+    long long dst;          // destination pointer
+    long long ld_dst;       // row pitch of the destination in elements
+    int rows, cols;
+    int mode;               // 0 bf16 copy, 1 bf16 hi|lo split (lo at column k_pad), 2 bf16 transposed, 3 fp32 copy
+    int k_pad;              // mode 1: columns [cols, k_pad) of both halves are zero filled
+    int tile0;              // index of this job's first tile in the launch
+    int tiles_x;            // tiles along the columns (of max(cols, k_pad))
+};
+
+__global__ void __launch_bounds__(256)
+repack_kernel(const float* __restrict__ flat, const RepackJob* __restrict__ jobs, int n_jobs) {
+    __shared__ float tile[32][33];
+    // binary search: the job whose tile range holds blockIdx.x
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].tile0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const RepackJob j = jobs[lo];
+    const int t = blockIdx.x - j.tile0;
+    const int r0 = (t / j.tiles_x) * 32, c0 = (t % j.tiles_x) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    const float* src = flat + j.src_off;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + tx;
+        tile[ty + 8 * i][tx] = (r < j.rows && c < j.cols) ? src[(long long)r * j.cols + c] : 0.f;
+    }
+    __syncthreads();
+    if (j.mode == 2) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(j.dst);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = c0 + ty + 8 * i, r = r0 + tx;          // destination row = source column
+            if (c < j.cols && r < j.rows) dst[(long long)c * j.ld_dst + r] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + tx;
+        if (r >= j.rows) continue;
+        const float v = tile[ty + 8 * i][tx];
+        if (j.mode == 0) {
+            if (c < j.cols) reinterpret_cast<__nv_bfloat16*>(j.dst)[(long long)r * j.ld_dst + c] = __float2bfloat16_rn(v);
+        } else if (j.mode == 1) {
+            if (c < j.k_pad) {
+                __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(j.dst) + (long long)r * j.ld_dst;
+                const __nv_bfloat16 h = __float2bfloat16_rn(v);              // v == 0 in the padding columns
+                d[c] = h;
+                d[j.k_pad + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+            }
+        } else {
+            if (c < j.cols) reinterpret_cast<float*>(j.dst)[(long long)r * j.ld_dst + c] = v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------- row sums / casts
 // out[map(r), :] (+)= a[r] + b[r] + c[r]   (inputs bf16, fp32 output); used to gather the gradient of the joint
 // embedding from the three grounding variants
@@ -900,6 +965,13 @@ extern "C" int t2s_info_nce_loss_bwd(const float* ref, const float* pos, const f
 
 extern "C" long long t2s_loss_bwd_workspace_bytes(int B, int T) {
     return (long long)(1024 * sizeof(double)) + (long long)B * T * 5 * sizeof(float) + (long long)B * 8 * sizeof(float);
+}
+
+extern "C" int t2s_repack_weights(const float* flat_param, const void* jobs, int n_jobs, int n_tiles, void* stream) {
+    if (!flat_param || !jobs || n_jobs <= 0 || n_tiles <= 0) { set_error("repack_weights: bad arguments"); return T2S_ERR_ARG; }
+    static_assert(sizeof(RepackJob) == 48, "RepackJob layout is mirrored on the host");
+    repack_kernel<<<n_tiles, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(flat_param, reinterpret_cast<const RepackJob*>(jobs), n_jobs);
+    return launch_status("repack_weights");
 }
 
 extern "C" int t2s_sumsq(const float* g, long long n, void* workspace, float* out, void* stream) {

@@ -72,6 +72,7 @@ SIGNATURES = {
     "t2s_pos_bce_loss_bwd": [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p],
     "t2s_info_nce_loss_bwd": [_p, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p, _i, _p],
     "t2s_sumsq": [_p, _ll, _p, _p, _p],
+    "t2s_repack_weights": [_p, _p, _i, _i, _p],
     # input featurisation
     "t2s_phoc_build": [_p, _p, _i, _i, _p, _ll, _p],
     "t2s_phoc_build_fixed": [_p, _i, _i, _p, _ll, _p],

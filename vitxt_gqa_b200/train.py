@@ -1024,9 +1024,93 @@ class TrainEngine:
                 L.adam_step(self.flat_param.data_ptr() + 4 * a, self.flat_grad.data_ptr() + 4 * a,
                             self.adam_m.data_ptr() + 4 * a, self.adam_v.data_ptr() + 4 * a, b - a, lr * scale, betas[0],
                             betas[1], eps, self.step_count, _ptr(self._sumsq), float(max_grad_l2_norm or 0.0), grad_scale, st)
-        self.model._packed = None      # weights changed: bf16 / split operand copies are stale
-        self._wt = None
+        self._refresh_operand_copies(L, st)      # weights changed: bf16 / hi|lo / transposed operand copies are stale
         return self._sumsq
+
+    # ------------------------------------------------------------------ operand copies after the step (t2s_repack_weights)
+    def _refresh_operand_copies(self, L, st):
+        """The fused Adam kernel writes the parameters through raw pointers, so every GEMM operand derived from them
+        (model._packed, self._wt) is stale after it.  Rebuilding them through torch ops costs ~300 small launches (3.3 ms
+        of host time per step); instead one kernel rewrites the existing tensors in place from a job table, built once per
+        (packed weights, transposed weights) pair.  Pointers stay put, so cached TMA maps and a captured greedy-decode
+        graph keep reading the current weights.  Falls back to dropping the copies when the table cannot be built."""
+        m = self.model
+        P, W = m._packed, self._wt
+        if P is None or W is None or os.environ.get("T2S_B200_REPACK", "1") in ("0", "False"):
+            m._packed = None
+            self._wt = None
+            return
+        tab = getattr(self, "_repack_tab", None)
+        if tab is None or tab["P"] is not P or tab["W"] is not W:
+            tab = self._repack_tab = self._build_repack_table(P, W)
+        if tab["jobs"] is None:
+            m._packed = None
+            self._wt = None
+            return
+        L.repack_weights(_ptr(self.flat_param), _ptr(tab["jobs"]), tab["n_jobs"], tab["n_tiles"], st)
+
+    def _build_repack_table(self, P, W):
+        import struct
+        m = self.model
+        off, named = self.offsets, self.named
+        jobs = []          # (src_off, dst tensor, ld_dst, rows, cols, mode, k_pad)
+
+        def add(src_off, rows, cols, dst, mode, k_pad=0):
+            jobs.append((src_off, dst, dst.stride(0) if dst.dim() > 1 else dst.numel(), rows, cols, mode, k_pad))
+
+        def qkv_block(pre):     # q, k, v weights (and biases) are adjacent in the flat buffer (_flatten)
+            wq, wk, wv = (pre + "attention.self.%s.weight" % t for t in ("query", "key", "value"))
+            bq, bk, bv = (pre + "attention.self.%s.bias" % t for t in ("query", "key", "value"))
+            ok = (off[wk] == off[wq] + H * H and off[wv] == off[wk] + H * H and off[bk] == off[bq] + H and off[bv] == off[bk] + H)
+            return ok, off[wq], off[bq]
+
+        try:
+            for key, prefix, mode in (("text", "text_bert.encoder.layer.%d.", 1), ("qtv", "TransLayer.encoder.layer.%d.", 1),
+                                      ("mmt", "mmt.encoder.layer.%d.", 0)):
+                for i, lw in enumerate(P.get(key, [])):
+                    pre = prefix % i
+                    ok, wq_off, bq_off = qkv_block(pre)
+                    if not ok:
+                        raise LookupError("q/k/v of %s are not adjacent in the flat buffer" % pre)
+                    add(wq_off, 3 * H, H, lw["wqkv"], mode, H if mode == 1 else 0)
+                    add(bq_off, 1, 3 * H, lw["bqkv"], 3)
+                    for name, dst in (("attention.output.dense.weight", "wo"), ("intermediate.dense.weight", "wi"),
+                                      ("output.dense.weight", "wo2")):
+                        p = named[pre + name]
+                        add(off[pre + name], p.shape[0], p.shape[1], lw[dst], mode, p.shape[1] if mode == 1 else 0)
+                    wt = W[key][i]
+                    add(wq_off, 3 * H, H, wt["wqkvT"], 2)
+                    for name, dst in (("attention.output.dense.weight", "woT"), ("intermediate.dense.weight", "wiT"),
+                                      ("output.dense.weight", "wo2T")):
+                        p = named[pre + name]
+                        add(off[pre + name], p.shape[0], p.shape[1], wt[dst], 2)
+            for which, lin in (("obj", "linear_obj_feat_to_mmt_in.weight"), ("ocr", "linear_ocr_feat_to_mmt_in.weight")):
+                p = named[lin]
+                add(off[lin], p.shape[0], p.shape[1], P["w_" + which], 1, P["k_%s_pad" % which])
+                add(off[lin], p.shape[0], p.shape[1], W[which + "T"], 2)
+            for name, dst, dstT in (("classifier.module.weight", "w_cls", "clsT"), ("ocr_ptr_net.query.weight", "w_ptr_q", "ptr_qT"),
+                                    ("ocr_ptr_net.key.weight", "w_ptr_k", "ptr_kT")):
+                p = named[name]
+                add(off[name], p.shape[0], p.shape[1], P[dst], 0)
+                add(off[name], p.shape[0], p.shape[1], W[dstT], 2)
+            # everything else in P is an fp32 view of the parameter itself (no copy): check, do not assume
+            for n, t in P["f32"].items():
+                if n in self.offsets and t.data_ptr() != named[n].data_ptr():
+                    raise LookupError("fp32 operand of %s is a copy, not a view" % n)
+            for n in self.live_names:
+                if not named[n].is_contiguous() or named[n].dtype != torch.float32:
+                    raise LookupError("parameter %s is not a contiguous fp32 view" % n)
+        except (LookupError, KeyError) as e:
+            self.model.writer.write("operand copies are rebuilt through torch after every step (%s)" % e, "warning")
+            return dict(P=P, W=W, jobs=None)
+        recs, tile0 = [], 0
+        for src_off, dst, ld, rows, cols, mode, k_pad in jobs:
+            tx = (max(cols, k_pad) + 31) // 32
+            ty = (rows + 31) // 32
+            recs.append(struct.pack("qqqiiiiii", src_off, dst.data_ptr(), ld, rows, cols, mode, k_pad, tile0, tx))
+            tile0 += tx * ty
+        blob = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(self.dev)
+        return dict(P=P, W=W, jobs=blob, n_jobs=len(recs), n_tiles=tile0, keep=[j[1] for j in jobs])
 
     # ------------------------------------------------------------------ optimizer state / checkpoints in the reference's format
     def _adam_template(self, config, lr):
@@ -1093,4 +1177,5 @@ class TrainEngine:
             self.load_optimizer_state_dict(ckpt["optimizer"], config)
         self.model._packed = None
         self._wt = None
+        self._repack_tab = None
         return ckpt
