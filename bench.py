@@ -734,6 +734,16 @@ def run_train(args, wl, model, d, inp, dev, world, rank, local):
 
     for _ in range(args.warmup):
         step(resident)
+    if args.ncu_window:
+        # profiling aid (see the eval leg): exactly ONE warmed-up training step inside the profiler window
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(resident)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     clocks = ClockSampler(local)
     barrier()
     if rank == 0:

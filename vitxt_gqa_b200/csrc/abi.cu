@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/t2s_b200.h"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace t2s {
 static thread_local char g_err[512] = "";
@@ -10,6 +11,14 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("T2S_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
 }
 }  // namespace t2s
 

@@ -552,6 +552,8 @@ attn_dec_kernel(const __nv_bfloat16* __restrict__ qkv_enc, long long ld_enc, int
     int* s_idx = reinterpret_cast<int*>(Os + AD_WARPS * QC * DH);   // [max_keys] row offsets of the encoder keys
     const int b = blockIdx.y, h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c = lane & 7, sub = lane >> 3;           // 16-byte chunk of the 128-byte row / row within the warp load
+    pdl_wait();            // one-row launches of the greedy chain come in early (common.cuh)
+    pdl_release();
     const int n_enc = n_keys[b];
     const int nk = n_enc + t0 + nq;
     const int* kidx = key_idx + (long long)b * key_stride;
@@ -793,8 +795,8 @@ static int attn_dec_entry(const void* qkv_enc, long long ld_enc, int L_enc, cons
     const __nv_bfloat16* pd = reinterpret_cast<const __nv_bfloat16*>(qkv_dec);
     __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(out);
     if (qc == 1)
-        attn_dec_kernel<1><<<grid, AD_THREADS, smem, st>>>(pe, ld_enc, L_enc, pd, ld_dec, T, H, key_idx, n_keys,
-                                                           key_stride, t0, nq, po, ldo, 0.125f, max_keys, drop, lse_out);
+        launch_pdl(true, attn_dec_kernel<1>, grid, dim3(AD_THREADS), (size_t)smem, st, pe, ld_enc, L_enc, pd, ld_dec, T, H,
+                   key_idx, n_keys, key_stride, t0, nq, po, ldo, 0.125f, max_keys, drop, lse_out);
     else if (qc == 4)
         attn_dec_kernel<4><<<grid, AD_THREADS, smem, st>>>(pe, ld_enc, L_enc, pd, ld_dec, T, H, key_idx, n_keys,
                                                            key_stride, t0, nq, po, ldo, 0.125f, max_keys, drop, lse_out);

@@ -30,6 +30,36 @@ inline int launch_status(const char* what) {
 
 constexpr int kWarp = 32;
 
+// ---------------------------------------------------------------- programmatic dependent launch (greedy decode chain)
+// The 26 kernels of a greedy decode step depend on each other one by one and each runs ~10 us: launch latency and the
+// set-up of the next kernel (barrier init, TMEM allocation, descriptor prefetch) are a visible part of the chain.  A kernel
+// launched through launch_pdl() may become resident while its predecessor in the stream still runs; it executes
+// pdl_wait() before it touches anything the predecessor reads or writes (griddepcontrol.wait returns when the preceding
+// grid has completed and its writes are visible) and then calls pdl_release() so that ITS successor may come in -- in
+// that order, so that at most one grid sits waiting.  Both instructions do nothing in a normally launched kernel.
+// Only the small launches of the decode chain ask for it (`early`): a waiting grid of tens of thousands of CTAs would sit
+// on the thread slots the other stream needs.  T2S_PDL=0 in the environment launches everything the ordinary way.
+bool pdl_enabled();
+constexpr int PDL_MAX_ROWS = 4096;      // row-wise kernels: launches of at most this many rows come in early
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(bool early, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (early && pdl_enabled()) ? 1 : 0;        // early = false: an ordinary launch
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);       // errors surface through launch_status()
+}
+
 // index into a table of `n` rows, forced into range (bad feedback / teacher-forcing indices must not read out of bounds)
 __device__ __forceinline__ long long clamp_index(long long i, long long n) {
     return i < 0 ? 0 : (i >= n ? n - 1 : i);

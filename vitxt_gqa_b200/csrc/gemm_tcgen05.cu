@@ -41,6 +41,7 @@ struct GemmEpi {
     long long ldc, ldr;
     int flags;
     int c_lo_off;   // T2S_GEMM_OUT_SPLIT: column offset of the `lo` half of the bf16 hi|lo output
+    int stages;     // BN == 64 only: pipeline depth of this launch (GemmCfg<64>::STAGES or DEEP_STAGES)
 };
 
 // BN = 64 is the latency tile of the greedy decode (M = batch rows, a few dozen CTAs per launch, run next to the capped
@@ -64,6 +65,11 @@ struct GemmCfg {
     static constexpr int ROW_WARPS = BM / 32;                 // epilogue warps per column group that own tile rows
     static constexpr int STAGING_BYTES = (BN == 64 ? 2 : EPI_WARPS) * 4096;    // one 32-row x 128-byte box per active epilogue warp
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    // BN == 64 launches that cannot fill the SMs left to them twice over (N = 768: 12 CTAs) give up the second resident
+    // CTA for a pipeline that holds 12 k-blocks: a K = 768 product is then ONE round of loads and K = 3072 four, where
+    // six stages took two and eight -- the decode chain is bound by exactly these round trips (profiles/r2_tail_kernels.md)
+    static constexpr int DEEP_STAGES = 12;
+    static constexpr int DEEP_SMEM_BYTES = DEEP_STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
 };
 
 // MODE >= 0: the epilogue flags (low 5 bits of ep.flags) and "has a residual operand" (bit 5) are compile-time
@@ -78,7 +84,7 @@ __global__ void __launch_bounds__(GemmCfg<BN>::THREADS, GemmCfg<BN>::MIN_CTAS)  
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, GemmEpi ep, int M, int N, int K, int k_lo_off) {
     using Cfg = GemmCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
+    const int STAGES = BN == 64 ? ep.stages : Cfg::STAGES;      // run-time depth for the latency tile (see GemmCfg)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;      // 1024-byte aligned (STAGE_BYTES is a multiple of 1024)
@@ -129,6 +135,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (PAIR) cluster_sync_all();        // the peer's barriers are initialised before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // launched through launch_pdl() (decode tile): everything above ran next to the tail of the preceding kernel
+    pdl_wait();
+    pdl_release();
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
@@ -517,7 +526,8 @@ static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const 
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, MODE, PAIR>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             BN == 64 ? Cfg::DEEP_SMEM_BYTES : Cfg::SMEM_BYTES);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
             return (int)e;
@@ -550,6 +560,19 @@ static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const 
         return launch_status("gemm_bf16_tcgen05 (pair)");
     }
     const int grid = tiles < sms ? tiles : sms;
+    if (BN == 64) {
+        static int deep_tiles = -1;          // T2S_GEMM_DEEP_TILES: largest tile count that takes the deep pipeline (0 = never)
+        if (deep_tiles < 0) {
+            const char* e = getenv("T2S_GEMM_DEEP_TILES");
+            deep_tiles = e ? atoi(e) : 24;
+        }
+        GemmEpi ep64 = ep;
+        const bool deep = tiles <= deep_tiles && (K + GEMM_BK - 1) / GEMM_BK > Cfg::STAGES;
+        ep64.stages = deep ? Cfg::DEEP_STAGES : Cfg::STAGES;
+        launch_pdl(true, gemm_bf16_tcgen05_kernel<BN, MODE, PAIR>, dim3(grid), dim3(Cfg::THREADS),
+                   deep ? Cfg::DEEP_SMEM_BYTES : Cfg::SMEM_BYTES, st, ta, tb, tc, ep64, M, N, K, k_lo_off);
+        return launch_status("gemm_bf16_tcgen05");
+    }
     gemm_bf16_tcgen05_kernel<BN, MODE, PAIR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, ep, M, N, K, k_lo_off);
     return launch_status("gemm_bf16_tcgen05");
 }
@@ -833,7 +856,7 @@ static int gemm_entry(const char* who, bool x3, const void* A, long long lda, co
     CUtensorMap tc;
     rc = make_tmap_2d(&tc, out_f32, C, M, out_split ? 2LL * N : N, ldc, out_f32 ? 32 : 64, 32);
     if (rc) return rc;
-    GemmEpi ep{C, bias, residual, ldc, ldr, flags, N};
+    GemmEpi ep{C, bias, residual, ldc, ldr, flags, N, 0};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int k_lo = x3 ? K : 0;
     const int cap = (flags >> T2S_GEMM_SM_CAP_SHIFT) & 0xff;

@@ -173,6 +173,8 @@ add_ln_kernel(const TX* x, long long ldx, const TR* __restrict__ res, long long 
               const float* __restrict__ tanh_base, long long ld_base, float* __restrict__ out32, long long ldo32,
               __nv_bfloat16* __restrict__ out16, long long ldo16, RowMap map, TX* h_out, DropCfg drop) {
     const int row0 = (blockIdx.x * (NE_THREADS / 32) + (threadIdx.x >> 5)) * RPW, lane = threadIdx.x & 31;
+    pdl_wait();            // decode-chain launches come in early (common.cuh)
+    pdl_release();
     if (row0 >= rows) return;
     const int nv = H / 128;
     float4 v[RPW][NE_MAXV];
@@ -268,6 +270,8 @@ prev_embed_kernel(const long long* __restrict__ prev_inds, int ld_prev, int B, i
                   float eps, __nv_bfloat16* __restrict__ out16, float* __restrict__ out32, long long ldo, int T,
                   int n_ocr) {
     const int w = blockIdx.x * (NE_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    pdl_wait();
+    pdl_release();
     if (w >= B * nt) return;
     const int b = w / nt, t = t0 + w % nt;
     const int nv = H / 128;
@@ -418,9 +422,10 @@ static int add_ln_entry(bool split, const void* x, int x_bf16, long long ldx, co
                 reinterpret_cast<const TX*>(x), ldx, reinterpret_cast<const TR*>(res), ldr, gamma, beta, eps,     \
                 rows, H, tanh_base, ld_base, out32, ldo32, o16, ldo16, map, reinterpret_cast<TX*>(h_out), drop);  \
         else                                                                                                      \
-            add_ln_kernel<TX, TR, SP, false, RPW><<<grid, NE_THREADS, 0, st>>>(                                   \
-                reinterpret_cast<const TX*>(x), ldx, reinterpret_cast<const TR*>(res), ldr, gamma, beta, eps,     \
-                rows, H, tanh_base, ld_base, out32, ldo32, o16, ldo16, map, nullptr, drop);                       \
+            launch_pdl(rows <= PDL_MAX_ROWS, add_ln_kernel<TX, TR, SP, false, RPW>, dim3(grid), dim3(NE_THREADS), \
+                       0, st, reinterpret_cast<const TX*>(x), ldx, reinterpret_cast<const TR*>(res), ldr, gamma,  \
+                       beta, eps, rows, H, tanh_base, ld_base, out32, ldo32, o16, ldo16, map,                     \
+                       static_cast<TX*>(nullptr), drop);                                                          \
     } while (0)
     if (split) {
         if (x_bf16) { set_error("add_ln_split: fp32 input only"); return T2S_ERR_ARG; }
@@ -522,9 +527,10 @@ extern "C" int t2s_prev_embed(const long long* prev_inds, int ld_prev, int B, in
                               const float* ocr_g, const float* ocr_b, const float* emb_g, const float* emb_b, float eps,
                               void* out16, float* out32, long long ldo, int n_ocr, void* stream) {
     if (!h_ok(H) || B <= 0 || nt <= 0 || t0 < 0 || t0 + nt > T || n_ocr < 0 || V <= 0) { set_error("prev_embed: bad arguments"); return T2S_ERR_SHAPE; }
-    prev_embed_kernel<<<rows_grid(B * nt), NE_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        prev_inds, ld_prev, B, t0, nt, V, H, ans_w, ocr_emb, ocr_batch_stride, ld_ocr, pos_emb, type_emb, ans_g, ans_b,
-        ocr_g, ocr_b, emb_g, emb_b, eps, reinterpret_cast<__nv_bfloat16*>(out16), out32, ldo, T, n_ocr);
+    launch_pdl(B * nt <= PDL_MAX_ROWS, prev_embed_kernel, dim3(rows_grid(B * nt)), dim3(NE_THREADS), 0,
+               reinterpret_cast<cudaStream_t>(stream), prev_inds, ld_prev, B, t0, nt, V, H, ans_w, ocr_emb,
+               ocr_batch_stride, ld_ocr, pos_emb, type_emb, ans_g, ans_b, ocr_g, ocr_b, emb_g, emb_b, eps,
+               reinterpret_cast<__nv_bfloat16*>(out16), out32, ldo, T, n_ocr);
     return launch_status("prev_embed");
 }
 

@@ -27,6 +27,8 @@ ptr_score_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, int T, int 
                  int V, float denom) {
     extern __shared__ float qs[];     // [nq][H]
     const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_wait();            // one-row launches of the greedy chain come in early (common.cuh)
+    pdl_release();
     for (int i = tid; i < nq * H; i += PS_THREADS) {
         const int r = i / H, d = i % H;
         qs[i] = __bfloat162float(q[((long long)b * T + t0 + r) * ldq + d]);
@@ -97,6 +99,8 @@ argmax_feedback_kernel(const float* __restrict__ scores, long long ld_scores, in
     __shared__ int si[8];
     const int w = blockIdx.x, b = w / nt, t = t0 + w % nt;
     const float* row = scores + ((long long)b * T + t) * ld_scores;
+    pdl_wait();
+    pdl_release();
     float best = -INFINITY;
     int bi = 0x7fffffff;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
@@ -295,8 +299,8 @@ extern "C" int t2s_ptr_score(const void* q, long long ldq, int B, int T, int t0,
     const __nv_bfloat16* qp = reinterpret_cast<const __nv_bfloat16*>(q);
     const __nv_bfloat16* kp = reinterpret_cast<const __nv_bfloat16*>(keyp);
     if (nq == 1)
-        ptr_score_kernel<1><<<grid, PS_THREADS, smem, st>>>(qp, ldq, T, t0, nq, kp, key_batch_stride, ldk, O, H, mask,
-                                                           mask_stride, scores, ld_scores, V, sqrtf((float)H));
+        launch_pdl(true, ptr_score_kernel<1>, grid, dim3(PS_THREADS), smem, st, qp, ldq, T, t0, nq, kp, key_batch_stride,
+                   ldk, O, H, mask, mask_stride, scores, ld_scores, V, sqrtf((float)H));
     else
         ptr_score_kernel<PS_MAXQ><<<grid, PS_THREADS, smem, st>>>(qp, ldq, T, t0, nq, kp, key_batch_stride, ldk, O, H,
                                                                  mask, mask_stride, scores, ld_scores, V, sqrtf((float)H));
@@ -306,7 +310,8 @@ extern "C" int t2s_ptr_score(const void* q, long long ldq, int B, int T, int t0,
 extern "C" int t2s_argmax_feedback(const float* scores, long long ld_scores, int B, int T, int t0, int nt, int N,
                                    long long* prev_inds, int ld_prev, long long* argmax_out, void* stream) {
     if (B <= 0 || nt <= 0 || t0 < 0 || t0 + nt > T) { set_error("argmax_feedback: bad arguments"); return T2S_ERR_SHAPE; }
-    argmax_feedback_kernel<<<B * nt, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(scores, ld_scores, T, t0, nt, N, prev_inds, ld_prev, argmax_out);
+    launch_pdl(B * nt <= PDL_MAX_ROWS, argmax_feedback_kernel, dim3(B * nt), dim3(256), 0,
+               reinterpret_cast<cudaStream_t>(stream), scores, ld_scores, T, t0, nt, N, prev_inds, ld_prev, argmax_out);
     return launch_status("argmax_feedback");
 }
 
