@@ -1,3 +1,6 @@
+#!/bin/bash
+# The six shapes of the stress sweep (BASELINE configs[4]) back to back; JSON lines land in gpurun_out/f_stress_FxOf.json.
+#   gpurun --timeout 900 -- "bash tools/gpu_stress_sweep.sh"
 mkdir -p gpurun_out
 for s in "64 15 64" "128 15 32" "64 30 32" "128 30 16" "256 30 8" "256 60 4"; do
   set -- $s
@@ -12,4 +15,4 @@ for f in sorted(glob.glob("gpurun_out/f_stress_*.json")):
         print(f, j["value"], j["ms_per_step"], r.get("kernel"), r.get("share"), r.get("frac"))
     except Exception as e: print(f, "ERR", e)
 PY
-bash tools/gpu_train_profile.sh f
+

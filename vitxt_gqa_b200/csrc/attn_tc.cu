@@ -54,6 +54,13 @@ struct TcCfg {
     static constexpr int NSW = 4 * HS;                        // softmax warps
     static constexpr int THREADS = 32 * (NSW + 5);
     static constexpr int XCH_BYTES = X3 ? 2 * 2 * 128 * 4 : 0; // [tile parity][half][row] floats
+    // PIPE (the one-CTA-per-SM form): nothing else on the SM hides the softmax, so the CTA pipelines itself -- S lives in
+    // two TMEM buffers and S(t+1) is issued BEFORE the tensor core waits for P(t), i.e. it runs under the softmax of tile
+    // t; the softmax keeps the P of a tile in registers and stores it once P.V(t-1) has released the single P tile.  Per
+    // key tile the tensor core then sees S + P.V back to back (2 x 768 cycles in the bf16x3 form) instead of
+    // S + softmax + P.V in series.  512 TMEM columns: S 2 x 128, O 64.
+    static constexpr bool PIPE = X3;
+    static constexpr int TMEM_COLS = PIPE ? 512 : 256;
     static constexpr int SMEM = Q_BYTES + 2 * KV_STAGE + P_BYTES + 128 + XCH_BYTES;
 };
 
@@ -95,15 +102,19 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
     uint8_t* sKV = sQ + Cfg::Q_BYTES;
     uint8_t* sP = sKV + 2 * Cfg::KV_STAGE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
-    uint64_t* kv_full = bars;          // [2] count 128 (loader threads)
-    uint64_t* kv_empty = bars + 2;     // [2] count 1   (tcgen05.commit)
-    uint64_t* s_full = bars + 4;       // count 1
-    uint64_t* p_full = bars + 5;       // count 128 (softmax threads)
-    uint64_t* o_done = bars + 6;       // count 1: committed behind the last P.V of a query tile
-    uint64_t* q_empty = bars + 7;      // count 1: committed behind the last S of a query tile (Q may be overwritten)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* k_full = bars;           // [2] count 128 (loader threads): K plane(s) of a stage have landed
+    uint64_t* k_empty = bars + 2;      // [2] count 1   (tcgen05.commit behind S: the K plane(s) may be overwritten)
+    uint64_t* v_full = bars + 4;       // [2] count 128
+    uint64_t* v_empty = bars + 6;      // [2] count 1   (tcgen05.commit behind P.V)
+    uint64_t* s_full = bars + 8;       // [2] count 1   (PIPE: one per S buffer; otherwise only [0])
+    uint64_t* p_full = bars + 10;      // count 128 (softmax threads)
+    uint64_t* o_done = bars + 11;      // count 1: committed behind the last P.V of a query tile
+    uint64_t* q_empty = bars + 12;     // count 1: committed behind the last S of a query tile (Q may be overwritten)
+    uint64_t* p_free = bars + 13;      // count 1: committed behind every P.V (PIPE: the P tile may be overwritten)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
     float* xch = reinterpret_cast<float*>(sP + Cfg::P_BYTES + 128);
     constexpr int HS = Cfg::HS, NSW = Cfg::NSW;
+    constexpr bool PIPE = Cfg::PIPE;
 
     const int b = blockIdx.z, h = blockIdx.y;
     const int it0 = blockIdx.x * TC_NQ;                                    // first query tile of this CTA
@@ -116,23 +127,28 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
 
     if (warp == NSW + 4) {
         if (lane == 0) {
-            mbar_init(&kv_full[0], 128); mbar_init(&kv_full[1], 128);
-            mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
-            mbar_init(s_full, 1); mbar_init(p_full, 128 * HS); mbar_init(o_done, 1); mbar_init(q_empty, 1);
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&k_full[i], 128); mbar_init(&v_full[i], 128);
+                mbar_init(&k_empty[i], 1); mbar_init(&v_empty[i], 1);
+                mbar_init(&s_full[i], 1);
+            }
+            mbar_init(p_full, 128 * HS); mbar_init(o_done, 1); mbar_init(q_empty, 1); mbar_init(p_free, 1);
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, 256);
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + (PIPE ? 256 : 128);      // PIPE: S buffers at columns 0 and 128
 
     if (warp >= NSW && warp < NSW + 4) {
         // ------------------------------------------------------------------ loaders
+        // K and V of a stage have their own full / empty barriers: the K plane(s) are free again as soon as S has
+        // retired, long before the P.V that frees the V plane(s).
         const int lt = threadIdx.x - 32 * NSW;       // 0..127
         const int c = lt & 7, r0 = lt >> 3;          // 16-byte chunk / first row; rows r0 + 16 i
         auto load_q = [&](int q0) {              // Q tile(s): rows q0 .. q0+127 (zero-filled past L)
@@ -146,44 +162,96 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                 if (X3) cp_async16(sQ + TC_TILE + off, src + lo_off, ok);
             }
         };
-        auto load_tile = [&](int t, int s) {
+        int krow[8];                             // gathered rows of the key tile in flight (-1: past the key list)
+        auto load_k = [&](int t, int s) {
             uint8_t* dst = sKV + s * Cfg::KV_STAGE;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = r0 + 16 * i;
                 const int k = t * TC_BK + r;
-                const bool ok = k < nk;
-                const long long row = ok ? kidx[k] : 0;
-                const __nv_bfloat16* src = base + row * ld + c * 8;
+                krow[i] = k < nk ? kidx[k] : -1;
+                const bool ok = krow[i] >= 0;
+                const __nv_bfloat16* src = base + (long long)(ok ? krow[i] : 0) * ld + c * 8 + H;
                 const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
-                cp_async16(dst + off, src + H, ok);                                   // K (hi)
-                cp_async16(dst + NP * TC_TILE + off, src + 2 * H, ok);                // V (hi)
-                if (X3) {
-                    cp_async16(dst + TC_TILE + off, src + H + lo_off, ok);            // K lo
-                    cp_async16(dst + 3 * TC_TILE + off, src + 2 * H + lo_off, ok);    // V lo
-                }
+                cp_async16(dst + off, src, ok);                                       // K (hi)
+                if (X3) cp_async16(dst + TC_TILE + off, src + lo_off, ok);            // K lo
             }
+        };
+        auto load_v = [&](int s) {               // V rows of the tile load_k() was last called for
+            uint8_t* dst = sKV + s * Cfg::KV_STAGE + NP * TC_TILE;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 16 * i;
+                const bool ok = krow[i] >= 0;
+                const __nv_bfloat16* src = base + (long long)(ok ? krow[i] : 0) * ld + c * 8 + 2 * H;
+                const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+                cp_async16(dst + off, src, ok);                                       // V (hi)
+                if (X3) cp_async16(dst + TC_TILE + off, src + lo_off, ok);            // V lo
+            }
+        };
+        auto publish = [&](uint64_t* bar) {
+            fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core (async proxy)
+            mbar_arrive(bar);
         };
         int g = 0;                               // key tiles handled so far by this CTA: stage g & 1, phase (g >> 1) & 1
         for (int it = 0; it < n_items; ++it) {
             // Q of this query tile may land once every S of the previous one has retired; its first K/V tile goes to
-            // the stage the tile before last has left.  Both waits pass at once for the first query tile.
+            // the stage the tile before last has left.  The waits pass at once for the first query tile.
             mbar_wait(q_empty, (it & 1) ^ 1);
-            mbar_wait(&kv_empty[g & 1], ((g >> 1) & 1) ^ 1);
+            mbar_wait(&k_empty[g & 1], ((g >> 1) & 1) ^ 1);
             load_q((it0 + it) * TC_BQ);
-            load_tile(0, g & 1);
+            load_k(0, g & 1);
             cp_async_commit();
-            for (int t = 0; t < nt; ++t, ++g) {
-                // publish tile t BEFORE gathering tile t + 1: the other stage only frees when P.V(t-1) retires, and a
-                // clock trace showed S(t) waiting ~1500 cycles behind that wait and the issue of the next gathers
-                cp_async_wait<0>();                  // this thread's share of tile t (and Q) has landed
-                fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
-                mbar_arrive(&kv_full[g & 1]);
-                if (t + 1 < nt) {
+            mbar_wait(&v_empty[g & 1], ((g >> 1) & 1) ^ 1);
+            load_v(g & 1);
+            cp_async_commit();
+            if (PIPE) {
+                // K runs one tile ahead of V.  In flight at the top of iteration t: V(t) and K(t+1), both requested a
+                // whole iteration ago, so neither wait exposes a gather latency (index load + row gather, ~1.7 us,
+                // longer than the ~1.3 us the tensor core needs per tile); K(t+1) is published as soon as it has landed
+                // -- S(t+1) goes out under the softmax of tile t -- and only then does the loader block on the V planes
+                // P.V(t-1) still reads.  K(t+2) follows into the planes S(t) has left (S(t) retires before P.V(t-1)).
+                if (nt > 1) {
+                    load_k(1, (g + 1) & 1);      // stage free: its last S belongs to the tile before last (waited above
+                    cp_async_commit();           // for g, and for g + 1 one query tile / iteration earlier)
+                    cp_async_wait<2>();
+                } else {
+                    cp_async_wait<1>();
+                }
+                publish(&k_full[g & 1]);
+                for (int t = 0; t < nt; ++t, ++g) {
+                    const bool more = t + 1 < nt;
                     const int s1 = (g + 1) & 1;
-                    mbar_wait(&kv_empty[s1], (((g + 1) >> 1) & 1) ^ 1);
-                    load_tile(t + 1, s1);
-                    cp_async_commit();
+                    if (more) cp_async_wait<1>(); else cp_async_wait<0>();       // V(t)
+                    publish(&v_full[g & 1]);
+                    if (more) {
+                        cp_async_wait<0>();                                      // K(t+1)
+                        publish(&k_full[s1]);
+                        mbar_wait(&v_empty[s1], (((g + 1) >> 1) & 1) ^ 1);
+                        load_v(s1);
+                        cp_async_commit();
+                        if (t + 2 < nt) {
+                            mbar_wait(&k_empty[g & 1], (((g + 2) >> 1) & 1) ^ 1);
+                            load_k(t + 2, g & 1);
+                            cp_async_commit();
+                        }
+                    }
+                }
+            } else {
+                for (int t = 0; t < nt; ++t, ++g) {
+                    // publish tile t BEFORE gathering tile t + 1: the other stage only frees when P.V(t-1) retires, and
+                    // a clock trace showed S(t) waiting ~1500 cycles behind that wait and the issue of the next gathers
+                    cp_async_wait<0>();                  // this thread's share of tile t (and Q) has landed
+                    fence_proxy_async();
+                    mbar_arrive(&k_full[g & 1]);
+                    mbar_arrive(&v_full[g & 1]);
+                    if (t + 1 < nt) {
+                        const int s1 = (g + 1) & 1;
+                        mbar_wait(&v_empty[s1], (((g + 1) >> 1) & 1) ^ 1);       // P.V(t-1): S(t-1) retired before it
+                        load_k(t + 1, s1);
+                        load_v(s1);
+                        cp_async_commit();
+                    }
                 }
             }
         }
@@ -192,8 +260,9 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         constexpr uint32_t idesc_s = make_idesc_bf16(TC_BQ, TC_BK);
         constexpr uint32_t idesc_o = make_idesc_bf16(TC_BQ, TC_DH) | (1u << 16);     // B operand (V) is MN-major
         const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-        auto issue_s = [&](int t) {
+        auto issue_s = [&](int t) {              // t = running key-tile count g: stage t & 1, (PIPE) S buffer t & 1
             const uint32_t aK = smem_u32(sKV + (t & 1) * Cfg::KV_STAGE);
+            const uint32_t d_s = tmem_S + (PIPE ? (uint32_t)(t & 1) * 128u : 0u);
             if (lane == 0) {
                 bool first = true;
                 // small terms first (X3): Ql.Kh, Qh.Kl, then Qh.Kh
@@ -203,26 +272,37 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                     const uint64_t dk = make_sw128_kmajor_desc(aK + ((X3 && term == 1) ? TC_TILE : 0));
 #pragma unroll
                     for (int k = 0; k < TC_DH / 16; ++k) {
-                        umma_bf16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, first ? 0u : 1u);
+                        umma_bf16(d_s, dq + 2 * k, dk + 2 * k, idesc_s, first ? 0u : 1u);
                         first = false;
                     }
                 }
-                umma_commit(s_full);
+                umma_commit(&k_empty[t & 1]);
+                umma_commit(&s_full[PIPE ? (t & 1) : 0]);
             }
             __syncwarp();
+        };
+        auto issue_next_s = [&](int g, int t) {      // S of the next key tile of the same query tile
+            mbar_wait(&k_full[(g + 1) & 1], ((g + 1) >> 1) & 1);
+            tc_fence_after();
+            issue_s(g + 1);
+            if (t + 2 == nt && lane == 0) umma_commit(q_empty);     // last S of this query tile
         };
         int g = 0;                               // key tiles issued so far by this CTA (all query tiles)
         for (int it = 0; it < n_items; ++it) {
             // S of the first key tile goes out right behind the previous query tile's last P.V: S in TMEM is free (its
             // softmax has arrived on p_full), and O is only overwritten by this tile's first P.V, which waits for a
             // p_full that the softmax warps raise after they have read the previous O out
-            mbar_wait(&kv_full[g & 1], (g >> 1) & 1);
+            mbar_wait(&k_full[g & 1], (g >> 1) & 1);
             tc_fence_after();
             issue_s(g);
             if (nt == 1 && lane == 0) umma_commit(q_empty);
             for (int t = 0; t < nt; ++t, ++g) {
                 const int s = g & 1;
+                // PIPE: S(t+1) goes out first, into the other S buffer (its last reader, the softmax of tile t-1, has
+                // arrived on the p_full this warp waited for one iteration ago) -- it runs under the softmax of tile t
+                if (PIPE && t + 1 < nt) issue_next_s(g, t);
                 mbar_wait(p_full, g & 1);
+                mbar_wait(&v_full[s], (g >> 1) & 1);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t aV = smem_u32(sKV + s * Cfg::KV_STAGE + NP * TC_TILE);
@@ -240,16 +320,12 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                             first = false;
                         }
                     }
-                    umma_commit(&kv_empty[s]);
+                    umma_commit(&v_empty[s]);
+                    if (PIPE) umma_commit(p_free);
                     if (t == nt - 1) umma_commit(o_done);
                 }
                 __syncwarp();
-                if (t + 1 < nt) {
-                    mbar_wait(&kv_full[(g + 1) & 1], ((g + 1) >> 1) & 1);
-                    tc_fence_after();
-                    issue_s(g + 1);
-                    if (t + 2 == nt && lane == 0) umma_commit(q_empty);     // last S of this query tile
-                }
+                if (!PIPE && t + 1 < nt) issue_next_s(g, t);
             }
         }
     } else {
@@ -274,12 +350,16 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         // true maximum is exact, and the rare larger excess takes the same raise-and-recompute path as later tiles.
         uint32_t drop_x0 = 0;                              // DROP: (query << 16) | (first key of the tile >> 1)
         const uint32_t drop_y = drop_attn_y(drop, b * (H / TC_DH) + h);
+        // PIPE: the thread's P of the current tile (hi / lo planes, 16 keys per row of the arrays) waits in registers
+        // until P.V of the previous tile has released the shared-memory P tile; s_buf = S buffer of the current tile
+        uint32_t PH[PIPE ? NC : 1][8], PL[PIPE ? NC : 1][8];
+        uint32_t s_buf = tmem_S;
         auto exp_sweep = [&](int valid, float& m_use, bool seed, float& tile_max_raw, float& sum) {
             tile_max_raw = -INFINITY;
             sum = 0.f;
             const bool full = valid == TC_BK;
             uint32_t va[16], vb[16];
-            auto step = [&](uint32_t (&v)[16], int c) {       // 16 keys: columns c*16 .. c*16+15
+            auto step = [&](uint32_t (&v)[16], int c, int li) {       // 16 keys: columns c*16 .. c*16+15; li = c - c0
                 uint32_t ph[8], pl[8];
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
@@ -300,6 +380,11 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                     ph[j >> 1] = pack_bf16x2(p0, p1);
                     if (X3) pl[j >> 1] = pack_bf16x2(p0 - bf16lo(ph[j >> 1]), p1 - bf16hi(ph[j >> 1]));
                 }
+                if (PIPE) {                      // li is a literal at every call site: PH / PL stay in registers
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { PH[li][q] = ph[q]; PL[li][q] = pl[q]; }
+                    return;
+                }
                 // -> tile (c >> 2), 16-byte chunks (c & 3) * 2 + 0..1 of row r
                 uint8_t* dst = p_row + (c >> 2) * TC_TILE;
 #pragma unroll
@@ -316,13 +401,12 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
             if (seed) {
                 // the seed must be the same for both threads of a row: both read the row's first 16 keys
                 if (HS == 2 && half == 1) {
-                    tmem_ld_32x16(tmem_S + lane_addr, vb);
+                    tmem_ld_32x16(s_buf + lane_addr, vb);
                     tmem_ld_wait_on(vb);
                 }
             }
-            tmem_ld_32x16(tmem_S + lane_addr + c0 * 16, va);
-#pragma unroll 1
-            for (int c = 0; c < NC; c += 2) {
+            tmem_ld_32x16(s_buf + lane_addr + c0 * 16, va);
+            auto pair = [&](int c) {                 // 16-column steps c and c + 1 of this thread
                 tmem_ld_wait_on(va);
                 if (c == 0 && seed) {
                     float m0 = -INFINITY;
@@ -332,12 +416,34 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                             m0 = fmaxf(m0, __uint_as_float((HS == 2 && half == 1) ? vb[j] : va[j]));
                     m_use = m0 * scale_log2;         // key lists are compacted: column 0 always exists
                 }
-                tmem_ld_32x16(tmem_S + lane_addr + (c0 + c + 1) * 16, vb);
-                step(va, c0 + c);
+                tmem_ld_32x16(s_buf + lane_addr + (c0 + c + 1) * 16, vb);
+                step(va, c0 + c, c);
                 tmem_ld_wait_on(vb);
-                if (c + 2 < NC) tmem_ld_32x16(tmem_S + lane_addr + (c0 + c + 2) * 16, va);
-                step(vb, c0 + c + 1);
+                if (c + 2 < NC) tmem_ld_32x16(s_buf + lane_addr + (c0 + c + 2) * 16, va);
+                step(vb, c0 + c + 1, c + 1);
+            };
+            if (PIPE) {
+                static_assert(!PIPE || NC == 4, "the PIPE form unrolls four 16-column steps per thread");
+                pair(0);
+                pair(2);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < NC; c += 2) pair(c);
             }
+        };
+        // PIPE: the registers of exp_sweep -> the P tile (columns half * 64 .. + 63 of row r, hi and lo planes)
+        auto store_p = [&]() {
+            uint8_t* dst = p_row + half * TC_TILE;
+#pragma unroll
+            for (int li = 0; li < (PIPE ? NC : 0); ++li)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int chunk = li * 2 + q;
+                    *reinterpret_cast<uint4*>(dst + ((chunk ^ sw) << 4)) =
+                        make_uint4(PH[li][4 * q], PH[li][4 * q + 1], PH[li][4 * q + 2], PH[li][4 * q + 3]);
+                    *reinterpret_cast<uint4*>(dst + 2 * TC_TILE + ((chunk ^ sw) << 4)) =
+                        make_uint4(PL[li][4 * q], PL[li][4 * q + 1], PL[li][4 * q + 2], PL[li][4 * q + 3]);
+                }
         };
         // HS == 2: the two threads of a row agree on the tile maximum through shared memory (slot = tile parity, so the
         // next tile's write cannot overtake a slow reader); named barrier 1 covers the 256 softmax threads
@@ -354,8 +460,12 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         for (int t = 0; t < nt; ++t, ++g) {
             const int valid = min(TC_BK, nk - t * TC_BK);          // keys of this tile that exist
             if (DROP) drop_x0 = drop_attn_x(q0 + r, t * TC_BK);
-            mbar_wait(s_full, g & 1);       // S(t) done; MMAs retire in order, so P.V(t-1) is done as well
+            // !PIPE: S(t) done; MMAs retire in order, so P.V(t-1) is done as well.  PIPE: S(t) was issued ahead of
+            // P.V(t-1); whoever touches O or the P tile waits for p_free (phase g - 1, passes at once for g == 0)
+            if (PIPE) s_buf = tmem_S + (uint32_t)(g & 1) * 128u;
+            mbar_wait(&s_full[PIPE ? (g & 1) : 0], PIPE ? (g >> 1) & 1 : g & 1);
             tc_fence_after();
+            bool pv_done = !PIPE;
             float mt_raw, sum;
             exp_sweep(valid, m_run, t == 0, mt_raw, sum);
             mt_raw = joint_max(mt_raw, g & 1);
@@ -369,6 +479,11 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                     l_run *= corr;
                 }
                 if (t > 0) {
+                    if (!pv_done) {
+                        mbar_wait(p_free, (g & 1) ^ 1);
+                        tc_fence_after();
+                        pv_done = true;
+                    }
                     // rescale this warp's 32 rows of O in TMEM (rows that keep their maximum use corr == 1);
                     // HS == 2: each thread of a row takes 32 of the 64 columns
 #pragma unroll
@@ -386,6 +501,10 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                 exp_sweep(valid, m_run, false, mt_raw, sum);      // P of this tile against the raised maximum
             }
             l_run += sum;
+            if (PIPE) {
+                if (!pv_done) mbar_wait(p_free, (g & 1) ^ 1);
+                store_p();
+            }
             tc_fence_before();                   // S reads / O rescale ordered before the issuer's next MMAs
             fence_proxy_async();                 // P tile visible to the tensor core
             mbar_arrive(p_full);
@@ -440,7 +559,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
     __syncthreads();
     if (warp == NSW + 4) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
