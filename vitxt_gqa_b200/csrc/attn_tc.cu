@@ -37,12 +37,20 @@ constexpr int TC_TILE = 128 * 128;           // bytes of a [128 rows x 64 bf16] 
 // i is in its last softmax, P.V and read-out.
 constexpr int TC_NQ = 3;
 
+// Threads per query row in the bf16x3 form (2 or 4).  One CTA per SM: with two threads per row the eight softmax warps
+// (two per scheduler) took ~3 000 cycles per 128 x 128 tile against ~1 500 of tensor work -- latency bound (tcgen05.ld,
+// MUFU, the hi / lo conversions), not issue bound; four threads per row = 16 softmax warps, 32 key columns each -- measured
+// on the t2s_abinet step: 1.65 ms against 1.62 ms with two, because the launches are already at ~0.7 of the power-capped
+// tensor rate once the padded tile work is counted.  The default stays 2.
+#ifndef T2S_TC_X3_HS
+#define T2S_TC_X3_HS 2
+#endif
+
 template <bool X3>
 struct TcCfg {
     static constexpr int NP = X3 ? 2 : 1;                     // hi (+ lo) planes
     static constexpr int Q_BYTES = NP * TC_TILE;               // Q tile(s)
     static constexpr int KV_STAGE = NP * 2 * TC_TILE;          // K plane(s) then V plane(s)
-    static constexpr int P_BYTES = NP * 2 * TC_TILE;           // per plane: keys 0-63 tile, keys 64-127 tile
     // no alignment slack: two CTAs (2 x (114 816 + 1 024 reserved)) must fit the 227 KB of an SM, so the kernel
     // relies on the dynamic shared-memory window starting 1024-byte aligned (it has no static shared memory)
     // and traps otherwise
@@ -50,10 +58,10 @@ struct TcCfg {
     // softmax also does twice the conversions (hi and lo planes).  So each row is split between two threads (columns
     // 0-63 / 64-127, warps w and w + 4 reach the same TMEM lane quarter): 8 softmax warps, two per scheduler, which
     // exchange the tile maximum (per tile) and the row sum (per query tile) through shared memory.
-    static constexpr int HS = X3 ? 2 : 1;                     // threads per query row
+    static constexpr int HS = X3 ? T2S_TC_X3_HS : 1;          // threads per query row
     static constexpr int NSW = 4 * HS;                        // softmax warps
     static constexpr int THREADS = 32 * (NSW + 5);
-    static constexpr int XCH_BYTES = X3 ? 2 * 2 * 128 * 4 : 0; // [tile parity][half][row] floats
+    static constexpr int XCH_BYTES = HS > 1 ? 2 * HS * 128 * 4 : 0;     // [tile parity][part][row] floats
     // PIPE (the one-CTA-per-SM form): nothing else on the SM hides the softmax, so the CTA pipelines itself -- S lives in
     // two TMEM buffers and S(t+1) is issued BEFORE the tensor core waits for P(t), i.e. it runs under the softmax of tile
     // t; the softmax keeps the P of a tile in registers and stores it once P.V(t-1) has released the single P tile.  Per
@@ -61,7 +69,7 @@ struct TcCfg {
     // S + softmax + P.V in series.  512 TMEM columns: S 2 x 128, O 64.
     static constexpr bool PIPE = X3;
     static constexpr int TMEM_COLS = PIPE ? 512 : 256;
-    static constexpr int SMEM = Q_BYTES + 2 * KV_STAGE + P_BYTES + 128 + XCH_BYTES;
+    static constexpr int SMEM = Q_BYTES + 2 * KV_STAGE + 128 + XCH_BYTES;
 };
 
 // MN-major (rows = K index, 64 contiguous N elements = one 128-byte row) 128B-swizzled operand: 8-row groups
@@ -100,8 +108,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
     if (smem_u32(smem) & 1023u) __trap();      // 128B-swizzled tiles need 1024-byte alignment
     uint8_t* sQ = smem;
     uint8_t* sKV = sQ + Cfg::Q_BYTES;
-    uint8_t* sP = sKV + 2 * Cfg::KV_STAGE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + 2 * Cfg::KV_STAGE);
     uint64_t* k_full = bars;           // [2] count 128 (loader threads): K plane(s) of a stage have landed
     uint64_t* k_empty = bars + 2;      // [2] count 1   (tcgen05.commit behind S: the K plane(s) may be overwritten)
     uint64_t* v_full = bars + 4;       // [2] count 128
@@ -112,7 +119,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
     uint64_t* q_empty = bars + 12;     // count 1: committed behind the last S of a query tile (Q may be overwritten)
     uint64_t* p_free = bars + 13;      // count 1: committed behind every P.V (PIPE: the P tile may be overwritten)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-    float* xch = reinterpret_cast<float*>(sP + Cfg::P_BYTES + 128);
+    float* xch = reinterpret_cast<float*>(sKV + 2 * Cfg::KV_STAGE + 128);
     constexpr int HS = Cfg::HS, NSW = Cfg::NSW;
     constexpr bool PIPE = Cfg::PIPE;
 
@@ -143,7 +150,9 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + (PIPE ? 256 : 128);      // PIPE: S buffers at columns 0 and 128
+    // columns: S (PIPE: two buffers) | O (64) | P as packed bf16 pairs, 64 per plane (the A operand of P.V, read by the
+    // tensor core straight from tensor memory: 256 columns in the two-CTA form, 448 of 512 in the PIPE form)
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + (PIPE ? 256 : 128), tmem_P = tmem_O + 64;
 
     if (warp >= NSW && warp < NSW + 4) {
         // ------------------------------------------------------------------ loaders
@@ -259,7 +268,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         // ------------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc_s = make_idesc_bf16(TC_BQ, TC_BK);
         constexpr uint32_t idesc_o = make_idesc_bf16(TC_BQ, TC_DH) | (1u << 16);     // B operand (V) is MN-major
-        const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+        const uint32_t aQ = smem_u32(sQ);
         auto issue_s = [&](int t) {              // t = running key-tile count g: stage t & 1, (PIPE) S buffer t & 1
             const uint32_t aK = smem_u32(sKV + (t & 1) * Cfg::KV_STAGE);
             const uint32_t d_s = tmem_S + (PIPE ? (uint32_t)(t & 1) * 128u : 0u);
@@ -309,14 +318,13 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                     bool first = t == 0;         // O accumulates across the key tiles of one query tile
 #pragma unroll
                     for (int term = X3 ? 0 : 2; term < 3; ++term) {      // Pl.Vh, Ph.Vl, Ph.Vh
-                        const uint32_t p_plane = aP + ((X3 && term == 0) ? 2 * TC_TILE : 0);
+                        const uint32_t p_plane = tmem_P + ((X3 && term == 0) ? 64u : 0u);      // Pl, then Ph
                         const uint32_t v_plane = aV + ((X3 && term == 1) ? TC_TILE : 0);
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k) {
-                            // P: two [128 x 64-key] K-major tiles side by side; V: 16 keys = 2048 B per k-step
-                            const uint64_t dp = make_sw128_kmajor_desc(p_plane + (k >> 2) * TC_TILE) + 2 * (k & 3);
+                            // P: 16 keys = 8 packed columns of its plane in tensor memory; V: 16 keys = 2048 B per k-step
                             const uint64_t dv = make_sw128_mnmajor_desc(v_plane + k * 2048);
-                            umma_bf16(tmem_O, dp, dv, idesc_o, first ? 0u : 1u);
+                            umma_bf16_ts(tmem_O, p_plane + 8 * k, dv, idesc_o, first ? 0u : 1u);
                             first = false;
                         }
                     }
@@ -331,11 +339,9 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
     } else {
         // ------------------------------------------------------------------ softmax (thread == query row == TMEM lane)
         const int r = threadIdx.x & 127;                   // query row of this thread
-        const int half = threadIdx.x >> 7;                 // HS == 2: which 64 key columns of the row (0 otherwise)
+        const int half = threadIdx.x >> 7;                 // HS > 1: which 128 / HS key columns of the row (0 otherwise)
         constexpr int NC = 8 / HS;                         // 16-column steps per sweep of this thread
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        uint8_t* p_row = sP + r * 128;
-        const int sw = r & 7;
         constexpr float kRescale = 8.0f;                   // log2 domain: P stays below 2^8
         float m_run = -INFINITY, l_run = 0.f;
         int g = 0;                                         // key tiles consumed so far by this CTA
@@ -385,22 +391,14 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                     for (int q = 0; q < 8; ++q) { PH[li][q] = ph[q]; PL[li][q] = pl[q]; }
                     return;
                 }
-                // -> tile (c >> 2), 16-byte chunks (c & 3) * 2 + 0..1 of row r
-                uint8_t* dst = p_row + (c >> 2) * TC_TILE;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int chunk = (c & 3) * 2 + q;
-                    *reinterpret_cast<uint4*>(dst + ((chunk ^ sw) << 4)) =
-                        make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
-                    if (X3)
-                        *reinterpret_cast<uint4*>(dst + 2 * TC_TILE + ((chunk ^ sw) << 4)) =
-                            make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
-                }
+                // -> packed columns c * 8 .. + 7 of this row's lane in the P plane(s)
+                tmem_st_32x8(tmem_P + lane_addr + c * 8, ph);
+                if (X3) tmem_st_32x8(tmem_P + 64 + lane_addr + c * 8, pl);
             };
             const int c0 = half * NC;                // first global 16-column step of this thread
             if (seed) {
-                // the seed must be the same for both threads of a row: both read the row's first 16 keys
-                if (HS == 2 && half == 1) {
+                // the seed must be the same for all threads of a row: all read the row's first 16 keys
+                if (HS > 1 && half > 0) {
                     tmem_ld_32x16(s_buf + lane_addr, vb);
                     tmem_ld_wait_on(vb);
                 }
@@ -413,7 +411,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if (full || j < valid)
-                            m0 = fmaxf(m0, __uint_as_float((HS == 2 && half == 1) ? vb[j] : va[j]));
+                            m0 = fmaxf(m0, __uint_as_float((HS > 1 && half > 0) ? vb[j] : va[j]));
                     m_use = m0 * scale_log2;         // key lists are compacted: column 0 always exists
                 }
                 tmem_ld_32x16(s_buf + lane_addr + (c0 + c + 1) * 16, vb);
@@ -423,9 +421,9 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                 step(vb, c0 + c + 1, c + 1);
             };
             if (PIPE) {
-                static_assert(!PIPE || NC == 4, "the PIPE form unrolls four 16-column steps per thread");
+                static_assert(!PIPE || NC == 4 || NC == 2, "the PIPE form unrolls two or four 16-column steps per thread");
                 pair(0);
-                pair(2);
+                if (NC == 4) pair(2);
             } else {
 #pragma unroll 1
                 for (int c = 0; c < NC; c += 2) pair(c);
@@ -433,25 +431,21 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         };
         // PIPE: the registers of exp_sweep -> the P tile (columns half * 64 .. + 63 of row r, hi and lo planes)
         auto store_p = [&]() {
-            uint8_t* dst = p_row + half * TC_TILE;
 #pragma unroll
-            for (int li = 0; li < (PIPE ? NC : 0); ++li)
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int chunk = li * 2 + q;
-                    *reinterpret_cast<uint4*>(dst + ((chunk ^ sw) << 4)) =
-                        make_uint4(PH[li][4 * q], PH[li][4 * q + 1], PH[li][4 * q + 2], PH[li][4 * q + 3]);
-                    *reinterpret_cast<uint4*>(dst + 2 * TC_TILE + ((chunk ^ sw) << 4)) =
-                        make_uint4(PL[li][4 * q], PL[li][4 * q + 1], PL[li][4 * q + 2], PL[li][4 * q + 3]);
-                }
+            for (int li = 0; li < (PIPE ? NC : 0); ++li) {
+                tmem_st_32x8(tmem_P + lane_addr + (half * NC + li) * 8, PH[li]);
+                tmem_st_32x8(tmem_P + 64 + lane_addr + (half * NC + li) * 8, PL[li]);
+            }
         };
         // HS == 2: the two threads of a row agree on the tile maximum through shared memory (slot = tile parity, so the
         // next tile's write cannot overtake a slow reader); named barrier 1 covers the 256 softmax threads
         auto joint_max = [&](float mine, int slot) {
             if (HS == 1) return mine;
-            xch[(slot * 2 + half) * 128 + r] = mine;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            return fmaxf(mine, xch[(slot * 2 + (half ^ 1)) * 128 + r]);
+            xch[(slot * HS + half) * 128 + r] = mine;
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * HS) : "memory");
+#pragma unroll
+            for (int o = 1; o < HS; ++o) mine = fmaxf(mine, xch[(slot * HS + ((half + o) & (HS - 1))) * 128 + r]);
+            return mine;
         };
         for (int it = 0; it < n_items; ++it) {
         const int q0 = (it0 + it) * TC_BQ;
@@ -486,15 +480,24 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                     }
                     // rescale this warp's 32 rows of O in TMEM (rows that keep their maximum use corr == 1);
                     // HS == 2: each thread of a row takes 32 of the 64 columns
-#pragma unroll
-                    for (int c = 0; c < 2 / HS; ++c) {
-                        uint32_t v[32];
-                        const uint32_t oc = (uint32_t)(HS == 2 ? half : c) * 32;
-                        tmem_ld_32x32(tmem_O + lane_addr + oc, v);
+                    if (HS == 4) {               // 16 of the 64 columns per thread
+                        uint32_t v[16];
+                        tmem_ld_32x16(tmem_O + lane_addr + half * 16, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * corr);
-                        tmem_st_32x32(tmem_O + lane_addr + oc, v);
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * corr);
+                        tmem_st_32x16(tmem_O + lane_addr + half * 16, v);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 2 / HS; ++c) {
+                            uint32_t v[32];
+                            const uint32_t oc = (uint32_t)(HS == 2 ? half : c) * 32;
+                            tmem_ld_32x32(tmem_O + lane_addr + oc, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * corr);
+                            tmem_st_32x32(tmem_O + lane_addr + oc, v);
+                        }
                     }
                     tmem_st_wait();
                 }
@@ -505,19 +508,20 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
                 if (!pv_done) mbar_wait(p_free, (g & 1) ^ 1);
                 store_p();
             }
-            tc_fence_before();                   // S reads / O rescale ordered before the issuer's next MMAs
-            fence_proxy_async();                 // P tile visible to the tensor core
+            tmem_st_wait();                      // P (and a rescaled O) have reached tensor memory
+            tc_fence_before();                   // S reads / P, O writes ordered before the issuer's next MMAs
             mbar_arrive(p_full);
         }
         mbar_wait(o_done, it & 1);
         tc_fence_after();
         const int row = q0 + r;
         float l_row = l_run;
-        if (HS == 2) {                           // row sum = the two threads' partial sums (slots are free: the last
-            xch[half * 128 + r] = l_run;         // joint_max of this query tile lies behind a barrier both have passed)
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            l_row += xch[(half ^ 1) * 128 + r];
-            asm volatile("bar.sync 1, 256;" ::: "memory");      // reads done before the next query tile writes
+        if (HS > 1) {                            // row sum = the threads' partial sums (slots are free: the last
+            xch[half * 128 + r] = l_run;         // joint_max of this query tile lies behind a barrier all have passed)
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * HS) : "memory");
+#pragma unroll
+            for (int o = 1; o < HS; ++o) l_row += xch[((half + o) & (HS - 1)) * 128 + r];
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * HS) : "memory");      // reads done before the next query tile writes
         }
         const float inv = l_row > 0.f ? (DROP ? drop.scale : 1.0f) / l_row : 0.f;
         // training step: log2-sum-exp of the row (exp2 domain of the scaled scores) in the {lse2, D} layout of the
@@ -525,29 +529,31 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int lo_off, 
         if (DROP && lse_out && row < L && (HS == 1 || half == 0))
             lse_out[(((long long)b * (H / TC_DH) + h) * lse_rows + row) * 2] = m_run + log2f(l_row);
         __nv_bfloat16* op = out + ((long long)b * L + row) * ldo + h * TC_DH;
+        constexpr int OW = HS == 4 ? 16 : 32;    // O columns per read-out chunk
 #pragma unroll
-        for (int cc = 0; cc < 2 / HS; ++cc) {
-            const int c = HS == 2 ? half : cc;   // 32-column half of O this thread writes out
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);      // warp-collective: rows past L load too
+        for (int cc = 0; cc < 64 / (HS * OW); ++cc) {
+            const int c = HS > 1 ? half : cc;    // chunk of O this thread writes out
+            uint32_t v[OW];
+            if (HS == 4) tmem_ld_32x16(tmem_O + lane_addr + c * OW, reinterpret_cast<uint32_t (&)[16]>(v));
+            else tmem_ld_32x32(tmem_O + lane_addr + c * OW, reinterpret_cast<uint32_t (&)[32]>(v));      // warp-collective: rows past L load too
             tmem_ld_wait();
             if (row < L) {
 #pragma unroll
-                for (int d = 0; d < 32; d += 8) {
+                for (int d = 0; d < OW; d += 8) {
                     float f[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[d + e]) * inv;
                     uint4 hi;
                     hi.x = pack_bf16x2(f[0], f[1]); hi.y = pack_bf16x2(f[2], f[3]);
                     hi.z = pack_bf16x2(f[4], f[5]); hi.w = pack_bf16x2(f[6], f[7]);
-                    *reinterpret_cast<uint4*>(op + c * 32 + d) = hi;
+                    *reinterpret_cast<uint4*>(op + c * OW + d) = hi;
                     if (X3) {
                         uint4 lo;
                         lo.x = pack_bf16x2(f[0] - bf16lo(hi.x), f[1] - bf16hi(hi.x));
                         lo.y = pack_bf16x2(f[2] - bf16lo(hi.y), f[3] - bf16hi(hi.y));
                         lo.z = pack_bf16x2(f[4] - bf16lo(hi.z), f[5] - bf16hi(hi.z));
                         lo.w = pack_bf16x2(f[6] - bf16lo(hi.w), f[7] - bf16hi(hi.w));
-                        *reinterpret_cast<uint4*>(op + H + c * 32 + d) = lo;
+                        *reinterpret_cast<uint4*>(op + H + c * OW + d) = lo;
                     }
                 }
             }
