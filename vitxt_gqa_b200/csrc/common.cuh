@@ -362,6 +362,55 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
                  "h"(cta_mask)
                  : "memory");
 }
+// ---- cta_group::2: the two CTAs of a cluster pair run ONE tcgen05.mma (M = 256) issued by the leader (cluster rank 0).
+// Each CTA keeps its own 128 rows of A and its own half of the B tile in shared memory (same offsets in both CTAs: the
+// leader's descriptors are applied to both) and receives its 128 accumulator rows in its own tensor memory.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank) {      // shared::cta -> shared::cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on an mbarrier of the pair's leader
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* desc, uint32_t bar_cluster_addr, int c0,
+                                                int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(desc), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier at this offset in every CTA of cta_mask once the pair's MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives lane (base_lane + i)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(

@@ -68,6 +68,10 @@ struct GemmCfg {
     // BN == 64 launches that cannot fill the SMs left to them twice over (N = 768: 12 CTAs) give up the second resident
     // CTA for a pipeline that holds 12 k-blocks: a K = 768 product is then ONE round of loads and K = 3072 four, where
     // six stages took two and eight -- the decode chain is bound by exactly these round trips (profiles/r2_tail_kernels.md)
+    // PAIR == 2 (cta_group::2): a stage holds this CTA's A tile and HALF of the W tile -- 32 KB, six stages
+    static constexpr int STAGE2_BYTES = A_BYTES + B_BYTES / 2;
+    static constexpr int STAGES2 = 6;
+    static constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + STAGING_BYTES + 1024 + 256;
     static constexpr int DEEP_STAGES = 12;
     static constexpr int DEEP_SMEM_BYTES = DEEP_STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
 };
@@ -75,19 +79,25 @@ struct GemmCfg {
 // MODE >= 0: the epilogue flags (low 5 bits of ep.flags) and "has a residual operand" (bit 5) are compile-time
 // constants -- the hot epilogues of the fusion transformer get their own lean instantiation; MODE < 0: read at run time.
 constexpr int GEMM_MODE_RES = 32;
-// PAIR: the CTAs of a 2-CTA cluster work on vertically adjacent tiles (rows 2p and 2p + 1 of the same n block) in step.
+// PAIR == 1: the CTAs of a 2-CTA cluster work on vertically adjacent tiles (rows 2p and 2p + 1 of the same n block) in step.
 // Each loads its own A tile and HALF of the shared W tile, multicast into both CTAs' shared memory, so a k-block costs
 // each SM 32 KB of L2 reads instead of 48 KB; a stage is refilled only when BOTH tensor cores have released it (the
 // MMA commits are multicast to the `empty` barriers of both CTAs).
-template <int BN, int MODE, bool PAIR>
+// PAIR == 2: the same pair of tiles as ONE tcgen05.mma.cta_group::2 of M = 256 issued by the leader CTA.  Each CTA keeps
+// only its own half of the W tile in shared memory (the tensor cores exchange the halves), so a k-block costs each SM
+// 32 KB of shared-memory fill and 8 KB instead of 12 KB of operand reads per K = 16 step: the single-CTA form asks its
+// shared memory for 96 + 96 B per clock (TMA fill + operand reads), the pair form for 64 + 64 of the 128 there are.
+template <int BN, int MODE, int PAIR>
 __global__ void __launch_bounds__(GemmCfg<BN>::THREADS, GemmCfg<BN>::MIN_CTAS)     // 10 warps = 3 on two of the four 16 K-register partitions: 168 registers at most
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, GemmEpi ep, int M, int N, int K, int k_lo_off) {
     using Cfg = GemmCfg<BN>;
-    const int STAGES = BN == 64 ? ep.stages : Cfg::STAGES;      // run-time depth for the latency tile (see GemmCfg)
+    constexpr bool TWO = PAIR == 2;
+    constexpr int STAGE_BYTES = TWO ? Cfg::STAGE2_BYTES : Cfg::STAGE_BYTES;
+    const int STAGES = BN == 64 ? ep.stages : (TWO ? Cfg::STAGES2 : Cfg::STAGES);      // run-time depth for the latency tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;      // 1024-byte aligned (STAGE_BYTES is a multiple of 1024)
+    uint8_t* staging = smem + STAGES * STAGE_BYTES;           // 1024-byte aligned (STAGE_BYTES is a multiple of 1024)
     uint64_t* full = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
@@ -118,17 +128,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) {
                 mbar_init(&full[s], 1);
-                mbar_init(&empty[s], PAIR ? 2 : 1);
+                mbar_init(&empty[s], PAIR == 1 ? 2 : 1);
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&tfull[a], 1);
-                mbar_init(&tempty[a], Cfg::EPI_WARPS);
+                mbar_init(&tempty[a], TWO ? 2 * Cfg::EPI_WARPS : Cfg::EPI_WARPS);       // TWO: the leader's counts both CTAs' epilogues
             }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if (TWO) {
+            tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -149,25 +164,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 if (lane == 0) {
                     const int seg = kb / kseg, kk = (kb - seg * kseg) * GEMM_BK;
                     mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(sa, &tmA, &full[stage], kk + (seg == 2 ? k_lo_off : 0), m_blk * Cfg::BM);
-                    if (PAIR)       // this CTA's half of the W tile (tmB box = BN / 2 rows), to both CTAs
-                        tma_load_2d_multicast(sa + Cfg::A_BYTES + rank * (Cfg::B_BYTES / 2), &tmB, &full[stage],
-                                              kk + (seg == 1 ? k_lo_off : 0), n_blk * BN + rank * (BN / 2), 3);
-                    else
-                        tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kk + (seg == 1 ? k_lo_off : 0), n_blk * BN);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    if (TWO) {
+                        // both CTAs' bytes are counted on the LEADER's barrier; each CTA fills only its own shared memory
+                        const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+                        tma_load_2d_2sm(sa, &tmA, lead_full, kk + (seg == 2 ? k_lo_off : 0), m_blk * Cfg::BM);
+                        tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmB, lead_full, kk + (seg == 1 ? k_lo_off : 0),
+                                        n_blk * BN + rank * (BN / 2));
+                    } else {
+                        mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                        tma_load_2d(sa, &tmA, &full[stage], kk + (seg == 2 ? k_lo_off : 0), m_blk * Cfg::BM);
+                        if (PAIR)       // this CTA's half of the W tile (tmB box = BN / 2 rows), to both CTAs
+                            tma_load_2d_multicast(sa + Cfg::A_BYTES + rank * (Cfg::B_BYTES / 2), &tmB, &full[stage],
+                                                  kk + (seg == 1 ? k_lo_off : 0), n_blk * BN + rank * (BN / 2), 3);
+                        else
+                            tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kk + (seg == 1 ? k_lo_off : 0), n_blk * BN);
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+        // ------------------------------------------------ MMA issuer (TWO: the leader CTA issues for the pair)
+        constexpr uint32_t idesc = make_idesc_bf16(TWO ? 2 * GEMM_BM : GEMM_BM, BN);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
-        for (int tile = first_tile; tile < tiles; tile += tile_step) {
+        for (int tile = first_tile; tile < tiles && !(TWO && rank != 0); tile += tile_step) {
             mbar_wait(&tempty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
@@ -175,16 +199,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                     const uint64_t da = make_sw128_kmajor_desc(sa);
                     const uint64_t db = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) {
                         // +32 B per K=16 step inside the swizzle atom == +2 in the (addr >> 4) field
-                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (TWO) umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    if (PAIR) umma_commit_multicast(&empty[stage], 3); else umma_commit(&empty[stage]);
-                    if (kb == kblocks - 1) umma_commit(&tfull[acc]);
+                    if (TWO) umma_commit_2sm(&empty[stage], 3);
+                    else if (PAIR) umma_commit_multicast(&empty[stage], 3);
+                    else umma_commit(&empty[stage]);
+                    if (kb == kblocks - 1) {
+                        if (TWO) umma_commit_2sm(&tfull[acc], 3); else umma_commit(&tfull[acc]);
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -249,7 +278,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     if (ci + 1 == NCH) {             // the accumulator is in registers: hand it back to the MMA warp
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[acc]);
+                        if (lane == 0) {
+                            if (TWO) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0)); else mbar_arrive(&tempty[acc]);
+                        }
                     }
                     const int col0 = col_w + c0;
                     if (col0 >= N) continue;     // warp-uniform: the whole 32-column chunk is outside the matrix
@@ -400,7 +431,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (PAIR) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (TWO) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -519,7 +550,7 @@ int num_sms() {
     return n;
 }
 
-template <int BN, int MODE, bool PAIR>
+template <int BN, int MODE, int PAIR>
 static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmEpi& ep,
                             int M, int N, int K, int k_lo_off, int sm_cap, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
@@ -527,7 +558,7 @@ static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const 
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, MODE, PAIR>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             BN == 64 ? Cfg::DEEP_SMEM_BYTES : Cfg::SMEM_BYTES);
+                                             BN == 64 ? Cfg::DEEP_SMEM_BYTES : (PAIR == 2 ? Cfg::SMEM2_BYTES : Cfg::SMEM_BYTES));
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
             return (int)e;
@@ -543,7 +574,7 @@ static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const 
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * pairs);
         cfg.blockDim = dim3(Cfg::THREADS);
-        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.dynamicSmemBytes = PAIR == 2 ? Cfg::SMEM2_BYTES : Cfg::SMEM_BYTES;
         cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
@@ -580,7 +611,7 @@ static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const 
 // The epilogues of the eval forward (qkv / ptr-net plain, +residual, GELU, fp32 out, fp32 out + fp32 residual,
 // GELU + hi|lo out, hi|lo out) and the GELU' dgrad of the training step are compiled with constant flags for the
 // throughput tiles; everything else (BN = 64 decode tiles, rare combinations) takes the run-time-flag instantiation.
-template <int BN, bool PAIR>
+template <int BN, int PAIR>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmEpi& ep, int M,
                        int N, int K, int k_lo_off, int sm_cap, cudaStream_t st) {
     if (BN >= 128) {
@@ -844,12 +875,14 @@ static int gemm_entry(const char* who, bool x3, const void* A, long long lda, co
     int rc = make_tmap_bf16(&ta, A, M, kcols, lda, bn == 64 ? 64 : GEMM_BM);
     if (rc) return rc;
     // CTA pairs for the throughput tile (see the kernel); T2S_GEMM_PAIR=0 in the environment turns them off
+    // (default 2: one cta_group::2 MMA per pair; T2S_GEMM_PAIR=1: two MMAs over a multicast W tile; 0: single CTAs.
+    // Same box, eval step: 22.4-22.5 ms with 1, 21.6-21.8 ms with 2, results bit-identical)
     static int pair_env = -1;
     if (pair_env < 0) {
         const char* e = getenv("T2S_GEMM_PAIR");
-        pair_env = (e && e[0] == '0') ? 0 : 1;
+        pair_env = e ? (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)) : 2;
     }
-    const bool pair = pair_env && bn == 256 && M >= 2 * GEMM_BM;
+    const int pair = (bn == 256 && M >= 2 * GEMM_BM) ? pair_env : 0;
     rc = make_tmap_bf16(&tb, W, N, kcols, ldw, pair ? bn / 2 : bn);
     if (rc) return rc;
     // C is written by TMA stores of 32-row x 128-byte boxes (clipped to [M, N] / [M, 2N] by the map)
@@ -861,10 +894,11 @@ static int gemm_entry(const char* who, bool x3, const void* A, long long lda, co
     const int k_lo = x3 ? K : 0;
     const int cap = (flags >> T2S_GEMM_SM_CAP_SHIFT) & 0xff;
     switch (bn) {
-        case 256: return pair ? launch_gemm<256, true>(ta, tb, tc, ep, M, N, K, k_lo, cap, st)
-                              : launch_gemm<256, false>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
-        case 128: return launch_gemm<128, false>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
-        case 64: return launch_gemm<64, false>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
+        case 256: return pair == 2 ? launch_gemm<256, 2>(ta, tb, tc, ep, M, N, K, k_lo, cap, st)
+                       : pair == 1 ? launch_gemm<256, 1>(ta, tb, tc, ep, M, N, K, k_lo, cap, st)
+                                   : launch_gemm<256, 0>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
+        case 128: return launch_gemm<128, 0>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
+        case 64: return launch_gemm<64, 0>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
         default: set_error("%s: block_n must be 0, 64, 128 or 256", who); return T2S_ERR_ARG;
     }
 }
