@@ -33,6 +33,12 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;          // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 320;    // 10 warps
 constexpr int GEMM_EPI_WARPS = 8;
+// 1: two staging boxes per epilogue warp in the cta_group::2 form (and five stages instead of six).  Measured on one box,
+// default build vs -DT2S_GEMM_DB_STAGING=1: every fusion shape 0-4 % slower, the epilogue-heavy ones (attn_out + residual,
+// ffn_up + GELU) unchanged -- their epilogues do not wait for the store to read its box.  Off.
+#ifndef T2S_GEMM_DB_STAGING
+#define T2S_GEMM_DB_STAGING 0
+#endif
 
 struct GemmEpi {
     void* C;
@@ -70,8 +76,11 @@ struct GemmCfg {
     // six stages took two and eight -- the decode chain is bound by exactly these round trips (profiles/r2_tail_kernels.md)
     // PAIR == 2 (cta_group::2): a stage holds this CTA's A tile and HALF of the W tile -- 32 KB, six stages
     static constexpr int STAGE2_BYTES = A_BYTES + B_BYTES / 2;
-    static constexpr int STAGES2 = 6;
-    static constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + STAGING_BYTES + 1024 + 256;
+    // ... or five with TWO staging boxes per epilogue warp (T2S_GEMM_DB_STAGING): the epilogue then writes box i + 1 while
+    // the TMA store of box i still reads its shared memory, instead of waiting for it
+    static constexpr int STAGES2 = T2S_GEMM_DB_STAGING ? 5 : 6;
+    static constexpr int STAGING2_BYTES = (T2S_GEMM_DB_STAGING ? 2 : 1) * STAGING_BYTES;
+    static constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + STAGING2_BYTES + 1024 + 256;
     static constexpr int DEEP_STAGES = 12;
     static constexpr int DEEP_SMEM_BYTES = DEEP_STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
 };
@@ -98,7 +107,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* staging = smem + STAGES * STAGE_BYTES;           // 1024-byte aligned (STAGE_BYTES is a multiple of 1024)
-    uint64_t* full = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(staging + (TWO ? Cfg::STAGING2_BYTES : Cfg::STAGING_BYTES));
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
@@ -236,8 +245,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const bool res_f32 = fl & T2S_GEMM_RES_F32;
         const bool out_split = fl & T2S_GEMM_OUT_SPLIT;
         const bool dgelu = fl & T2S_GEMM_DGELU;
-        uint8_t* box = staging + (BN == 64 ? quarter & 1 : ew) * 4096;      // this warp's staging box: 32 rows x 128 B, 128B swizzle
+        // this warp's staging box: 32 rows x 128 B, 128B swizzle.  DB: two boxes used in turn -- the wait before a box is
+        // rewritten then covers the store issued two stores ago
+        constexpr bool DB = TWO && T2S_GEMM_DB_STAGING;
+        uint8_t* const box0 = staging + (BN == 64 ? quarter & 1 : (DB ? 2 * ew : ew)) * 4096;
+        uint8_t* box = box0;
         uint8_t* my_row = box + lane * 128;
+        auto next_box = [&]() {                  // after every committed store (warp-uniform)
+            if (DB) {
+                box = box == box0 ? box0 + 4096 : box0;
+                my_row = box + lane * 128;
+            }
+        };
+        auto box_wait = [&]() {                  // the store that last used `box` has read it
+            if (lane == 0) { if (DB) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+            __syncwarp();
+        };
         const int sw = lane & 7;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -348,8 +371,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     }
                     if (out_f32) {
                         // one box = 32 rows x 32 fp32 columns; the previous store must have read the box
-                        if (lane == 0) tma_store_wait_read<0>();
-                        __syncwarp();
+                        box_wait();
 #pragma unroll
                         for (int c = 0; c < 8; ++c)
                             *reinterpret_cast<float4*>(my_row + ((c ^ sw) << 4)) =
@@ -360,16 +382,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             tma_store_2d(&tmC, box, col0, row0);
                             tma_store_commit();
                         }
+                        next_box();
                     } else {
                         // one box = 32 rows x 64 bf16 columns = two 32-column chunks
                         const int hpos = (c0 >> 5) & 1;          // which half of the box this chunk fills
                         uint32_t hi[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-                        if (hpos == 0) {
-                            if (lane == 0) tma_store_wait_read<0>();
-                            __syncwarp();
-                        }
+                        if (hpos == 0) box_wait();
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             *reinterpret_cast<uint4*>(my_row + (((hpos * 4 + c) ^ sw) << 4)) =
@@ -382,6 +402,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                 tma_store_2d(&tmC, box, col0 - hpos * 32, row0);
                                 tma_store_commit();
                             }
+                            next_box();
                         }
                         if (out_split) {
                             // lo = bf16(v - hi), stored ep.c_lo_off columns to the right; 32-column boxes reuse the
@@ -394,8 +415,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) lo_keep[j] = lo[j];
                             } else {
-                                if (lane == 0) tma_store_wait_read<0>();
-                                __syncwarp();
+                                box_wait();
 #pragma unroll
                                 for (int c = 0; c < 4; ++c) {
                                     *reinterpret_cast<uint4*>(my_row + ((c ^ sw) << 4)) =
@@ -409,6 +429,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                     tma_store_2d(&tmC, box, ep.c_lo_off + col0 - 32, row0);
                                     tma_store_commit();
                                 }
+                                next_box();
                             }
                         }
                     }
