@@ -3,7 +3,8 @@
 # captures of (a) the throughput GEMM instantiations, (b) the tcgen05 attention, (c) the full-size memory-bound kernels.
 # Everything lands in gpurun_out/ (scratch); the summaries made from it are committed under profiles/.
 #   gpurun --timeout 1700 -- 'bash tools/gpu_round2.sh [tag]'      (SKIP_TESTS=1 / SKIP_NCU=1 to skip parts;
-#   ONLY_ATTN=1: of the `--set full` captures only the attention one -- what was re-taken after the P-in-TMEM rewrite)
+#   ONLY_ATTN=1: of the `--set full` captures only the attention one; SKIP_MEM=1: GEMM and attention captures only -- what was
+#   re-taken after the cta_group::2 GEMM and the P-in-TMEM attention went in)
 TAG=${1:-x}
 OUT=gpurun_out
 mkdir -p $OUT
@@ -25,7 +26,7 @@ if [ -z "$SKIP_NCU" ]; then
   fi
   timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:attn_tc -c 8 \
       -f -o $OUT/${TAG}_attn_full $W > $OUT/${TAG}_attn_full.log 2>&1
-  if [ -z "$ONLY_ATTN" ]; then
+  if [ -z "$ONLY_ATTN$SKIP_MEM" ]; then
   timeout 900 ncu --profile-from-start off --set full --clock-control none --kernel-name-base demangled \
       -k 'regex:add_ln_kernel|feat_concat_kernel|ocr_finish_kernel|phoc_build_kernel|split_bf16_kernel|sim_scores_kernel' -c 60 \
       -f -o $OUT/${TAG}_mem_full $W > $OUT/${TAG}_mem_full.log 2>&1
