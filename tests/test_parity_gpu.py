@@ -353,7 +353,7 @@ def test_t2s_submit_pipelined_is_bit_identical_to_the_plain_call():
 
 def test_t2s_headline_configuration_batch64():
     """BASELINE configs[1] as benchmarked: t2s_abinet, batch 64, every throughput GEMM on the <256, *, PAIR> tile with
-    the 124-SM cap, the greedy decode on the side stream and replayed as a CUDA graph (third forward on).
+    the 100-SM cap, the greedy decode on the side stream and replayed as a CUDA graph (third forward on).
     (1) the two samples of the real-reference fixture `t2s_abinet_eval`, embedded at rows 5 and 40 of the 64, match
         that fixture (grounding exact, logits within the stated tolerance, answer indices margin-aware);
     (2) three samples give bit-identical results alone (batch 1) and inside the 64;

@@ -222,7 +222,12 @@ class _FusionModelBase(BaseModel):
         # eval only: run the latency-bound greedy decode of the `pos` variant on a second (high-priority) stream
         # while the throughput-bound encoder passes of `ref` / `neg` run on the caller's stream with their
         # persistent GEMM grids capped at (SMs - overlap_sms) CTAs.  0 disables the overlap.
-        self.overlap_sms = int(os.environ.get("T2S_B200_OVERLAP_SMS", str(self.config.get("b200_overlap_sms", 24))))
+        # Measured with the pair-form GEMMs (tools/overlap_sweep.sh, one box): 24 -> 21.8 ms per step, 48 -> 21.5, 64 -> 22.4;
+        # the pipelined serving path (submit), whose side stream also competes with the NEXT batch's front, prefers 24
+        # (3.0 k against 2.8 k samples/s), hence its own knob.
+        self.overlap_sms = int(os.environ.get("T2S_B200_OVERLAP_SMS", str(self.config.get("b200_overlap_sms", 48))))
+        self.submit_overlap_sms = int(os.environ.get("T2S_B200_SUBMIT_OVERLAP_SMS",
+                                                     str(self.config.get("b200_submit_overlap_sms", 24))))
         self._side_streams = {}
         # pipelined eval (submit / PendingForward.result): two workspace sets used alternately; the event that ends
         # the decode tail of the forward that last used a set gates its reuse
@@ -961,7 +966,7 @@ class T2S(_FusionModelBase):
             slot, self._pipe_slot = self._pipe_slot, self._pipe_slot ^ 1
             if self._slot_done[slot] is not None:       # the forward that used this set two submits ago
                 torch.cuda.current_stream(dev).wait_event(self._slot_done[slot])
-            L.gemm_cap = max(1, n_sms - self.overlap_sms)
+            L.gemm_cap = max(1, n_sms - self.submit_overlap_sms)
         else:
             for i_, ev_ in enumerate(self._slot_done):     # a plain call after submits: their tails still own set 0 / 1
                 if ev_ is not None:
