@@ -44,7 +44,8 @@ long long t2s_tmap_cache_stats(int which);
  * Replaces nn.Linear/addmm of BertSelfAttention.query/key/value, BertSelfOutput.dense,
  * BertIntermediate.dense(+gelu), BertOutput.dense (via models/t2s.py:622), ClassifierLayer
  * (modules/layers.py:101-107), OcrPtrNet.query/key (models/t2s.py:653,659).
- * block_n: 0 = auto, or 64 / 128 / 256.  lda, ldw multiples of 8; bases 16-byte aligned. */
+ * block_n: 0 = auto, or 64 / 128 / 256.  lda, ldw multiples of 8; bases 16-byte aligned.
+ * block_n 256 with M >= 256 launches 2-CTA clusters (one tcgen05.mma.cta_group::2 of M = 256 per pair). */
 int t2s_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const float* bias,
                   const void* residual, long long ldr, void* C, long long ldc, int M, int N, int K,
                   int flags, int block_n, void* stream);
