@@ -321,6 +321,23 @@ int t2s_phoc_build(const unsigned char* bytes, const int* offsets, int n_tokens,
  * the alphabet) -- the batched `ocr_token_bytes` [B, O, width] field of a SampleList, so that the forward takes the OCR
  * token TEXT instead of the 604 fp32 of `context_feature_1` per token (vtextgqa/dataset.py:237, processors.py:904-928) */
 int t2s_phoc_build_fixed(const unsigned char* bytes, int width, int n_tokens, float* out, long long ldo, void* stream);
+/* Frame sampling + per-frame OCR truncate / pad / pack, the python list work of the dataset in front of the featurisers:
+ * replaces vtextgqa/dataset.py:103-158 (uniform frame ids via sample_frames :371-381, per frame the first Of detections,
+ * box = min / max of the quadrilateral, "<pad>" slots that keep the frame index), :166-195 (middel_frame_id / _idx),
+ * :199-243 (zero-padded id / mask vectors, float64 box normalisation by 1/width, 1/height + CopyProcessor
+ * processors.py:932-944).  Detections of all videos of the batch back to back in OCR-info frame order: det_points
+ * [n, 8] fp32, det_track [n], det_tokens [n, width] zero-padded UTF-8 records (already through the token processor);
+ * frame_ptr = CSR index of the info frames of all videos, info_base[b] = first info frame of video b, n_info[b] =
+ * len(ocr_info), n_frames[b] = number of video frames (needs n_frames - 1 <= n_info), vid_w / vid_h as binary64.
+ * Outputs as the Sample fields of the reference: ocr_bbox [B, F*Of, 4] fp32, track_id / temporal_id / ocr_mask
+ * [B, F*Of] int64, frame_id / frame_mask [B, F] int64, frame_num / mid_frame_id / mid_frame_idx [B] int64, and
+ * ocr_token_bytes [B, F*Of, width] (the input of t2s_phoc_build_fixed; empty records on missing frames). */
+int t2s_pack_ocr_frames(const float* det_points, const long long* det_track, const unsigned char* det_tokens, int width,
+                        const int* frame_ptr, const int* info_base, const int* n_info, const int* n_frames,
+                        const double* vid_w, const double* vid_h, int B, int F, int Of, float* ocr_bbox,
+                        long long* track_id, long long* temporal_id, long long* ocr_mask, long long* frame_id,
+                        long long* frame_mask, long long* frame_num, long long* mid_frame_id, long long* mid_frame_idx,
+                        unsigned char* ocr_token_bytes, void* stream);
 
 /* K9  Evaluation step that consumes the forward's outputs.
  * t2s_answer_decode: `pos_scores.argmax(-1)` and the EOS cut of the python loop in modules/metrics.py:186-207 (= 395-416,

@@ -141,3 +141,77 @@ def test_forward_takes_ocr_token_text_instead_of_phoc_rows():
     assert torch.equal(rows.cpu(), featurize.phoc_rows(["Hello", "<pad>", "naïve-42"]).cpu())
     with pytest.raises(ValueError):
         featurize.pack_tokens_fixed(["x" * 65])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# frame sampling + per-frame OCR truncate / pad / pack (vtextgqa/dataset.py:103-253): goldens produced by the
+# reference's own source text (tests/golden/make_pack_golden.py)
+# ------------------------------------------------------------------------------------------------------------------
+PACK_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ocr_pack_golden.npz")
+PACK_FIELDS = ("ocr_bbox_coordinates", "track_id", "temporal_id", "ocr_mask", "frame_id", "frame_mask", "frame_num",
+               "middel_frame_id", "middel_frame_idx")
+
+
+def _pack_cases():
+    z = np.load(PACK_GOLDEN)
+    for ci in range(int(z["n_cases"])):
+        p = "c%d_" % ci
+        n_frames, n_info, F, Of = [int(v) for v in z[p + "geom"]]
+        yield ci, {k[len(p):]: z[k] for k in z.files if k.startswith(p)}, n_frames, n_info, F, Of
+
+
+def test_pack_oracle_matches_the_reference_method_bit_exact():
+    from oracle import pack_oracle
+    for ci, g, n_frames, n_info, F, Of in _pack_cases():
+        r = pack_oracle.pack_ocr_frames(g["det_points"], g["det_track"], g["det_tokens"], g["frame_ptr"], n_info, n_frames,
+                                        float(g["size"][0]), float(g["size"][1]), F, Of)
+        for k in PACK_FIELDS:
+            assert np.array_equal(np.asarray(r[k]), g[k]), (ci, k)
+        assert r["ocr_bbox_coordinates"].dtype == g["ocr_bbox_coordinates"].dtype == np.float32
+        nt = g["ocr_tokens"].shape[0]                      # len(sampled frames) * Of entries, then the processors' padding
+        assert np.array_equal(r["ocr_token_bytes"][:nt], g["ocr_tokens"]) and not r["ocr_token_bytes"][nt:].any(), ci
+        assert featurize.sample_frames(n_frames, F) == [int(v) for v in g["frame_id"] if v > 0] == \
+            pack_oracle.sample_frames(n_frames, F)
+
+
+def test_ocr_info_to_csr_round_trip():
+    info = {"1": [{"points": [1, 2, 30, 2, 30, 20, 1, 20], "ocr": "Exit", "ID": 7}], "2": [],
+            "3": [{"points": [5.5, 6, 9, 6, 9, 8, 5, 8.25], "ocr": "a", "ID": 1},
+                  {"points": [0, 0, 1, 0, 1, 1, 0, 1], "ocr": "b", "ID": 2}]}
+    c = featurize.ocr_info_to_csr(info, token_processor=str.lower, width=16)
+    assert c["frame_ptr"].tolist() == [0, 1, 1, 3] and c["det_track"].tolist() == [7, 1, 2]
+    assert c["det_points"].shape == (3, 8) and c["det_points"].dtype == np.float32
+    assert bytes(c["det_tokens"][0]).rstrip(b"\0") == b"exit" and c["det_tokens"].shape == (3, 16)
+    if not torch.cuda.is_available():          # no CPU fallback: the call refuses without a device
+        with pytest.raises(tlib.T2SLibraryError):
+            featurize.pack_ocr_frames([dict(c, n_frames=3, width=10, height=10)], 4, 2)
+
+
+@pytest.mark.gpu
+def test_pack_kernel_matches_the_reference_method_bit_exact():
+    """Videos of one geometry go through ONE launch as a batch; every field equals what the reference's
+    add_sample_details produced for that video, and the token records feed the PHOC kernel."""
+    groups = {}
+    for ci, g, n_frames, n_info, F, Of in _pack_cases():
+        groups.setdefault((F, Of), []).append((ci, g, n_frames))
+    assert len(groups) == 2
+    for (F, Of), cases in groups.items():
+        videos = [{"det_points": g["det_points"], "det_track": g["det_track"], "det_tokens": g["det_tokens"],
+                   "frame_ptr": g["frame_ptr"], "n_frames": n_frames, "width": float(g["size"][0]),
+                   "height": float(g["size"][1])} for _, g, n_frames in cases]
+        out = featurize.pack_ocr_frames(videos, F, Of)
+        torch.cuda.synchronize()
+        for b, (ci, g, _) in enumerate(cases):
+            for k in PACK_FIELDS:
+                got = out[k][b].cpu().numpy()
+                assert np.array_equal(got.reshape(g[k].shape), g[k]), (ci, k)
+            tok = out["ocr_token_bytes"][b].cpu().numpy()
+            nt = g["ocr_tokens"].shape[0]
+            assert np.array_equal(tok[:nt], g["ocr_tokens"]) and not tok[nt:].any(), ci
+        # the records are what t2s_phoc_build_fixed takes: "<pad>" slots get the descriptor of the word "pad", missing frames zero rows
+        rows = featurize.phoc_from_records(out["ocr_token_bytes"]).cpu().numpy().reshape(len(cases), F * Of, -1)
+        for b, (ci, g, _) in enumerate(cases):
+            words = [bytes(r).rstrip(b"\0").decode("utf-8") for r in out["ocr_token_bytes"][b].cpu().numpy()]
+            want = np.stack([phoc_oracle.build_phoc(w) for w in words])
+            assert np.array_equal(rows[b], want), ci
+            assert rows[b][g["ocr_tokens"].shape[0]:].sum() == 0

@@ -84,6 +84,38 @@ def main():
         "cpu_baseline": {"value": n_cpu / cpu_s, "unit": "tokens/s", "cores": 1, "kind": kind,
                          "sample": "%d tokens, %.2f s" % (n_cpu, cpu_s)}}))
 
+    # ---- frame sampling + OCR truncate / pad / pack: B videos of 130 frames, up to 20 detections per frame -> 64 x 15 slots
+    import random
+    import numpy as np
+    rng = random.Random(5)
+    F, Of, n_frames = 64, 15, 130
+    short = [t for t in flat[:2048] if len(t.encode()) <= 64]
+    videos = []
+    for b in range(B):
+        info = {}
+        for f in range(1, n_frames + 1):
+            dets = []
+            for _ in range(rng.randint(0, 20)):
+                x, y, w, h = rng.uniform(0, 1200), rng.uniform(0, 700), rng.uniform(5, 200), rng.uniform(5, 80)
+                dets.append({"points": [x, y, x + w, y, x + w, y + h, x, y + h], "ocr": rng.choice(short), "ID": rng.randint(1, 400)})
+            info[str(f)] = dets
+        videos.append(dict(featurize.ocr_info_to_csr(info), n_frames=n_frames, width=1280, height=720))
+    ms_pack_api = dev_ms(lambda: featurize.pack_ocr_frames(videos, F, Of), iters=10)      # concat + H2D + launch
+    packed = featurize.pack_ocr_frames(videos, F, Of)
+    from oracle import pack_oracle
+    t0 = time.perf_counter()
+    n_cpu_v = 8
+    for v in videos[:n_cpu_v]:
+        pack_oracle.pack_ocr_frames(v["det_points"], v["det_track"], v["det_tokens"], v["frame_ptr"], n_frames, n_frames,
+                                    1280.0, 720.0, F, Of)
+    cpu_pack = (time.perf_counter() - t0) / n_cpu_v
+    bytes_pack = sum(t.numel() * t.element_size() for t in packed.values())
+    print(json.dumps({
+        "component": "frame sampling + OCR pad / pack (t2s_pack_ocr_frames)", "videos": B, "slots": F * Of,
+        "api_ms_incl_concat_and_h2d": ms_pack_api, "output_bytes": bytes_pack,
+        "cpu_baseline": {"value": cpu_pack * 1e3, "unit": "ms per video", "cores": 1, "kind": "port",
+                         "sample": "%d videos through oracle/pack_oracle.py (the reference's python list loop restated)" % n_cpu_v}}))
+
     # ---- evaluation step: all six metrics of one batch
     case = synth.make_metrics_case(B=B, T=T, V=V, O=O, frame_topk=5, ocr_topk=5, n_boxes=320, seed=7)
     registry.register("vtextgqa_answer_processor", synth.SynthAnswerProcessor(case["vocab"]))

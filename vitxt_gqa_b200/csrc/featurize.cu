@@ -124,7 +124,113 @@ static int upload_bigram_table() {
     return (int)cudaMemcpyToSymbol(c_bigram, tab, sizeof(tab));
 }
 
+// ------------------------------------------------------------------------------- frame sampling + OCR pad / pack
+// One CTA per (sampled frame slot i, sample b).  Replaces the python list work of the dataset
+// (vtextgqa/dataset.py:103-158 frame ids + per-frame truncate / pad, :166-195 the middle-frame ids, :199-243 the padded
+// id / mask vectors and the float64 box normalisation; sample_frames :371-381).  Detections of a video lie back to back
+// in OCR-info frame order; frame_ptr is their CSR index over ALL videos of the batch.
+struct PackOut {
+    float* bbox;                 // [B, F * Of, 4]
+    long long* track;            // [B, F * Of]
+    long long* temporal;         // [B, F * Of]
+    long long* ocr_mask;         // [B, F * Of]
+    long long* frame_id;         // [B, F]
+    long long* frame_mask;       // [B, F]
+    long long* frame_num;        // [B]
+    long long* mid_id;           // [B]
+    long long* mid_idx;          // [B]
+    unsigned char* tokens;       // [B, F * Of, width]
+};
+
+__global__ void __launch_bounds__(128)
+pack_ocr_frames_kernel(const float* __restrict__ det_points, const long long* __restrict__ det_track,
+                       const unsigned char* __restrict__ det_tokens, int width, const int* __restrict__ frame_ptr,
+                       const int* __restrict__ info_base, const int* __restrict__ n_info,
+                       const int* __restrict__ n_frames, const double* __restrict__ vid_w,
+                       const double* __restrict__ vid_h, int F, int Of, PackOut out) {
+    const int i = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int n = n_frames[b];
+    const int count = n < F ? n : F;                                   // len(idxs)
+    const int step = n / F;                                            // sample_frames: frames[i * step] when n > F
+    const long long slot0 = ((long long)b * F + i) * Of;
+    if (tid == 0) {
+        const int fid = i < count ? (n <= F ? i + 1 : 1 + i * step) : 0;
+        out.frame_id[(long long)b * F + i] = fid;
+        out.frame_mask[(long long)b * F + i] = i < count ? 1 : 0;
+        if (i == 0) {
+            const int last = n <= F ? count : 1 + (count - 1) * step;  // the LAST sampled frame (dataset.py:180)
+            out.frame_num[b] = count;
+            out.mid_id[b] = last;
+            out.mid_idx[b] = last >= F ? count / 2 + 1 : last;
+        }
+    }
+    if (i >= count) {        // frame slots past the video: zero ids, zero boxes, empty token records
+        for (int o = tid; o < Of; o += blockDim.x) {
+            out.track[slot0 + o] = 0;
+            out.temporal[slot0 + o] = 0;
+            out.ocr_mask[slot0 + o] = 0;
+            *reinterpret_cast<float4*>(out.bbox + (slot0 + o) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int e = tid; e < Of * width; e += blockDim.x) out.tokens[slot0 * width + e] = 0;
+        return;
+    }
+    const int frame_idx = n <= F ? i + 1 : 1 + i * step;
+    const int j = n_info[b] >= frame_idx ? frame_idx : frame_idx - 1;  // dataset.py:121-124
+    const int row = info_base[b] + j - 1;
+    const int lo = frame_ptr[row];
+    const int k = min(frame_ptr[row + 1] - lo, Of);
+    const double sx = 1.0 / vid_w[b], sy = 1.0 / vid_h[b];            // python floats: the product is binary64
+    for (int o = tid; o < Of; o += blockDim.x) {
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        long long trk = 0;
+        if (o < k) {
+            const float* p = det_points + (long long)(lo + o) * 8;
+            const float x1 = fminf(p[0], p[6]), y1 = fminf(p[1], p[3]), x2 = fmaxf(p[2], p[4]), y2 = fmaxf(p[5], p[7]);
+            box = make_float4(__double2float_rn(__dmul_rn((double)x1, sx)), __double2float_rn(__dmul_rn((double)y1, sy)),
+                              __double2float_rn(__dmul_rn((double)x2, sx)), __double2float_rn(__dmul_rn((double)y2, sy)));
+            trk = det_track[lo + o];
+        }
+        *reinterpret_cast<float4*>(out.bbox + (slot0 + o) * 4) = box;
+        out.track[slot0 + o] = trk;
+        out.temporal[slot0 + o] = frame_idx;                           // padded slots keep the frame index
+        out.ocr_mask[slot0 + o] = o < k ? 1 : 0;
+    }
+    for (int e = tid; e < Of * width; e += blockDim.x) {
+        const int o = e / width, c = e - o * width;
+        unsigned char v;
+        if (o < k) v = det_tokens[(long long)(lo + o) * width + c];
+        else v = c < 5 ? (unsigned char)"<pad>"[c] : 0;                // the dataset's literal pad token (dataset.py:140)
+        out.tokens[slot0 * width + e] = v;
+    }
+}
+
 }  // namespace t2s
+
+extern "C" int t2s_pack_ocr_frames(const float* det_points, const long long* det_track, const unsigned char* det_tokens,
+                                   int width, const int* frame_ptr, const int* info_base, const int* n_info,
+                                   const int* n_frames, const double* vid_w, const double* vid_h, int B, int F, int Of,
+                                   float* ocr_bbox, long long* track_id, long long* temporal_id, long long* ocr_mask,
+                                   long long* frame_id, long long* frame_mask, long long* frame_num,
+                                   long long* mid_frame_id, long long* mid_frame_idx, unsigned char* ocr_token_bytes,
+                                   void* stream) {
+    using namespace t2s;
+    if (B <= 0 || F <= 0 || Of <= 0 || width < 5 || B > 65535) {
+        set_error("t2s_pack_ocr_frames: bad shape (B %d, F %d, Of %d, width %d >= 5)", B, F, Of, width);
+        return T2S_ERR_SHAPE;
+    }
+    if (!frame_ptr || !info_base || !n_info || !n_frames || !vid_w || !vid_h || !ocr_bbox || !track_id || !temporal_id ||
+        !ocr_mask || !frame_id || !frame_mask || !frame_num || !mid_frame_id || !mid_frame_idx || !ocr_token_bytes) {
+        set_error("t2s_pack_ocr_frames: null pointer");
+        return T2S_ERR_ARG;
+    }
+    if (reinterpret_cast<uintptr_t>(ocr_bbox) & 15) { set_error("t2s_pack_ocr_frames: ocr_bbox needs 16-byte alignment"); return T2S_ERR_ALIGN; }
+    PackOut out{ocr_bbox, track_id, temporal_id, ocr_mask, frame_id, frame_mask, frame_num, mid_frame_id, mid_frame_idx,
+                ocr_token_bytes};
+    pack_ocr_frames_kernel<<<dim3(F, B), 128, 0, (cudaStream_t)stream>>>(det_points, det_track, det_tokens, width,
+                                                                        frame_ptr, info_base, n_info, n_frames, vid_w,
+                                                                        vid_h, F, Of, out);
+    return launch_status("t2s_pack_ocr_frames");
+}
 
 static int phoc_entry(const unsigned char* bytes, const int* offsets, int width, int n_tokens, int rows, float* out,
                       long long ldo, void* stream) {

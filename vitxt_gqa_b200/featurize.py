@@ -104,6 +104,87 @@ def phoc_batch(token_lists, max_length, device=None):
     return phoc_rows(flat, device=device).view(B, max_length, PHOC_DIM)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Frame sampling + per-frame OCR truncate / pad / pack (reference vtextgqa/dataset.py:103-253, sample_frames :371-381)
+# ---------------------------------------------------------------------------------------------------------------
+def sample_frames(n_frames, num_frames):
+    """1-based ids of the uniformly sampled frames of a video of n_frames frames (dataset.py:103-109, 371-381): all of them
+    when there are at most num_frames, else every (n_frames // num_frames)-th starting with the first.  (The kernel
+    applies the same law on the device; this is the host-side mirror for code that needs the ids, e.g. to read the
+    per-frame ViT features.)"""
+    if n_frames <= num_frames:
+        return list(range(1, n_frames + 1))
+    step = n_frames // num_frames
+    return [1 + i * step for i in range(num_frames)]
+
+
+def ocr_info_to_csr(ocr_info, token_processor=None, width=OCR_TOKEN_WIDTH):
+    """One video's OCR info ({str(frame index from 1): [{"points": 8 numbers, "ocr": str, "ID": int}, ...]}, the .npy the
+    reference loads at dataset.py:96-97) -> the flat arrays `pack_ocr_frames` takes: det_points fp32 [n, 8], det_track
+    int64 [n], det_tokens uint8 [n, width], frame_ptr int32 [len(ocr_info) + 1].  A per-video, per-dataset constant:
+    build it once (offline, or on first touch) and keep it next to the video.  `token_processor` = the dataset's
+    `ocr_token_processor` (str -> str), applied before the bytes are packed."""
+    n_info = len(ocr_info)
+    pts, trk, toks, ptr = [], [], [], [0]
+    for f in range(1, n_info + 1):
+        for d in ocr_info[str(f)]:
+            pts.append(d["points"])
+            trk.append(d["ID"])
+            toks.append(token_processor(d["ocr"]) if token_processor else d["ocr"])
+        ptr.append(len(pts))
+    return {"det_points": np.asarray(pts, np.float32).reshape(-1, 8), "det_track": np.asarray(trk, np.int64),
+            "det_tokens": pack_tokens_fixed(toks, width).numpy().reshape(-1, width),
+            "frame_ptr": np.asarray(ptr, np.int32)}
+
+
+def pack_ocr_frames(videos, num_frames, frame_ocr_num, device=None):
+    """Batch of videos -> the OCR-side Sample fields of the reference, built on the device in one launch.
+
+    videos: list (B) of dicts with the arrays of `ocr_info_to_csr` plus "n_frames" (number of video frames) and "width",
+    "height" (pixels, python numbers).  Returns CUDA tensors named like the reference's fields: ocr_bbox_coordinates
+    [B, O, 4] fp32, track_id / temporal_id / ocr_mask [B, O] int64, frame_id / frame_mask [B, F] int64, frame_num /
+    middel_frame_id / middel_frame_idx [B] int64, and ocr_token_bytes [B, O, width] uint8 (which `T2S.forward` takes
+    instead of `context_feature_1`), O = num_frames * frame_ocr_num.  No CPU fallback."""
+    if not torch.cuda.is_available():
+        raise _lib.T2SLibraryError("pack_ocr_frames needs a CUDA device (no CPU fallback)")
+    device = torch.device("cuda" if device is None else device)
+    if device.type != "cuda":
+        raise _lib.T2SLibraryError("pack_ocr_frames runs on a CUDA device only (no CPU fallback); got %s" % device)
+    B, F, Of = len(videos), int(num_frames), int(frame_ocr_num)
+    width = videos[0]["det_tokens"].shape[1]
+    n_info = np.asarray([len(v["frame_ptr"]) - 1 for v in videos], np.int32)
+    n_frames = np.asarray([v["n_frames"] for v in videos], np.int32)
+    if (n_frames - 1 > n_info).any() or (n_frames < 1).any():
+        raise ValueError("every video needs 1 <= n_frames <= len(ocr_info) + 1 (the reference reads frame n or n - 1)")
+    det_base = np.concatenate([[0], np.cumsum([len(v["det_track"]) for v in videos])]).astype(np.int64)
+    info_base = np.concatenate([[0], np.cumsum(n_info + 1)[:-1]]).astype(np.int32)       # each video keeps its own ptr[0]
+    frame_ptr = np.concatenate([v["frame_ptr"].astype(np.int64) + det_base[i] for i, v in enumerate(videos)]).astype(np.int32)
+    cat = lambda k, shape, dt: (np.concatenate([v[k] for v in videos]) if det_base[-1] else np.zeros(shape, dt))
+    host = {"det_points": cat("det_points", (0, 8), np.float32), "det_track": cat("det_track", (0,), np.int64),
+            "det_tokens": cat("det_tokens", (0, width), np.uint8), "frame_ptr": frame_ptr, "info_base": info_base,
+            "n_info": n_info, "n_frames": n_frames,
+            "vid_w": np.asarray([float(v["width"]) for v in videos], np.float64),
+            "vid_h": np.asarray([float(v["height"]) for v in videos], np.float64)}
+    O = F * Of
+    with torch.cuda.device(device):
+        d = {k: torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True) for k, a in host.items()}
+        i64 = lambda *s: torch.empty(*s, dtype=torch.int64, device=device)
+        out = {"ocr_bbox_coordinates": torch.empty(B, O, 4, dtype=torch.float32, device=device),
+               "track_id": i64(B, O), "temporal_id": i64(B, O), "ocr_mask": i64(B, O), "frame_id": i64(B, F),
+               "frame_mask": i64(B, F), "frame_num": i64(B), "middel_frame_id": i64(B), "middel_frame_idx": i64(B),
+               "ocr_token_bytes": torch.empty(B, O, width, dtype=torch.uint8, device=device)}
+        ptr = lambda t: t.data_ptr() if t.numel() else None
+        _lib.get_lib().pack_ocr_frames(
+            ptr(d["det_points"]), ptr(d["det_track"]), ptr(d["det_tokens"]), width, d["frame_ptr"].data_ptr(),
+            d["info_base"].data_ptr(), d["n_info"].data_ptr(), d["n_frames"].data_ptr(), d["vid_w"].data_ptr(),
+            d["vid_h"].data_ptr(), B, F, Of, out["ocr_bbox_coordinates"].data_ptr(), out["track_id"].data_ptr(),
+            out["temporal_id"].data_ptr(), out["ocr_mask"].data_ptr(), out["frame_id"].data_ptr(),
+            out["frame_mask"].data_ptr(), out["frame_num"].data_ptr(), out["middel_frame_id"].data_ptr(),
+            out["middel_frame_idx"].data_ptr(), out["ocr_token_bytes"].data_ptr(),
+            torch.cuda.current_stream().cuda_stream)
+    return out
+
+
 class PhocProcessor:
     """Drop-in for the reference's `@registry.register_processor("phoc")` (processors.py:904-928 on top of
     VocabProcessor.__call__, processors.py:237-284): `proc({"tokens": [...]})` ->

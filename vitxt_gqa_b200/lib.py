@@ -76,6 +76,7 @@ SIGNATURES = {
     # input featurisation
     "t2s_phoc_build": [_p, _p, _i, _i, _p, _ll, _p],
     "t2s_phoc_build_fixed": [_p, _i, _i, _p, _ll, _p],
+    "t2s_pack_ocr_frames": [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     # evaluation step
     "t2s_answer_decode": [_p, _ll, _i, _i, _i, _i, _i, _p, _p, _p],
     "t2s_ground_metrics": [_p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _d, _d, _p, _p, _p, _p, _p, _p, _p],
