@@ -39,6 +39,9 @@ constexpr int GEMM_EPI_WARPS = 8;
 #ifndef T2S_GEMM_DB_STAGING
 #define T2S_GEMM_DB_STAGING 0
 #endif
+#ifndef T2S_GEMM_RES_TMA
+#define T2S_GEMM_RES_TMA 1
+#endif
 
 struct GemmEpi {
     void* C;
@@ -78,9 +81,13 @@ struct GemmCfg {
     static constexpr int STAGE2_BYTES = A_BYTES + B_BYTES / 2;
     // ... or five with TWO staging boxes per epilogue warp (T2S_GEMM_DB_STAGING): the epilogue then writes box i + 1 while
     // the TMA store of box i still reads its shared memory, instead of waiting for it
-    static constexpr int STAGES2 = T2S_GEMM_DB_STAGING ? 5 : 6;
-    static constexpr int STAGING2_BYTES = (T2S_GEMM_DB_STAGING ? 2 : 1) * STAGING_BYTES;
-    static constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + STAGING2_BYTES + 1024 + 256;
+    // The + bf16 residual epilogue of the pair form (MODE == GEMM_MODE_RES, "RT") always runs with two boxes: the residual
+    // tile is brought into the box by TMA one 64-column group ahead and the result is written over it in place (below).
+    __host__ __device__ static constexpr bool rt(int mode, int pair) { return pair == 2 && mode == 32 && T2S_GEMM_RES_TMA; }
+    __host__ __device__ static constexpr bool db(int mode, int pair) { return pair == 2 && (T2S_GEMM_DB_STAGING || rt(mode, pair)); }
+    __host__ __device__ static constexpr int stages2(int mode) { return db(mode, 2) ? 5 : 6; }
+    __host__ __device__ static constexpr int staging2(int mode) { return (db(mode, 2) ? 2 : 1) * STAGING_BYTES; }
+    __host__ __device__ static constexpr int smem2(int mode) { return stages2(mode) * STAGE2_BYTES + staging2(mode) + 1024 + 256; }
     static constexpr int DEEP_STAGES = 12;
     static constexpr int DEEP_SMEM_BYTES = DEEP_STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
 };
@@ -99,19 +106,23 @@ constexpr int GEMM_MODE_RES = 32;
 template <int BN, int MODE, int PAIR>
 __global__ void __launch_bounds__(GemmCfg<BN>::THREADS, GemmCfg<BN>::MIN_CTAS)     // 10 warps = 3 on two of the four 16 K-register partitions: 168 registers at most
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, GemmEpi ep, int M, int N, int K, int k_lo_off) {
+                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, GemmEpi ep,
+                         int M, int N, int K, int k_lo_off) {
     using Cfg = GemmCfg<BN>;
     constexpr bool TWO = PAIR == 2;
     constexpr int STAGE_BYTES = TWO ? Cfg::STAGE2_BYTES : Cfg::STAGE_BYTES;
-    const int STAGES = BN == 64 ? ep.stages : (TWO ? Cfg::STAGES2 : Cfg::STAGES);      // run-time depth for the latency tile
+    constexpr bool RT = Cfg::rt(MODE, PAIR);          // bf16 residual by TMA into the staging box, result written in place
+    constexpr bool DB = Cfg::db(MODE, PAIR);          // two staging boxes per epilogue warp
+    const int STAGES = BN == 64 ? ep.stages : (TWO ? Cfg::stages2(MODE) : Cfg::STAGES);      // run-time depth for the latency tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* staging = smem + STAGES * STAGE_BYTES;           // 1024-byte aligned (STAGE_BYTES is a multiple of 1024)
-    uint64_t* full = reinterpret_cast<uint64_t*>(staging + (TWO ? Cfg::STAGING2_BYTES : Cfg::STAGING_BYTES));
+    uint64_t* full = reinterpret_cast<uint64_t*>(staging + (TWO ? Cfg::staging2(MODE) : Cfg::STAGING_BYTES));
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* rbar = tempty + 2;           // RT: [epilogue warp][box]: the residual tile of a 64-column group has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + (RT ? 2 * Cfg::EPI_WARPS : 0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_n = (N + BN - 1) / BN;
@@ -132,6 +143,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmC);
+        if (RT) tma_prefetch_desc(&tmR);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -143,6 +155,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 mbar_init(&tfull[a], 1);
                 mbar_init(&tempty[a], TWO ? 2 * Cfg::EPI_WARPS : Cfg::EPI_WARPS);       // TWO: the leader's counts both CTAs' epilogues
             }
+            if (RT)
+                for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&rbar[i], 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -247,7 +261,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const bool dgelu = fl & T2S_GEMM_DGELU;
         // this warp's staging box: 32 rows x 128 B, 128B swizzle.  DB: two boxes used in turn -- the wait before a box is
         // rewritten then covers the store issued two stores ago
-        constexpr bool DB = TWO && T2S_GEMM_DB_STAGING;
         uint8_t* const box0 = staging + (BN == 64 ? quarter & 1 : (DB ? 2 * ew : ew)) * 4096;
         uint8_t* box = box0;
         uint8_t* my_row = box + lane * 128;
@@ -264,6 +277,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int sw = lane & 7;
         int acc = 0;
         uint32_t acc_phase = 0;
+        // RT: 64-column groups handled so far by this warp; group u uses box u & 1, barrier phase (u >> 1) & 1.  The
+        // residual tile of group u + 1 is requested while group u is processed (the box it goes to was last read by the
+        // store of group u - 1), the first group of the first tile before the loop.
+        int ruse = 0;
+        auto res_issue = [&](int use, int col, int row_first) {
+            if (lane == 0) {
+                uint64_t* b = &rbar[2 * ew + (use & 1)];
+                mbar_arrive_expect_tx(b, 4096);
+                tma_load_2d(box0 + (use & 1) * 4096, &tmR, b, col, row_first);
+            }
+        };
+        auto group_origin = [&](int t, int& col, int& row_first) {       // first group of tile t for this warp
+            const int mb = PAIR ? 2 * (t / num_n) + rank : t / num_n, nb = t % num_n;
+            col = nb * BN + (ew >> 2) * COLS_PER_WARP;
+            row_first = mb * Cfg::BM + quarter * 32;
+        };
+        if (RT && first_tile < tiles) {
+            int col, row_first;
+            group_origin(first_tile, col, row_first);
+            res_issue(0, col, row_first);
+        }
         for (int tile = first_tile; tile < tiles; tile += tile_step) {
             const int m_blk = PAIR ? 2 * (tile / num_n) + rank : tile / num_n, n_blk = tile % num_n;
             // the bias slice of this warp (first touched here by the whole grid at once) comes in under the main loop
@@ -282,7 +316,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 constexpr int NCH = COLS_PER_WARP / 32;
                 const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * COLS_PER_WARP;
                 const int col_w = n_blk * BN + half * COLS_PER_WARP;
-                const bool pre_res = has_res && !res_f32 && row_ok;
+                const bool pre_res = !RT && has_res && !res_f32 && row_ok;
                 const __nv_bfloat16* res16 =
                     reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + col_w;
                 uint32_t rbuf[2][32];
@@ -327,6 +361,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
+                    if (RT) {
+                        // The group's residual tile sits in this warp's box (same swizzled positions the result is written
+                        // to below).  Warp-uniform, whatever rows of the tile exist: at the first chunk of a group wait
+                        // for it, at the second request the next group's tile into the other box.
+                        if (((c0 >> 5) & 1) == 0) {
+                            mbar_wait(&rbar[2 * ew + (ruse & 1)], (ruse >> 1) & 1);
+                        } else {
+                            int ncol = col0 + 32, nrow = row0;
+                            bool have = c0 + 32 < COLS_PER_WARP;
+                            if (!have && tile + tile_step < tiles) {
+                                group_origin(tile + tile_step, ncol, nrow);
+                                have = true;
+                            }
+                            if (have) {
+                                if (lane == 0) tma_store_wait_read<0>();     // the other box: its store has read it
+                                __syncwarp();
+                                res_issue(ruse + 1, ncol, nrow);
+                            }
+                        }
+                    }
                     if (has_res && row_ok) {
                         // residual add, or (T2S_GEMM_DGELU) multiply by GELU'(aux) of the saved pre-activation
                         auto comb = [dgelu](float acc_v, float aux) { return dgelu ? acc_v * gelu_grad(aux) : acc_v + aux; };
@@ -345,7 +399,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             }
                         } else {
                             const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + col0;
-                            if (full32) {
+                            if (RT) {
+                                const int hp = (c0 >> 5) & 1;
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    const uint4 a = *reinterpret_cast<const uint4*>(my_row + (((hp * 4 + (j >> 3)) ^ sw) << 4));
+                                    v[j] = comb(v[j], bf16lo(a.x)); v[j + 1] = comb(v[j + 1], bf16hi(a.x));
+                                    v[j + 2] = comb(v[j + 2], bf16lo(a.y)); v[j + 3] = comb(v[j + 3], bf16hi(a.y));
+                                    v[j + 4] = comb(v[j + 4], bf16lo(a.z)); v[j + 5] = comb(v[j + 5], bf16hi(a.z));
+                                    v[j + 6] = comb(v[j + 6], bf16lo(a.w)); v[j + 7] = comb(v[j + 7], bf16hi(a.w));
+                                }
+                            } else if (full32) {
 #pragma unroll
                                 for (int j = 0; j < 32; j += 8) {
                                     const uint4 a = q[j >> 3];       // prefetched one chunk ahead
@@ -389,7 +453,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         uint32_t hi[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) hi[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-                        if (hpos == 0) box_wait();
+                        if (hpos == 0 && !RT) box_wait();       // RT: the box already holds the residual tile
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             *reinterpret_cast<uint4*>(my_row + (((hpos * 4 + c) ^ sw) << 4)) =
@@ -403,6 +467,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                 tma_store_commit();
                             }
                             next_box();
+                            if (RT) ++ruse;
                         }
                         if (out_split) {
                             // lo = bf16(v - hi), stored ep.c_lo_off columns to the right; 32-column boxes reuse the
@@ -572,14 +637,14 @@ int num_sms() {
 }
 
 template <int BN, int MODE, int PAIR>
-static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmEpi& ep,
-                            int M, int N, int K, int k_lo_off, int sm_cap, cudaStream_t st) {
+static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
+                            const GemmEpi& ep, int M, int N, int K, int k_lo_off, int sm_cap, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, MODE, PAIR>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             BN == 64 ? Cfg::DEEP_SMEM_BYTES : (PAIR == 2 ? Cfg::SMEM2_BYTES : Cfg::SMEM_BYTES));
+                                             BN == 64 ? Cfg::DEEP_SMEM_BYTES : (PAIR == 2 ? Cfg::smem2(MODE) : Cfg::SMEM_BYTES));
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
             return (int)e;
@@ -595,7 +660,7 @@ static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const 
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * pairs);
         cfg.blockDim = dim3(Cfg::THREADS);
-        cfg.dynamicSmemBytes = PAIR == 2 ? Cfg::SMEM2_BYTES : Cfg::SMEM_BYTES;
+        cfg.dynamicSmemBytes = PAIR == 2 ? Cfg::smem2(MODE) : Cfg::SMEM_BYTES;
         cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
@@ -604,7 +669,7 @@ static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const 
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, MODE, PAIR>, ta, tb, tc, ep, M, N, K, k_lo_off);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, MODE, PAIR>, ta, tb, tc, tr, ep, M, N, K, k_lo_off);
         if (e != cudaSuccess) {
             set_error("gemm_bf16_tcgen05 (pair): %s", cudaGetErrorString(e));
             return (int)e;
@@ -622,10 +687,10 @@ static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const 
         const bool deep = tiles <= deep_tiles && (K + GEMM_BK - 1) / GEMM_BK > Cfg::STAGES;
         ep64.stages = deep ? Cfg::DEEP_STAGES : Cfg::STAGES;
         launch_pdl(true, gemm_bf16_tcgen05_kernel<BN, MODE, PAIR>, dim3(grid), dim3(Cfg::THREADS),
-                   deep ? Cfg::DEEP_SMEM_BYTES : Cfg::SMEM_BYTES, st, ta, tb, tc, ep64, M, N, K, k_lo_off);
+                   deep ? Cfg::DEEP_SMEM_BYTES : Cfg::SMEM_BYTES, st, ta, tb, tc, tr, ep64, M, N, K, k_lo_off);
         return launch_status("gemm_bf16_tcgen05");
     }
-    gemm_bf16_tcgen05_kernel<BN, MODE, PAIR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, ep, M, N, K, k_lo_off);
+    gemm_bf16_tcgen05_kernel<BN, MODE, PAIR><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tr, ep, M, N, K, k_lo_off);
     return launch_status("gemm_bf16_tcgen05");
 }
 
@@ -633,12 +698,14 @@ static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const 
 // GELU + hi|lo out, hi|lo out) and the GELU' dgrad of the training step are compiled with constant flags for the
 // throughput tiles; everything else (BN = 64 decode tiles, rare combinations) takes the run-time-flag instantiation.
 template <int BN, int PAIR>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmEpi& ep, int M,
-                       int N, int K, int k_lo_off, int sm_cap, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
+                       const GemmEpi& ep, int M, int N, int K, int k_lo_off, int sm_cap, cudaStream_t st) {
     if (BN >= 128) {
-        const int mode = (ep.flags & 31) | (ep.residual ? GEMM_MODE_RES : 0);
+        int mode = (ep.flags & 31) | (ep.residual ? GEMM_MODE_RES : 0);
+        // the TMA-fed residual epilogue works on whole 64-column groups of whole 256-column blocks
+        if (GemmCfg<BN>::rt(mode, PAIR) && (N % 256)) mode = -1;
 #define T2S_GEMM_MODE_CASE(m) \
-        case (m): return launch_gemm_mode<(BN >= 128 ? BN : 128), (m), PAIR>(ta, tb, tc, ep, M, N, K, k_lo_off, sm_cap, st);
+        case (m): return launch_gemm_mode<(BN >= 128 ? BN : 128), (m), PAIR>(ta, tb, tc, tr, ep, M, N, K, k_lo_off, sm_cap, st);
         switch (mode) {
             T2S_GEMM_MODE_CASE(0)
             T2S_GEMM_MODE_CASE(GEMM_MODE_RES)
@@ -653,7 +720,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
         }
 #undef T2S_GEMM_MODE_CASE
     }
-    return launch_gemm_mode<BN, -1, PAIR>(ta, tb, tc, ep, M, N, K, k_lo_off, sm_cap, st);
+    return launch_gemm_mode<BN, -1, PAIR>(ta, tb, tc, tr, ep, M, N, K, k_lo_off, sm_cap, st);
 }
 
 
@@ -910,16 +977,22 @@ static int gemm_entry(const char* who, bool x3, const void* A, long long lda, co
     CUtensorMap tc;
     rc = make_tmap_2d(&tc, out_f32, C, M, out_split ? 2LL * N : N, ldc, out_f32 ? 32 : 64, 32);
     if (rc) return rc;
+    // residual tile map of the TMA-fed + bf16 residual epilogue (same 32-row x 64-column boxes as the bf16 output)
+    CUtensorMap tr = tc;
+    if (residual && !(flags & T2S_GEMM_RES_F32) && !out_f32 && !out_split) {
+        rc = make_tmap_2d(&tr, false, residual, M, N, ldr, 64, 32);
+        if (rc) return rc;
+    }
     GemmEpi ep{C, bias, residual, ldc, ldr, flags, N, 0};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int k_lo = x3 ? K : 0;
     const int cap = (flags >> T2S_GEMM_SM_CAP_SHIFT) & 0xff;
     switch (bn) {
-        case 256: return pair == 2 ? launch_gemm<256, 2>(ta, tb, tc, ep, M, N, K, k_lo, cap, st)
-                       : pair == 1 ? launch_gemm<256, 1>(ta, tb, tc, ep, M, N, K, k_lo, cap, st)
-                                   : launch_gemm<256, 0>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
-        case 128: return launch_gemm<128, 0>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
-        case 64: return launch_gemm<64, 0>(ta, tb, tc, ep, M, N, K, k_lo, cap, st);
+        case 256: return pair == 2 ? launch_gemm<256, 2>(ta, tb, tc, tr, ep, M, N, K, k_lo, cap, st)
+                       : pair == 1 ? launch_gemm<256, 1>(ta, tb, tc, tr, ep, M, N, K, k_lo, cap, st)
+                                   : launch_gemm<256, 0>(ta, tb, tc, tr, ep, M, N, K, k_lo, cap, st);
+        case 128: return launch_gemm<128, 0>(ta, tb, tc, tr, ep, M, N, K, k_lo, cap, st);
+        case 64: return launch_gemm<64, 0>(ta, tb, tc, tr, ep, M, N, K, k_lo, cap, st);
         default: set_error("%s: block_n must be 0, 64, 128 or 256", who); return T2S_ERR_ARG;
     }
 }
