@@ -5,23 +5,26 @@
 // bf16x3 form, for TextBert / QTV of the grounding chain (t2s.py:423,538).  Masked keys are skipped
 // through the compacted per-sample key list (see attention.cu): exp(-10000 - max) == 0 in fp32.
 //
-// One CTA = 128 query rows of one (sample, head); key tiles of 128 gathered rows.
-//   warps 0-3  softmax: thread r owns query row r == TMEM lane r.  One software-pipelined sweep over S in TMEM
-//              (exp2 against the carried maximum, row sum), P written as bf16 into a 128B-swizzled shared-memory
-//              tile (the A operand of P.V).  O accumulates in TMEM across key tiles; the online-
-//              softmax correction is LAZY: the running maximum is only raised (and O rescaled in
-//              TMEM by tcgen05.ld / st) when a tile exceeds it by more than 2^8, which keeps the
-//              result exact (the final division uses the same maximum) and the rescale rare.
-//   warps 4-7  loaders: cp.async 16-byte gathers of the K / V rows named by the key list into the
-//              same 128B-swizzled layout a TMA tile load would produce (TMA cannot gather rows),
-//              two stages, fence.proxy.async + mbarrier hand-off to the tensor core.
-//   warp 8     one thread issues tcgen05.mma: S = Q.K^T (M128 N128 K64) into TMEM columns [0,128),
-//              O += P.V (M128 N64 K128, V consumed as an MN-major operand straight from its
-//              row-per-key layout) into columns [128,192); tcgen05.commit drives the mbarriers.
-// S(t+1) is issued right behind P.V(t); two CTAs per SM (112 KB smem, 256 TMEM columns each) overlap
-// one CTA's softmax with the other's tensor work.
-// X3 = true: q|k|v are bf16 hi|lo pairs, S = Ql.Kh + Qh.Kl + Qh.Kh, O = Pl.Vh + Ph.Vl + Ph.Vh
-// (fp32-class; 224 KB smem, one CTA per SM).
+// One CTA = 128 query rows of one (sample, head) at a time (TC_NQ consecutive query tiles per CTA); key tiles of 128
+// gathered rows.
+//   softmax warps (4, or 8 with two threads per row in the bf16x3 form): a thread owns (half of) query row r == TMEM
+//              lane r.  One software-pipelined sweep over S in TMEM (exp2 against the carried maximum, row sum); P goes
+//              back into TENSOR MEMORY as packed bf16 pairs (tcgen05.st, 64 columns per plane) and is the A operand of
+//              P.V from there -- it never touches shared memory.  O accumulates in TMEM across key tiles; the online-
+//              softmax correction is LAZY: the running maximum is only raised (and O rescaled in TMEM by tcgen05.ld /
+//              st) when a tile exceeds it by more than 2^8, which keeps the result exact (the final division uses the
+//              same maximum) and the rescale rare.
+//   4 loader warps: cp.async 16-byte gathers of the K / V rows named by the key list into the same 128B-swizzled
+//              layout a TMA tile load would produce (TMA cannot gather rows), two stages, K and V with their own
+//              full / empty barriers, fence.proxy.async + mbarrier hand-off to the tensor core.
+//   1 issuer warp: one thread issues tcgen05.mma: S = Q.K^T (M128 N128 K64, both operands from shared memory) and
+//              O += P.V (M128 N64 K128: A = P from tensor memory, B = V consumed as an MN-major operand straight from
+//              its row-per-key layout); tcgen05.commit drives the mbarriers.
+// bf16 form: S(t+1) is issued right behind P.V(t); two CTAs per SM (80 KB smem, 256 TMEM columns each: S 128, O 64,
+// P 64) overlap one CTA's softmax with the other's tensor work.
+// X3 = true: q|k|v are bf16 hi|lo pairs, S = Ql.Kh + Qh.Kl + Qh.Kh, O = Pl.Vh + Ph.Vl + Ph.Vh (fp32-class; 162 KB smem,
+// one CTA per SM, which therefore pipelines itself: two S buffers, S(t+1) issued under the softmax of tile t, the P of a
+// tile held in registers until P.V(t-1) has released the P columns; 448 of 512 TMEM columns).
 #include "common.cuh"
 #include "../../include/t2s_b200.h"
 

@@ -22,6 +22,9 @@
 //               otherwise scatter 16-byte stores over 32 rows per instruction).
 // Tiles are walked n-fastest so the CTAs running concurrently share one A row-block
 // through L2 and A streams from HBM once.
+// The throughput launches (BN = 256, M >= 256) run as 2-CTA clusters: by default ONE tcgen05.mma.cta_group::2 of
+// M = 256 per pair, issued by the leader, each CTA holding its A tile and half of the W tile (PAIR == 2 below); their
+// + bf16 residual epilogue gets the residual tile by TMA into the staging box and overwrites it in place (RT below).
 #include "common.cuh"
 #include <stdlib.h>
 #include <mutex>
