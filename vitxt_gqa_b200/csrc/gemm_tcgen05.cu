@@ -747,18 +747,24 @@ struct WgradCfg {
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * 4096;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+    // TWO (cta_group::2, as in the forward GEMM): a pair takes two vertically adjacent P tiles of one Q block; each CTA
+    // keeps its [128 P x 64 rows] tile of G and HALF of the X tile -- 32 KB stages, six of them
+    static constexpr int STAGE2_BYTES = A_BYTES + B_BYTES / 2;
+    static constexpr int STAGES2 = 6;
+    static constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + STAGING_BYTES + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, bool TWO>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
                           const __grid_constant__ CUtensorMap tmD, int rows, int P, int Q, int splits,
                           int kb_per_split) {
     using Cfg = WgradCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
+    constexpr int STAGES = TWO ? Cfg::STAGES2 : Cfg::STAGES;
+    constexpr int STAGE_BYTES = TWO ? Cfg::STAGE2_BYTES : Cfg::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+    uint8_t* staging = smem + STAGES * STAGE_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
@@ -768,8 +774,13 @@ gemm_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_q = (Q + BN - 1) / BN;
     const int num_p = (P + GEMM_BM - 1) / GEMM_BM;
-    const int tiles = num_p * num_q;
+    // TWO: "tiles" counts pair tiles (P tiles 2p and 2p + 1 of one Q block; the host only takes this form for an even
+    // number of P tiles); this CTA's item list is that of its pair, of which it takes P tile 2p + rank
+    const int rank = TWO ? (int)cluster_ctarank() : 0;
+    const int tiles = (TWO ? num_p / 2 : num_p) * num_q;
     const int items = tiles * splits;             // item = split * tiles + tile: neighbours share a row range in L2
+    const int item0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int item_step = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int kb_total = (rows + GEMM_BK - 1) / GEMM_BK;
 
     if (warp == 0 && lane == 0) {
@@ -785,48 +796,65 @@ gemm_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&tfull[a], 1);
-                mbar_init(&tempty[a], GEMM_EPI_WARPS);
+                mbar_init(&tempty[a], TWO ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);
             }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if (TWO) {
+            tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (TWO) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        for (int item = item0; item < items; item += item_step) {
             const int split = item / tiles, tile = item - split * tiles;
-            const int p0 = (tile / num_q) * GEMM_BM, q0 = (tile % num_q) * BN;
+            const int p0 = (TWO ? 2 * (tile / num_q) + rank : tile / num_q) * GEMM_BM, q0 = (tile % num_q) * BN;
             const int kb0 = split * kb_per_split;
             const int kb1 = min(kb_total, kb0 + kb_per_split);
             for (int kb = kb0; kb < kb1; ++kb) {
                 if (lane == 0) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
                     const int r = kb * GEMM_BK;
-                    tma_load_2d(sa, &tmG, &full[stage], p0, r);
-                    tma_load_2d(sa + 8192, &tmG, &full[stage], p0 + 64, r);
+                    if (TWO) {
+                        // both CTAs' bytes are counted on the leader's barrier; this CTA's half of the X tile
+                        const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+                        tma_load_2d_2sm(sa, &tmG, lead_full, p0, r);
+                        tma_load_2d_2sm(sa + 8192, &tmG, lead_full, p0 + 64, r);
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j)
-                        tma_load_2d(sa + Cfg::A_BYTES + j * 8192, &tmX, &full[stage], q0 + 64 * j, r);
+                        for (int j = 0; j < BN / 128; ++j)
+                            tma_load_2d_2sm(sa + Cfg::A_BYTES + j * 8192, &tmX, lead_full, q0 + rank * (BN / 2) + 64 * j, r);
+                    } else {
+                        mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                        tma_load_2d(sa, &tmG, &full[stage], p0, r);
+                        tma_load_2d(sa + 8192, &tmG, &full[stage], p0 + 64, r);
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_2d(sa + Cfg::A_BYTES + j * 8192, &tmX, &full[stage], q0 + 64 * j, r);
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN) | (1u << 15) | (1u << 16);    // A and B MN-major
+        constexpr uint32_t idesc = make_idesc_bf16(TWO ? 2 * GEMM_BM : GEMM_BM, BN) | (1u << 15) | (1u << 16);    // A and B MN-major
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        for (int item = item0; item < items && !(TWO && rank != 0); item += item_step) {
             const int split = item / tiles;
             const int kb0 = split * kb_per_split;
             const int kb1 = min(kb_total, kb0 + kb_per_split);
@@ -837,16 +865,19 @@ gemm_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) {
                         // 16 rows of the contraction = two 8-row groups = 2048 B
                         const uint64_t da = make_sw128_mnmajor_desc_lbo(sa + k * 2048, 8192);
                         const uint64_t db = make_sw128_mnmajor_desc_lbo(sa + Cfg::A_BYTES + k * 2048, 8192);
-                        umma_bf16(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                        if (TWO) umma_bf16_2sm(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                        else umma_bf16(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty[stage]);
-                    if (kb == kb1 - 1) umma_commit(&tfull[acc]);
+                    if (TWO) umma_commit_2sm(&empty[stage], 3); else umma_commit(&empty[stage]);
+                    if (kb == kb1 - 1) {
+                        if (TWO) umma_commit_2sm(&tfull[acc], 3); else umma_commit(&tfull[acc]);
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -864,9 +895,9 @@ gemm_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_
         const int sw = lane & 7;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        for (int item = item0; item < items; item += item_step) {
             const int split = item / tiles, tile = item - split * tiles;
-            const int p0 = (tile / num_q) * GEMM_BM, q0 = (tile % num_q) * BN;
+            const int p0 = (TWO ? 2 * (tile / num_q) + rank : tile / num_q) * GEMM_BM, q0 = (tile % num_q) * BN;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const int row0 = p0 + quarter * 32;
@@ -893,7 +924,9 @@ gemm_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) {
+                if (TWO) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0)); else mbar_arrive(&tempty[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -901,26 +934,47 @@ gemm_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_
     }
     tc_fence_before();
     __syncthreads();
+    if (TWO) cluster_sync_all();          // neither CTA leaves while the pair's MMAs may still touch its memory
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (TWO) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
-template <int BN>
+template <int BN, bool TWO>
 static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, const CUtensorMap& td, int rows, int P, int Q,
                         int splits, int kb_per_split, cudaStream_t st) {
     using Cfg = WgradCfg<BN>;
+    constexpr int SMEM = TWO ? Cfg::SMEM2_BYTES : Cfg::SMEM_BYTES;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_tcgen05_kernel<BN, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SMEM);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad BN=%d): %s", BN, cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    const int items = ((P + GEMM_BM - 1) / GEMM_BM) * ((Q + BN - 1) / BN) * splits;
+    const int num_p = (P + GEMM_BM - 1) / GEMM_BM;
+    const int items = (TWO ? num_p / 2 : num_p) * ((Q + BN - 1) / BN) * splits;
+    if (TWO) {
+        const int pairs = items < num_sms() / 2 ? items : num_sms() / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_wgrad_tcgen05_kernel<BN, TWO>, tg, tx, td, rows, P, Q, splits, kb_per_split);
+        if (e != cudaSuccess) { set_error("gemm_wgrad_tcgen05 (pair): %s", cudaGetErrorString(e)); return (int)e; }
+        return launch_status("gemm_wgrad_tcgen05 (pair)");
+    }
     const int grid = items < num_sms() ? items : num_sms();
-    gemm_wgrad_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tg, tx, td, rows, P, Q, splits, kb_per_split);
+    gemm_wgrad_tcgen05_kernel<BN, TWO><<<grid, GEMM_THREADS, SMEM, st>>>(tg, tx, td, rows, P, Q, splits, kb_per_split);
     return launch_status("gemm_wgrad_tcgen05");
 }
 
@@ -1048,6 +1102,16 @@ extern "C" int t2s_gemm_wgrad_bf16(const void* G, long long ldg, const void* X, 
     rc = make_tmap_2d(&td, true, dW, P, Q, ldd, 32, 32);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (bn == 256) return launch_wgrad<256>(tg, tx, td, rows, P, Q, splits, kb_per_split, st);
-    return launch_wgrad<64>(tg, tx, td, rows, P, Q, splits, kb_per_split, st);
+    // pair form (one cta_group::2 MMA of M = 256 per CTA pair) when the P tiles pair up; T2S_WGRAD_PAIR=0 turns it off
+    static int wpair = -1;
+    if (wpair < 0) {
+        const char* e = getenv("T2S_WGRAD_PAIR");
+        wpair = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (bn == 256) {
+        if (wpair && ((P + GEMM_BM - 1) / GEMM_BM) % 2 == 0)
+            return launch_wgrad<256, true>(tg, tx, td, rows, P, Q, splits, kb_per_split, st);
+        return launch_wgrad<256, false>(tg, tx, td, rows, P, Q, splits, kb_per_split, st);
+    }
+    return launch_wgrad<64, false>(tg, tx, td, rows, P, Q, splits, kb_per_split, st);
 }
