@@ -166,6 +166,8 @@ feat_concat_kernel(const float* __restrict__ f0, int d0, const float* __restrict
 // RPW rows per warp.  A bf16 row is 1.5 KB and ncu shows the 66 816-row bf16 launches at 3.4 TB/s against 5.3 - 6.1 TB/s
 // for the fp32 rows of the same kernel, so loading two rows before the first reduction was tried (RPW = 2): add_ln went
 // from 1.87 to 3.34 ms per eval step (96 registers, five CTAs per SM).  RPW stays 1; the template is kept for the record.
+// The opposite direction -- __launch_bounds__(128, 10): 48 registers instead of 60, ten CTAs per SM instead of eight, ~50 B of
+// spills -- measured 2.12 against 1.95 ms per step: not kept either.
 template <typename TX, typename TR, bool SPLIT, bool DROP, int RPW>
 __global__ void __launch_bounds__(NE_THREADS)
 add_ln_kernel(const TX* x, long long ldx, const TR* __restrict__ res, long long ldr,
